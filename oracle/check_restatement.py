@@ -1,0 +1,188 @@
+#!/usr/bin/env python
+"""
+ORACLE TEST INFRASTRUCTURE -- not product code.
+
+Pins the C restatement (``oracle/gw_oracle.c``) against the reference ITSELF:
+both replay the same action tapes; every trace record (transmission start /
+stop / bit counts, every BER value, every decider input and verdict, every RRM
+delivery) and every step result (obs, reward, done, step end time) must be
+bit-identical.  BER values are additionally compared with a relative tolerance
+switch for libm differences (none expected: both sides call glibc).
+
+Runs only where ``/root/reference`` exists (the build container):
+
+    python oracle/check_restatement.py            # default env + random scenarios
+    python oracle/check_restatement.py --selfcheck  # harness ScenarioEnv == CounterTrafficEnv
+"""
+import argparse
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+import gw_oracle as O  # noqa: E402
+import ref_harness as H  # noqa: E402
+
+
+def canonical(records):
+    glob = [r for r in records if r[0] in ("tx", "rx")]
+    per = {}
+    for r in records:
+        if r[0] in ("ber", "dec"):
+            per.setdefault((r[2], r[3]), []).append(r)
+    out = list(glob)
+    for k in sorted(per):
+        out += per[k]
+    return out
+
+
+def compare(ref, ora, label, ber_rtol=0.0):
+    """Returns the number of mismatching steps (prints the first one)."""
+    bad = 0
+    assert ref["reset_obs"] == ora["reset_obs"], (label, ref["reset_obs"], ora["reset_obs"])
+    for i, (a, b) in enumerate(zip(ref["steps"], ora["steps"])):
+        ok = (a["obs"] == b["obs"] and a["reward"] == b["reward"] and a["done"] == b["done"]
+              and a["now"] == b["now"])
+        # Same-instant callbacks of DIFFERENT PHYs run in Python-set order in the reference
+        # (simtools.py:255) and touch only their own PHY, so records are compared per
+        # (band, device) subsequence for ber/dec and as one global subsequence for tx/rx.
+        ra, rb = canonical(a["records"]), canonical(b["records"])
+        if ra != rb:
+            ok = False
+        if not ok:
+            bad += 1
+            if bad == 1:
+                print("[%s] MISMATCH at step %d action %s" % (label, i, a["action"]))
+                print("  ref: obs %s rew %s now %r nrec %d" % (a["obs"], a["reward"], a["now"], len(ra)))
+                print("  ora: obs %s rew %s now %r nrec %d" % (b["obs"], b["reward"], b["now"], len(rb)))
+                for j in range(max(len(ra), len(rb))):
+                    x = ra[j] if j < len(ra) else None
+                    y = rb[j] if j < len(rb) else None
+                    if x != y:
+                        print("  first differing record %d:\n    ref %s\n    ora %s" % (j, x, y))
+                        break
+    return bad
+
+
+def run_case(scenario, tape, label, do_reset=True, use_default_class=False):
+    tr = H.Tracer()
+    if use_default_class:
+        env = H.make_default_env(tr)
+    else:
+        env = H.ScenarioEnv(scenario, tr)
+    ref = H.run_tape(env, tape, tr, do_reset=do_reset)
+    ora = O.run_tape(O.Oracle(scenario, trace=True), tape, do_reset=do_reset)
+    bad = compare(ref, ora, label)
+    ev_ref = sum(s["events"] for s in ref["steps"])
+    ev_ora = sum(s["events"] for s in ora["steps"])
+    print("[%s] steps %d mismatching %d ; heap pops ref %d / restatement %d" %
+          (label, len(tape), bad, ev_ref, ev_ora))
+    return bad
+
+
+def random_scenario(rs, nbands=1, jammers=1, fixed_payload=None, spread=20.0, factor=1000):
+    bands = []
+    for b in range(nbands):
+        devs = []
+        for k in range(2):
+            devs.append({"role": "sender", "x": float(rs.uniform(-spread, spread)),
+                         "y": float(rs.uniform(-spread, spread)), "mult": int(rs.randint(1, 4)),
+                         "payload": "counter" if fixed_payload is None else int(fixed_payload),
+                         "interval": 0.001, "dest": 1 - k})
+        devs.append({"role": "rrm", "x": float(rs.uniform(-spread, spread)),
+                     "y": float(rs.uniform(-spread, spread))})
+        for j in range(jammers):
+            payload = int(rs.randint(12, 200))
+            airtime = (13 + payload) * 8 / 99999.9975
+            # interval > airtime: otherwise the jammer's SEND queue grows without bound
+            devs.append({"role": "jammer", "x": float(rs.uniform(-spread, spread)),
+                         "y": float(rs.uniform(-spread, spread)),
+                         "interval": float(airtime * rs.uniform(1.3, 6.0)),
+                         "delay": float(rs.uniform(0, 1e-2)),
+                         "power": float(rs.choice([0.0, 10.0, 20.0])), "hdr": 13,
+                         "payload": payload})
+        bands.append({"frequency": 2.4e9 + b * 25e6, "bandwidth": 22e6, "devices": devs})
+    return {"assignment_duration_factor": factor, "bands": bands}
+
+
+def child(args):
+    """One case per process: the reference allows one env per process."""
+    rs = np.random.RandomState(args.seed)
+    if args.case == "default":
+        tape = H.random_actions(args.steps, seed=args.seed)
+        return run_case(H.default_scenario(), tape, "default seed %d" % args.seed,
+                        use_default_class=True)
+    if args.case == "default_noreset":
+        tape = H.random_actions(args.steps, seed=args.seed)
+        return run_case(H.default_scenario(), tape, "default/no-reset seed %d" % args.seed,
+                        do_reset=False, use_default_class=True)
+    if args.case == "kat":
+        tape = [{"device": 0, "duration": 3}, {"device": 1, "duration": 12}]
+        return run_case(H.default_scenario(), tape, "reference KAT", do_reset=False,
+                        use_default_class=True)
+    if args.case == "positions":
+        sc = random_scenario(rs, jammers=0, spread=args.spread)
+        tape = H.random_actions(args.steps, seed=args.seed + 1000)
+        return run_case(sc, tape, "positions seed %d" % args.seed)
+    if args.case == "jammer":
+        sc = random_scenario(rs, jammers=args.jammers, spread=args.spread)
+        tape = H.random_actions(args.steps, seed=args.seed + 2000)
+        return run_case(sc, tape, "jammer seed %d" % args.seed)
+    if args.case == "long":
+        sc = random_scenario(rs, jammers=args.jammers, fixed_payload=1500, spread=args.spread,
+                             factor=10000)
+        tape = H.random_actions(args.steps, seed=args.seed + 3000)
+        return run_case(sc, tape, "long-packet seed %d" % args.seed)
+    if args.case == "multiband":
+        sc = random_scenario(rs, nbands=4, jammers=1, spread=args.spread)
+        tapes = [H.random_actions(args.steps, seed=args.seed + 4000 + b) for b in range(4)]
+        tape = [list(x) for x in zip(*tapes)]
+        return run_case(sc, tape, "multiband seed %d" % args.seed)
+    raise SystemExit("unknown case")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default=None)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--jammers", type=int, default=1)
+    ap.add_argument("--spread", type=float, default=8.0)
+    ap.add_argument("--selfcheck", action="store_true")
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+
+    H.setup_paths()
+    if args.selfcheck:
+        tape = H.random_actions(300, seed=0)
+        tr = H.Tracer()
+        a = H.run_tape(H.make_default_env(tr), tape, tr)
+        tr2 = H.Tracer()
+        b = H.run_tape(H.ScenarioEnv(H.default_scenario(), tr2), tape, tr2)
+        print("ScenarioEnv(default) == CounterTrafficEnv:", a == b)
+        return 0 if a == b else 1
+    if args.case:
+        return 1 if child(args) else 0
+
+    # driver: every case in its own process
+    O.build()
+    plan = [("kat", 0, 2), ("default", 0, 400), ("default", 1, 400), ("default_noreset", 2, 200)]
+    nseeds = 2 if args.quick else 6
+    for sd in range(nseeds):
+        plan += [("positions", sd, 200), ("jammer", sd, 200), ("long", sd, 40), ("multiband", sd, 80)]
+    failed = 0
+    for case, sd, steps in plan:
+        rc = subprocess.call([sys.executable, os.path.abspath(__file__), "--case", case,
+                              "--seed", str(sd), "--steps", str(steps),
+                              "--jammers", str(args.jammers), "--spread", str(args.spread)])
+        failed += 1 if rc else 0
+    print("FAILED CASES:", failed)
+    return 1 if failed else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
