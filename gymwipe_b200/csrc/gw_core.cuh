@@ -1,0 +1,778 @@
+// gymwipe_b200 -- per-env simulation core of the fused, event-ordered step kernel (K4).
+//
+// One "band-sim" (one frequency band of one env) is advanced by ONE GPU thread; a warp
+// holds 32 band-sims.  The SimPy heap of the reference is replaced by a fixed set of
+// TIMED event slots per band-sim (traffic ticks, jammer wake-ups, one PHY event per
+// device, MAC window time-outs, the RRM time-out), ordered by (time, creation seq) --
+// the reference's (time, priority, eid) order restricted to timed events -- while every
+// zero-delay event chain of the reference (Initialize / succeed() / process-end events)
+// is executed inline, in the order SimPy would pop it.  DESIGN.md section 4 derives the
+// reduction; tests/ check it bit-exactly against the literal restatement in oracle/.
+//
+// Reference semantics implemented here (file:line under /root/reference):
+//   SimplePhy  (power bookkeeping, BER accounting, decider)  networking/simple_stack.py:77-286
+//   SimpleMac  (queue, assignment-window loop)                networking/simple_stack.py:386-471
+//   SimpleRrmMac (announcement, guard slot)                   networking/simple_stack.py:527-561
+//   Transmission / FrequencyBand.transmit                     networking/physical.py:224-290,576-608
+//   BpskMcs / Eb-N0 / Q-function / dB helpers                 networking/physical.py:25-98,187-212
+//   FsplAttenuation / Position.distanceTo                     networking/attenuation_models.py:28-36, devices/core.py:88-95
+//   SenderDevice.senderProcess, CounterTrafficInterpreter     envs/counter_traffic.py:53-61,63-112
+//   SimMan.nextTimeSlot / timeoutUntil                        simtools.py:44-53,103-116
+//
+// This header is plain C++ (no CUDA intrinsics): the kernels in gw_kernels.cu include it
+// for the device, and tests/hostsim compiles the very same code for the host so that the
+// event logic is validated against the oracle without a GPU.  Floating point: every
+// operation is IEEE fp64 in the reference's order; compile with -fmad=false (nvcc) /
+// -ffp-contract=off (gcc) so that no multiply-add is contracted.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GW_HD __host__ __device__ __forceinline__
+#else
+#define GW_HD inline
+#endif
+
+namespace gw {
+
+constexpr double kSlot = 1e-6;          // TIME_SLOT_LENGTH, simple_stack.py:27
+constexpr int kMacHdr = 13;             // SimpleMacHeader byteSize, messages.py:154
+constexpr int kNetHdr = 12;             // SimpleNetworkHeader byteSize, messages.py:180
+constexpr int kQueueCap = 100;          // deque(maxlen=100), simple_stack.py:361
+constexpr int kCounterBound = 65536;    // COUNTER_BOUND, counter_traffic.py:35
+constexpr int kCounterByteLen = 2;      // COUNTER_BYTE_LENGTH, counter_traffic.py:33
+
+enum : int { S_IDLE = 0, S_WAITRX = 1, S_SLOT = 2, S_HDR = 3, S_PAY = 4 };
+enum : int { MAC_NONE = 0, MAC_WAIT_COND = 1, MAC_WAIT_TX = 2, MAC_IDLE = 3 };
+enum : int { EV_NONE = 0, EV_TICK = 1, EV_JAM = 2, EV_PHY = 3, EV_W = 4, EV_RRM = 5 };
+enum : int { MODE_R = 0, MODE_M_PHILOX = 1, MODE_M_FED = 2 };
+enum : int { FAULT_NONE = 0, FAULT_REF_KEYERROR = 2, FAULT_REF_ASSERT = 3, FAULT_SENDQ = 4,
+             FAULT_EMPTY = 6 };
+
+constexpr int kMaxBands = 4, kMaxDev = 4, kMaxSend = 2, kMaxJam = 1;
+
+// Scenario constants shared by all envs (kernel parameter).
+struct BandParams {
+    int ndev, ns, nj;
+    int mult[kMaxSend];
+    int payloadRule[kMaxSend];          // -1: byteSize = counter
+    double interval[kMaxSend];
+    double jamInterval[kMaxJam], jamDelay[kMaxJam];
+    int jamHdr[kMaxJam], jamPay[kMaxJam];
+};
+
+struct Params {
+    int nbands, factor, maxDuration, mode;
+    double bitRate;                     // 133.33333e3, physical.py:196
+    double dataRate;                    // 0.75 * bitRate, physical.py:197
+    double maxBer;                      // Mcs.maxCorrectableBer(), physical.py:160-185
+    double tenLog10BitRate;             // 10*log10(bitRate), host libm
+    double qDen;                        // 1.135 * sqrt(2*pi), physical.py:44,58
+    double bitsFactor;                  // float(2 - codeRate) = 1.25, physical.py:259-263
+    BandParams band[kMaxBands];
+};
+
+// ---------------------------------------------------------------------------
+// physical-layer arithmetic
+// ---------------------------------------------------------------------------
+
+// BpskMcs.calculateBitErrorRate on powers in mW (simple_stack.py:166-172, physical.py:208-212,
+// 25-42, 46-58).  Operation order follows the Python source literally.
+GW_HD double ber_bpsk_mw(double S, double N, double tenLog10BitRate, double qDen)
+{
+    const double sd = 10 * log10(S);            // milliwattsToDbm, physical.py:82-89
+    const double nd = 10 * log10(N);
+    if (sd <= nd) return 0.5;
+    const double ratio_db = sd - nd - tenLog10BitRate;
+    const double ratio = pow(10.0, ratio_db / 10);
+    const double x = sqrt(2 * ratio);
+    const double e = 2.718281828459045;         // math.e
+    return (1 - pow(e, -1.4 * x)) * pow(e, -(x * x / 2)) / (qDen * x);
+}
+
+// FsplAttenuation._update (attenuation_models.py:28-36); equal positions keep 0 dB.
+GW_HD double fspl_db(double ax, double ay, double bx, double by, double frequency)
+{
+    if (ax == bx && ay == by) return 0.0;
+    const double dx = ax - bx, dy = ay - by;
+    const double d = sqrt(dx * dx + dy * dy);   // Position.distanceTo, devices/core.py:88-95
+    return 20 * log10(d) + 20 * log10(frequency) - 147.55;
+}
+
+// dbmToMilliwatts(power - attenuation), simple_stack.py:111, physical.py:91-98
+GW_HD double rx_power_mw(double power_dbm, double att_db) { return pow(10.0, (power_dbm - att_db) / 10); }
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Random123), counter-based; mode M error masks
+// ---------------------------------------------------------------------------
+
+GW_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                         uint32_t out[4])
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Key of the error flag of on-air bit k of transmission `txseq` of device `sender` on
+// band `band` of GLOBAL env `env`, as seen by `receiver`: the Philox counter is
+// (k>>2, txseq, sender | receiver<<8 | band<<16, env_lo), the key (seed_lo ^ env_hi, seed_hi);
+// bit k uses output word k&3 and is an error iff word < floor(ber * 2^32).
+GW_HD uint32_t ber_threshold(double ber) { return (uint32_t)(ber * 4294967296.0); }
+
+GW_HD void mask_words4(uint64_t seed, int64_t env, int band, int sender, uint32_t txseq, int receiver,
+                       uint32_t kq, uint32_t out[4])
+{
+    philox4x32_10(kq, txseq, (uint32_t)sender | ((uint32_t)receiver << 8) | ((uint32_t)band << 16),
+                  (uint32_t)(uint64_t)env, (uint32_t)seed ^ (uint32_t)((uint64_t)env >> 32),
+                  (uint32_t)(seed >> 32), out);
+}
+
+// serial reference of the per-range error count (host tests, tiny ranges); the kernels
+// use the warp-cooperative version in gw_kernels.cu
+GW_HD int64_t mask_errors_serial(uint64_t seed, int64_t env, int band, int sender, uint32_t txseq,
+                                 int receiver, int64_t k0, int64_t k1, double ber)
+{
+    const uint32_t thr = ber_threshold(ber);
+    int64_t n = 0;
+    uint32_t w[4];
+    int64_t cur = -1;
+    for (int64_t k = k0; k < k1; ++k) {
+        if ((k >> 2) != cur) { cur = k >> 2; mask_words4(seed, env, band, sender, txseq, receiver, (uint32_t)cur, w); }
+        n += (w[k & 3] < thr) ? 1 : 0;
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// band-sim state
+// ---------------------------------------------------------------------------
+
+template <int D, int NS, int NJ>
+struct Sim {
+    static constexpr int kD = D, kNS = NS, kNJ = NJ, kRrm = NS;
+    static constexpr int NJa = NJ > 0 ? NJ : 1;
+
+    double now;
+    uint32_t seq;                       // creation counter of timed events (the eid order)
+    int fault;
+    uint32_t ties;                      // exact-time ties between independent events (diagnostic)
+
+    // PHY, per device
+    double P[D];                        // SimplePhy._receivedPower (mW), simple_stack.py:80-82
+    int sphase[D];                      // S_*: macInHandler progress (simple_stack.py:192-212)
+    double tEv[D];                      // next PHY event: slot start / header end / completion
+    uint32_t sEv[D];
+    double txStart[D], tStop[D], tC[D]; // Transmission.startTime / stopTime / eCompletes time
+    uint32_t sC[D];
+    int cmdPay[D];                      // payload bytes of the SEND command in flight
+    uint32_t txSeq[D];                  // transmissions started by this device (mode M key)
+    int rxOf[D];                        // device whose transmission is being received, -1 idle
+    int rxSec[D];                       // 0 header, 1 payload
+    double ber[D], err[D], tReset[D];   // _receivedBitErrorRate / Sum / _lastReceivedErrorCountTime
+    double segT0[D];                    // mode M: start of the current constant-BER segment
+
+    // senders: traffic process + MAC
+    double tTick[NS];
+    uint32_t sTick[NS];
+    uint64_t ticks[NS];                 // ticks fired; packets enqueued = ticks * mult
+    int qn[NS];                         // queue length (<= 100)
+    uint64_t epochK[NS];                // counter(tick k) = min(65536, epochC + (k - epochK))
+    int epochC[NS];
+    uint64_t snapEnd[NS];               // packets with index < snapEnd read their size from the ring
+    int mac[NS];                        // MAC_*
+    int wDone[NS], wPend[NS];
+    double stopW[NS];
+    uint32_t sW[NS];
+
+    // jammers
+    double tJam[NJa];
+    uint32_t sJam[NJa];
+    int jamStage[NJa], jamPending[NJa];
+
+    // RRM
+    int annDest, annBytes;
+    double annSlots;
+    int rrmPend;
+    double tRrm;
+    uint32_t sRrm;
+    int assignDone;
+
+    // interpreter (counter_traffic.py:63-112)
+    int rv0, rv1, latestDiff, lastAbsDiff, done;
+
+    // statistics
+    uint32_t nTx;
+    uint32_t nDeliv[NS];
+};
+
+struct Event {
+    int kind, idx;
+    double t;
+};
+
+// construction-time state (CounterTrafficEnv.__init__, counter_traffic.py:114-133)
+template <int D, int NS, int NJ>
+GW_HD void init_sim(Sim<D, NS, NJ> &s, double thermal)
+{
+    s.now = 0.0; s.seq = 0; s.fault = 0; s.ties = 0;
+    for (int p = 0; p < D; ++p) {
+        s.P[p] = thermal; s.sphase[p] = S_IDLE; s.tEv[p] = 0; s.sEv[p] = 0;
+        s.txStart[p] = 0; s.tStop[p] = 0; s.tC[p] = 0; s.sC[p] = 0; s.cmdPay[p] = 0; s.txSeq[p] = 0;
+        s.rxOf[p] = -1; s.rxSec[p] = 0; s.ber[p] = 0; s.err[p] = 0; s.tReset[p] = 0; s.segT0[p] = 0;
+    }
+    // process Initialize events in construction order: senders, then jammers (URGENT, t = 0)
+    for (int k = 0; k < NS; ++k) {
+        s.tTick[k] = 0.0; s.sTick[k] = s.seq++;
+        s.ticks[k] = 0; s.qn[k] = 0; s.epochK[k] = 0; s.epochC[k] = 1; s.snapEnd[k] = 0;
+        s.mac[k] = MAC_NONE; s.wDone[k] = 0; s.wPend[k] = 0; s.stopW[k] = 0; s.sW[k] = 0;
+        s.nDeliv[k] = 0;
+    }
+    for (int j = 0; j < Sim<D, NS, NJ>::NJa; ++j) {
+        s.tJam[j] = 0.0; s.sJam[j] = (j < NJ) ? s.seq++ : 0; s.jamStage[j] = 0; s.jamPending[j] = 0;
+    }
+    s.annDest = 0; s.annBytes = 0; s.annSlots = 0; s.rrmPend = 0; s.tRrm = 0; s.sRrm = 0; s.assignDone = 0;
+    s.rv0 = s.rv1 = 0; s.latestDiff = 0; s.lastAbsDiff = 0; s.done = 0;
+    s.nTx = 0;
+}
+
+GW_HD bool seq_before(uint32_t a, uint32_t b) { return (int32_t)(a - b) < 0; }
+
+// ---------------------------------------------------------------------------
+// event selection: earliest (time, seq) among the timed slots
+// ---------------------------------------------------------------------------
+
+template <int D, int NS, int NJ>
+GW_HD Event select_event(Sim<D, NS, NJ> &s)
+{
+    double tmin = INFINITY;
+    uint32_t smin = 0;
+    int kind = EV_NONE, idx = 0, tie = 0;
+#define GW_CONSIDER(T, SQ, K, I)                                                        \
+    do {                                                                                \
+        const double t_ = (T);                                                          \
+        const uint32_t q_ = (SQ);                                                       \
+        if (t_ < tmin) { tmin = t_; smin = q_; kind = (K); idx = (I); tie = 0; }        \
+        else if (t_ == tmin) {                                                          \
+            tie |= ((K) != EV_TICK || kind != EV_TICK);                                 \
+            if (seq_before(q_, smin)) { smin = q_; kind = (K); idx = (I); }             \
+        }                                                                               \
+    } while (0)
+    for (int k = 0; k < NS; ++k) GW_CONSIDER(s.tTick[k], s.sTick[k], EV_TICK, k);
+    for (int j = 0; j < NJ; ++j) GW_CONSIDER(s.tJam[j], s.sJam[j], EV_JAM, j);
+    for (int d = 0; d < D; ++d)
+        if (s.sphase[d] >= S_SLOT) GW_CONSIDER(s.tEv[d], s.sEv[d], EV_PHY, d);
+    for (int k = 0; k < NS; ++k)
+        if (s.wPend[k]) GW_CONSIDER(s.stopW[k], s.sW[k], EV_W, k);
+    if (s.rrmPend) GW_CONSIDER(s.tRrm, s.sRrm, EV_RRM, 0);
+#undef GW_CONSIDER
+    Event e;
+    e.kind = kind; e.idx = idx; e.t = tmin;
+    s.ties += (uint32_t)tie;    // counted when selected AND when left behind; diagnostic only
+    return e;
+}
+
+// ---------------------------------------------------------------------------
+// which PHYs run SimplePhy._countBitErrors for this event (simple_stack.py:180-188)
+//   once[p]  : bit p set -> one count
+//   twice[p] : bit p set -> a second count (payload end: the completion callback counts,
+//              then the receive process counts again -- appendix B #4)
+// ---------------------------------------------------------------------------
+
+template <int D, int NS, int NJ>
+GW_HD void count_set(const Sim<D, NS, NJ> &s, const Event &ev, const double *srx, int &once, int &twice)
+{
+    once = 0; twice = 0;
+    if (ev.kind != EV_PHY) return;
+    int d = ev.idx, ph = 0;
+    for (int q = 0; q < D; ++q) if (q == d) ph = s.sphase[q];
+    for (int p = 0; p < D; ++p) {
+        const int rx = s.rxOf[p];
+        if (rx < 0) continue;
+        if (ph == S_HDR) {
+            if (rx == d && s.rxSec[p] == 0) once |= 1 << p;
+        } else {
+            // S_SLOT: the new transmission adds power; S_PAY: the completing one removes it.
+            // onReceivedPowerChange counts only for delta != 0 (simple_stack.py:224)
+            const bool delta_nz = (p != d) && (srx[p * D + d] != 0.0);
+            if (delta_nz) once |= 1 << p;
+            if (ph == S_PAY && rx == d && s.rxSec[p] == 1) {
+                if (delta_nz) twice |= 1 << p; else once |= 1 << p;
+            }
+        }
+    }
+}
+
+// mode R: expected-value accounting, `duration` measured from the last RESET (appendix B #5)
+template <int D, int NS, int NJ>
+GW_HD void do_counts_R(Sim<D, NS, NJ> &s, int once, int twice, double bitRate)
+{
+    for (int p = 0; p < D; ++p) {
+        if (!((once >> p) & 1)) continue;
+        const double duration = s.now - s.tReset[p];
+        const double bitErrors = s.ber[p] * duration * bitRate;
+        s.err[p] += bitErrors;
+        if ((twice >> p) & 1) s.err[p] += bitErrors;
+    }
+}
+
+// mode M: on-air bit range [k0, k1) of the segment that ends now, for PHY p
+template <int D, int NS, int NJ>
+GW_HD void mask_range(const Sim<D, NS, NJ> &s, int p, double bitRate, int &sender, uint32_t &txseq,
+                      int64_t &k0, int64_t &k1)
+{
+    int e = 0;
+    for (int q = 0; q < D; ++q) if (q == p) e = s.rxOf[q];
+    double start = 0; uint32_t sq = 0;
+    for (int q = 0; q < D; ++q) if (q == e) { start = s.txStart[q]; sq = s.txSeq[q] - 1u; }
+    double t0 = 0;
+    for (int q = 0; q < D; ++q) if (q == p) t0 = s.segT0[q];
+    sender = e; txseq = sq;
+    k0 = (int64_t)floor((t0 - start) * bitRate);
+    k1 = (int64_t)floor((s.now - start) * bitRate);
+}
+
+// ---------------------------------------------------------------------------
+// helpers of the transition function
+// ---------------------------------------------------------------------------
+
+template <int D, int NS, int NJ>
+GW_HD void begin_slot_wait(Sim<D, NS, NJ> &s, int d)
+{
+    // self._transmitting = True; yield SimMan.nextTimeSlot(TIME_SLOT_LENGTH)  (simple_stack.py:202-204)
+    const double t = s.now + (kSlot - fmod(s.now, kSlot));      // simtools.py:53
+    const uint32_t q = s.seq++;
+    for (int p = 0; p < D; ++p) if (p == d) { s.sphase[p] = S_SLOT; s.tEv[p] = t; s.sEv[p] = q; }
+}
+
+template <int D, int NS, int NJ>
+GW_HD void phy_send_init(Sim<D, NS, NJ> &s, int d)
+{
+    // SimplePhy.macInHandler start: wait while the receiver is active (simple_stack.py:199-200)
+    bool receiving = false;
+    for (int p = 0; p < D; ++p) if (p == d) receiving = s.rxOf[p] >= 0;
+    if (receiving) { for (int p = 0; p < D; ++p) if (p == d) s.sphase[p] = S_WAITRX; }
+    else begin_slot_wait(s, d);
+}
+
+// size of the head packet of sender k's queue (bytes of the Transmittable):
+// packets are enqueued `mult` per tick with byteSize = counter at that tick
+template <int D, int NS, int NJ, class Ring>
+GW_HD int head_size(const Sim<D, NS, NJ> &s, const BandParams &B, int k, const Ring &ring)
+{
+    int size = 0;
+    for (int q = 0; q < NS; ++q) {
+        if (q != k) continue;
+        if (B.payloadRule[q] >= 0) { size = B.payloadRule[q]; continue; }
+        const uint32_t m = (uint32_t)B.mult[q];
+        const uint64_t enq = s.ticks[q] * m;
+        const uint64_t j = enq - (uint64_t)s.qn[q];
+        if (j < s.snapEnd[q]) { size = ring(q, (uint32_t)(j % (uint64_t)kQueueCap)); continue; }
+        // tick of packet j = ticks - ceil(qn / m)
+        const uint64_t back = ((uint32_t)s.qn[q] + m - 1u) / m;
+        const uint64_t tick = s.ticks[q] - back;
+        const uint64_t c = (uint64_t)s.epochC[q] + (tick - s.epochK[q]);
+        size = c > (uint64_t)kCounterBound ? kCounterBound : (int)c;
+    }
+    return size;
+}
+
+// one pass of the SimpleMac window loop body with a non-empty queue (simple_stack.py:417-434)
+template <int D, int NS, int NJ, class Ring>
+GW_HD void mac_try_send(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, int k, const Ring &ring)
+{
+    const int size = head_size(s, B, k, ring);
+    const int bitSize = (kMacHdr + kNetHdr + size) * 8;
+    double stopW = 0;
+    for (int q = 0; q < NS; ++q) if (q == k) stopW = s.stopW[q];
+    const double timeLeft = stopW - s.now;
+    const double txTime = bitSize / P.dataRate;
+    if (!(timeLeft > txTime)) {
+        for (int q = 0; q < NS; ++q) if (q == k) s.mac[q] = MAC_IDLE;       // yield timeoutEvent
+        return;
+    }
+    for (int q = 0; q < NS; ++q) if (q == k) { s.qn[q] -= 1; s.mac[q] = MAC_WAIT_TX; }
+    for (int p = 0; p < D; ++p) if (p == k) s.cmdPay[p] = kNetHdr + size;
+    phy_send_init(s, k);
+}
+
+// loop head of the window loop (simple_stack.py:408-416)
+template <int D, int NS, int NJ, class Ring>
+GW_HD void mac_loop_head(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, int k, const Ring &ring)
+{
+    bool done = false, empty = false;
+    for (int q = 0; q < NS; ++q) if (q == k) { done = s.wDone[q] != 0; empty = s.qn[q] == 0; }
+    if (done) { for (int q = 0; q < NS; ++q) if (q == k) s.mac[q] = MAC_NONE; return; }
+    if (empty) { for (int q = 0; q < NS; ++q) if (q == k) s.mac[q] = MAC_WAIT_COND; return; }
+    mac_try_send(s, P, B, k, ring);
+}
+
+// end of SimplePhy._receive (simple_stack.py:264-267) without the deferred wake-up
+template <int D, int NS, int NJ>
+GW_HD void rx_clear(Sim<D, NS, NJ> &s, int p)
+{
+    for (int q = 0; q < D; ++q) if (q == p) { s.rxOf[q] = -1; s.err[q] = 0; s.ber[q] = 0.0; s.tReset[q] = s.now; s.segT0[q] = s.now; }
+}
+
+template <int D, int NS, int NJ>
+GW_HD bool decide(const Sim<D, NS, NJ> &s, const Params &P, int p, double totalBits)
+{
+    // bitErrorSum = round(bitErrorSum); bitErrorSum / totalBits <= maxCorrectableBer  (simple_stack.py:274-277)
+    double e = 0;
+    for (int q = 0; q < D; ++q) if (q == p) e = s.err[q];
+    return rint(e) / totalBits <= P.maxBer;
+}
+
+// ---------------------------------------------------------------------------
+// transition function: applies one timed event (counts already done); returns the set of
+// PHYs whose bit error rate must be re-evaluated afterwards (SimplePhy._updateBitErrorRate)
+// ---------------------------------------------------------------------------
+
+template <int D, int NS, int NJ, class Ring>
+GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const Event &ev,
+                      const double *srx, const Ring &ring)
+{
+    constexpr int RRM = NS;
+    int berMask = 0;
+    s.now = ev.t;
+    switch (ev.kind) {
+    case EV_TICK: {
+        // SenderDevice.senderProcess (counter_traffic.py:53-61): `mult` packets, counter += 1,
+        // next tick; then the MAC wakes if it waits on (_packetAddedEvent | timeoutEvent)
+        const int k = ev.idx;
+        bool wake = false;
+        for (int q = 0; q < NS; ++q) {
+            if (q != k) continue;
+            int n = s.qn[q] + B.mult[q];
+            s.qn[q] = n > kQueueCap ? kQueueCap : n;               // drop-oldest
+            s.ticks[q] += 1;
+            s.tTick[q] = s.now + B.interval[q];
+            s.sTick[q] = s.seq++;
+            wake = s.mac[q] == MAC_WAIT_COND;
+        }
+        if (wake) mac_try_send(s, P, B, k, ring);
+        break;
+    }
+    case EV_JAM: {
+        const int j = ev.idx, d = RRM + 1 + j;
+        for (int q = 0; q < NJ; ++q) {
+            if (q != j) continue;
+            if (s.jamStage[q] == 0) {               // yield timeout(initialDelay)
+                s.jamStage[q] = 1; s.tJam[q] = s.now + B.jamDelay[q]; s.sJam[q] = s.seq++;
+            } else if (s.jamStage[q] == 1) {        // first yield timeout(sendInterval)
+                s.jamStage[q] = 2; s.tJam[q] = s.now + B.jamInterval[q]; s.sJam[q] = s.seq++;
+            } else {
+                // macIn.send(SEND) -> queued executor; then yield timeout(sendInterval)
+                s.tJam[q] = s.now + B.jamInterval[q]; s.sJam[q] = s.seq++;
+                bool busy = false;
+                for (int p = 0; p < D; ++p) if (p == d) busy = s.sphase[p] != S_IDLE;
+                if (busy) { s.jamPending[q] += 1; if (s.jamPending[q] > 60) s.fault = FAULT_SENDQ; }
+                else { for (int p = 0; p < D; ++p) if (p == d) s.cmdPay[p] = B.jamPay[q]; phy_send_init(s, d); }
+            }
+        }
+        break;
+    }
+    case EV_PHY: {
+        const int d = ev.idx;
+        int ph = 0;
+        for (int q = 0; q < D; ++q) if (q == d) ph = s.sphase[q];
+        if (ph == S_SLOT) {
+            // FrequencyBand.transmit -> Transmission.__init__ (physical.py:224-279,596-608)
+            int hdrBytes = kMacHdr, payBytes = 0;
+            for (int q = 0; q < D; ++q) if (q == d) payBytes = s.cmdPay[q];
+            for (int j = 0; j < NJ; ++j) if (d == RRM + 1 + j) hdrBytes = B.jamHdr[j];
+            const double hd = (hdrBytes * 8) / P.dataRate;
+            const double pd = (payBytes * 8) / P.dataRate;
+            const double duration = hd + pd;
+            const double stop = s.now + duration;
+            const double headerStop = s.now + hd;
+            const double tH = s.now + (headerStop > s.now ? headerStop - s.now : 0.0);   // timeoutUntil
+            const double tC = s.now + (stop > s.now ? stop - s.now : 0.0);
+            const uint32_t qH = s.seq++, qC = s.seq++;
+            for (int q = 0; q < D; ++q) if (q == d) {
+                s.sphase[q] = S_HDR; s.tEv[q] = tH; s.sEv[q] = qH; s.tC[q] = tC; s.sC[q] = qC;
+                s.txStart[q] = s.now; s.tStop[q] = stop; s.txSeq[q] += 1;
+            }
+            s.nTx += 1;
+            // zero-delay notification: every other PHY registers the received power
+            // (simple_stack.py:130-144); a PHY that is receiving re-evaluates its BER
+            for (int p = 0; p < D; ++p) {
+                if (p == d) continue;
+                const double rp = srx[p * D + d];
+                s.P[p] += rp;
+                if (s.rxOf[p] >= 0 && rp != 0.0) {
+                    bool completed = false;
+                    for (int q = 0; q < D; ++q) if (q == s.rxOf[p]) completed = s.now >= s.tStop[q];
+                    if (!completed) berMask |= 1 << p;
+                }
+            }
+            // receive processes in PHY construction order: idle, non-transmitting PHYs lock on
+            // (simple_stack.py:214-235)
+            for (int p = 0; p < D; ++p) {
+                if (p == d || s.rxOf[p] >= 0 || s.sphase[p] >= S_SLOT) continue;
+                s.rxOf[p] = d; s.rxSec[p] = 0;
+                s.err[p] = 0; s.ber[p] = 0.0; s.tReset[p] = s.now; s.segT0[p] = s.now;
+                berMask |= 1 << p;
+            }
+        } else if (ph == S_HDR) {
+            // eHeaderCompletes: receivers decide on the header (simple_stack.py:241-251)
+            int hdrBytes = kMacHdr;
+            for (int j = 0; j < NJ; ++j) if (d == RRM + 1 + j) hdrBytes = B.jamHdr[j];
+            const double hdrBits = (hdrBytes * 8) * P.bitsFactor;
+            int wake = 0;
+            for (int p = 0; p < D; ++p) {
+                if (s.rxOf[p] != d || s.rxSec[p] != 0) continue;
+                if (decide(s, P, p, hdrBits)) {
+                    s.rxSec[p] = 1; s.err[p] = 0; s.ber[p] = 0.0; s.tReset[p] = s.now; s.segT0[p] = s.now;
+                    berMask |= 1 << p;
+                } else {
+                    rx_clear(s, p);
+                    if (s.sphase[p] == S_WAITRX) wake |= 1 << p;
+                }
+            }
+            for (int q = 0; q < D; ++q) if (q == d) { s.sphase[q] = S_PAY; s.tEv[q] = s.tC[q]; s.sEv[q] = s.sC[q]; }
+            for (int p = 0; p < D; ++p) if ((wake >> p) & 1) begin_slot_wait(s, p);   // _nReceivingFinished.event
+        } else {
+            // eCompletes, callbacks in registration order:
+            // 1. the sender's macInHandler resumes: _transmitting = False (simple_stack.py:210)
+            int payBytes = 0;
+            double stopD = 0;
+            for (int q = 0; q < D; ++q) if (q == d) { s.sphase[q] = S_IDLE; payBytes = s.cmdPay[q]; stopD = s.tStop[q]; }
+            const double payBits = (payBytes * 8) * P.bitsFactor;
+            // 2. _onCompletingTransmission of every other PHY (simple_stack.py:146-157)
+            for (int p = 0; p < D; ++p) {
+                if (p == d) continue;
+                const double rp = srx[p * D + d];
+                s.P[p] += -rp;
+                if (s.rxOf[p] >= 0 && rp != 0.0) {
+                    if (s.rxOf[p] == d) {
+                        // `if not t.completed: _updateBitErrorRate(t)` with the power entry
+                        // already popped: the reference raises KeyError (appendix B #12)
+                        if (!(s.now >= stopD)) s.fault = FAULT_REF_KEYERROR;
+                    } else {
+                        bool completed = false;
+                        for (int q = 0; q < D; ++q) if (q == s.rxOf[p]) completed = s.now >= s.tStop[q];
+                        if (!completed) berMask |= 1 << p;
+                    }
+                }
+            }
+            // 3. receivers that passed the header decide on the payload and deliver
+            int window = -1, wake = 0;
+            for (int p = 0; p < D; ++p) {
+                if (s.rxOf[p] != d || s.rxSec[p] != 1) continue;
+                if (decide(s, P, p, payBits)) {
+                    if (p < NS) {
+                        // SimpleMac.phyInHandler (blocking, not queued): only an announcement
+                        // addressed to an idle MAC has an effect (simple_stack.py:386-448)
+                        if (d == RRM && s.annDest == p) {
+                            bool idle = false;
+                            for (int q = 0; q < NS; ++q) if (q == p) idle = s.mac[q] == MAC_NONE;
+                            if (idle) window = p;
+                        }
+                    } else if (p == RRM) {
+                        // SimpleRrmMac.phyInHandler -> interpreter.onPacketReceived
+                        // (devices.py:163-168, counter_traffic.py:75-80); payload.value == 2 always
+                        if (d < NS) {
+                            if (d == 0) s.rv0 = kCounterByteLen;
+                            if (d == 1) s.rv1 = kCounterByteLen;
+                            s.latestDiff = s.rv0 - s.rv1;
+                            for (int q = 0; q < NS; ++q) if (q == d) s.nDeliv[q] += 1;
+                        }
+                    }
+                }
+                rx_clear(s, p);
+                if (s.sphase[p] == S_WAITRX) wake |= 1 << p;
+            }
+            // zero-delay children in SimPy's pop order:
+            // a. URGENT: phyInHandler of the grantee opens its window (simple_stack.py:399-406)
+            if (window >= 0) {
+                const double timeTotal = s.annSlots * kSlot;
+                const double stopW = s.now + timeTotal;
+                const uint32_t qW = s.seq++;
+                for (int q = 0; q < NS; ++q) if (q == window) { s.stopW[q] = stopW; s.sW[q] = qW; s.wPend[q] = 1; s.wDone[q] = 0; }
+                mac_loop_head(s, P, B, window, ring);
+            }
+            // b. SEND eProcessed: the sender's upper layer resumes
+            if (d < NS) {
+                mac_loop_head(s, P, B, d, ring);                // `yield message.eProcessed` returns
+            } else if (d == RRM) {
+                s.tRrm = s.now + (s.annSlots + 1) * kSlot;      // simple_stack.py:558
+                s.sRrm = s.seq++;
+                s.rrmPend = 1;
+            } else {
+                // c. executeNext of the queued macIn executor: a jammer's pending SEND starts
+                for (int j = 0; j < NJ; ++j) if (d == RRM + 1 + j && s.jamPending[j] > 0) {
+                    s.jamPending[j] -= 1;
+                    phy_send_init(s, d);
+                }
+            }
+            // d. _nReceivingFinished.event of the receivers that finished
+            for (int p = 0; p < D; ++p) if ((wake >> p) & 1) begin_slot_wait(s, p);
+        }
+        break;
+    }
+    case EV_W: {
+        // window timeoutEvent processed (simple_stack.py:406-420)
+        for (int q = 0; q < NS; ++q) {
+            if (q != ev.idx) continue;
+            s.wPend[q] = 0;
+            if (s.mac[q] == MAC_WAIT_TX) s.wDone[q] = 1;
+            else s.mac[q] = MAC_NONE;
+        }
+        break;
+    }
+    case EV_RRM:
+        // assignMessage.setProcessed() (simple_stack.py:561): the step ends here
+        s.rrmPend = 0;
+        s.assignDone = 1;
+        break;
+    default:
+        s.fault = FAULT_EMPTY;
+    }
+    return berMask;
+}
+
+// SimplePhy._updateBitErrorRate for the PHYs in berMask (simple_stack.py:161-173)
+template <int D, int NS, int NJ>
+GW_HD void update_bers(Sim<D, NS, NJ> &s, const Params &P, int berMask, const double *srx)
+{
+    for (int p = 0; p < D; ++p) {
+        if (!((berMask >> p) & 1)) continue;
+        const int e = s.rxOf[p];
+        if (e < 0) continue;
+        double S = 0;
+        for (int q = 0; q < D; ++q) if (q == e) S = srx[p * D + q];
+        const double N = s.P[p] - S;
+        if (!(S >= 0) || !(N >= 0)) { s.fault = FAULT_REF_ASSERT; continue; }   // simple_stack.py:168-169
+        s.ber[p] = ber_bpsk_mw(S, N, P.tenLog10BitRate, P.qDen);
+    }
+}
+
+// SimpleRrmDevice.assignFrequencyBand + SimpleRrmMac._sendAnnouncement start
+// (devices.py:178-203, simple_stack.py:536-556): the RRM PHY receives a SEND command
+template <int D, int NS, int NJ>
+GW_HD void begin_assignment(Sim<D, NS, NJ> &s, const Params &P, int device, int duration)
+{
+    const long long slots = (long long)duration * P.factor;         // counter_traffic.py:149
+    int nbytes = 1;                                                  // len(str(slots)), messages.py:62-64
+    for (long long v = slots; v >= 10; v /= 10) ++nbytes;
+    s.annDest = device;
+    s.annSlots = (double)slots;
+    s.annBytes = nbytes;
+    s.assignDone = 0;
+    // the RRM PHY's queued macIn executor is idle here: its previous SEND completed before
+    // the previous assignment's guard time-out (simple_stack.py:557-558)
+    if (s.sphase[NS] != S_IDLE) s.fault = FAULT_SENDQ;
+    for (int p = 0; p < D; ++p) if (p == NS) s.cmdPay[p] = nbytes;
+    phy_send_init(s, NS);
+}
+
+// ---------------------------------------------------------------------------
+// serial drivers (one band-sim at a time): used by the host build and by mode R on the
+// device; the mode-M kernels interleave the same pieces with warp-cooperative counting
+// ---------------------------------------------------------------------------
+
+struct NoMasks {
+    GW_HD int64_t operator()(int, int, uint32_t, int64_t, int64_t, double) const { return 0; }
+};
+
+// processes ONE timed event; `masks(receiver, sender, txseq, k0, k1, ber)` supplies mode-M counts
+template <int D, int NS, int NJ, class Ring, class Masks>
+GW_HD void process_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const Event &ev,
+                         const double *srx, const Ring &ring, const Masks &masks)
+{
+    int once, twice;
+    s.now = ev.t;
+    count_set(s, ev, srx, once, twice);
+    if (P.mode == MODE_R) {
+        do_counts_R(s, once, twice, P.bitRate);
+    } else {
+        for (int p = 0; p < D; ++p) {
+            if (!((once >> p) & 1)) continue;
+            int sender; uint32_t txseq; int64_t k0, k1;
+            mask_range(s, p, P.bitRate, sender, txseq, k0, k1);
+            if (k1 > k0) s.err[p] += (double)masks(p, sender, txseq, k0, k1, s.ber[p]);
+            s.segT0[p] = s.now;
+        }
+    }
+    const int berMask = apply_event(s, P, B, ev, srx, ring);
+    update_bers(s, P, berMask, srx);
+}
+
+// SimMan.runSimulation(assignSignal.eProcessed) (counter_traffic.py:155)
+template <int D, int NS, int NJ, class Ring, class Masks>
+GW_HD void run_until_assign(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B,
+                            const double *srx, const Ring &ring, const Masks &masks)
+{
+    while (!s.assignDone && !s.fault) {
+        const Event ev = select_event(s);
+        process_event(s, P, B, ev, srx, ring, masks);
+    }
+}
+
+// another band of the same env ended its assignment later, at time T: events strictly
+// before T are processed, then the clock is the env's clock
+template <int D, int NS, int NJ, class Ring, class Masks>
+GW_HD void run_until_time(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const double *srx,
+                          const Ring &ring, const Masks &masks, double T)
+{
+    while (!s.fault) {
+        const Event ev = select_event(s);
+        if (!(ev.t < T)) break;
+        process_event(s, P, B, ev, srx, ring, masks);
+    }
+    s.now = T;
+}
+
+// CounterTrafficEnv.reset (counter_traffic.py:135-144): sender counters := 0, interpreter
+// reset; time, queues and PHY state stay.  Queued packets keep the sizes they were enqueued
+// with: they are materialised into the snapshot ring (`ringw(sender, slot, size)`) before
+// the counter epoch changes.
+template <int D, int NS, int NJ, class RingW>
+GW_HD void reset_sim(Sim<D, NS, NJ> &s, const BandParams &B, RingW &ringw)
+{
+    for (int k = 0; k < NS; ++k) {
+        const uint64_t m = (uint64_t)B.mult[k];
+        const uint64_t enq = s.ticks[k] * m;
+        if (B.payloadRule[k] < 0) {
+            uint64_t j = enq - (uint64_t)s.qn[k];
+            if (j < s.snapEnd[k]) j = s.snapEnd[k];
+            for (; j < enq; ++j) {
+                const uint64_t tick = j / m;
+                const uint64_t c = (uint64_t)s.epochC[k] + (tick - s.epochK[k]);
+                ringw(k, (uint32_t)(j % (uint64_t)kQueueCap), c > (uint64_t)kCounterBound ? kCounterBound : (int)c);
+            }
+        }
+        s.snapEnd[k] = enq;
+        s.epochK[k] = s.ticks[k];
+        s.epochC[k] = 0;
+    }
+    s.latestDiff = 0; s.lastAbsDiff = 0; s.rv0 = 0; s.rv1 = 0; s.done = 0;   // counter_traffic.py:69-73
+}
+
+// Interpreter.getFeedback (envs/core.py:142-153, counter_traffic.py:85-107)
+template <int D, int NS, int NJ>
+GW_HD void feedback(Sim<D, NS, NJ> &s, long long &obs, double &reward, unsigned char &done)
+{
+    obs = (long long)s.latestDiff + kCounterBound;
+    const int absd = s.latestDiff < 0 ? -s.latestDiff : s.latestDiff;
+    int r = s.lastAbsDiff - absd;
+    s.lastAbsDiff = absd;
+    if (r > 10) r = 10; else if (r < -10) r = -10;
+    reward = (double)r;
+    done = (unsigned char)s.done;
+}
+
+}  // namespace gw

@@ -1,0 +1,207 @@
+/*
+ * gymwipe_b200 -- C ABI of the B200-native batched simulator for Gym-WiPE's per-step
+ * wireless hot path (CounterTrafficEnv.step and the networking stack below it).
+ *
+ * The reference (Gryph66/gymwipe) is 100 % Python and has NO plugin / FFI layer: the
+ * operator API of this path is the gym `Env` object itself.  Each entry point below
+ * therefore cites the reference interface it replaces (file:line under
+ * /root/reference); INTEGRATION.md shows the ctypes binding a maintainer would add to
+ * gymwipe/envs/counter_traffic.py.
+ *
+ * Conventions
+ *  - plain C, no torch / C++ types; all device buffers are raw CUDA device pointers
+ *    owned by the caller (e.g. torch.Tensor.data_ptr()), contiguous, on the handle's
+ *    device; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - every function returns 0 on success or a negative GW_E_* code; the message is
+ *    available from gw_last_error() (thread-local).  Nothing throws across the ABI.
+ *  - no allocation and no host synchronisation inside gw_step(); work is enqueued on the
+ *    caller's stream.  A handle is bound to one device and driven by one host thread at
+ *    a time; several handles (one per GPU / process) are independent.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *    with GW_E_CUDA.
+ */
+#ifndef GYMWIPE_B200_H
+#define GYMWIPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GW_ABI_VERSION 1
+
+#define GW_MAX_BANDS 4
+#define GW_MAX_DEVICES 4            /* per frequency band */
+#define GW_MAX_SENDERS 2
+#define GW_MAX_JAMMERS 1
+
+/* error codes */
+#define GW_OK 0
+#define GW_E_INVALID (-1)           /* bad argument / unsupported scenario */
+#define GW_E_CUDA (-2)              /* CUDA runtime error (message has the detail) */
+#define GW_E_STATE (-3)             /* state buffer too small / misaligned */
+#define GW_E_ACTION (-4)            /* an action was outside the action space (device flag) */
+#define GW_E_SIMFAULT (-5)          /* an env hit a condition under which the reference raises */
+
+/* error-accounting modes */
+#define GW_MODE_REFERENCE 0         /* "mode R": the reference's expected-value accounting, quirks included */
+#define GW_MODE_MASK_PHILOX 1       /* "mode M": per-bit Philox4x32-10 error masks generated in the kernel */
+#define GW_MODE_MASK_FED 2          /* "mode M": per-bit error masks read from HBM (gw_set_masks) */
+
+/* device roles on a band; canonical device order is senders, RRM, jammers */
+#define GW_ROLE_SENDER 1            /* SimpleNetworkDevice + traffic process, counter_traffic.py:37-61 */
+#define GW_ROLE_RRM 2               /* SimpleRrmDevice, networking/devices.py:113-203 */
+#define GW_ROLE_JAMMER 3            /* PHY-only periodic sender, tests/test_benchmark.py:20-50 */
+
+typedef struct {
+    int32_t role;
+    double x, y;                    /* default position (m), devices/core.py:15-98 */
+    /* GW_ROLE_SENDER */
+    int32_t multiplicity;           /* packets per tick, counter_traffic.py:44 */
+    int32_t payload_bytes;          /* -1: byteSize = counter (reference behaviour, app. B #1); >=0 fixed */
+    double interval;                /* COUNTER_INTERVAL, counter_traffic.py:31 */
+    /* GW_ROLE_JAMMER */
+    double jam_interval, jam_delay, jam_power_dbm;
+    int32_t jam_header_bytes, jam_payload_bytes;
+} gw_device_config;
+
+typedef struct {
+    int32_t n_devices;
+    double frequency_hz, bandwidth_hz;   /* FrequencyBandSpec, physical.py:293-306 */
+    gw_device_config device[GW_MAX_DEVICES];
+} gw_band_config;
+
+typedef struct {
+    int32_t abi_version;            /* GW_ABI_VERSION */
+    int64_t n_envs;                 /* envs held by this handle (this GPU's shard) */
+    int64_t env_id_offset;          /* global id of env 0: RNG keys use global ids (sharding-invariant) */
+    int32_t n_bands;
+    int32_t assignment_duration_factor;  /* BaseEnv.ASSIGNMENT_DURATION_FACTOR, envs/core.py:27 */
+    int32_t max_assign_duration;         /* BaseEnv.MAX_ASSIGN_DURATION, envs/core.py:25 */
+    int32_t mode;                   /* GW_MODE_* */
+    uint64_t seed;                  /* Philox key (mode M) */
+    int32_t per_env_positions;      /* 0: all envs share the scenario's positions */
+    gw_band_config band[GW_MAX_BANDS];
+} gw_config;
+
+typedef struct gw_handle gw_handle;
+
+/* Library / device probing. */
+int gw_abi_version(void);
+const char *gw_last_error(void);
+int gw_device_count(int *count);
+
+/* Fills `cfg` with CounterTrafficEnv's scenario: two senders at (0,+-2) m with
+ * multiplicity 1 and 3, the RRM at (0,0), one 2.4 GHz / 22 MHz band
+ * (gymwipe/envs/counter_traffic.py:114-133). */
+int gw_default_config(gw_config *cfg, int64_t n_envs);
+
+/* Bytes of device memory the env-batch state needs for `cfg`. */
+int gw_state_bytes(const gw_config *cfg, size_t *bytes);
+
+/* Replaces CounterTrafficEnv.__init__ (counter_traffic.py:114-133) for a batch of envs.
+ * `state` is a caller-owned device buffer of at least gw_state_bytes() bytes, 256-byte
+ * aligned (e.g. a torch uint8 tensor), or NULL to let the handle allocate its own.
+ * The construction-time state of the reference (time 0, counters 1, empty queues,
+ * thermal-noise-only received power) is written on `stream`. */
+int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes, void *stream,
+              gw_handle **out);
+void gw_destroy(gw_handle *h);
+
+/* Per-env device positions, float64 [n_envs][n_bands][GW_MAX_DEVICES][2] on the device
+ * (Device / Position, devices/core.py); recomputes the FSPL attenuation and received-
+ * power tables (kernel K1; attenuation_models.py:28-36, simple_stack.py:99-111).  With
+ * `positions == NULL` the scenario's default positions are applied to every env. */
+int gw_set_positions(gw_handle *h, const double *positions, void *stream);
+
+/* Replaces CounterTrafficEnv.reset (counter_traffic.py:135-144): sender counters := 0,
+ * interpreter reset; simulated time, queues and PHY state are NOT touched (app. B #10).
+ * `env_ids` (device int64[n]) selects envs, NULL = all.  `obs` (device int64
+ * [n_envs][n_bands]) may be NULL. */
+int gw_reset(gw_handle *h, const int64_t *env_ids, int64_t n, int64_t *obs, void *stream);
+
+/* Replaces CounterTrafficEnv.step (counter_traffic.py:146-158): one RRM assignment cycle
+ * for every env.  `device`, `duration`: device int32 [n_envs][n_bands] (action["device"],
+ * action["duration"]).  Outputs (device): obs int64, reward float64, done uint8, each
+ * [n_envs][n_bands].  Out-of-space actions set the handle's error flag (gw_check) and are
+ * clamped -- the reference asserts (counter_traffic.py:147). */
+int gw_step(gw_handle *h, const int32_t *device, const int32_t *duration,
+            int64_t *obs, double *reward, uint8_t *done, void *stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies the actions in, steps, copies
+ * obs / reward / done out and synchronises the stream.  This is the end-to-end path a
+ * gym-style caller with host-resident actions uses. */
+int gw_step_host(gw_handle *h, const int32_t *device, const int32_t *duration,
+                 int64_t *obs, double *reward, uint8_t *done, void *stream);
+
+/* Synchronises and reports the error flag the kernels raised since the last call:
+ * 0, GW_E_ACTION or GW_E_SIMFAULT (with the first faulting env in the message). */
+int gw_check(gw_handle *h, void *stream);
+
+/* Per-step statistics reduced over this handle's envs by the step kernel's epilogue
+ * (K5): out[0]=sum reward, [1]=deliveries of sender 0, [2]=of sender 1, [3]=sum done,
+ * [4]=env-steps, [5]=sum |latest difference|, [6]=transmissions, [7]=exact-time ties
+ * between independent events (diagnostic, expected 0).  `out` is device float64[8]; the
+ * accumulators are cleared after the copy when `clear` != 0.  Feeds the learner
+ * (agents/dqn_counter_traffic.py:70) -- and the NCCL all-reduce when envs are sharded. */
+int gw_stats(gw_handle *h, double *out8, int clear, void *stream);
+
+/* Read-back views of the structure-of-arrays state (device pointers into `state`). */
+typedef struct {
+    int64_t n_sims;                 /* n_envs * n_bands */
+    const double *now;              /* [n_envs] simulated time, simtools.py:56-58 */
+    const double *received_power;   /* [GW_MAX_DEVICES][n_sims] SimplePhy._receivedPower (mW) */
+    const double *next_tick;        /* [GW_MAX_SENDERS][n_sims] next traffic tick */
+    const uint64_t *ticks;          /* [GW_MAX_SENDERS][n_sims] ticks fired (counter = f(ticks)) */
+    const uint32_t *queue_len;      /* [GW_MAX_SENDERS][n_sims] SimpleMac._packetQueue length */
+    const uint32_t *n_transmissions;/* [n_sims] */
+    const uint32_t *n_delivered;    /* [GW_MAX_SENDERS][n_sims] packets the RRM decoded per sender */
+    const int32_t *received_values; /* [2][n_sims] interpreter.receivedValues */
+    const double *attenuation_db;   /* [GW_MAX_DEVICES*GW_MAX_DEVICES][n_tables] FSPL table */
+    const double *rx_power_mw;      /* [GW_MAX_DEVICES*GW_MAX_DEVICES][n_tables] 10**((P-att)/10) */
+    int64_t n_tables;               /* 1 (shared positions) or n_sims */
+} gw_state_view;
+int gw_state_ptrs(gw_handle *h, gw_state_view *view);
+
+/* Mode M, fed masks: `mask_words` is a device uint32 buffer laid out
+ * [n_envs][n_bands][GW_MAX_DEVICES sender][slots][GW_MAX_DEVICES receiver][words_per_row];
+ * transmission number q of a sender uses slot q % slots; bit k of a row is the error
+ * flag of on-air bit k (bit k%32 of word k/32).  The buffer stays caller-owned. */
+int gw_set_masks(gw_handle *h, const uint32_t *mask_words, int32_t slots, int32_t words_per_row,
+                 void *stream);
+
+/* ---- standalone kernels (numeric parity tests, roofline measurements) ------------- */
+
+/* K1: FSPL attenuation in dB, FsplAttenuation._update (attenuation_models.py:28-36) with
+ * Position.distanceTo (devices/core.py:88-95).  All arrays device float64[n]. */
+int gw_fspl_attenuation(const double *ax, const double *ay, const double *bx, const double *by,
+                        double frequency_hz, double *att_db, int64_t n, void *stream);
+
+/* K2: BPSK bit error rate from signal / noise power in mW: SimplePhy._updateBitErrorRate
+ * (simple_stack.py:161-173) -> BpskMcs.calculateBitErrorRate (physical.py:208-212) ->
+ * calculateEbToN0Ratio (:25-42) -> approxQFunction (:46-58). */
+int gw_ber_bpsk(const double *signal_mw, const double *noise_mw, double *ber, int64_t n,
+                void *stream);
+
+/* K3: bit-error count of mask rows over bit ranges (mode M accounting,
+ * SimplePhy._countBitErrors, simple_stack.py:180-188, with per-bit masks):
+ * counts[i] = popcount(bits [k0[i], k1[i]) of row rows[i]).  HBM-bound streaming
+ * popcount, one warp per descriptor. */
+int gw_count_bit_errors(const uint32_t *mask_words, int32_t words_per_row,
+                        const int64_t *rows, const int32_t *k0, const int32_t *k1,
+                        int32_t *counts, int64_t n, void *stream);
+
+/* Philox4x32-10 (Random123) block function, for known-answer tests: out[4*i..] =
+ * philox(counter[4*i..], key[2*i..]).  Device uint32 arrays. */
+int gw_philox4x32(const uint32_t *counter, const uint32_t *key, uint32_t *out, int64_t n,
+                  void *stream);
+
+/* The decider threshold Mcs.maxCorrectableBer (physical.py:160-185), host-side. */
+double gw_max_correctable_ber(int k, int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GYMWIPE_B200_H */

@@ -293,6 +293,12 @@ static void schedule_unobserved(gwo_sim *s) { s->eid++; }
 /* physical-layer arithmetic (physical.py:25-98,208-212)                    */
 /* ---------------------------------------------------------------------- */
 
+/* CPython evaluates `x ** y` on floats through libm pow(); gcc would fold pow(x, 2.0)
+ * into x*x (1 ulp away from glibc's pow in rare cases), so every power goes through a
+ * volatile function pointer (and the Makefile passes -fno-builtin-pow). */
+static double (*volatile libm_pow)(double, double) = pow;
+#define pow(a, b) libm_pow((a), (b))
+
 static double mw_to_dbm(double mw) { return 10 * log10(mw); }          /* physical.py:82-89 */
 static double dbm_to_mw(double dbm) { return pow(10.0, dbm / 10); }    /* physical.py:91-98 */
 

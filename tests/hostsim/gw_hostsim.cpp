@@ -1,0 +1,179 @@
+// TEST INFRASTRUCTURE -- host build of the device simulation core (gymwipe_b200/csrc/gw_core.cuh).
+//
+// The product runs this code only inside CUDA kernels; here the very same header is compiled
+// with g++ so that the event logic can be compared with the oracle in the `-m "not gpu"` test
+// suite (no GPU in the build container).  Never loaded by the gymwipe_b200 package.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../gymwipe_b200/csrc/gw_core.cuh"
+
+using namespace gw;
+
+namespace {
+
+struct HostRing {
+    int32_t *data;      // [NS][100]
+    int operator()(int k, uint32_t slot) const { return data[k * kQueueCap + slot]; }
+    void operator()(int k, uint32_t slot, int v) { data[k * kQueueCap + slot] = v; }
+};
+
+struct HostMasks {
+    uint64_t seed; int64_t env; int band;
+    int64_t operator()(int receiver, int sender, uint32_t txseq, int64_t k0, int64_t k1, double ber) const
+    {
+        return mask_errors_serial(seed, env, band, sender, txseq, receiver, k0, k1, ber);
+    }
+};
+
+struct HsBand {
+    int32_t ns, nj;
+    double frequency, bandwidth;
+    double x[kMaxDev], y[kMaxDev], power[kMaxDev];
+    int32_t mult[kMaxSend], payloadRule[kMaxSend];
+    double interval[kMaxSend];
+    double jamInterval, jamDelay;
+    int32_t jamHdr, jamPay;
+};
+
+struct HsScenario {
+    int32_t nbands, factor, mode;
+    uint64_t seed;
+    HsBand band[kMaxBands];
+};
+
+void fill_params(const HsScenario &sc, Params &P)
+{
+    std::memset(&P, 0, sizeof P);
+    P.nbands = sc.nbands; P.factor = sc.factor; P.maxDuration = 20; P.mode = sc.mode;
+    P.bitRate = 133.33333e3;
+    P.dataRate = 0.75 * P.bitRate;
+    P.maxBer = 0.25;
+    P.tenLog10BitRate = 10 * std::log10(P.bitRate);
+    P.qDen = 1.135 * std::sqrt(2 * 3.141592653589793);
+    P.bitsFactor = 1.25;
+    for (int b = 0; b < sc.nbands; ++b) {
+        BandParams &B = P.band[b];
+        const HsBand &h = sc.band[b];
+        B.ns = h.ns; B.nj = h.nj; B.ndev = h.ns + 1 + h.nj;
+        for (int k = 0; k < kMaxSend; ++k) { B.mult[k] = h.mult[k]; B.payloadRule[k] = h.payloadRule[k]; B.interval[k] = h.interval[k]; }
+        B.jamInterval[0] = h.jamInterval; B.jamDelay[0] = h.jamDelay; B.jamHdr[0] = h.jamHdr; B.jamPay[0] = h.jamPay;
+    }
+}
+
+template <int D, int NS, int NJ>
+struct EnvT {
+    Sim<D, NS, NJ> sim[kMaxBands];
+    double srx[kMaxBands][D * D];
+    int32_t ring[kMaxBands][NS * kQueueCap];
+};
+
+template <int D, int NS, int NJ>
+int run_t(const HsScenario &sc, int64_t nenv, int nsteps, int do_reset, const double *pos,
+          const int32_t *dev_tape, const int32_t *dur_tape, int64_t *obs, double *reward, uint8_t *done,
+          double *now, int64_t *counts, double *power_out, int64_t env_offset)
+{
+    Params P;
+    fill_params(sc, P);
+    const int nb = sc.nbands;
+    std::vector<EnvT<D, NS, NJ>> envs(1);
+    int fault_any = 0;
+    for (int64_t e = 0; e < nenv; ++e) {
+        EnvT<D, NS, NJ> &E = envs[0];
+        std::memset(&E, 0, sizeof E);
+        for (int b = 0; b < nb; ++b) {
+            const HsBand &h = sc.band[b];
+            const double npd = 1.38e-23 * (20.0 + 273.15);
+            const double thermal = npd * h.bandwidth * 1000;
+            init_sim(E.sim[b], thermal);
+            double x[D], y[D];
+            for (int d = 0; d < D; ++d) {
+                if (pos) { x[d] = pos[((e * nb + b) * kMaxDev + d) * 2]; y[d] = pos[((e * nb + b) * kMaxDev + d) * 2 + 1]; }
+                else { x[d] = h.x[d]; y[d] = h.y[d]; }
+            }
+            for (int p = 0; p < D; ++p)
+                for (int d = 0; d < D; ++d)
+                    E.srx[b][p * D + d] = (p == d) ? 0.0
+                        : rx_power_mw(h.power[d], fspl_db(x[p], y[p], x[d], y[d], h.frequency));
+        }
+        if (do_reset)
+            for (int b = 0; b < nb; ++b) { HostRing r{E.ring[b]}; reset_sim(E.sim[b], P.band[b], r); }
+        for (int t = 0; t < nsteps; ++t) {
+            const size_t base = ((size_t)t * nenv + e) * nb;
+            double T = 0;
+            for (int b = 0; b < nb; ++b) {
+                begin_assignment(E.sim[b], P, dev_tape[base + b], dur_tape[base + b]);
+            }
+            for (int b = 0; b < nb; ++b) {
+                HostRing r{E.ring[b]};
+                HostMasks mk{sc.seed, env_offset + e, b};
+                run_until_assign(E.sim[b], P, P.band[b], E.srx[b], r, mk);
+                if (E.sim[b].now > T) T = E.sim[b].now;
+            }
+            for (int b = 0; b < nb; ++b) {
+                HostRing r{E.ring[b]};
+                HostMasks mk{sc.seed, env_offset + e, b};
+                if (E.sim[b].now < T) run_until_time(E.sim[b], P, P.band[b], E.srx[b], r, mk, T);
+                long long o; double rw; unsigned char dn;
+                feedback(E.sim[b], o, rw, dn);
+                if (obs) obs[base + b] = o;
+                if (reward) reward[base + b] = rw;
+                if (done) done[base + b] = dn;
+                if (E.sim[b].fault) fault_any = E.sim[b].fault;
+            }
+            if (now) now[(size_t)t * nenv + e] = T;
+            if (fault_any) return fault_any;
+        }
+        for (int b = 0; b < nb; ++b) {
+            if (counts) {
+                int64_t *c = counts + ((size_t)e * nb + b) * 9;
+                c[0] = E.sim[b].nTx;
+                for (int k = 0; k < NS; ++k) c[1 + k] = E.sim[b].nDeliv[k];
+                c[8] = E.sim[b].ties;
+            }
+            if (power_out)
+                for (int d = 0; d < D; ++d) power_out[((size_t)e * nb + b) * kMaxDev + d] = E.sim[b].P[d];
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hs_run(const HsScenario *sc, int64_t nenv, int nsteps, int do_reset, const double *pos,
+           const int32_t *dev_tape, const int32_t *dur_tape, int64_t *obs, double *reward, uint8_t *done,
+           double *now, int64_t *counts, double *power_out, int64_t env_offset)
+{
+    const int ns = sc->band[0].ns, nj = sc->band[0].nj;
+    for (int b = 1; b < sc->nbands; ++b)
+        if (sc->band[b].ns != ns || sc->band[b].nj != nj) return -1;
+    if (ns == 2 && nj == 0)
+        return run_t<3, 2, 0>(*sc, nenv, nsteps, do_reset, pos, dev_tape, dur_tape, obs, reward, done, now, counts, power_out, env_offset);
+    if (ns == 2 && nj == 1)
+        return run_t<4, 2, 1>(*sc, nenv, nsteps, do_reset, pos, dev_tape, dur_tape, obs, reward, done, now, counts, power_out, env_offset);
+    return -1;
+}
+
+double hs_ber(double S, double N)
+{
+    return ber_bpsk_mw(S, N, 10 * std::log10(133.33333e3), 1.135 * std::sqrt(2 * 3.141592653589793));
+}
+
+double hs_fspl(double ax, double ay, double bx, double by, double f) { return fspl_db(ax, ay, bx, by, f); }
+
+void hs_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out)
+{
+    philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+}
+
+int64_t hs_mask_errors(uint64_t seed, int64_t env, int band, int sender, uint32_t txseq, int receiver,
+                       int64_t k0, int64_t k1, double ber)
+{
+    return mask_errors_serial(seed, env, band, sender, txseq, receiver, k0, k1, ber);
+}
+
+}

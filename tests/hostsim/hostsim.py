@@ -1,0 +1,117 @@
+"""
+TEST INFRASTRUCTURE -- ctypes wrapper of the host build of the device simulation core
+(``tests/hostsim/gw_hostsim.cpp`` includes ``gymwipe_b200/csrc/gw_core.cuh``).  Lets the
+``-m "not gpu"`` suite compare the kernel's event logic with the oracle without a GPU.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_hostsim.so")
+SRC = os.path.join(HERE, "gw_hostsim.cpp")
+CORE = os.path.join(HERE, "..", "..", "gymwipe_b200", "csrc", "gw_core.cuh")
+
+MAXDEV, MAXSEND, MAXBAND = 4, 2, 4
+
+
+class HsBand(C.Structure):
+    _fields_ = [("ns", C.c_int32), ("nj", C.c_int32), ("frequency", C.c_double), ("bandwidth", C.c_double),
+                ("x", C.c_double * MAXDEV), ("y", C.c_double * MAXDEV), ("power", C.c_double * MAXDEV),
+                ("mult", C.c_int32 * MAXSEND), ("payloadRule", C.c_int32 * MAXSEND),
+                ("interval", C.c_double * MAXSEND),
+                ("jamInterval", C.c_double), ("jamDelay", C.c_double),
+                ("jamHdr", C.c_int32), ("jamPay", C.c_int32)]
+
+
+class HsScenario(C.Structure):
+    _fields_ = [("nbands", C.c_int32), ("factor", C.c_int32), ("mode", C.c_int32), ("seed", C.c_uint64),
+                ("band", HsBand * MAXBAND)]
+
+
+_lib = None
+
+
+def build(force=False):
+    if force or not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(CORE)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared",
+                               "-o", SO, SRC])
+    return SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(SO)
+        L.hs_run.restype = C.c_int
+        L.hs_run.argtypes = [C.POINTER(HsScenario), C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int64]
+        L.hs_ber.restype = C.c_double
+        L.hs_ber.argtypes = [C.c_double, C.c_double]
+        L.hs_fspl.restype = C.c_double
+        L.hs_fspl.argtypes = [C.c_double] * 5
+        L.hs_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hs_mask_errors.restype = C.c_int64
+        L.hs_mask_errors.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.c_int,
+                                     C.c_int64, C.c_int64, C.c_double]
+        _lib = L
+    return _lib
+
+
+def scenario_from_dict(d, mode=0, seed=0):
+    sc = HsScenario()
+    sc.nbands = len(d["bands"])
+    sc.factor = int(d.get("assignment_duration_factor", 1000))
+    sc.mode = mode
+    sc.seed = seed
+    for b, bd in enumerate(d["bands"]):
+        hb = sc.band[b]
+        devs = bd["devices"]
+        roles = [x["role"] for x in devs]
+        hb.ns = roles.count("sender")
+        hb.nj = roles.count("jammer")
+        assert roles == ["sender"] * hb.ns + ["rrm"] + ["jammer"] * hb.nj
+        hb.frequency = float(bd.get("frequency", 2.4e9))
+        hb.bandwidth = float(bd.get("bandwidth", 22e6))
+        for i, x in enumerate(devs):
+            hb.x[i], hb.y[i] = float(x["x"]), float(x["y"])
+            hb.power[i] = float(x.get("power", 0.0)) if x["role"] == "jammer" else 0.0
+            if x["role"] == "sender":
+                hb.mult[i] = int(x["mult"])
+                p = x.get("payload", "counter")
+                hb.payloadRule[i] = -1 if p == "counter" else int(p)
+                hb.interval[i] = float(x.get("interval", 0.001))
+                assert int(x["dest"]) == 1 - i
+            elif x["role"] == "jammer":
+                hb.jamInterval = float(x["interval"])
+                hb.jamDelay = float(x["delay"])
+                hb.jamHdr = int(x.get("hdr", 13))
+                hb.jamPay = int(x["payload"])
+    return sc
+
+
+def run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, mode=0, seed=0, env_offset=0):
+    L = lib()
+    sc = scenario_from_dict(scenario, mode, seed) if isinstance(scenario, dict) else scenario
+    nb = sc.nbands
+    dev_tape = np.ascontiguousarray(dev_tape, dtype=np.int32)
+    dur_tape = np.ascontiguousarray(dur_tape, dtype=np.int32)
+    if dev_tape.ndim == 2:
+        dev_tape, dur_tape = dev_tape[:, :, None], dur_tape[:, :, None]
+    nsteps, nenv, _ = dev_tape.shape
+    obs = np.zeros((nsteps, nenv, nb), np.int64)
+    rew = np.zeros((nsteps, nenv, nb), np.float64)
+    done = np.zeros((nsteps, nenv, nb), np.uint8)
+    now = np.zeros((nsteps, nenv), np.float64)
+    counts = np.zeros((nenv, nb, 9), np.int64)
+    power = np.zeros((nenv, nb, MAXDEV), np.float64)
+    if pos is not None:
+        pos = np.ascontiguousarray(pos[:, :, :MAXDEV, :], dtype=np.float64)
+
+    def ptr(a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+    rc = L.hs_run(C.byref(sc), nenv, nsteps, 1 if do_reset else 0, ptr(pos), ptr(dev_tape), ptr(dur_tape),
+                  ptr(obs), ptr(rew), ptr(done), ptr(now), ptr(counts), ptr(power), env_offset)
+    return {"rc": rc, "obs": obs, "reward": rew, "done": done, "now": now, "counts": counts, "power": power}
