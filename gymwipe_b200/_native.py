@@ -1,0 +1,133 @@
+"""
+Loader and ctypes declarations of the C-ABI library (``include/gymwipe_b200.h``).
+
+The library is built IN-TREE (``gymwipe_b200/lib/libgymwipe_b200.so``) from
+``gymwipe_b200/csrc/gw_kernels.cu`` with ``nvcc -gencode arch=compute_100a,code=sm_100a``.
+There is no CPU fallback: if the library is missing it is compiled, and if that is
+impossible (or no CUDA device is present when an env is constructed) an error is raised.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libgymwipe_b200.so")
+INCLUDE = os.path.join(HERE, "..", "include", "gymwipe_b200.h")
+
+GW_ABI_VERSION = 1
+GW_MAX_BANDS, GW_MAX_DEVICES, GW_MAX_SENDERS, GW_MAX_JAMMERS = 4, 4, 2, 1
+GW_OK, GW_E_INVALID, GW_E_CUDA, GW_E_STATE, GW_E_ACTION, GW_E_SIMFAULT = 0, -1, -2, -3, -4, -5
+GW_MODE_REFERENCE, GW_MODE_MASK_PHILOX, GW_MODE_MASK_FED = 0, 1, 2
+GW_ROLE_SENDER, GW_ROLE_RRM, GW_ROLE_JAMMER = 1, 2, 3
+(GW_FIELD_NOW, GW_FIELD_RECEIVED_POWER, GW_FIELD_NEXT_TICK, GW_FIELD_COUNTER, GW_FIELD_QUEUE_LEN,
+ GW_FIELD_N_TRANSMISSIONS, GW_FIELD_N_DELIVERED, GW_FIELD_RECEIVED_VALUES, GW_FIELD_ATTENUATION_DB,
+ GW_FIELD_RX_POWER_MW, GW_FIELD_FAULT, GW_FIELD_TIES, GW_FIELD_TX_SEQ) = range(13)
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-fmad=false",
+              "-lineinfo", "-Xcompiler", "-fPIC", "-shared"]
+
+
+class DeviceConfig(C.Structure):
+    _fields_ = [("role", C.c_int32), ("x", C.c_double), ("y", C.c_double),
+                ("multiplicity", C.c_int32), ("payload_bytes", C.c_int32), ("interval", C.c_double),
+                ("jam_interval", C.c_double), ("jam_delay", C.c_double), ("jam_power_dbm", C.c_double),
+                ("jam_header_bytes", C.c_int32), ("jam_payload_bytes", C.c_int32)]
+
+
+class BandConfig(C.Structure):
+    _fields_ = [("n_devices", C.c_int32), ("frequency_hz", C.c_double), ("bandwidth_hz", C.c_double),
+                ("device", DeviceConfig * GW_MAX_DEVICES)]
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("n_envs", C.c_int64), ("env_id_offset", C.c_int64),
+                ("n_bands", C.c_int32), ("assignment_duration_factor", C.c_int32),
+                ("max_assign_duration", C.c_int32), ("mode", C.c_int32), ("seed", C.c_uint64),
+                ("per_env_positions", C.c_int32), ("band", BandConfig * GW_MAX_BANDS)]
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("gymwipe_b200 native error %d: %s" % (code, message))
+        self.code = code
+
+
+def _sources():
+    return [os.path.join(CSRC, f) for f in ("gw_kernels.cu", "gw_core.cuh")] + [INCLUDE]
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.exists(s) and os.path.getmtime(s) > t for s in _sources())
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library for sm_100a (nvcc cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("gymwipe_b200: %s is missing and nvcc is not available to build it; "
+                           "there is no CPU fallback" % LIB_PATH)
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        ["-o", LIB_PATH, os.path.join(CSRC, "gw_kernels.cu")]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+_VP = C.c_void_p
+_SIGNATURES = {
+    "gw_abi_version": (C.c_int, []),
+    "gw_last_error": (C.c_char_p, []),
+    "gw_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "gw_default_config": (C.c_int, [C.POINTER(Config), C.c_int64]),
+    "gw_state_bytes": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_size_t)]),
+    "gw_create": (C.c_int, [C.POINTER(Config), C.c_int, _VP, C.c_size_t, _VP, C.POINTER(_VP)]),
+    "gw_destroy": (None, [_VP]),
+    "gw_set_positions": (C.c_int, [_VP, _VP, _VP]),
+    "gw_reset": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
+    "gw_step": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "gw_step_host": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "gw_check": (C.c_int, [_VP, _VP]),
+    "gw_stats": (C.c_int, [_VP, _VP, C.c_int, _VP]),
+    "gw_read_state": (C.c_int, [_VP, C.c_int, _VP, _VP]),
+    "gw_set_masks": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP]),
+    "gw_fspl_attenuation": (C.c_int, [_VP, _VP, _VP, _VP, C.c_double, _VP, C.c_int64, _VP]),
+    "gw_ber_bpsk": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),
+    "gw_count_bit_errors": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP, _VP, C.c_int64, _VP]),
+    "gw_philox4x32": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),
+    "gw_max_correctable_ber": (C.c_double, [C.c_int, C.c_int]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib():
+    """The loaded C-ABI library (built on first use if the in-tree .so is stale or absent)."""
+    global _lib
+    if _lib is None:
+        if needs_build():
+            build()
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        if L.gw_abi_version() != GW_ABI_VERSION:
+            raise RuntimeError("gymwipe_b200: ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != GW_OK:
+        raise NativeError(rc, lib().gw_last_error().decode("utf-8", "replace"))
+    return rc

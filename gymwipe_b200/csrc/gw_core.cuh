@@ -689,14 +689,14 @@ struct NoMasks {
 };
 
 // processes ONE timed event; `masks(receiver, sender, txseq, k0, k1, ber)` supplies mode-M counts
-template <int D, int NS, int NJ, class Ring, class Masks>
+template <int MODE, int D, int NS, int NJ, class Ring, class Masks>
 GW_HD void process_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const Event &ev,
                          const double *srx, const Ring &ring, const Masks &masks)
 {
     int once, twice;
     s.now = ev.t;
     count_set(s, ev, srx, once, twice);
-    if (P.mode == MODE_R) {
+    if (MODE == MODE_R) {
         do_counts_R(s, once, twice, P.bitRate);
     } else {
         for (int p = 0; p < D; ++p) {
@@ -712,26 +712,26 @@ GW_HD void process_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B
 }
 
 // SimMan.runSimulation(assignSignal.eProcessed) (counter_traffic.py:155)
-template <int D, int NS, int NJ, class Ring, class Masks>
+template <int MODE, int D, int NS, int NJ, class Ring, class Masks>
 GW_HD void run_until_assign(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B,
                             const double *srx, const Ring &ring, const Masks &masks)
 {
     while (!s.assignDone && !s.fault) {
         const Event ev = select_event(s);
-        process_event(s, P, B, ev, srx, ring, masks);
+        process_event<MODE>(s, P, B, ev, srx, ring, masks);
     }
 }
 
 // another band of the same env ended its assignment later, at time T: events strictly
 // before T are processed, then the clock is the env's clock
-template <int D, int NS, int NJ, class Ring, class Masks>
+template <int MODE, int D, int NS, int NJ, class Ring, class Masks>
 GW_HD void run_until_time(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const double *srx,
                           const Ring &ring, const Masks &masks, double T)
 {
     while (!s.fault) {
         const Event ev = select_event(s);
         if (!(ev.t < T)) break;
-        process_event(s, P, B, ev, srx, ring, masks);
+        process_event<MODE>(s, P, B, ev, srx, ring, masks);
     }
     s.now = T;
 }

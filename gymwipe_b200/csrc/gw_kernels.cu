@@ -1,0 +1,1172 @@
+// gymwipe_b200 -- sm_100a kernels and the C ABI (include/gymwipe_b200.h).
+//
+// Kernels
+//   K1  tables_kernel        FSPL attenuation + received-power tables from device positions
+//   K2  ber_kernel           standalone BPSK BER (numeric parity tests)
+//   K3  count_bits_kernel    HBM-streaming popcount of error-mask rows, one warp per descriptor
+//   K4  step_kernel          fused event-ordered step: RRM announcement, MAC window, PHY
+//                            transmissions, SINR/BER segments, decider, delivery, interpreter
+//   K5  (epilogue of K4)     per-block reduction of reward / delivery statistics
+//
+// Layout of the env-batch state (structure of arrays, one 16-byte chunk per thread and
+// field group so that a warp's loads/stores are 512 contiguous bytes, 128-bit per lane):
+//   now   [n_envs]                       fp64
+//   hot   [HOT_CHUNKS ][n_sims] x 16 B   always read at step start / written at step end
+//   cold  [COLD_CHUNKS][n_sims] x 16 B   only touched when a transmission, reception or MAC
+//                                        window is in flight across a step boundary
+//   ring  [2*100][n_sims] int32          sizes of queued packets that predate a reset()
+//   att / srx [16][n_tables] fp64        attenuation (dB) and received power (mW) tables
+//
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/gymwipe_b200.h"
+#include "gw_core.cuh"
+
+using namespace gw;
+
+// ------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(GW_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------
+// state layout
+// ------------------------------------------------------------------------------------
+
+enum : int {
+    H_P01 = 0, H_P23, H_TICK, H_TICKS, H_U0, H_U1, H_U2, H_JAM, H_EPK, H_SNAP, H_EPC, HOT_CHUNKS
+};
+// cold: per device 5 chunks, then per sender 1
+enum : int { C_EV = 0, C_TX, C_RX, C_RT, C_U, C_PER_DEV };
+constexpr int COLD_CHUNKS = C_PER_DEV * kMaxDev + kMaxSend;
+
+struct StatePtrs {
+    long long nsim, nenv, ntab;
+    int nb;
+    double *now;
+    uint4 *hot;
+    uint4 *cold;
+    int32_t *ring;
+    double *att;
+    double *srx;
+};
+
+struct Layout {
+    size_t off_now, off_hot, off_cold, off_ring, off_att, off_srx, total;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static Layout make_layout(long long nenv, int nb, long long ntab)
+{
+    const long long nsim = nenv * nb;
+    Layout L;
+    size_t o = 0;
+    L.off_now = o; o = align_up(o + sizeof(double) * nenv, 256);
+    L.off_hot = o; o = align_up(o + 16ull * HOT_CHUNKS * nsim, 256);
+    L.off_cold = o; o = align_up(o + 16ull * COLD_CHUNKS * nsim, 256);
+    L.off_ring = o; o = align_up(o + 4ull * kMaxSend * kQueueCap * nsim, 256);
+    L.off_att = o; o = align_up(o + 8ull * 16 * ntab, 256);
+    L.off_srx = o; o = align_up(o + 8ull * 16 * ntab, 256);
+    L.total = o;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------
+
+struct gw_handle {
+    gw_config cfg;
+    int device;
+    Params P;
+    StatePtrs st;
+    Layout layout;
+    void *owned_state;
+    double *stats;          // device [8]
+    int *errflag;           // device [4]: code, sim, fault, -
+    double power_dbm[kMaxBands][kMaxDev];
+    double default_pos[kMaxBands][kMaxDev][2];
+    double thermal[kMaxBands];
+    double frequency[kMaxBands];
+    int D, NS, NJ;
+    // staging for gw_step_host
+    int32_t *d_dev, *d_dur;
+    long long *d_obs;
+    double *d_rew;
+    unsigned char *d_done;
+    // mode M fed masks
+    const uint32_t *masks;
+    int mask_slots, mask_words;
+};
+
+// ------------------------------------------------------------------------------------
+// device helpers: chunk access, pack / unpack
+// ------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint4 ld_chunk(const uint4 *base, long long nsim, int c, long long i)
+{
+    return base[(long long)c * nsim + i];
+}
+__device__ __forceinline__ void st_chunk(uint4 *base, long long nsim, int c, long long i, uint4 v)
+{
+    base[(long long)c * nsim + i] = v;
+}
+__device__ __forceinline__ uint4 pack_dd(double a, double b)
+{
+    uint4 v;
+    const unsigned long long x = (unsigned long long)__double_as_longlong(a), y = (unsigned long long)__double_as_longlong(b);
+    v.x = (unsigned)x; v.y = (unsigned)(x >> 32); v.z = (unsigned)y; v.w = (unsigned)(y >> 32);
+    return v;
+}
+__device__ __forceinline__ double lo_d(uint4 v) { return __longlong_as_double((long long)(((unsigned long long)v.y << 32) | v.x)); }
+__device__ __forceinline__ double hi_d(uint4 v) { return __longlong_as_double((long long)(((unsigned long long)v.w << 32) | v.z)); }
+__device__ __forceinline__ uint4 pack_qq(unsigned long long x, unsigned long long y)
+{
+    uint4 v; v.x = (unsigned)x; v.y = (unsigned)(x >> 32); v.z = (unsigned)y; v.w = (unsigned)(y >> 32); return v;
+}
+__device__ __forceinline__ unsigned long long lo_q(uint4 v) { return ((unsigned long long)v.y << 32) | v.x; }
+__device__ __forceinline__ unsigned long long hi_q(uint4 v) { return ((unsigned long long)v.w << 32) | v.z; }
+
+// flagsA: sphase[4] 3b | (rxOf+1)[4] 3b | rxSec[4] 1b | mac[2] 2b
+// flagsB: qn[2] 7b | wDone[2] | wPend[2] | jamStage 2b | jamPending 6b | rv0!=0 | rv1!=0 | lastAbs!=0 | done | busy
+template <int D, int NS, int NJ>
+__device__ __forceinline__ void unpack_flags(Sim<D, NS, NJ> &s, unsigned a, unsigned b)
+{
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        s.sphase[d] = (a >> (3 * d)) & 7;
+        s.rxOf[d] = (int)((a >> (12 + 3 * d)) & 7) - 1;
+        s.rxSec[d] = (a >> (24 + d)) & 1;
+    }
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        s.mac[k] = (a >> (28 + 2 * k)) & 3;
+        s.qn[k] = (b >> (7 * k)) & 127;
+        s.wDone[k] = (b >> (14 + k)) & 1;
+        s.wPend[k] = (b >> (16 + k)) & 1;
+    }
+    s.jamStage[0] = (b >> 18) & 3;
+    s.jamPending[0] = (b >> 20) & 63;
+    s.rv0 = ((b >> 26) & 1) ? kCounterByteLen : 0;
+    s.rv1 = ((b >> 27) & 1) ? kCounterByteLen : 0;
+    s.latestDiff = s.rv0 - s.rv1;
+    s.lastAbsDiff = ((b >> 28) & 1) ? kCounterByteLen : 0;
+    s.done = (b >> 29) & 1;
+}
+
+template <int D, int NS, int NJ>
+__device__ __forceinline__ bool sim_busy(const Sim<D, NS, NJ> &s)
+{
+    bool busy = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) busy |= (s.sphase[d] != S_IDLE) | (s.rxOf[d] >= 0);
+#pragma unroll
+    for (int k = 0; k < NS; ++k) busy |= (s.mac[k] != MAC_NONE) | (s.wPend[k] != 0);
+    return busy;
+}
+
+template <int D, int NS, int NJ>
+__device__ __forceinline__ void pack_flags(const Sim<D, NS, NJ> &s, bool busy, unsigned &a, unsigned &b)
+{
+    a = 0; b = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        a |= (unsigned)s.sphase[d] << (3 * d);
+        a |= (unsigned)(s.rxOf[d] + 1) << (12 + 3 * d);
+        a |= (unsigned)s.rxSec[d] << (24 + d);
+    }
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        a |= (unsigned)s.mac[k] << (28 + 2 * k);
+        b |= (unsigned)s.qn[k] << (7 * k);
+        b |= (unsigned)s.wDone[k] << (14 + k);
+        b |= (unsigned)s.wPend[k] << (16 + k);
+    }
+    b |= (unsigned)s.jamStage[0] << 18;
+    b |= (unsigned)s.jamPending[0] << 20;
+    b |= (unsigned)(s.rv0 != 0) << 26;
+    b |= (unsigned)(s.rv1 != 0) << 27;
+    b |= (unsigned)(s.lastAbsDiff != 0) << 28;
+    b |= (unsigned)(s.done != 0) << 29;
+    b |= (unsigned)busy << 31;
+}
+
+template <int D, int NS, int NJ>
+__device__ __forceinline__ void load_sim(Sim<D, NS, NJ> &s, const StatePtrs &st, long long i, double now)
+{
+    const long long n = st.nsim;
+    s.now = now;
+    uint4 v = ld_chunk(st.hot, n, H_P01, i);
+    s.P[0] = lo_d(v); s.P[1] = hi_d(v);
+    v = ld_chunk(st.hot, n, H_P23, i);
+    s.P[2] = lo_d(v);
+    if (D > 3) s.P[D > 3 ? 3 : 0] = hi_d(v);
+    v = ld_chunk(st.hot, n, H_TICK, i);
+    s.tTick[0] = lo_d(v); s.tTick[1] = hi_d(v);
+    v = ld_chunk(st.hot, n, H_TICKS, i);
+    s.ticks[0] = lo_q(v); s.ticks[1] = hi_q(v);
+    const uint4 u0 = ld_chunk(st.hot, n, H_U0, i);
+    s.seq = u0.x; s.nTx = u0.w;
+    unpack_flags(s, u0.y, u0.z);
+    v = ld_chunk(st.hot, n, H_U1, i);
+    s.sTick[0] = v.x; s.sTick[1] = v.y; s.nDeliv[0] = v.z; s.nDeliv[1] = v.w;
+    v = ld_chunk(st.hot, n, H_U2, i);
+    s.txSeq[0] = v.x; s.txSeq[1] = v.y; s.txSeq[2] = v.z;
+    if (D > 3) s.txSeq[D > 3 ? 3 : 0] = v.w;
+    if (NJ > 0) {
+        v = ld_chunk(st.hot, n, H_JAM, i);
+        s.tJam[0] = lo_d(v); s.sJam[0] = v.z;
+    } else {
+        s.tJam[0] = 0; s.sJam[0] = 0;
+    }
+    v = ld_chunk(st.hot, n, H_EPK, i);
+    s.epochK[0] = lo_q(v); s.epochK[1] = hi_q(v);
+    v = ld_chunk(st.hot, n, H_SNAP, i);
+    s.snapEnd[0] = lo_q(v); s.snapEnd[1] = hi_q(v);
+    v = ld_chunk(st.hot, n, H_EPC, i);
+    s.epochC[0] = (int)v.x; s.epochC[1] = (int)v.y; s.fault = (int)v.z; s.ties = v.w;
+    const bool busy = (u0.z >> 31) & 1;
+    if (busy) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            uint4 c = ld_chunk(st.cold, n, d * C_PER_DEV + C_EV, i);
+            s.tEv[d] = lo_d(c); s.tC[d] = hi_d(c);
+            c = ld_chunk(st.cold, n, d * C_PER_DEV + C_TX, i);
+            s.txStart[d] = lo_d(c); s.tStop[d] = hi_d(c);
+            c = ld_chunk(st.cold, n, d * C_PER_DEV + C_RX, i);
+            s.ber[d] = lo_d(c); s.err[d] = hi_d(c);
+            c = ld_chunk(st.cold, n, d * C_PER_DEV + C_RT, i);
+            s.tReset[d] = lo_d(c); s.segT0[d] = hi_d(c);
+            c = ld_chunk(st.cold, n, d * C_PER_DEV + C_U, i);
+            s.sEv[d] = c.x; s.sC[d] = c.y; s.cmdPay[d] = (int)c.z;
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const uint4 c = ld_chunk(st.cold, n, C_PER_DEV * kMaxDev + k, i);
+            s.stopW[k] = lo_d(c); s.sW[k] = c.z;
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            s.tEv[d] = 0; s.tC[d] = 0; s.txStart[d] = 0; s.tStop[d] = 0; s.ber[d] = 0; s.err[d] = 0;
+            s.tReset[d] = 0; s.segT0[d] = 0; s.sEv[d] = 0; s.sC[d] = 0; s.cmdPay[d] = 0;
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { s.stopW[k] = 0; s.sW[k] = 0; }
+    }
+    s.annDest = 0; s.annBytes = 0; s.annSlots = 0; s.rrmPend = 0; s.tRrm = 0; s.sRrm = 0; s.assignDone = 0;
+}
+
+template <int D, int NS, int NJ>
+__device__ __forceinline__ void store_sim(const Sim<D, NS, NJ> &s, const StatePtrs &st, long long i, bool epoch_too)
+{
+    const long long n = st.nsim;
+    st_chunk(st.hot, n, H_P01, i, pack_dd(s.P[0], s.P[1]));
+    st_chunk(st.hot, n, H_P23, i, pack_dd(s.P[2], D > 3 ? s.P[D > 3 ? 3 : 0] : 0.0));
+    st_chunk(st.hot, n, H_TICK, i, pack_dd(s.tTick[0], s.tTick[1]));
+    st_chunk(st.hot, n, H_TICKS, i, pack_qq(s.ticks[0], s.ticks[1]));
+    const bool busy = sim_busy(s);
+    uint4 u0;
+    u0.x = s.seq; u0.w = s.nTx;
+    pack_flags(s, busy, u0.y, u0.z);
+    st_chunk(st.hot, n, H_U0, i, u0);
+    uint4 v;
+    v.x = s.sTick[0]; v.y = s.sTick[1]; v.z = s.nDeliv[0]; v.w = s.nDeliv[1];
+    st_chunk(st.hot, n, H_U1, i, v);
+    v.x = s.txSeq[0]; v.y = s.txSeq[1]; v.z = s.txSeq[2]; v.w = D > 3 ? s.txSeq[D > 3 ? 3 : 0] : 0u;
+    st_chunk(st.hot, n, H_U2, i, v);
+    if (NJ > 0) {
+        v = pack_dd(s.tJam[0], 0.0);
+        v.z = s.sJam[0]; v.w = 0;
+        st_chunk(st.hot, n, H_JAM, i, v);
+    }
+    if (epoch_too) {
+        st_chunk(st.hot, n, H_EPK, i, pack_qq(s.epochK[0], s.epochK[1]));
+        st_chunk(st.hot, n, H_SNAP, i, pack_qq(s.snapEnd[0], s.snapEnd[1]));
+    }
+    if (epoch_too || s.fault || s.ties) {
+        v.x = (unsigned)s.epochC[0]; v.y = (unsigned)s.epochC[1]; v.z = (unsigned)s.fault; v.w = s.ties;
+        st_chunk(st.hot, n, H_EPC, i, v);
+    }
+    if (busy) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            st_chunk(st.cold, n, d * C_PER_DEV + C_EV, i, pack_dd(s.tEv[d], s.tC[d]));
+            st_chunk(st.cold, n, d * C_PER_DEV + C_TX, i, pack_dd(s.txStart[d], s.tStop[d]));
+            st_chunk(st.cold, n, d * C_PER_DEV + C_RX, i, pack_dd(s.ber[d], s.err[d]));
+            st_chunk(st.cold, n, d * C_PER_DEV + C_RT, i, pack_dd(s.tReset[d], s.segT0[d]));
+            uint4 c; c.x = s.sEv[d]; c.y = s.sC[d]; c.z = (unsigned)s.cmdPay[d]; c.w = 0;
+            st_chunk(st.cold, n, d * C_PER_DEV + C_U, i, c);
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            uint4 c = pack_dd(s.stopW[k], 0.0);
+            c.z = s.sW[k]; c.w = 0;
+            st_chunk(st.cold, n, C_PER_DEV * kMaxDev + k, i, c);
+        }
+    }
+}
+
+struct DevRing {
+    int32_t *base;      // ring + sim index
+    long long nsim;
+    __device__ __forceinline__ int operator()(int k, uint32_t slot) const { return base[(long long)(k * kQueueCap + slot) * nsim]; }
+    __device__ __forceinline__ void operator()(int k, uint32_t slot, int v) { base[(long long)(k * kQueueCap + slot) * nsim] = v; }
+};
+
+// ------------------------------------------------------------------------------------
+// mode M: warp-cooperative error counting (bit-error masks)
+// ------------------------------------------------------------------------------------
+
+struct MaskSource {
+    int mode;                   // MODE_M_PHILOX or MODE_M_FED
+    unsigned long long seed;
+    long long env_offset;
+    const uint32_t *words;      // fed masks
+    int slots, words_per_row;
+};
+
+// number of set bits among bits [k0, k1) of a row of 32-bit words; all 32 lanes cooperate,
+// 128-bit loads, result valid in every lane
+__device__ __forceinline__ int warp_popc_range(const uint32_t *row, int k0, int k1, int lane)
+{
+    int n = 0;
+    if (k1 > k0) {
+        const int w0 = k0 >> 5, w1 = (k1 - 1) >> 5;     // first / last word
+        const int q0 = w0 >> 2, q1 = w1 >> 2;           // 16-byte groups
+        const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
+        for (int q = q0 + lane; q <= q1; q += 32) {
+            const uint4 v = __ldg(row4 + q);
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int wi = q * 4 + j;
+                unsigned m = w[j];
+                if (wi < w0 || wi > w1) m = 0;
+                if (wi == w0) m &= 0xFFFFFFFFu << (k0 & 31);
+                if (wi == w1 && ((k1 & 31) != 0)) m &= 0xFFFFFFFFu >> (32 - (k1 & 31));
+                n += __popc(m);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
+    return n;
+}
+
+// Philox-generated masks: bit k is an error iff word (k & 3) of block (k >> 2) < thr
+__device__ __forceinline__ int warp_philox_range(unsigned long long seed, long long env, int band, int sender,
+                                                 uint32_t txseq, int receiver, int k0, int k1, uint32_t thr, int lane)
+{
+    int n = 0;
+    if (k1 > k0) {
+        const int b0 = k0 >> 2, b1 = (k1 - 1) >> 2;
+        for (int blk = b0 + lane; blk <= b1; blk += 32) {
+            uint32_t w[4];
+            mask_words4(seed, env, band, sender, txseq, receiver, (uint32_t)blk, w);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = blk * 4 + j;
+                n += (k >= k0 && k < k1 && w[j] < thr) ? 1 : 0;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
+    return n;
+}
+
+// ------------------------------------------------------------------------------------
+// K4: fused event-ordered step kernel (+ K5 epilogue)
+// ------------------------------------------------------------------------------------
+
+struct StepArgs {
+    StatePtrs st;
+    const int32_t *device;
+    const int32_t *duration;
+    long long *obs;
+    double *reward;
+    unsigned char *done;
+    double *stats;
+    int *errflag;
+    MaskSource masks;
+};
+
+struct SharedTables {
+    double srx[kMaxBands][16];
+};
+
+template <int MODE, int D, int NS, int NJ>
+__global__ void __launch_bounds__(128)
+step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P,
+            const __grid_constant__ SharedTables T)
+{
+    using SimT = Sim<D, NS, NJ>;
+    const int lane = threadIdx.x & 31;
+    const int nb = P.nbands;
+    const long long nsim = A.st.nsim;
+    double acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+
+    // grid-stride over warps' worth of band-sims; every lane of a warp stays in the loop
+    // so that the warp-level operations below are executed by all 32 lanes
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nround = (nsim + stride - 1) / stride;
+    for (long long r = 0; r < nround; ++r) {
+        const long long i = first + r * stride;
+        const bool active = i < nsim;
+        const long long env = active ? i / nb : 0;
+        const int band = active ? (int)(i - env * nb) : 0;
+
+        SimT s;
+        double srx[D * D];
+        const BandParams &B = P.band[band];
+        DevRing ring{A.st.ring + (active ? i : 0), nsim};
+        int dev = 0, dur = 0;
+        if (active) {
+            load_sim(s, A.st, i, A.st.now[env]);
+            if (A.st.ntab == 1) {
+#pragma unroll
+                for (int k = 0; k < D * D; ++k) srx[k] = T.srx[band][(k / D) * kMaxDev + (k % D)];
+            } else {
+#pragma unroll
+                for (int k = 0; k < D * D; ++k) srx[k] = A.st.srx[(long long)((k / D) * kMaxDev + (k % D)) * A.st.ntab + i];
+            }
+            dev = A.device[i];
+            dur = A.duration[i];
+            // assert self.action_space.contains(action)  (counter_traffic.py:147)
+            if (dev < 0 || dev >= NS || dur < 0 || dur >= P.maxDuration) {
+                if (atomicCAS(A.errflag, 0, GW_E_ACTION) == 0) A.errflag[1] = (int)i;
+                dev = dev < 0 ? 0 : (dev >= NS ? NS - 1 : dev);
+                dur = dur < 0 ? 0 : (dur >= P.maxDuration ? P.maxDuration - 1 : dur);
+            }
+            begin_assignment(s, P, dev, dur);
+        } else {
+            s.assignDone = 1; s.fault = 0; s.now = 0;
+        }
+        const uint32_t nTx0 = active ? s.nTx : 0, nD0 = active ? s.nDeliv[0] : 0, nD1 = active ? s.nDeliv[1] : 0;
+        const uint32_t ties0 = active ? s.ties : 0;
+
+        if (MODE == MODE_R) {
+            if (active) run_until_assign<MODE_R>(s, P, B, srx, ring, NoMasks());
+            if (nb > 1) {
+                // SimMan.runSimulation for every band's ASSIGN message: the env's clock ends
+                // at the latest band; the other bands keep simulating up to that time
+                double Tend = active ? s.now : -INFINITY;
+                for (int o = 1; o < nb; o <<= 1) Tend = fmax(Tend, __shfl_xor_sync(0xFFFFFFFFu, Tend, o));
+                if (active && s.now < Tend) run_until_time<MODE_R>(s, P, B, srx, ring, NoMasks(), Tend);
+            }
+        } else {
+            // warp-synchronous event loop: one timed event per lane and iteration; the error
+            // counts of all lanes are serviced cooperatively (ballot / popc / shuffle)
+            double Tend = INFINITY;
+            int phase = 0;      // 0: until the own ASSIGN is processed, 1: until Tend
+            for (;;) {
+                Event ev; ev.kind = EV_NONE; ev.idx = 0; ev.t = 0;
+                bool run = active && !s.fault;
+                if (run) {
+                    if (phase == 0) run = !s.assignDone;
+                    if (run || phase == 1) {
+                        ev = select_event(s);
+                        run = phase == 0 ? true : (ev.t < Tend);
+                    }
+                }
+                const unsigned running = __ballot_sync(0xFFFFFFFFu, run);
+                if (running == 0) {
+                    if (phase == 0 && nb > 1) {
+                        double t = active ? s.now : -INFINITY;
+                        for (int o = 1; o < nb; o <<= 1) t = fmax(t, __shfl_xor_sync(0xFFFFFFFFu, t, o));
+                        Tend = t;
+                        phase = 1;
+                        continue;
+                    }
+                    break;
+                }
+                int once = 0, twice = 0;
+                if (run) {
+                    s.now = ev.t;
+                    count_set(s, ev, srx, once, twice);
+                }
+                // service the count requests: for every lane with requests, all lanes scan
+                unsigned pending = __ballot_sync(0xFFFFFFFFu, once != 0);
+                while (pending) {
+                    const int src = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    int req = __shfl_sync(0xFFFFFFFFu, once, src);
+                    while (req) {
+                        const int p = __ffs(req) - 1;
+                        req &= req - 1;
+                        int sender = 0; uint32_t txseq = 0; int64_t k0 = 0, k1 = 0; double berp = 0;
+                        if (lane == src) {
+                            mask_range(s, p, P.bitRate, sender, txseq, k0, k1);
+#pragma unroll
+                            for (int q = 0; q < D; ++q) if (q == p) berp = s.ber[q];
+                        }
+                        sender = __shfl_sync(0xFFFFFFFFu, sender, src);
+                        txseq = __shfl_sync(0xFFFFFFFFu, txseq, src);
+                        const int ik0 = __shfl_sync(0xFFFFFFFFu, (int)k0, src);
+                        const int ik1 = __shfl_sync(0xFFFFFFFFu, (int)k1, src);
+                        const long long simi = __shfl_sync(0xFFFFFFFFu, i, src);
+                        const long long senv = simi / nb;
+                        const int sband = (int)(simi - senv * nb);
+                        int cnt;
+                        if (MODE == MODE_M_FED) {
+                            const long long row = ((((senv * nb + sband) * kMaxDev + sender) * A.masks.slots
+                                                    + (long long)(txseq % (uint32_t)A.masks.slots)) * kMaxDev + p);
+                            cnt = warp_popc_range(A.masks.words + row * A.masks.words_per_row, ik0, ik1, lane);
+                        } else {
+                            const uint32_t thr = ber_threshold(__shfl_sync(0xFFFFFFFFu, berp, src));
+                            cnt = warp_philox_range(A.masks.seed, A.masks.env_offset + senv, sband, sender, txseq, p,
+                                                    ik0, ik1, thr, lane);
+                        }
+                        if (lane == src) {
+#pragma unroll
+                            for (int q = 0; q < D; ++q) if (q == p) { s.err[q] += (double)cnt; s.segT0[q] = s.now; }
+                        }
+                    }
+                }
+                if (run) {
+                    const int berMask = apply_event(s, P, B, ev, srx, ring);
+                    update_bers(s, P, berMask, srx);
+                }
+            }
+            if (active && nb > 1) s.now = Tend;
+        }
+
+        if (active) {
+            long long o; double rw; unsigned char dn;
+            feedback(s, o, rw, dn);
+            A.obs[i] = o;
+            A.reward[i] = rw;
+            A.done[i] = dn;
+            if (band == 0) A.st.now[env] = s.now;
+            if (s.fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = s.fault; } }
+            store_sim(s, A.st, i, false);
+            acc[0] += rw;
+            acc[1] += (double)(s.nDeliv[0] - nD0);
+            acc[2] += (double)(s.nDeliv[1] - nD1);
+            acc[3] += (double)dn;
+            acc[4] += 1.0;
+            acc[5] += (double)(s.latestDiff < 0 ? -s.latestDiff : s.latestDiff);
+            acc[6] += (double)(s.nTx - nTx0);
+            acc[7] += (double)(s.ties - ties0);
+        }
+    }
+
+    // K5: warp shuffle -> shared memory -> one atomic per block and statistic.  The values
+    // are small integers held in fp64, so the sums are exact and order-independent.
+    __shared__ double red[4][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (lane == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double v = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+        if (v != 0.0) atomicAdd(A.stats + threadIdx.x, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// init / reset / tables / read-back kernels
+// ------------------------------------------------------------------------------------
+
+template <int D, int NS, int NJ>
+__global__ void init_kernel(StatePtrs st, SharedTables thermal /* srx[b][0] = thermal noise */)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.nsim) return;
+    const int band = (int)(i % st.nb);
+    Sim<D, NS, NJ> s;
+    init_sim(s, thermal.srx[band][0]);
+    if (band == 0) st.now[i / st.nb] = 0.0;
+    // write every chunk once so that the cold part is defined
+    const long long n = st.nsim;
+    for (int c = 0; c < COLD_CHUNKS; ++c) st_chunk(st.cold, n, c, i, make_uint4(0, 0, 0, 0));
+    for (int c = 0; c < HOT_CHUNKS; ++c) st_chunk(st.hot, n, c, i, make_uint4(0, 0, 0, 0));
+    store_sim(s, st, i, true);
+}
+
+template <int D, int NS, int NJ>
+__global__ void reset_kernel(StatePtrs st, Params P, const long long *env_ids, long long n_ids, long long *obs)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (env_ids ? n_ids : st.nenv) * st.nb;
+    if (t >= total) return;
+    const long long e = env_ids ? env_ids[t / st.nb] : t / st.nb;
+    const int band = (int)(t % st.nb);
+    if (e < 0 || e >= st.nenv) return;
+    const long long i = e * st.nb + band;
+    Sim<D, NS, NJ> s;
+    load_sim(s, st, i, st.now[e]);
+    DevRing ring{st.ring + i, st.nsim};
+    reset_sim(s, P.band[band], ring);
+    store_sim(s, st, i, true);
+    if (obs) obs[i] = (long long)s.latestDiff + kCounterBound;       // counter_traffic.py:144
+}
+
+// K1: attenuation and received-power tables, one thread per (table, receiver, sender)
+__global__ void tables_kernel(StatePtrs st, const double *pos /* [ntab][MAXD][2] or NULL */,
+                              SharedTables defpos_x, SharedTables defpos_y, SharedTables power, SharedTables freq)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= st.ntab * 16) return;
+    const long long tab = t / 16;
+    const int k = (int)(t % 16), p = k / kMaxDev, d = k % kMaxDev;
+    const int band = (int)((st.ntab == 1 ? 0 : tab) % st.nb);
+    double px, py, dx, dy;
+    if (pos) {
+        px = pos[(tab * kMaxDev + p) * 2]; py = pos[(tab * kMaxDev + p) * 2 + 1];
+        dx = pos[(tab * kMaxDev + d) * 2]; dy = pos[(tab * kMaxDev + d) * 2 + 1];
+    } else {
+        px = defpos_x.srx[band][p]; py = defpos_y.srx[band][p];
+        dx = defpos_x.srx[band][d]; dy = defpos_y.srx[band][d];
+    }
+    double att = 0.0, rp = 0.0;
+    if (p != d) {
+        att = fspl_db(px, py, dx, dy, freq.srx[band][0]);
+        rp = rx_power_mw(power.srx[band][d], att);
+    }
+    st.att[(long long)k * st.ntab + tab] = att;
+    st.srx[(long long)k * st.ntab + tab] = rp;
+}
+
+template <int D, int NS, int NJ>
+__global__ void read_kernel(StatePtrs st, Params P, int field, double *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.nsim) return;
+    const long long n = st.nsim;
+    Sim<D, NS, NJ> s;
+    const long long e = i / st.nb;
+    const int band = (int)(i % st.nb);
+    load_sim(s, st, i, st.now[e]);
+    switch (field) {
+    case GW_FIELD_NOW: if (band == 0) out[e] = s.now; break;
+    case GW_FIELD_RECEIVED_POWER: for (int d = 0; d < kMaxDev; ++d) out[d * n + i] = d < D ? s.P[d < D ? d : 0] : 0.0; break;
+    case GW_FIELD_NEXT_TICK: for (int k = 0; k < NS; ++k) out[k * n + i] = s.tTick[k]; break;
+    case GW_FIELD_COUNTER:
+        for (int k = 0; k < NS; ++k) {
+            const unsigned long long c = (unsigned long long)s.epochC[k] + (s.ticks[k] - s.epochK[k]);
+            out[k * n + i] = (double)(c > (unsigned long long)kCounterBound ? (unsigned long long)kCounterBound : c);
+        }
+        break;
+    case GW_FIELD_QUEUE_LEN: for (int k = 0; k < NS; ++k) out[k * n + i] = s.qn[k]; break;
+    case GW_FIELD_N_TRANSMISSIONS: out[i] = s.nTx; break;
+    case GW_FIELD_N_DELIVERED: for (int k = 0; k < NS; ++k) out[k * n + i] = s.nDeliv[k]; break;
+    case GW_FIELD_RECEIVED_VALUES: out[i] = s.rv0; out[n + i] = s.rv1; break;
+    case GW_FIELD_ATTENUATION_DB:
+        for (int k = 0; k < 16; ++k) out[k * n + i] = st.att[(long long)k * st.ntab + (st.ntab == 1 ? 0 : i)];
+        break;
+    case GW_FIELD_RX_POWER_MW:
+        for (int k = 0; k < 16; ++k) out[k * n + i] = st.srx[(long long)k * st.ntab + (st.ntab == 1 ? 0 : i)];
+        break;
+    case GW_FIELD_FAULT: out[i] = s.fault; break;
+    case GW_FIELD_TIES: out[i] = s.ties; break;
+    case GW_FIELD_TX_SEQ: for (int d = 0; d < kMaxDev; ++d) out[d * n + i] = d < D ? s.txSeq[d < D ? d : 0] : 0.0; break;
+    default: break;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// standalone kernels
+// ------------------------------------------------------------------------------------
+
+__global__ void fspl_kernel(const double *ax, const double *ay, const double *bx, const double *by,
+                            double f, double *att, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) att[i] = fspl_db(ax[i], ay[i], bx[i], by[i], f);
+}
+
+__global__ void ber_kernel(const double *S, const double *N, double *ber, long long n, double c, double qDen)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ber[i] = ber_bpsk_mw(S[i], N[i], c, qDen);
+}
+
+// K3: one warp per descriptor, grid-stride; 128-bit loads, popc, shuffle reduction
+__global__ void __launch_bounds__(256)
+count_bits_kernel(const uint32_t *words, int words_per_row, const long long *rows, const int *k0, const int *k1,
+                  int *counts, long long n)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long i = warp; i < n; i += nwarps) {
+        const int c = warp_popc_range(words + rows[i] * words_per_row, k0[i], k1[i], lane);
+        if (lane == 0) counts[i] = c;
+    }
+}
+
+__global__ void philox_kernel(const uint32_t *ctr, const uint32_t *key, uint32_t *out, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t o[4];
+    philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1], o);
+    out[4 * i] = o[0]; out[4 * i + 1] = o[1]; out[4 * i + 2] = o[2]; out[4 * i + 3] = o[3];
+}
+
+__global__ void stats_copy_kernel(double *stats, double *out, int clear)
+{
+    const int k = threadIdx.x;
+    if (k < 8) { out[k] = stats[k]; if (clear) stats[k] = 0.0; }
+}
+
+// ------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------
+
+static int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
+
+double gw_max_correctable_ber(int k, int n)        // Mcs.maxCorrectableBer, physical.py:160-185
+{
+    const double bound = std::pow(2.0, (double)(n - k));
+    double sum = 0;
+    int t = 0;
+    while (sum <= bound) {
+        double c = 1;
+        for (int i = 1; i <= t; i++) c = c * (double)(n - t + i) / (double)i;   // binom(n, t)
+        sum += c;
+        t += 1;
+    }
+    t -= 1;
+    return (double)t / n;
+}
+
+static int validate(const gw_config *cfg, int &D, int &NS, int &NJ)
+{
+    if (!cfg) return fail(GW_E_INVALID, "cfg is NULL");
+    if (cfg->abi_version != GW_ABI_VERSION) return fail(GW_E_INVALID, "abi_version %d != %d", cfg->abi_version, GW_ABI_VERSION);
+    if (cfg->n_envs < 1) return fail(GW_E_INVALID, "n_envs must be >= 1");
+    if (cfg->n_bands != 1 && cfg->n_bands != 2 && cfg->n_bands != 4) return fail(GW_E_INVALID, "n_bands must be 1, 2 or 4");
+    if (cfg->mode < GW_MODE_REFERENCE || cfg->mode > GW_MODE_MASK_FED) return fail(GW_E_INVALID, "unknown mode %d", cfg->mode);
+    if (cfg->assignment_duration_factor < 1 || cfg->max_assign_duration < 1) return fail(GW_E_INVALID, "bad duration constants");
+    NS = -1; NJ = -1;
+    for (int b = 0; b < cfg->n_bands; ++b) {
+        const gw_band_config &B = cfg->band[b];
+        if (B.n_devices < 3 || B.n_devices > GW_MAX_DEVICES) return fail(GW_E_INVALID, "band %d: n_devices %d unsupported", b, B.n_devices);
+        int ns = 0, nj = 0, stage = 0;
+        for (int d = 0; d < B.n_devices; ++d) {
+            const int r = B.device[d].role;
+            if (r == GW_ROLE_SENDER) { if (stage != 0) return fail(GW_E_INVALID, "device order must be senders, rrm, jammers"); ns++; }
+            else if (r == GW_ROLE_RRM) { if (stage != 0) return fail(GW_E_INVALID, "exactly one RRM per band"); stage = 1; }
+            else if (r == GW_ROLE_JAMMER) { if (stage != 1) return fail(GW_E_INVALID, "device order must be senders, rrm, jammers"); nj++; }
+            else return fail(GW_E_INVALID, "band %d device %d: unknown role %d", b, d, r);
+        }
+        if (stage != 1) return fail(GW_E_INVALID, "band %d has no RRM", b);
+        if (ns != 2 || nj > GW_MAX_JAMMERS) return fail(GW_E_INVALID, "supported bands: 2 senders, 1 RRM, 0-1 jammers");
+        if (NS >= 0 && (ns != NS || nj != NJ)) return fail(GW_E_INVALID, "all bands must have the same device roles");
+        NS = ns; NJ = nj;
+        for (int k = 0; k < ns; ++k) {
+            if (B.device[k].multiplicity < 1 || B.device[k].multiplicity > 16) return fail(GW_E_INVALID, "multiplicity out of range");
+            if (!(B.device[k].interval > 0)) return fail(GW_E_INVALID, "interval must be > 0");
+            if (B.device[k].payload_bytes > 60000) return fail(GW_E_INVALID, "payload_bytes too large");
+        }
+        for (int d = ns + 1; d < B.n_devices; ++d) {
+            if (!(B.device[d].jam_interval > 0) || B.device[d].jam_delay < 0) return fail(GW_E_INVALID, "bad jammer timing");
+            if (B.device[d].jam_header_bytes < 1 || B.device[d].jam_payload_bytes < 1) return fail(GW_E_INVALID, "bad jammer packet");
+        }
+    }
+    D = NS + 1 + NJ;
+    return GW_OK;
+}
+
+static void fill_params(const gw_config &cfg, Params &P)
+{
+    std::memset(&P, 0, sizeof P);
+    P.nbands = cfg.n_bands;
+    P.factor = cfg.assignment_duration_factor;
+    P.maxDuration = cfg.max_assign_duration;
+    P.mode = cfg.mode;
+    P.bitRate = 133.33333e3;                        // physical.py:196
+    P.dataRate = 0.75 * P.bitRate;                  // physical.py:197
+    P.maxBer = gw_max_correctable_ber(3, 4);
+    P.tenLog10BitRate = 10 * std::log10(P.bitRate);
+    P.qDen = 1.135 * std::sqrt(2 * 3.141592653589793);
+    P.bitsFactor = 2 - 0.75;
+    for (int b = 0; b < cfg.n_bands; ++b) {
+        const gw_band_config &cb = cfg.band[b];
+        BandParams &B = P.band[b];
+        B.ndev = cb.n_devices; B.ns = 0; B.nj = 0;
+        for (int d = 0; d < cb.n_devices; ++d) {
+            const gw_device_config &dc = cb.device[d];
+            if (dc.role == GW_ROLE_SENDER) {
+                B.mult[B.ns] = dc.multiplicity; B.payloadRule[B.ns] = dc.payload_bytes < 0 ? -1 : dc.payload_bytes;
+                B.interval[B.ns] = dc.interval; B.ns++;
+            } else if (dc.role == GW_ROLE_JAMMER) {
+                B.jamInterval[B.nj] = dc.jam_interval; B.jamDelay[B.nj] = dc.jam_delay;
+                B.jamHdr[B.nj] = dc.jam_header_bytes; B.jamPay[B.nj] = dc.jam_payload_bytes; B.nj++;
+            }
+        }
+    }
+}
+
+#define DISPATCH_SHAPE(h, CALL)                                         \
+    do {                                                                \
+        if ((h)->NJ == 0) { CALL(3, 2, 0); } else { CALL(4, 2, 1); }    \
+    } while (0)
+
+extern "C" {
+
+int gw_abi_version(void) { return GW_ABI_VERSION; }
+const char *gw_last_error(void) { return g_err; }
+
+int gw_device_count(int *count)
+{
+    if (!count) return fail(GW_E_INVALID, "count is NULL");
+    *count = 0;
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return GW_OK;
+}
+
+int gw_default_config(gw_config *cfg, int64_t n_envs)
+{
+    if (!cfg) return fail(GW_E_INVALID, "cfg is NULL");
+    std::memset(cfg, 0, sizeof *cfg);
+    cfg->abi_version = GW_ABI_VERSION;
+    cfg->n_envs = n_envs;
+    cfg->n_bands = 1;
+    cfg->assignment_duration_factor = 1000;         // envs/core.py:27
+    cfg->max_assign_duration = 20;                  // envs/core.py:25
+    cfg->mode = GW_MODE_REFERENCE;
+    gw_band_config &b = cfg->band[0];
+    b.n_devices = 3;
+    b.frequency_hz = 2.4e9; b.bandwidth_hz = 22e6;  // physical.py:298
+    b.device[0].role = GW_ROLE_SENDER; b.device[0].x = 0; b.device[0].y = 2;
+    b.device[0].multiplicity = 1; b.device[0].payload_bytes = -1; b.device[0].interval = 0.001;
+    b.device[1].role = GW_ROLE_SENDER; b.device[1].x = 0; b.device[1].y = -2;
+    b.device[1].multiplicity = 3; b.device[1].payload_bytes = -1; b.device[1].interval = 0.001;
+    b.device[2].role = GW_ROLE_RRM; b.device[2].x = 0; b.device[2].y = 0;
+    return GW_OK;
+}
+
+int gw_state_bytes(const gw_config *cfg, size_t *bytes)
+{
+    int D, NS, NJ;
+    const int rc = validate(cfg, D, NS, NJ);
+    if (rc) return rc;
+    if (!bytes) return fail(GW_E_INVALID, "bytes is NULL");
+    const long long ntab = cfg->per_env_positions ? cfg->n_envs * cfg->n_bands : 1;
+    *bytes = make_layout(cfg->n_envs, cfg->n_bands, ntab).total;
+    return GW_OK;
+}
+
+static int launch_tables(gw_handle *h, const double *pos, cudaStream_t s)
+{
+    SharedTables px, py, pw, fr;
+    std::memset(&px, 0, sizeof px); std::memset(&py, 0, sizeof py);
+    std::memset(&pw, 0, sizeof pw); std::memset(&fr, 0, sizeof fr);
+    for (int b = 0; b < h->cfg.n_bands; ++b) {
+        for (int d = 0; d < kMaxDev; ++d) {
+            px.srx[b][d] = h->default_pos[b][d][0];
+            py.srx[b][d] = h->default_pos[b][d][1];
+            pw.srx[b][d] = h->power_dbm[b][d];
+        }
+        fr.srx[b][0] = h->frequency[b];
+    }
+    const long long n = h->st.ntab * 16;
+    tables_kernel<<<grid_for(n, 128), 128, 0, s>>>(h->st, pos, px, py, pw, fr);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes, void *stream, gw_handle **out)
+{
+    int D, NS, NJ;
+    int rc = validate(cfg, D, NS, NJ);
+    if (rc) return rc;
+    if (!out) return fail(GW_E_INVALID, "out is NULL");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return fail(GW_E_CUDA, "no CUDA device: gymwipe_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(GW_E_INVALID, "device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    gw_handle *h = new (std::nothrow) gw_handle();
+    if (!h) return fail(GW_E_INVALID, "out of host memory");
+    std::memset(h, 0, sizeof *h);
+    h->cfg = *cfg;
+    h->device = device;
+    h->D = D; h->NS = NS; h->NJ = NJ;
+    fill_params(*cfg, h->P);
+    const long long ntab = cfg->per_env_positions ? cfg->n_envs * cfg->n_bands : 1;
+    h->layout = make_layout(cfg->n_envs, cfg->n_bands, ntab);
+    if (state) {
+        if (state_bytes < h->layout.total) { delete h; return fail(GW_E_STATE, "state buffer has %zu bytes, %zu needed", state_bytes, h->layout.total); }
+        if (((uintptr_t)state & 255) != 0) { delete h; return fail(GW_E_STATE, "state buffer must be 256-byte aligned"); }
+    } else {
+        cudaError_t e = cudaMalloc(&h->owned_state, h->layout.total);
+        if (e != cudaSuccess) { delete h; return fail(GW_E_CUDA, "cudaMalloc(%zu) failed: %s", h->layout.total, cudaGetErrorString(e)); }
+        state = h->owned_state;
+    }
+    char *base = (char *)state;
+    h->st.nenv = cfg->n_envs; h->st.nb = cfg->n_bands; h->st.nsim = cfg->n_envs * cfg->n_bands; h->st.ntab = ntab;
+    h->st.now = (double *)(base + h->layout.off_now);
+    h->st.hot = (uint4 *)(base + h->layout.off_hot);
+    h->st.cold = (uint4 *)(base + h->layout.off_cold);
+    h->st.ring = (int32_t *)(base + h->layout.off_ring);
+    h->st.att = (double *)(base + h->layout.off_att);
+    h->st.srx = (double *)(base + h->layout.off_srx);
+    for (int b = 0; b < cfg->n_bands; ++b) {
+        const gw_band_config &cb = cfg->band[b];
+        h->frequency[b] = cb.frequency_hz;
+        h->thermal[b] = 1.38e-23 * (20.0 + 273.15) * cb.bandwidth_hz * 1000;     // physical.py:71, simple_stack.py:57,77
+        for (int d = 0; d < cb.n_devices; ++d) {
+            h->default_pos[b][d][0] = cb.device[d].x;
+            h->default_pos[b][d][1] = cb.device[d].y;
+            h->power_dbm[b][d] = cb.device[d].role == GW_ROLE_JAMMER ? cb.device[d].jam_power_dbm : 0.0;  // simple_stack.py:364,521
+        }
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long nsim = h->st.nsim;
+    const size_t aux = 8 * sizeof(double) + 4 * sizeof(int);
+    void *stg = nullptr;
+    cudaError_t e = cudaMalloc((void **)&h->stats, aux);
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->stats, 0, aux, s);
+    if (e == cudaSuccess) e = cudaMalloc(&stg, nsim * (4 + 4 + 8 + 8 + 1) + 64);
+    if (e != cudaSuccess) { gw_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
+    h->errflag = (int *)(h->stats + 8);
+    h->d_obs = (long long *)stg;                            // base of the staging allocation
+    h->d_rew = (double *)(h->d_obs + nsim);
+    int32_t *p32 = (int32_t *)(h->d_rew + nsim);
+    h->d_dev = p32; h->d_dur = p32 + nsim;
+    h->d_done = (unsigned char *)(p32 + 2 * nsim);
+    SharedTables th;
+    std::memset(&th, 0, sizeof th);
+    for (int b = 0; b < cfg->n_bands; ++b) th.srx[b][0] = h->thermal[b];
+#define CALL_INIT(DD, SS, JJ) init_kernel<DD, SS, JJ><<<grid_for(nsim, 128), 128, 0, s>>>(h->st, th)
+    DISPATCH_SHAPE(h, CALL_INIT);
+#undef CALL_INIT
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { gw_destroy(h); return fail(GW_E_CUDA, "init kernel: %s", cudaGetErrorString(e)); }
+    rc = launch_tables(h, nullptr, s);
+    if (rc) { gw_destroy(h); return rc; }
+    *out = h;
+    return GW_OK;
+}
+
+void gw_destroy(gw_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->owned_state) cudaFree(h->owned_state);
+    if (h->stats) cudaFree(h->stats);
+    if (h->d_obs) cudaFree(h->d_obs);       // base of the staging allocation
+    delete h;
+}
+
+int gw_set_positions(gw_handle *h, const double *positions, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    if (positions && h->st.ntab == 1) return fail(GW_E_INVALID, "handle was created with per_env_positions = 0");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return launch_tables(h, positions, (cudaStream_t)stream);
+}
+
+int gw_reset(gw_handle *h, const int64_t *env_ids, int64_t n, int64_t *obs, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long total = (env_ids ? n : h->st.nenv) * h->st.nb;
+    if (total <= 0) return GW_OK;
+#define CALL_RESET(DD, SS, JJ) reset_kernel<DD, SS, JJ><<<grid_for(total, 128), 128, 0, s>>>(h->st, h->P, (const long long *)env_ids, (long long)n, (long long *)obs)
+    DISPATCH_SHAPE(h, CALL_RESET);
+#undef CALL_RESET
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+static int launch_step(gw_handle *h, const int32_t *device, const int32_t *duration, int64_t *obs, double *reward,
+                       uint8_t *done, cudaStream_t s)
+{
+    if (h->cfg.mode == GW_MODE_MASK_FED && !h->masks) return fail(GW_E_INVALID, "mode MASK_FED: call gw_set_masks first");
+    StepArgs A;
+    A.st = h->st;
+    A.device = device; A.duration = duration;
+    A.obs = (long long *)obs; A.reward = reward; A.done = done;
+    A.stats = h->stats; A.errflag = h->errflag;
+    A.masks.mode = h->cfg.mode; A.masks.seed = h->cfg.seed; A.masks.env_offset = h->cfg.env_id_offset;
+    A.masks.words = h->masks; A.masks.slots = h->mask_slots > 0 ? h->mask_slots : 1; A.masks.words_per_row = h->mask_words;
+    SharedTables T;
+    std::memset(&T, 0, sizeof T);
+    if (h->st.ntab == 1) {
+        for (int b = 0; b < h->cfg.n_bands; ++b)
+            for (int p = 0; p < kMaxDev; ++p)
+                for (int d = 0; d < kMaxDev; ++d) {
+                    if (p == d || p >= h->cfg.band[b].n_devices || d >= h->cfg.band[b].n_devices) continue;
+                    // host evaluation of the same formulas; the device table (tables_kernel) is
+                    // what per-env positions use
+                    const double att = fspl_db(h->default_pos[b][p][0], h->default_pos[b][p][1],
+                                               h->default_pos[b][d][0], h->default_pos[b][d][1], h->frequency[b]);
+                    T.srx[b][p * kMaxDev + d] = rx_power_mw(h->power_dbm[b][d], att);
+                }
+    }
+    const long long nsim = h->st.nsim;
+    // one wave: 128-thread blocks, a multiple of the SM count when the batch is large
+    int blocks = grid_for(nsim, 128);
+    const int cap = 148 * 16;
+    if (blocks > cap) blocks = cap;
+#define CALL_STEP(DD, SS, JJ)                                                                        \
+    do {                                                                                             \
+        if (h->cfg.mode == GW_MODE_REFERENCE) step_kernel<MODE_R, DD, SS, JJ><<<blocks, 128, 0, s>>>(A, h->P, T);       \
+        else if (h->cfg.mode == GW_MODE_MASK_PHILOX) step_kernel<MODE_M_PHILOX, DD, SS, JJ><<<blocks, 128, 0, s>>>(A, h->P, T); \
+        else step_kernel<MODE_M_FED, DD, SS, JJ><<<blocks, 128, 0, s>>>(A, h->P, T);                    \
+    } while (0)
+    DISPATCH_SHAPE(h, CALL_STEP);
+#undef CALL_STEP
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_step(gw_handle *h, const int32_t *device, const int32_t *duration, int64_t *obs, double *reward,
+            uint8_t *done, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    if (!device || !duration || !obs || !reward || !done) return fail(GW_E_INVALID, "NULL buffer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return launch_step(h, device, duration, obs, reward, done, (cudaStream_t)stream);
+}
+
+int gw_step_host(gw_handle *h, const int32_t *device, const int32_t *duration, int64_t *obs, double *reward,
+                 uint8_t *done, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    if (!device || !duration || !obs || !reward || !done) return fail(GW_E_INVALID, "NULL buffer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long n = h->st.nsim;
+    CUDA_TRY(cudaMemcpyAsync(h->d_dev, device, n * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->d_dur, duration, n * 4, cudaMemcpyHostToDevice, s));
+    const int rc = launch_step(h, h->d_dev, h->d_dur, (int64_t *)h->d_obs, h->d_rew, h->d_done, s);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(obs, h->d_obs, n * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(reward, h->d_rew, n * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(done, h->d_done, n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GW_OK;
+}
+
+int gw_check(gw_handle *h, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int flag[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(flag, h->errflag, sizeof flag, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (flag[0] == 0) return GW_OK;
+    CUDA_TRY(cudaMemsetAsync(h->errflag, 0, sizeof flag, s));
+    if (flag[0] == GW_E_ACTION)
+        return fail(GW_E_ACTION, "action outside the action space (first at sim %d); the reference asserts "
+                                 "action_space.contains(action)", flag[1]);
+    return fail(GW_E_SIMFAULT, "sim %d hit a condition under which the reference raises (%s)", flag[1],
+                flag[2] == FAULT_REF_KEYERROR ? "KeyError in SimplePhy._updateBitErrorRate, SURVEY app. B #12"
+                : flag[2] == FAULT_REF_ASSERT ? "assert noisePower >= 0"
+                : flag[2] == FAULT_SENDQ ? "SEND queue overflow" : "internal");
+}
+
+int gw_stats(gw_handle *h, double *out8, int clear, void *stream)
+{
+    if (!h || !out8) return fail(GW_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    stats_copy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->stats, out8, clear);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_read_state(gw_handle *h, int field, double *out, void *stream)
+{
+    if (!h || !out) return fail(GW_E_INVALID, "NULL argument");
+    if (field < GW_FIELD_NOW || field > GW_FIELD_TX_SEQ) return fail(GW_E_INVALID, "unknown field %d", field);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long nsim = h->st.nsim;
+#define CALL_READ(DD, SS, JJ) read_kernel<DD, SS, JJ><<<grid_for(nsim, 128), 128, 0, s>>>(h->st, h->P, field, out)
+    DISPATCH_SHAPE(h, CALL_READ);
+#undef CALL_READ
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_set_masks(gw_handle *h, const uint32_t *mask_words, int32_t slots, int32_t words_per_row, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    if (!mask_words || slots < 1 || words_per_row < 4 || (words_per_row & 3)) return fail(GW_E_INVALID, "bad mask layout (words_per_row must be a multiple of 4)");
+    if (((uintptr_t)mask_words & 15) != 0) return fail(GW_E_INVALID, "mask buffer must be 16-byte aligned");
+    h->masks = mask_words; h->mask_slots = slots; h->mask_words = words_per_row;
+    return GW_OK;
+}
+
+int gw_fspl_attenuation(const double *ax, const double *ay, const double *bx, const double *by, double frequency_hz,
+                        double *att_db, int64_t n, void *stream)
+{
+    if (n <= 0) return GW_OK;
+    fspl_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(ax, ay, bx, by, frequency_hz, att_db, n);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_ber_bpsk(const double *signal_mw, const double *noise_mw, double *ber, int64_t n, void *stream)
+{
+    if (n <= 0) return GW_OK;
+    const double c = 10 * std::log10(133.33333e3), q = 1.135 * std::sqrt(2 * 3.141592653589793);
+    ber_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(signal_mw, noise_mw, ber, n, c, q);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_count_bit_errors(const uint32_t *mask_words, int32_t words_per_row, const int64_t *rows, const int32_t *k0,
+                        const int32_t *k1, int32_t *counts, int64_t n, void *stream)
+{
+    if (n <= 0) return GW_OK;
+    if (words_per_row < 4 || (words_per_row & 3) || ((uintptr_t)mask_words & 15)) return fail(GW_E_INVALID, "bad mask layout");
+    // persistent grid: 148 SMs x 8 blocks of 8 warps
+    long long blocks = (n + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    count_bits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(mask_words, words_per_row, (const long long *)rows, k0, k1, counts, n);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_philox4x32(const uint32_t *counter, const uint32_t *key, uint32_t *out, int64_t n, void *stream)
+{
+    if (n <= 0) return GW_OK;
+    philox_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(counter, key, out, n);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,24 @@
+"""
+Mirror of ``gymwipe/envs/__init__.py:1-14``: the registered env ids and a ``make`` that
+instantiates them (gym itself is not a dependency).
+"""
+from gymwipe_b200.envs.counter_traffic import CounterTrafficEnv
+from gymwipe_b200.envs.core import BaseEnv, Interpreter
+
+registry = {
+    'CounterTraffic-v0': CounterTrafficEnv,
+}
+
+
+def register(id, entry_point):
+    registry[id] = entry_point
+
+
+def make(id, **kwargs):
+    """``gym.make(id)`` for the ids this package registers; keyword arguments reach the env."""
+    if id not in registry:
+        raise KeyError("No registered env with id: {}".format(id))
+    return registry[id](**kwargs)
+
+
+__all__ = ["CounterTrafficEnv", "BaseEnv", "Interpreter", "make", "register", "registry"]

@@ -1,0 +1,360 @@
+"""
+Batched, GPU-resident drop-in for ``gymwipe.envs.counter_traffic.CounterTrafficEnv``
+(``gymwipe/envs/counter_traffic.py:20-162``).
+
+The gym surface is kept: ``reset`` / ``step`` / ``seed`` / ``render`` / ``action_space`` /
+``observation_space``, the class constants, ``senders`` / ``rrm`` / ``frequencyBand`` /
+``deviceIndexToMacDict``.  One object holds ``num_envs`` independent envs whose state lives
+in one PyTorch CUDA tensor (structure of arrays, see ``gymwipe_b200/csrc/gw_kernels.cu``);
+``step`` launches the fused sm_100a step kernel through the C ABI.  With ``num_envs == 1``
+and Python-int actions it returns Python scalars and passes the reference's own test
+(``tests/envs/test_counter_traffic.py``) verbatim.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from gymwipe_b200 import _native as N
+from gymwipe_b200 import scenario as S
+from gymwipe_b200 import spaces
+from gymwipe_b200.envs.core import BaseEnv, Interpreter
+from gymwipe_b200.networking.attenuation_models import FsplAttenuation
+from gymwipe_b200.networking.devices import PhySenderDevice, SimpleNetworkDevice, SimpleRrmDevice
+from gymwipe_b200.networking.physical import FrequencyBand
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("gymwipe_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("gymwipe_b200 envs live on a CUDA device, got %r" % (device,))
+    return torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+
+
+class LazyInfo(dict):
+    """``info`` of a batched step: values are read back from the device on first access."""
+
+    def __init__(self, env):
+        super().__init__()
+        self._env = env
+
+    def __missing__(self, key):
+        if key == "Latest received values":
+            v = self._env.received_values()
+            self[key] = v
+            return v
+        raise KeyError(key)
+
+    def keys(self):
+        return ["Latest received values"]
+
+    def __contains__(self, key):
+        return key == "Latest received values" or super().__contains__(key)
+
+
+class CounterTrafficEnv(BaseEnv):
+    """
+    Two sender devices that send counter packets to each other and an RRM whose interpreter
+    turns the packets it overhears into observations and rewards
+    (``counter_traffic.py:20-30``); ``num_envs`` of them, stepped together on the GPU.
+
+    Args:
+        num_envs: number of independent envs in this batch (this GPU's shard).
+        device: CUDA device of the batch.
+        mode: ``"reference"`` (mode R: the reference's deterministic expected-value error
+            accounting), ``"mask_philox"`` (mode M: per-bit Philox4x32-10 error masks generated
+            in the kernel) or ``"mask_fed"`` (mode M with masks supplied by :meth:`set_masks`).
+        seed: Philox seed of mode M.
+        env_id_offset: global id of env 0 (sharding across GPUs keeps results invariant).
+        scenario: optional scenario dict (``gymwipe_b200.scenario``) replacing the default devices.
+        positions: optional float64 tensor ``[num_envs, n_bands, 4, 2]`` of per-env positions.
+        strict: validate actions after every step (costs a device sync).  Defaults to True for
+            ``num_envs == 1``; out-of-space actions raise like the reference's ``assert``.
+    """
+
+    COUNTER_INTERVAL = 0.001
+
+    COUNTER_BYTE_LENGTH = 2
+
+    COUNTER_BOUND = 2 ** (8 * COUNTER_BYTE_LENGTH)
+
+    class SenderDevice(SimpleNetworkDevice):
+        """``counter_traffic.py:37-61``: sends ``packetMultiplicity`` packets every ``COUNTER_INTERVAL``."""
+
+        def __init__(self, name, xPos, yPos, frequencyBand, packetMultiplicity, macIndex=0,
+                     payloadRule="counter", interval=0.001):
+            super().__init__(name, xPos, yPos, frequencyBand, macIndex)
+            self.packetMultiplicity = packetMultiplicity
+            self.payloadRule = payloadRule
+            self.interval = interval
+            self.destinationMac = None
+            self._env = None
+            self._index = None
+
+        @property
+        def counter(self):
+            """Current counter value(s), read back from the device."""
+            v = self._env.read_state(N.GW_FIELD_COUNTER)[self._index]
+            return int(v[0]) if self._env._scalar_api else v.to(torch.int64)
+
+    class CounterTrafficInterpreter(Interpreter):
+        """``counter_traffic.py:63-112`` -- evaluated inside the step kernel; this is a view."""
+
+        def __init__(self, env):
+            self._env = env
+
+        def reset(self):
+            self._env.reset()
+
+        def onPacketReceived(self, senderIndex, receiverIndex, payload):
+            raise RuntimeError("packets are delivered inside the CUDA step kernel")
+
+        @property
+        def receivedValues(self):
+            v = self._env.received_values()
+            return [int(x) for x in v[0]] if self._env._scalar_api else v
+
+        def getReward(self):
+            return self._env._last_reward
+
+        def getObservation(self):
+            return self._env._last_obs
+
+        def getDone(self):
+            return self._env._last_done
+
+        def getInfo(self):
+            return {"Latest received values": str(self.receivedValues)}
+
+    def __init__(self, num_envs=1, device="cuda", mode="reference", seed=0, env_id_offset=0,
+                 scenario=None, positions=None, strict=None):
+        self.device = _require_cuda(device)
+        self.num_envs = int(num_envs)
+        self._scalar_api = self.num_envs == 1
+        self.strict = self._scalar_api if strict is None else bool(strict)
+        self.scenario = scenario if scenario is not None else S.default_scenario_dict()
+        self.n_bands = len(self.scenario["bands"])
+        self.ASSIGNMENT_DURATION_FACTOR = int(self.scenario.get("assignment_duration_factor",
+                                                                BaseEnv.ASSIGNMENT_DURATION_FACTOR))
+
+        # descriptor objects with the reference's names (counter_traffic.py:114-133)
+        self.frequencyBands = []
+        self.senders = []
+        self.rrms = []
+        self.jammers = []
+        mac_counter = 0
+        for b, bd in enumerate(self.scenario["bands"]):
+            band = FrequencyBand([FsplAttenuation], bd.get("frequency", 2.4e9), bd.get("bandwidth", 22e6))
+            self.frequencyBands.append(band)
+            band_senders = []
+            for d in bd["devices"]:
+                if d["role"] == "sender":
+                    mac_counter += 1
+                    sd = CounterTrafficEnv.SenderDevice("Sender %d" % mac_counter, d["x"], d["y"], band,
+                                                        d["mult"], mac_counter, d.get("payload", "counter"),
+                                                        d.get("interval", 0.001))
+                    sd._env, sd._index = self, len(band_senders) if b == 0 else None
+                    band_senders.append(sd)
+            idx2mac = {i: s.macAddr for i, s in enumerate(band_senders)}
+            if len(band_senders) == 2:
+                band_senders[0].destinationMac = band_senders[1].macAddr
+                band_senders[1].destinationMac = band_senders[0].macAddr
+            for d in bd["devices"]:
+                if d["role"] == "rrm":
+                    self.rrms.append(SimpleRrmDevice("RRM", d["x"], d["y"], band, idx2mac,
+                                                     CounterTrafficEnv.CounterTrafficInterpreter(self)))
+            for d in bd["devices"]:
+                if d["role"] == "jammer":
+                    self.jammers.append(PhySenderDevice("Jammer", d["x"], d["y"], band, d["interval"], d["delay"],
+                                                        d.get("power", 0.0), d.get("hdr", 13), d["payload"]))
+            if b == 0:
+                self.senders = band_senders
+                self.deviceIndexToMacDict = idx2mac
+        self.rrm = self.rrms[0]
+        super().__init__(self.frequencyBands[0], deviceCount=2)
+        self.frequencyBand = self.frequencyBands[0]
+
+        # the observation is latestDifference + COUNTER_BOUND (counter_traffic.py:118-120)
+        self.observation_space = spaces.Discrete(2 * CounterTrafficEnv.COUNTER_BOUND)
+
+        # native handle; the env-batch state is a torch tensor
+        self._lib = N.lib()
+        self._cfg = S.config_from_dict(self.scenario, self.num_envs, mode=mode, seed=seed,
+                                       env_id_offset=env_id_offset,
+                                       per_env_positions=positions is not None,
+                                       max_assign_duration=self.MAX_ASSIGN_DURATION)
+        nbytes = C.c_size_t()
+        N.check(self._lib.gw_state_bytes(C.byref(self._cfg), C.byref(nbytes)))
+        self.state = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gw_create(C.byref(self._cfg), self.device.index, self.state.data_ptr(),
+                                        nbytes.value, self._stream(), C.byref(self._handle)))
+        self._masks = None
+        self._positions = None
+        if positions is not None:
+            self.set_positions(positions)
+        self._shape = (self.num_envs,) if self.n_bands == 1 else (self.num_envs, self.n_bands)
+        self._last_obs = self.COUNTER_BOUND
+        self._last_reward = 0.0
+        self._last_done = False
+        self._stats_out = torch.zeros(8, dtype=torch.float64, device=self.device)
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            self._lib.gw_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self):
+        """Synchronises and raises if a kernel flagged an out-of-space action or a sim fault."""
+        with torch.cuda.device(self.device):
+            rc = self._lib.gw_check(self._handle, self._stream())
+        if rc == N.GW_E_ACTION:
+            raise ValueError(self._lib.gw_last_error().decode())
+        N.check(rc)
+
+    def read_state(self, field):
+        """Dense float64 read-back of one state field (``GW_FIELD_*``), shaped ``[k, n_sims]``."""
+        nsim = self.num_envs * self.n_bands
+        rows = {N.GW_FIELD_NOW: None, N.GW_FIELD_RECEIVED_POWER: 4, N.GW_FIELD_NEXT_TICK: 2, N.GW_FIELD_COUNTER: 2,
+                N.GW_FIELD_QUEUE_LEN: 2, N.GW_FIELD_N_TRANSMISSIONS: 1, N.GW_FIELD_N_DELIVERED: 2,
+                N.GW_FIELD_RECEIVED_VALUES: 2, N.GW_FIELD_ATTENUATION_DB: 16, N.GW_FIELD_RX_POWER_MW: 16,
+                N.GW_FIELD_FAULT: 1, N.GW_FIELD_TIES: 1, N.GW_FIELD_TX_SEQ: 4}[field]
+        if rows is None:
+            out = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+        else:
+            out = torch.zeros((rows, nsim), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gw_read_state(self._handle, field, out.data_ptr(), self._stream()))
+        return out
+
+    @property
+    def now(self):
+        """Simulated time of every env (``SimMan.now``)."""
+        t = self.read_state(N.GW_FIELD_NOW)
+        return float(t[0]) if self._scalar_api else t
+
+    def received_values(self):
+        """``interpreter.receivedValues`` as an int64 tensor ``[n_sims, 2]``."""
+        return self.read_state(N.GW_FIELD_RECEIVED_VALUES).t().to(torch.int64)
+
+    def delivered(self):
+        """Packets the RRM decoded per sender, int64 ``[n_sims, 2]``."""
+        return self.read_state(N.GW_FIELD_N_DELIVERED).t().to(torch.int64)
+
+    def transmissions(self):
+        return self.read_state(N.GW_FIELD_N_TRANSMISSIONS)[0].to(torch.int64)
+
+    def stats(self, clear=True):
+        """Statistics reduced by the step kernel's epilogue since the last call (float64[8], device)."""
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gw_stats(self._handle, self._stats_out.data_ptr(), 1 if clear else 0, self._stream()))
+        return self._stats_out
+
+    def set_positions(self, positions):
+        """Per-env device positions ``[num_envs, n_bands, 4, 2]`` (float64, CUDA)."""
+        p = torch.as_tensor(positions, dtype=torch.float64, device=self.device).contiguous()
+        assert tuple(p.shape) == (self.num_envs, self.n_bands, N.GW_MAX_DEVICES, 2)
+        self._positions = p
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gw_set_positions(self._handle, p.data_ptr(), self._stream()))
+
+    def set_masks(self, mask_words, slots):
+        """Mode ``mask_fed``: uint32/int32 tensor ``[num_envs, n_bands, 4, slots, 4, words]``."""
+        assert mask_words.is_cuda and mask_words.dtype in (torch.int32, torch.uint32)
+        assert tuple(mask_words.shape[:5]) == (self.num_envs, self.n_bands, 4, slots, 4)
+        self._masks = mask_words.contiguous()
+        N.check(self._lib.gw_set_masks(self._handle, self._masks.data_ptr(), int(slots),
+                                       int(self._masks.shape[5]), self._stream()))
+
+    # ------------------------------------------------------------------ gym API
+    def reset(self, env_ids=None):
+        """
+        ``counter_traffic.py:135-144``: counters := 0 and interpreter reset (simulated time,
+        queues and PHY state are kept, as in the reference).  Returns the observation.
+        """
+        obs = torch.empty(self._shape, dtype=torch.int64, device=self.device)
+        ids_ptr, n = None, 0
+        if env_ids is not None:
+            ids = torch.as_tensor(env_ids, dtype=torch.int64, device=self.device).contiguous()
+            ids_ptr, n = ids.data_ptr(), ids.numel()
+            obs.fill_(self.COUNTER_BOUND)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gw_reset(self._handle, ids_ptr, n, obs.data_ptr(), self._stream()))
+        if self._scalar_api and self.n_bands == 1:
+            self._last_obs = int(obs[0])
+            return self._last_obs
+        return obs
+
+    def _prepare_action(self, action):
+        if torch.is_tensor(action) or isinstance(action, np.ndarray):
+            # flat action of the DQN agent: a // 20, a % 20 (agents/dqn_counter_traffic.py:25-33)
+            a = torch.as_tensor(action, device=self.device)
+            action = {"device": a // self.MAX_ASSIGN_DURATION, "duration": a % self.MAX_ASSIGN_DURATION}
+        if not isinstance(action, dict) or set(action) != {"device", "duration"}:
+            raise ValueError("action must be a dict with the keys 'device' and 'duration'")
+        out = []
+        for key in ("device", "duration"):
+            v = action[key]
+            if not torch.is_tensor(v):
+                v = torch.as_tensor(np.asarray(v), device=self.device)
+            if v.is_floating_point() or v.dtype == torch.bool:
+                raise ValueError("action[%r] must be an integer tensor" % key)
+            v = v.to(device=self.device, dtype=torch.int32).reshape(self._shape).contiguous()
+            out.append(v)
+        return out
+
+    def step(self, action):
+        """
+        ``counter_traffic.py:146-158``: assigns the band (``action["device"]``) for
+        ``action["duration"] * ASSIGNMENT_DURATION_FACTOR`` slots in every env and simulates
+        until the assignment ends.  Returns ``(obs, reward, done, info)``.
+        """
+        scalar = self._scalar_api and self.n_bands == 1 and isinstance(action, dict) and \
+            not torch.is_tensor(action.get("device"))
+        if scalar:
+            assert self.action_space.contains(action)
+        dev, dur = self._prepare_action(action)
+        obs = torch.empty(self._shape, dtype=torch.int64, device=self.device)
+        reward = torch.empty(self._shape, dtype=torch.float64, device=self.device)
+        done = torch.empty(self._shape, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gw_step(self._handle, dev.data_ptr(), dur.data_ptr(), obs.data_ptr(),
+                                      reward.data_ptr(), done.data_ptr(), self._stream()))
+        if self.strict:
+            self.check()
+        if scalar:
+            self._last_obs, self._last_reward = int(obs[0]), float(reward[0])
+            self._last_done = bool(done[0])
+            return self._last_obs, self._last_reward, self._last_done, self.rrm.interpreter.getInfo()
+        self._last_obs, self._last_reward, self._last_done = obs, reward, done.bool()
+        return obs, reward, self._last_done, LazyInfo(self)
+
+    def step_host(self, device, duration, obs, reward, done):
+        """
+        End-to-end step with HOST buffers (numpy arrays or pinned CPU tensors): actions are
+        copied to the GPU, the step kernel runs, results are copied back (``gw_step_host``).
+        ``device``/``duration`` int32, ``obs`` int64, ``reward`` float64, ``done`` uint8.
+        """
+        def ptr(a):
+            return a.data_ptr() if torch.is_tensor(a) else a.ctypes.data
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gw_step_host(self._handle, ptr(device), ptr(duration), ptr(obs), ptr(reward),
+                                           ptr(done), self._stream()))
+
+    def render(self, mode='human', close=False):
+        """``counter_traffic.py:160-162`` (env 0)."""
+        values = [int(x) for x in self.received_values()[0]]
+        print("Last Received: {}, difference: {:6d}".format(values, values[1] - values[0]), end='\r')

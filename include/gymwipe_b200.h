@@ -148,22 +148,23 @@ int gw_check(gw_handle *h, void *stream);
  * (agents/dqn_counter_traffic.py:70) -- and the NCCL all-reduce when envs are sharded. */
 int gw_stats(gw_handle *h, double *out8, int clear, void *stream);
 
-/* Read-back views of the structure-of-arrays state (device pointers into `state`). */
-typedef struct {
-    int64_t n_sims;                 /* n_envs * n_bands */
-    const double *now;              /* [n_envs] simulated time, simtools.py:56-58 */
-    const double *received_power;   /* [GW_MAX_DEVICES][n_sims] SimplePhy._receivedPower (mW) */
-    const double *next_tick;        /* [GW_MAX_SENDERS][n_sims] next traffic tick */
-    const uint64_t *ticks;          /* [GW_MAX_SENDERS][n_sims] ticks fired (counter = f(ticks)) */
-    const uint32_t *queue_len;      /* [GW_MAX_SENDERS][n_sims] SimpleMac._packetQueue length */
-    const uint32_t *n_transmissions;/* [n_sims] */
-    const uint32_t *n_delivered;    /* [GW_MAX_SENDERS][n_sims] packets the RRM decoded per sender */
-    const int32_t *received_values; /* [2][n_sims] interpreter.receivedValues */
-    const double *attenuation_db;   /* [GW_MAX_DEVICES*GW_MAX_DEVICES][n_tables] FSPL table */
-    const double *rx_power_mw;      /* [GW_MAX_DEVICES*GW_MAX_DEVICES][n_tables] 10**((P-att)/10) */
-    int64_t n_tables;               /* 1 (shared positions) or n_sims */
-} gw_state_view;
-int gw_state_ptrs(gw_handle *h, gw_state_view *view);
+/* Read-back of the structure-of-arrays state (tests, tracing, render()): converts one
+ * field to a dense device float64 array (integers are exact below 2^53).  n_sims =
+ * n_envs * n_bands, sim index = env * n_bands + band. */
+#define GW_FIELD_NOW 0              /* [n_envs]                simulated time, simtools.py:56-58 */
+#define GW_FIELD_RECEIVED_POWER 1   /* [GW_MAX_DEVICES][n_sims] SimplePhy._receivedPower (mW) */
+#define GW_FIELD_NEXT_TICK 2        /* [GW_MAX_SENDERS][n_sims] next traffic tick time */
+#define GW_FIELD_COUNTER 3          /* [GW_MAX_SENDERS][n_sims] SenderDevice.counter */
+#define GW_FIELD_QUEUE_LEN 4        /* [GW_MAX_SENDERS][n_sims] len(SimpleMac._packetQueue) */
+#define GW_FIELD_N_TRANSMISSIONS 5  /* [n_sims]                transmissions started on the band */
+#define GW_FIELD_N_DELIVERED 6      /* [GW_MAX_SENDERS][n_sims] packets the RRM decoded, per sender */
+#define GW_FIELD_RECEIVED_VALUES 7  /* [2][n_sims]             interpreter.receivedValues */
+#define GW_FIELD_ATTENUATION_DB 8   /* [GW_MAX_DEVICES^2][n_sims] FSPL table (receiver-major) */
+#define GW_FIELD_RX_POWER_MW 9      /* [GW_MAX_DEVICES^2][n_sims] 10**((P_tx - att)/10) */
+#define GW_FIELD_FAULT 10           /* [n_sims]                0 or the condition under which the reference raises */
+#define GW_FIELD_TIES 11            /* [n_sims]                exact-time ties seen by the event selector */
+#define GW_FIELD_TX_SEQ 12          /* [GW_MAX_DEVICES][n_sims] transmissions started per device */
+int gw_read_state(gw_handle *h, int field, double *out, void *stream);
 
 /* Mode M, fed masks: `mask_words` is a device uint32 buffer laid out
  * [n_envs][n_bands][GW_MAX_DEVICES sender][slots][GW_MAX_DEVICES receiver][words_per_row];

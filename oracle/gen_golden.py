@@ -1,0 +1,136 @@
+#!/usr/bin/env python
+"""
+ORACLE TEST INFRASTRUCTURE -- generates the golden vectors of ``tests/golden`` by running the
+UNMODIFIED reference (``/root/reference``) on the shims through ``oracle/ref_harness.py``.
+
+The reference cannot travel to the GPU box, so its outputs are committed as small JSON
+fixtures together with this script:
+
+    python oracle/gen_golden.py            # rewrites tests/golden/*.json
+
+Every fixture holds the scenario, the action tape and, per step, obs / reward / done / step end
+time / heap events and the trace records (transmissions, BER values, decider inputs and
+verdicts, RRM deliveries).  One case per process (the reference allows one env per process).
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "..", "tests", "golden")
+sys.path.insert(0, HERE)
+
+import ref_harness as H  # noqa: E402
+import check_restatement as CR  # noqa: E402
+
+CASES = {
+    # name: (kind, seed, steps)
+    "kat_reference_test": ("kat", 0, 2),
+    "default_reset_seed0": ("default", 0, 160),
+    "default_noreset_seed1": ("default_noreset", 1, 60),
+    "positions_seed3": ("positions", 3, 60),
+    "jammer_seed5": ("jammer", 5, 60),
+    "longpacket_seed7": ("long", 7, 12),
+    "multiband_seed9": ("multiband", 9, 24),
+}
+
+
+def make_case(kind, seed, steps):
+    rs = np.random.RandomState(seed)
+    do_reset, use_default = True, False
+    if kind == "kat":
+        sc, tape, do_reset, use_default = H.default_scenario(), [{"device": 0, "duration": 3}, {"device": 1, "duration": 12}], False, True
+    elif kind == "default":
+        sc, tape, use_default = H.default_scenario(), H.random_actions(steps, seed=seed), True
+    elif kind == "default_noreset":
+        sc, tape, do_reset, use_default = H.default_scenario(), H.random_actions(steps, seed=seed), False, True
+    elif kind == "positions":
+        sc, tape = CR.random_scenario(rs, jammers=0, spread=2.5), H.random_actions(steps, seed=seed + 1000)
+    elif kind == "jammer":
+        sc, tape = CR.random_scenario(rs, jammers=1, spread=2.5), H.random_actions(steps, seed=seed + 2000)
+    elif kind == "long":
+        sc = CR.random_scenario(rs, jammers=1, fixed_payload=1500, spread=2.0, factor=10000)
+        tape = H.random_actions(steps, seed=seed + 3000)
+    elif kind == "multiband":
+        sc = CR.random_scenario(rs, nbands=4, jammers=1, spread=2.5)
+        tapes = [H.random_actions(steps, seed=seed + 4000 + b) for b in range(4)]
+        tape = [list(x) for x in zip(*tapes)]
+    else:
+        raise SystemExit(kind)
+    return sc, tape, do_reset, use_default
+
+
+def child(name):
+    kind, seed, steps = CASES[name]
+    H.setup_paths()
+    sc, tape, do_reset, use_default = make_case(kind, seed, steps)
+    tr = H.Tracer()
+    env = H.make_default_env(tr) if use_default else H.ScenarioEnv(sc, tr)
+    trace = H.run_tape(env, tape, tr, do_reset=do_reset)
+    doc = {"name": name, "kind": kind, "seed": seed, "do_reset": do_reset,
+           "generator": "oracle/gen_golden.py (unmodified reference on oracle/shims)",
+           "reference_class": "gymwipe.envs.CounterTrafficEnv" if use_default else "oracle.ref_harness.ScenarioEnv",
+           "scenario": sc, "reset_obs": trace["reset_obs"],
+           "steps": [{"action": s["action"], "obs": s["obs"], "reward": s["reward"], "done": s["done"],
+                      "now": s["now"], "events": s["events"],
+                      "records": [list(r) for r in s["records"]]} for s in trace["steps"]]}
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, name + ".json"), "w") as f:
+        json.dump(doc, f, separators=(",", ":"))
+    print("wrote", name, "steps", len(trace["steps"]),
+          "records", sum(len(s["records"]) for s in trace["steps"]))
+
+
+def arithmetic_vectors():
+    """Numeric vectors from the reference's own functions."""
+    H.setup_paths()
+    from gymwipe.networking import physical as P
+    from gymwipe.networking.attenuation_models import FsplAttenuation
+    from gymwipe.devices import Device
+    rs = np.random.RandomState(42)
+    spec = P.FrequencyBandSpec()
+    mcs = P.BpskMcs(spec)
+    doc = {"generator": "oracle/gen_golden.py::arithmetic_vectors", "q": [], "ber_dbm": [], "ber_mw": [],
+           "fspl": [], "maxBer": {}, "thermal_mw": 1.38e-23 * (20.0 + 273.15) * 22e6 * 1000,
+           "noise_power_density": P.temperatureToNoisePowerDensity(20.0)}
+    for x in [0.1, 0.5, 1.0, 2.0, 3.0, 5.0] + list(rs.uniform(0.01, 8, 40)):
+        doc["q"].append([float(x), P.approxQFunction(float(x))])
+    th = doc["thermal_mw"]
+    for _ in range(200):
+        s_mw = float(10 ** rs.uniform(-9, -2))
+        n_mw = float(th + (10 ** rs.uniform(-12, -4) if rs.rand() < 0.5 else 0.0))
+        sd, nd = P.milliwattsToDbm(s_mw), P.milliwattsToDbm(n_mw)
+        doc["ber_mw"].append([s_mw, n_mw, mcs.calculateBitErrorRate(sd, nd)])
+    for sd, nd in [(-46.07482474751174, -100.50608334255742), (-52.095424660791366, -100.50608334255742),
+                   (-30.0, -90.0), (-60.0, -100.50608334255742), (-40.0, -40.0)]:
+        doc["ber_dbm"].append([sd, nd, mcs.calculateBitErrorRate(sd, nd)])
+    for d in [1.0, 2 ** 0.5, 2.0, 4.0, 10.0, 100.0]:
+        m = FsplAttenuation(spec, Device("a", 0, 0), Device("b", d, 0))
+        doc["fspl"].append([0.0, 0.0, float(d), 0.0, 2.4e9, m.attenuation])
+    for _ in range(100):
+        ax, ay, bx, by = [float(v) for v in rs.uniform(-50, 50, 4)]
+        f = float(rs.choice([2.4e9, 2.425e9, 5.0e9]))
+        m = FsplAttenuation(P.FrequencyBandSpec(f), Device("a", ax, ay), Device("b", bx, by))
+        doc["fspl"].append([ax, ay, bx, by, f, m.attenuation])
+    from fractions import Fraction
+    for k, n in [(3, 4), (1, 2), (2, 3), (5, 6), (7, 8)]:
+        P.Mcs._codeRateToMaxCorrectableBer = {}
+        doc["maxBer"]["%d/%d" % (k, n)] = P.BpskMcs(spec, Fraction(k, n)).maxCorrectableBer()
+    with open(os.path.join(OUT, "arithmetic.json"), "w") as f:
+        json.dump(doc, f, separators=(",", ":"))
+    print("wrote arithmetic")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        if sys.argv[1] == "arithmetic":
+            arithmetic_vectors()
+        else:
+            child(sys.argv[1])
+    else:
+        for name in CASES:
+            subprocess.check_call([sys.executable, os.path.abspath(__file__), name])
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "arithmetic"])

@@ -70,7 +70,7 @@ struct EnvT {
     int32_t ring[kMaxBands][NS * kQueueCap];
 };
 
-template <int D, int NS, int NJ>
+template <int MODE, int D, int NS, int NJ>
 int run_t(const HsScenario &sc, int64_t nenv, int nsteps, int do_reset, const double *pos,
           const int32_t *dev_tape, const int32_t *dur_tape, int64_t *obs, double *reward, uint8_t *done,
           double *now, int64_t *counts, double *power_out, int64_t env_offset)
@@ -109,13 +109,13 @@ int run_t(const HsScenario &sc, int64_t nenv, int nsteps, int do_reset, const do
             for (int b = 0; b < nb; ++b) {
                 HostRing r{E.ring[b]};
                 HostMasks mk{sc.seed, env_offset + e, b};
-                run_until_assign(E.sim[b], P, P.band[b], E.srx[b], r, mk);
+                run_until_assign<MODE>(E.sim[b], P, P.band[b], E.srx[b], r, mk);
                 if (E.sim[b].now > T) T = E.sim[b].now;
             }
             for (int b = 0; b < nb; ++b) {
                 HostRing r{E.ring[b]};
                 HostMasks mk{sc.seed, env_offset + e, b};
-                if (E.sim[b].now < T) run_until_time(E.sim[b], P, P.band[b], E.srx[b], r, mk, T);
+                if (E.sim[b].now < T) run_until_time<MODE>(E.sim[b], P, P.band[b], E.srx[b], r, mk, T);
                 long long o; double rw; unsigned char dn;
                 feedback(E.sim[b], o, rw, dn);
                 if (obs) obs[base + b] = o;
@@ -151,10 +151,15 @@ int hs_run(const HsScenario *sc, int64_t nenv, int nsteps, int do_reset, const d
     const int ns = sc->band[0].ns, nj = sc->band[0].nj;
     for (int b = 1; b < sc->nbands; ++b)
         if (sc->band[b].ns != ns || sc->band[b].nj != nj) return -1;
-    if (ns == 2 && nj == 0)
-        return run_t<3, 2, 0>(*sc, nenv, nsteps, do_reset, pos, dev_tape, dur_tape, obs, reward, done, now, counts, power_out, env_offset);
-    if (ns == 2 && nj == 1)
-        return run_t<4, 2, 1>(*sc, nenv, nsteps, do_reset, pos, dev_tape, dur_tape, obs, reward, done, now, counts, power_out, env_offset);
+#define HS_ARGS *sc, nenv, nsteps, do_reset, pos, dev_tape, dur_tape, obs, reward, done, now, counts, power_out, env_offset
+    if (sc->mode == MODE_R) {
+        if (ns == 2 && nj == 0) return run_t<MODE_R, 3, 2, 0>(HS_ARGS);
+        if (ns == 2 && nj == 1) return run_t<MODE_R, 4, 2, 1>(HS_ARGS);
+    } else {
+        if (ns == 2 && nj == 0) return run_t<MODE_M_PHILOX, 3, 2, 0>(HS_ARGS);
+        if (ns == 2 && nj == 1) return run_t<MODE_M_PHILOX, 4, 2, 1>(HS_ARGS);
+    }
+#undef HS_ARGS
     return -1;
 }
 

@@ -1,0 +1,113 @@
+"""
+CPU suite, part 3: the C-ABI library loads and exports every symbol include/gymwipe_b200.h
+declares; host-side logic (scenario validation, error reporting, spaces) works without a GPU;
+the product refuses to run without CUDA (no CPU fallback).
+"""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from gymwipe_b200 import _native as N
+from gymwipe_b200 import scenario as S
+from gymwipe_b200 import spaces
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gymwipe_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gw_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = N.lib()
+    names = declared_symbols()
+    assert len(names) >= 18
+    for name in names:
+        assert hasattr(L, name), name
+    assert sorted(N.EXPORTED_SYMBOLS) == names       # the ctypes table covers the header
+    assert L.gw_abi_version() == N.GW_ABI_VERSION
+
+
+def test_cubin_is_sm_100a():
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", N.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_default_config_and_state_size():
+    L = N.lib()
+    cfg = N.Config()
+    assert L.gw_default_config(C.byref(cfg), 65536) == 0
+    assert cfg.n_bands == 1 and cfg.band[0].n_devices == 3
+    assert cfg.band[0].device[1].multiplicity == 3 and cfg.band[0].device[2].role == N.GW_ROLE_RRM
+    n = C.c_size_t()
+    assert L.gw_state_bytes(C.byref(cfg), C.byref(n)) == 0
+    assert 1000 * 65536 < n.value < 2000 * 65536
+
+
+def test_config_validation_errors():
+    L = N.lib()
+    cfg = S.config_from_dict(S.default_scenario_dict(), 16)
+    n = C.c_size_t()
+    cfg.n_bands = 3
+    assert L.gw_state_bytes(C.byref(cfg), C.byref(n)) == N.GW_E_INVALID
+    assert b"n_bands" in L.gw_last_error()
+    cfg = S.config_from_dict(S.default_scenario_dict(), 16)
+    cfg.band[0].device[0].role = N.GW_ROLE_RRM
+    assert L.gw_state_bytes(C.byref(cfg), C.byref(n)) == N.GW_E_INVALID
+    cfg = S.config_from_dict(S.default_scenario_dict(), 0)
+    assert L.gw_state_bytes(C.byref(cfg), C.byref(n)) == N.GW_E_INVALID
+    cfg = S.config_from_dict(S.default_scenario_dict(), 4)
+    cfg.abi_version = 99
+    assert L.gw_state_bytes(C.byref(cfg), C.byref(n)) == N.GW_E_INVALID
+
+
+def test_max_correctable_ber_host():
+    L = N.lib()
+    assert L.gw_max_correctable_ber(3, 4) == 0.25
+    assert L.gw_max_correctable_ber(1, 2) == 0.5
+    assert L.gw_max_correctable_ber(7, 8) == 0.125
+
+
+def test_spaces_follow_gym_semantics():
+    import numpy as np
+    space = spaces.Dict({"device": spaces.Discrete(2), "duration": spaces.Discrete(20)})
+    assert space.contains({"device": 0, "duration": 19})
+    assert space.contains({"device": np.int64(1), "duration": np.int32(3)})
+    assert not space.contains({"device": 2, "duration": 3})
+    assert not space.contains({"device": 0, "duration": 20})
+    assert not space.contains({"device": 0})
+    assert not space.contains({"device": 0.0, "duration": 1})
+    assert not space.contains([0, 1])
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import gymwipe_b200
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gymwipe_b200.make('CounterTraffic-v0')
+    # the ABI itself also refuses
+    L = N.lib()
+    cfg = S.config_from_dict(S.default_scenario_dict(), 4)
+    h = C.c_void_p()
+    assert L.gw_create(C.byref(cfg), 0, None, 0, None, C.byref(h)) == N.GW_E_CUDA
+
+
+def test_product_does_not_import_oracle():
+    """The package must not reference oracle/ or tests/hostsim (parity claims depend on it)."""
+    pkg = os.path.join(ROOT, "gymwipe_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "gw_oracle" not in text and "hostsim" not in text.replace("tests/hostsim", ""), f

@@ -1,0 +1,112 @@
+"""
+CPU suite, part 2: the kernel's simulation core (gymwipe_b200/csrc/gw_core.cuh) compiled for
+the HOST (tests/hostsim) against the oracle and the golden vectors.  This checks the event
+logic of the CUDA step kernel -- the reduction of the reference's SimPy heap to timed slots --
+without a GPU; the `-m gpu` suite repeats the comparison through the C ABI on the device.
+"""
+import numpy as np
+import pytest
+
+import gw_oracle as O
+import hostsim as HS
+from util import (GOLDEN_CASES, golden_results, load_golden, random_scenario, random_tapes,
+                  tapes_from_golden)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_core_matches_golden(name):
+    doc = load_golden(name)
+    dev, dur = tapes_from_golden(doc)
+    h = HS.run(doc["scenario"], dev, dur, do_reset=doc["do_reset"])
+    obs, rew, done, now = golden_results(doc)
+    assert h["rc"] == 0
+    assert (h["obs"][:, 0, :] == obs).all()
+    assert (h["reward"][:, 0, :] == rew).all()
+    assert (h["done"][:, 0, :] == done).all()
+    assert (h["now"][:, 0] == now).all()            # bit-exact fp64 step end times
+    n_tx = sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "tx")
+    assert h["counts"][0, :, 0].sum() == n_tx
+
+
+def _compare(sc, nenv, nsteps, seed, do_reset=True):
+    rs = np.random.RandomState(seed)
+    nb = len(sc["bands"])
+    dev, dur = random_tapes(rs, nsteps, nenv, nb)
+    o = O.run_batch(sc, dev, dur, do_reset=do_reset)
+    h = HS.run(sc, dev, dur, do_reset=do_reset)
+    assert h["rc"] == 0
+    assert (o["obs"] == h["obs"]).all()
+    assert (o["reward"] == h["reward"]).all()
+    assert (o["done"] == h["done"]).all()
+    assert (o["now"] == h["now"]).all()
+    assert (o["counts"][:, :, :3] == h["counts"][:, :, :3]).all()     # transmissions, deliveries
+    return o, h
+
+
+def test_core_default_batch():
+    from gymwipe_b200.scenario import default_scenario_dict
+    o, h = _compare(default_scenario_dict(), 512, 160, 11)
+    assert o["counts"][:, :, 1:3].sum() > 10000          # the productive regime is exercised
+    assert h["counts"][:, :, 8].sum() == 0               # no exact-time ties in the default env
+
+
+def test_core_default_no_reset():
+    from gymwipe_b200.scenario import default_scenario_dict
+    _compare(default_scenario_dict(), 128, 100, 12, do_reset=False)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_core_random_scenarios(seed):
+    rs = np.random.RandomState(900 + seed)
+    spread = [1.5, 2.5, 4.0][seed % 3]
+    _compare(random_scenario(rs, jammers=0, spread=spread), 48, 150, seed)
+    _compare(random_scenario(rs, jammers=1, spread=spread), 48, 150, seed)
+    _compare(random_scenario(rs, jammers=1, spread=spread, fixed_payload=1500, factor=10000), 16, 50, seed)
+    _compare(random_scenario(rs, nbands=4, jammers=1, spread=spread), 16, 80, seed)
+
+
+def test_core_reset_mid_run_keeps_queue_sizes():
+    """reset() zeroes the counters but queued packets keep their sizes (snapshot ring)."""
+    from gymwipe_b200.scenario import default_scenario_dict
+    sc = default_scenario_dict()
+    # the oracle has no mid-run reset in run_batch: drive it step by step
+    rs = np.random.RandomState(5)
+    acts = [{"device": int(rs.randint(2)), "duration": int(rs.randint(20))} for _ in range(90)]
+    ora = O.Oracle(sc)
+    res = []
+    for i, a in enumerate(acts):
+        if i in (0, 30, 31, 60):
+            ora.reset()
+        res.append(ora.step(a) + (ora.now,))
+    # host core: segments with do_reset at the same places are not expressible in one hs_run
+    # call, so the same schedule is replayed by the GPU test; here the oracle's own invariants
+    # are checked: obs stays in {-2,0,2}+65536 and time is strictly increasing
+    assert all(r[0] - 65536 in (-2, 0, 2) for r in res)
+    assert all(res[i][3] < res[i + 1][3] for i in range(len(res) - 1))
+
+
+def test_arithmetic_close_to_reference():
+    """fp64 BER / FSPL of the core vs the reference's values (host libm here, CUDA libm on the GPU)."""
+    doc = load_golden("arithmetic")
+    L = HS.lib()
+    for s_mw, n_mw, ber in doc["ber_mw"]:
+        got = L.hs_ber(s_mw, n_mw)
+        assert abs(got - ber) <= 1e-12 * abs(ber)
+    for ax, ay, bx, by, f, att in doc["fspl"]:
+        got = L.hs_fspl(ax, ay, bx, by, f)
+        assert abs(got - att) <= 1e-12 * max(1.0, abs(att))
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    L = HS.lib()
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        c = np.array(ctr, np.uint32)
+        k = np.array(key, np.uint32)
+        o = np.zeros(4, np.uint32)
+        L.hs_philox(c.ctypes.data, k.ctypes.data, o.ctypes.data)
+        assert tuple(int(x) for x in o) == want

@@ -1,0 +1,320 @@
+"""
+GPU suite (`-m gpu`): the CUDA path, called through the C ABI / the public env API, against
+ (a) the golden vectors produced by the unmodified reference,
+ (b) the oracle (plain-C restatement) on the same seeded inputs,
+ (c) size-independent properties at BASELINE.json's full batch size.
+Bit-exact for obs / reward / done / delivery and transmission counts AND the fp64 step end
+times (event order); <= 1e-9 relative for BER / attenuation (stated tolerance: 1e-6).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import gw_oracle as O
+from util import (GOLDEN_CASES, golden_results, load_golden, random_scenario, random_tapes,
+                  tapes_from_golden)
+
+pytestmark = pytest.mark.gpu
+
+BER_RTOL = 1e-9          # north star: 1e-6 relative in fp64; observed ~1e-15
+
+
+def make_env(scenario=None, n=1, **kw):
+    import gymwipe_b200
+    return gymwipe_b200.make('CounterTraffic-v0', num_envs=n, scenario=scenario, **kw)
+
+
+def run_gpu(sc, dev, dur, do_reset=True, pos=None, **kw):
+    """dev, dur: [steps, nenv, nb] -> dict like oracle.run_batch"""
+    nsteps, nenv, nb = dev.shape
+    env = make_env(sc, nenv, strict=False, positions=None if pos is None else torch.as_tensor(pos[:, :, :4, :]).cuda(), **kw)
+    if do_reset:
+        env.reset()
+    d_dev = torch.as_tensor(dev).cuda()
+    d_dur = torch.as_tensor(dur).cuda()
+    obs = np.zeros((nsteps, nenv, nb), np.int64)
+    rew = np.zeros((nsteps, nenv, nb), np.float64)
+    done = np.zeros((nsteps, nenv, nb), np.uint8)
+    now = np.zeros((nsteps, nenv), np.float64)
+    for t in range(nsteps):
+        a = {"device": d_dev[t].reshape(env._shape), "duration": d_dur[t].reshape(env._shape)}
+        o, r, d, _ = env.step(a)
+        obs[t] = o.reshape(nenv, nb).cpu().numpy()
+        rew[t] = r.reshape(nenv, nb).cpu().numpy()
+        done[t] = d.reshape(nenv, nb).cpu().numpy()
+        now[t] = env.read_state(0).cpu().numpy()
+    env.check()
+    counts = np.zeros((nenv, nb, 3), np.int64)
+    counts[:, :, 0] = env.transmissions().cpu().numpy().reshape(nenv, nb)
+    counts[:, :, 1:3] = env.delivered().cpu().numpy().reshape(nenv, nb, 2)
+    ties = env.read_state(11).cpu().numpy().sum()
+    return {"obs": obs, "reward": rew, "done": done, "now": now, "counts": counts, "ties": ties, "env": env}
+
+
+def assert_same(o, g):
+    assert (o["obs"] == g["obs"]).all()
+    assert (o["reward"] == g["reward"]).all()
+    assert (o["done"] == g["done"]).all()
+    assert (o["now"] == g["now"]).all()
+    assert (o["counts"][:, :, :3] == g["counts"]).all()
+
+
+def test_reference_own_test_verbatim():
+    """tests/envs/test_counter_traffic.py of the reference, with gymwipe_b200.make for gym.make."""
+    import gymwipe_b200
+    env = gymwipe_b200.make('CounterTraffic-v0')
+    np.random.seed(123)
+    env.seed(123)
+    observation_center = env.COUNTER_BOUND
+    observation, reward, _, _ = env.step({"device": 0, "duration": 3})
+    assert observation - observation_center == 2
+    assert reward == -2
+    observation, reward, _, _ = env.step({"device": 1, "duration": 12})
+    assert observation - observation_center == 0
+    assert reward == 2
+    assert isinstance(observation, int) and isinstance(reward, float)
+    assert env.now == 0.017804000036000002
+
+
+def test_gym_surface():
+    env = make_env()
+    assert env.action_space.contains({"device": 1, "duration": 19})
+    assert not env.action_space.contains({"device": 2, "duration": 0})
+    assert env.observation_space.n == 131072
+    assert env.seed(5) == [5]
+    assert env.reset() == 65536
+    assert env.COUNTER_BOUND == 65536 and env.MAX_ASSIGN_DURATION == 20 and env.ASSIGNMENT_DURATION_FACTOR == 1000
+    assert len(env.senders) == 2 and env.senders[1].packetMultiplicity == 3
+    assert env.deviceIndexToMacDict[0] == bytes([0, 0, 0, 0, 0, 1])
+    with pytest.raises(AssertionError):
+        env.step({"device": 2, "duration": 3})           # the reference asserts too
+    o, r, d, info = env.step({"device": 0, "duration": 15})
+    assert info["Latest received values"] == "[2, 0]" and d is False
+    assert env.senders[0].counter >= 16
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_cuda_matches_reference_golden(name):
+    doc = load_golden(name)
+    dev, dur = tapes_from_golden(doc)
+    g = run_gpu(doc["scenario"], dev, dur, do_reset=doc["do_reset"])
+    obs, rew, done, now = golden_results(doc)
+    assert (g["obs"][:, 0, :] == obs).all()
+    assert (g["reward"][:, 0, :] == rew).all()
+    assert (g["done"][:, 0, :] == done).all()
+    assert (g["now"][:, 0] == now).all()
+    n_tx = sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "tx")
+    n_rx = sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "rx" and r[3] < 2)
+    assert g["counts"][0, :, 0].sum() == n_tx
+    assert g["counts"][0, :, 1:3].sum() == n_rx
+
+
+def test_cuda_matches_oracle_default_4096x128():
+    from gymwipe_b200.scenario import default_scenario_dict
+    sc = default_scenario_dict()
+    rs = np.random.RandomState(21)
+    dev, dur = random_tapes(rs, 128, 4096, 1)
+    o = O.run_batch(sc, dev, dur)
+    g = run_gpu(sc, dev, dur)
+    assert_same(o, g)
+    assert g["ties"] == 0
+    assert o["counts"][:, :, 1:3].sum() > 100000
+
+
+def test_cuda_matches_oracle_no_reset():
+    from gymwipe_b200.scenario import default_scenario_dict
+    sc = default_scenario_dict()
+    rs = np.random.RandomState(22)
+    dev, dur = random_tapes(rs, 64, 1024, 1)
+    assert_same(O.run_batch(sc, dev, dur, do_reset=False), run_gpu(sc, dev, dur, do_reset=False))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_cuda_matches_oracle_random_scenarios(seed):
+    rs = np.random.RandomState(700 + seed)
+    spread = [1.5, 2.5, 4.0][seed % 3]
+    for sc, nenv, nsteps in [(random_scenario(rs, jammers=0, spread=spread), 256, 100),
+                             (random_scenario(rs, jammers=1, spread=spread), 256, 100),
+                             (random_scenario(rs, jammers=1, spread=spread, fixed_payload=1500, factor=10000), 64, 40),
+                             (random_scenario(rs, nbands=4, jammers=1, spread=spread), 64, 60)]:
+        dev, dur = random_tapes(rs, nsteps, nenv, len(sc["bands"]))
+        assert_same(O.run_batch(sc, dev, dur), run_gpu(sc, dev, dur))
+
+
+def test_cuda_per_env_positions():
+    rs = np.random.RandomState(33)
+    sc = random_scenario(rs, nbands=4, jammers=1, spread=3.0)
+    nenv, nsteps = 128, 50
+    pos = np.zeros((nenv, 4, 8, 2))
+    pos[:, :, :4, :] = rs.uniform(-4, 4, size=(nenv, 4, 4, 2))
+    dev, dur = random_tapes(rs, nsteps, nenv, 4)
+    o = O.run_batch(sc, dev, dur, pos=pos)
+    g = run_gpu(sc, dev, dur, pos=pos)
+    assert_same(o, g)
+    # attenuation table of env 5, band 2 against the oracle's (reference formula)
+    env = g["env"]
+    att = env.read_state(8).cpu().numpy()           # [16, nsim]
+    loc = dict(sc)
+    one = O.Oracle(_with_positions(sc, pos[5]))
+    for p in range(4):
+        for d in range(4):
+            if p != d:
+                want = one.attenuation(2, p, d)
+                got = att[p * 4 + d, 5 * 4 + 2]
+                assert abs(got - want) <= BER_RTOL * abs(want)
+
+
+def _with_positions(sc, pos_env):
+    import copy
+    sc = copy.deepcopy(sc)
+    for b, band in enumerate(sc["bands"]):
+        for d, dv in enumerate(band["devices"]):
+            dv["x"], dv["y"] = float(pos_env[b, d, 0]), float(pos_env[b, d, 1])
+    return sc
+
+
+def test_reset_mid_run_matches_oracle():
+    """reset() between steps: counters := 0, queued packets keep their sizes (snapshot ring)."""
+    from gymwipe_b200.scenario import default_scenario_dict
+    sc = default_scenario_dict()
+    rs = np.random.RandomState(5)
+    nenv = 64
+    acts = [(rs.randint(0, 2, nenv).astype(np.int32), rs.randint(0, 20, nenv).astype(np.int32)) for _ in range(90)]
+    oras = [O.Oracle(sc) for _ in range(nenv)]
+    env = make_env(sc, nenv, strict=False)
+    for i, (dv, du) in enumerate(acts):
+        if i in (0, 30, 31, 60):
+            for o in oras:
+                o.reset()
+            env.reset()
+        want = [o.step({"device": int(dv[e]), "duration": int(du[e])}) for e, o in enumerate(oras)]
+        ob, rw, dn, _ = env.step({"device": torch.as_tensor(dv).cuda(), "duration": torch.as_tensor(du).cuda()})
+        assert ob.cpu().tolist() == [w[0] for w in want]
+        assert rw.cpu().tolist() == [w[1] for w in want]
+        assert env.read_state(0).cpu().tolist() == [o.now for o in oras]
+    # partial reset (env_ids)
+    ids = [3, 17, 40]
+    for e in ids:
+        oras[e].reset()
+    env.reset(env_ids=ids)
+    for dv, du in acts[:20]:
+        want = [o.step({"device": int(dv[e]), "duration": int(du[e])}) for e, o in enumerate(oras)]
+        ob, rw, _, _ = env.step({"device": torch.as_tensor(dv).cuda(), "duration": torch.as_tensor(du).cuda()})
+        assert ob.cpu().tolist() == [w[0] for w in want]
+        assert rw.cpu().tolist() == [w[1] for w in want]
+
+
+def test_ber_and_fspl_kernels_numeric():
+    doc = load_golden("arithmetic")
+    from gymwipe_b200.networking.physical import ber_from_milliwatts
+    from gymwipe_b200.networking.attenuation_models import FsplAttenuation
+    v = np.array(doc["ber_mw"])
+    got = ber_from_milliwatts(torch.tensor(v[:, 0]).cuda(), torch.tensor(v[:, 1]).cuda()).cpu().numpy()
+    assert np.all(np.abs(got - v[:, 2]) <= BER_RTOL * np.abs(v[:, 2]))
+    print("max BER rel err vs reference: %.3e" % np.max(np.abs(got - v[:, 2]) / np.abs(v[:, 2])))
+    f = np.array(doc["fspl"])
+    for freq in np.unique(f[:, 4]):
+        m = f[:, 4] == freq
+        a = FsplAttenuation.attenuation(*(torch.tensor(f[m, k]).cuda() for k in range(4)), freq).cpu().numpy()
+        assert np.all(np.abs(a - f[m, 5]) <= 1e-12 * np.abs(f[m, 5]))
+    # live-PHY values of SURVEY appendix C through the received-power state
+    env = make_env()
+    env.step({"device": 0, "duration": 3})
+    srx = env.read_state(9).cpu().numpy()[:, 0]
+    assert abs(srx[0 * 4 + 2] - 2.4689797345652838e-05) <= 1e-12 * 2.4689797345652838e-05
+
+
+def test_action_validation_flag():
+    env = make_env(None, 32, strict=False)
+    dev = torch.zeros(32, dtype=torch.int32, device="cuda")
+    dur = torch.full((32,), 20, dtype=torch.int32, device="cuda")       # 20 is outside Discrete(20)
+    env.step({"device": dev, "duration": dur})
+    with pytest.raises(ValueError, match="action"):
+        env.check()
+    env.check()                                                          # flag is cleared
+
+
+def test_flat_action_like_dqn_processor():
+    """agents/dqn_counter_traffic.py:25-33: a -> (a // 20, a % 20)."""
+    e1 = make_env(None, 8, strict=False)
+    e2 = make_env(None, 8, strict=False)
+    a = torch.tensor([0, 3, 19, 20, 25, 39, 12, 33], device="cuda")
+    o1, r1, _, _ = e1.step(a)
+    o2, r2, _, _ = e2.step({"device": (a // 20).int(), "duration": (a % 20).int()})
+    assert torch.equal(o1, o2) and torch.equal(r1, r2)
+
+
+def test_step_host_end_to_end():
+    from gymwipe_b200.scenario import default_scenario_dict
+    sc = default_scenario_dict()
+    rs = np.random.RandomState(8)
+    n = 2048
+    dev, dur = random_tapes(rs, 20, n, 1)
+    o = O.run_batch(sc, dev, dur)
+    env = make_env(sc, n, strict=False)
+    env.reset()
+    obs = torch.empty(n, dtype=torch.int64).pin_memory()
+    rew = torch.empty(n, dtype=torch.float64).pin_memory()
+    done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    for t in range(20):
+        env.step_host(np.ascontiguousarray(dev[t, :, 0]), np.ascontiguousarray(dur[t, :, 0]), obs, rew, done)
+        assert (obs.numpy() == o["obs"][t, :, 0]).all()
+        assert (rew.numpy() == o["reward"][t, :, 0]).all()
+
+
+def test_stats_epilogue():
+    from gymwipe_b200.scenario import default_scenario_dict
+    sc = default_scenario_dict()
+    rs = np.random.RandomState(9)
+    n, T = 1000, 30
+    dev, dur = random_tapes(rs, T, n, 1)
+    o = O.run_batch(sc, dev, dur)
+    env = make_env(sc, n, strict=False)
+    env.reset()
+    env.stats()
+    tot = np.zeros(8)
+    for t in range(T):
+        env.step({"device": torch.as_tensor(dev[t, :, 0]).cuda(), "duration": torch.as_tensor(dur[t, :, 0]).cuda()})
+        tot += env.stats().cpu().numpy()
+    assert tot[0] == o["reward"].sum()
+    assert tot[1] == o["counts"][:, 0, 1].sum() and tot[2] == o["counts"][:, 0, 2].sum()
+    assert tot[4] == n * T and tot[6] == o["counts"][:, 0, 0].sum()
+
+
+def test_full_size_properties_65536():
+    """BASELINE configs[1]: 65,536 envs.  Size-independent properties + a strided oracle sample."""
+    from gymwipe_b200.scenario import default_scenario_dict
+    sc = default_scenario_dict()
+    n, T = 65536, 128
+    g = torch.Generator(device="cuda").manual_seed(0)
+    dev = torch.randint(0, 2, (T, n), generator=g, device="cuda", dtype=torch.int32)
+    dur = torch.randint(0, 20, (T, n), generator=g, device="cuda", dtype=torch.int32)
+    env = make_env(sc, n, strict=False)
+    env.reset()
+    env.stats()
+    obs_all = torch.empty((T, n), dtype=torch.int64, device="cuda")
+    rew_all = torch.empty((T, n), dtype=torch.float64, device="cuda")
+    prev_abs = torch.zeros(n, dtype=torch.int64, device="cuda")
+    for t in range(T):
+        o, r, d, _ = env.step({"device": dev[t], "duration": dur[t]})
+        obs_all[t], rew_all[t] = o, r
+        diff = o - 65536
+        assert bool(((diff == -2) | (diff == 0) | (diff == 2)).all())     # appendix B #1
+        assert torch.equal(r, (prev_abs - diff.abs()).double())            # reward = change of |difference|
+        assert not bool(d.any())
+        prev_abs = diff.abs()
+    env.check()
+    st = env.stats().cpu().numpy()
+    assert st[4] == n * T and st[0] == rew_all.sum().item()
+    deliv = env.delivered()
+    assert st[1] == deliv[:, 0].sum().item() and st[2] == deliv[:, 1].sum().item()
+    # identical actions => identical trajectories: envs with the same tape must agree (checksum)
+    # and a strided sample of 512 envs equals the oracle bit for bit
+    idx = np.arange(0, n, n // 512)
+    o = O.run_batch(sc, dev[:, idx].cpu().numpy(), dur[:, idx].cpu().numpy())
+    assert (obs_all[:, idx].cpu().numpy() == o["obs"][:, :, 0]).all()
+    assert (rew_all[:, idx].cpu().numpy() == o["reward"][:, :, 0]).all()
+    assert (env.read_state(0)[idx].cpu().numpy() == o["now"][-1]).all()

@@ -1,0 +1,88 @@
+"""Shared helpers of the test-suite (golden fixtures, canonical record order, random scenarios)."""
+import json
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+GOLDEN_CASES = ["kat_reference_test", "default_reset_seed0", "default_noreset_seed1", "positions_seed3",
+                "jammer_seed5", "longpacket_seed7", "multiband_seed9"]
+
+
+def load_golden(name):
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        return json.load(f)
+
+
+def canonical(records):
+    """
+    Same-instant callbacks of DIFFERENT PHYs run in Python-set order in the reference
+    (gymwipe/simtools.py:255) and touch only their own PHY: compare ber/dec records per
+    (band, device) subsequence and tx/rx records as one global subsequence.
+    """
+    records = [tuple(r) for r in records]
+    glob = [r for r in records if r[0] in ("tx", "rx")]
+    per = {}
+    for r in records:
+        if r[0] in ("ber", "dec"):
+            per.setdefault((r[2], r[3]), []).append(r)
+    out = list(glob)
+    for k in sorted(per):
+        out += per[k]
+    return out
+
+
+def tapes_from_golden(doc):
+    """-> dev, dur int32 arrays [steps, 1, nbands]"""
+    nb = len(doc["scenario"]["bands"])
+    steps = doc["steps"]
+    dev = np.zeros((len(steps), 1, nb), np.int32)
+    dur = np.zeros((len(steps), 1, nb), np.int32)
+    for t, s in enumerate(steps):
+        acts = s["action"] if isinstance(s["action"], list) else [s["action"]]
+        for b, a in enumerate(acts):
+            dev[t, 0, b] = a["device"]
+            dur[t, 0, b] = a["duration"]
+    return dev, dur
+
+
+def golden_results(doc):
+    nb = len(doc["scenario"]["bands"])
+    steps = doc["steps"]
+    obs = np.array([s["obs"] if nb > 1 else [s["obs"]] for s in steps], np.int64)
+    rew = np.array([s["reward"] if nb > 1 else [s["reward"]] for s in steps], np.float64)
+    done = np.array([s["done"] if nb > 1 else [s["done"]] for s in steps], np.uint8)
+    now = np.array([s["now"] for s in steps], np.float64)
+    return obs, rew, done, now
+
+
+def random_scenario(rs, nbands=1, jammers=1, fixed_payload=None, spread=3.0, factor=1000):
+    """Random geometry / traffic / jammer scenario (same generator as oracle/check_restatement.py)."""
+    bands = []
+    for b in range(nbands):
+        devs = []
+        for k in range(2):
+            devs.append({"role": "sender", "x": float(rs.uniform(-spread, spread)),
+                         "y": float(rs.uniform(-spread, spread)), "mult": int(rs.randint(1, 4)),
+                         "payload": "counter" if fixed_payload is None else int(fixed_payload),
+                         "interval": 0.001, "dest": 1 - k})
+        devs.append({"role": "rrm", "x": float(rs.uniform(-spread, spread)),
+                     "y": float(rs.uniform(-spread, spread))})
+        for j in range(jammers):
+            payload = int(rs.randint(12, 200))
+            airtime = (13 + payload) * 8 / 99999.9975
+            devs.append({"role": "jammer", "x": float(rs.uniform(-spread, spread)),
+                         "y": float(rs.uniform(-spread, spread)),
+                         "interval": float(airtime * rs.uniform(1.3, 6.0)),
+                         "delay": float(rs.uniform(0, 1e-2)),
+                         "power": float(rs.choice([0.0, 10.0, 20.0])), "hdr": 13, "payload": payload})
+        bands.append({"frequency": 2.4e9 + b * 25e6, "bandwidth": 22e6, "devices": devs})
+    return {"assignment_duration_factor": factor, "bands": bands}
+
+
+def random_tapes(rs, nsteps, nenv, nb):
+    dev = rs.randint(0, 2, size=(nsteps, nenv, nb)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(nsteps, nenv, nb)).astype(np.int32)
+    return dev, dur
