@@ -68,6 +68,24 @@ def compare(ref, ora, label, ber_rtol=0.0):
     return bad
 
 
+def run_case_m(scenario, tape, label, seed=77, env_id=12345):
+    """mode M: reference + MaskedPhy subclass (numpy Philox) vs the restatement (C Philox)."""
+    tr = H.Tracer()
+    H.setup_paths()
+    H.install_masked_phy(lambda band, sender, seq, receiver, k0, k1, ber:
+                         H.philox_mask_errors(seed, env_id, band, sender, seq, receiver, k0, k1, ber), tr)
+    env = H.ScenarioEnv(scenario, tr)
+    ref = H.run_tape(env, tape, tr)
+    ora_env = O.Oracle(scenario, trace=True, mode=O.MODE_M)
+    ora_env.use_philox_masks(seed, env_id)
+    ora = O.run_tape(ora_env, tape)
+    bad = compare(ref, ora, label)
+    ndec = sum(1 for s in ref["steps"] for r in s["records"] if r[0] == "dec")
+    nfail = sum(1 for s in ref["steps"] for r in s["records"] if r[0] == "dec" and not r[7])
+    print("[%s] steps %d mismatching %d ; decisions %d (failed %d)" % (label, len(tape), bad, ndec, nfail))
+    return bad
+
+
 def run_case(scenario, tape, label, do_reset=True, use_default_class=False):
     tr = H.Tracer()
     if use_default_class:
@@ -137,6 +155,17 @@ def child(args):
                              factor=10000)
         tape = H.random_actions(args.steps, seed=args.seed + 3000)
         return run_case(sc, tape, "long-packet seed %d" % args.seed)
+    if args.case == "maskdefault":
+        tape = H.random_actions(args.steps, seed=args.seed + 5000)
+        return run_case_m(H.default_scenario(), tape, "mode M default seed %d" % args.seed, seed=args.seed + 77)
+    if args.case == "maskjammer":
+        sc = random_scenario(rs, jammers=1, spread=args.spread)
+        tape = H.random_actions(args.steps, seed=args.seed + 6000)
+        return run_case_m(sc, tape, "mode M jammer seed %d" % args.seed, seed=args.seed + 78)
+    if args.case == "masklong":
+        sc = random_scenario(rs, jammers=1, fixed_payload=1500, spread=args.spread, factor=10000)
+        tape = H.random_actions(args.steps, seed=args.seed + 7000)
+        return run_case_m(sc, tape, "mode M long-packet seed %d" % args.seed, seed=args.seed + 79)
     if args.case == "multiband":
         sc = random_scenario(rs, nbands=4, jammers=1, spread=args.spread)
         tapes = [H.random_actions(args.steps, seed=args.seed + 4000 + b) for b in range(4)]
@@ -173,7 +202,8 @@ def main():
     plan = [("kat", 0, 2), ("default", 0, 400), ("default", 1, 400), ("default_noreset", 2, 200)]
     nseeds = 2 if args.quick else 6
     for sd in range(nseeds):
-        plan += [("positions", sd, 200), ("jammer", sd, 200), ("long", sd, 40), ("multiband", sd, 80)]
+        plan += [("positions", sd, 200), ("jammer", sd, 200), ("long", sd, 40), ("multiband", sd, 80),
+                 ("maskdefault", sd, 120), ("maskjammer", sd, 120), ("masklong", sd, 20)]
     failed = 0
     for case, sd, steps in plan:
         rc = subprocess.call([sys.executable, os.path.abspath(__file__), "--case", case,

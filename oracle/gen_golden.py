@@ -35,7 +35,11 @@ CASES = {
     "jammer_seed5": ("jammer", 5, 60),
     "longpacket_seed7": ("long", 7, 12),
     "multiband_seed9": ("multiband", 9, 24),
+    "modeM_jammer_seed11": ("maskjammer", 11, 40),
+    "modeM_default_seed12": ("maskdefault", 12, 60),
 }
+
+MASK_SEED, MASK_ENV = 20261018, 4242
 
 
 def make_case(kind, seed, steps):
@@ -58,6 +62,10 @@ def make_case(kind, seed, steps):
         sc = CR.random_scenario(rs, nbands=4, jammers=1, spread=2.5)
         tapes = [H.random_actions(steps, seed=seed + 4000 + b) for b in range(4)]
         tape = [list(x) for x in zip(*tapes)]
+    elif kind == "maskjammer":
+        sc, tape = CR.random_scenario(rs, jammers=1, spread=2.5), H.random_actions(steps, seed=seed + 6000)
+    elif kind == "maskdefault":
+        sc, tape = H.default_scenario(), H.random_actions(steps, seed=seed + 5000)
     else:
         raise SystemExit(kind)
     return sc, tape, do_reset, use_default
@@ -68,11 +76,18 @@ def child(name):
     H.setup_paths()
     sc, tape, do_reset, use_default = make_case(kind, seed, steps)
     tr = H.Tracer()
+    mode_m = kind.startswith("mask")
+    if mode_m:
+        H.install_masked_phy(lambda band, sender, seq, receiver, k0, k1, ber:
+                             H.philox_mask_errors(MASK_SEED, MASK_ENV, band, sender, seq, receiver, k0, k1, ber), tr)
     env = H.make_default_env(tr) if use_default else H.ScenarioEnv(sc, tr)
     trace = H.run_tape(env, tape, tr, do_reset=do_reset)
     doc = {"name": name, "kind": kind, "seed": seed, "do_reset": do_reset,
+           "mode": "M" if mode_m else "R", "mask_seed": MASK_SEED if mode_m else None,
+           "mask_env_id": MASK_ENV if mode_m else None,
            "generator": "oracle/gen_golden.py (unmodified reference on oracle/shims)",
-           "reference_class": "gymwipe.envs.CounterTrafficEnv" if use_default else "oracle.ref_harness.ScenarioEnv",
+           "reference_class": ("gymwipe.envs.CounterTrafficEnv" if use_default else "oracle.ref_harness.ScenarioEnv")
+           + (" + oracle.ref_harness.MaskedPhy (SimplePhy subclass)" if mode_m else ""),
            "scenario": sc, "reset_obs": trace["reset_obs"],
            "steps": [{"action": s["action"], "obs": s["obs"], "reward": s["reward"], "done": s["done"],
                       "now": s["now"], "events": s["events"],

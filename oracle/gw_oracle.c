@@ -1009,6 +1009,83 @@ void gwo_set_mask_fn(gwo_sim *s, gwo_mask_fn fn, void *ctx, int64_t env_id)
     s->mask_fn = fn; s->mask_ctx = ctx; s->env_id = env_id;
 }
 
+/* ---------------------------------------------------------------------- */
+/* mode M: built-in mask providers                                          */
+/* ---------------------------------------------------------------------- */
+
+/* Philox4x32-10 (Random123; Salmon et al., SC'11), restated from the published algorithm */
+void gwo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* Error flag of on-air bit k: word (k & 3) of philox(ctr = (k >> 2, txseq,
+ * sender | receiver << 8 | band << 16, env_lo), key = (seed_lo ^ env_hi, seed_hi))
+ * is below floor(ber * 2^32).  (The keying is this project's definition of mode M.) */
+static int64_t philox_mask_fn(void *ctx, int64_t env, int band, int sender, uint32_t seq,
+                              int receiver, int64_t k0, int64_t k1, double ber)
+{
+    uint64_t seed = *(uint64_t *)ctx;
+    uint32_t thr = (uint32_t)(ber * 4294967296.0);
+    uint32_t key[2] = { (uint32_t)seed ^ (uint32_t)((uint64_t)env >> 32), (uint32_t)(seed >> 32) };
+    int64_t n = 0, cur = -1;
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int64_t k = k0; k < k1; k++) {
+        if ((k >> 2) != cur) {
+            cur = k >> 2;
+            uint32_t ctr[4] = { (uint32_t)cur, seq,
+                                (uint32_t)sender | ((uint32_t)receiver << 8) | ((uint32_t)band << 16),
+                                (uint32_t)(uint64_t)env };
+            gwo_philox4x32_10(ctr, key, w);
+        }
+        n += w[k & 3] < thr;
+    }
+    return n;
+}
+
+typedef struct { const uint32_t *words; int slots, words_per_row, nbands; } FedCtx;
+
+/* fed masks: [env][band][GWO_FED_DEV sender][slots][GWO_FED_DEV receiver][words_per_row] */
+static int64_t fed_mask_fn(void *ctx, int64_t env, int band, int sender, uint32_t seq,
+                           int receiver, int64_t k0, int64_t k1, double ber)
+{
+    const FedCtx *f = (const FedCtx *)ctx;
+    int64_t row = ((((env * f->nbands + band) * GWO_FED_DEV + sender) * f->slots
+                    + (int64_t)(seq % (uint32_t)f->slots)) * GWO_FED_DEV + receiver);
+    const uint32_t *w = f->words + row * f->words_per_row;
+    int64_t n = 0;
+    (void)ber;
+    for (int64_t k = k0; k < k1; k++) n += (w[k >> 5] >> (k & 31)) & 1u;
+    return n;
+}
+
+static uint64_t g_seed_store[1024];
+static FedCtx g_fed_store[1024];
+static int g_store_next = 0;
+
+void gwo_use_philox_masks(gwo_sim *s, uint64_t seed, int64_t env_id)
+{
+    int i = __sync_fetch_and_add(&g_store_next, 1) & 1023;
+    g_seed_store[i] = seed;
+    s->mask_fn = philox_mask_fn; s->mask_ctx = &g_seed_store[i]; s->env_id = env_id;
+}
+
+void gwo_use_fed_masks(gwo_sim *s, const uint32_t *words, int slots, int words_per_row, int64_t env_index)
+{
+    int i = __sync_fetch_and_add(&g_store_next, 1) & 1023;
+    g_fed_store[i].words = words; g_fed_store[i].slots = slots;
+    g_fed_store[i].words_per_row = words_per_row; g_fed_store[i].nbands = s->nbands;
+    s->mask_fn = fed_mask_fn; s->mask_ctx = &g_fed_store[i]; s->env_id = env_index;
+}
+
 void gwo_reset(gwo_sim *s, int64_t *obs)           /* counter_traffic.py:135-144 */
 {
     for (int b = 0; b < s->nbands; b++) {
@@ -1096,10 +1173,28 @@ void gwo_default_scenario(gwo_scenario *sc)        /* counter_traffic.py:114-133
  * counts[env][band][1 + GWO_MAXDEV] (n_tx, deliveries per device) after the last step.
  * Envs [env_begin, env_end) are processed -- the caller shards threads.
  */
+int gwo_run_batch_m(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_reset,
+                    const double *pos, const int32_t *dev_tape, const int32_t *dur_tape,
+                    int64_t *obs, double *reward, uint8_t *done, double *now, int64_t *counts,
+                    int64_t env_begin, int64_t env_end,
+                    uint64_t seed, int64_t env_id_offset, const uint32_t *fed_words, int fed_slots,
+                    int fed_words_per_row);
+
 int gwo_run_batch(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_reset,
                   const double *pos, const int32_t *dev_tape, const int32_t *dur_tape,
                   int64_t *obs, double *reward, uint8_t *done, double *now, int64_t *counts,
                   int64_t env_begin, int64_t env_end)
+{
+    return gwo_run_batch_m(sc, nenv, nsteps, do_reset, pos, dev_tape, dur_tape, obs, reward, done, now,
+                           counts, env_begin, env_end, 0, 0, NULL, 0, 0);
+}
+
+int gwo_run_batch_m(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_reset,
+                    const double *pos, const int32_t *dev_tape, const int32_t *dur_tape,
+                    int64_t *obs, double *reward, uint8_t *done, double *now, int64_t *counts,
+                    int64_t env_begin, int64_t env_end,
+                    uint64_t seed, int64_t env_id_offset, const uint32_t *fed_words, int fed_slots,
+                    int fed_words_per_row)
 {
     int nb = sc->nbands;
     int rc_all = 0;
@@ -1115,6 +1210,41 @@ int gwo_run_batch(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_reset
         }
         gwo_sim *s = gwo_create(&local);
         if (!s) return GWO_FAULT_INTERNAL;
+        if (sc->mode == GWO_MODE_M) {
+            uint64_t seed_local = seed;
+            FedCtx fed_local;
+            if (fed_words) {
+                fed_local.words = fed_words; fed_local.slots = fed_slots;
+                fed_local.words_per_row = fed_words_per_row; fed_local.nbands = nb;
+                s->mask_fn = fed_mask_fn; s->mask_ctx = &fed_local; s->env_id = e;
+            } else {
+                s->mask_fn = philox_mask_fn; s->mask_ctx = &seed_local; s->env_id = env_id_offset + e;
+            }
+            /* the contexts live on this stack frame for the lifetime of `s` (destroyed below) */
+            if (do_reset) gwo_reset(s, NULL);
+            int rc_m = 0;
+            int64_t om[GWO_MAXBAND]; double rm[GWO_MAXBAND]; uint8_t dm[GWO_MAXBAND];
+            for (int t = 0; t < nsteps; t++) {
+                size_t base = ((size_t)t * nenv + e) * nb;
+                rc_m = gwo_step(s, dev_tape + base, dur_tape + base, om, rm, dm);
+                if (rc_m) break;
+                for (int b = 0; b < nb; b++) {
+                    if (obs) obs[base + b] = om[b];
+                    if (reward) reward[base + b] = rm[b];
+                    if (done) done[base + b] = dm[b];
+                }
+                if (now) now[(size_t)t * nenv + e] = s->now;
+            }
+            if (counts) {
+                for (int b = 0; b < nb; b++) {
+                    int64_t *c = counts + ((size_t)e * nb + b) * (1 + GWO_MAXDEV);
+                    gwo_counts(s, b, c, c + 1);
+                }
+            }
+            gwo_destroy(s);
+            if (rc_m) return rc_m;
+            continue;
+        }
         if (do_reset) gwo_reset(s, NULL);
         int64_t o[GWO_MAXBAND]; double r[GWO_MAXBAND]; uint8_t dn[GWO_MAXBAND];
         for (int t = 0; t < nsteps; t++) {

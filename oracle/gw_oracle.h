@@ -91,6 +91,18 @@ int gwo_run_batch(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_reset
                   int64_t *obs, double *reward, uint8_t *done, double *now, int64_t *counts,
                   int64_t env_begin, int64_t env_end);
 
+/* mode M mask providers (GWO_FED_DEV = device stride of the fed-mask layout) */
+#define GWO_FED_DEV 4
+void gwo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void gwo_use_philox_masks(gwo_sim *s, uint64_t seed, int64_t env_id);
+void gwo_use_fed_masks(gwo_sim *s, const uint32_t *words, int slots, int words_per_row, int64_t env_index);
+int gwo_run_batch_m(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_reset,
+                    const double *pos, const int32_t *dev_tape, const int32_t *dur_tape,
+                    int64_t *obs, double *reward, uint8_t *done, double *now, int64_t *counts,
+                    int64_t env_begin, int64_t env_end,
+                    uint64_t seed, int64_t env_id_offset, const uint32_t *fed_words, int fed_slots,
+                    int fed_words_per_row);
+
 /* arithmetic helpers, exported for the numeric parity tests */
 double gwo_q_function(double x);
 double gwo_ber_bpsk(double s_dbm, double n_dbm, double bitRate);

@@ -91,6 +91,14 @@ def lib():
                                     C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int64, C.c_int64]
+        L.gwo_use_philox_masks.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
+        L.gwo_use_fed_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64]
+        L.gwo_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gwo_run_batch_m.restype = C.c_int
+        L.gwo_run_batch_m.argtypes = [C.POINTER(Scenario), C.c_int64, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int64, C.c_int64, C.c_uint64, C.c_int64, C.c_void_p, C.c_int, C.c_int]
         for name, args in (("gwo_q_function", [C.c_double]),
                            ("gwo_ber_bpsk", [C.c_double] * 3),
                            ("gwo_fspl", [C.c_double] * 5),
@@ -179,6 +187,16 @@ class Oracle:
         self._mask_cb = MASK_FN(cb)
         self.L.gwo_set_mask_fn(self.h, self._mask_cb, None, env_id)
 
+    def use_philox_masks(self, seed, env_id=0):
+        """Mode M with the built-in Philox4x32-10 mask provider (same keying as the CUDA kernel)."""
+        self.L.gwo_use_philox_masks(self.h, int(seed), int(env_id))
+
+    def use_fed_masks(self, words, slots, env_index=0):
+        """Mode M with fed masks: uint32 array [nenv][nbands][4][slots][4][words_per_row]."""
+        self._fed = np.ascontiguousarray(words, dtype=np.uint32)
+        self.L.gwo_use_fed_masks(self.h, self._fed.ctypes.data_as(C.c_void_p), int(slots),
+                                 int(self._fed.shape[-1]), int(env_index))
+
     def reset(self):
         o = (C.c_int64 * MAXBAND)()
         self.L.gwo_reset(self.h, o)
@@ -259,7 +277,8 @@ def run_tape(oracle, actions, do_reset=True):
 
 
 def run_batch(scenario, dev_tape, dur_tape, pos=None, do_reset=True, threads=None,
-              want=("obs", "reward", "done", "now", "counts")):
+              want=("obs", "reward", "done", "now", "counts"), mode=MODE_R, seed=0, env_id_offset=0,
+              fed_words=None, fed_slots=0):
     """
     Run ``nenv`` independent envs for ``nsteps`` steps with ``threads`` host threads.
     ``dev_tape`` / ``dur_tape``: int32 ``[nsteps, nenv, nbands]`` (or ``[nsteps, nenv]``).
@@ -268,7 +287,10 @@ def run_batch(scenario, dev_tape, dur_tape, pos=None, do_reset=True, threads=Non
     """
     L = lib()
     if isinstance(scenario, dict):
-        scenario = scenario_from_dict(scenario)
+        scenario = scenario_from_dict(scenario, mode)
+    scenario.mode = mode
+    if fed_words is not None:
+        fed_words = np.ascontiguousarray(fed_words, dtype=np.uint32)
     nb = scenario.nbands
     dev_tape = np.ascontiguousarray(dev_tape, dtype=np.int32)
     dur_tape = np.ascontiguousarray(dur_tape, dtype=np.int32)
@@ -301,11 +323,13 @@ def run_batch(scenario, dev_tape, dur_tape, pos=None, do_reset=True, threads=Non
     rcs = [0] * threads
 
     def work(i):
-        rcs[i] = L.gwo_run_batch(C.byref(scenario), nenv, nsteps, 1 if do_reset else 0,
-                                 ptr(pos), ptr(dev_tape), ptr(dur_tape),
-                                 ptr(res.get("obs")), ptr(res.get("reward")), ptr(res.get("done")),
-                                 ptr(res.get("now")), ptr(res.get("counts")),
-                                 int(bounds[i]), int(bounds[i + 1]))
+        rcs[i] = L.gwo_run_batch_m(C.byref(scenario), nenv, nsteps, 1 if do_reset else 0,
+                                   ptr(pos), ptr(dev_tape), ptr(dur_tape),
+                                   ptr(res.get("obs")), ptr(res.get("reward")), ptr(res.get("done")),
+                                   ptr(res.get("now")), ptr(res.get("counts")),
+                                   int(bounds[i]), int(bounds[i + 1]),
+                                   int(seed), int(env_id_offset), ptr(fed_words), int(fed_slots),
+                                   0 if fed_words is None else int(fed_words.shape[-1]))
 
     if threads == 1:
         work(0)

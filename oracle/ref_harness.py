@@ -97,6 +97,10 @@ class Tracer:
         def transmit(self, sender, power, packet, mcsHeader, mcsPayload):
             t = orig_transmit(self, sender, power, packet, mcsHeader, mcsPayload)
             tr = holder[0]
+            if tr is not None:
+                seqs = tr.__dict__.setdefault("tx_seq", {})
+                t._oracle_seq = seqs.get(sender, 0)
+                seqs[sender] = t._oracle_seq + 1
             if tr is not None and tr.enabled and sender in tr.device_index:
                 band, dev = tr.device_index[sender]
                 tr.records.append(("tx", t.startTime, band, dev, t.stopTime,
@@ -142,6 +146,95 @@ class Tracer:
     def take(self):
         r, self.records = self.records, []
         return r
+
+
+# --------------------------------------------------------------------------
+# mode M on the reference side: a SimplePhy subclass that replaces ONLY the error
+# bookkeeping (_countBitErrors / _resetBitErrorCounter) by per-bit error masks;
+# MAC / RRM / timing / power bookkeeping stay the reference's
+# --------------------------------------------------------------------------
+
+def philox4x32_10(ctr, key):
+    """Vectorised Philox4x32-10 (Random123): ctr uint32 [n,4], key uint32 [2] -> uint32 [n,4]."""
+    import numpy as np
+    c = [ctr[:, i].astype(np.uint64) for i in range(4)]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        n0 = ((p1 >> np.uint64(32)) ^ c[1] ^ k0) & mask
+        n1 = p1 & mask
+        n2 = ((p0 >> np.uint64(32)) ^ c[3] ^ k1) & mask
+        n3 = p0 & mask
+        c = [n0, n1, n2, n3]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask
+    return np.stack(c, axis=1).astype(np.uint32)
+
+
+def philox_mask_errors(seed, env, band, sender, seq, receiver, k0, k1, ber):
+    """Number of error flags among on-air bits [k0, k1) (the project's mode-M keying)."""
+    import numpy as np
+    if k1 <= k0:
+        return 0
+    thr = int(ber * 4294967296.0)
+    blocks = np.arange(k0 >> 2, ((k1 - 1) >> 2) + 1, dtype=np.uint64)
+    ctr = np.zeros((len(blocks), 4), np.uint32)
+    ctr[:, 0] = blocks.astype(np.uint32)
+    ctr[:, 1] = seq
+    ctr[:, 2] = sender | (receiver << 8) | (band << 16)
+    ctr[:, 3] = env & 0xFFFFFFFF
+    key = [(seed & 0xFFFFFFFF) ^ ((env >> 32) & 0xFFFFFFFF), (seed >> 32) & 0xFFFFFFFF]
+    w = philox4x32_10(ctr, key).reshape(-1)
+    ks = np.arange((k0 >> 2) * 4, (((k1 - 1) >> 2) + 1) * 4)
+    sel = (ks >= k0) & (ks < k1)
+    return int(np.count_nonzero(w[sel] < thr))
+
+
+def install_masked_phy(mask_fn, tracer):
+    """
+    Makes the reference's devices construct ``MaskedPhy`` instead of ``SimplePhy`` (run-time
+    rebinding of the name in ``gymwipe.networking.devices``; no source is modified).
+    ``mask_fn(band, sender, seq, receiver, k0, k1, ber) -> int``.
+    """
+    from math import floor
+    import gymwipe.networking.devices as devices_mod
+    from gymwipe.networking.simple_stack import SimplePhy
+    from gymwipe.simtools import SimMan
+
+    class MaskedPhy(SimplePhy):
+        def _resetBitErrorCounter(self):
+            super()._resetBitErrorCounter()
+            self._segT0 = SimMan.now
+            self._errInt = 0
+
+        def _receive(self, t):
+            if not self._transmitting:
+                self._rxT = t
+            yield from super()._receive(t)
+
+        def _countBitErrors(self):
+            # errors of the on-air bits of the segment that ends now (counted since the last
+            # CHANGE, integer): replaces the expected-value accounting of simple_stack.py:180-188
+            t = self._rxT
+            now = SimMan.now
+            rate = self._currentReceiverMcs.bitRate
+            k0 = int(floor((self._segT0 - t.startTime) * rate))
+            k1 = int(floor((now - t.startTime) * rate))
+            if k1 > k0:
+                band, sender = tracer.device_index[t.sender]
+                _, receiver = tracer.phy_index[self]
+                self._errInt += mask_fn(band, sender, t._oracle_seq, receiver, k0, k1,
+                                        self._receivedBitErrorRate)
+            self._segT0 = now
+            self._receivedBitErrorSum = float(self._errInt)
+
+    devices_mod.SimplePhy = MaskedPhy
+    import sys
+    me = sys.modules[__name__]
+    me._MaskedPhy = MaskedPhy
+    return MaskedPhy
 
 
 def _reset_mac_counter():
@@ -238,7 +331,8 @@ class ScenarioEnv:
             def __init__(self, name, x, y, band, interval, delay, power, hdr, payload, mac):
                 super().__init__(name, x, y, band)
                 self.macAddr = mac
-                self._phy = SimplePhy("phy", self, band)
+                import gymwipe.networking.devices as devices_mod
+                self._phy = devices_mod.SimplePhy("phy", self, band)    # MaskedPhy in mode M
                 mcs = BpskMcs(band.spec)
                 assert payload >= 12
 

@@ -9,7 +9,7 @@ import pytest
 
 import gw_oracle as O
 import hostsim as HS
-from util import (GOLDEN_CASES, golden_results, load_golden, random_scenario, random_tapes,
+from util import (GOLDEN_CASES, GOLDEN_CASES_M, golden_results, load_golden, random_scenario, random_tapes,
                   tapes_from_golden)
 
 
@@ -26,6 +26,34 @@ def test_core_matches_golden(name):
     assert (h["now"][:, 0] == now).all()            # bit-exact fp64 step end times
     n_tx = sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "tx")
     assert h["counts"][0, :, 0].sum() == n_tx
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES_M)
+def test_core_mode_m_matches_golden(name):
+    doc = load_golden(name)
+    dev, dur = tapes_from_golden(doc)
+    h = HS.run(doc["scenario"], dev, dur, do_reset=doc["do_reset"], mode=1, seed=doc["mask_seed"],
+               env_offset=doc["mask_env_id"])
+    obs, rew, done, now = golden_results(doc)
+    assert h["rc"] == 0
+    assert (h["obs"][:, 0, :] == obs).all() and (h["reward"][:, 0, :] == rew).all()
+    assert (h["now"][:, 0] == now).all()
+    n_rx = sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "rx" and r[3] < 2)
+    assert h["counts"][0, :, 1:3].sum() == n_rx
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_core_mode_m_random(seed):
+    rs = np.random.RandomState(300 + seed)
+    for sc, nenv, nsteps in [(random_scenario(rs, jammers=1, spread=2.5), 24, 80),
+                             (random_scenario(rs, jammers=1, spread=2.0, fixed_payload=600, factor=10000), 8, 30)]:
+        dev, dur = random_tapes(rs, nsteps, nenv, 1)
+        o = O.run_batch(sc, dev, dur, mode=O.MODE_M, seed=99 + seed, env_id_offset=1000)
+        h = HS.run(sc, dev, dur, mode=1, seed=99 + seed, env_offset=1000)
+        assert h["rc"] == 0
+        assert (o["obs"] == h["obs"]).all() and (o["reward"] == h["reward"]).all()
+        assert (o["now"] == h["now"]).all()
+        assert (o["counts"][:, :, :3] == h["counts"][:, :, :3]).all()
 
 
 def _compare(sc, nenv, nsteps, seed, do_reset=True):

@@ -8,13 +8,17 @@ import numpy as np
 import pytest
 
 import gw_oracle as O
-from util import GOLDEN_CASES, canonical, load_golden
+from util import GOLDEN_CASES, GOLDEN_CASES_M, canonical, load_golden
 
 
-@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("name", GOLDEN_CASES + GOLDEN_CASES_M)
 def test_restatement_matches_reference_trace(name):
     doc = load_golden(name)
-    ora = O.Oracle(doc["scenario"], trace=True)
+    if doc.get("mode", "R") == "M":
+        ora = O.Oracle(doc["scenario"], trace=True, mode=O.MODE_M)
+        ora.use_philox_masks(doc["mask_seed"], doc["mask_env_id"])
+    else:
+        ora = O.Oracle(doc["scenario"], trace=True)
     if doc["do_reset"]:
         assert ora.reset() == doc["reset_obs"]
     ora.take_records()
@@ -29,7 +33,8 @@ def test_restatement_matches_reference_trace(name):
         assert done == s["done"], (name, i)
         assert ora.now == s["now"], (name, i)          # bit-exact fp64 time
         assert canonical(ora.take_records()) == canonical(s["records"]), (name, i)
-    assert ora.near_ties == 0
+    if doc.get("mode", "R") == "R":
+        assert ora.near_ties == 0          # no decider threshold is within rounding distance
 
 
 def test_reference_known_answer():
@@ -73,6 +78,31 @@ def test_arithmetic_vectors():
         a, b = k.split("/")
         assert L.gwo_max_correctable_ber(int(a), int(b)) == v
     assert L.gwo_thermal_noise_mw(22e6) == doc["thermal_mw"]
+
+
+def test_philox_known_answers_oracle():
+    """Random123 kat_vectors for philox4x32-10 (the oracle's own restatement of the algorithm)."""
+    L = O.lib()
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        c, k, o = np.array(ctr, np.uint32), np.array(key, np.uint32), np.zeros(4, np.uint32)
+        L.gwo_philox4x32_10(c.ctypes.data, k.ctypes.data, o.ctypes.data)
+        assert tuple(int(x) for x in o) == want
+
+
+def test_mode_m_differs_from_mode_r_as_documented():
+    """Mode M counts errors since the last CHANGE and once: the 4 m link that mode R fails
+    through double counting (SURVEY appendix B #4) is decoded in mode M."""
+    a = O.Oracle(mode=O.MODE_R)
+    b = O.Oracle(mode=O.MODE_M)
+    b.use_philox_masks(1, 0)
+    for o in (a, b):
+        o.reset()
+        o.step({"device": 0, "duration": 15})
+    assert a.counts()[1][0] > 0 and b.counts()[1][0] > 0
 
 
 def test_degenerate_regime():

@@ -11,6 +11,9 @@ GOLDEN_CASES = ["kat_reference_test", "default_reset_seed0", "default_noreset_se
                 "jammer_seed5", "longpacket_seed7", "multiband_seed9"]
 
 
+GOLDEN_CASES_M = ["modeM_jammer_seed11", "modeM_default_seed12"]
+
+
 def load_golden(name):
     with open(os.path.join(GOLDEN, name + ".json")) as f:
         return json.load(f)
