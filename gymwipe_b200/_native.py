@@ -14,7 +14,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libgymwipe_b200.so")
+LIB_PATH = os.environ.get("GYMWIPE_B200_LIB") or os.path.join(LIB_DIR, "libgymwipe_b200.so")
 INCLUDE = os.path.join(HERE, "..", "include", "gymwipe_b200.h")
 
 GW_ABI_VERSION = 1
@@ -60,6 +60,8 @@ def _sources():
 
 
 def needs_build():
+    if os.environ.get("GYMWIPE_B200_LIB"):
+        return False            # an explicitly chosen build (kernel-variant experiments)
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

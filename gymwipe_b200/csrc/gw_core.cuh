@@ -31,8 +31,10 @@
 
 #if defined(__CUDACC__)
 #define GW_HD __host__ __device__ __forceinline__
+#define GW_UNROLL _Pragma("unroll")
 #else
 #define GW_HD inline
+#define GW_UNROLL
 #endif
 
 namespace gw {
@@ -221,6 +223,7 @@ struct Sim {
 struct Event {
     int kind, idx;
     double t;
+    uint32_t seq;
 };
 
 // construction-time state (CounterTrafficEnv.__init__, counter_traffic.py:114-133)
@@ -228,18 +231,21 @@ template <int D, int NS, int NJ>
 GW_HD void init_sim(Sim<D, NS, NJ> &s, double thermal)
 {
     s.now = 0.0; s.seq = 0; s.fault = 0; s.ties = 0;
+    GW_UNROLL
     for (int p = 0; p < D; ++p) {
         s.P[p] = thermal; s.sphase[p] = S_IDLE; s.tEv[p] = 0; s.sEv[p] = 0;
         s.txStart[p] = 0; s.tStop[p] = 0; s.tC[p] = 0; s.sC[p] = 0; s.cmdPay[p] = 0; s.txSeq[p] = 0;
         s.rxOf[p] = -1; s.rxSec[p] = 0; s.ber[p] = 0; s.err[p] = 0; s.tReset[p] = 0; s.segT0[p] = 0;
     }
     // process Initialize events in construction order: senders, then jammers (URGENT, t = 0)
+    GW_UNROLL
     for (int k = 0; k < NS; ++k) {
         s.tTick[k] = 0.0; s.sTick[k] = s.seq++;
         s.ticks[k] = 0; s.qn[k] = 0; s.epochK[k] = 0; s.epochC[k] = 1; s.snapEnd[k] = 0;
         s.mac[k] = MAC_NONE; s.wDone[k] = 0; s.wPend[k] = 0; s.stopW[k] = 0; s.sW[k] = 0;
         s.nDeliv[k] = 0;
     }
+    GW_UNROLL
     for (int j = 0; j < Sim<D, NS, NJ>::NJa; ++j) {
         s.tJam[j] = 0.0; s.sJam[j] = (j < NJ) ? s.seq++ : 0; s.jamStage[j] = 0; s.jamPending[j] = 0;
     }
@@ -250,38 +256,102 @@ GW_HD void init_sim(Sim<D, NS, NJ> &s, double thermal)
 
 GW_HD bool seq_before(uint32_t a, uint32_t b) { return (int32_t)(a - b) < 0; }
 
+// element access with a RUN-TIME index through fully unrolled selects: keeps the per-sim
+// state in registers (a dynamically indexed member array would force the whole struct
+// into local memory)
+template <int N, class T, class V>
+GW_HD void set_at(T (&a)[N], int i, V v)
+{
+    GW_UNROLL
+    for (int q = 0; q < N; ++q) a[q] = (q == i) ? (T)v : a[q];
+}
+template <int N, class T>
+GW_HD T get_at(const T (&a)[N], int i)
+{
+    T r = a[0];
+    GW_UNROLL
+    for (int q = 1; q < N; ++q) r = (q == i) ? a[q] : r;
+    return r;
+}
+// received power of receiver p (compile-time after unrolling) from sender d (run time)
+template <int D>
+GW_HD double srx_at(const double *srx, int p, int d)
+{
+    double r = srx[p * D];
+    GW_UNROLL
+    for (int q = 1; q < D; ++q) r = (q == d) ? srx[p * D + q] : r;
+    return r;
+}
+
 // ---------------------------------------------------------------------------
-// event selection: earliest (time, seq) among the timed slots
+// event selection: earliest (time, seq) among the timed slots.
+//
+// Traffic ticks are ~80 % of all timed events and touch nothing but their sender's queue
+// counters -- unless that sender's MAC is waiting for a packet.  next_event() therefore
+// applies such "silent" ticks in a tight loop, in exact (time, seq) order, and only hands
+// PHY / MAC / RRM / jammer events and MAC-waking ticks to the full transition function.
 // ---------------------------------------------------------------------------
 
-template <int D, int NS, int NJ>
-GW_HD Event select_event(Sim<D, NS, NJ> &s)
+GW_HD bool before(double ta, uint32_t qa, double tb, uint32_t qb)
 {
-    double tmin = INFINITY;
-    uint32_t smin = 0;
-    int kind = EV_NONE, idx = 0, tie = 0;
+    return ta < tb || (ta == tb && seq_before(qa, qb));
+}
+
+template <int D, int NS, int NJ>
+GW_HD Event select_nontick(const Sim<D, NS, NJ> &s)
+{
+    Event e;
+    e.kind = EV_NONE; e.idx = 0; e.t = INFINITY; e.seq = 0;
 #define GW_CONSIDER(T, SQ, K, I)                                                        \
     do {                                                                                \
         const double t_ = (T);                                                          \
         const uint32_t q_ = (SQ);                                                       \
-        if (t_ < tmin) { tmin = t_; smin = q_; kind = (K); idx = (I); tie = 0; }        \
-        else if (t_ == tmin) {                                                          \
-            tie |= ((K) != EV_TICK || kind != EV_TICK);                                 \
-            if (seq_before(q_, smin)) { smin = q_; kind = (K); idx = (I); }             \
+        if (before(t_, q_, e.t, e.seq) || e.kind == EV_NONE) {                          \
+            e.t = t_; e.seq = q_; e.kind = (K); e.idx = (I);                            \
         }                                                                               \
     } while (0)
-    for (int k = 0; k < NS; ++k) GW_CONSIDER(s.tTick[k], s.sTick[k], EV_TICK, k);
+    GW_UNROLL
     for (int j = 0; j < NJ; ++j) GW_CONSIDER(s.tJam[j], s.sJam[j], EV_JAM, j);
+    GW_UNROLL
     for (int d = 0; d < D; ++d)
         if (s.sphase[d] >= S_SLOT) GW_CONSIDER(s.tEv[d], s.sEv[d], EV_PHY, d);
+    GW_UNROLL
     for (int k = 0; k < NS; ++k)
         if (s.wPend[k]) GW_CONSIDER(s.stopW[k], s.sW[k], EV_W, k);
     if (s.rrmPend) GW_CONSIDER(s.tRrm, s.sRrm, EV_RRM, 0);
 #undef GW_CONSIDER
-    Event e;
-    e.kind = kind; e.idx = idx; e.t = tmin;
-    s.ties += (uint32_t)tie;    // counted when selected AND when left behind; diagnostic only
     return e;
+}
+
+// Next event for the full transition function.  Silent ticks that precede it -- and lie
+// strictly before `tLimit` -- are applied on the way (SenderDevice.senderProcess,
+// counter_traffic.py:53-61: `mult` packets into the drop-oldest queue, counter += 1, next tick).
+template <int D, int NS, int NJ>
+GW_HD Event next_event(Sim<D, NS, NJ> &s, const BandParams &B, double tLimit)
+{
+    const Event nt = select_nontick(s);
+    for (;;) {
+        int k = 0;
+        GW_UNROLL
+        for (int q = 1; q < NS; ++q)
+            if (before(s.tTick[q], s.sTick[q], get_at(s.tTick, k), get_at(s.sTick, k))) k = q;
+        const double tk = get_at(s.tTick, k);
+        const uint32_t qk = get_at(s.sTick, k);
+        if (nt.kind != EV_NONE && !before(tk, qk, nt.t, nt.seq)) {
+            s.ties += (tk == nt.t) ? 1u : 0u;       // exact tie of independent events (diagnostic)
+            return nt;
+        }
+        Event tick;
+        tick.kind = EV_TICK; tick.idx = k; tick.t = tk; tick.seq = qk;
+        if (!(tk < tLimit) || get_at(s.mac, k) == MAC_WAIT_COND) return tick;
+        const int mult = k == 0 ? B.mult[0] : B.mult[kMaxSend - 1];
+        const double interval = k == 0 ? B.interval[0] : B.interval[kMaxSend - 1];
+        const int n = get_at(s.qn, k) + mult;
+        set_at(s.qn, k, n > kQueueCap ? kQueueCap : n);
+        set_at(s.ticks, k, get_at(s.ticks, k) + 1);
+        set_at(s.tTick, k, tk + interval);
+        set_at(s.sTick, k, s.seq++);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -296,8 +366,8 @@ GW_HD void count_set(const Sim<D, NS, NJ> &s, const Event &ev, const double *srx
 {
     once = 0; twice = 0;
     if (ev.kind != EV_PHY) return;
-    int d = ev.idx, ph = 0;
-    for (int q = 0; q < D; ++q) if (q == d) ph = s.sphase[q];
+    const int d = ev.idx, ph = get_at(s.sphase, d);
+    GW_UNROLL
     for (int p = 0; p < D; ++p) {
         const int rx = s.rxOf[p];
         if (rx < 0) continue;
@@ -306,7 +376,7 @@ GW_HD void count_set(const Sim<D, NS, NJ> &s, const Event &ev, const double *srx
         } else {
             // S_SLOT: the new transmission adds power; S_PAY: the completing one removes it.
             // onReceivedPowerChange counts only for delta != 0 (simple_stack.py:224)
-            const bool delta_nz = (p != d) && (srx[p * D + d] != 0.0);
+            const bool delta_nz = (p != d) && (srx_at<D>(srx, p, d) != 0.0);
             if (delta_nz) once |= 1 << p;
             if (ph == S_PAY && rx == d && s.rxSec[p] == 1) {
                 if (delta_nz) twice |= 1 << p; else once |= 1 << p;
@@ -319,6 +389,7 @@ GW_HD void count_set(const Sim<D, NS, NJ> &s, const Event &ev, const double *srx
 template <int D, int NS, int NJ>
 GW_HD void do_counts_R(Sim<D, NS, NJ> &s, int once, int twice, double bitRate)
 {
+    GW_UNROLL
     for (int p = 0; p < D; ++p) {
         if (!((once >> p) & 1)) continue;
         const double duration = s.now - s.tReset[p];
@@ -333,12 +404,10 @@ template <int D, int NS, int NJ>
 GW_HD void mask_range(const Sim<D, NS, NJ> &s, int p, double bitRate, int &sender, uint32_t &txseq,
                       int64_t &k0, int64_t &k1)
 {
-    int e = 0;
-    for (int q = 0; q < D; ++q) if (q == p) e = s.rxOf[q];
-    double start = 0; uint32_t sq = 0;
-    for (int q = 0; q < D; ++q) if (q == e) { start = s.txStart[q]; sq = s.txSeq[q] - 1u; }
-    double t0 = 0;
-    for (int q = 0; q < D; ++q) if (q == p) t0 = s.segT0[q];
+    const int e = get_at(s.rxOf, p);
+    const double start = get_at(s.txStart, e);
+    const uint32_t sq = get_at(s.txSeq, e) - 1u;
+    const double t0 = get_at(s.segT0, p);
     sender = e; txseq = sq;
     k0 = (int64_t)floor((t0 - start) * bitRate);
     k1 = (int64_t)floor((s.now - start) * bitRate);
@@ -354,16 +423,17 @@ GW_HD void begin_slot_wait(Sim<D, NS, NJ> &s, int d)
     // self._transmitting = True; yield SimMan.nextTimeSlot(TIME_SLOT_LENGTH)  (simple_stack.py:202-204)
     const double t = s.now + (kSlot - fmod(s.now, kSlot));      // simtools.py:53
     const uint32_t q = s.seq++;
-    for (int p = 0; p < D; ++p) if (p == d) { s.sphase[p] = S_SLOT; s.tEv[p] = t; s.sEv[p] = q; }
+    set_at(s.sphase, d, (int)S_SLOT);
+    set_at(s.tEv, d, t);
+    set_at(s.sEv, d, q);
 }
 
 template <int D, int NS, int NJ>
 GW_HD void phy_send_init(Sim<D, NS, NJ> &s, int d)
 {
     // SimplePhy.macInHandler start: wait while the receiver is active (simple_stack.py:199-200)
-    bool receiving = false;
-    for (int p = 0; p < D; ++p) if (p == d) receiving = s.rxOf[p] >= 0;
-    if (receiving) { for (int p = 0; p < D; ++p) if (p == d) s.sphase[p] = S_WAITRX; }
+    const bool receiving = get_at(s.rxOf, d) >= 0;
+    if (receiving) set_at(s.sphase, d, (int)S_WAITRX);
     else begin_slot_wait(s, d);
 }
 
@@ -372,20 +442,19 @@ GW_HD void phy_send_init(Sim<D, NS, NJ> &s, int d)
 template <int D, int NS, int NJ, class Ring>
 GW_HD int head_size(const Sim<D, NS, NJ> &s, const BandParams &B, int k, const Ring &ring)
 {
-    int size = 0;
-    for (int q = 0; q < NS; ++q) {
-        if (q != k) continue;
-        if (B.payloadRule[q] >= 0) { size = B.payloadRule[q]; continue; }
-        const uint32_t m = (uint32_t)B.mult[q];
-        const uint64_t enq = s.ticks[q] * m;
-        const uint64_t j = enq - (uint64_t)s.qn[q];
-        if (j < s.snapEnd[q]) { size = ring(q, (uint32_t)(j % (uint64_t)kQueueCap)); continue; }
-        // tick of packet j = ticks - ceil(qn / m)
-        const uint64_t back = ((uint32_t)s.qn[q] + m - 1u) / m;
-        const uint64_t tick = s.ticks[q] - back;
-        const uint64_t c = (uint64_t)s.epochC[q] + (tick - s.epochK[q]);
-        size = c > (uint64_t)kCounterBound ? kCounterBound : (int)c;
-    }
+    const int rule = k == 0 ? B.payloadRule[0] : B.payloadRule[kMaxSend - 1];
+    if (rule >= 0) return rule;
+    const uint32_t m = (uint32_t)(k == 0 ? B.mult[0] : B.mult[kMaxSend - 1]);
+    const uint64_t ticks = get_at(s.ticks, k);
+    const uint32_t qn = (uint32_t)get_at(s.qn, k);
+    const uint64_t enq = ticks * m;
+    const uint64_t j = enq - (uint64_t)qn;
+    if (j < get_at(s.snapEnd, k)) return ring(k, (uint32_t)(j % (uint64_t)kQueueCap));
+    // tick of packet j = ticks - ceil(qn / m)
+    const uint64_t back = (qn + m - 1u) / m;
+    const uint64_t tick = ticks - back;
+    const uint64_t c = (uint64_t)get_at(s.epochC, k) + (tick - get_at(s.epochK, k));
+    const int size = c > (uint64_t)kCounterBound ? kCounterBound : (int)c;
     return size;
 }
 
@@ -395,16 +464,16 @@ GW_HD void mac_try_send(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B,
 {
     const int size = head_size(s, B, k, ring);
     const int bitSize = (kMacHdr + kNetHdr + size) * 8;
-    double stopW = 0;
-    for (int q = 0; q < NS; ++q) if (q == k) stopW = s.stopW[q];
+    const double stopW = get_at(s.stopW, k);
     const double timeLeft = stopW - s.now;
     const double txTime = bitSize / P.dataRate;
     if (!(timeLeft > txTime)) {
-        for (int q = 0; q < NS; ++q) if (q == k) s.mac[q] = MAC_IDLE;       // yield timeoutEvent
+        set_at(s.mac, k, (int)MAC_IDLE);        // yield timeoutEvent
         return;
     }
-    for (int q = 0; q < NS; ++q) if (q == k) { s.qn[q] -= 1; s.mac[q] = MAC_WAIT_TX; }
-    for (int p = 0; p < D; ++p) if (p == k) s.cmdPay[p] = kNetHdr + size;
+    set_at(s.qn, k, get_at(s.qn, k) - 1);
+    set_at(s.mac, k, (int)MAC_WAIT_TX);
+    set_at(s.cmdPay, k, kNetHdr + size);
     phy_send_init(s, k);
 }
 
@@ -412,10 +481,9 @@ GW_HD void mac_try_send(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B,
 template <int D, int NS, int NJ, class Ring>
 GW_HD void mac_loop_head(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, int k, const Ring &ring)
 {
-    bool done = false, empty = false;
-    for (int q = 0; q < NS; ++q) if (q == k) { done = s.wDone[q] != 0; empty = s.qn[q] == 0; }
-    if (done) { for (int q = 0; q < NS; ++q) if (q == k) s.mac[q] = MAC_NONE; return; }
-    if (empty) { for (int q = 0; q < NS; ++q) if (q == k) s.mac[q] = MAC_WAIT_COND; return; }
+    const bool done = get_at(s.wDone, k) != 0, empty = get_at(s.qn, k) == 0;
+    if (done) { set_at(s.mac, k, (int)MAC_NONE); return; }
+    if (empty) { set_at(s.mac, k, (int)MAC_WAIT_COND); return; }
     mac_try_send(s, P, B, k, ring);
 }
 
@@ -423,15 +491,18 @@ GW_HD void mac_loop_head(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B
 template <int D, int NS, int NJ>
 GW_HD void rx_clear(Sim<D, NS, NJ> &s, int p)
 {
-    for (int q = 0; q < D; ++q) if (q == p) { s.rxOf[q] = -1; s.err[q] = 0; s.ber[q] = 0.0; s.tReset[q] = s.now; s.segT0[q] = s.now; }
+    set_at(s.rxOf, p, -1);
+    set_at(s.err, p, 0.0);
+    set_at(s.ber, p, 0.0);
+    set_at(s.tReset, p, s.now);
+    set_at(s.segT0, p, s.now);
 }
 
 template <int D, int NS, int NJ>
 GW_HD bool decide(const Sim<D, NS, NJ> &s, const Params &P, int p, double totalBits)
 {
     // bitErrorSum = round(bitErrorSum); bitErrorSum / totalBits <= maxCorrectableBer  (simple_stack.py:274-277)
-    double e = 0;
-    for (int q = 0; q < D; ++q) if (q == p) e = s.err[q];
+    const double e = get_at(s.err, p);
     return rint(e) / totalBits <= P.maxBer;
 }
 
@@ -452,47 +523,41 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
         // SenderDevice.senderProcess (counter_traffic.py:53-61): `mult` packets, counter += 1,
         // next tick; then the MAC wakes if it waits on (_packetAddedEvent | timeoutEvent)
         const int k = ev.idx;
-        bool wake = false;
-        for (int q = 0; q < NS; ++q) {
-            if (q != k) continue;
-            int n = s.qn[q] + B.mult[q];
-            s.qn[q] = n > kQueueCap ? kQueueCap : n;               // drop-oldest
-            s.ticks[q] += 1;
-            s.tTick[q] = s.now + B.interval[q];
-            s.sTick[q] = s.seq++;
-            wake = s.mac[q] == MAC_WAIT_COND;
-        }
+        const int mult = k == 0 ? B.mult[0] : B.mult[kMaxSend - 1];
+        const double interval = k == 0 ? B.interval[0] : B.interval[kMaxSend - 1];
+        const int n = get_at(s.qn, k) + mult;
+        set_at(s.qn, k, n > kQueueCap ? kQueueCap : n);             // drop-oldest
+        set_at(s.ticks, k, get_at(s.ticks, k) + 1);
+        set_at(s.tTick, k, s.now + interval);
+        set_at(s.sTick, k, s.seq++);
+        const bool wake = get_at(s.mac, k) == MAC_WAIT_COND;
         if (wake) mac_try_send(s, P, B, k, ring);
         break;
     }
     case EV_JAM: {
-        const int j = ev.idx, d = RRM + 1 + j;
-        for (int q = 0; q < NJ; ++q) {
-            if (q != j) continue;
-            if (s.jamStage[q] == 0) {               // yield timeout(initialDelay)
-                s.jamStage[q] = 1; s.tJam[q] = s.now + B.jamDelay[q]; s.sJam[q] = s.seq++;
-            } else if (s.jamStage[q] == 1) {        // first yield timeout(sendInterval)
-                s.jamStage[q] = 2; s.tJam[q] = s.now + B.jamInterval[q]; s.sJam[q] = s.seq++;
+        const int d = RRM + 1 + ev.idx;            // kMaxJam == 1: jammer slot 0
+        if (NJ > 0) {
+            if (s.jamStage[0] == 0) {                   // yield timeout(initialDelay)
+                s.jamStage[0] = 1; s.tJam[0] = s.now + B.jamDelay[0]; s.sJam[0] = s.seq++;
+            } else if (s.jamStage[0] == 1) {            // first yield timeout(sendInterval)
+                s.jamStage[0] = 2; s.tJam[0] = s.now + B.jamInterval[0]; s.sJam[0] = s.seq++;
             } else {
                 // macIn.send(SEND) -> queued executor; then yield timeout(sendInterval)
-                s.tJam[q] = s.now + B.jamInterval[q]; s.sJam[q] = s.seq++;
-                bool busy = false;
-                for (int p = 0; p < D; ++p) if (p == d) busy = s.sphase[p] != S_IDLE;
-                if (busy) { s.jamPending[q] += 1; if (s.jamPending[q] > 60) s.fault = FAULT_SENDQ; }
-                else { for (int p = 0; p < D; ++p) if (p == d) s.cmdPay[p] = B.jamPay[q]; phy_send_init(s, d); }
+                s.tJam[0] = s.now + B.jamInterval[0]; s.sJam[0] = s.seq++;
+                const bool busy = get_at(s.sphase, d) != S_IDLE;
+                if (busy) { s.jamPending[0] += 1; if (s.jamPending[0] > 60) s.fault = FAULT_SENDQ; }
+                else { set_at(s.cmdPay, d, B.jamPay[0]); phy_send_init(s, d); }
             }
         }
         break;
     }
     case EV_PHY: {
         const int d = ev.idx;
-        int ph = 0;
-        for (int q = 0; q < D; ++q) if (q == d) ph = s.sphase[q];
+        const int ph = get_at(s.sphase, d);
         if (ph == S_SLOT) {
             // FrequencyBand.transmit -> Transmission.__init__ (physical.py:224-279,596-608)
-            int hdrBytes = kMacHdr, payBytes = 0;
-            for (int q = 0; q < D; ++q) if (q == d) payBytes = s.cmdPay[q];
-            for (int j = 0; j < NJ; ++j) if (d == RRM + 1 + j) hdrBytes = B.jamHdr[j];
+            const int payBytes = get_at(s.cmdPay, d);
+            const int hdrBytes = (NJ > 0 && d > RRM) ? B.jamHdr[0] : kMacHdr;
             const double hd = (hdrBytes * 8) / P.dataRate;
             const double pd = (payBytes * 8) / P.dataRate;
             const double duration = hd + pd;
@@ -501,25 +566,30 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
             const double tH = s.now + (headerStop > s.now ? headerStop - s.now : 0.0);   // timeoutUntil
             const double tC = s.now + (stop > s.now ? stop - s.now : 0.0);
             const uint32_t qH = s.seq++, qC = s.seq++;
-            for (int q = 0; q < D; ++q) if (q == d) {
-                s.sphase[q] = S_HDR; s.tEv[q] = tH; s.sEv[q] = qH; s.tC[q] = tC; s.sC[q] = qC;
-                s.txStart[q] = s.now; s.tStop[q] = stop; s.txSeq[q] += 1;
-            }
+            set_at(s.sphase, d, (int)S_HDR);
+            set_at(s.tEv, d, tH);
+            set_at(s.sEv, d, qH);
+            set_at(s.tC, d, tC);
+            set_at(s.sC, d, qC);
+            set_at(s.txStart, d, s.now);
+            set_at(s.tStop, d, stop);
+            set_at(s.txSeq, d, get_at(s.txSeq, d) + 1u);
             s.nTx += 1;
             // zero-delay notification: every other PHY registers the received power
             // (simple_stack.py:130-144); a PHY that is receiving re-evaluates its BER
+            GW_UNROLL
             for (int p = 0; p < D; ++p) {
                 if (p == d) continue;
-                const double rp = srx[p * D + d];
+                const double rp = srx_at<D>(srx, p, d);
                 s.P[p] += rp;
                 if (s.rxOf[p] >= 0 && rp != 0.0) {
-                    bool completed = false;
-                    for (int q = 0; q < D; ++q) if (q == s.rxOf[p]) completed = s.now >= s.tStop[q];
+                    const bool completed = s.now >= get_at(s.tStop, s.rxOf[p]);
                     if (!completed) berMask |= 1 << p;
                 }
             }
             // receive processes in PHY construction order: idle, non-transmitting PHYs lock on
             // (simple_stack.py:214-235)
+            GW_UNROLL
             for (int p = 0; p < D; ++p) {
                 if (p == d || s.rxOf[p] >= 0 || s.sphase[p] >= S_SLOT) continue;
                 s.rxOf[p] = d; s.rxSec[p] = 0;
@@ -528,10 +598,10 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
             }
         } else if (ph == S_HDR) {
             // eHeaderCompletes: receivers decide on the header (simple_stack.py:241-251)
-            int hdrBytes = kMacHdr;
-            for (int j = 0; j < NJ; ++j) if (d == RRM + 1 + j) hdrBytes = B.jamHdr[j];
+            const int hdrBytes = (NJ > 0 && d > RRM) ? B.jamHdr[0] : kMacHdr;
             const double hdrBits = (hdrBytes * 8) * P.bitsFactor;
             int wake = 0;
+            GW_UNROLL
             for (int p = 0; p < D; ++p) {
                 if (s.rxOf[p] != d || s.rxSec[p] != 0) continue;
                 if (decide(s, P, p, hdrBits)) {
@@ -542,19 +612,23 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
                     if (s.sphase[p] == S_WAITRX) wake |= 1 << p;
                 }
             }
-            for (int q = 0; q < D; ++q) if (q == d) { s.sphase[q] = S_PAY; s.tEv[q] = s.tC[q]; s.sEv[q] = s.sC[q]; }
+            set_at(s.sphase, d, (int)S_PAY);
+            set_at(s.tEv, d, get_at(s.tC, d));
+            set_at(s.sEv, d, get_at(s.sC, d));
+            GW_UNROLL
             for (int p = 0; p < D; ++p) if ((wake >> p) & 1) begin_slot_wait(s, p);   // _nReceivingFinished.event
         } else {
             // eCompletes, callbacks in registration order:
             // 1. the sender's macInHandler resumes: _transmitting = False (simple_stack.py:210)
-            int payBytes = 0;
-            double stopD = 0;
-            for (int q = 0; q < D; ++q) if (q == d) { s.sphase[q] = S_IDLE; payBytes = s.cmdPay[q]; stopD = s.tStop[q]; }
+            const int payBytes = get_at(s.cmdPay, d);
+            const double stopD = get_at(s.tStop, d);
+            set_at(s.sphase, d, (int)S_IDLE);
             const double payBits = (payBytes * 8) * P.bitsFactor;
             // 2. _onCompletingTransmission of every other PHY (simple_stack.py:146-157)
+            GW_UNROLL
             for (int p = 0; p < D; ++p) {
                 if (p == d) continue;
-                const double rp = srx[p * D + d];
+                const double rp = srx_at<D>(srx, p, d);
                 s.P[p] += -rp;
                 if (s.rxOf[p] >= 0 && rp != 0.0) {
                     if (s.rxOf[p] == d) {
@@ -562,14 +636,14 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
                         // already popped: the reference raises KeyError (appendix B #12)
                         if (!(s.now >= stopD)) s.fault = FAULT_REF_KEYERROR;
                     } else {
-                        bool completed = false;
-                        for (int q = 0; q < D; ++q) if (q == s.rxOf[p]) completed = s.now >= s.tStop[q];
+                        const bool completed = s.now >= get_at(s.tStop, s.rxOf[p]);
                         if (!completed) berMask |= 1 << p;
                     }
                 }
             }
             // 3. receivers that passed the header decide on the payload and deliver
             int window = -1, wake = 0;
+            GW_UNROLL
             for (int p = 0; p < D; ++p) {
                 if (s.rxOf[p] != d || s.rxSec[p] != 1) continue;
                 if (decide(s, P, p, payBits)) {
@@ -577,8 +651,7 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
                         // SimpleMac.phyInHandler (blocking, not queued): only an announcement
                         // addressed to an idle MAC has an effect (simple_stack.py:386-448)
                         if (d == RRM && s.annDest == p) {
-                            bool idle = false;
-                            for (int q = 0; q < NS; ++q) if (q == p) idle = s.mac[q] == MAC_NONE;
+                            const bool idle = get_at(s.mac, p) == MAC_NONE;
                             if (idle) window = p;
                         }
                     } else if (p == RRM) {
@@ -588,7 +661,7 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
                             if (d == 0) s.rv0 = kCounterByteLen;
                             if (d == 1) s.rv1 = kCounterByteLen;
                             s.latestDiff = s.rv0 - s.rv1;
-                            for (int q = 0; q < NS; ++q) if (q == d) s.nDeliv[q] += 1;
+                            set_at(s.nDeliv, d, get_at(s.nDeliv, d) + 1u);
                         }
                     }
                 }
@@ -601,7 +674,10 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
                 const double timeTotal = s.annSlots * kSlot;
                 const double stopW = s.now + timeTotal;
                 const uint32_t qW = s.seq++;
-                for (int q = 0; q < NS; ++q) if (q == window) { s.stopW[q] = stopW; s.sW[q] = qW; s.wPend[q] = 1; s.wDone[q] = 0; }
+                set_at(s.stopW, window, stopW);
+                set_at(s.sW, window, qW);
+                set_at(s.wPend, window, 1);
+                set_at(s.wDone, window, 0);
                 mac_loop_head(s, P, B, window, ring);
             }
             // b. SEND eProcessed: the sender's upper layer resumes
@@ -613,24 +689,23 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
                 s.rrmPend = 1;
             } else {
                 // c. executeNext of the queued macIn executor: a jammer's pending SEND starts
-                for (int j = 0; j < NJ; ++j) if (d == RRM + 1 + j && s.jamPending[j] > 0) {
-                    s.jamPending[j] -= 1;
+                if (NJ > 0 && s.jamPending[0] > 0) {
+                    s.jamPending[0] -= 1;
                     phy_send_init(s, d);
                 }
             }
             // d. _nReceivingFinished.event of the receivers that finished
+            GW_UNROLL
             for (int p = 0; p < D; ++p) if ((wake >> p) & 1) begin_slot_wait(s, p);
         }
         break;
     }
     case EV_W: {
         // window timeoutEvent processed (simple_stack.py:406-420)
-        for (int q = 0; q < NS; ++q) {
-            if (q != ev.idx) continue;
-            s.wPend[q] = 0;
-            if (s.mac[q] == MAC_WAIT_TX) s.wDone[q] = 1;
-            else s.mac[q] = MAC_NONE;
-        }
+        const int k = ev.idx;
+        set_at(s.wPend, k, 0);
+        if (get_at(s.mac, k) == MAC_WAIT_TX) set_at(s.wDone, k, 1);
+        else set_at(s.mac, k, (int)MAC_NONE);
         break;
     }
     case EV_RRM:
@@ -644,20 +719,39 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
     return berMask;
 }
 
+// BER(S, N) is a pure function and, with static geometry, the same few (S, N) pairs recur in
+// every env and step: a memo (exact fp64 results keyed by the exact bit patterns of S and N)
+// replaces ~10^3 dependent fp64 instructions by one table probe.  NoMemo = always evaluate.
+struct NoMemo {
+    GW_HD bool get(double, double, double &) const { return false; }
+    GW_HD void put(double, double, double) const {}
+};
+
 // SimplePhy._updateBitErrorRate for the PHYs in berMask (simple_stack.py:161-173)
-template <int D, int NS, int NJ>
-GW_HD void update_bers(Sim<D, NS, NJ> &s, const Params &P, int berMask, const double *srx)
+template <int D, int NS, int NJ, class Memo>
+GW_HD void update_bers(Sim<D, NS, NJ> &s, const Params &P, int berMask, const double *srx, const Memo &memo)
 {
+    GW_UNROLL
     for (int p = 0; p < D; ++p) {
         if (!((berMask >> p) & 1)) continue;
         const int e = s.rxOf[p];
         if (e < 0) continue;
-        double S = 0;
-        for (int q = 0; q < D; ++q) if (q == e) S = srx[p * D + q];
+        const double S = srx_at<D>(srx, p, e);
         const double N = s.P[p] - S;
         if (!(S >= 0) || !(N >= 0)) { s.fault = FAULT_REF_ASSERT; continue; }   // simple_stack.py:168-169
-        s.ber[p] = ber_bpsk_mw(S, N, P.tenLog10BitRate, P.qDen);
+        double ber;
+        if (!memo.get(S, N, ber)) {
+            ber = ber_bpsk_mw(S, N, P.tenLog10BitRate, P.qDen);
+            memo.put(S, N, ber);
+        }
+        s.ber[p] = ber;
     }
+}
+
+template <int D, int NS, int NJ>
+GW_HD void update_bers(Sim<D, NS, NJ> &s, const Params &P, int berMask, const double *srx)
+{
+    update_bers(s, P, berMask, srx, NoMemo());
 }
 
 // SimpleRrmDevice.assignFrequencyBand + SimpleRrmMac._sendAnnouncement start
@@ -675,7 +769,7 @@ GW_HD void begin_assignment(Sim<D, NS, NJ> &s, const Params &P, int device, int 
     // the RRM PHY's queued macIn executor is idle here: its previous SEND completed before
     // the previous assignment's guard time-out (simple_stack.py:557-558)
     if (s.sphase[NS] != S_IDLE) s.fault = FAULT_SENDQ;
-    for (int p = 0; p < D; ++p) if (p == NS) s.cmdPay[p] = nbytes;
+    s.cmdPay[NS] = nbytes;
     phy_send_init(s, NS);
 }
 
@@ -689,9 +783,9 @@ struct NoMasks {
 };
 
 // processes ONE timed event; `masks(receiver, sender, txseq, k0, k1, ber)` supplies mode-M counts
-template <int MODE, int D, int NS, int NJ, class Ring, class Masks>
+template <int MODE, int D, int NS, int NJ, class Ring, class Masks, class Memo>
 GW_HD void process_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const Event &ev,
-                         const double *srx, const Ring &ring, const Masks &masks)
+                         const double *srx, const Ring &ring, const Masks &masks, const Memo &memo)
 {
     int once, twice;
     s.now = ev.t;
@@ -699,6 +793,7 @@ GW_HD void process_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B
     if (MODE == MODE_R) {
         do_counts_R(s, once, twice, P.bitRate);
     } else {
+        GW_UNROLL
         for (int p = 0; p < D; ++p) {
             if (!((once >> p) & 1)) continue;
             int sender; uint32_t txseq; int64_t k0, k1;
@@ -708,30 +803,30 @@ GW_HD void process_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B
         }
     }
     const int berMask = apply_event(s, P, B, ev, srx, ring);
-    update_bers(s, P, berMask, srx);
+    update_bers(s, P, berMask, srx, memo);
 }
 
 // SimMan.runSimulation(assignSignal.eProcessed) (counter_traffic.py:155)
-template <int MODE, int D, int NS, int NJ, class Ring, class Masks>
+template <int MODE, int D, int NS, int NJ, class Ring, class Masks, class Memo = NoMemo>
 GW_HD void run_until_assign(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B,
-                            const double *srx, const Ring &ring, const Masks &masks)
+                            const double *srx, const Ring &ring, const Masks &masks, const Memo &memo = Memo())
 {
     while (!s.assignDone && !s.fault) {
-        const Event ev = select_event(s);
-        process_event<MODE>(s, P, B, ev, srx, ring, masks);
+        const Event ev = next_event(s, B, INFINITY);
+        process_event<MODE>(s, P, B, ev, srx, ring, masks, memo);
     }
 }
 
 // another band of the same env ended its assignment later, at time T: events strictly
 // before T are processed, then the clock is the env's clock
-template <int MODE, int D, int NS, int NJ, class Ring, class Masks>
+template <int MODE, int D, int NS, int NJ, class Ring, class Masks, class Memo = NoMemo>
 GW_HD void run_until_time(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const double *srx,
-                          const Ring &ring, const Masks &masks, double T)
+                          const Ring &ring, const Masks &masks, double T, const Memo &memo = Memo())
 {
     while (!s.fault) {
-        const Event ev = select_event(s);
+        const Event ev = next_event(s, B, T);
         if (!(ev.t < T)) break;
-        process_event<MODE>(s, P, B, ev, srx, ring, masks);
+        process_event<MODE>(s, P, B, ev, srx, ring, masks, memo);
     }
     s.now = T;
 }
@@ -743,6 +838,7 @@ GW_HD void run_until_time(Sim<D, NS, NJ> &s, const Params &P, const BandParams &
 template <int D, int NS, int NJ, class RingW>
 GW_HD void reset_sim(Sim<D, NS, NJ> &s, const BandParams &B, RingW &ringw)
 {
+    GW_UNROLL
     for (int k = 0; k < NS; ++k) {
         const uint64_t m = (uint64_t)B.mult[k];
         const uint64_t enq = s.ticks[k] * m;

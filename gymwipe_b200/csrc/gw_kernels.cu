@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -122,6 +123,9 @@ struct gw_handle {
     // mode M fed masks
     const uint32_t *masks;
     int mask_slots, mask_words;
+    // BER memo (shared positions only)
+    ulonglong2 *memo;
+    unsigned memo_entries;
 };
 
 // ------------------------------------------------------------------------------------
@@ -340,6 +344,43 @@ struct DevRing {
 };
 
 // ------------------------------------------------------------------------------------
+// BER memo: direct-mapped table of exact (S, N) -> BER results in device memory (L2 / L1
+// resident).  An entry is 32 bytes {S bits, N bits, BER bits, S ^ N ^ BER ^ MAGIC}; it is
+// written with two 16-byte stores and validated by the checksum, so a torn or stale read is
+// a miss, never a wrong value.  Because BER(S, N) is a pure function evaluated by the same
+// device code, a hit returns bit-for-bit what the evaluation would.
+// ------------------------------------------------------------------------------------
+
+struct DevMemo {
+    ulonglong2 *tab;        // 2 x ulonglong2 per entry
+    unsigned mask;          // entries - 1 (power of two)
+    static constexpr unsigned long long MAGIC = 0x9E3779B97F4A7C15ull;
+    __device__ __forceinline__ unsigned slot(unsigned long long a, unsigned long long b) const
+    {
+        unsigned long long h = a * 0x9E3779B97F4A7C15ull ^ (b + 0xC2B2AE3D27D4EB4Full) * 0xD6E8FEB86659FD93ull;
+        return (unsigned)(h >> 40) & mask;
+    }
+    __device__ __forceinline__ bool get(double S, double N, double &ber) const
+    {
+        if (!tab) return false;
+        const unsigned long long a = (unsigned long long)__double_as_longlong(S), b = (unsigned long long)__double_as_longlong(N);
+        const unsigned h = slot(a, b);
+        const ulonglong2 e0 = tab[2 * h], e1 = tab[2 * h + 1];
+        if (e0.x == a && e0.y == b && e1.y == (a ^ b ^ e1.x ^ MAGIC)) { ber = __longlong_as_double((long long)e1.x); return true; }
+        return false;
+    }
+    __device__ __forceinline__ void put(double S, double N, double ber) const
+    {
+        if (!tab) return;
+        const unsigned long long a = (unsigned long long)__double_as_longlong(S), b = (unsigned long long)__double_as_longlong(N);
+        const unsigned long long c = (unsigned long long)__double_as_longlong(ber);
+        const unsigned h = slot(a, b);
+        tab[2 * h] = make_ulonglong2(a, b);
+        tab[2 * h + 1] = make_ulonglong2(c, a ^ b ^ c ^ MAGIC);
+    }
+};
+
+// ------------------------------------------------------------------------------------
 // mode M: warp-cooperative error counting (bit-error masks)
 // ------------------------------------------------------------------------------------
 
@@ -415,14 +456,19 @@ struct StepArgs {
     double *stats;
     int *errflag;
     MaskSource masks;
+    DevMemo memo;
 };
 
 struct SharedTables {
     double srx[kMaxBands][16];
 };
 
+#ifndef GW_STEP_MIN_BLOCKS
+#define GW_STEP_MIN_BLOCKS 4
+#endif
+
 template <int MODE, int D, int NS, int NJ>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, GW_STEP_MIN_BLOCKS)
 step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P,
             const __grid_constant__ SharedTables T)
 {
@@ -475,13 +521,13 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         const uint32_t ties0 = active ? s.ties : 0;
 
         if (MODE == MODE_R) {
-            if (active) run_until_assign<MODE_R>(s, P, B, srx, ring, NoMasks());
+            if (active) run_until_assign<MODE_R>(s, P, B, srx, ring, NoMasks(), A.memo);
             if (nb > 1) {
                 // SimMan.runSimulation for every band's ASSIGN message: the env's clock ends
                 // at the latest band; the other bands keep simulating up to that time
                 double Tend = active ? s.now : -INFINITY;
                 for (int o = 1; o < nb; o <<= 1) Tend = fmax(Tend, __shfl_xor_sync(0xFFFFFFFFu, Tend, o));
-                if (active && s.now < Tend) run_until_time<MODE_R>(s, P, B, srx, ring, NoMasks(), Tend);
+                if (active && s.now < Tend) run_until_time<MODE_R>(s, P, B, srx, ring, NoMasks(), Tend, A.memo);
             }
         } else {
             // warp-synchronous event loop: one timed event per lane and iteration; the error
@@ -489,12 +535,12 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
             double Tend = INFINITY;
             int phase = 0;      // 0: until the own ASSIGN is processed, 1: until Tend
             for (;;) {
-                Event ev; ev.kind = EV_NONE; ev.idx = 0; ev.t = 0;
+                Event ev; ev.kind = EV_NONE; ev.idx = 0; ev.t = 0; ev.seq = 0;
                 bool run = active && !s.fault;
                 if (run) {
                     if (phase == 0) run = !s.assignDone;
                     if (run || phase == 1) {
-                        ev = select_event(s);
+                        ev = next_event(s, B, phase == 0 ? (double)INFINITY : Tend);
                         run = phase == 0 ? true : (ev.t < Tend);
                     }
                 }
@@ -526,8 +572,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
                         int sender = 0; uint32_t txseq = 0; int64_t k0 = 0, k1 = 0; double berp = 0;
                         if (lane == src) {
                             mask_range(s, p, P.bitRate, sender, txseq, k0, k1);
-#pragma unroll
-                            for (int q = 0; q < D; ++q) if (q == p) berp = s.ber[q];
+                            berp = get_at(s.ber, p);
                         }
                         sender = __shfl_sync(0xFFFFFFFFu, sender, src);
                         txseq = __shfl_sync(0xFFFFFFFFu, txseq, src);
@@ -547,14 +592,14 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
                                                     ik0, ik1, thr, lane);
                         }
                         if (lane == src) {
-#pragma unroll
-                            for (int q = 0; q < D; ++q) if (q == p) { s.err[q] += (double)cnt; s.segT0[q] = s.now; }
+                            set_at(s.err, p, get_at(s.err, p) + (double)cnt);
+                            set_at(s.segT0, p, s.now);
                         }
                     }
                 }
                 if (run) {
                     const int berMask = apply_event(s, P, B, ev, srx, ring);
-                    update_bers(s, P, berMask, srx);
+                    update_bers(s, P, berMask, srx, A.memo);
                 }
             }
             if (active && nb > 1) s.now = Tend;
@@ -957,6 +1002,13 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
     if (e == cudaSuccess) e = cudaMemsetAsync(h->stats, 0, aux, s);
     if (e == cudaSuccess) e = cudaMalloc(&stg, nsim * (4 + 4 + 8 + 8 + 1) + 64);
     if (e != cudaSuccess) { gw_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
+    if (ntab == 1 && !std::getenv("GYMWIPE_B200_NO_MEMO")) {
+        // identical geometry in every env: a small table holds every (S, N) pair that occurs
+        h->memo_entries = 1u << 14;
+        e = cudaMalloc((void **)&h->memo, 32ull * h->memo_entries);
+        if (e == cudaSuccess) e = cudaMemsetAsync(h->memo, 0, 32ull * h->memo_entries, s);
+        if (e != cudaSuccess) { cudaFree(stg); gw_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
+    }
     h->errflag = (int *)(h->stats + 8);
     h->d_obs = (long long *)stg;                            // base of the staging allocation
     h->d_rew = (double *)(h->d_obs + nsim);
@@ -984,6 +1036,7 @@ void gw_destroy(gw_handle *h)
     if (h->owned_state) cudaFree(h->owned_state);
     if (h->stats) cudaFree(h->stats);
     if (h->d_obs) cudaFree(h->d_obs);       // base of the staging allocation
+    if (h->memo) cudaFree(h->memo);
     delete h;
 }
 
@@ -1020,6 +1073,7 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     A.stats = h->stats; A.errflag = h->errflag;
     A.masks.mode = h->cfg.mode; A.masks.seed = h->cfg.seed; A.masks.env_offset = h->cfg.env_id_offset;
     A.masks.words = h->masks; A.masks.slots = h->mask_slots > 0 ? h->mask_slots : 1; A.masks.words_per_row = h->mask_words;
+    A.memo.tab = h->memo; A.memo.mask = h->memo_entries ? h->memo_entries - 1 : 0;
     SharedTables T;
     std::memset(&T, 0, sizeof T);
     if (h->st.ntab == 1) {

@@ -127,10 +127,10 @@ def test_k3_count_bit_errors_kernel():
     want = cs[ridx, k1] - cs[ridx, k0]
     dm = torch.as_tensor(m.view(np.int32)).cuda()
     out = torch.zeros(n, dtype=torch.int32, device="cuda")
-    N.check(N.lib().gw_count_bit_errors(dm.data_ptr(), words, torch.as_tensor(ridx).cuda().data_ptr(),
-                                        torch.as_tensor(k0).cuda().data_ptr(), torch.as_tensor(k1).cuda().data_ptr(),
+    d_rows, d_k0, d_k1 = torch.as_tensor(ridx).cuda(), torch.as_tensor(k0).cuda(), torch.as_tensor(k1).cuda()
+    N.check(N.lib().gw_count_bit_errors(dm.data_ptr(), words, d_rows.data_ptr(), d_k0.data_ptr(), d_k1.data_ptr(),
                                         out.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
-    assert (out.cpu().numpy() == want).all()
+    assert (out.cpu().numpy().astype(np.int64) == want.astype(np.int64)).all()
 
 
 def test_philox_known_answers_device():
