@@ -32,6 +32,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 ENVS_PER_GPU = 65536
 ALGO_BYTES_PER_ENV_STEP = 193          # SURVEY.md section 8d / DESIGN.md section 6
+STATS_EVERY = 8                        # steps between two NCCL reductions of the statistics vector
 METRIC = "env-steps/sec CounterTrafficEnv batch"
 UNIT = "env-steps/s"
 
@@ -65,26 +66,37 @@ def ncu_traffic_per_launch():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).
+    The sampler is started before the warm-up (nvidia-smi needs ~0.1 s to come up); samples are
+    kept if their timestamp falls inside [mark_begin, mark_end] -- the timed loop."""
 
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
+        self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=self.file, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -92,28 +104,118 @@ class ClockSampler:
             self.proc.kill()
         self.file.flush()
         self.file.seek(0)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.file.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
+            if len(parts) < 10:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[2]), float(parts[3]),
+                             [nm for nm, v in zip(names, parts[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         try:
             os.unlink(self.file.name)
         except OSError:
             pass
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        window = "timed loop"
+        if not inside:
+            inside, window = rows, "warm-up + timed loop (the timed loop is shorter than the sampling period)"
+        if inside:
+            sm = sorted(r[1] for r in inside)
+            reasons = sorted({x for r in inside for x in r[3]})
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(r[2] for r in inside), reasons=reasons,
+                       samples=len(inside), window=window)
         return out
+
+
+def mask_scan_roofline(dev_t, peak):
+    """
+    K3, the HBM-bound kernel of the path (mode M accounting over fed masks): streaming popcount of
+    1 Mi mask rows of 2 KiB (one 1525-byte packet as seen by one receiver: 16 267 on-air bits),
+    2 GiB in total -- far larger than the 126 MB L2, so every launch streams from HBM.
+    """
+    import torch
+    from gymwipe_b200 import _native as N
+    rows, words = 1 << 20, 512
+    nbits = 16267
+    masks = torch.randint(-2 ** 31, 2 ** 31 - 1, (rows, words), dtype=torch.int32, device=dev_t)
+    ridx = torch.randperm(rows, device=dev_t).to(torch.int64)
+    k0 = torch.zeros(rows, dtype=torch.int32, device=dev_t)
+    k1 = torch.full((rows,), nbits, dtype=torch.int32, device=dev_t)
+    out = torch.empty(rows, dtype=torch.int32, device=dev_t)
+    stream = torch.cuda.current_stream(dev_t)
+    lib = N.lib()
+
+    def launch():
+        N.check(lib.gw_count_bit_errors(masks.data_ptr(), words, ridx.data_ptr(), k0.data_ptr(), k1.data_ptr(),
+                                        out.data_ptr(), rows, stream.cuda_stream))
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize(dev_t)
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        launch()
+    e1.record(stream)
+    torch.cuda.synchronize(dev_t)
+    ms = e0.elapsed_time(e1) / reps
+    algo = rows * ((nbits + 7) // 8 + 8 + 4 + 4 + 4)       # mask bytes + descriptor (row, k0, k1) + count
+    achieved = algo / (ms * 1e-3) / 1e9
+    check = int(out[:1024].sum())
+    del masks
+    return {"kernel": "count_bits_kernel (gw_count_bit_errors)", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "rows": rows, "bits_per_row": nbits,
+            "algorithmic_bytes_per_launch": algo, "avg_launch_ms": ms, "input": "2 GiB of masks (> L2), random row order",
+            "checksum_first_1024": check}
+
+
+def cfg3_long_packet(dev_t, steps=24):
+    """
+    BASELINE configs[2]: 1500-byte payloads, fed per-bit masks, a PHY-only interferer creating
+    mid-packet SINR segments; ASSIGNMENT_DURATION_FACTOR = 10000 so that windows fit 122 ms packets.
+    """
+    import torch
+    import gymwipe_b200
+    n, slots, words = 16384, 2, 512
+    sc = {"assignment_duration_factor": 10000, "bands": [{"frequency": 2.4e9, "bandwidth": 22e6, "devices": [
+        {"role": "sender", "x": 0.0, "y": 2.0, "mult": 1, "payload": 1500, "interval": 0.001, "dest": 1},
+        {"role": "sender", "x": 0.0, "y": -2.0, "mult": 3, "payload": 1500, "interval": 0.001, "dest": 0},
+        {"role": "rrm", "x": 0.0, "y": 0.0},
+        {"role": "jammer", "x": 6.0, "y": 0.0, "interval": 0.05, "delay": 0.003, "power": 0.0, "hdr": 13, "payload": 200}]}]}
+    env = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, scenario=sc, mode="mask_fed", strict=False)
+    # Bernoulli(0.02) masks: 1 GiB, resident before the timed region
+    masks = (torch.rand((n, 1, 4, slots, 4, words), device=dev_t) < 0.5).to(torch.int32)
+    masks = torch.randint(-2 ** 31, 2 ** 31 - 1, masks.shape, dtype=torch.int32, device=dev_t) & \
+        torch.randint(-2 ** 31, 2 ** 31 - 1, masks.shape, dtype=torch.int32, device=dev_t) & \
+        torch.randint(-2 ** 31, 2 ** 31 - 1, masks.shape, dtype=torch.int32, device=dev_t) & \
+        torch.randint(-2 ** 31, 2 ** 31 - 1, masks.shape, dtype=torch.int32, device=dev_t)     # density 1/16
+    env.set_masks(masks, slots)
+    env.reset()
+    g = torch.Generator(device=dev_t).manual_seed(7)
+    a_dev = torch.randint(0, 2, (steps + 4, n), generator=g, device=dev_t, dtype=torch.int32)
+    a_dur = torch.randint(12, 20, (steps + 4, n), generator=g, device=dev_t, dtype=torch.int32)
+    stream = torch.cuda.current_stream(dev_t)
+    for t in range(4):
+        env.step({"device": a_dev[t], "duration": a_dur[t]})
+    env.stats()
+    torch.cuda.synchronize(dev_t)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(4, steps + 4):
+        env.step({"device": a_dev[t], "duration": a_dur[t]})
+    e1.record(stream)
+    torch.cuda.synchronize(dev_t)
+    env.check()
+    st = env.stats().cpu().numpy()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": "configs[2]: 1500-byte payloads, fed per-bit masks (mode M), PHY-only interferer, %d envs" % n,
+            "env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "transmissions_per_step": float(st[6]) / steps,
+            "deliveries_per_step": float(st[1] + st[2]) / steps, "mask_bytes_resident": int(masks.numel() * 4)}
 
 
 def cpu_baseline_run(target_seconds, threads=None):
@@ -214,14 +316,17 @@ def own_arm(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_t)
     reducer = StatsReducer(dev_t) if world > 1 else None
     stream = torch.cuda.current_stream(dev_t)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
 
     def one_step(t, timed):
         flush.zero_()                                   # L2 flush, outside the timed span
         if timed is not None:
             timed[0].record(stream)
         env.step({"device": a_dev[t], "duration": a_dur[t]})
-        if reducer is not None:
-            reducer.submit(env.stats())                 # K5 partials -> NCCL all-reduce on a side stream
+        if reducer is not None and (t + 1) % STATS_EVERY == 0:
+            # K5 partial sums of the last STATS_EVERY steps -> NCCL all-reduce on a side stream
+            env.stats(out=reducer.next_slot())
+            reducer.submit()
         if timed is not None:
             timed[1].record(stream)
 
@@ -230,8 +335,9 @@ def own_arm(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev_t)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    if sampler is not None:
+        sampler.mark_begin()
     wall0 = time.perf_counter()
     for k in range(K):
         one_step(W + k, evs[k])
@@ -239,6 +345,8 @@ def own_arm(args, rank, world, local_rank):
         dist.barrier()
     torch.cuda.synchronize(dev_t)
     wall = time.perf_counter() - wall0
+    if sampler is not None:
+        sampler.mark_end()
     clocks = sampler.stop() if sampler is not None else None
     env.check()
     if reducer is not None:
@@ -298,8 +406,8 @@ def own_arm(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": config_dict(total_envs, "dp%d (independent env shards, no data-path collective; per-step NCCL "
-                              "all-reduce of the 64-byte statistics vector on a side stream)" % world if world > 1
+        "config": config_dict(total_envs, "dp%d (independent env shards, no data-path collective; NCCL all-reduce of the 64-byte "
+                              "statistics vector every %d steps on a side stream)" % (world, STATS_EVERY) if world > 1
                               else "single GPU",
                               "steps %d..%d from a fresh env: productive regime (~first 100 steps, packets delivered) "
                               "then the reference's degenerate regime (announcements only)" % (W, W + K)),
@@ -319,6 +427,15 @@ def own_arm(args, rank, world, local_rank):
         "clocks": clocks,
         "wall_s_timed_loop": wall,
     }
+    if world == 1 and not args.no_extras:
+        del flush, env2
+        torch.cuda.empty_cache()
+        try:
+            line["mask_scan"] = mask_scan_roofline(dev_t, peak)
+            torch.cuda.empty_cache()
+            line["cfg3_long_packet_mode_m"] = cfg3_long_packet(dev_t)
+        except Exception as exc:                      # extras must never take the headline down
+            line["extras_error"] = repr(exc)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_run(args.cpu_seconds)
     print(json.dumps(line))
@@ -333,6 +450,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the mask-scan roofline and the cfg-3 run")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -401,6 +401,7 @@ __device__ __forceinline__ int warp_popc_range(const uint32_t *row, int k0, int 
         const int w0 = k0 >> 5, w1 = (k1 - 1) >> 5;     // first / last word
         const int q0 = w0 >> 2, q1 = w1 >> 2;           // 16-byte groups
         const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
+#pragma unroll 4
         for (int q = q0 + lane; q <= q1; q += 32) {
             const uint4 v = __ldg(row4 + q);
             const unsigned w[4] = {v.x, v.y, v.z, v.w};

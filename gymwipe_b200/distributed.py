@@ -59,10 +59,16 @@ class StatsReducer:
         self.cuda = self.device.type == "cuda"
         self.side = torch.cuda.Stream(device=self.device) if self.cuda else None
 
-    def submit(self, local_stats):
+    def next_slot(self):
+        """The tensor the next statistics vector should be written into (no extra copy)."""
+        return self.buf[self.head % self.depth]
+
+    def submit(self, local_stats=None):
+        """Queue the all-reduce of ``local_stats`` (or of the slot from :meth:`next_slot`)."""
         slot = self.buf[self.head % self.depth]
         self.head += 1
-        slot.copy_(local_stats, non_blocking=True)
+        if local_stats is not None and local_stats.data_ptr() != slot.data_ptr():
+            slot.copy_(local_stats, non_blocking=True)
         work, ev = None, None
         if self.world > 1:
             if self.cuda:

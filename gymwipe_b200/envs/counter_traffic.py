@@ -257,11 +257,16 @@ class CounterTrafficEnv(BaseEnv):
     def transmissions(self):
         return self.read_state(N.GW_FIELD_N_TRANSMISSIONS)[0].to(torch.int64)
 
-    def stats(self, clear=True):
-        """Statistics reduced by the step kernel's epilogue since the last call (float64[8], device)."""
+    def stats(self, clear=True, out=None):
+        """
+        Statistics accumulated by the step kernel's epilogue since the last clearing call
+        (float64[8] on the device, see ``gw_stats``); ``out`` lets the caller supply the tensor
+        (e.g. the all-reduce buffer of ``gymwipe_b200.distributed.StatsReducer``).
+        """
+        out = self._stats_out if out is None else out
         with torch.cuda.device(self.device):
-            N.check(self._lib.gw_stats(self._handle, self._stats_out.data_ptr(), 1 if clear else 0, self._stream()))
-        return self._stats_out
+            N.check(self._lib.gw_stats(self._handle, out.data_ptr(), 1 if clear else 0, self._stream()))
+        return out
 
     def set_positions(self, positions):
         """Per-env device positions ``[num_envs, n_bands, 4, 2]`` (float64, CUDA)."""
