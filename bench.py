@@ -132,7 +132,7 @@ class ClockSampler:
         return out
 
 
-def mask_scan_roofline(dev_t, peak):
+def mask_scan_roofline(dev_t, peak, order="random"):
     """
     K3, the HBM-bound kernel of the path (mode M accounting over fed masks): streaming popcount of
     1 Mi mask rows of 2 KiB (one 1525-byte packet as seen by one receiver: 16 267 on-air bits),
@@ -143,7 +143,8 @@ def mask_scan_roofline(dev_t, peak):
     rows, words = 1 << 20, 512
     nbits = 16267
     masks = torch.randint(-2 ** 31, 2 ** 31 - 1, (rows, words), dtype=torch.int32, device=dev_t)
-    ridx = torch.randperm(rows, device=dev_t).to(torch.int64)
+    ridx = torch.randperm(rows, device=dev_t).to(torch.int64) if order == "random" else \
+        torch.arange(rows, device=dev_t, dtype=torch.int64)
     k0 = torch.zeros(rows, dtype=torch.int32, device=dev_t)
     k1 = torch.full((rows,), nbits, dtype=torch.int32, device=dev_t)
     out = torch.empty(rows, dtype=torch.int32, device=dev_t)
@@ -170,7 +171,7 @@ def mask_scan_roofline(dev_t, peak):
     del masks
     return {"kernel": "count_bits_kernel (gw_count_bit_errors)", "bound": "hbm", "achieved": achieved, "peak": peak,
             "unit": "GB/s", "frac": achieved / peak, "rows": rows, "bits_per_row": nbits,
-            "algorithmic_bytes_per_launch": algo, "avg_launch_ms": ms, "input": "2 GiB of masks (> L2), random row order",
+            "algorithmic_bytes_per_launch": algo, "avg_launch_ms": ms, "input": "2 GiB of masks (> L2), %s row order" % order,
             "checksum_first_1024": check}
 
 
@@ -431,7 +432,9 @@ def own_arm(args, rank, world, local_rank):
         del flush, env2
         torch.cuda.empty_cache()
         try:
-            line["mask_scan"] = mask_scan_roofline(dev_t, peak)
+            line["mask_scan"] = mask_scan_roofline(dev_t, peak, "random")
+            torch.cuda.empty_cache()
+            line["mask_scan_sequential_rows"] = mask_scan_roofline(dev_t, peak, "sequential")
             torch.cuda.empty_cache()
             line["cfg3_long_packet_mode_m"] = cfg3_long_packet(dev_t)
         except Exception as exc:                      # extras must never take the headline down

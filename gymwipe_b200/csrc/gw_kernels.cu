@@ -393,27 +393,52 @@ struct MaskSource {
 };
 
 // number of set bits among bits [k0, k1) of a row of 32-bit words; all 32 lanes cooperate,
-// 128-bit loads, result valid in every lane
+// 128-bit streaming loads issued four at a time per lane (2 KiB of a row in flight per warp),
+// result valid in every lane.  Interior 128-bit groups are counted unmasked (4 POPC); only the
+// first and the last group of the range get a prefix / suffix correction.
+#ifndef GW_MASK_LOAD
+#define GW_MASK_LOAD __ldcs
+#endif
+
+__device__ __forceinline__ int popc4(uint4 v) { return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
+
+// set bits among the first r bits (0 <= r <= 128) of a 128-bit group
+__device__ __forceinline__ int popc_prefix(uint4 v, int r)
+{
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int b = r - 32 * j;
+        const unsigned m = b >= 32 ? 0xFFFFFFFFu : (b <= 0 ? 0u : (0xFFFFFFFFu >> (32 - b)));
+        n += __popc(w[j] & m);
+    }
+    return n;
+}
+
+// contribution of group g (content v) to the count of bits [k0, k1); q0 / q1 = first / last group
+__device__ __forceinline__ int popc_group(uint4 v, int g, int q0, int q1, int k0, int k1)
+{
+    int n = popc4(v);
+    if (g == q0) n -= popc_prefix(v, k0 - q0 * 128);
+    if (g == q1) n -= popc4(v) - popc_prefix(v, k1 - q1 * 128);
+    return n;
+}
+
 __device__ __forceinline__ int warp_popc_range(const uint32_t *row, int k0, int k1, int lane)
 {
     int n = 0;
     if (k1 > k0) {
-        const int w0 = k0 >> 5, w1 = (k1 - 1) >> 5;     // first / last word
-        const int q0 = w0 >> 2, q1 = w1 >> 2;           // 16-byte groups
+        const int q0 = k0 >> 7, q1 = (k1 - 1) >> 7;     // first / last 16-byte group
         const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
-#pragma unroll 4
-        for (int q = q0 + lane; q <= q1; q += 32) {
-            const uint4 v = __ldg(row4 + q);
-            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+        for (int q = q0 + lane; q <= q1; q += 128) {
+            uint4 v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int wi = q * 4 + j;
-                unsigned m = w[j];
-                if (wi < w0 || wi > w1) m = 0;
-                if (wi == w0) m &= 0xFFFFFFFFu << (k0 & 31);
-                if (wi == w1 && ((k1 & 31) != 0)) m &= 0xFFFFFFFFu >> (32 - (k1 & 31));
-                n += __popc(m);
-            }
+            for (int u = 0; u < 4; ++u)
+                v[u] = (q + 32 * u <= q1) ? GW_MASK_LOAD(row4 + q + 32 * u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (q + 32 * u <= q1) n += popc_group(v[u], q + 32 * u, q0, q1, k0, k1);
         }
     }
 #pragma unroll
@@ -762,7 +787,8 @@ __global__ void ber_kernel(const double *S, const double *N, double *ber, long l
     if (i < n) ber[i] = ber_bpsk_mw(S[i], N[i], c, qDen);
 }
 
-// K3: one warp per descriptor, grid-stride; 128-bit loads, popc, shuffle reduction
+// K3: one warp per descriptor, grid-stride, software-pipelined: the descriptor of the next
+// row is loaded while the current row is scanned; 128-bit streaming loads, popc, shuffle reduction
 __global__ void __launch_bounds__(256)
 count_bits_kernel(const uint32_t *words, int words_per_row, const long long *rows, const int *k0, const int *k1,
                   int *counts, long long n)
@@ -770,9 +796,137 @@ count_bits_kernel(const uint32_t *words, int words_per_row, const long long *row
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long i = warp; i < n; i += nwarps) {
-        const int c = warp_popc_range(words + rows[i] * words_per_row, k0[i], k1[i], lane);
+    long long i = warp, r = 0;
+    int a0 = 0, a1 = 0;
+    if (i < n) { a0 = __ldg(k0 + i); a1 = __ldg(k1 + i); r = __ldg(rows + i); }
+    while (i < n) {
+        const long long inext = i + nwarps;
+        long long rn = 0;
+        int b0 = 0, b1 = 0;
+        if (inext < n) { b0 = __ldg(k0 + inext); b1 = __ldg(k1 + inext); rn = __ldg(rows + inext); }
+        const int c = warp_popc_range(words + r * words_per_row, a0, a1, lane);
         if (lane == 0) counts[i] = c;
+        i = inext; a0 = b0; a1 = b1; r = rn;
+    }
+}
+
+// K3, TMA variant: every warp runs its own 4-deep ring of 2 KiB shared-memory stages that are
+// filled by 1-D bulk async copies (cp.async.bulk, SASS UBLKCP) completing on mbarriers, so a warp
+// keeps up to 8 KiB of mask rows in flight without holding them in registers; the popcount
+// reads shared memory.  Rows longer than one stage are processed in 2 KiB pieces.
+namespace tma {
+constexpr int STAGES = 4;
+constexpr int WARPS = 8;
+constexpr int STAGE_BYTES = 2048;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}  // namespace tma
+
+constexpr int TMA_SMEM_BYTES = tma::WARPS * tma::STAGES * (tma::STAGE_BYTES + 8 + 16);
+
+__global__ void __launch_bounds__(256)
+count_bits_tma_kernel(const uint32_t *words, int words_per_row, const long long *rows, const int *k0, const int *k1,
+                      int *counts, long long n)
+{
+    using namespace tma;
+    extern __shared__ __align__(128) unsigned char tma_smem[];
+    typedef uint4 StageBuf[STAGES][STAGE_BYTES / 16];
+    StageBuf *buf = reinterpret_cast<StageBuf *>(tma_smem);                                   // [WARPS]
+    typedef unsigned long long BarRow[STAGES];
+    BarRow *bars = reinterpret_cast<BarRow *>(tma_smem + WARPS * STAGES * STAGE_BYTES);       // [WARPS]
+    typedef int MetaRow[STAGES][4];                 // k0, k1 (relative to the staged span), valid bytes, -
+    MetaRow *meta = reinterpret_cast<MetaRow *>(tma_smem + WARPS * STAGES * STAGE_BYTES + WARPS * STAGES * 8);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long warp = (long long)blockIdx.x * WARPS + w;
+    const long long nwarps = (long long)gridDim.x * WARPS;
+    if (lane == 0)
+        for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(&bars[w][s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+
+    // rows of this warp: warp, warp + nwarps, ...  (this kernel handles rows that fit one stage;
+    // the host falls back to the register variant otherwise)
+    const long long mine = warp < n ? (n - warp + nwarps - 1) / nwarps : 0;
+
+    // lane 0 issues the copies; the descriptor of the NEXT row to issue is prefetched into
+    // registers one iteration ahead so that its load latency is off the critical path
+    int d0 = 0, d1 = 0;
+    long long drow = 0;
+    auto fetch = [&](long long j) {
+        if (j < mine) {
+            const long long i = warp + j * nwarps;
+            d0 = __ldg(k0 + i); d1 = __ldg(k1 + i); drow = __ldg(rows + i);
+        }
+    };
+    auto issue = [&](long long j) {                 // uses (d0, d1, drow) fetched for row j
+        const int s = (int)(j % STAGES);
+        const int a0 = d0, a1 = d1;
+        const long long row = drow;
+        fetch(j + 1);
+        const unsigned bar = smem_u32(&bars[w][s]);
+        if (a1 > a0) {
+            const int q0 = (a0 >> 5) >> 2, q1 = ((a1 - 1) >> 5) >> 2;
+            const unsigned bytes = (unsigned)(q1 - q0 + 1) * 16u;
+            const uint32_t *src = words + row * words_per_row + q0 * 4;
+            meta[w][s][0] = a0 - q0 * 128; meta[w][s][1] = a1 - q0 * 128; meta[w][s][2] = (int)bytes;
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(smem_u32(&buf[w][s][0]), src, bytes, bar);
+        } else {
+            meta[w][s][0] = 0; meta[w][s][1] = 0; meta[w][s][2] = 0;
+            mbar_expect_tx(bar, 0);
+        }
+    };
+
+    if (lane == 0) {
+        fetch(0);
+        for (long long j = 0; j < mine && j < STAGES; ++j) issue(j);
+    }
+
+    for (long long j = 0; j < mine; ++j) {
+        const int s = (int)(j % STAGES);
+        const unsigned parity = (unsigned)((j / STAGES) & 1);
+        mbar_wait(smem_u32(&bars[w][s]), parity);
+        const int r0 = meta[w][s][0], r1 = meta[w][s][1];
+        int cnt = 0;
+        if (r1 > r0) {
+            const int q1 = (r1 - 1) >> 7;               // the staged span starts at group 0
+#pragma unroll 4
+            for (int q = lane; q <= q1; q += 32) cnt += popc_group(buf[w][s][q], q, 0, q1, r0, r1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        if (lane == 0) counts[warp + j * nwarps] = cnt;
+        __syncwarp();                               // every lane is done reading this stage
+        if (lane == 0 && j + STAGES < mine) {
+            fence_async_proxy();                    // generic-proxy reads before the async-proxy refill
+            issue(j + STAGES);
+        }
     }
 }
 
@@ -1208,10 +1362,28 @@ int gw_count_bit_errors(const uint32_t *mask_words, int32_t words_per_row, const
 {
     if (n <= 0) return GW_OK;
     if (words_per_row < 4 || (words_per_row & 3) || ((uintptr_t)mask_words & 15)) return fail(GW_E_INVALID, "bad mask layout");
-    // persistent grid: 148 SMs x 8 blocks of 8 warps
+    cudaStream_t st = (cudaStream_t)stream;
+    static int sms = 0, occ_reg = 0, occ_tma = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_reg, count_bits_kernel, 256, 0) != cudaSuccess || occ_reg < 1) occ_reg = 6;
+        cudaFuncSetAttribute(count_bits_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tma, count_bits_tma_kernel, 256, TMA_SMEM_BYTES) != cudaSuccess || occ_tma < 1) occ_tma = 3;
+        if (sms < 1) sms = 148;
+    }
+    // persistent grid: one full wave (SM count x resident blocks per SM), 8 warps per block.
+    // Rows that fit one 2 KiB stage take the TMA-staged kernel (unless GYMWIPE_B200_K3=reg).
+    static const char *force = std::getenv("GYMWIPE_B200_K3");
+    const bool use_tma = words_per_row * 4 <= tma::STAGE_BYTES && !(force && force[0] == 'r');
     long long blocks = (n + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    count_bits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(mask_words, words_per_row, (const long long *)rows, k0, k1, counts, n);
+    const long long wave = (long long)sms * (use_tma ? occ_tma : occ_reg);
+    if (blocks > wave) blocks = wave;
+    if (use_tma)
+        count_bits_tma_kernel<<<(int)blocks, 256, TMA_SMEM_BYTES, st>>>(mask_words, words_per_row, (const long long *)rows, k0, k1, counts, n);
+    else
+        count_bits_kernel<<<(int)blocks, 256, 0, st>>>(mask_words, words_per_row, (const long long *)rows, k0, k1, counts, n);
     CUDA_TRY(cudaGetLastError());
     return GW_OK;
 }
