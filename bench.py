@@ -182,19 +182,18 @@ def cfg3_long_packet(dev_t, steps=24):
     """
     import torch
     import gymwipe_b200
-    n, slots, words = 16384, 2, 512
+    n, slots, words = 65536, 2, 512
     sc = {"assignment_duration_factor": 10000, "bands": [{"frequency": 2.4e9, "bandwidth": 22e6, "devices": [
         {"role": "sender", "x": 0.0, "y": 2.0, "mult": 1, "payload": 1500, "interval": 0.001, "dest": 1},
         {"role": "sender", "x": 0.0, "y": -2.0, "mult": 3, "payload": 1500, "interval": 0.001, "dest": 0},
         {"role": "rrm", "x": 0.0, "y": 0.0},
         {"role": "jammer", "x": 6.0, "y": 0.0, "interval": 0.05, "delay": 0.003, "power": 0.0, "hdr": 13, "payload": 200}]}]}
     env = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, scenario=sc, mode="mask_fed", strict=False)
-    # Bernoulli(0.02) masks: 1 GiB, resident before the timed region
-    masks = (torch.rand((n, 1, 4, slots, 4, words), device=dev_t) < 0.5).to(torch.int32)
-    masks = torch.randint(-2 ** 31, 2 ** 31 - 1, masks.shape, dtype=torch.int32, device=dev_t) & \
-        torch.randint(-2 ** 31, 2 ** 31 - 1, masks.shape, dtype=torch.int32, device=dev_t) & \
-        torch.randint(-2 ** 31, 2 ** 31 - 1, masks.shape, dtype=torch.int32, device=dev_t) & \
-        torch.randint(-2 ** 31, 2 ** 31 - 1, masks.shape, dtype=torch.int32, device=dev_t)     # density 1/16
+    # Bernoulli(1/16) masks: 4 GiB, resident before the timed region
+    shape = (n, 1, 4, slots, 4, words)
+    masks = torch.randint(-2 ** 31, 2 ** 31 - 1, shape, dtype=torch.int32, device=dev_t)
+    for _ in range(3):                                  # AND of 4 random words: bit density 1/16
+        masks &= torch.randint(-2 ** 31, 2 ** 31 - 1, shape, dtype=torch.int32, device=dev_t)
     env.set_masks(masks, slots)
     env.reset()
     g = torch.Generator(device=dev_t).manual_seed(7)
@@ -217,6 +216,49 @@ def cfg3_long_packet(dev_t, steps=24):
     return {"workload": "configs[2]: 1500-byte payloads, fed per-bit masks (mode M), PHY-only interferer, %d envs" % n,
             "env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "transmissions_per_step": float(st[6]) / steps,
             "deliveries_per_step": float(st[1] + st[2]) / steps, "mask_bytes_resident": int(masks.numel() * 4)}
+
+
+def cfg4_multiband(dev_t, steps=64):
+    """
+    BASELINE configs[3] on ONE GPU's share: 16 devices over 4 FrequencyBands (per band: RRM + 2 MAC
+    senders + 1 PHY-only interferer), positions ~U(-20, 20) m per env, one action per band; the env's
+    clock ends at the latest band (mode R).  131 072 envs x 4 bands = 524 288 band-sims.
+    """
+    import torch
+    import gymwipe_b200
+    n = 131072
+    bands = []
+    for b in range(4):
+        bands.append({"frequency": 2.4e9 + b * 25e6, "bandwidth": 22e6, "devices": [
+            {"role": "sender", "x": 0.0, "y": 2.0, "mult": 1, "payload": "counter", "interval": 0.001, "dest": 1},
+            {"role": "sender", "x": 0.0, "y": -2.0, "mult": 3, "payload": "counter", "interval": 0.001, "dest": 0},
+            {"role": "rrm", "x": 0.0, "y": 0.0},
+            {"role": "jammer", "x": 5.0, "y": 5.0, "interval": 0.013 + 0.002 * b, "delay": 0.001 * b, "power": 10.0,
+             "hdr": 13, "payload": 60}]})
+    sc = {"assignment_duration_factor": 1000, "bands": bands}
+    g = torch.Generator(device=dev_t).manual_seed(11)
+    pos = (torch.rand((n, 4, 4, 2), generator=g, device=dev_t, dtype=torch.float64) * 40.0 - 20.0)
+    env = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, scenario=sc, positions=pos, strict=False)
+    env.reset()
+    a_dev = torch.randint(0, 2, (steps + 4, n, 4), generator=g, device=dev_t, dtype=torch.int32)
+    a_dur = torch.randint(0, 20, (steps + 4, n, 4), generator=g, device=dev_t, dtype=torch.int32)
+    stream = torch.cuda.current_stream(dev_t)
+    for t in range(4):
+        env.step({"device": a_dev[t], "duration": a_dur[t]})
+    env.stats()
+    torch.cuda.synchronize(dev_t)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(4, steps + 4):
+        env.step({"device": a_dev[t], "duration": a_dur[t]})
+    e1.record(stream)
+    torch.cuda.synchronize(dev_t)
+    env.check()
+    st = env.stats().cpu().numpy()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": "configs[3] share of one GPU: %d envs x 4 bands x 4 devices, per-env positions, mode R" % n,
+            "env_steps_per_s": n / (ms * 1e-3), "band_steps_per_s": 4 * n / (ms * 1e-3), "ms_per_step": ms,
+            "transmissions_per_env_step": float(st[6]) / steps / n, "deliveries_per_env_step": float(st[1] + st[2]) / steps / n}
 
 
 def cpu_baseline_run(target_seconds, threads=None):
@@ -437,6 +479,8 @@ def own_arm(args, rank, world, local_rank):
             line["mask_scan_sequential_rows"] = mask_scan_roofline(dev_t, peak, "sequential")
             torch.cuda.empty_cache()
             line["cfg3_long_packet_mode_m"] = cfg3_long_packet(dev_t)
+            torch.cuda.empty_cache()
+            line["cfg4_multiband"] = cfg4_multiband(dev_t)
         except Exception as exc:                      # extras must never take the headline down
             line["extras_error"] = repr(exc)
     if world == 1 and not args.no_cpu_baseline:

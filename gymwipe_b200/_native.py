@@ -24,7 +24,8 @@ GW_MODE_REFERENCE, GW_MODE_MASK_PHILOX, GW_MODE_MASK_FED = 0, 1, 2
 GW_ROLE_SENDER, GW_ROLE_RRM, GW_ROLE_JAMMER = 1, 2, 3
 (GW_FIELD_NOW, GW_FIELD_RECEIVED_POWER, GW_FIELD_NEXT_TICK, GW_FIELD_COUNTER, GW_FIELD_QUEUE_LEN,
  GW_FIELD_N_TRANSMISSIONS, GW_FIELD_N_DELIVERED, GW_FIELD_RECEIVED_VALUES, GW_FIELD_ATTENUATION_DB,
- GW_FIELD_RX_POWER_MW, GW_FIELD_FAULT, GW_FIELD_TIES, GW_FIELD_TX_SEQ) = range(13)
+ GW_FIELD_RX_POWER_MW, GW_FIELD_FAULT, GW_FIELD_TIES, GW_FIELD_TX_SEQ, GW_FIELD_PLANT) = range(14)
+GW_PLANT_NONE, GW_PLANT_SLIDING_PENDULUM = 0, 1
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-fmad=false",
               "-lineinfo", "-Xcompiler", "-fPIC", "-shared"]
@@ -42,11 +43,19 @@ class BandConfig(C.Structure):
                 ("device", DeviceConfig * GW_MAX_DEVICES)]
 
 
+class PendulumConfig(C.Structure):
+    _fields_ = [("cart_mass", C.c_double), ("pendulum_mass", C.c_double), ("arm_length", C.c_double),
+                ("gravity", C.c_double), ("motor_fmax", C.c_double), ("motor_kservo", C.c_double),
+                ("motor_v_init", C.c_double), ("dt_max", C.c_double),
+                ("kp", C.c_double), ("ki", C.c_double), ("kd", C.c_double), ("mobility", C.c_int32)]
+
+
 class Config(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("n_envs", C.c_int64), ("env_id_offset", C.c_int64),
                 ("n_bands", C.c_int32), ("assignment_duration_factor", C.c_int32),
                 ("max_assign_duration", C.c_int32), ("mode", C.c_int32), ("seed", C.c_uint64),
-                ("per_env_positions", C.c_int32), ("band", BandConfig * GW_MAX_BANDS)]
+                ("per_env_positions", C.c_int32), ("band", BandConfig * GW_MAX_BANDS),
+                ("plant", C.c_int32), ("pendulum", PendulumConfig)]
 
 
 class NativeError(RuntimeError):
@@ -56,7 +65,7 @@ class NativeError(RuntimeError):
 
 
 def _sources():
-    return [os.path.join(CSRC, f) for f in ("gw_kernels.cu", "gw_core.cuh")] + [INCLUDE]
+    return [os.path.join(CSRC, f) for f in ("gw_kernels.cu", "gw_core.cuh", "gw_pendulum.cuh")] + [INCLUDE]
 
 
 def needs_build():

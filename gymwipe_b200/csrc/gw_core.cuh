@@ -180,6 +180,7 @@ struct Sim {
     double txStart[D], tStop[D], tC[D]; // Transmission.startTime / stopTime / eCompletes time
     uint32_t sC[D];
     int cmdPay[D];                      // payload bytes of the SEND command in flight
+    double txVal[D];                    // payload.value of the packet in flight (plant envs only)
     uint32_t txSeq[D];                  // transmissions started by this device (mode M key)
     int rxOf[D];                        // device whose transmission is being received, -1 idle
     int rxSec[D];                       // 0 header, 1 payload
@@ -234,7 +235,7 @@ GW_HD void init_sim(Sim<D, NS, NJ> &s, double thermal)
     GW_UNROLL
     for (int p = 0; p < D; ++p) {
         s.P[p] = thermal; s.sphase[p] = S_IDLE; s.tEv[p] = 0; s.sEv[p] = 0;
-        s.txStart[p] = 0; s.tStop[p] = 0; s.tC[p] = 0; s.sC[p] = 0; s.cmdPay[p] = 0; s.txSeq[p] = 0;
+        s.txStart[p] = 0; s.tStop[p] = 0; s.tC[p] = 0; s.sC[p] = 0; s.cmdPay[p] = 0; s.txSeq[p] = 0; s.txVal[p] = 0;
         s.rxOf[p] = -1; s.rxSec[p] = 0; s.ber[p] = 0; s.err[p] = 0; s.tReset[p] = 0; s.segT0[p] = 0;
     }
     // process Initialize events in construction order: senders, then jammers (URGENT, t = 0)
@@ -326,7 +327,7 @@ GW_HD Event select_nontick(const Sim<D, NS, NJ> &s)
 // Next event for the full transition function.  Silent ticks that precede it -- and lie
 // strictly before `tLimit` -- are applied on the way (SenderDevice.senderProcess,
 // counter_traffic.py:53-61: `mult` packets into the drop-oldest queue, counter += 1, next tick).
-template <int D, int NS, int NJ>
+template <bool ALL_TICKS = false, int D, int NS, int NJ>
 GW_HD Event next_event(Sim<D, NS, NJ> &s, const BandParams &B, double tLimit)
 {
     const Event nt = select_nontick(s);
@@ -343,7 +344,7 @@ GW_HD Event next_event(Sim<D, NS, NJ> &s, const BandParams &B, double tLimit)
         }
         Event tick;
         tick.kind = EV_TICK; tick.idx = k; tick.t = tk; tick.seq = qk;
-        if (!(tk < tLimit) || get_at(s.mac, k) == MAC_WAIT_COND) return tick;
+        if (ALL_TICKS || !(tk < tLimit) || get_at(s.mac, k) == MAC_WAIT_COND) return tick;
         const int mult = k == 0 ? B.mult[0] : B.mult[kMaxSend - 1];
         const double interval = k == 0 ? B.interval[0] : B.interval[kMaxSend - 1];
         const int n = get_at(s.qn, k) + mult;
@@ -414,6 +415,24 @@ GW_HD void mask_range(const Sim<D, NS, NJ> &s, int p, double bitRate, int &sende
 }
 
 // ---------------------------------------------------------------------------
+// plant hook: envs whose packets carry values of a simulated plant (the networked inverted
+// pendulum, gymwipe/envs/inverted_pendulum.py) plug a plant object into the transition
+// function.  NoPlant (CounterTrafficEnv) compiles to nothing.
+//   tick_value(k, now)            value the sender's packets of this tick carry
+//   delivered(d, p, value, now)   a data packet of sender d was decoded by device p
+//   refresh_links(d, now, srx)    received powers from sender d at the start of its transmission
+// ---------------------------------------------------------------------------
+
+struct NoPlant {
+    static constexpr bool active = false;
+    GW_HD double tick_value(int, double) { return 0.0; }
+    GW_HD void delivered(int, int, double, double) {}
+    GW_HD void refresh_links(int, double, double *) {}
+    GW_HD void put_value(int, uint64_t, double) {}
+    GW_HD double get_value(int, uint64_t) { return 0.0; }
+};
+
+// ---------------------------------------------------------------------------
 // helpers of the transition function
 // ---------------------------------------------------------------------------
 
@@ -459,8 +478,8 @@ GW_HD int head_size(const Sim<D, NS, NJ> &s, const BandParams &B, int k, const R
 }
 
 // one pass of the SimpleMac window loop body with a non-empty queue (simple_stack.py:417-434)
-template <int D, int NS, int NJ, class Ring>
-GW_HD void mac_try_send(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, int k, const Ring &ring)
+template <int D, int NS, int NJ, class Ring, class Plant>
+GW_HD void mac_try_send(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, int k, const Ring &ring, Plant &plant)
 {
     const int size = head_size(s, B, k, ring);
     const int bitSize = (kMacHdr + kNetHdr + size) * 8;
@@ -471,6 +490,12 @@ GW_HD void mac_try_send(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B,
         set_at(s.mac, k, (int)MAC_IDLE);        // yield timeoutEvent
         return;
     }
+    if (Plant::active) {
+        // tick that enqueued the head packet = ticks - ceil(qn / mult)
+        const uint32_t m = (uint32_t)(k == 0 ? B.mult[0] : B.mult[kMaxSend - 1]);
+        const uint64_t tick = get_at(s.ticks, k) - (((uint32_t)get_at(s.qn, k) + m - 1u) / m);
+        set_at(s.txVal, k, plant.get_value(k, tick));
+    }
     set_at(s.qn, k, get_at(s.qn, k) - 1);
     set_at(s.mac, k, (int)MAC_WAIT_TX);
     set_at(s.cmdPay, k, kNetHdr + size);
@@ -478,13 +503,13 @@ GW_HD void mac_try_send(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B,
 }
 
 // loop head of the window loop (simple_stack.py:408-416)
-template <int D, int NS, int NJ, class Ring>
-GW_HD void mac_loop_head(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, int k, const Ring &ring)
+template <int D, int NS, int NJ, class Ring, class Plant>
+GW_HD void mac_loop_head(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, int k, const Ring &ring, Plant &plant)
 {
     const bool done = get_at(s.wDone, k) != 0, empty = get_at(s.qn, k) == 0;
     if (done) { set_at(s.mac, k, (int)MAC_NONE); return; }
     if (empty) { set_at(s.mac, k, (int)MAC_WAIT_COND); return; }
-    mac_try_send(s, P, B, k, ring);
+    mac_try_send(s, P, B, k, ring, plant);
 }
 
 // end of SimplePhy._receive (simple_stack.py:264-267) without the deferred wake-up
@@ -511,9 +536,9 @@ GW_HD bool decide(const Sim<D, NS, NJ> &s, const Params &P, int p, double totalB
 // PHYs whose bit error rate must be re-evaluated afterwards (SimplePhy._updateBitErrorRate)
 // ---------------------------------------------------------------------------
 
-template <int D, int NS, int NJ, class Ring>
+template <int D, int NS, int NJ, class Ring, class Plant>
 GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const Event &ev,
-                      const double *srx, const Ring &ring)
+                      double *srx, const Ring &ring, Plant &plant)
 {
     constexpr int RRM = NS;
     int berMask = 0;
@@ -530,8 +555,9 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
         set_at(s.ticks, k, get_at(s.ticks, k) + 1);
         set_at(s.tTick, k, s.now + interval);
         set_at(s.sTick, k, s.seq++);
+        if (Plant::active) plant.put_value(k, get_at(s.ticks, k) - 1, plant.tick_value(k, s.now));
         const bool wake = get_at(s.mac, k) == MAC_WAIT_COND;
-        if (wake) mac_try_send(s, P, B, k, ring);
+        if (wake) mac_try_send(s, P, B, k, ring, plant);
         break;
     }
     case EV_JAM: {
@@ -575,6 +601,7 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
             set_at(s.tStop, d, stop);
             set_at(s.txSeq, d, get_at(s.txSeq, d) + 1u);
             s.nTx += 1;
+            if (Plant::active) plant.refresh_links(d, s.now, srx);
             // zero-delay notification: every other PHY registers the received power
             // (simple_stack.py:130-144); a PHY that is receiving re-evaluates its BER
             GW_UNROLL
@@ -647,6 +674,7 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
             for (int p = 0; p < D; ++p) {
                 if (s.rxOf[p] != d || s.rxSec[p] != 1) continue;
                 if (decide(s, P, p, payBits)) {
+                    if (Plant::active && d != RRM) plant.delivered(d, p, get_at(s.txVal, d), s.now);
                     if (p < NS) {
                         // SimpleMac.phyInHandler (blocking, not queued): only an announcement
                         // addressed to an idle MAC has an effect (simple_stack.py:386-448)
@@ -678,11 +706,11 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
                 set_at(s.sW, window, qW);
                 set_at(s.wPend, window, 1);
                 set_at(s.wDone, window, 0);
-                mac_loop_head(s, P, B, window, ring);
+                mac_loop_head(s, P, B, window, ring, plant);
             }
             // b. SEND eProcessed: the sender's upper layer resumes
             if (d < NS) {
-                mac_loop_head(s, P, B, d, ring);                // `yield message.eProcessed` returns
+                mac_loop_head(s, P, B, d, ring, plant);         // `yield message.eProcessed` returns
             } else if (d == RRM) {
                 s.tRrm = s.now + (s.annSlots + 1) * kSlot;      // simple_stack.py:558
                 s.sRrm = s.seq++;
@@ -717,6 +745,14 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
         s.fault = FAULT_EMPTY;
     }
     return berMask;
+}
+
+template <int D, int NS, int NJ, class Ring>
+GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const Event &ev,
+                      const double *srx, const Ring &ring)
+{
+    NoPlant np;
+    return apply_event(s, P, B, ev, const_cast<double *>(srx), ring, np);
 }
 
 // BER(S, N) is a pure function and, with static geometry, the same few (S, N) pairs recur in
@@ -783,9 +819,9 @@ struct NoMasks {
 };
 
 // processes ONE timed event; `masks(receiver, sender, txseq, k0, k1, ber)` supplies mode-M counts
-template <int MODE, int D, int NS, int NJ, class Ring, class Masks, class Memo>
+template <int MODE, int D, int NS, int NJ, class Ring, class Masks, class Memo, class Plant>
 GW_HD void process_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const Event &ev,
-                         const double *srx, const Ring &ring, const Masks &masks, const Memo &memo)
+                         double *srx, const Ring &ring, const Masks &masks, const Memo &memo, Plant &plant)
 {
     int once, twice;
     s.now = ev.t;
@@ -802,8 +838,27 @@ GW_HD void process_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B
             s.segT0[p] = s.now;
         }
     }
-    const int berMask = apply_event(s, P, B, ev, srx, ring);
+    const int berMask = apply_event(s, P, B, ev, srx, ring, plant);
     update_bers(s, P, berMask, srx, memo);
+}
+
+template <int MODE, int D, int NS, int NJ, class Ring, class Masks, class Memo>
+GW_HD void process_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const Event &ev,
+                         const double *srx, const Ring &ring, const Masks &masks, const Memo &memo)
+{
+    NoPlant np;
+    process_event<MODE>(s, P, B, ev, const_cast<double *>(srx), ring, masks, memo, np);
+}
+
+// SimMan.runSimulation(assignSignal.eProcessed) for an env with a plant: every tick is an event
+template <int MODE, int D, int NS, int NJ, class Ring, class Masks, class Memo, class Plant>
+GW_HD void run_until_assign_plant(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, double *srx,
+                                  const Ring &ring, const Masks &masks, const Memo &memo, Plant &plant)
+{
+    while (!s.assignDone && !s.fault) {
+        const Event ev = next_event<true>(s, B, INFINITY);
+        process_event<MODE>(s, P, B, ev, srx, ring, masks, memo, plant);
+    }
 }
 
 // SimMan.runSimulation(assignSignal.eProcessed) (counter_traffic.py:155)

@@ -29,6 +29,7 @@
 
 #include "../../include/gymwipe_b200.h"
 #include "gw_core.cuh"
+#include "gw_pendulum.cuh"
 
 using namespace gw;
 
@@ -62,7 +63,7 @@ enum : int {
     H_P01 = 0, H_P23, H_TICK, H_TICKS, H_U0, H_U1, H_U2, H_JAM, H_EPK, H_SNAP, H_EPC, HOT_CHUNKS
 };
 // cold: per device 5 chunks, then per sender 1
-enum : int { C_EV = 0, C_TX, C_RX, C_RT, C_U, C_PER_DEV };
+enum : int { C_EV = 0, C_TX, C_RX, C_RT, C_U, C_V, C_PER_DEV };
 constexpr int COLD_CHUNKS = C_PER_DEV * kMaxDev + kMaxSend;
 
 struct StatePtrs {
@@ -74,15 +75,17 @@ struct StatePtrs {
     int32_t *ring;
     double *att;
     double *srx;
+    double *plant;      // [8][nsim] plant state (plant envs)
+    double *pval;       // [2*100][nsim] values of queued packets (plant envs)
 };
 
 struct Layout {
-    size_t off_now, off_hot, off_cold, off_ring, off_att, off_srx, total;
+    size_t off_now, off_hot, off_cold, off_ring, off_att, off_srx, off_plant, off_pval, total;
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static Layout make_layout(long long nenv, int nb, long long ntab)
+static Layout make_layout(long long nenv, int nb, long long ntab, int plant = 0)
 {
     const long long nsim = nenv * nb;
     Layout L;
@@ -93,6 +96,8 @@ static Layout make_layout(long long nenv, int nb, long long ntab)
     L.off_ring = o; o = align_up(o + 4ull * kMaxSend * kQueueCap * nsim, 256);
     L.off_att = o; o = align_up(o + 8ull * 16 * ntab, 256);
     L.off_srx = o; o = align_up(o + 8ull * 16 * ntab, 256);
+    L.off_plant = o; if (plant) o = align_up(o + 8ull * 8 * nsim, 256);
+    L.off_pval = o; if (plant) o = align_up(o + 8ull * kMaxSend * kQueueCap * nsim, 256);
     L.total = o;
     return L;
 }
@@ -123,9 +128,10 @@ struct gw_handle {
     // mode M fed masks
     const uint32_t *masks;
     int mask_slots, mask_words;
-    // BER memo (shared positions only)
+    // BER memo
     ulonglong2 *memo;
     unsigned memo_entries;
+    PendulumParams pend;
 };
 
 // ------------------------------------------------------------------------------------
@@ -268,6 +274,7 @@ __device__ __forceinline__ void load_sim(Sim<D, NS, NJ> &s, const StatePtrs &st,
             s.tReset[d] = lo_d(c); s.segT0[d] = hi_d(c);
             c = ld_chunk(st.cold, n, d * C_PER_DEV + C_U, i);
             s.sEv[d] = c.x; s.sC[d] = c.y; s.cmdPay[d] = (int)c.z;
+            if (st.plant) { c = ld_chunk(st.cold, n, d * C_PER_DEV + C_V, i); s.txVal[d] = lo_d(c); } else s.txVal[d] = 0;
         }
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
@@ -278,7 +285,7 @@ __device__ __forceinline__ void load_sim(Sim<D, NS, NJ> &s, const StatePtrs &st,
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             s.tEv[d] = 0; s.tC[d] = 0; s.txStart[d] = 0; s.tStop[d] = 0; s.ber[d] = 0; s.err[d] = 0;
-            s.tReset[d] = 0; s.segT0[d] = 0; s.sEv[d] = 0; s.sC[d] = 0; s.cmdPay[d] = 0;
+            s.tReset[d] = 0; s.segT0[d] = 0; s.sEv[d] = 0; s.sC[d] = 0; s.cmdPay[d] = 0; s.txVal[d] = 0;
         }
 #pragma unroll
         for (int k = 0; k < NS; ++k) { s.stopW[k] = 0; s.sW[k] = 0; }
@@ -326,6 +333,7 @@ __device__ __forceinline__ void store_sim(const Sim<D, NS, NJ> &s, const StatePt
             st_chunk(st.cold, n, d * C_PER_DEV + C_RT, i, pack_dd(s.tReset[d], s.segT0[d]));
             uint4 c; c.x = s.sEv[d]; c.y = s.sC[d]; c.z = (unsigned)s.cmdPay[d]; c.w = 0;
             st_chunk(st.cold, n, d * C_PER_DEV + C_U, i, c);
+            if (st.plant) st_chunk(st.cold, n, d * C_PER_DEV + C_V, i, pack_dd(s.txVal[d], 0.0));
         }
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
@@ -670,6 +678,100 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
 }
 
 // ------------------------------------------------------------------------------------
+// config 5: networked inverted pendulum -- the same transition function with a plant plugged in
+// ------------------------------------------------------------------------------------
+
+struct DevVals {
+    double *base;       // pval + sim index
+    long long nsim;
+    __device__ __forceinline__ void put(int k, uint32_t slot, double v) { base[(long long)(k * kQueueCap + slot) * nsim] = v; }
+    __device__ __forceinline__ double get(int k, uint32_t slot) const { return base[(long long)(k * kQueueCap + slot) * nsim]; }
+};
+struct DevSrxOut {
+    double *base;       // srx table + sim index (per-sim tables)
+    long long ntab;
+    __device__ __forceinline__ void put(int k, double v) { base[(long long)k * ntab] = v; }
+};
+
+__device__ __forceinline__ void load_plant(PendulumState &S, const StatePtrs &st, long long i)
+{
+    const long long n = st.nsim;
+    S.x = st.plant[0 * n + i]; S.v = st.plant[1 * n + i]; S.th = st.plant[2 * n + i]; S.om = st.plant[3 * n + i];
+    S.vTarget = st.plant[4 * n + i]; S.tPlant = st.plant[5 * n + i]; S.ctrlAngleDeg = st.plant[6 * n + i];
+    S.lastError = st.plant[7 * n + i];
+}
+__device__ __forceinline__ void store_plant(const PendulumState &S, const StatePtrs &st, long long i)
+{
+    const long long n = st.nsim;
+    st.plant[0 * n + i] = S.x; st.plant[1 * n + i] = S.v; st.plant[2 * n + i] = S.th; st.plant[3 * n + i] = S.om;
+    st.plant[4 * n + i] = S.vTarget; st.plant[5 * n + i] = S.tPlant; st.plant[6 * n + i] = S.ctrlAngleDeg;
+    st.plant[7 * n + i] = S.lastError;
+}
+
+__global__ void __launch_bounds__(128)
+pendulum_step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P,
+                     const __grid_constant__ PendulumParams Q)
+{
+    using SimT = Sim<4, 2, 1>;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nsim = A.st.nsim;
+    if (i >= nsim) return;
+    SimT s;
+    PendulumState S;
+    double srx[16];
+    load_sim(s, A.st, i, A.st.now[i]);
+    load_plant(S, A.st, i);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) srx[k] = A.st.srx[(long long)k * A.st.ntab + i];
+    int dev = A.device[i], dur = A.duration[i];
+    if (dev < 0 || dev >= 2 || dur < 0 || dur >= P.maxDuration) {
+        if (atomicCAS(A.errflag, 0, GW_E_ACTION) == 0) A.errflag[1] = (int)i;
+        dev = dev < 0 ? 0 : (dev >= 2 ? 1 : dev);
+        dur = dur < 0 ? 0 : (dur >= P.maxDuration ? P.maxDuration - 1 : dur);
+    }
+    const uint32_t nTx0 = s.nTx, nD0 = s.nDeliv[0], nD1 = s.nDeliv[1];
+    begin_assignment(s, P, dev, dur);
+    DevRing ring{A.st.ring + i, nsim};
+    PendulumPlant<DevVals, DevSrxOut> plant(Q, S, DevVals{A.st.pval + i, nsim}, DevSrxOut{A.st.srx + i, A.st.ntab});
+    run_until_assign_plant<MODE_R>(s, P, P.band[0], srx, ring, NoMasks(), NoMemo(), plant);
+    // InvertedPendulumInterpreter (inverted_pendulum.py:42-56): the angle is read from the plant
+    pendulum_advance(Q, S, s.now);
+    const double deg = S.th * (180.0 / 3.141592653589793);
+    A.obs[i] = (long long)deg;                                 // int(degrees(angle)): truncation
+    const double rw = fabs(180.0 - deg);
+    A.reward[i] = rw;
+    A.done[i] = 0;
+    A.st.now[i] = s.now;
+    if (s.fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = s.fault; } }
+    store_sim(s, A.st, i, false);
+    store_plant(S, A.st, i);
+    // statistics (no block reduction: this env is not the throughput path)
+    atomicAdd(A.stats + 0, rw);
+    atomicAdd(A.stats + 1, (double)(s.nDeliv[0] - nD0));
+    atomicAdd(A.stats + 2, (double)(s.nDeliv[1] - nD1));
+    atomicAdd(A.stats + 4, 1.0);
+    atomicAdd(A.stats + 5, fabs(deg));
+    atomicAdd(A.stats + 6, (double)(s.nTx - nTx0));
+}
+
+__global__ void pendulum_init_kernel(StatePtrs st, PendulumParams Q)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.nsim) return;
+    PendulumState S;
+    pendulum_init(Q, S);
+    store_plant(S, st, i);
+    for (int k = 0; k < kMaxSend * kQueueCap; ++k) st.pval[(long long)k * st.nsim + i] = 0.0;
+}
+
+__global__ void plant_read_kernel(StatePtrs st, double *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.nsim) return;
+    for (int k = 0; k < 8; ++k) out[(long long)k * st.nsim + i] = st.plant[(long long)k * st.nsim + i];
+}
+
+// ------------------------------------------------------------------------------------
 // init / reset / tables / read-back kernels
 // ------------------------------------------------------------------------------------
 
@@ -1001,6 +1103,15 @@ static int validate(const gw_config *cfg, int &D, int &NS, int &NJ)
         }
     }
     D = NS + 1 + NJ;
+    if (cfg->plant != GW_PLANT_NONE) {
+        if (cfg->plant != GW_PLANT_SLIDING_PENDULUM) return fail(GW_E_INVALID, "unknown plant %d", cfg->plant);
+        if (cfg->n_bands != 1 || NS != 2 || NJ != 1) return fail(GW_E_INVALID, "a plant env has one band: sensor, controller, RRM, actuator");
+        if (cfg->mode != GW_MODE_REFERENCE) return fail(GW_E_INVALID, "plant envs run in GW_MODE_REFERENCE");
+        if (!cfg->per_env_positions) return fail(GW_E_INVALID, "plant envs need per_env_positions = 1 (links follow the wagon)");
+        const gw_pendulum_config &pc = cfg->pendulum;
+        if (!(pc.cart_mass > 0) || !(pc.pendulum_mass > 0) || !(pc.arm_length > 0) || !(pc.dt_max > 0) || !(pc.motor_kservo >= 0))
+            return fail(GW_E_INVALID, "bad pendulum parameters");
+    }
     return GW_OK;
 }
 
@@ -1080,7 +1191,7 @@ int gw_state_bytes(const gw_config *cfg, size_t *bytes)
     if (rc) return rc;
     if (!bytes) return fail(GW_E_INVALID, "bytes is NULL");
     const long long ntab = cfg->per_env_positions ? cfg->n_envs * cfg->n_bands : 1;
-    *bytes = make_layout(cfg->n_envs, cfg->n_bands, ntab).total;
+    *bytes = make_layout(cfg->n_envs, cfg->n_bands, ntab, cfg->plant).total;
     return GW_OK;
 }
 
@@ -1122,7 +1233,7 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
     h->D = D; h->NS = NS; h->NJ = NJ;
     fill_params(*cfg, h->P);
     const long long ntab = cfg->per_env_positions ? cfg->n_envs * cfg->n_bands : 1;
-    h->layout = make_layout(cfg->n_envs, cfg->n_bands, ntab);
+    h->layout = make_layout(cfg->n_envs, cfg->n_bands, ntab, cfg->plant);
     if (state) {
         if (state_bytes < h->layout.total) { delete h; return fail(GW_E_STATE, "state buffer has %zu bytes, %zu needed", state_bytes, h->layout.total); }
         if (((uintptr_t)state & 255) != 0) { delete h; return fail(GW_E_STATE, "state buffer must be 256-byte aligned"); }
@@ -1139,6 +1250,21 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
     h->st.ring = (int32_t *)(base + h->layout.off_ring);
     h->st.att = (double *)(base + h->layout.off_att);
     h->st.srx = (double *)(base + h->layout.off_srx);
+    h->st.plant = cfg->plant ? (double *)(base + h->layout.off_plant) : nullptr;
+    h->st.pval = cfg->plant ? (double *)(base + h->layout.off_pval) : nullptr;
+    if (cfg->plant) {
+        const gw_pendulum_config &pc = cfg->pendulum;
+        PendulumParams &Q = h->pend;
+        Q.M = pc.cart_mass; Q.m = pc.pendulum_mass; Q.l = pc.arm_length; Q.g = pc.gravity;
+        Q.fMax = pc.motor_fmax; Q.kServo = pc.motor_kservo; Q.dtMax = pc.dt_max;
+        Q.kp = pc.kp; Q.ki = pc.ki; Q.kd = pc.kd; Q.vInit = pc.motor_v_init;
+        Q.frequency = cfg->band[0].frequency_hz;
+        Q.sensorY = cfg->band[0].device[0].y;
+        Q.ctrlX = cfg->band[0].device[1].x; Q.ctrlY = cfg->band[0].device[1].y;
+        Q.rrmX = cfg->band[0].device[2].x; Q.rrmY = cfg->band[0].device[2].y;
+        Q.actuatorY = cfg->band[0].device[3].y;
+        Q.mobility = pc.mobility;
+    }
     for (int b = 0; b < cfg->n_bands; ++b) {
         const gw_band_config &cb = cfg->band[b];
         h->frequency[b] = cb.frequency_hz;
@@ -1157,9 +1283,15 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
     if (e == cudaSuccess) e = cudaMemsetAsync(h->stats, 0, aux, s);
     if (e == cudaSuccess) e = cudaMalloc(&stg, nsim * (4 + 4 + 8 + 8 + 1) + 64);
     if (e != cudaSuccess) { gw_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
-    if (ntab == 1 && !std::getenv("GYMWIPE_B200_NO_MEMO")) {
-        // identical geometry in every env: a small table holds every (S, N) pair that occurs
+    if (!std::getenv("GYMWIPE_B200_NO_MEMO")) {
+        // identical geometry in every env: a small table holds every (S, N) pair that occurs;
+        // per-env geometries: ~20 recurring pairs per band-sim, so the table scales with the batch
+        // (32 entries per band-sim, 32 B each, capped at 2 GiB)
         h->memo_entries = 1u << 14;
+        if (ntab > 1) {
+            unsigned long long want = 32ull * (unsigned long long)nsim;
+            while (h->memo_entries < want && h->memo_entries < (1u << 26)) h->memo_entries <<= 1;
+        }
         e = cudaMalloc((void **)&h->memo, 32ull * h->memo_entries);
         if (e == cudaSuccess) e = cudaMemsetAsync(h->memo, 0, 32ull * h->memo_entries, s);
         if (e != cudaSuccess) { cudaFree(stg); gw_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
@@ -1176,6 +1308,7 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
 #define CALL_INIT(DD, SS, JJ) init_kernel<DD, SS, JJ><<<grid_for(nsim, 128), 128, 0, s>>>(h->st, th)
     DISPATCH_SHAPE(h, CALL_INIT);
 #undef CALL_INIT
+    if (cfg->plant) pendulum_init_kernel<<<grid_for(nsim, 128), 128, 0, s>>>(h->st, h->pend);
     e = cudaGetLastError();
     if (e != cudaSuccess) { gw_destroy(h); return fail(GW_E_CUDA, "init kernel: %s", cudaGetErrorString(e)); }
     rc = launch_tables(h, nullptr, s);
@@ -1244,6 +1377,11 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
                 }
     }
     const long long nsim = h->st.nsim;
+    if (h->cfg.plant) {
+        pendulum_step_kernel<<<grid_for(nsim, 128), 128, 0, s>>>(A, h->P, h->pend);
+        CUDA_TRY(cudaGetLastError());
+        return GW_OK;
+    }
     // one wave: 128-thread blocks, a multiple of the SM count when the batch is large
     int blocks = grid_for(nsim, 128);
     const int cap = 148 * 16;
@@ -1319,10 +1457,16 @@ int gw_stats(gw_handle *h, double *out8, int clear, void *stream)
 int gw_read_state(gw_handle *h, int field, double *out, void *stream)
 {
     if (!h || !out) return fail(GW_E_INVALID, "NULL argument");
-    if (field < GW_FIELD_NOW || field > GW_FIELD_TX_SEQ) return fail(GW_E_INVALID, "unknown field %d", field);
+    if (field < GW_FIELD_NOW || field > GW_FIELD_PLANT) return fail(GW_E_INVALID, "unknown field %d", field);
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     const long long nsim = h->st.nsim;
+    if (field == GW_FIELD_PLANT) {
+        if (!h->cfg.plant) return fail(GW_E_INVALID, "not a plant env");
+        plant_read_kernel<<<grid_for(nsim, 128), 128, 0, s>>>(h->st, out);
+        CUDA_TRY(cudaGetLastError());
+        return GW_OK;
+    }
 #define CALL_READ(DD, SS, JJ) read_kernel<DD, SS, JJ><<<grid_for(nsim, 128), 128, 0, s>>>(h->st, h->P, field, out)
     DISPATCH_SHAPE(h, CALL_READ);
 #undef CALL_READ

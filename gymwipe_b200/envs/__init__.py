@@ -4,9 +4,11 @@ instantiates them (gym itself is not a dependency).
 """
 from gymwipe_b200.envs.counter_traffic import CounterTrafficEnv
 from gymwipe_b200.envs.core import BaseEnv, Interpreter
+from gymwipe_b200.envs.inverted_pendulum import InvertedPendulumEnv
 
 registry = {
     'CounterTraffic-v0': CounterTrafficEnv,
+    'InvertedPendulum-v0': InvertedPendulumEnv,
 }
 
 
@@ -21,4 +23,4 @@ def make(id, **kwargs):
     return registry[id](**kwargs)
 
 
-__all__ = ["CounterTrafficEnv", "BaseEnv", "Interpreter", "make", "register", "registry"]
+__all__ = ["CounterTrafficEnv", "InvertedPendulumEnv", "BaseEnv", "Interpreter", "make", "register", "registry"]

@@ -183,8 +183,9 @@ class CounterTrafficEnv(BaseEnv):
         self._lib = N.lib()
         self._cfg = S.config_from_dict(self.scenario, self.num_envs, mode=mode, seed=seed,
                                        env_id_offset=env_id_offset,
-                                       per_env_positions=positions is not None,
+                                       per_env_positions=positions is not None or self._needs_per_env_tables(),
                                        max_assign_duration=self.MAX_ASSIGN_DURATION)
+        self._configure_native(self._cfg)
         nbytes = C.c_size_t()
         N.check(self._lib.gw_state_bytes(C.byref(self._cfg), C.byref(nbytes)))
         self.state = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
@@ -203,6 +204,12 @@ class CounterTrafficEnv(BaseEnv):
         self._stats_out = torch.zeros(8, dtype=torch.float64, device=self.device)
 
     # ------------------------------------------------------------------ plumbing
+    def _needs_per_env_tables(self):
+        return False
+
+    def _configure_native(self, cfg):
+        """Hook for subclasses (plant envs) to extend the native config before ``gw_create``."""
+
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -231,7 +238,7 @@ class CounterTrafficEnv(BaseEnv):
         rows = {N.GW_FIELD_NOW: None, N.GW_FIELD_RECEIVED_POWER: 4, N.GW_FIELD_NEXT_TICK: 2, N.GW_FIELD_COUNTER: 2,
                 N.GW_FIELD_QUEUE_LEN: 2, N.GW_FIELD_N_TRANSMISSIONS: 1, N.GW_FIELD_N_DELIVERED: 2,
                 N.GW_FIELD_RECEIVED_VALUES: 2, N.GW_FIELD_ATTENUATION_DB: 16, N.GW_FIELD_RX_POWER_MW: 16,
-                N.GW_FIELD_FAULT: 1, N.GW_FIELD_TIES: 1, N.GW_FIELD_TX_SEQ: 4}[field]
+                N.GW_FIELD_FAULT: 1, N.GW_FIELD_TIES: 1, N.GW_FIELD_TX_SEQ: 4, N.GW_FIELD_PLANT: 8}[field]
         if rows is None:
             out = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
         else:

@@ -73,6 +73,18 @@ typedef struct {
     gw_device_config device[GW_MAX_DEVICES];
 } gw_band_config;
 
+/* optional plant coupled to the network (config 5: networked inverted pendulum) */
+#define GW_PLANT_NONE 0
+#define GW_PLANT_SLIDING_PENDULUM 1  /* gymwipe/plants/sliding_pendulum.py:15-114 */
+
+typedef struct {
+    double cart_mass, pendulum_mass, arm_length, gravity;   /* sliding_pendulum.py:24-45, plants/core.py:33-35 */
+    double motor_fmax, motor_kservo, motor_v_init;          /* slider ParamFMax = 22, ParamVel = 0.1 (:52-53) */
+    double dt_max;                                          /* largest integrator sub-step (s) */
+    double kp, ki, kd;                                      /* control/inverted_pendulum.py:46-50 */
+    int32_t mobility;               /* sensor / actuator x follow the wagon (sliding_pendulum.py:132,149) */
+} gw_pendulum_config;
+
 typedef struct {
     int32_t abi_version;            /* GW_ABI_VERSION */
     int64_t n_envs;                 /* envs held by this handle (this GPU's shard) */
@@ -84,6 +96,9 @@ typedef struct {
     uint64_t seed;                  /* Philox key (mode M) */
     int32_t per_env_positions;      /* 0: all envs share the scenario's positions */
     gw_band_config band[GW_MAX_BANDS];
+    int32_t plant;                  /* GW_PLANT_*; a plant env has one band with the devices
+                                       sensor (sender 0), controller (sender 1), RRM, actuator (receive-only) */
+    gw_pendulum_config pendulum;
 } gw_config;
 
 typedef struct gw_handle gw_handle;
@@ -121,6 +136,10 @@ int gw_set_positions(gw_handle *h, const double *positions, void *stream);
  * `env_ids` (device int64[n]) selects envs, NULL = all.  `obs` (device int64
  * [n_envs][n_bands]) may be NULL. */
 int gw_reset(gw_handle *h, const int64_t *env_ids, int64_t n, int64_t *obs, void *stream);
+
+/* Plant envs (cfg.plant != 0) use the same entry points: gw_step replaces
+ * InvertedPendulumEnv.step (gymwipe/envs/inverted_pendulum.py:79-91) -- obs = int(degrees(angle)),
+ * reward = |180 - degrees(angle)| (:42-50) -- and integrates the plant inside the step kernel. */
 
 /* Replaces CounterTrafficEnv.step (counter_traffic.py:146-158): one RRM assignment cycle
  * for every env.  `device`, `duration`: device int32 [n_envs][n_bands] (action["device"],
@@ -164,6 +183,8 @@ int gw_stats(gw_handle *h, double *out8, int clear, void *stream);
 #define GW_FIELD_FAULT 10           /* [n_sims]                0 or the condition under which the reference raises */
 #define GW_FIELD_TIES 11            /* [n_sims]                exact-time ties seen by the event selector */
 #define GW_FIELD_TX_SEQ 12          /* [GW_MAX_DEVICES][n_sims] transmissions started per device */
+#define GW_FIELD_PLANT 13           /* [8][n_sims] x, v, theta, omega, motor target velocity, plant time,
+                                       controller's angle estimate (deg), PID memory (plant envs) */
 int gw_read_state(gw_handle *h, int field, double *out, void *stream);
 
 /* Mode M, fed masks: `mask_words` is a device uint32 buffer laid out

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../gymwipe_b200/csrc/gw_core.cuh"
+#include "../../gymwipe_b200/csrc/gw_pendulum.cuh"
 
 using namespace gw;
 
@@ -166,6 +167,20 @@ int hs_run(const HsScenario *sc, int64_t nenv, int nsteps, int do_reset, const d
 double hs_ber(double S, double N)
 {
     return ber_bpsk_mw(S, N, 10 * std::log10(133.33333e3), 1.135 * std::sqrt(2 * 3.141592653589793));
+}
+
+// plant integrator of config 5: advances state[8] = {x, v, theta, omega, vTarget, tPlant, -, -}
+void hs_pendulum_advance(const double *params /* M m l g fMax kServo dtMax */, double *state, double now)
+{
+    PendulumParams Q;
+    std::memset(&Q, 0, sizeof Q);
+    Q.M = params[0]; Q.m = params[1]; Q.l = params[2]; Q.g = params[3]; Q.fMax = params[4]; Q.kServo = params[5];
+    Q.dtMax = params[6];
+    PendulumState S;
+    S.x = state[0]; S.v = state[1]; S.th = state[2]; S.om = state[3]; S.vTarget = state[4]; S.tPlant = state[5];
+    S.ctrlAngleDeg = 0; S.lastError = 0;
+    pendulum_advance(Q, S, now);
+    state[0] = S.x; state[1] = S.v; state[2] = S.th; state[3] = S.om; state[5] = S.tPlant;
 }
 
 double hs_fspl(double ax, double ay, double bx, double by, double f) { return fspl_db(ax, ay, bx, by, f); }

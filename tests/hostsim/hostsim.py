@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "_hostsim.so")
 SRC = os.path.join(HERE, "gw_hostsim.cpp")
 CORE = os.path.join(HERE, "..", "..", "gymwipe_b200", "csrc", "gw_core.cuh")
+PEND = os.path.join(HERE, "..", "..", "gymwipe_b200", "csrc", "gw_pendulum.cuh")
 
 MAXDEV, MAXSEND, MAXBAND = 4, 2, 4
 
@@ -35,7 +36,7 @@ _lib = None
 
 
 def build(force=False):
-    if force or not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(CORE)):
+    if force or not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(PEND)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared",
                                "-o", SO, SRC])
     return SO
@@ -53,6 +54,7 @@ def lib():
         L.hs_fspl.restype = C.c_double
         L.hs_fspl.argtypes = [C.c_double] * 5
         L.hs_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hs_pendulum_advance.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
         L.hs_mask_errors.restype = C.c_int64
         L.hs_mask_errors.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.c_int,
                                      C.c_int64, C.c_int64, C.c_double]
