@@ -327,31 +327,42 @@ GW_HD Event select_nontick(const Sim<D, NS, NJ> &s)
 // Next event for the full transition function.  Silent ticks that precede it -- and lie
 // strictly before `tLimit` -- are applied on the way (SenderDevice.senderProcess,
 // counter_traffic.py:53-61: `mult` packets into the drop-oldest queue, counter += 1, next tick).
+// one silent tick of sender K (compile-time index: plain register updates, no selects)
+template <int K, int D, int NS, int NJ>
+GW_HD void silent_tick(Sim<D, NS, NJ> &s, int mult, double interval)
+{
+    const int n = s.qn[K] + mult;
+    s.qn[K] = n > kQueueCap ? kQueueCap : n;
+    s.ticks[K] += 1;
+    s.tTick[K] = s.tTick[K] + interval;
+    s.sTick[K] = s.seq++;
+}
+
 template <bool ALL_TICKS = false, int D, int NS, int NJ>
 GW_HD Event next_event(Sim<D, NS, NJ> &s, const BandParams &B, double tLimit)
 {
+    static_assert(NS == 2, "the tick loop is written for two senders per band");
     const Event nt = select_nontick(s);
+    const int mult0 = B.mult[0], mult1 = B.mult[1];
+    const double int0 = B.interval[0], int1 = B.interval[1];
+    const bool have_nt = nt.kind != EV_NONE;
     for (;;) {
-        int k = 0;
-        GW_UNROLL
-        for (int q = 1; q < NS; ++q)
-            if (before(s.tTick[q], s.sTick[q], get_at(s.tTick, k), get_at(s.sTick, k))) k = q;
-        const double tk = get_at(s.tTick, k);
-        const uint32_t qk = get_at(s.sTick, k);
-        if (nt.kind != EV_NONE && !before(tk, qk, nt.t, nt.seq)) {
+        // earliest tick: sender 1 only if strictly before sender 0 in (time, seq)
+        const bool one = before(s.tTick[1], s.sTick[1], s.tTick[0], s.sTick[0]);
+        const double tk = one ? s.tTick[1] : s.tTick[0];
+        const uint32_t qk = one ? s.sTick[1] : s.sTick[0];
+        if (have_nt && !before(tk, qk, nt.t, nt.seq)) {
             s.ties += (tk == nt.t) ? 1u : 0u;       // exact tie of independent events (diagnostic)
             return nt;
         }
-        Event tick;
-        tick.kind = EV_TICK; tick.idx = k; tick.t = tk; tick.seq = qk;
-        if (ALL_TICKS || !(tk < tLimit) || get_at(s.mac, k) == MAC_WAIT_COND) return tick;
-        const int mult = k == 0 ? B.mult[0] : B.mult[kMaxSend - 1];
-        const double interval = k == 0 ? B.interval[0] : B.interval[kMaxSend - 1];
-        const int n = get_at(s.qn, k) + mult;
-        set_at(s.qn, k, n > kQueueCap ? kQueueCap : n);
-        set_at(s.ticks, k, get_at(s.ticks, k) + 1);
-        set_at(s.tTick, k, tk + interval);
-        set_at(s.sTick, k, s.seq++);
+        const int mac = one ? s.mac[1] : s.mac[0];
+        if (ALL_TICKS || !(tk < tLimit) || mac == MAC_WAIT_COND) {
+            Event tick;
+            tick.kind = EV_TICK; tick.idx = one ? 1 : 0; tick.t = tk; tick.seq = qk;
+            return tick;
+        }
+        if (one) silent_tick<1>(s, mult1, int1);
+        else silent_tick<0>(s, mult0, int0);
     }
 }
 
@@ -436,11 +447,25 @@ struct NoPlant {
 // helpers of the transition function
 // ---------------------------------------------------------------------------
 
+// fmod(t, kSlot) for t >= 0, bit-identical to the C library's (fmod is exact by definition):
+// q = trunc(t / L) may be one too large through the rounding of the division; t - q L is a
+// multiple of ulp(L) smaller than 2 L, hence exactly representable, so one explicit fma returns
+// it without rounding and a single correction step finishes.  ~30 instructions instead of the
+// generic iterative fmod.  Valid while t / L < 2^52 (t < 4.5e9 s).
+GW_HD double fmod_slot(double t)
+{
+    const double q = trunc(t / kSlot);
+    double r = fma(-q, kSlot, t);
+    if (r < 0.0) r += kSlot;
+    else if (r >= kSlot) r -= kSlot;
+    return r;
+}
+
 template <int D, int NS, int NJ>
 GW_HD void begin_slot_wait(Sim<D, NS, NJ> &s, int d)
 {
     // self._transmitting = True; yield SimMan.nextTimeSlot(TIME_SLOT_LENGTH)  (simple_stack.py:202-204)
-    const double t = s.now + (kSlot - fmod(s.now, kSlot));      // simtools.py:53
+    const double t = s.now + (kSlot - fmod_slot(s.now));        // simtools.py:53
     const uint32_t q = s.seq++;
     set_at(s.sphase, d, (int)S_SLOT);
     set_at(s.tEv, d, t);
@@ -468,11 +493,11 @@ GW_HD int head_size(const Sim<D, NS, NJ> &s, const BandParams &B, int k, const R
     const uint32_t qn = (uint32_t)get_at(s.qn, k);
     const uint64_t enq = ticks * m;
     const uint64_t j = enq - (uint64_t)qn;
-    if (j < get_at(s.snapEnd, k)) return ring(k, (uint32_t)(j % (uint64_t)kQueueCap));
+    if (j < ring.snapEnd(s, k)) return ring(k, (uint32_t)(j % (uint64_t)kQueueCap));
     // tick of packet j = ticks - ceil(qn / m)
     const uint64_t back = (qn + m - 1u) / m;
     const uint64_t tick = ticks - back;
-    const uint64_t c = (uint64_t)get_at(s.epochC, k) + (tick - get_at(s.epochK, k));
+    const uint64_t c = (uint64_t)ring.epochC(s, k) + (tick - ring.epochK(s, k));
     const int size = c > (uint64_t)kCounterBound ? kCounterBound : (int)c;
     return size;
 }
@@ -797,7 +822,7 @@ GW_HD void begin_assignment(Sim<D, NS, NJ> &s, const Params &P, int device, int 
 {
     const long long slots = (long long)duration * P.factor;         // counter_traffic.py:149
     int nbytes = 1;                                                  // len(str(slots)), messages.py:62-64
-    for (long long v = slots; v >= 10; v /= 10) ++nbytes;
+    for (long long lim = 10; lim <= slots && nbytes < 18; lim *= 10) ++nbytes;
     s.annDest = device;
     s.annSlots = (double)slots;
     s.annBytes = nbytes;

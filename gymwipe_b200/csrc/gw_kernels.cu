@@ -226,7 +226,10 @@ __device__ __forceinline__ void pack_flags(const Sim<D, NS, NJ> &s, bool busy, u
     b |= (unsigned)busy << 31;
 }
 
-template <int D, int NS, int NJ>
+// FULL = false: the step kernels skip fields they never read (counter epochs -- fetched on demand
+// through DevRing --, mode-M segment starts in mode R, packet values without a plant), which
+// makes them dead in registers
+template <bool FULL = true, bool WITH_SEG = true, int D, int NS, int NJ>
 __device__ __forceinline__ void load_sim(Sim<D, NS, NJ> &s, const StatePtrs &st, long long i, double now)
 {
     const long long n = st.nsim;
@@ -254,12 +257,17 @@ __device__ __forceinline__ void load_sim(Sim<D, NS, NJ> &s, const StatePtrs &st,
     } else {
         s.tJam[0] = 0; s.sJam[0] = 0;
     }
-    v = ld_chunk(st.hot, n, H_EPK, i);
-    s.epochK[0] = lo_q(v); s.epochK[1] = hi_q(v);
-    v = ld_chunk(st.hot, n, H_SNAP, i);
-    s.snapEnd[0] = lo_q(v); s.snapEnd[1] = hi_q(v);
-    v = ld_chunk(st.hot, n, H_EPC, i);
-    s.epochC[0] = (int)v.x; s.epochC[1] = (int)v.y; s.fault = (int)v.z; s.ties = v.w;
+    if (FULL) {
+        v = ld_chunk(st.hot, n, H_EPK, i);
+        s.epochK[0] = lo_q(v); s.epochK[1] = hi_q(v);
+        v = ld_chunk(st.hot, n, H_SNAP, i);
+        s.snapEnd[0] = lo_q(v); s.snapEnd[1] = hi_q(v);
+        v = ld_chunk(st.hot, n, H_EPC, i);
+        s.epochC[0] = (int)v.x; s.epochC[1] = (int)v.y; s.fault = (int)v.z; s.ties = v.w;
+    } else {
+        s.epochK[0] = s.epochK[1] = 0; s.snapEnd[0] = s.snapEnd[1] = 0; s.epochC[0] = s.epochC[1] = 0;
+        s.fault = 0; s.ties = 0;        // a faulted sim stays flagged in memory (store_sim ORs nothing back)
+    }
     const bool busy = (u0.z >> 31) & 1;
     if (busy) {
 #pragma unroll
@@ -271,10 +279,10 @@ __device__ __forceinline__ void load_sim(Sim<D, NS, NJ> &s, const StatePtrs &st,
             c = ld_chunk(st.cold, n, d * C_PER_DEV + C_RX, i);
             s.ber[d] = lo_d(c); s.err[d] = hi_d(c);
             c = ld_chunk(st.cold, n, d * C_PER_DEV + C_RT, i);
-            s.tReset[d] = lo_d(c); s.segT0[d] = hi_d(c);
+            s.tReset[d] = lo_d(c); s.segT0[d] = WITH_SEG ? hi_d(c) : 0.0;
             c = ld_chunk(st.cold, n, d * C_PER_DEV + C_U, i);
             s.sEv[d] = c.x; s.sC[d] = c.y; s.cmdPay[d] = (int)c.z;
-            if (st.plant) { c = ld_chunk(st.cold, n, d * C_PER_DEV + C_V, i); s.txVal[d] = lo_d(c); } else s.txVal[d] = 0;
+            if (FULL && st.plant) { c = ld_chunk(st.cold, n, d * C_PER_DEV + C_V, i); s.txVal[d] = lo_d(c); } else s.txVal[d] = 0;
         }
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
@@ -293,7 +301,7 @@ __device__ __forceinline__ void load_sim(Sim<D, NS, NJ> &s, const StatePtrs &st,
     s.annDest = 0; s.annBytes = 0; s.annSlots = 0; s.rrmPend = 0; s.tRrm = 0; s.sRrm = 0; s.assignDone = 0;
 }
 
-template <int D, int NS, int NJ>
+template <bool FULL = true, bool WITH_SEG = true, int D, int NS, int NJ>
 __device__ __forceinline__ void store_sim(const Sim<D, NS, NJ> &s, const StatePtrs &st, long long i, bool epoch_too)
 {
     const long long n = st.nsim;
@@ -320,9 +328,16 @@ __device__ __forceinline__ void store_sim(const Sim<D, NS, NJ> &s, const StatePt
         st_chunk(st.hot, n, H_EPK, i, pack_qq(s.epochK[0], s.epochK[1]));
         st_chunk(st.hot, n, H_SNAP, i, pack_qq(s.snapEnd[0], s.snapEnd[1]));
     }
-    if (epoch_too || s.fault || s.ties) {
-        v.x = (unsigned)s.epochC[0]; v.y = (unsigned)s.epochC[1]; v.z = (unsigned)s.fault; v.w = s.ties;
-        st_chunk(st.hot, n, H_EPC, i, v);
+    if (FULL) {
+        if (epoch_too || s.fault || s.ties) {
+            v.x = (unsigned)s.epochC[0]; v.y = (unsigned)s.epochC[1]; v.z = (unsigned)s.fault; v.w = s.ties;
+            st_chunk(st.hot, n, H_EPC, i, v);
+        }
+    } else if (s.fault || s.ties) {
+        // step kernels: fault / tie counters are merged into the stored words (rare path)
+        unsigned *w = reinterpret_cast<unsigned *>(st.hot + (long long)H_EPC * n + i);
+        if (s.fault) w[2] = (unsigned)s.fault;
+        w[3] += s.ties;
     }
     if (busy) {
 #pragma unroll
@@ -330,10 +345,10 @@ __device__ __forceinline__ void store_sim(const Sim<D, NS, NJ> &s, const StatePt
             st_chunk(st.cold, n, d * C_PER_DEV + C_EV, i, pack_dd(s.tEv[d], s.tC[d]));
             st_chunk(st.cold, n, d * C_PER_DEV + C_TX, i, pack_dd(s.txStart[d], s.tStop[d]));
             st_chunk(st.cold, n, d * C_PER_DEV + C_RX, i, pack_dd(s.ber[d], s.err[d]));
-            st_chunk(st.cold, n, d * C_PER_DEV + C_RT, i, pack_dd(s.tReset[d], s.segT0[d]));
+            st_chunk(st.cold, n, d * C_PER_DEV + C_RT, i, pack_dd(s.tReset[d], WITH_SEG ? s.segT0[d] : 0.0));
             uint4 c; c.x = s.sEv[d]; c.y = s.sC[d]; c.z = (unsigned)s.cmdPay[d]; c.w = 0;
             st_chunk(st.cold, n, d * C_PER_DEV + C_U, i, c);
-            if (st.plant) st_chunk(st.cold, n, d * C_PER_DEV + C_V, i, pack_dd(s.txVal[d], 0.0));
+            if (FULL && st.plant) st_chunk(st.cold, n, d * C_PER_DEV + C_V, i, pack_dd(s.txVal[d], 0.0));
         }
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
@@ -347,8 +362,24 @@ __device__ __forceinline__ void store_sim(const Sim<D, NS, NJ> &s, const StatePt
 struct DevRing {
     int32_t *base;      // ring + sim index
     long long nsim;
+    const uint4 *hot;   // hot chunks + sim index: the counter epochs are read on demand (rare)
     __device__ __forceinline__ int operator()(int k, uint32_t slot) const { return base[(long long)(k * kQueueCap + slot) * nsim]; }
     __device__ __forceinline__ void operator()(int k, uint32_t slot, int v) { base[(long long)(k * kQueueCap + slot) * nsim] = v; }
+    template <class S> __device__ __forceinline__ unsigned long long snapEnd(const S &, int k) const
+    {
+        const uint4 v = hot[(long long)H_SNAP * nsim];
+        return k == 0 ? lo_q(v) : hi_q(v);
+    }
+    template <class S> __device__ __forceinline__ unsigned long long epochK(const S &, int k) const
+    {
+        const uint4 v = hot[(long long)H_EPK * nsim];
+        return k == 0 ? lo_q(v) : hi_q(v);
+    }
+    template <class S> __device__ __forceinline__ int epochC(const S &, int k) const
+    {
+        const uint4 v = hot[(long long)H_EPC * nsim];
+        return (int)(k == 0 ? v.x : v.y);
+    }
 };
 
 // ------------------------------------------------------------------------------------
@@ -522,16 +553,18 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
     for (long long r = 0; r < nround; ++r) {
         const long long i = first + r * stride;
         const bool active = i < nsim;
-        const long long env = active ? i / nb : 0;
-        const int band = active ? (int)(i - env * nb) : 0;
+        // nb is 1, 2 or 4: shifts instead of 64-bit divisions
+        const int nbShift = nb == 4 ? 2 : (nb == 2 ? 1 : 0);
+        const long long env = active ? (i >> nbShift) : 0;
+        const int band = active ? (int)(i & (nb - 1)) : 0;
 
         SimT s;
         double srx[D * D];
         const BandParams &B = P.band[band];
-        DevRing ring{A.st.ring + (active ? i : 0), nsim};
+        DevRing ring{A.st.ring + (active ? i : 0), nsim, A.st.hot + (active ? i : 0)};
         int dev = 0, dur = 0;
         if (active) {
-            load_sim(s, A.st, i, A.st.now[env]);
+            load_sim<false, MODE != MODE_R>(s, A.st, i, A.st.now[env]);
             if (A.st.ntab == 1) {
 #pragma unroll
                 for (int k = 0; k < D * D; ++k) srx[k] = T.srx[band][(k / D) * kMaxDev + (k % D)];
@@ -552,7 +585,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
             s.assignDone = 1; s.fault = 0; s.now = 0;
         }
         const uint32_t nTx0 = active ? s.nTx : 0, nD0 = active ? s.nDeliv[0] : 0, nD1 = active ? s.nDeliv[1] : 0;
-        const uint32_t ties0 = active ? s.ties : 0;
+        const uint32_t ties0 = 0;           // the lean load starts the per-step tie counter at 0
 
         if (MODE == MODE_R) {
             if (active) run_until_assign<MODE_R>(s, P, B, srx, ring, NoMasks(), A.memo);
@@ -647,7 +680,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
             A.done[i] = dn;
             if (band == 0) A.st.now[env] = s.now;
             if (s.fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = s.fault; } }
-            store_sim(s, A.st, i, false);
+            store_sim<false, MODE != MODE_R>(s, A.st, i, false);
             acc[0] += rw;
             acc[1] += (double)(s.nDeliv[0] - nD0);
             acc[2] += (double)(s.nDeliv[1] - nD1);
@@ -731,7 +764,7 @@ pendulum_step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__
     }
     const uint32_t nTx0 = s.nTx, nD0 = s.nDeliv[0], nD1 = s.nDeliv[1];
     begin_assignment(s, P, dev, dur);
-    DevRing ring{A.st.ring + i, nsim};
+    DevRing ring{A.st.ring + i, nsim, A.st.hot + i};
     PendulumPlant<DevVals, DevSrxOut> plant(Q, S, DevVals{A.st.pval + i, nsim}, DevSrxOut{A.st.srx + i, A.st.ntab});
     run_until_assign_plant<MODE_R>(s, P, P.band[0], srx, ring, NoMasks(), NoMemo(), plant);
     // InvertedPendulumInterpreter (inverted_pendulum.py:42-56): the angle is read from the plant
@@ -803,7 +836,7 @@ __global__ void reset_kernel(StatePtrs st, Params P, const long long *env_ids, l
     const long long i = e * st.nb + band;
     Sim<D, NS, NJ> s;
     load_sim(s, st, i, st.now[e]);
-    DevRing ring{st.ring + i, st.nsim};
+    DevRing ring{st.ring + i, st.nsim, st.hot + i};
     reset_sim(s, P.band[band], ring);
     store_sim(s, st, i, true);
     if (obs) obs[i] = (long long)s.latestDiff + kCounterBound;       // counter_traffic.py:144

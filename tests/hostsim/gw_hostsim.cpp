@@ -19,6 +19,10 @@ struct HostRing {
     int32_t *data;      // [NS][100]
     int operator()(int k, uint32_t slot) const { return data[k * kQueueCap + slot]; }
     void operator()(int k, uint32_t slot, int v) { data[k * kQueueCap + slot] = v; }
+    // counter epochs (the device reads them from global memory on demand)
+    template <class S> uint64_t snapEnd(const S &s, int k) const { return get_at(s.snapEnd, k); }
+    template <class S> uint64_t epochK(const S &s, int k) const { return get_at(s.epochK, k); }
+    template <class S> int epochC(const S &s, int k) const { return get_at(s.epochC, k); }
 };
 
 struct HostMasks {
@@ -182,6 +186,8 @@ void hs_pendulum_advance(const double *params /* M m l g fMax kServo dtMax */, d
     pendulum_advance(Q, S, now);
     state[0] = S.x; state[1] = S.v; state[2] = S.th; state[3] = S.om; state[5] = S.tPlant;
 }
+
+double hs_fmod_slot(double t) { return fmod_slot(t); }
 
 double hs_fspl(double ax, double ay, double bx, double by, double f) { return fspl_db(ax, ay, bx, by, f); }
 

@@ -54,6 +54,8 @@ def lib():
         L.hs_fspl.restype = C.c_double
         L.hs_fspl.argtypes = [C.c_double] * 5
         L.hs_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hs_fmod_slot.restype = C.c_double
+        L.hs_fmod_slot.argtypes = [C.c_double]
         L.hs_pendulum_advance.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
         L.hs_mask_errors.restype = C.c_int64
         L.hs_mask_errors.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.c_int,

@@ -125,6 +125,20 @@ def test_arithmetic_close_to_reference():
         assert abs(got - att) <= 1e-12 * max(1.0, abs(att))
 
 
+def test_fmod_slot_is_bit_identical_to_libm():
+    """The kernel's fast slot alignment must equal fmod(t, 1e-6) bit for bit."""
+    import math
+    L = HS.lib()
+    rs = np.random.RandomState(0)
+    ts = np.concatenate([rs.uniform(0, 1e-5, 20000), rs.uniform(0, 1.0, 200000), rs.uniform(0, 1e4, 200000),
+                         10.0 ** rs.uniform(-9, 8, 200000),
+                         np.arange(1, 5000) * 1e-6, np.arange(1, 5000) * 1e-6 * (1 + 2.5e-8),
+                         np.nextafter(np.arange(1, 5000) * 1e-6, 0), np.nextafter(np.arange(1, 5000) * 1e-6, 1)])
+    for t in ts:
+        assert L.hs_fmod_slot(float(t)) == math.fmod(float(t), 1e-6), t
+    assert L.hs_fmod_slot(0.0) == 0.0
+
+
 def test_philox_known_answers():
     """Random123 kat_vectors for philox4x32-10."""
     L = HS.lib()
