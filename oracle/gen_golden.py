@@ -35,6 +35,7 @@ CASES = {
     "jammer_seed5": ("jammer", 5, 60),
     "longpacket_seed7": ("long", 7, 12),
     "multiband_seed9": ("multiband", 9, 24),
+    "mobility_seed13": ("mobility", 13, 80),
     "modeM_jammer_seed11": ("maskjammer", 11, 40),
     "modeM_default_seed12": ("maskdefault", 12, 60),
 }
@@ -62,6 +63,8 @@ def make_case(kind, seed, steps):
         sc = CR.random_scenario(rs, nbands=4, jammers=1, spread=2.5)
         tapes = [H.random_actions(steps, seed=seed + 4000 + b) for b in range(4)]
         tape = [list(x) for x in zip(*tapes)]
+    elif kind == "mobility":
+        sc, tape = CR.random_scenario(rs, jammers=0, spread=2.0), H.random_actions(steps, seed=seed + 8000)
     elif kind == "maskjammer":
         sc, tape = CR.random_scenario(rs, jammers=1, spread=2.5), H.random_actions(steps, seed=seed + 6000)
     elif kind == "maskdefault":
@@ -81,7 +84,13 @@ def child(name):
         H.install_masked_phy(lambda band, sender, seq, receiver, k0, k1, ber:
                              H.philox_mask_errors(MASK_SEED, MASK_ENV, band, sender, seq, receiver, k0, k1, ber), tr)
     env = H.make_default_env(tr) if use_default else H.ScenarioEnv(sc, tr)
-    trace = H.run_tape(env, tape, tr, do_reset=do_reset)
+    moves = None
+    if kind == "mobility":
+        # every 3rd step one device jumps to a new position (between steps: nothing is on the air)
+        mrs = np.random.RandomState(seed + 1)
+        moves = {t: [(0, int(mrs.randint(3)), float(mrs.uniform(-2.5, 2.5)), float(mrs.uniform(-2.5, 2.5)))]
+                 for t in range(2, steps, 3)}
+    trace = H.run_tape(env, tape, tr, do_reset=do_reset, moves=moves)
     doc = {"name": name, "kind": kind, "seed": seed, "do_reset": do_reset,
            "mode": "M" if mode_m else "R", "mask_seed": MASK_SEED if mode_m else None,
            "mask_env_id": MASK_ENV if mode_m else None,
@@ -89,6 +98,7 @@ def child(name):
            "reference_class": ("gymwipe.envs.CounterTrafficEnv" if use_default else "oracle.ref_harness.ScenarioEnv")
            + (" + oracle.ref_harness.MaskedPhy (SimplePhy subclass)" if mode_m else ""),
            "scenario": sc, "reset_obs": trace["reset_obs"],
+           "moves": {str(k): v for k, v in moves.items()} if moves else None,
            "steps": [{"action": s["action"], "obs": s["obs"], "reward": s["reward"], "done": s["done"],
                       "now": s["now"], "events": s["events"],
                       "records": [list(r) for r in s["records"]]} for s in trace["steps"]]}

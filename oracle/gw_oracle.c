@@ -1124,6 +1124,26 @@ int gwo_step(gwo_sim *s, const int32_t *device, const int32_t *duration,
     return 0;
 }
 
+/* Position.set (devices/core.py:75-84) -> FsplAttenuation._positionChanged -> _update
+ * (attenuation_models.py:28-39, physical.py:383-386).  Only valid while no transmission that
+ * involves the device is on the air (the restatement does not model _onAttenuationChange). */
+int gwo_set_position(gwo_sim *s, int band, int dev, double x, double y)
+{
+    Band *B = &s->band[band];
+    for (int i = 0; i < GWO_MAXTX; i++) if (B->tx[i].used) return -1;
+    B->dev[dev].x = x; B->dev[dev].y = y;
+    for (int j = 0; j < B->ndev; j++) {
+        if (j == dev) continue;
+        double d = sqrt(pow(B->dev[dev].x - B->dev[j].x, 2.0) + pow(B->dev[dev].y - B->dev[j].y, 2.0));
+        if (!(d < 3000.0)) continue;                              /* STANDBY_THRESHOLD, physical.py:371 */
+        if (B->dev[dev].x == B->dev[j].x && B->dev[dev].y == B->dev[j].y) continue;   /* _update returns early */
+        /* devices[0] / devices[1] order of the model is the frozenset order: the formula is symmetric */
+        double att = 20 * log10(d) + 20 * log10(B->frequency) - 147.55;
+        B->att[dev][j] = att; B->att[j][dev] = att;
+    }
+    return 0;
+}
+
 double gwo_now(const gwo_sim *s) { return s->now; }
 int64_t gwo_popped(const gwo_sim *s) { return s->popped; }
 int gwo_fault(const gwo_sim *s) { return s->fault; }

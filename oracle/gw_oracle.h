@@ -77,6 +77,7 @@ void gwo_set_mask_fn(gwo_sim *s, gwo_mask_fn fn, void *ctx, int64_t env_id);
 void gwo_reset(gwo_sim *s, int64_t *obs);
 int gwo_step(gwo_sim *s, const int32_t *device, const int32_t *duration,
              int64_t *obs, double *reward, uint8_t *done);
+int gwo_set_position(gwo_sim *s, int band, int dev, double x, double y);
 double gwo_now(const gwo_sim *s);
 int64_t gwo_popped(const gwo_sim *s);
 int gwo_fault(const gwo_sim *s);

@@ -71,6 +71,8 @@ def lib():
         L.gwo_step.restype = C.c_int
         L.gwo_step.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_uint8)]
+        L.gwo_set_position.restype = C.c_int
+        L.gwo_set_position.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
         L.gwo_now.restype = C.c_double
         L.gwo_now.argtypes = [C.c_void_p]
         L.gwo_popped.restype = C.c_int64
@@ -216,6 +218,11 @@ class Oracle:
             return [(int(o[i]), float(r[i]), bool(d[i])) for i in range(self.nb)]
         return int(o[0]), float(r[0]), bool(d[0])
 
+    def set_position(self, band, dev, x, y):
+        """``device.position.set(x, y)`` between steps (no transmission may be on the air)."""
+        if self.L.gwo_set_position(self.h, band, dev, float(x), float(y)) != 0:
+            raise OracleFault("a transmission is on the air: mid-packet attenuation changes are not modelled")
+
     @property
     def now(self):
         return float(self.L.gwo_now(self.h))
@@ -257,13 +264,15 @@ class Oracle:
         return out
 
 
-def run_tape(oracle, actions, do_reset=True):
+def run_tape(oracle, actions, do_reset=True, moves=None):
     """Same output structure as ``ref_harness.run_tape`` (without ``events``)."""
     out = {"reset_obs": None, "steps": []}
     if do_reset:
         out["reset_obs"] = oracle.reset()
     oracle.take_records()
-    for a in actions:
+    for t, a in enumerate(actions):
+        for (band, dev, x, y) in (moves or {}).get(t, []):
+            oracle.set_position(band, dev, x, y)
         p0 = oracle.popped
         fb = oracle.step(a)
         if isinstance(fb, list):

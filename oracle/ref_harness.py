@@ -438,7 +438,7 @@ class _InterpEnvView:
 # running action tapes
 # --------------------------------------------------------------------------
 
-def run_tape(env, actions, tracer, do_reset=True):
+def run_tape(env, actions, tracer, do_reset=True, moves=None):
     """
     Replays ``actions`` (list of dicts, or list of per-band lists of dicts) and
     returns a trace dict: per-step ``obs/reward/done/now/events`` plus the
@@ -449,7 +449,10 @@ def run_tape(env, actions, tracer, do_reset=True):
     if do_reset:
         out["reset_obs"] = env.reset()
     tracer.take()
-    for a in actions:
+    for t, a in enumerate(actions):
+        for (band, dev, x, y) in (moves or {}).get(t, []):
+            # Position.set -> nChange -> FsplAttenuation._update (devices/core.py:75-84)
+            env.bands[band]["devices"][dev].position.set(float(x), float(y))
         popped0 = SimMan.env.popped_events
         fb = env.step(a)
         if isinstance(fb, list):

@@ -167,6 +167,31 @@ def test_cuda_per_env_positions():
                 assert abs(got - want) <= BER_RTOL * abs(want)
 
 
+def test_cuda_moving_devices_match_reference_golden():
+    """gw_set_positions between steps vs the reference's Position.set (golden from the reference)."""
+    doc = load_golden("mobility_seed13")
+    moves = {int(k): [tuple(m) for m in v] for k, v in doc["moves"].items()}
+    devs = doc["scenario"]["bands"][0]["devices"]
+    pos = torch.zeros((1, 1, 4, 2), dtype=torch.float64)
+    for d, dv in enumerate(devs):
+        pos[0, 0, d, 0], pos[0, 0, d, 1] = dv["x"], dv["y"]
+    env = make_env(doc["scenario"], 1, strict=False, positions=pos.cuda())
+    if doc["do_reset"]:
+        env.reset()
+    for t, s in enumerate(doc["steps"]):
+        if t in moves:
+            for (_, d, x, y) in moves[t]:
+                pos[0, 0, d, 0], pos[0, 0, d, 1] = x, y
+            env.set_positions(pos.cuda())
+        a = s["action"]
+        o, r, dn, _ = env.step({"device": torch.tensor([a["device"]], dtype=torch.int32).cuda(),
+                                "duration": torch.tensor([a["duration"]], dtype=torch.int32).cuda()})
+        assert int(o[0]) == s["obs"] and float(r[0]) == s["reward"], t
+        assert float(env.read_state(0)[0]) == s["now"], t
+    n_rx = sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "rx")
+    assert int(env.delivered().sum()) == n_rx and n_rx > 0
+
+
 def _with_positions(sc, pos_env):
     import copy
     sc = copy.deepcopy(sc)

@@ -37,6 +37,17 @@ def test_restatement_matches_reference_trace(name):
         assert ora.near_ties == 0          # no decider threshold is within rounding distance
 
 
+def test_restatement_matches_reference_with_moving_devices():
+    """Devices move between steps (Position.set in the reference); goldens from the reference."""
+    doc = load_golden("mobility_seed13")
+    moves = {int(k): [tuple(m) for m in v] for k, v in doc["moves"].items()}
+    ora = O.Oracle(doc["scenario"], trace=True)
+    res = O.run_tape(ora, [s["action"] for s in doc["steps"]], do_reset=doc["do_reset"], moves=moves)
+    for i, (a, b) in enumerate(zip(doc["steps"], res["steps"])):
+        assert a["obs"] == b["obs"] and a["reward"] == b["reward"] and a["now"] == b["now"], i
+        assert canonical(a["records"]) == canonical(b["records"]), i
+
+
 def test_reference_known_answer():
     """tests/envs/test_counter_traffic.py:25-34 of the reference."""
     ora = O.Oracle()
