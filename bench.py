@@ -426,14 +426,30 @@ def own_arm(args, rank, world, local_rank):
     for k in range(KE):
         env2.step_host(h_dev[W + k], h_dur[W + k], h_obs, h_rew, h_done)
     torch.cuda.synchronize(dev_t)
+    e2e_wide_s = time.perf_counter() - t0
+    # packed variant (gw_step_host_packed): one copy in (8 B/env), one copy out (9 B/env)
+    h_act = torch.stack([h_dev, h_dur], dim=1).contiguous().pin_memory()      # [steps, 2, n]
+    h_res = torch.empty(9 * n, dtype=torch.uint8).pin_memory()
+    env3 = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, env_id_offset=rank * n, strict=False)
+    env3.reset()
+    for t in range(W):
+        env3.step_host_packed(h_act[t], h_res)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev_t)
+    t0 = time.perf_counter()
+    for k in range(KE):
+        env3.step_host_packed(h_act[W + k], h_res)
+    torch.cuda.synchronize(dev_t)
     e2e_s = time.perf_counter() - t0
-    checksum = float(h_rew.sum())
+    checksum = float(env3.unpack_results(h_res)[1].double().sum())
+    assert torch.equal(env3.unpack_results(h_res)[0].to(torch.int64), h_obs)   # both paths agree on the last step
 
     # max over ranks
     if world > 1:
-        v = torch.tensor([elapsed_ms, e2e_s, warm_ms, wall], dtype=torch.float64, device=dev_t)
+        v = torch.tensor([elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s], dtype=torch.float64, device=dev_t)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_s, warm_ms, wall = [float(x) for x in v]
+        elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s = [float(x) for x in v]
     if rank != 0:
         return 0
 
@@ -463,15 +479,18 @@ def own_arm(args, rank, world, local_rank):
                      "avg_launch_ms": kernel_ms,
                      "note": "mode-R state is ~190 B/env-step: the fused step kernel is latency / fp64-ALU bound, "
                              "not HBM bound (SURVEY.md 8d); the fraction is reported as required"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 17 * n,
-                "steps": KE, "api": "CounterTrafficEnv.step_host -> gw_step_host (pinned host buffers)",
-                "reward_checksum": checksum},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 9 * n,
+                "steps": KE, "api": "CounterTrafficEnv.step_host_packed -> gw_step_host_packed (pinned host buffers: "
+                                    "int32 actions [2][n] in, int32 obs | float32 reward | uint8 done out)",
+                "reward_checksum": checksum,
+                "wide_api": {"value": total_envs * KE / e2e_wide_s, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 17 * n,
+                             "api": "CounterTrafficEnv.step_host -> gw_step_host (int64 obs, float64 reward, uint8 done)"}},
         "gpu_launches": K,
         "clocks": clocks,
         "wall_s_timed_loop": wall,
     }
     if world == 1 and not args.no_extras:
-        del flush, env2
+        del flush, env2, env3
         torch.cuda.empty_cache()
         try:
             line["mask_scan"] = mask_scan_roofline(dev_t, peak, "random")

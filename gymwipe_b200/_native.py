@@ -107,6 +107,7 @@ _SIGNATURES = {
     "gw_reset": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
     "gw_step": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "gw_step_host": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "gw_step_host_packed": (C.c_int, [_VP, _VP, _VP, _VP]),
     "gw_check": (C.c_int, [_VP, _VP]),
     "gw_stats": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "gw_read_state": (C.c_int, [_VP, C.c_int, _VP, _VP]),

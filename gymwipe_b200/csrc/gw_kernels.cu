@@ -69,6 +69,7 @@ constexpr int COLD_CHUNKS = C_PER_DEV * kMaxDev + kMaxSend;
 struct StatePtrs {
     long long nsim, nenv, ntab;
     int nb;
+    int per_env;        // 1: one attenuation / power table per band-sim (ntab == nsim), 0: one shared table
     double *now;
     uint4 *hot;
     uint4 *cold;
@@ -522,6 +523,9 @@ struct StepArgs {
     int *errflag;
     MaskSource masks;
     DevMemo memo;
+    // compact outputs (gw_step_host_packed): used instead of obs / reward when non-NULL
+    int *obs32;
+    float *reward32;
 };
 
 struct SharedTables {
@@ -565,7 +569,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         int dev = 0, dur = 0;
         if (active) {
             load_sim<false, MODE != MODE_R>(s, A.st, i, A.st.now[env]);
-            if (A.st.ntab == 1) {
+            if (!A.st.per_env) {
 #pragma unroll
                 for (int k = 0; k < D * D; ++k) srx[k] = T.srx[band][(k / D) * kMaxDev + (k % D)];
             } else {
@@ -675,8 +679,8 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         if (active) {
             long long o; double rw; unsigned char dn;
             feedback(s, o, rw, dn);
-            A.obs[i] = o;
-            A.reward[i] = rw;
+            if (A.obs32) { A.obs32[i] = (int)o; A.reward32[i] = (float)rw; }
+            else { A.obs[i] = o; A.reward[i] = rw; }
             A.done[i] = dn;
             if (band == 0) A.st.now[env] = s.now;
             if (s.fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = s.fault; } }
@@ -770,9 +774,9 @@ pendulum_step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__
     // InvertedPendulumInterpreter (inverted_pendulum.py:42-56): the angle is read from the plant
     pendulum_advance(Q, S, s.now);
     const double deg = S.th * (180.0 / 3.141592653589793);
-    A.obs[i] = (long long)deg;                                 // int(degrees(angle)): truncation
     const double rw = fabs(180.0 - deg);
-    A.reward[i] = rw;
+    if (A.obs32) { A.obs32[i] = (int)deg; A.reward32[i] = (float)rw; }
+    else { A.obs[i] = (long long)deg; A.reward[i] = rw; }       // int(degrees(angle)): truncation
     A.done[i] = 0;
     A.st.now[i] = s.now;
     if (s.fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = s.fault; } }
@@ -850,7 +854,7 @@ __global__ void tables_kernel(StatePtrs st, const double *pos /* [ntab][MAXD][2]
     if (t >= st.ntab * 16) return;
     const long long tab = t / 16;
     const int k = (int)(t % 16), p = k / kMaxDev, d = k % kMaxDev;
-    const int band = (int)((st.ntab == 1 ? 0 : tab) % st.nb);
+    const int band = (int)((st.per_env ? tab : 0) % st.nb);
     double px, py, dx, dy;
     if (pos) {
         px = pos[(tab * kMaxDev + p) * 2]; py = pos[(tab * kMaxDev + p) * 2 + 1];
@@ -893,10 +897,10 @@ __global__ void read_kernel(StatePtrs st, Params P, int field, double *out)
     case GW_FIELD_N_DELIVERED: for (int k = 0; k < NS; ++k) out[k * n + i] = s.nDeliv[k]; break;
     case GW_FIELD_RECEIVED_VALUES: out[i] = s.rv0; out[n + i] = s.rv1; break;
     case GW_FIELD_ATTENUATION_DB:
-        for (int k = 0; k < 16; ++k) out[k * n + i] = st.att[(long long)k * st.ntab + (st.ntab == 1 ? 0 : i)];
+        for (int k = 0; k < 16; ++k) out[k * n + i] = st.att[(long long)k * st.ntab + (st.per_env ? i : 0)];
         break;
     case GW_FIELD_RX_POWER_MW:
-        for (int k = 0; k < 16; ++k) out[k * n + i] = st.srx[(long long)k * st.ntab + (st.ntab == 1 ? 0 : i)];
+        for (int k = 0; k < 16; ++k) out[k * n + i] = st.srx[(long long)k * st.ntab + (st.per_env ? i : 0)];
         break;
     case GW_FIELD_FAULT: out[i] = s.fault; break;
     case GW_FIELD_TIES: out[i] = s.ties; break;
@@ -1277,6 +1281,7 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
     }
     char *base = (char *)state;
     h->st.nenv = cfg->n_envs; h->st.nb = cfg->n_bands; h->st.nsim = cfg->n_envs * cfg->n_bands; h->st.ntab = ntab;
+    h->st.per_env = cfg->per_env_positions ? 1 : 0;
     h->st.now = (double *)(base + h->layout.off_now);
     h->st.hot = (uint4 *)(base + h->layout.off_hot);
     h->st.cold = (uint4 *)(base + h->layout.off_cold);
@@ -1321,7 +1326,7 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
         // per-env geometries: ~20 recurring pairs per band-sim, so the table scales with the batch
         // (32 entries per band-sim, 32 B each, capped at 2 GiB)
         h->memo_entries = 1u << 14;
-        if (ntab > 1) {
+        if (cfg->per_env_positions) {
             unsigned long long want = 32ull * (unsigned long long)nsim;
             while (h->memo_entries < want && h->memo_entries < (1u << 26)) h->memo_entries <<= 1;
         }
@@ -1364,7 +1369,7 @@ void gw_destroy(gw_handle *h)
 int gw_set_positions(gw_handle *h, const double *positions, void *stream)
 {
     if (!h) return fail(GW_E_INVALID, "handle is NULL");
-    if (positions && h->st.ntab == 1) return fail(GW_E_INVALID, "handle was created with per_env_positions = 0");
+    if (positions && !h->st.per_env) return fail(GW_E_INVALID, "handle was created with per_env_positions = 0");
     CUDA_TRY(cudaSetDevice(h->device));
     return launch_tables(h, positions, (cudaStream_t)stream);
 }
@@ -1384,7 +1389,7 @@ int gw_reset(gw_handle *h, const int64_t *env_ids, int64_t n, int64_t *obs, void
 }
 
 static int launch_step(gw_handle *h, const int32_t *device, const int32_t *duration, int64_t *obs, double *reward,
-                       uint8_t *done, cudaStream_t s)
+                       uint8_t *done, cudaStream_t s, int *obs32 = nullptr, float *reward32 = nullptr)
 {
     if (h->cfg.mode == GW_MODE_MASK_FED && !h->masks) return fail(GW_E_INVALID, "mode MASK_FED: call gw_set_masks first");
     StepArgs A;
@@ -1392,12 +1397,13 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     A.device = device; A.duration = duration;
     A.obs = (long long *)obs; A.reward = reward; A.done = done;
     A.stats = h->stats; A.errflag = h->errflag;
+    A.obs32 = obs32; A.reward32 = reward32;
     A.masks.mode = h->cfg.mode; A.masks.seed = h->cfg.seed; A.masks.env_offset = h->cfg.env_id_offset;
     A.masks.words = h->masks; A.masks.slots = h->mask_slots > 0 ? h->mask_slots : 1; A.masks.words_per_row = h->mask_words;
     A.memo.tab = h->memo; A.memo.mask = h->memo_entries ? h->memo_entries - 1 : 0;
     SharedTables T;
     std::memset(&T, 0, sizeof T);
-    if (h->st.ntab == 1) {
+    if (!h->st.per_env) {
         for (int b = 0; b < h->cfg.n_bands; ++b)
             for (int p = 0; p < kMaxDev; ++p)
                 for (int d = 0; d < kMaxDev; ++d) {
@@ -1455,6 +1461,26 @@ int gw_step_host(gw_handle *h, const int32_t *device, const int32_t *duration, i
     CUDA_TRY(cudaMemcpyAsync(obs, h->d_obs, n * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(reward, h->d_rew, n * 8, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(done, h->d_done, n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GW_OK;
+}
+
+int gw_step_host_packed(gw_handle *h, const int32_t *actions, void *results, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    if (!actions || !results) return fail(GW_E_INVALID, "NULL buffer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long n = h->st.nsim;
+    // staging: d_dev and d_dur are adjacent (actions [2][n]); the compact results reuse the
+    // obs / reward staging area: int32 obs[n] | float reward[n] | uint8 done[n]
+    CUDA_TRY(cudaMemcpyAsync(h->d_dev, actions, n * 8, cudaMemcpyHostToDevice, s));
+    int *obs32 = (int *)h->d_obs;
+    float *rew32 = (float *)(obs32 + n);
+    unsigned char *done8 = (unsigned char *)(rew32 + n);
+    const int rc = launch_step(h, h->d_dev, h->d_dur, nullptr, nullptr, done8, s, obs32, rew32);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(results, obs32, n * 9, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return GW_OK;
 }

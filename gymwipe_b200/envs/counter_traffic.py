@@ -366,6 +366,24 @@ class CounterTrafficEnv(BaseEnv):
             N.check(self._lib.gw_step_host(self._handle, ptr(device), ptr(duration), ptr(obs), ptr(reward),
                                            ptr(done), self._stream()))
 
+    def step_host_packed(self, actions, results):
+        """
+        Throughput variant of :meth:`step_host` (``gw_step_host_packed``): ``actions`` is a pinned
+        int32 tensor / array ``[2, n_sims]`` (row 0 device, row 1 duration), ``results`` a pinned
+        uint8 buffer of ``9 * n_sims`` bytes that receives ``int32 obs | float32 reward | uint8 done``.
+        Use :meth:`unpack_results` for typed views.  One copy in, one copy out.
+        """
+        def ptr(a):
+            return a.data_ptr() if torch.is_tensor(a) else a.ctypes.data
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gw_step_host_packed(self._handle, ptr(actions), ptr(results), self._stream()))
+
+    def unpack_results(self, results):
+        """Typed views (obs int32, reward float32, done uint8) of a packed result buffer."""
+        n = self.num_envs * self.n_bands
+        r = results if torch.is_tensor(results) else torch.from_numpy(results)
+        return r[:4 * n].view(torch.int32), r[4 * n:8 * n].view(torch.float32), r[8 * n:9 * n]
+
     def render(self, mode='human', close=False):
         """``counter_traffic.py:160-162`` (env 0)."""
         values = [int(x) for x in self.received_values()[0]]

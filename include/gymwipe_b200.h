@@ -155,6 +155,13 @@ int gw_step(gw_handle *h, const int32_t *device, const int32_t *duration,
 int gw_step_host(gw_handle *h, const int32_t *device, const int32_t *duration,
                  int64_t *obs, double *reward, uint8_t *done, void *stream);
 
+/* Packed host-buffer variant for throughput-bound callers: ONE host-to-device copy of
+ * `actions` = int32 [2][n_sims] (row 0 action["device"], row 1 action["duration"]) and ONE
+ * device-to-host copy of `results` = { int32 obs[n_sims]; float reward[n_sims]; uint8 done[n_sims] }
+ * laid out back to back (9 bytes per sim; obs and reward are small integers, exactly representable).
+ * Synchronises the stream. */
+int gw_step_host_packed(gw_handle *h, const int32_t *actions, void *results, void *stream);
+
 /* Synchronises and reports the error flag the kernels raised since the last call:
  * 0, GW_E_ACTION or GW_E_SIMFAULT (with the first faulting env in the message). */
 int gw_check(gw_handle *h, void *stream);

@@ -290,6 +290,27 @@ def test_step_host_end_to_end():
         assert (rew.numpy() == o["reward"][t, :, 0]).all()
 
 
+def test_step_host_packed_end_to_end():
+    from gymwipe_b200.scenario import default_scenario_dict
+    sc = default_scenario_dict()
+    rs = np.random.RandomState(18)
+    n = 4096
+    dev, dur = random_tapes(rs, 20, n, 1)
+    o = O.run_batch(sc, dev, dur)
+    env = make_env(sc, n, strict=False)
+    env.reset()
+    act = torch.empty((2, n), dtype=torch.int32).pin_memory()
+    res = torch.empty(9 * n, dtype=torch.uint8).pin_memory()
+    for t in range(20):
+        act[0].copy_(torch.as_tensor(dev[t, :, 0]))
+        act[1].copy_(torch.as_tensor(dur[t, :, 0]))
+        env.step_host_packed(act, res)
+        obs, rew, done = env.unpack_results(res)
+        assert (obs.numpy() == o["obs"][t, :, 0]).all()
+        assert (rew.numpy().astype(np.float64) == o["reward"][t, :, 0]).all()
+        assert not done.numpy().any()
+
+
 def test_stats_epilogue():
     from gymwipe_b200.scenario import default_scenario_dict
     sc = default_scenario_dict()
