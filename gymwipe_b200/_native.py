@@ -106,6 +106,7 @@ _SIGNATURES = {
     "gw_set_positions": (C.c_int, [_VP, _VP, _VP]),
     "gw_reset": (C.c_int, [_VP, _VP, C.c_int64, _VP, _VP]),
     "gw_step": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "gw_step_traced": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
     "gw_step_host": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "gw_step_host_packed": (C.c_int, [_VP, _VP, _VP, _VP]),
     "gw_check": (C.c_int, [_VP, _VP]),

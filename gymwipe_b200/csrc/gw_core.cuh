@@ -219,7 +219,25 @@ struct Sim {
     // statistics
     uint32_t nTx;
     uint32_t nDeliv[NS];
+
+    // optional event trace (traced step variant only; nullptr in the production kernels, where
+    // every recording site folds away): records of 8 doubles {kind, t, dev, x0, x1, x2, x3, -}
+    double *trace;
+    int ntrace, traceCap;
 };
+
+enum : int { REC_TX = 1, REC_BER = 2, REC_DEC = 3, REC_RX = 4 };
+
+template <int D, int NS, int NJ>
+GW_HD void trace_rec(Sim<D, NS, NJ> &s, int kind, double t, int dev, double x0, double x1, double x2, double x3)
+{
+    if (s.trace == nullptr) return;
+    if (s.ntrace < s.traceCap) {
+        double *r = s.trace + (long long)s.ntrace * 8;
+        r[0] = kind; r[1] = t; r[2] = dev; r[3] = x0; r[4] = x1; r[5] = x2; r[6] = x3; r[7] = 0;
+    }
+    s.ntrace += 1;
+}
 
 struct Event {
     int kind, idx;
@@ -253,6 +271,7 @@ GW_HD void init_sim(Sim<D, NS, NJ> &s, double thermal)
     s.annDest = 0; s.annBytes = 0; s.annSlots = 0; s.rrmPend = 0; s.tRrm = 0; s.sRrm = 0; s.assignDone = 0;
     s.rv0 = s.rv1 = 0; s.latestDiff = 0; s.lastAbsDiff = 0; s.done = 0;
     s.nTx = 0;
+    s.trace = nullptr; s.ntrace = 0; s.traceCap = 0;
 }
 
 GW_HD bool seq_before(uint32_t a, uint32_t b) { return (int32_t)(a - b) < 0; }
@@ -556,6 +575,14 @@ GW_HD bool decide(const Sim<D, NS, NJ> &s, const Params &P, int p, double totalB
     return rint(e) / totalBits <= P.maxBer;
 }
 
+template <int D, int NS, int NJ>
+GW_HD bool decide_rec(Sim<D, NS, NJ> &s, const Params &P, int p, int section, double totalBits)
+{
+    const bool ok = decide(s, P, p, totalBits);
+    trace_rec(s, REC_DEC, s.now, p, section, get_at(s.err, p), totalBits, ok ? 1.0 : 0.0);
+    return ok;
+}
+
 // ---------------------------------------------------------------------------
 // transition function: applies one timed event (counts already done); returns the set of
 // PHYs whose bit error rate must be re-evaluated afterwards (SimplePhy._updateBitErrorRate)
@@ -626,6 +653,7 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
             set_at(s.tStop, d, stop);
             set_at(s.txSeq, d, get_at(s.txSeq, d) + 1u);
             s.nTx += 1;
+            trace_rec(s, REC_TX, s.now, d, stop, (hdrBytes * 8) * P.bitsFactor, (payBytes * 8) * P.bitsFactor, 0.0);
             if (Plant::active) plant.refresh_links(d, s.now, srx);
             // zero-delay notification: every other PHY registers the received power
             // (simple_stack.py:130-144); a PHY that is receiving re-evaluates its BER
@@ -656,7 +684,7 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
             GW_UNROLL
             for (int p = 0; p < D; ++p) {
                 if (s.rxOf[p] != d || s.rxSec[p] != 0) continue;
-                if (decide(s, P, p, hdrBits)) {
+                if (decide_rec(s, P, p, 0, hdrBits)) {
                     s.rxSec[p] = 1; s.err[p] = 0; s.ber[p] = 0.0; s.tReset[p] = s.now; s.segT0[p] = s.now;
                     berMask |= 1 << p;
                 } else {
@@ -698,7 +726,7 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
             GW_UNROLL
             for (int p = 0; p < D; ++p) {
                 if (s.rxOf[p] != d || s.rxSec[p] != 1) continue;
-                if (decide(s, P, p, payBits)) {
+                if (decide_rec(s, P, p, 1, payBits)) {
                     if (Plant::active && d != RRM) plant.delivered(d, p, get_at(s.txVal, d), s.now);
                     if (p < NS) {
                         // SimpleMac.phyInHandler (blocking, not queued): only an announcement
@@ -715,6 +743,10 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
                             if (d == 1) s.rv1 = kCounterByteLen;
                             s.latestDiff = s.rv0 - s.rv1;
                             set_at(s.nDeliv, d, get_at(s.nDeliv, d) + 1u);
+                            trace_rec(s, REC_RX, s.now, d, 0.0, 0.0, 0.0, 0.0);
+                        } else {
+                            // a PHY-only sender's packet: the interpreter sees it, nothing changes
+                            trace_rec(s, REC_RX, s.now, d, 0.0, 0.0, 0.0, 0.0);
                         }
                     }
                 }
@@ -806,6 +838,7 @@ GW_HD void update_bers(Sim<D, NS, NJ> &s, const Params &P, int berMask, const do
             memo.put(S, N, ber);
         }
         s.ber[p] = ber;
+        trace_rec(s, REC_BER, s.now, p, ber, 0.0, 0.0, 0.0);
     }
 }
 

@@ -300,6 +300,7 @@ __device__ __forceinline__ void load_sim(Sim<D, NS, NJ> &s, const StatePtrs &st,
         for (int k = 0; k < NS; ++k) { s.stopW[k] = 0; s.sW[k] = 0; }
     }
     s.annDest = 0; s.annBytes = 0; s.annSlots = 0; s.rrmPend = 0; s.tRrm = 0; s.sRrm = 0; s.assignDone = 0;
+    s.trace = nullptr; s.ntrace = 0; s.traceCap = 0;
 }
 
 template <bool FULL = true, bool WITH_SEG = true, int D, int NS, int NJ>
@@ -526,6 +527,10 @@ struct StepArgs {
     // compact outputs (gw_step_host_packed): used instead of obs / reward when non-NULL
     int *obs32;
     float *reward32;
+    // event trace (gw_step_traced)
+    double *trace;
+    int *traceCount;
+    int traceCap;
 };
 
 struct SharedTables {
@@ -536,7 +541,7 @@ struct SharedTables {
 #define GW_STEP_MIN_BLOCKS 4
 #endif
 
-template <int MODE, int D, int NS, int NJ>
+template <int MODE, int D, int NS, int NJ, bool TRACE = false>
 __global__ void __launch_bounds__(128, GW_STEP_MIN_BLOCKS)
 step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P,
             const __grid_constant__ SharedTables T)
@@ -576,6 +581,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
 #pragma unroll
                 for (int k = 0; k < D * D; ++k) srx[k] = A.st.srx[(long long)((k / D) * kMaxDev + (k % D)) * A.st.ntab + i];
             }
+            if (TRACE) { s.trace = A.trace + (long long)i * A.traceCap * 8; s.traceCap = A.traceCap; s.ntrace = 0; }
             dev = A.device[i];
             dur = A.duration[i];
             // assert self.action_space.contains(action)  (counter_traffic.py:147)
@@ -685,6 +691,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
             if (band == 0) A.st.now[env] = s.now;
             if (s.fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = s.fault; } }
             store_sim<false, MODE != MODE_R>(s, A.st, i, false);
+            if (TRACE) A.traceCount[i] = s.ntrace;
             acc[0] += rw;
             acc[1] += (double)(s.nDeliv[0] - nD0);
             acc[2] += (double)(s.nDeliv[1] - nD1);
@@ -1389,7 +1396,8 @@ int gw_reset(gw_handle *h, const int64_t *env_ids, int64_t n, int64_t *obs, void
 }
 
 static int launch_step(gw_handle *h, const int32_t *device, const int32_t *duration, int64_t *obs, double *reward,
-                       uint8_t *done, cudaStream_t s, int *obs32 = nullptr, float *reward32 = nullptr)
+                       uint8_t *done, cudaStream_t s, int *obs32 = nullptr, float *reward32 = nullptr,
+                       double *trace = nullptr, int *trace_count = nullptr, int trace_cap = 0)
 {
     if (h->cfg.mode == GW_MODE_MASK_FED && !h->masks) return fail(GW_E_INVALID, "mode MASK_FED: call gw_set_masks first");
     StepArgs A;
@@ -1398,6 +1406,7 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     A.obs = (long long *)obs; A.reward = reward; A.done = done;
     A.stats = h->stats; A.errflag = h->errflag;
     A.obs32 = obs32; A.reward32 = reward32;
+    A.trace = trace; A.traceCount = trace_count; A.traceCap = trace_cap;
     A.masks.mode = h->cfg.mode; A.masks.seed = h->cfg.seed; A.masks.env_offset = h->cfg.env_id_offset;
     A.masks.words = h->masks; A.masks.slots = h->mask_slots > 0 ? h->mask_slots : 1; A.masks.words_per_row = h->mask_words;
     A.memo.tab = h->memo; A.memo.mask = h->memo_entries ? h->memo_entries - 1 : 0;
@@ -1427,7 +1436,8 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     if (blocks > cap) blocks = cap;
 #define CALL_STEP(DD, SS, JJ)                                                                        \
     do {                                                                                             \
-        if (h->cfg.mode == GW_MODE_REFERENCE) step_kernel<MODE_R, DD, SS, JJ><<<blocks, 128, 0, s>>>(A, h->P, T);       \
+        if (trace) step_kernel<MODE_R, DD, SS, JJ, true><<<blocks, 128, 0, s>>>(A, h->P, T);           \
+        else if (h->cfg.mode == GW_MODE_REFERENCE) step_kernel<MODE_R, DD, SS, JJ><<<blocks, 128, 0, s>>>(A, h->P, T);  \
         else if (h->cfg.mode == GW_MODE_MASK_PHILOX) step_kernel<MODE_M_PHILOX, DD, SS, JJ><<<blocks, 128, 0, s>>>(A, h->P, T); \
         else step_kernel<MODE_M_FED, DD, SS, JJ><<<blocks, 128, 0, s>>>(A, h->P, T);                    \
     } while (0)
@@ -1444,6 +1454,16 @@ int gw_step(gw_handle *h, const int32_t *device, const int32_t *duration, int64_
     if (!device || !duration || !obs || !reward || !done) return fail(GW_E_INVALID, "NULL buffer");
     CUDA_TRY(cudaSetDevice(h->device));
     return launch_step(h, device, duration, obs, reward, done, (cudaStream_t)stream);
+}
+
+int gw_step_traced(gw_handle *h, const int32_t *device, const int32_t *duration, int64_t *obs, double *reward,
+                   uint8_t *done, double *trace, int32_t *trace_count, int32_t cap, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    if (!device || !duration || !obs || !reward || !done || !trace || !trace_count || cap < 1) return fail(GW_E_INVALID, "bad argument");
+    if (h->cfg.mode != GW_MODE_REFERENCE || h->cfg.plant) return fail(GW_E_INVALID, "tracing is available in GW_MODE_REFERENCE without a plant");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return launch_step(h, device, duration, obs, reward, done, (cudaStream_t)stream, nullptr, nullptr, trace, trace_count, cap);
 }
 
 int gw_step_host(gw_handle *h, const int32_t *device, const int32_t *duration, int64_t *obs, double *reward,

@@ -354,6 +354,47 @@ class CounterTrafficEnv(BaseEnv):
         self._last_obs, self._last_reward, self._last_done = obs, reward, done.bool()
         return obs, reward, self._last_done, LazyInfo(self)
 
+    def step_traced(self, action, cap=1024):
+        """
+        :meth:`step` plus the device-side event trace (``gw_step_traced``): returns
+        ``(obs, reward, done, records)`` where ``records[sim]`` is the list of
+        ``("tx", t, band, sender, stop, headerBits, payloadBits)`` /
+        ``("ber", t, band, receiver, ber)`` / ``("dec", t, band, receiver, section, errSum, bits, ok)`` /
+        ``("rx", t, band, senderIndex)`` tuples of that band-sim, in event order -- the read-back
+        view of the reference's ``Transmission`` objects and decider verdicts.
+        """
+        dev, dur = self._prepare_action(action)
+        nsim = self.num_envs * self.n_bands
+        obs = torch.empty(self._shape, dtype=torch.int64, device=self.device)
+        reward = torch.empty(self._shape, dtype=torch.float64, device=self.device)
+        done = torch.empty(self._shape, dtype=torch.uint8, device=self.device)
+        trace = torch.zeros((nsim, cap, 8), dtype=torch.float64, device=self.device)
+        count = torch.zeros(nsim, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gw_step_traced(self._handle, dev.data_ptr(), dur.data_ptr(), obs.data_ptr(),
+                                             reward.data_ptr(), done.data_ptr(), trace.data_ptr(), count.data_ptr(),
+                                             int(cap), self._stream()))
+        self.check()
+        tr, cn = trace.cpu().numpy(), count.cpu().numpy()
+        if (cn > cap).any():
+            raise RuntimeError("trace truncated: raise cap (max count %d)" % int(cn.max()))
+        records = []
+        for i in range(nsim):
+            band = i % self.n_bands
+            out = []
+            for r in tr[i, :cn[i]]:
+                k = int(r[0])
+                if k == 1:
+                    out.append(("tx", float(r[1]), band, int(r[2]), float(r[3]), float(r[4]), float(r[5])))
+                elif k == 2:
+                    out.append(("ber", float(r[1]), band, int(r[2]), float(r[3])))
+                elif k == 3:
+                    out.append(("dec", float(r[1]), band, int(r[2]), int(r[3]), float(r[4]), float(r[5]), bool(r[6])))
+                elif k == 4:
+                    out.append(("rx", float(r[1]), band, int(r[2])))
+            records.append(out)
+        return obs, reward, done.bool(), records
+
     def step_host(self, device, duration, obs, reward, done):
         """
         End-to-end step with HOST buffers (numpy arrays or pinned CPU tensors): actions are

@@ -149,6 +149,19 @@ int gw_reset(gw_handle *h, const int64_t *env_ids, int64_t n, int64_t *obs, void
 int gw_step(gw_handle *h, const int32_t *device, const int32_t *duration,
             int64_t *obs, double *reward, uint8_t *done, void *stream);
 
+/* gw_step with an event trace (debugging / parity checks; mode R): every band-sim appends
+ * records of 8 float64 {kind, time, device, x0, x1, x2, x3, 0} to trace[sim][cap][8] and its record
+ * count to trace_count[sim] (counts above `cap` mean truncation):
+ *   kind 1 transmission start (Transmission, physical.py:224-279): device = sender, x0 = stopTime,
+ *          x1 = headerBits, x2 = payloadBits
+ *   kind 2 SimplePhy._updateBitErrorRate (simple_stack.py:161-173): device = receiver, x0 = BER
+ *   kind 3 SimplePhy._decide (simple_stack.py:269-286): device = receiver, x0 = section (0 header,
+ *          1 payload), x1 = bit error sum, x2 = total bits, x3 = verdict
+ *   kind 4 interpreter.onPacketReceived (devices.py:163-168): device = sender index */
+int gw_step_traced(gw_handle *h, const int32_t *device, const int32_t *duration,
+                   int64_t *obs, double *reward, uint8_t *done,
+                   double *trace, int32_t *trace_count, int32_t cap, void *stream);
+
 /* Same call with HOST buffers (pinned or pageable): copies the actions in, steps, copies
  * obs / reward / done out and synchronises the stream.  This is the end-to-end path a
  * gym-style caller with host-resident actions uses. */

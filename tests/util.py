@@ -37,6 +37,16 @@ def canonical(records):
     return out
 
 
+def canonical_per_band(records):
+    """Like :func:`canonical`, with the tx/rx records grouped per band as well: the bands of an
+    env are independent simulations, only their order WITHIN a band is meaningful."""
+    records = [tuple(r) for r in records]
+    out = []
+    for b in sorted({r[2] for r in records}):
+        out += canonical([r for r in records if r[2] == b])
+    return out
+
+
 def tapes_from_golden(doc):
     """-> dev, dur int32 arrays [steps, 1, nbands]"""
     nb = len(doc["scenario"]["bands"])
