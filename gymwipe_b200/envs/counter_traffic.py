@@ -198,6 +198,7 @@ class CounterTrafficEnv(BaseEnv):
         if positions is not None:
             self.set_positions(positions)
         self._shape = (self.num_envs,) if self.n_bands == 1 else (self.num_envs, self.n_bands)
+        self._shape_t = torch.Size(self._shape)
         self._last_obs = self.COUNTER_BOUND
         self._last_reward = 0.0
         self._last_done = False
@@ -328,31 +329,53 @@ class CounterTrafficEnv(BaseEnv):
             out.append(v)
         return out
 
+    def _fast_action(self, action):
+        """Zero-copy path: a dict of contiguous int32 CUDA tensors of the batch shape."""
+        if type(action) is dict and len(action) == 2:
+            dev, dur = action.get("device"), action.get("duration")
+            if (torch.is_tensor(dev) and torch.is_tensor(dur) and dev.dtype == torch.int32 and dur.dtype == torch.int32
+                    and dev.device == self.device and dur.device == self.device
+                    and dev.shape == self._shape_t and dur.shape == self._shape_t
+                    and dev.is_contiguous() and dur.is_contiguous()):
+                return dev, dur
+        return None
+
     def step(self, action):
         """
         ``counter_traffic.py:146-158``: assigns the band (``action["device"]``) for
         ``action["duration"] * ASSIGNMENT_DURATION_FACTOR`` slots in every env and simulates
         until the assignment ends.  Returns ``(obs, reward, done, info)``.
         """
-        scalar = self._scalar_api and self.n_bands == 1 and isinstance(action, dict) and \
-            not torch.is_tensor(action.get("device"))
-        if scalar:
-            assert self.action_space.contains(action)
-        dev, dur = self._prepare_action(action)
+        fast = self._fast_action(action)
+        scalar = False
+        if fast is not None:
+            dev, dur = fast
+        else:
+            scalar = self._scalar_api and self.n_bands == 1 and isinstance(action, dict) and \
+                not torch.is_tensor(action.get("device"))
+            if scalar:
+                assert self.action_space.contains(action)
+            dev, dur = self._prepare_action(action)
         obs = torch.empty(self._shape, dtype=torch.int64, device=self.device)
         reward = torch.empty(self._shape, dtype=torch.float64, device=self.device)
-        done = torch.empty(self._shape, dtype=torch.uint8, device=self.device)
-        with torch.cuda.device(self.device):
-            N.check(self._lib.gw_step(self._handle, dev.data_ptr(), dur.data_ptr(), obs.data_ptr(),
-                                      reward.data_ptr(), done.data_ptr(), self._stream()))
+        done = torch.empty(self._shape, dtype=torch.bool, device=self.device)
+        if torch.cuda.current_device() == self.device.index:
+            rc = self._lib.gw_step(self._handle, dev.data_ptr(), dur.data_ptr(), obs.data_ptr(),
+                                   reward.data_ptr(), done.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        else:
+            with torch.cuda.device(self.device):
+                rc = self._lib.gw_step(self._handle, dev.data_ptr(), dur.data_ptr(), obs.data_ptr(),
+                                       reward.data_ptr(), done.data_ptr(), self._stream())
+        if rc:
+            N.check(rc)
         if self.strict:
             self.check()
         if scalar:
             self._last_obs, self._last_reward = int(obs[0]), float(reward[0])
             self._last_done = bool(done[0])
             return self._last_obs, self._last_reward, self._last_done, self.rrm.interpreter.getInfo()
-        self._last_obs, self._last_reward, self._last_done = obs, reward, done.bool()
-        return obs, reward, self._last_done, LazyInfo(self)
+        self._last_obs, self._last_reward, self._last_done = obs, reward, done
+        return obs, reward, done, LazyInfo(self)
 
     def step_traced(self, action, cap=1024):
         """
