@@ -159,13 +159,51 @@ GW_HD int64_t mask_errors_serial(uint64_t seed, int64_t env, int band, int sende
 }
 
 // ---------------------------------------------------------------------------
+// storage of the per-device / per-sender state arrays
+//
+// The transition function indexes these arrays with RUN-TIME device indices.  Two storages:
+//  * RegArr  -- a plain array that the compiler keeps in registers; run-time indices are resolved
+//    by fully unrolled selects (get_at / set_at), because a dynamically indexed member would push
+//    the whole state struct into local memory.  Used by the host build and for the fields of the
+//    tick loop.
+//  * a "direct" storage supplied by the kernels (shared memory, [field][index][thread]) where a
+//    run-time index is just an address computation.
+// ---------------------------------------------------------------------------
+
+template <class T, int N>
+struct RegArr {
+    T v[N];
+    using value_type = T;
+    static constexpr int size = N;
+    static constexpr bool direct = false;
+    GW_HD T &operator[](int i) { return v[i]; }
+    GW_HD const T &operator[](int i) const { return v[i]; }
+};
+
+struct RegStore {
+    template <class T, int N, int OFF> using Arr = RegArr<T, N>;
+    template <class T, int N> using Aux = RegArr<T, N>;     // mode-M / plant-only arrays
+};
+
+// ---------------------------------------------------------------------------
 // band-sim state
 // ---------------------------------------------------------------------------
 
-template <int D, int NS, int NJ>
+template <int D, int NS, int NJ, class ST = RegStore>
 struct Sim {
     static constexpr int kD = D, kNS = NS, kNJ = NJ, kRrm = NS;
     static constexpr int NJa = NJ > 0 ? NJ : 1;
+    // byte offsets (per thread) of the arrays inside a direct storage
+    enum : int {
+        O_P = 0, O_tEv = O_P + 8 * D, O_txStart = O_tEv + 8 * D, O_tStop = O_txStart + 8 * D, O_tC = O_tStop + 8 * D,
+        O_ber = O_tC + 8 * D, O_err = O_ber + 8 * D, O_tReset = O_err + 8 * D, O_stopW = O_tReset + 8 * D,
+        O_sphase = O_stopW + 8 * NS, O_sEv = O_sphase + 4 * D, O_sC = O_sEv + 4 * D, O_cmdPay = O_sC + 4 * D,
+        O_txSeq = O_cmdPay + 4 * D, O_rxOf = O_txSeq + 4 * D, O_rxSec = O_rxOf + 4 * D,
+        O_mac = O_rxSec + 4 * D, O_wDone = O_mac + 4 * NS, O_wPend = O_wDone + 4 * NS, O_sW = O_wPend + 4 * NS,
+        O_nDeliv = O_sW + 4 * NS, kDirectBytes = O_nDeliv + 4 * NS
+    };
+    template <class T, int N, int OFF> using Arr = typename ST::template Arr<T, N, OFF>;
+    template <class T, int N> using Aux = typename ST::template Aux<T, N>;
 
     double now;
     uint32_t seq;                       // creation counter of timed events (the eid order)
@@ -173,37 +211,42 @@ struct Sim {
     uint32_t ties;                      // exact-time ties between independent events (diagnostic)
 
     // PHY, per device
-    double P[D];                        // SimplePhy._receivedPower (mW), simple_stack.py:80-82
-    int sphase[D];                      // S_*: macInHandler progress (simple_stack.py:192-212)
-    double tEv[D];                      // next PHY event: slot start / header end / completion
-    uint32_t sEv[D];
-    double txStart[D], tStop[D], tC[D]; // Transmission.startTime / stopTime / eCompletes time
-    uint32_t sC[D];
-    int cmdPay[D];                      // payload bytes of the SEND command in flight
-    double txVal[D];                    // payload.value of the packet in flight (plant envs only)
-    uint32_t txSeq[D];                  // transmissions started by this device (mode M key)
-    int rxOf[D];                        // device whose transmission is being received, -1 idle
-    int rxSec[D];                       // 0 header, 1 payload
-    double ber[D], err[D], tReset[D];   // _receivedBitErrorRate / Sum / _lastReceivedErrorCountTime
-    double segT0[D];                    // mode M: start of the current constant-BER segment
+    Arr<double, D, O_P> P;              // SimplePhy._receivedPower (mW), simple_stack.py:80-82
+    Arr<int, D, O_sphase> sphase;       // S_*: macInHandler progress (simple_stack.py:192-212)
+    Arr<double, D, O_tEv> tEv;          // next PHY event: slot start / header end / completion
+    Arr<uint32_t, D, O_sEv> sEv;
+    Arr<double, D, O_txStart> txStart;  // Transmission.startTime
+    Arr<double, D, O_tStop> tStop;      // Transmission.stopTime
+    Arr<double, D, O_tC> tC;            // time of eCompletes
+    Arr<uint32_t, D, O_sC> sC;
+    Arr<int, D, O_cmdPay> cmdPay;       // payload bytes of the SEND command in flight
+    Aux<double, D> txVal;               // payload.value of the packet in flight (plant envs only)
+    Arr<uint32_t, D, O_txSeq> txSeq;    // transmissions started by this device (mode M key)
+    Arr<int, D, O_rxOf> rxOf;           // device whose transmission is being received, -1 idle
+    Arr<int, D, O_rxSec> rxSec;         // 0 header, 1 payload
+    Arr<double, D, O_ber> ber;          // _receivedBitErrorRate
+    Arr<double, D, O_err> err;          // _receivedBitErrorSum
+    Arr<double, D, O_tReset> tReset;    // _lastReceivedErrorCountTime
+    Aux<double, D> segT0;               // mode M: start of the current constant-BER segment
 
-    // senders: traffic process + MAC
-    double tTick[NS];
-    uint32_t sTick[NS];
-    uint64_t ticks[NS];                 // ticks fired; packets enqueued = ticks * mult
-    int qn[NS];                         // queue length (<= 100)
-    uint64_t epochK[NS];                // counter(tick k) = min(65536, epochC + (k - epochK))
-    int epochC[NS];
-    uint64_t snapEnd[NS];               // packets with index < snapEnd read their size from the ring
-    int mac[NS];                        // MAC_*
-    int wDone[NS], wPend[NS];
-    double stopW[NS];
-    uint32_t sW[NS];
+    // senders: traffic process (registers: the tick loop indexes them statically) + MAC
+    RegArr<double, NS> tTick;
+    RegArr<uint32_t, NS> sTick;
+    RegArr<uint64_t, NS> ticks;         // ticks fired; packets enqueued = ticks * mult
+    RegArr<int, NS> qn;                 // queue length (<= 100)
+    RegArr<uint64_t, NS> epochK;        // counter(tick k) = min(65536, epochC + (k - epochK))
+    RegArr<int, NS> epochC;
+    RegArr<uint64_t, NS> snapEnd;       // packets with index < snapEnd read their size from the ring
+    Arr<int, NS, O_mac> mac;            // MAC_*
+    Arr<int, NS, O_wDone> wDone;
+    Arr<int, NS, O_wPend> wPend;
+    Arr<double, NS, O_stopW> stopW;
+    Arr<uint32_t, NS, O_sW> sW;
 
     // jammers
-    double tJam[NJa];
-    uint32_t sJam[NJa];
-    int jamStage[NJa], jamPending[NJa];
+    RegArr<double, NJa> tJam;
+    RegArr<uint32_t, NJa> sJam;
+    RegArr<int, NJa> jamStage, jamPending;
 
     // RRM
     int annDest, annBytes;
@@ -218,7 +261,7 @@ struct Sim {
 
     // statistics
     uint32_t nTx;
-    uint32_t nDeliv[NS];
+    Arr<uint32_t, NS, O_nDeliv> nDeliv;
 
     // optional event trace (traced step variant only; nullptr in the production kernels, where
     // every recording site folds away): records of 8 doubles {kind, t, dev, x0, x1, x2, x3, -}
@@ -228,8 +271,8 @@ struct Sim {
 
 enum : int { REC_TX = 1, REC_BER = 2, REC_DEC = 3, REC_RX = 4 };
 
-template <int D, int NS, int NJ>
-GW_HD void trace_rec(Sim<D, NS, NJ> &s, int kind, double t, int dev, double x0, double x1, double x2, double x3)
+template <int D, int NS, int NJ, class ST>
+GW_HD void trace_rec(Sim<D, NS, NJ, ST> &s, int kind, double t, int dev, double x0, double x1, double x2, double x3)
 {
     if (s.trace == nullptr) return;
     if (s.ntrace < s.traceCap) {
@@ -246,8 +289,8 @@ struct Event {
 };
 
 // construction-time state (CounterTrafficEnv.__init__, counter_traffic.py:114-133)
-template <int D, int NS, int NJ>
-GW_HD void init_sim(Sim<D, NS, NJ> &s, double thermal)
+template <int D, int NS, int NJ, class ST>
+GW_HD void init_sim(Sim<D, NS, NJ, ST> &s, double thermal)
 {
     s.now = 0.0; s.seq = 0; s.fault = 0; s.ties = 0;
     GW_UNROLL
@@ -265,7 +308,7 @@ GW_HD void init_sim(Sim<D, NS, NJ> &s, double thermal)
         s.nDeliv[k] = 0;
     }
     GW_UNROLL
-    for (int j = 0; j < Sim<D, NS, NJ>::NJa; ++j) {
+    for (int j = 0; j < Sim<D, NS, NJ, ST>::NJa; ++j) {
         s.tJam[j] = 0.0; s.sJam[j] = (j < NJ) ? s.seq++ : 0; s.jamStage[j] = 0; s.jamPending[j] = 0;
     }
     s.annDest = 0; s.annBytes = 0; s.annSlots = 0; s.rrmPend = 0; s.tRrm = 0; s.sRrm = 0; s.assignDone = 0;
@@ -279,19 +322,29 @@ GW_HD bool seq_before(uint32_t a, uint32_t b) { return (int32_t)(a - b) < 0; }
 // element access with a RUN-TIME index through fully unrolled selects: keeps the per-sim
 // state in registers (a dynamically indexed member array would force the whole struct
 // into local memory)
-template <int N, class T, class V>
-GW_HD void set_at(T (&a)[N], int i, V v)
+template <class A, class V>
+GW_HD void set_at(A &a, int i, V v)
 {
-    GW_UNROLL
-    for (int q = 0; q < N; ++q) a[q] = (q == i) ? (T)v : a[q];
+    using T = typename A::value_type;
+    if constexpr (A::direct) {
+        a[i] = (T)v;
+    } else {
+        GW_UNROLL
+        for (int q = 0; q < A::size; ++q) a[q] = (q == i) ? (T)v : a[q];
+    }
 }
-template <int N, class T>
-GW_HD T get_at(const T (&a)[N], int i)
+template <class A>
+GW_HD typename A::value_type get_at(const A &a, int i)
 {
-    T r = a[0];
-    GW_UNROLL
-    for (int q = 1; q < N; ++q) r = (q == i) ? a[q] : r;
-    return r;
+    using T = typename A::value_type;
+    if constexpr (A::direct) {
+        return a[i];
+    } else {
+        T r = a[0];
+        GW_UNROLL
+        for (int q = 1; q < A::size; ++q) r = (q == i) ? a[q] : r;
+        return r;
+    }
 }
 // received power of receiver p (compile-time after unrolling) from sender d (run time)
 template <int D>
@@ -317,8 +370,8 @@ GW_HD bool before(double ta, uint32_t qa, double tb, uint32_t qb)
     return ta < tb || (ta == tb && seq_before(qa, qb));
 }
 
-template <int D, int NS, int NJ>
-GW_HD Event select_nontick(const Sim<D, NS, NJ> &s)
+template <int D, int NS, int NJ, class ST>
+GW_HD Event select_nontick(const Sim<D, NS, NJ, ST> &s)
 {
     Event e;
     e.kind = EV_NONE; e.idx = 0; e.t = INFINITY; e.seq = 0;
@@ -347,8 +400,8 @@ GW_HD Event select_nontick(const Sim<D, NS, NJ> &s)
 // strictly before `tLimit` -- are applied on the way (SenderDevice.senderProcess,
 // counter_traffic.py:53-61: `mult` packets into the drop-oldest queue, counter += 1, next tick).
 // one silent tick of sender K (compile-time index: plain register updates, no selects)
-template <int K, int D, int NS, int NJ>
-GW_HD void silent_tick(Sim<D, NS, NJ> &s, int mult, double interval)
+template <int K, int D, int NS, int NJ, class ST>
+GW_HD void silent_tick(Sim<D, NS, NJ, ST> &s, int mult, double interval)
 {
     const int n = s.qn[K] + mult;
     s.qn[K] = n > kQueueCap ? kQueueCap : n;
@@ -357,8 +410,8 @@ GW_HD void silent_tick(Sim<D, NS, NJ> &s, int mult, double interval)
     s.sTick[K] = s.seq++;
 }
 
-template <bool ALL_TICKS = false, int D, int NS, int NJ>
-GW_HD Event next_event(Sim<D, NS, NJ> &s, const BandParams &B, double tLimit)
+template <bool ALL_TICKS = false, int D, int NS, int NJ, class ST>
+GW_HD Event next_event(Sim<D, NS, NJ, ST> &s, const BandParams &B, double tLimit)
 {
     static_assert(NS == 2, "the tick loop is written for two senders per band");
     const Event nt = select_nontick(s);
@@ -392,8 +445,8 @@ GW_HD Event next_event(Sim<D, NS, NJ> &s, const BandParams &B, double tLimit)
 //              then the receive process counts again -- appendix B #4)
 // ---------------------------------------------------------------------------
 
-template <int D, int NS, int NJ>
-GW_HD void count_set(const Sim<D, NS, NJ> &s, const Event &ev, const double *srx, int &once, int &twice)
+template <int D, int NS, int NJ, class ST>
+GW_HD void count_set(const Sim<D, NS, NJ, ST> &s, const Event &ev, const double *srx, int &once, int &twice)
 {
     once = 0; twice = 0;
     if (ev.kind != EV_PHY) return;
@@ -417,8 +470,8 @@ GW_HD void count_set(const Sim<D, NS, NJ> &s, const Event &ev, const double *srx
 }
 
 // mode R: expected-value accounting, `duration` measured from the last RESET (appendix B #5)
-template <int D, int NS, int NJ>
-GW_HD void do_counts_R(Sim<D, NS, NJ> &s, int once, int twice, double bitRate)
+template <int D, int NS, int NJ, class ST>
+GW_HD void do_counts_R(Sim<D, NS, NJ, ST> &s, int once, int twice, double bitRate)
 {
     GW_UNROLL
     for (int p = 0; p < D; ++p) {
@@ -431,8 +484,8 @@ GW_HD void do_counts_R(Sim<D, NS, NJ> &s, int once, int twice, double bitRate)
 }
 
 // mode M: on-air bit range [k0, k1) of the segment that ends now, for PHY p
-template <int D, int NS, int NJ>
-GW_HD void mask_range(const Sim<D, NS, NJ> &s, int p, double bitRate, int &sender, uint32_t &txseq,
+template <int D, int NS, int NJ, class ST>
+GW_HD void mask_range(const Sim<D, NS, NJ, ST> &s, int p, double bitRate, int &sender, uint32_t &txseq,
                       int64_t &k0, int64_t &k1)
 {
     const int e = get_at(s.rxOf, p);
@@ -480,8 +533,8 @@ GW_HD double fmod_slot(double t)
     return r;
 }
 
-template <int D, int NS, int NJ>
-GW_HD void begin_slot_wait(Sim<D, NS, NJ> &s, int d)
+template <int D, int NS, int NJ, class ST>
+GW_HD void begin_slot_wait(Sim<D, NS, NJ, ST> &s, int d)
 {
     // self._transmitting = True; yield SimMan.nextTimeSlot(TIME_SLOT_LENGTH)  (simple_stack.py:202-204)
     const double t = s.now + (kSlot - fmod_slot(s.now));        // simtools.py:53
@@ -491,8 +544,8 @@ GW_HD void begin_slot_wait(Sim<D, NS, NJ> &s, int d)
     set_at(s.sEv, d, q);
 }
 
-template <int D, int NS, int NJ>
-GW_HD void phy_send_init(Sim<D, NS, NJ> &s, int d)
+template <int D, int NS, int NJ, class ST>
+GW_HD void phy_send_init(Sim<D, NS, NJ, ST> &s, int d)
 {
     // SimplePhy.macInHandler start: wait while the receiver is active (simple_stack.py:199-200)
     const bool receiving = get_at(s.rxOf, d) >= 0;
@@ -502,8 +555,8 @@ GW_HD void phy_send_init(Sim<D, NS, NJ> &s, int d)
 
 // size of the head packet of sender k's queue (bytes of the Transmittable):
 // packets are enqueued `mult` per tick with byteSize = counter at that tick
-template <int D, int NS, int NJ, class Ring>
-GW_HD int head_size(const Sim<D, NS, NJ> &s, const BandParams &B, int k, const Ring &ring)
+template <int D, int NS, int NJ, class ST, class Ring>
+GW_HD int head_size(const Sim<D, NS, NJ, ST> &s, const BandParams &B, int k, const Ring &ring)
 {
     const int rule = k == 0 ? B.payloadRule[0] : B.payloadRule[kMaxSend - 1];
     if (rule >= 0) return rule;
@@ -522,8 +575,8 @@ GW_HD int head_size(const Sim<D, NS, NJ> &s, const BandParams &B, int k, const R
 }
 
 // one pass of the SimpleMac window loop body with a non-empty queue (simple_stack.py:417-434)
-template <int D, int NS, int NJ, class Ring, class Plant>
-GW_HD void mac_try_send(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, int k, const Ring &ring, Plant &plant)
+template <int D, int NS, int NJ, class ST, class Ring, class Plant>
+GW_HD void mac_try_send(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, int k, const Ring &ring, Plant &plant)
 {
     const int size = head_size(s, B, k, ring);
     const int bitSize = (kMacHdr + kNetHdr + size) * 8;
@@ -547,8 +600,8 @@ GW_HD void mac_try_send(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B,
 }
 
 // loop head of the window loop (simple_stack.py:408-416)
-template <int D, int NS, int NJ, class Ring, class Plant>
-GW_HD void mac_loop_head(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, int k, const Ring &ring, Plant &plant)
+template <int D, int NS, int NJ, class ST, class Ring, class Plant>
+GW_HD void mac_loop_head(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, int k, const Ring &ring, Plant &plant)
 {
     const bool done = get_at(s.wDone, k) != 0, empty = get_at(s.qn, k) == 0;
     if (done) { set_at(s.mac, k, (int)MAC_NONE); return; }
@@ -557,8 +610,8 @@ GW_HD void mac_loop_head(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B
 }
 
 // end of SimplePhy._receive (simple_stack.py:264-267) without the deferred wake-up
-template <int D, int NS, int NJ>
-GW_HD void rx_clear(Sim<D, NS, NJ> &s, int p)
+template <int D, int NS, int NJ, class ST>
+GW_HD void rx_clear(Sim<D, NS, NJ, ST> &s, int p)
 {
     set_at(s.rxOf, p, -1);
     set_at(s.err, p, 0.0);
@@ -567,16 +620,16 @@ GW_HD void rx_clear(Sim<D, NS, NJ> &s, int p)
     set_at(s.segT0, p, s.now);
 }
 
-template <int D, int NS, int NJ>
-GW_HD bool decide(const Sim<D, NS, NJ> &s, const Params &P, int p, double totalBits)
+template <int D, int NS, int NJ, class ST>
+GW_HD bool decide(const Sim<D, NS, NJ, ST> &s, const Params &P, int p, double totalBits)
 {
     // bitErrorSum = round(bitErrorSum); bitErrorSum / totalBits <= maxCorrectableBer  (simple_stack.py:274-277)
     const double e = get_at(s.err, p);
     return rint(e) / totalBits <= P.maxBer;
 }
 
-template <int D, int NS, int NJ>
-GW_HD bool decide_rec(Sim<D, NS, NJ> &s, const Params &P, int p, int section, double totalBits)
+template <int D, int NS, int NJ, class ST>
+GW_HD bool decide_rec(Sim<D, NS, NJ, ST> &s, const Params &P, int p, int section, double totalBits)
 {
     const bool ok = decide(s, P, p, totalBits);
     trace_rec(s, REC_DEC, s.now, p, section, get_at(s.err, p), totalBits, ok ? 1.0 : 0.0);
@@ -588,8 +641,8 @@ GW_HD bool decide_rec(Sim<D, NS, NJ> &s, const Params &P, int p, int section, do
 // PHYs whose bit error rate must be re-evaluated afterwards (SimplePhy._updateBitErrorRate)
 // ---------------------------------------------------------------------------
 
-template <int D, int NS, int NJ, class Ring, class Plant>
-GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const Event &ev,
+template <int D, int NS, int NJ, class ST, class Ring, class Plant>
+GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const Event &ev,
                       double *srx, const Ring &ring, Plant &plant)
 {
     constexpr int RRM = NS;
@@ -804,8 +857,8 @@ GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, c
     return berMask;
 }
 
-template <int D, int NS, int NJ, class Ring>
-GW_HD int apply_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const Event &ev,
+template <int D, int NS, int NJ, class ST, class Ring>
+GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const Event &ev,
                       const double *srx, const Ring &ring)
 {
     NoPlant np;
@@ -821,8 +874,8 @@ struct NoMemo {
 };
 
 // SimplePhy._updateBitErrorRate for the PHYs in berMask (simple_stack.py:161-173)
-template <int D, int NS, int NJ, class Memo>
-GW_HD void update_bers(Sim<D, NS, NJ> &s, const Params &P, int berMask, const double *srx, const Memo &memo)
+template <int D, int NS, int NJ, class ST, class Memo>
+GW_HD void update_bers(Sim<D, NS, NJ, ST> &s, const Params &P, int berMask, const double *srx, const Memo &memo)
 {
     GW_UNROLL
     for (int p = 0; p < D; ++p) {
@@ -842,16 +895,16 @@ GW_HD void update_bers(Sim<D, NS, NJ> &s, const Params &P, int berMask, const do
     }
 }
 
-template <int D, int NS, int NJ>
-GW_HD void update_bers(Sim<D, NS, NJ> &s, const Params &P, int berMask, const double *srx)
+template <int D, int NS, int NJ, class ST>
+GW_HD void update_bers(Sim<D, NS, NJ, ST> &s, const Params &P, int berMask, const double *srx)
 {
     update_bers(s, P, berMask, srx, NoMemo());
 }
 
 // SimpleRrmDevice.assignFrequencyBand + SimpleRrmMac._sendAnnouncement start
 // (devices.py:178-203, simple_stack.py:536-556): the RRM PHY receives a SEND command
-template <int D, int NS, int NJ>
-GW_HD void begin_assignment(Sim<D, NS, NJ> &s, const Params &P, int device, int duration)
+template <int D, int NS, int NJ, class ST>
+GW_HD void begin_assignment(Sim<D, NS, NJ, ST> &s, const Params &P, int device, int duration)
 {
     const long long slots = (long long)duration * P.factor;         // counter_traffic.py:149
     int nbytes = 1;                                                  // len(str(slots)), messages.py:62-64
@@ -877,8 +930,8 @@ struct NoMasks {
 };
 
 // processes ONE timed event; `masks(receiver, sender, txseq, k0, k1, ber)` supplies mode-M counts
-template <int MODE, int D, int NS, int NJ, class Ring, class Masks, class Memo, class Plant>
-GW_HD void process_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const Event &ev,
+template <int MODE, int D, int NS, int NJ, class ST, class Ring, class Masks, class Memo, class Plant>
+GW_HD void process_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const Event &ev,
                          double *srx, const Ring &ring, const Masks &masks, const Memo &memo, Plant &plant)
 {
     int once, twice;
@@ -900,8 +953,8 @@ GW_HD void process_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B
     update_bers(s, P, berMask, srx, memo);
 }
 
-template <int MODE, int D, int NS, int NJ, class Ring, class Masks, class Memo>
-GW_HD void process_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const Event &ev,
+template <int MODE, int D, int NS, int NJ, class ST, class Ring, class Masks, class Memo>
+GW_HD void process_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const Event &ev,
                          const double *srx, const Ring &ring, const Masks &masks, const Memo &memo)
 {
     NoPlant np;
@@ -909,8 +962,8 @@ GW_HD void process_event(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B
 }
 
 // SimMan.runSimulation(assignSignal.eProcessed) for an env with a plant: every tick is an event
-template <int MODE, int D, int NS, int NJ, class Ring, class Masks, class Memo, class Plant>
-GW_HD void run_until_assign_plant(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, double *srx,
+template <int MODE, int D, int NS, int NJ, class ST, class Ring, class Masks, class Memo, class Plant>
+GW_HD void run_until_assign_plant(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, double *srx,
                                   const Ring &ring, const Masks &masks, const Memo &memo, Plant &plant)
 {
     while (!s.assignDone && !s.fault) {
@@ -920,8 +973,8 @@ GW_HD void run_until_assign_plant(Sim<D, NS, NJ> &s, const Params &P, const Band
 }
 
 // SimMan.runSimulation(assignSignal.eProcessed) (counter_traffic.py:155)
-template <int MODE, int D, int NS, int NJ, class Ring, class Masks, class Memo = NoMemo>
-GW_HD void run_until_assign(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B,
+template <int MODE, int D, int NS, int NJ, class ST, class Ring, class Masks, class Memo = NoMemo>
+GW_HD void run_until_assign(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B,
                             const double *srx, const Ring &ring, const Masks &masks, const Memo &memo = Memo())
 {
     while (!s.assignDone && !s.fault) {
@@ -932,8 +985,8 @@ GW_HD void run_until_assign(Sim<D, NS, NJ> &s, const Params &P, const BandParams
 
 // another band of the same env ended its assignment later, at time T: events strictly
 // before T are processed, then the clock is the env's clock
-template <int MODE, int D, int NS, int NJ, class Ring, class Masks, class Memo = NoMemo>
-GW_HD void run_until_time(Sim<D, NS, NJ> &s, const Params &P, const BandParams &B, const double *srx,
+template <int MODE, int D, int NS, int NJ, class ST, class Ring, class Masks, class Memo = NoMemo>
+GW_HD void run_until_time(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const double *srx,
                           const Ring &ring, const Masks &masks, double T, const Memo &memo = Memo())
 {
     while (!s.fault) {
@@ -948,8 +1001,8 @@ GW_HD void run_until_time(Sim<D, NS, NJ> &s, const Params &P, const BandParams &
 // reset; time, queues and PHY state stay.  Queued packets keep the sizes they were enqueued
 // with: they are materialised into the snapshot ring (`ringw(sender, slot, size)`) before
 // the counter epoch changes.
-template <int D, int NS, int NJ, class RingW>
-GW_HD void reset_sim(Sim<D, NS, NJ> &s, const BandParams &B, RingW &ringw)
+template <int D, int NS, int NJ, class ST, class RingW>
+GW_HD void reset_sim(Sim<D, NS, NJ, ST> &s, const BandParams &B, RingW &ringw)
 {
     GW_UNROLL
     for (int k = 0; k < NS; ++k) {
@@ -972,8 +1025,8 @@ GW_HD void reset_sim(Sim<D, NS, NJ> &s, const BandParams &B, RingW &ringw)
 }
 
 // Interpreter.getFeedback (envs/core.py:142-153, counter_traffic.py:85-107)
-template <int D, int NS, int NJ>
-GW_HD void feedback(Sim<D, NS, NJ> &s, long long &obs, double &reward, unsigned char &done)
+template <int D, int NS, int NJ, class ST>
+GW_HD void feedback(Sim<D, NS, NJ, ST> &s, long long &obs, double &reward, unsigned char &done)
 {
     obs = (long long)s.latestDiff + kCounterBound;
     const int absd = s.latestDiff < 0 ? -s.latestDiff : s.latestDiff;

@@ -136,6 +136,38 @@ struct gw_handle {
 };
 
 // ------------------------------------------------------------------------------------
+// shared-memory staging of the per-device state of every band-sim of a block: the arrays the
+// transition function indexes with run-time device indices (active transmissions, receptions,
+// MAC windows) live in dynamic shared memory, laid out [field][index][thread] -- consecutive
+// threads hit consecutive banks, and a run-time index is a plain address computation.
+// ------------------------------------------------------------------------------------
+
+constexpr int STEP_BLOCK = 128;
+
+template <class T, int N, int OFF>
+struct ShArr {
+    using value_type = T;
+    static constexpr int size = N;
+    static constexpr bool direct = true;
+    __host__ __device__ __forceinline__ T &operator[](int i) const
+    {
+#ifdef __CUDA_ARCH__
+        extern __shared__ __align__(16) unsigned char gw_step_smem[];
+        return *reinterpret_cast<T *>(gw_step_smem + (size_t)(OFF + i * (int)sizeof(T)) * STEP_BLOCK + threadIdx.x * sizeof(T));
+#else
+        static T dummy;
+        (void)i;
+        return dummy;       // never executed: the shared storage exists on the device only
+#endif
+    }
+};
+
+struct ShStore {
+    template <class T, int N, int OFF> using Arr = ShArr<T, N, OFF>;
+    template <class T, int N> using Aux = RegArr<T, N>;     // dead (mode R) or few (mode M) registers
+};
+
+// ------------------------------------------------------------------------------------
 // device helpers: chunk access, pack / unpack
 // ------------------------------------------------------------------------------------
 
@@ -165,8 +197,8 @@ __device__ __forceinline__ unsigned long long hi_q(uint4 v) { return ((unsigned 
 
 // flagsA: sphase[4] 3b | (rxOf+1)[4] 3b | rxSec[4] 1b | mac[2] 2b
 // flagsB: qn[2] 7b | wDone[2] | wPend[2] | jamStage 2b | jamPending 6b | rv0!=0 | rv1!=0 | lastAbs!=0 | done | busy
-template <int D, int NS, int NJ>
-__device__ __forceinline__ void unpack_flags(Sim<D, NS, NJ> &s, unsigned a, unsigned b)
+template <int D, int NS, int NJ, class ST>
+__device__ __forceinline__ void unpack_flags(Sim<D, NS, NJ, ST> &s, unsigned a, unsigned b)
 {
 #pragma unroll
     for (int d = 0; d < D; ++d) {
@@ -190,8 +222,8 @@ __device__ __forceinline__ void unpack_flags(Sim<D, NS, NJ> &s, unsigned a, unsi
     s.done = (b >> 29) & 1;
 }
 
-template <int D, int NS, int NJ>
-__device__ __forceinline__ bool sim_busy(const Sim<D, NS, NJ> &s)
+template <int D, int NS, int NJ, class ST>
+__device__ __forceinline__ bool sim_busy(const Sim<D, NS, NJ, ST> &s)
 {
     bool busy = false;
 #pragma unroll
@@ -201,8 +233,8 @@ __device__ __forceinline__ bool sim_busy(const Sim<D, NS, NJ> &s)
     return busy;
 }
 
-template <int D, int NS, int NJ>
-__device__ __forceinline__ void pack_flags(const Sim<D, NS, NJ> &s, bool busy, unsigned &a, unsigned &b)
+template <int D, int NS, int NJ, class ST>
+__device__ __forceinline__ void pack_flags(const Sim<D, NS, NJ, ST> &s, bool busy, unsigned &a, unsigned &b)
 {
     a = 0; b = 0;
 #pragma unroll
@@ -230,8 +262,8 @@ __device__ __forceinline__ void pack_flags(const Sim<D, NS, NJ> &s, bool busy, u
 // FULL = false: the step kernels skip fields they never read (counter epochs -- fetched on demand
 // through DevRing --, mode-M segment starts in mode R, packet values without a plant), which
 // makes them dead in registers
-template <bool FULL = true, bool WITH_SEG = true, int D, int NS, int NJ>
-__device__ __forceinline__ void load_sim(Sim<D, NS, NJ> &s, const StatePtrs &st, long long i, double now)
+template <bool FULL = true, bool WITH_SEG = true, int D, int NS, int NJ, class ST>
+__device__ __forceinline__ void load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs &st, long long i, double now)
 {
     const long long n = st.nsim;
     s.now = now;
@@ -303,8 +335,8 @@ __device__ __forceinline__ void load_sim(Sim<D, NS, NJ> &s, const StatePtrs &st,
     s.trace = nullptr; s.ntrace = 0; s.traceCap = 0;
 }
 
-template <bool FULL = true, bool WITH_SEG = true, int D, int NS, int NJ>
-__device__ __forceinline__ void store_sim(const Sim<D, NS, NJ> &s, const StatePtrs &st, long long i, bool epoch_too)
+template <bool FULL = true, bool WITH_SEG = true, int D, int NS, int NJ, class ST>
+__device__ __forceinline__ void store_sim(const Sim<D, NS, NJ, ST> &s, const StatePtrs &st, long long i, bool epoch_too)
 {
     const long long n = st.nsim;
     st_chunk(st.hot, n, H_P01, i, pack_dd(s.P[0], s.P[1]));
@@ -542,11 +574,11 @@ struct SharedTables {
 #endif
 
 template <int MODE, int D, int NS, int NJ, bool TRACE = false>
-__global__ void __launch_bounds__(128, GW_STEP_MIN_BLOCKS)
+__global__ void __launch_bounds__(STEP_BLOCK, GW_STEP_MIN_BLOCKS)
 step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P,
             const __grid_constant__ SharedTables T)
 {
-    using SimT = Sim<D, NS, NJ>;
+    using SimT = Sim<D, NS, NJ, ShStore>;
     const int lane = threadIdx.x & 31;
     const int nb = P.nbands;
     const long long nsim = A.st.nsim;
@@ -593,8 +625,10 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
             begin_assignment(s, P, dev, dur);
         } else {
             s.assignDone = 1; s.fault = 0; s.now = 0;
+            s.nTx = 0;
         }
-        const uint32_t nTx0 = active ? s.nTx : 0, nD0 = active ? s.nDeliv[0] : 0, nD1 = active ? s.nDeliv[1] : 0;
+        uint32_t nTx0 = 0, nD0 = 0, nD1 = 0;
+        if (active) { nTx0 = s.nTx; nD0 = s.nDeliv[0]; nD1 = s.nDeliv[1]; }
         const uint32_t ties0 = 0;           // the lean load starts the per-step tie counter at 0
 
         if (MODE == MODE_R) {
@@ -1434,12 +1468,22 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     int blocks = grid_for(nsim, 128);
     const int cap = 148 * 16;
     if (blocks > cap) blocks = cap;
+#define LAUNCH_STEP(KERNEL, DD, SS, JJ)                                                              \
+    do {                                                                                             \
+        constexpr int smem = Sim<DD, SS, JJ, ShStore>::kDirectBytes * STEP_BLOCK;                     \
+        static bool configured = false;                                                              \
+        if (!configured) {                                                                           \
+            CUDA_TRY(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            configured = true;                                                                       \
+        }                                                                                            \
+        KERNEL<<<blocks, STEP_BLOCK, smem, s>>>(A, h->P, T);                                          \
+    } while (0)
 #define CALL_STEP(DD, SS, JJ)                                                                        \
     do {                                                                                             \
-        if (trace) step_kernel<MODE_R, DD, SS, JJ, true><<<blocks, 128, 0, s>>>(A, h->P, T);           \
-        else if (h->cfg.mode == GW_MODE_REFERENCE) step_kernel<MODE_R, DD, SS, JJ><<<blocks, 128, 0, s>>>(A, h->P, T);  \
-        else if (h->cfg.mode == GW_MODE_MASK_PHILOX) step_kernel<MODE_M_PHILOX, DD, SS, JJ><<<blocks, 128, 0, s>>>(A, h->P, T); \
-        else step_kernel<MODE_M_FED, DD, SS, JJ><<<blocks, 128, 0, s>>>(A, h->P, T);                    \
+        if (trace) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ, true>), DD, SS, JJ);                  \
+        else if (h->cfg.mode == GW_MODE_REFERENCE) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ>), DD, SS, JJ);  \
+        else if (h->cfg.mode == GW_MODE_MASK_PHILOX) LAUNCH_STEP((step_kernel<MODE_M_PHILOX, DD, SS, JJ>), DD, SS, JJ); \
+        else LAUNCH_STEP((step_kernel<MODE_M_FED, DD, SS, JJ>), DD, SS, JJ);                          \
     } while (0)
     DISPATCH_SHAPE(h, CALL_STEP);
 #undef CALL_STEP
