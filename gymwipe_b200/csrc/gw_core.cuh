@@ -399,43 +399,60 @@ GW_HD Event select_nontick(const Sim<D, NS, NJ, ST> &s)
 // Next event for the full transition function.  Silent ticks that precede it -- and lie
 // strictly before `tLimit` -- are applied on the way (SenderDevice.senderProcess,
 // counter_traffic.py:53-61: `mult` packets into the drop-oldest queue, counter += 1, next tick).
-// one silent tick of sender K (compile-time index: plain register updates, no selects)
+// Silent ticks of sender K strictly before (tEnd, qEnd) -- and before tLimit -- applied in one
+// tight loop: the tick times are accumulated with the reference's fp64 additions, one per tick
+// (counter_traffic.py:61), everything else is counted and applied once.  Ticks of different senders
+// touch only their own sender's queue counters, so the senders are advanced one after the other;
+// the creation numbers they consume only matter for exact-time ties with other events (`ties`).
 template <int K, int D, int NS, int NJ, class ST>
-GW_HD void silent_tick(Sim<D, NS, NJ, ST> &s, int mult, double interval)
+GW_HD void silent_ticks(Sim<D, NS, NJ, ST> &s, int mult, double interval, double tEnd, uint32_t qEnd, bool haveEnd,
+                        double tLimit)
 {
-    const int n = s.qn[K] + mult;
-    s.qn[K] = n > kQueueCap ? kQueueCap : n;
-    s.ticks[K] += 1;
-    s.tTick[K] = s.tTick[K] + interval;
-    s.sTick[K] = s.seq++;
+    double t = s.tTick[K];
+    if (!(t < tLimit)) return;
+    if (haveEnd && !before(t, s.sTick[K], tEnd, qEnd)) return;
+    // the first tick is admitted by the full (time, seq) comparison; ticks created from now on
+    // have larger creation numbers than the bounding event, so they need t < tEnd strictly
+    const double stop = haveEnd ? (tEnd < tLimit ? tEnd : tLimit) : tLimit;
+    uint32_t c = 0;
+    do {
+        t = t + interval;
+        ++c;
+    } while (t < stop);
+    s.ties += (haveEnd && t == tEnd) ? 1u : 0u;     // exact tie of independent events (diagnostic)
+    s.tTick[K] = t;
+    s.ticks[K] += c;
+    const uint32_t n = (uint32_t)s.qn[K] + c * (uint32_t)mult;
+    s.qn[K] = n > (uint32_t)kQueueCap ? kQueueCap : (int)n;
+    s.seq += c;
+    s.sTick[K] = s.seq - 1u;
 }
 
 template <bool ALL_TICKS = false, int D, int NS, int NJ, class ST>
 GW_HD Event next_event(Sim<D, NS, NJ, ST> &s, const BandParams &B, double tLimit)
 {
-    static_assert(NS == 2, "the tick loop is written for two senders per band");
-    const Event nt = select_nontick(s);
-    const int mult0 = B.mult[0], mult1 = B.mult[1];
-    const double int0 = B.interval[0], int1 = B.interval[1];
-    const bool have_nt = nt.kind != EV_NONE;
-    for (;;) {
-        // earliest tick: sender 1 only if strictly before sender 0 in (time, seq)
-        const bool one = before(s.tTick[1], s.sTick[1], s.tTick[0], s.sTick[0]);
-        const double tk = one ? s.tTick[1] : s.tTick[0];
-        const uint32_t qk = one ? s.sTick[1] : s.sTick[0];
-        if (have_nt && !before(tk, qk, nt.t, nt.seq)) {
-            s.ties += (tk == nt.t) ? 1u : 0u;       // exact tie of independent events (diagnostic)
-            return nt;
-        }
-        const int mac = one ? s.mac[1] : s.mac[0];
-        if (ALL_TICKS || !(tk < tLimit) || mac == MAC_WAIT_COND) {
-            Event tick;
-            tick.kind = EV_TICK; tick.idx = one ? 1 : 0; tick.t = tk; tick.seq = qk;
-            return tick;
-        }
-        if (one) silent_tick<1>(s, mult1, int1);
-        else silent_tick<0>(s, mult0, int0);
+    static_assert(NS == 2, "the tick logic is written for two senders per band");
+    Event ev = select_nontick(s);
+    // ticks that must go through the transition function: every tick of a plant env, otherwise
+    // the ticks of a sender whose MAC waits for a packet
+    const bool wake0 = ALL_TICKS || s.mac[0] == MAC_WAIT_COND;
+    const bool wake1 = ALL_TICKS || s.mac[1] == MAC_WAIT_COND;
+    if (wake0 && (ev.kind == EV_NONE || before(s.tTick[0], s.sTick[0], ev.t, ev.seq))) {
+        ev.kind = EV_TICK; ev.idx = 0; ev.t = s.tTick[0]; ev.seq = s.sTick[0];
     }
+    if (wake1 && (ev.kind == EV_NONE || before(s.tTick[1], s.sTick[1], ev.t, ev.seq))) {
+        ev.kind = EV_TICK; ev.idx = 1; ev.t = s.tTick[1]; ev.seq = s.sTick[1];
+    }
+    const bool have = ev.kind != EV_NONE;
+    if (!wake0) silent_ticks<0>(s, B.mult[0], B.interval[0], ev.t, ev.seq, have, tLimit);
+    if (!wake1) silent_ticks<1>(s, B.mult[1], B.interval[1], ev.t, ev.seq, have, tLimit);
+    if (!have) {
+        // nothing but silent ticks is pending: report the earliest one (its time is >= tLimit)
+        const bool one = before(s.tTick[1], s.sTick[1], s.tTick[0], s.sTick[0]);
+        ev.kind = EV_TICK; ev.idx = one ? 1 : 0;
+        ev.t = one ? s.tTick[1] : s.tTick[0]; ev.seq = one ? s.sTick[1] : s.sTick[0];
+    }
+    return ev;
 }
 
 // ---------------------------------------------------------------------------
