@@ -402,3 +402,54 @@ def test_full_size_properties_65536():
     assert (obs_all[:, idx].cpu().numpy() == o["obs"][:, :, 0]).all()
     assert (rew_all[:, idx].cpu().numpy() == o["reward"][:, :, 0]).all()
     assert (env.read_state(0)[idx].cpu().numpy() == o["now"][-1]).all()
+
+
+def test_long_run_through_counter_saturation():
+    """
+    Maximum sizes: 7 000 steps of ~10 ms each cross COUNTER_BOUND = 65536 ticks (the counter
+    saturates, counter_traffic.py:59-60; packets reach 64 KiB), the queue is in permanent
+    drop-oldest overflow, and simulated time passes 70 s (slot alignment at large times).
+    """
+    from gymwipe_b200.scenario import default_scenario_dict
+    sc = default_scenario_dict()
+    rs = np.random.RandomState(77)
+    n, T = 16, 7000
+    dev, dur = random_tapes(rs, T, n, 1)
+    dur[:] = np.maximum(dur, 8)                       # long assignments: >= 8 ms per step
+    o = O.run_batch(sc, dev, dur, want=("obs", "reward", "now", "counts"))
+    env = make_env(sc, n, strict=False)
+    env.reset()
+    d_dev, d_dur = torch.as_tensor(dev[:, :, 0]).cuda(), torch.as_tensor(dur[:, :, 0]).cuda()
+    obs = torch.empty((T, n), dtype=torch.int64, device="cuda")
+    for t in range(T):
+        ob, rw, dn, _ = env.step({"device": d_dev[t], "duration": d_dur[t]})
+        obs[t] = ob
+    env.check()
+    assert (obs.cpu().numpy() == o["obs"][:, :, 0]).all()
+    now = env.read_state(0).cpu().numpy()
+    assert (now == o["now"][-1]).all() and now.min() > 70.0
+    assert (env.read_state(3).cpu().numpy() == 65536).all()              # SenderDevice.counter saturated
+    assert (env.read_state(4).cpu().numpy() == 100).all()                # deque(maxlen=100) is full
+    assert (env.transmissions().cpu().numpy() == o["counts"][:, 0, 0]).all()
+    assert (env.delivered().cpu().numpy() == o["counts"][:, 0, 1:3]).all()
+
+
+def test_send_queue_overflow_is_reported():
+    """A PHY-only sender whose interval is shorter than its airtime queues SEND commands without
+    bound in the reference; both the oracle and the CUDA path report it instead of mis-simulating."""
+    sc = {"assignment_duration_factor": 1000, "bands": [{"frequency": 2.4e9, "bandwidth": 22e6, "devices": [
+        {"role": "sender", "x": 0.0, "y": 2.0, "mult": 1, "payload": "counter", "interval": 0.001, "dest": 1},
+        {"role": "sender", "x": 0.0, "y": -2.0, "mult": 3, "payload": "counter", "interval": 0.001, "dest": 0},
+        {"role": "rrm", "x": 0.0, "y": 0.0},
+        {"role": "jammer", "x": 3.0, "y": 0.0, "interval": 0.001, "delay": 0.0, "power": 0.0, "hdr": 13, "payload": 200}]}]}
+    dev = np.zeros((400, 1, 1), np.int32)
+    dur = np.full((400, 1, 1), 19, np.int32)
+    with pytest.raises(O.OracleFault):
+        O.run_batch(sc, dev, dur)
+    env = make_env(sc, 4, strict=False)
+    a = {"device": torch.zeros(4, dtype=torch.int32, device="cuda"), "duration": torch.full((4,), 19, dtype=torch.int32, device="cuda")}
+    from gymwipe_b200._native import NativeError
+    with pytest.raises(NativeError, match="SEND queue overflow"):
+        for _ in range(400):
+            env.step(a)
+        env.check()
