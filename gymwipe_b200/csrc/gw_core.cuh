@@ -31,9 +31,11 @@
 
 #if defined(__CUDACC__)
 #define GW_HD __host__ __device__ __forceinline__
+#define GW_HD_COLD __host__ __device__ __noinline__
 #define GW_UNROLL _Pragma("unroll")
 #else
 #define GW_HD inline
+#define GW_HD_COLD inline
 #define GW_UNROLL
 #endif
 
@@ -43,6 +45,7 @@ constexpr double kSlot = 1e-6;          // TIME_SLOT_LENGTH, simple_stack.py:27
 constexpr int kMacHdr = 13;             // SimpleMacHeader byteSize, messages.py:154
 constexpr int kNetHdr = 12;             // SimpleNetworkHeader byteSize, messages.py:180
 constexpr int kQueueCap = 100;          // deque(maxlen=100), simple_stack.py:361
+constexpr int kRingSlots = 128;         // slots of the snapshot / value rings (power of two >= kQueueCap)
 constexpr int kCounterBound = 65536;    // COUNTER_BOUND, counter_traffic.py:35
 constexpr int kCounterByteLen = 2;      // COUNTER_BYTE_LENGTH, counter_traffic.py:33
 
@@ -92,6 +95,14 @@ GW_HD double ber_bpsk_mw(double S, double N, double tenLog10BitRate, double qDen
     const double x = sqrt(2 * ratio);
     const double e = 2.718281828459045;         // math.e
     return (1 - pow(e, -1.4 * x)) * pow(e, -(x * x / 2)) / (qDen * x);
+}
+
+// Out-of-line copy for the step kernels: with the BER memo the evaluation is a cold path, and
+// inlining its ~10^3 instructions at every call site would blow the instruction cache.  A leaf
+// function with scalar arguments can be called without forcing the state struct into memory.
+GW_HD_COLD double ber_bpsk_mw_cold(double S, double N, double tenLog10BitRate, double qDen)
+{
+    return ber_bpsk_mw(S, N, tenLog10BitRate, qDen);
 }
 
 // FsplAttenuation._update (attenuation_models.py:28-36); equal positions keep 0 dB.
@@ -537,13 +548,13 @@ struct NoPlant {
 // ---------------------------------------------------------------------------
 
 // fmod(t, kSlot) for t >= 0, bit-identical to the C library's (fmod is exact by definition):
-// q = trunc(t / L) may be one too large through the rounding of the division; t - q L is a
-// multiple of ulp(L) smaller than 2 L, hence exactly representable, so one explicit fma returns
-// it without rounding and a single correction step finishes.  ~30 instructions instead of the
-// generic iterative fmod.  Valid while t / L < 2^52 (t < 4.5e9 s).
+// q = trunc(t * 1e6) estimates the slot number to within +-1 (relative error ~2e-16 of a number
+// below 2^52); t - q L is a multiple of ulp(L) smaller than 2 L, hence exactly representable, so one
+// explicit fma returns it without rounding and a single correction step finishes.  ~12
+// instructions instead of the generic iterative fmod.  Valid while t < 4.5e9 s.
 GW_HD double fmod_slot(double t)
 {
-    const double q = trunc(t / kSlot);
+    const double q = trunc(t * 1e6);
     double r = fma(-q, kSlot, t);
     if (r < 0.0) r += kSlot;
     else if (r >= kSlot) r -= kSlot;
@@ -582,7 +593,7 @@ GW_HD int head_size(const Sim<D, NS, NJ, ST> &s, const BandParams &B, int k, con
     const uint32_t qn = (uint32_t)get_at(s.qn, k);
     const uint64_t enq = ticks * m;
     const uint64_t j = enq - (uint64_t)qn;
-    if (j < ring.snapEnd(s, k)) return ring(k, (uint32_t)(j % (uint64_t)kQueueCap));
+    if (j < ring.snapEnd(s, k)) return ring(k, (uint32_t)j & (uint32_t)(kRingSlots - 1));
     // tick of packet j = ticks - ceil(qn / m)
     const uint64_t back = (qn + m - 1u) / m;
     const uint64_t tick = ticks - back;
@@ -904,7 +915,7 @@ GW_HD void update_bers(Sim<D, NS, NJ, ST> &s, const Params &P, int berMask, cons
         if (!(S >= 0) || !(N >= 0)) { s.fault = FAULT_REF_ASSERT; continue; }   // simple_stack.py:168-169
         double ber;
         if (!memo.get(S, N, ber)) {
-            ber = ber_bpsk_mw(S, N, P.tenLog10BitRate, P.qDen);
+            ber = ber_bpsk_mw_cold(S, N, P.tenLog10BitRate, P.qDen);
             memo.put(S, N, ber);
         }
         s.ber[p] = ber;
@@ -1031,7 +1042,7 @@ GW_HD void reset_sim(Sim<D, NS, NJ, ST> &s, const BandParams &B, RingW &ringw)
             for (; j < enq; ++j) {
                 const uint64_t tick = j / m;
                 const uint64_t c = (uint64_t)s.epochC[k] + (tick - s.epochK[k]);
-                ringw(k, (uint32_t)(j % (uint64_t)kQueueCap), c > (uint64_t)kCounterBound ? kCounterBound : (int)c);
+                ringw(k, (uint32_t)j & (uint32_t)(kRingSlots - 1), c > (uint64_t)kCounterBound ? kCounterBound : (int)c);
             }
         }
         s.snapEnd[k] = enq;

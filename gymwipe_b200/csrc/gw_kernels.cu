@@ -94,11 +94,11 @@ static Layout make_layout(long long nenv, int nb, long long ntab, int plant = 0)
     L.off_now = o; o = align_up(o + sizeof(double) * nenv, 256);
     L.off_hot = o; o = align_up(o + 16ull * HOT_CHUNKS * nsim, 256);
     L.off_cold = o; o = align_up(o + 16ull * COLD_CHUNKS * nsim, 256);
-    L.off_ring = o; o = align_up(o + 4ull * kMaxSend * kQueueCap * nsim, 256);
+    L.off_ring = o; o = align_up(o + 4ull * kMaxSend * kRingSlots * nsim, 256);
     L.off_att = o; o = align_up(o + 8ull * 16 * ntab, 256);
     L.off_srx = o; o = align_up(o + 8ull * 16 * ntab, 256);
     L.off_plant = o; if (plant) o = align_up(o + 8ull * 8 * nsim, 256);
-    L.off_pval = o; if (plant) o = align_up(o + 8ull * kMaxSend * kQueueCap * nsim, 256);
+    L.off_pval = o; if (plant) o = align_up(o + 8ull * kMaxSend * kRingSlots * nsim, 256);
     L.total = o;
     return L;
 }
@@ -397,8 +397,8 @@ struct DevRing {
     int32_t *base;      // ring + sim index
     long long nsim;
     const uint4 *hot;   // hot chunks + sim index: the counter epochs are read on demand (rare)
-    __device__ __forceinline__ int operator()(int k, uint32_t slot) const { return base[(long long)(k * kQueueCap + slot) * nsim]; }
-    __device__ __forceinline__ void operator()(int k, uint32_t slot, int v) { base[(long long)(k * kQueueCap + slot) * nsim] = v; }
+    __device__ __forceinline__ int operator()(int k, uint32_t slot) const { return base[(long long)(k * kRingSlots + slot) * nsim]; }
+    __device__ __forceinline__ void operator()(int k, uint32_t slot, int v) { base[(long long)(k * kRingSlots + slot) * nsim] = v; }
     template <class S> __device__ __forceinline__ unsigned long long snapEnd(const S &, int k) const
     {
         const uint4 v = hot[(long long)H_SNAP * nsim];
@@ -762,8 +762,8 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
 struct DevVals {
     double *base;       // pval + sim index
     long long nsim;
-    __device__ __forceinline__ void put(int k, uint32_t slot, double v) { base[(long long)(k * kQueueCap + slot) * nsim] = v; }
-    __device__ __forceinline__ double get(int k, uint32_t slot) const { return base[(long long)(k * kQueueCap + slot) * nsim]; }
+    __device__ __forceinline__ void put(int k, uint32_t slot, double v) { base[(long long)(k * kRingSlots + slot) * nsim] = v; }
+    __device__ __forceinline__ double get(int k, uint32_t slot) const { return base[(long long)(k * kRingSlots + slot) * nsim]; }
 };
 struct DevSrxOut {
     double *base;       // srx table + sim index (per-sim tables)
@@ -839,7 +839,7 @@ __global__ void pendulum_init_kernel(StatePtrs st, PendulumParams Q)
     PendulumState S;
     pendulum_init(Q, S);
     store_plant(S, st, i);
-    for (int k = 0; k < kMaxSend * kQueueCap; ++k) st.pval[(long long)k * st.nsim + i] = 0.0;
+    for (int k = 0; k < kMaxSend * kRingSlots; ++k) st.pval[(long long)k * st.nsim + i] = 0.0;
 }
 
 __global__ void plant_read_kernel(StatePtrs st, double *out)

@@ -98,8 +98,8 @@ struct PendulumPlant {
     SrxOut srxOut;
     GW_HD PendulumPlant(const PendulumParams &q, PendulumState &s, Vals v, SrxOut o) : Q(q), S(s), vals(v), srxOut(o) {}
 
-    GW_HD void put_value(int k, uint64_t tick, double v) { vals.put(k, (uint32_t)(tick % (uint64_t)kQueueCap), v); }
-    GW_HD double get_value(int k, uint64_t tick) { return vals.get(k, (uint32_t)(tick % (uint64_t)kQueueCap)); }
+    GW_HD void put_value(int k, uint64_t tick, double v) { vals.put(k, (uint32_t)tick & (uint32_t)(kRingSlots - 1), v); }
+    GW_HD double get_value(int k, uint64_t tick) { return vals.get(k, (uint32_t)tick & (uint32_t)(kRingSlots - 1)); }
 
     GW_HD double tick_value(int k, double now)
     {

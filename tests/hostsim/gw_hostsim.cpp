@@ -17,8 +17,8 @@ namespace {
 
 struct HostRing {
     int32_t *data;      // [NS][100]
-    int operator()(int k, uint32_t slot) const { return data[k * kQueueCap + slot]; }
-    void operator()(int k, uint32_t slot, int v) { data[k * kQueueCap + slot] = v; }
+    int operator()(int k, uint32_t slot) const { return data[k * kRingSlots + slot]; }
+    void operator()(int k, uint32_t slot, int v) { data[k * kRingSlots + slot] = v; }
     // counter epochs (the device reads them from global memory on demand)
     template <class S> uint64_t snapEnd(const S &s, int k) const { return get_at(s.snapEnd, k); }
     template <class S> uint64_t epochK(const S &s, int k) const { return get_at(s.epochK, k); }
@@ -72,7 +72,7 @@ template <int D, int NS, int NJ>
 struct EnvT {
     Sim<D, NS, NJ> sim[kMaxBands];
     double srx[kMaxBands][D * D];
-    int32_t ring[kMaxBands][NS * kQueueCap];
+    int32_t ring[kMaxBands][NS * kRingSlots];
 };
 
 template <int MODE, int D, int NS, int NJ>
