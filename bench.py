@@ -485,7 +485,7 @@ def own_arm(args, rank, world, local_rank):
                 "reward_checksum": checksum,
                 "wide_api": {"value": total_envs * KE / e2e_wide_s, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 17 * n,
                              "api": "CounterTrafficEnv.step_host -> gw_step_host (int64 obs, float64 reward, uint8 done)"}},
-        "gpu_launches": K,
+        "gpu_launches": K + (K // STATS_EVERY if world > 1 else 0),     # step kernels (+ statistics copies when sharded)
         "clocks": clocks,
         "wall_s_timed_loop": wall,
     }
