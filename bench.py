@@ -5,12 +5,13 @@ bench.py -- env-steps/sec of the batched CounterTrafficEnv hot path (BASELINE.js
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Own arm: N ranks (one per GPU; torchrun supplies RANK / LOCAL_RANK / WORLD_SIZE for N > 1), each
-steps an independent shard of 65,536 envs (BASELINE configs[1], weak scaling) for W warm-up and
-K timed steps.  A "step" is ONE pass of the hot path over the batch (`CounterTrafficEnv.step`
-of every env = one launch of the fused step kernel).  Timing: CUDA events around every step on
-the launching stream, L2 flushed (256 MiB memset) between steps outside the timed spans, the
-K spans are summed, max over ranks.  `e2e` is the same metric through `gw_step_host` with
-pinned HOST buffers (H2D actions + D2H obs/reward/done inside the timed region).
+owning an independent shard of 16 batches of 65,536 envs (BASELINE configs[1], weak scaling).  A
+"step" is ONE pass of the hot path over ONE batch (`CounterTrafficEnv.step` of its 65,536 envs = one
+launch of the fused step kernel); the batches are stepped round-robin so that every launch finds its
+inputs in HBM, not in L2 ("inputs larger than L2", no flush).  W warm-up launches, then EXACTLY K timed
+launches replayed from CUDA graphs, one CUDA-event pair around them on the launching stream, barrier +
+synchronize on both sides, max over ranks.  `e2e` is the same metric through `gw_step_host_packed`
+with pinned HOST buffers (H2D actions + D2H obs/reward/done inside the timed region).
 
 Reference arm (`--impl reference`): the reference's algorithm on the box's host cores -- the
 oracle port (plain-C restatement, pinned bit-exactly against the unmodified Python reference;
@@ -31,19 +32,25 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 ENVS_PER_GPU = 65536
+ROTATING_BATCHES = 16                  # independent 65,536-env batches stepped round-robin (inputs > L2)
 ALGO_BYTES_PER_ENV_STEP = 193          # SURVEY.md section 8d / DESIGN.md section 6
-STATS_EVERY = 8                        # steps between two NCCL reductions of the statistics vector
+STATS_EVERY_CHUNKS = 4                 # graph chunks (of 64 launches) between two NCCL reductions of the statistics vector
 METRIC = "env-steps/sec CounterTrafficEnv batch"
 UNIT = "env-steps/s"
 
 
 def config_dict(n_envs_total, parallelism, regime):
     return {"workload": "CounterTrafficEnv default scenario (2 counter senders + RRM, 1 FrequencyBand, FSPL, BPSK), "
-                        "mode R (reference-exact accounting), %d envs per GPU, random actions "
-                        "(device~U{0,1}, duration~U{0..19}), fresh env + reset() then warm-up + timed steps" % ENVS_PER_GPU,
-            "n_envs": n_envs_total, "envs_per_gpu": ENVS_PER_GPU, "parallelism": parallelism,
+                        "mode R (reference-exact accounting), batches of %d envs per GPU (BASELINE configs[1]), random "
+                        "actions (device~U{0,1}, duration~U{0..19}); one step = one launch of the fused step kernel over "
+                        "one batch" % ENVS_PER_GPU,
+            "n_envs": n_envs_total * ROTATING_BATCHES, "envs_per_launch": ENVS_PER_GPU,
+            "batches_per_gpu": ROTATING_BATCHES, "parallelism": parallelism,
             "regime": regime,
-            "l2": "flushed between steps (256 MiB memset outside the timed spans); per-step CUDA-event spans summed"}
+            "l2": "inputs larger than L2: %d independent %d-env batches per GPU are stepped round-robin, so a batch's "
+                  "state (~13 MB hot), its fresh action rows and outputs are re-touched only after ~%d MB of other "
+                  "traffic (L2 = 126 MB); no flush, launches replayed from CUDA graphs (64 launches each), one "
+                  "CUDA-event pair around the K timed launches" % (ROTATING_BATCHES, ENVS_PER_GPU, 13 * (ROTATING_BATCHES - 1))}
 
 
 def measured_peak():
@@ -348,65 +355,140 @@ def own_arm(args, rank, world, local_rank):
     dev_t = torch.device("cuda", local_rank)
     K, W = args.steps, args.warmup
     n = ENVS_PER_GPU
-    env = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, env_id_offset=rank * n, strict=False)
-    env.reset()
+    M = ROTATING_BATCHES
+    # M independent 65,536-env batches stepped round-robin: one "step" = one launch of the fused
+    # step kernel over one batch.  A batch is touched again only after the M - 1 others (M x ~13 MB of
+    # hot state + fresh action rows + outputs > the 126 MB L2), so every launch finds its inputs in
+    # HBM, not in L2 ("inputs larger than L2"); nothing is flushed and nothing sits between two
+    # launches inside the timed region.
+    envs = [gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t,
+                              env_id_offset=(rank * M + b) * n, strict=False) for b in range(M)]
+    for e in envs:
+        e.reset()
 
-    # synthetic action tapes, resident in HBM before the timed region
+    # synthetic action tapes for every launch, resident in HBM before the timed region
     g = torch.Generator(device=dev_t).manual_seed(1234 + rank)
     total = W + K
+    rounds = (total + M - 1) // M                       # every batch is stepped `rounds` times at most
     a_dev = torch.randint(0, 2, (total, n), generator=g, device=dev_t, dtype=torch.int32)
     a_dur = torch.randint(0, 20, (total, n), generator=g, device=dev_t, dtype=torch.int32)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_t)
     reducer = StatsReducer(dev_t) if world > 1 else None
-    stream = torch.cuda.current_stream(dev_t)
+    stats_acc = torch.zeros(8, dtype=torch.float64, device=dev_t)
+    stream = torch.cuda.Stream(device=dev_t)
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
-    def one_step(t, timed):
-        flush.zero_()                                   # L2 flush, outside the timed span
-        if timed is not None:
-            timed[0].record(stream)
-        env.step({"device": a_dev[t], "duration": a_dur[t]})
-        if reducer is not None and (t + 1) % STATS_EVERY == 0:
-            # K5 partial sums of the last STATS_EVERY steps -> NCCL all-reduce on a side stream
-            env.stats(out=reducer.next_slot())
-            reducer.submit()
-        if timed is not None:
-            timed[1].record(stream)
+    def launch(j):
+        envs[j % M].step({"device": a_dev[j], "duration": a_dur[j]})
 
-    for t in range(W):
-        one_step(t, None)
-    if world > 1:
-        dist.barrier()
+    # launches are captured into CUDA graphs of CHUNK launches each (pointers of the action rows are
+    # baked in, hence one graph per chunk); a replay enqueues the chunk without per-launch host work
+    CHUNK = 64
     torch.cuda.synchronize(dev_t)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    if sampler is not None:
-        sampler.mark_begin()
-    wall0 = time.perf_counter()
-    for k in range(K):
-        one_step(W + k, evs[k])
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev_t)
-    wall = time.perf_counter() - wall0
+    with torch.cuda.stream(stream):
+        for j in range(W):
+            launch(j)
+        torch.cuda.synchronize(dev_t)
+        graphs = []
+        j = W
+        while j < total:
+            cnt = min(CHUNK, total - j)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=stream):
+                for q in range(j, j + cnt):
+                    launch(q)
+            graphs.append((gr, j, cnt))
+            j += cnt
+        # (capturing does not execute: the envs are still at launch W)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev_t)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(len(graphs) + 1)]
+        if sampler is not None:
+            sampler.mark_begin()
+        wall0 = time.perf_counter()
+        marks[0].record(stream)
+        for c, (gr, j0, cnt) in enumerate(graphs):
+            gr.replay()
+            if reducer is not None and ((c + 1) % STATS_EVERY_CHUNKS == 0 or c + 1 == len(graphs)):
+                # K5 partial sums of the last chunks -> NCCL all-reduce on a side stream
+                buf = reducer.next_slot()
+                buf.zero_()
+                for e in envs:
+                    buf += e.stats()
+                reducer.submit()
+            marks[c + 1].record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev_t)
+        wall = time.perf_counter() - wall0
     if sampler is not None:
         sampler.mark_end()
     clocks = sampler.stop() if sampler is not None else None
-    env.check()
+    for e in envs:
+        e.check()
     if reducer is not None:
         reducer.drain()
-    per_step_ms = np.array([a.elapsed_time(b) for a, b in evs])
-    elapsed_ms = float(per_step_ms.sum())
+    chunk_ms = np.array([marks[c].elapsed_time(marks[c + 1]) for c in range(len(graphs))])
+    chunk_cnt = np.array([cnt for _, _, cnt in graphs])
+    chunk_first = np.array([j0 for _, j0, _ in graphs])
+    elapsed_ms = float(marks[0].elapsed_time(marks[-1]))
+    per_step_ms = chunk_ms / chunk_cnt                  # average launch duration per chunk
 
-    # back-to-back loop without flush (transparency: L2-warm number)
-    torch.cuda.synchronize(dev_t)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    KB = min(K, 256)
-    e0.record(stream)
-    for k in range(KB):
-        env.step({"device": a_dev[W + k], "duration": a_dur[W + k]})
-    e1.record(stream)
-    torch.cuda.synchronize(dev_t)
+    # transparency: (a) one batch stepped back to back from one graph (state stays in L2),
+    # (b) the round-1 protocol: per-launch event pairs with a 256 MiB L2-flush memset before each
+    env1 = envs[0]
+    KB = 64
+    with torch.cuda.stream(stream):
+        gw = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gw, stream=stream):
+            for k in range(KB):
+                env1.step({"device": a_dev[k], "duration": a_dur[k]})
+        gw.replay()
+        torch.cuda.synchronize(dev_t)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        gw.replay()
+        e1.record(stream)
+        torch.cuda.synchronize(dev_t)
     warm_ms = e0.elapsed_time(e1) / KB
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_t)
+    KF = 64
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KF)]
+    cur = torch.cuda.current_stream(dev_t)
+    for k in range(KF):
+        flush.zero_()
+        evs[k][0].record(cur)
+        env1.step({"device": a_dev[k], "duration": a_dur[k]})
+        evs[k][1].record(cur)
+    torch.cuda.synchronize(dev_t)
+    flushed_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    del flush
+    # (c) the reference's degenerate regime (counters too large for any window: announcements only):
+    # every batch is advanced 128 more steps untimed, then 256 round-robin launches are timed
+    for r in range(128):
+        for b in range(M):
+            envs[b].step({"device": a_dev[(r * M + b) % total], "duration": a_dur[(r * M + b) % total]})
+    torch.cuda.synchronize(dev_t)
+    KD = 256
+    with torch.cuda.stream(stream):
+        gd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gd, stream=stream):
+            for q in range(KD):
+                envs[q % M].step({"device": a_dev[q % total], "duration": a_dur[q % total]})
+        torch.cuda.synchronize(dev_t)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        gd.replay()
+        e1.record(stream)
+        torch.cuda.synchronize(dev_t)
+    degen_ms = e0.elapsed_time(e1) / KD
+    for e in envs:
+        e.check()
+    del gd
+    for e in envs[1:]:
+        e.close()
+    del envs, graphs, gw
+    torch.cuda.empty_cache()
 
     # e2e: host buffers through gw_step_host (pinned), copies inside the timed region
     env2 = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, env_id_offset=rank * n, strict=False)
@@ -447,9 +529,9 @@ def own_arm(args, rank, world, local_rank):
 
     # max over ranks
     if world > 1:
-        v = torch.tensor([elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s], dtype=torch.float64, device=dev_t)
+        v = torch.tensor([elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, flushed_ms, degen_ms], dtype=torch.float64, device=dev_t)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s = [float(x) for x in v]
+        elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, flushed_ms, degen_ms = [float(x) for x in v]
     if rank != 0:
         return 0
 
@@ -457,22 +539,28 @@ def own_arm(args, rank, world, local_rank):
     value = total_envs * K / (elapsed_ms * 1e-3)
     e2e_value = total_envs * KE / e2e_s
     peak, peak_src = measured_peak()
-    kernel_ms = float(per_step_ms.mean())
+    kernel_ms = elapsed_ms / K                          # average launch duration over the timed region
     achieved = ALGO_BYTES_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e9
-    prod = per_step_ms[:max(1, min(K, 96 - W))] if W < 96 else per_step_ms[:1]
-    degen = per_step_ms[-min(K, 256):]
+    steps_per_env = (W + K + M - 1) // M
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": config_dict(total_envs, "dp%d (independent env shards, no data-path collective; NCCL all-reduce of the 64-byte "
-                              "statistics vector every %d steps on a side stream)" % (world, STATS_EVERY) if world > 1
+                              "statistics vector every %d launches on a side stream)" % (world, STATS_EVERY_CHUNKS * 64) if world > 1
                               else "single GPU",
-                              "steps %d..%d from a fresh env: productive regime (~first 100 steps, packets delivered) "
-                              "then the reference's degenerate regime (announcements only)" % (W, W + K)),
-        "regimes": {"productive_env_steps_per_s": n * world * len(prod) / (float(prod.sum()) * 1e-3),
-                    "degenerate_env_steps_per_s": n * world * len(degen) / (float(degen.sum()) * 1e-3),
-                    "l2_warm_back_to_back_env_steps_per_s": n * world / (warm_ms * 1e-3)},
+                              "fresh envs + reset(); every env advances %d steps during warm-up + timed region: the "
+                              "productive regime (packets delivered; the first ~100 steps of an env)" % steps_per_env),
+        "regimes": {"timed_region_env_steps_per_s": value,
+                    "degenerate_env_steps_per_s": total_envs / (degen_ms * 1e-3),
+                    "degenerate_note": "same round-robin protocol, 256 launches after every env advanced 128 more steps "
+                                       "(counters too large for any window: announcements only)",
+                    "l2_warm_one_batch_env_steps_per_s": total_envs / (warm_ms * 1e-3),
+                    "l2_warm_note": "ONE batch stepped 64x back to back from a CUDA graph (its state stays in L2)",
+                    "round1_protocol_env_steps_per_s": total_envs / (flushed_ms * 1e-3),
+                    "round1_protocol_note": "one batch, 256 MiB memset before every launch, CUDA-event pair around every launch "
+                                            "(includes the launch latency behind the flush)",
+                    "per_chunk_ms_per_launch": [float(x) for x in per_step_ms]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
                      "kernel": "step_kernel<MODE_R,3,2,0>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
@@ -485,12 +573,12 @@ def own_arm(args, rank, world, local_rank):
                 "reward_checksum": checksum,
                 "wide_api": {"value": total_envs * KE / e2e_wide_s, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 17 * n,
                              "api": "CounterTrafficEnv.step_host -> gw_step_host (int64 obs, float64 reward, uint8 done)"}},
-        "gpu_launches": K + (K // STATS_EVERY if world > 1 else 0),     # step kernels (+ statistics copies when sharded)
+        "gpu_launches": K + (M * ((len(chunk_cnt) + STATS_EVERY_CHUNKS - 1) // STATS_EVERY_CHUNKS) if world > 1 else 0),   # step kernels (+ statistics copies when sharded)
         "clocks": clocks,
         "wall_s_timed_loop": wall,
     }
     if world == 1 and not args.no_extras:
-        del flush, env2, env3
+        del env2, env3
         torch.cuda.empty_cache()
         try:
             line["mask_scan"] = mask_scan_roofline(dev_t, peak, "random")

@@ -39,6 +39,11 @@
 #define GW_UNROLL
 #endif
 
+// test hook of the host build (tests/hostsim): counts how often each macro event applies
+#ifndef GW_STAT_MACRO
+#define GW_STAT_MACRO(i) ((void)0)
+#endif
+
 namespace gw {
 
 constexpr double kSlot = 1e-6;          // TIME_SLOT_LENGTH, simple_stack.py:27
@@ -48,6 +53,7 @@ constexpr int kQueueCap = 100;          // deque(maxlen=100), simple_stack.py:36
 constexpr int kRingSlots = 128;         // slots of the snapshot / value rings (power of two >= kQueueCap)
 constexpr int kCounterBound = 65536;    // COUNTER_BOUND, counter_traffic.py:35
 constexpr int kCounterByteLen = 2;      // COUNTER_BYTE_LENGTH, counter_traffic.py:33
+constexpr int kMaxAirBytes = 70000;     // largest packet on the path: 13 + 12 + COUNTER_BOUND bytes (and fixed payloads <= 60000)
 
 enum : int { S_IDLE = 0, S_WAITRX = 1, S_SLOT = 2, S_HDR = 3, S_PAY = 4 };
 enum : int { MAC_NONE = 0, MAC_WAIT_COND = 1, MAC_WAIT_TX = 2, MAC_IDLE = 3 };
@@ -76,6 +82,10 @@ struct Params {
     double tenLog10BitRate;             // 10*log10(bitRate), host libm
     double qDen;                        // 1.135 * sqrt(2*pi), physical.py:44,58
     double bitsFactor;                  // float(2 - codeRate) = 1.25, physical.py:259-263
+    int noMacro;                        // 1: every timed event goes through the generic transition function
+    double berMult;                     // 1 / maxBer if that is a power of two and bit counts are integers, else 0
+    double airtime[32];                 // (k * 8) / dataRate for k < 32 bytes (same IEEE division, done once)
+    double rateInv;                     // fl(1 / dataRate) if the multiply-and-correct quotient below was verified, else 0
     BandParams band[kMaxBands];
 };
 
@@ -561,6 +571,52 @@ GW_HD double fmod_slot(double t)
     return r;
 }
 
+// derived constants of Params (host side, after bitRate / dataRate / maxBer / bitsFactor are set)
+inline void finish_params(Params &P)
+{
+    P.berMult = 0.0;
+    int e = 0;
+    const double m = frexp(P.maxBer, &e);
+    const double bitsPerByte = 8 * P.bitsFactor;
+    if (m == 0.5 && P.maxBer <= 1.0 && bitsPerByte == floor(bitsPerByte)) P.berMult = 1.0 / P.maxBer;
+    for (int k = 0; k < 32; ++k) P.airtime[k] = (k * 8) / P.dataRate;
+    // x / dataRate through the reciprocal: q0 = x * y, r = fma(-q0, R, x), q = fma(r, y, q0) is the
+    // correctly rounded quotient for almost all operands (Markstein); it is USED only if it equals the
+    // division on the whole domain of the path, which is finite -- bit counts 8 k, k <= kMaxAirBytes --
+    // and checked here exhaustively (~70 k divisions, once per gw_create)
+    P.rateInv = 1.0 / P.dataRate;
+    for (int k = 0; k <= kMaxAirBytes; ++k) {
+        const double x = k * 8;
+        const double q0 = x * P.rateInv;
+        const double q = fma(fma(-q0, P.dataRate, x), P.rateInv, q0);
+        if (q != x / P.dataRate) { P.rateInv = 0.0; break; }
+    }
+}
+
+// duration of `bytes` bytes on air at the data rate (physical.py:244-250): (bytes * 8) / dataRate
+GW_HD double airtime_of(const Params &P, int bytes)
+{
+    if ((unsigned)bytes < 32u) return P.airtime[bytes];
+    const double x = bytes * 8;
+    if (P.rateInv != 0.0 && bytes <= kMaxAirBytes) {
+        const double q0 = x * P.rateInv;
+        return fma(fma(-q0, P.dataRate, x), P.rateInv, q0);     // == x / dataRate, verified in finish_params
+    }
+    return x / P.dataRate;
+}
+
+// SimplePhy._decide: round(bitErrorSum) / totalBits <= maxCorrectableBer (simple_stack.py:274-277).
+// With maxBer = 2^-k and integer-valued operands (x = rint(errSum), totalBits = bytes * 8 * 1.25 < 2^52)
+// the correctly rounded quotient is <= 2^-k exactly when x * 2^k <= totalBits: fl(x / y) <= m  <=>
+// x / y <= m (1 + 2^-53)  <=>  x 2^k - y <= y 2^-53 < 1, and the left side is an integer.  Saves an
+// fp64 division (~30 dependent instructions) per decision; other code rates take the division.
+GW_HD bool within_max_ber(const Params &P, double errSum, double totalBits)
+{
+    const double x = rint(errSum);
+    if (P.berMult != 0.0) return x * P.berMult <= totalBits;
+    return x / totalBits <= P.maxBer;
+}
+
 template <int D, int NS, int NJ, class ST>
 GW_HD void begin_slot_wait(Sim<D, NS, NJ, ST> &s, int d)
 {
@@ -607,10 +663,9 @@ template <int D, int NS, int NJ, class ST, class Ring, class Plant>
 GW_HD void mac_try_send(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, int k, const Ring &ring, Plant &plant)
 {
     const int size = head_size(s, B, k, ring);
-    const int bitSize = (kMacHdr + kNetHdr + size) * 8;
     const double stopW = get_at(s.stopW, k);
     const double timeLeft = stopW - s.now;
-    const double txTime = bitSize / P.dataRate;
+    const double txTime = airtime_of(P, kMacHdr + kNetHdr + size);      // bitSize / dataRate
     if (!(timeLeft > txTime)) {
         set_at(s.mac, k, (int)MAC_IDLE);        // yield timeoutEvent
         return;
@@ -652,8 +707,7 @@ template <int D, int NS, int NJ, class ST>
 GW_HD bool decide(const Sim<D, NS, NJ, ST> &s, const Params &P, int p, double totalBits)
 {
     // bitErrorSum = round(bitErrorSum); bitErrorSum / totalBits <= maxCorrectableBer  (simple_stack.py:274-277)
-    const double e = get_at(s.err, p);
-    return rint(e) / totalBits <= P.maxBer;
+    return within_max_ber(P, get_at(s.err, p), totalBits);
 }
 
 template <int D, int NS, int NJ, class ST>
@@ -717,8 +771,8 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
             // FrequencyBand.transmit -> Transmission.__init__ (physical.py:224-279,596-608)
             const int payBytes = get_at(s.cmdPay, d);
             const int hdrBytes = (NJ > 0 && d > RRM) ? B.jamHdr[0] : kMacHdr;
-            const double hd = (hdrBytes * 8) / P.dataRate;
-            const double pd = (payBytes * 8) / P.dataRate;
+            const double hd = airtime_of(P, hdrBytes);
+            const double pd = airtime_of(P, payBytes);
             const double duration = hd + pd;
             const double stop = s.now + duration;
             const double headerStop = s.now + hd;
@@ -936,7 +990,13 @@ GW_HD void begin_assignment(Sim<D, NS, NJ, ST> &s, const Params &P, int device, 
 {
     const long long slots = (long long)duration * P.factor;         // counter_traffic.py:149
     int nbytes = 1;                                                  // len(str(slots)), messages.py:62-64
-    for (long long lim = 10; lim <= slots && nbytes < 18; lim *= 10) ++nbytes;
+    if (slots < 1000000000LL) {
+        const int v = (int)slots;
+        nbytes += (v >= 10) + (v >= 100) + (v >= 1000) + (v >= 10000) + (v >= 100000) + (v >= 1000000)
+                + (v >= 10000000) + (v >= 100000000);
+    } else {
+        for (long long lim = 10; lim <= slots && nbytes < 18; lim *= 10) ++nbytes;
+    }
     s.annDest = device;
     s.annSlots = (double)slots;
     s.annBytes = nbytes;
@@ -963,6 +1023,7 @@ GW_HD void process_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParam
                          double *srx, const Ring &ring, const Masks &masks, const Memo &memo, Plant &plant)
 {
     int once, twice;
+    GW_STAT_MACRO(2 + (ev.kind == EV_TICK ? 1 : 0));
     s.now = ev.t;
     count_set(s, ev, srx, once, twice);
     if (MODE == MODE_R) {
@@ -989,6 +1050,247 @@ GW_HD void process_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParam
     process_event<MODE>(s, P, B, ev, const_cast<double *>(srx), ring, masks, memo, np);
 }
 
+// ---------------------------------------------------------------------------
+// macro events (mode R): exact shortcuts through event sequences whose order is known in advance
+//
+// isolated_tx(): the slot-start event of device d is the next event, every other PHY is idle and
+// not receiving, no MAC waits for a packet (ticks stay silent) and every other timed event lies
+// strictly after the completion of d's transmission.  Then nothing can interleave with the three
+// events of the transmission (slot start, header end, completion), every other PHY locks on at the
+// start, and the three handlers of apply_event() + their counts + BER updates collapse into
+// straight-line code on registers.  The arithmetic, its order, the creation numbers of the non-tick
+// events and the trace records are those of the generic path, operation for operation; the silent
+// ticks of the whole transmission are applied in ONE batch bounded by the completion event (nothing
+// observes a queue before the completion handler), so a pending tick's creation number may differ
+// from the generic path's -- it only breaks exact-time ties between a tick and an unrelated event,
+// which are counted in `ties` either way.  Anything unusual (a power table entry that fails the
+// reference's assertions, a completion time that rounds below the stop time -- appendix B #12)
+// declines, and the generic path handles it.
+//
+// quiet_tail(): after the announcement (and the data packets) nothing is on air, no MAC waits for a
+// packet or a transmission and only window time-outs and the RRM guard time-out are pending: they
+// cannot create events, so they are applied in (time, seq) order without the selection machinery.
+// ---------------------------------------------------------------------------
+
+template <int D, int NS, int NJ, class ST, class Ring, class Memo>
+GW_HD bool isolated_tx_one(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const int d, const double ts,
+                           const double *srx, const Ring &ring, const Memo &memo, double tLimit)
+{
+    static_assert(NS == 2, "the tick logic is written for two senders per band");
+    constexpr int RRM = NS;
+    if (get_at(s.sphase, d) != S_SLOT) return false;
+    bool ok = true;
+    GW_UNROLL
+    for (int p = 0; p < D; ++p) ok &= (s.rxOf[p] < 0) & ((p == d) | (s.sphase[p] == S_IDLE));
+    GW_UNROLL
+    for (int k = 0; k < NS; ++k) ok &= s.mac[k] != MAC_WAIT_COND;
+    if (!ok) return false;
+
+    // Transmission.__init__ (physical.py:224-279), as in apply_event / S_SLOT
+    const int payBytes = get_at(s.cmdPay, d);
+    const int hdrBytes = (NJ > 0 && d > RRM) ? B.jamHdr[0] : kMacHdr;
+    const double hd = airtime_of(P, hdrBytes);
+    const double pd = airtime_of(P, payBytes);
+    const double duration = hd + pd;
+    const double stop = ts + duration;
+    const double headerStop = ts + hd;
+    const double tH = ts + (headerStop > ts ? headerStop - ts : 0.0);
+    const double tC = ts + (stop > ts ? stop - ts : 0.0);
+    ok = (tH > ts) & (tC > tH) & (tC >= stop) & (tC < tLimit);
+    GW_UNROLL
+    for (int k = 0; k < NS; ++k) ok &= (s.wPend[k] == 0) | (s.stopW[k] > tC);
+    ok &= (s.rrmPend == 0) | (s.tRrm > tC);
+    GW_UNROLL
+    for (int j = 0; j < NJ; ++j) ok &= s.tJam[j] > tC;
+    // received powers; the reference's assertions on signal / noise power (simple_stack.py:168-169)
+    double rp[D], Pn[D];
+    GW_UNROLL
+    for (int p = 0; p < D; ++p) {
+        rp[p] = srx_at<D>(srx, p, d);
+        Pn[p] = s.P[p] + rp[p];
+        const double N = Pn[p] - rp[p];
+        ok &= (p == d) | ((rp[p] >= 0) & (N >= 0));
+    }
+    if (!ok) return false;
+
+    GW_STAT_MACRO(0);
+
+    // ---- slot start: the transmission begins, every other PHY registers its power and locks on
+    s.now = ts;
+    s.seq++;                                    // creation number of the header-end event
+    const uint32_t qC = s.seq++;
+    set_at(s.tC, d, tC);
+    set_at(s.sC, d, qC);
+    set_at(s.txStart, d, ts);
+    set_at(s.tStop, d, stop);
+    set_at(s.txSeq, d, get_at(s.txSeq, d) + 1u);
+    s.nTx += 1;
+    const double hdrBits = (hdrBytes * 8) * P.bitsFactor;
+    const double payBits = (payBytes * 8) * P.bitsFactor;
+    trace_rec(s, REC_TX, ts, d, stop, hdrBits, payBits, 0.0);
+    double ber[D];
+    GW_UNROLL
+    for (int p = 0; p < D; ++p) {
+        ber[p] = 0.0;
+        if (p == d) continue;
+        s.P[p] = Pn[p];
+        const double S = rp[p], N = Pn[p] - S;
+        double b;
+        if (!memo.get(S, N, b)) {
+            b = ber_bpsk_mw_cold(S, N, P.tenLog10BitRate, P.qDen);
+            memo.put(S, N, b);
+        }
+        ber[p] = b;
+        trace_rec(s, REC_BER, ts, p, b, 0.0, 0.0, 0.0);
+    }
+
+    // ---- header end (simple_stack.py:241-251).  Ticks are silent here: those up to the completion
+    // are applied in one batch below (nothing observes the queues before the completion handler)
+    s.now = tH;
+    bool locked[D];
+    GW_UNROLL
+    for (int p = 0; p < D; ++p) {
+        locked[p] = false;
+        if (p == d) continue;
+        const double bitErrors = ber[p] * (tH - ts) * P.bitRate;
+        const double e = 0.0 + bitErrors;
+        locked[p] = within_max_ber(P, e, hdrBits);
+        trace_rec(s, REC_DEC, tH, p, 0, e, hdrBits, locked[p] ? 1.0 : 0.0);
+    }
+    if (s.trace != nullptr) {
+        // the BER of a receiver that passed the header is evaluated again: same powers, same value
+        GW_UNROLL
+        for (int p = 0; p < D; ++p) if (p != d && locked[p]) trace_rec(s, REC_BER, tH, p, ber[p], 0.0, 0.0, 0.0);
+    }
+
+    // ---- completion (simple_stack.py:146-157, 253-267)
+    silent_ticks<0>(s, B.mult[0], B.interval[0], tC, qC, true, tLimit);
+    silent_ticks<1>(s, B.mult[1], B.interval[1], tC, qC, true, tLimit);
+    s.now = tC;
+    set_at(s.sphase, d, (int)S_IDLE);
+    set_at(s.tEv, d, tC);
+    set_at(s.sEv, d, qC);
+    int window = -1;
+    GW_UNROLL
+    for (int p = 0; p < D; ++p) {
+        if (p == d) continue;
+        double e = 0.0;
+        if (locked[p]) {
+            // the completion callback counts (if the power changes), then the receive process
+            // counts again -- appendix B #4
+            const double bitErrors = ber[p] * (tC - tH) * P.bitRate;
+            e = 0.0 + bitErrors;
+            if (rp[p] != 0.0) e += bitErrors;
+        }
+        s.P[p] += -rp[p];
+        if (locked[p]) {
+            const bool okP = within_max_ber(P, e, payBits);
+            trace_rec(s, REC_DEC, tC, p, 1, e, payBits, okP ? 1.0 : 0.0);
+            if (okP) {
+                if (p < NS) {
+                    if (d == RRM && s.annDest == p && s.mac[p] == MAC_NONE) window = p;
+                } else if (p == RRM) {
+                    if (d < NS) {
+                        if (d == 0) s.rv0 = kCounterByteLen;
+                        if (d == 1) s.rv1 = kCounterByteLen;
+                        s.latestDiff = s.rv0 - s.rv1;
+                        set_at(s.nDeliv, d, get_at(s.nDeliv, d) + 1u);
+                    }
+                    trace_rec(s, REC_RX, tC, d, 0.0, 0.0, 0.0, 0.0);
+                }
+            }
+        }
+        // end of the reception (rx_clear); rxOf stays -1
+        s.rxSec[p] = locked[p] ? 1 : 0;
+        s.err[p] = 0.0; s.ber[p] = 0.0;
+        s.tReset[p] = locked[p] ? tC : tH;
+        s.segT0[p] = s.tReset[p];
+    }
+    NoPlant plant;
+    if (window >= 0) {
+        const double timeTotal = s.annSlots * kSlot;
+        const double stopW = tC + timeTotal;
+        const uint32_t qW = s.seq++;
+        set_at(s.stopW, window, stopW);
+        set_at(s.sW, window, qW);
+        set_at(s.wPend, window, 1);
+        set_at(s.wDone, window, 0);
+        mac_loop_head(s, P, B, window, ring, plant);
+    }
+    if (d < NS) {
+        mac_loop_head(s, P, B, d, ring, plant);
+    } else if (d == RRM) {
+        s.tRrm = tC + (s.annSlots + 1) * kSlot;
+        s.sRrm = s.seq++;
+        s.rrmPend = 1;
+    } else if (NJ > 0 && s.jamPending[0] > 0) {
+        s.jamPending[0] -= 1;
+        phy_send_init(s, d);
+    }
+    return true;
+}
+
+// The slot-start event `ev` of device ev.idx, and -- chained -- the transmissions that follow it
+// back to back: the grantee's first packet after the announcement, the next packet of the same
+// sender's window.  The follower's slot-start event is the next event by the same isolation test
+// (every other timed event lies after ITS completion), so no event selection is needed in between.
+template <int D, int NS, int NJ, class ST, class Ring, class Memo>
+GW_HD bool isolated_tx(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const Event &ev,
+                       const double *srx, const Ring &ring, const Memo &memo, double tLimit)
+{
+    constexpr int RRM = NS;
+    int d = ev.idx;
+    double ts = ev.t;
+    bool any = false;
+    for (;;) {
+        if (!isolated_tx_one(s, P, B, d, ts, srx, ring, memo, tLimit)) break;
+        any = true;
+        // the only device that can have started a SEND in the completion handler
+        const int nx = (d == RRM) ? s.annDest : d;
+        if (get_at(s.sphase, nx) != S_SLOT) break;
+        d = nx;
+        ts = get_at(s.tEv, d);
+    }
+    return any;
+}
+
+template <int D, int NS, int NJ, class ST>
+GW_HD bool quiet_tail(Sim<D, NS, NJ, ST> &s, const BandParams &B)
+{
+    static_assert(NS == 2, "the tick logic is written for two senders per band");
+    bool ok = s.rrmPend != 0;
+    GW_UNROLL
+    for (int p = 0; p < D; ++p) ok &= (s.sphase[p] == S_IDLE) & (s.rxOf[p] < 0);
+    GW_UNROLL
+    for (int k = 0; k < NS; ++k) ok &= (s.mac[k] == MAC_NONE) | (s.mac[k] == MAC_IDLE);
+    GW_UNROLL
+    for (int j = 0; j < NJ; ++j) ok &= s.tJam[j] > s.tRrm;
+    if (!ok) return false;
+    GW_STAT_MACRO(1);
+    // window time-outs that precede the guard time-out, in (time, seq) order (simple_stack.py:406-420)
+    for (;;) {
+        int k = -1;
+        if (s.wPend[0] && before(s.stopW[0], s.sW[0], s.tRrm, s.sRrm)) k = 0;
+        if (s.wPend[1] && before(s.stopW[1], s.sW[1], s.tRrm, s.sRrm)
+            && (k < 0 || before(s.stopW[1], s.sW[1], s.stopW[0], s.sW[0]))) k = 1;
+        if (k < 0) break;
+        const double tw = get_at(s.stopW, k);
+        const uint32_t qw = get_at(s.sW, k);
+        silent_ticks<0>(s, B.mult[0], B.interval[0], tw, qw, true, INFINITY);
+        silent_ticks<1>(s, B.mult[1], B.interval[1], tw, qw, true, INFINITY);
+        s.now = tw;
+        set_at(s.wPend, k, 0);
+        set_at(s.mac, k, (int)MAC_NONE);
+    }
+    // assignMessage.setProcessed() (simple_stack.py:561)
+    silent_ticks<0>(s, B.mult[0], B.interval[0], s.tRrm, s.sRrm, true, INFINITY);
+    silent_ticks<1>(s, B.mult[1], B.interval[1], s.tRrm, s.sRrm, true, INFINITY);
+    s.now = s.tRrm;
+    s.rrmPend = 0;
+    s.assignDone = 1;
+    return true;
+}
+
 // SimMan.runSimulation(assignSignal.eProcessed) for an env with a plant: every tick is an event
 template <int MODE, int D, int NS, int NJ, class ST, class Ring, class Masks, class Memo, class Plant>
 GW_HD void run_until_assign_plant(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, double *srx,
@@ -1005,8 +1307,11 @@ template <int MODE, int D, int NS, int NJ, class ST, class Ring, class Masks, cl
 GW_HD void run_until_assign(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B,
                             const double *srx, const Ring &ring, const Masks &masks, const Memo &memo = Memo())
 {
+    const bool macros = MODE == MODE_R && !P.noMacro;
     while (!s.assignDone && !s.fault) {
+        if (macros && quiet_tail(s, B)) break;
         const Event ev = next_event(s, B, INFINITY);
+        if (macros && ev.kind == EV_PHY && isolated_tx(s, P, B, ev, srx, ring, memo, INFINITY)) continue;
         process_event<MODE>(s, P, B, ev, srx, ring, masks, memo);
     }
 }
@@ -1020,6 +1325,7 @@ GW_HD void run_until_time(Sim<D, NS, NJ, ST> &s, const Params &P, const BandPara
     while (!s.fault) {
         const Event ev = next_event(s, B, T);
         if (!(ev.t < T)) break;
+        if (MODE == MODE_R && !P.noMacro && ev.kind == EV_PHY && isolated_tx(s, P, B, ev, srx, ring, memo, T)) continue;
         process_event<MODE>(s, P, B, ev, srx, ring, masks, memo);
     }
     s.now = T;

@@ -60,7 +60,7 @@ static int fail(int code, const char *fmt, ...)
 // ------------------------------------------------------------------------------------
 
 enum : int {
-    H_P01 = 0, H_P23, H_TICK, H_TICKS, H_U0, H_U1, H_U2, H_JAM, H_EPK, H_SNAP, H_EPC, HOT_CHUNKS
+    H_P01 = 0, H_P23, H_TICK, H_TICKS, H_U0, H_U1, H_U2, H_JAM, H_EP0, H_EP1, H_EPC, HOT_CHUNKS
 };
 // cold: per device 5 chunks, then per sender 1
 enum : int { C_EV = 0, C_TX, C_RX, C_RT, C_U, C_V, C_PER_DEV };
@@ -133,6 +133,7 @@ struct gw_handle {
     ulonglong2 *memo;
     unsigned memo_entries;
     PendulumParams pend;
+    int pdl;                // launch the step kernel with programmatic stream serialization
 };
 
 // ------------------------------------------------------------------------------------
@@ -142,7 +143,10 @@ struct gw_handle {
 // threads hit consecutive banks, and a run-time index is a plain address computation.
 // ------------------------------------------------------------------------------------
 
-constexpr int STEP_BLOCK = 128;
+#ifndef GW_STEP_BLOCK
+#define GW_STEP_BLOCK 128
+#endif
+constexpr int STEP_BLOCK = GW_STEP_BLOCK;
 
 template <class T, int N, int OFF>
 struct ShArr {
@@ -291,12 +295,15 @@ __device__ __forceinline__ void load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs 
         s.tJam[0] = 0; s.sJam[0] = 0;
     }
     if (FULL) {
-        v = ld_chunk(st.hot, n, H_EPK, i);
-        s.epochK[0] = lo_q(v); s.epochK[1] = hi_q(v);
-        v = ld_chunk(st.hot, n, H_SNAP, i);
-        s.snapEnd[0] = lo_q(v); s.snapEnd[1] = hi_q(v);
+        // per sender one chunk {snapEnd, epochK | epochC << 63}: the counter epoch of sender k
+        // (counter value 0 or 1 at tick epochK) and the end of its snapshot ring
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            v = ld_chunk(st.hot, n, H_EP0 + k, i);
+            s.snapEnd[k] = lo_q(v); s.epochK[k] = hi_q(v) & ~(1ull << 63); s.epochC[k] = (int)(hi_q(v) >> 63);
+        }
         v = ld_chunk(st.hot, n, H_EPC, i);
-        s.epochC[0] = (int)v.x; s.epochC[1] = (int)v.y; s.fault = (int)v.z; s.ties = v.w;
+        s.fault = (int)v.z; s.ties = v.w;
     } else {
         s.epochK[0] = s.epochK[1] = 0; s.snapEnd[0] = s.snapEnd[1] = 0; s.epochC[0] = s.epochC[1] = 0;
         s.fault = 0; s.ties = 0;        // a faulted sim stays flagged in memory (store_sim ORs nothing back)
@@ -359,12 +366,13 @@ __device__ __forceinline__ void store_sim(const Sim<D, NS, NJ, ST> &s, const Sta
         st_chunk(st.hot, n, H_JAM, i, v);
     }
     if (epoch_too) {
-        st_chunk(st.hot, n, H_EPK, i, pack_qq(s.epochK[0], s.epochK[1]));
-        st_chunk(st.hot, n, H_SNAP, i, pack_qq(s.snapEnd[0], s.snapEnd[1]));
+#pragma unroll
+        for (int k = 0; k < NS; ++k)
+            st_chunk(st.hot, n, H_EP0 + k, i, pack_qq(s.snapEnd[k], s.epochK[k] | ((unsigned long long)(s.epochC[k] & 1) << 63)));
     }
     if (FULL) {
         if (epoch_too || s.fault || s.ties) {
-            v.x = (unsigned)s.epochC[0]; v.y = (unsigned)s.epochC[1]; v.z = (unsigned)s.fault; v.w = s.ties;
+            v.x = 0; v.y = 0; v.z = (unsigned)s.fault; v.w = s.ties;
             st_chunk(st.hot, n, H_EPC, i, v);
         }
     } else if (s.fault || s.ties) {
@@ -396,24 +404,22 @@ __device__ __forceinline__ void store_sim(const Sim<D, NS, NJ, ST> &s, const Sta
 struct DevRing {
     int32_t *base;      // ring + sim index
     long long nsim;
-    const uint4 *hot;   // hot chunks + sim index: the counter epochs are read on demand (rare)
+    const uint4 *hot;   // hot chunks + sim index
+    // counter epochs {snapEnd, epochK | epochC << 63} of both senders: the step kernels fetch them
+    // together with the rest of the state (head_size() needs them at every window), the other
+    // kernels read them on demand
+    bool have;
+    uint4 ep0, ep1;
     __device__ __forceinline__ int operator()(int k, uint32_t slot) const { return base[(long long)(k * kRingSlots + slot) * nsim]; }
     __device__ __forceinline__ void operator()(int k, uint32_t slot, int v) { base[(long long)(k * kRingSlots + slot) * nsim] = v; }
-    template <class S> __device__ __forceinline__ unsigned long long snapEnd(const S &, int k) const
+    __device__ __forceinline__ uint4 ep(int k) const
     {
-        const uint4 v = hot[(long long)H_SNAP * nsim];
-        return k == 0 ? lo_q(v) : hi_q(v);
+        if (have) return k == 0 ? ep0 : ep1;
+        return hot[(long long)(H_EP0 + k) * nsim];
     }
-    template <class S> __device__ __forceinline__ unsigned long long epochK(const S &, int k) const
-    {
-        const uint4 v = hot[(long long)H_EPK * nsim];
-        return k == 0 ? lo_q(v) : hi_q(v);
-    }
-    template <class S> __device__ __forceinline__ int epochC(const S &, int k) const
-    {
-        const uint4 v = hot[(long long)H_EPC * nsim];
-        return (int)(k == 0 ? v.x : v.y);
-    }
+    template <class S> __device__ __forceinline__ unsigned long long snapEnd(const S &, int k) const { return lo_q(ep(k)); }
+    template <class S> __device__ __forceinline__ unsigned long long epochK(const S &, int k) const { return hi_q(ep(k)) & ~(1ull << 63); }
+    template <class S> __device__ __forceinline__ int epochC(const S &, int k) const { return (int)(hi_q(ep(k)) >> 63); }
 };
 
 // ------------------------------------------------------------------------------------
@@ -424,22 +430,55 @@ struct DevRing {
 // device code, a hit returns bit-for-bit what the evaluation would.
 // ------------------------------------------------------------------------------------
 
+constexpr int MEMO_L0 = 32;     // entries of the block-local first level of the BER memo
+
+#ifdef GW_MEMO_STATS
+// instrumented builds only (-DGW_MEMO_STATS): {evaluations, second-level hits} since load
+__device__ unsigned long long g_memo_stats[2];
+#define GW_MEMO_COUNT(i) atomicAdd(&g_memo_stats[i], 1ull)
+#else
+#define GW_MEMO_COUNT(i) ((void)0)
+#endif
+
 struct DevMemo {
     ulonglong2 *tab;        // 2 x ulonglong2 per entry
     unsigned mask;          // entries - 1 (power of two)
+    // first level (shared geometry only): MEMO_L0 direct-mapped entries that every block copies
+    // from `l0g` into shared memory (`l0s`) together with its state loads; a hit costs two
+    // shared-memory reads instead of a trip to L2 / DRAM.  Filled from the second level.
+    ulonglong2 *l0g;
+    const ulonglong2 *l0s;
     static constexpr unsigned long long MAGIC = 0x9E3779B97F4A7C15ull;
     __device__ __forceinline__ unsigned slot(unsigned long long a, unsigned long long b) const
     {
         unsigned long long h = a * 0x9E3779B97F4A7C15ull ^ (b + 0xC2B2AE3D27D4EB4Full) * 0xD6E8FEB86659FD93ull;
         return (unsigned)(h >> 40) & mask;
     }
+    // first-level index: a few XORs of mantissa bits (no multiplies on the hot path)
+    __device__ __forceinline__ unsigned slot0(unsigned long long a, unsigned long long b) const
+    {
+        unsigned x = (unsigned)a ^ (unsigned)(a >> 32) ^ ((unsigned)b >> 3) ^ ((unsigned)(b >> 32) << 2);
+        x ^= x >> 16;
+        x ^= x >> 8;
+        return (x ^ (x >> 5)) & (MEMO_L0 - 1);
+    }
     __device__ __forceinline__ bool get(double S, double N, double &ber) const
     {
         if (!tab) return false;
         const unsigned long long a = (unsigned long long)__double_as_longlong(S), b = (unsigned long long)__double_as_longlong(N);
+        if (l0s) {
+            const unsigned h0 = slot0(a, b);
+            const ulonglong2 f0 = l0s[2 * h0], f1 = l0s[2 * h0 + 1];
+            if (f0.x == a && f0.y == b && f1.y == (a ^ b ^ f1.x ^ MAGIC)) { ber = __longlong_as_double((long long)f1.x); return true; }
+        }
         const unsigned h = slot(a, b);
         const ulonglong2 e0 = tab[2 * h], e1 = tab[2 * h + 1];
-        if (e0.x == a && e0.y == b && e1.y == (a ^ b ^ e1.x ^ MAGIC)) { ber = __longlong_as_double((long long)e1.x); return true; }
+        if (e0.x == a && e0.y == b && e1.y == (a ^ b ^ e1.x ^ MAGIC)) {
+            ber = __longlong_as_double((long long)e1.x);
+            GW_MEMO_COUNT(1);
+            if (l0g) { const unsigned h0 = slot0(a, b); l0g[2 * h0] = e0; l0g[2 * h0 + 1] = e1; }
+            return true;
+        }
         return false;
     }
     __device__ __forceinline__ void put(double S, double N, double ber) const
@@ -448,8 +487,14 @@ struct DevMemo {
         const unsigned long long a = (unsigned long long)__double_as_longlong(S), b = (unsigned long long)__double_as_longlong(N);
         const unsigned long long c = (unsigned long long)__double_as_longlong(ber);
         const unsigned h = slot(a, b);
+        GW_MEMO_COUNT(0);
         tab[2 * h] = make_ulonglong2(a, b);
         tab[2 * h + 1] = make_ulonglong2(c, a ^ b ^ c ^ MAGIC);
+        if (l0g) {
+            const unsigned h0 = slot0(a, b);
+            l0g[2 * h0] = make_ulonglong2(a, b);
+            l0g[2 * h0 + 1] = make_ulonglong2(c, a ^ b ^ c ^ MAGIC);
+        }
     }
 };
 
@@ -582,17 +627,32 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
     const int lane = threadIdx.x & 31;
     const int nb = P.nbands;
     const long long nsim = A.st.nsim;
-    double acc[8];
+    int acc[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+    for (int k = 0; k < 8; ++k) acc[k] = 0;
+
+    // first level of the BER memo: copied into shared memory while the state loads are in flight.
+    // (Read before the grid dependency is resolved: entries are checksum-validated, a stale or
+    // torn one is a miss.)
+    __shared__ ulonglong2 memo_l0[2 * MEMO_L0];
+    DevMemo memo = A.memo;
+    if (memo.l0g != nullptr) {
+        for (int t = threadIdx.x; t < 2 * MEMO_L0; t += blockDim.x) memo_l0[t] = memo.l0g[t];
+        memo.l0s = memo_l0;
+    }
+    // Programmatic dependent launch: this grid may have been scheduled while the previous kernel
+    // of the stream (the previous step, or whatever produced the actions) was still draining; its
+    // memory is visible from here on.  The next kernel may start launching right away -- it waits
+    // at the same point for this grid to complete.
+    cudaGridDependencySynchronize();
+    cudaTriggerProgrammaticLaunchCompletion();
+    __syncthreads();
 
     // grid-stride over warps' worth of band-sims; every lane of a warp stays in the loop
     // so that the warp-level operations below are executed by all 32 lanes
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nround = (nsim + stride - 1) / stride;
-    for (long long r = 0; r < nround; ++r) {
-        const long long i = first + r * stride;
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < nsim; base += stride) {
+        const long long i = base + threadIdx.x;
         const bool active = i < nsim;
         // nb is 1, 2 or 4: shifts instead of 64-bit divisions
         const int nbShift = nb == 4 ? 2 : (nb == 2 ? 1 : 0);
@@ -602,10 +662,13 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         SimT s;
         double srx[D * D];
         const BandParams &B = P.band[band];
-        DevRing ring{A.st.ring + (active ? i : 0), nsim, A.st.hot + (active ? i : 0)};
+        DevRing ring{A.st.ring + (active ? i : 0), nsim, A.st.hot + (active ? i : 0), false, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
         int dev = 0, dur = 0;
         if (active) {
             load_sim<false, MODE != MODE_R>(s, A.st, i, A.st.now[env]);
+            ring.ep0 = ld_chunk(A.st.hot, nsim, H_EP0, i);
+            ring.ep1 = ld_chunk(A.st.hot, nsim, H_EP1, i);
+            ring.have = true;
             if (!A.st.per_env) {
 #pragma unroll
                 for (int k = 0; k < D * D; ++k) srx[k] = T.srx[band][(k / D) * kMaxDev + (k % D)];
@@ -632,13 +695,13 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         const uint32_t ties0 = 0;           // the lean load starts the per-step tie counter at 0
 
         if (MODE == MODE_R) {
-            if (active) run_until_assign<MODE_R>(s, P, B, srx, ring, NoMasks(), A.memo);
+            if (active) run_until_assign<MODE_R>(s, P, B, srx, ring, NoMasks(), memo);
             if (nb > 1) {
                 // SimMan.runSimulation for every band's ASSIGN message: the env's clock ends
                 // at the latest band; the other bands keep simulating up to that time
                 double Tend = active ? s.now : -INFINITY;
                 for (int o = 1; o < nb; o <<= 1) Tend = fmax(Tend, __shfl_xor_sync(0xFFFFFFFFu, Tend, o));
-                if (active && s.now < Tend) run_until_time<MODE_R>(s, P, B, srx, ring, NoMasks(), Tend, A.memo);
+                if (active && s.now < Tend) run_until_time<MODE_R>(s, P, B, srx, ring, NoMasks(), Tend, memo);
             }
         } else {
             // warp-synchronous event loop: one timed event per lane and iteration; the error
@@ -710,7 +773,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
                 }
                 if (run) {
                     const int berMask = apply_event(s, P, B, ev, srx, ring);
-                    update_bers(s, P, berMask, srx, A.memo);
+                    update_bers(s, P, berMask, srx, memo);
                 }
             }
             if (active && nb > 1) s.now = Tend;
@@ -726,32 +789,30 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
             if (s.fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = s.fault; } }
             store_sim<false, MODE != MODE_R>(s, A.st, i, false);
             if (TRACE) A.traceCount[i] = s.ntrace;
-            acc[0] += rw;
-            acc[1] += (double)(s.nDeliv[0] - nD0);
-            acc[2] += (double)(s.nDeliv[1] - nD1);
-            acc[3] += (double)dn;
-            acc[4] += 1.0;
-            acc[5] += (double)(s.latestDiff < 0 ? -s.latestDiff : s.latestDiff);
-            acc[6] += (double)(s.nTx - nTx0);
-            acc[7] += (double)(s.ties - ties0);
+            acc[0] += (int)rw;                  // rewards are integers in [-10, 10] (counter_traffic.py:96-107)
+            acc[1] += (int)(s.nDeliv[0] - nD0);
+            acc[2] += (int)(s.nDeliv[1] - nD1);
+            acc[3] += (int)dn;
+            acc[4] += 1;
+            acc[5] += s.latestDiff < 0 ? -s.latestDiff : s.latestDiff;
+            acc[6] += (int)(s.nTx - nTx0);
+            acc[7] += (int)(s.ties - ties0);
         }
     }
 
-    // K5: warp shuffle -> shared memory -> one atomic per block and statistic.  The values
-    // are small integers held in fp64, so the sums are exact and order-independent.
-    __shared__ double red[4][8];
+    // K5: warp reduction (REDUX) -> shared memory -> one atomic per block and statistic.  The
+    // per-block partial sums are small integers, so the fp64 totals are exact and order-independent.
+    __shared__ int red[STEP_BLOCK / 32][8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        double v = acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        const int v = __reduce_add_sync(0xFFFFFFFFu, acc[k]);
         if (lane == 0) red[threadIdx.x >> 5][k] = v;
     }
     __syncthreads();
     if (threadIdx.x < 8) {
-        double v = 0;
+        int v = 0;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
-        if (v != 0.0) atomicAdd(A.stats + threadIdx.x, v);
+        if (v != 0) atomicAdd(A.stats + threadIdx.x, (double)v);
     }
 }
 
@@ -809,7 +870,7 @@ pendulum_step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__
     }
     const uint32_t nTx0 = s.nTx, nD0 = s.nDeliv[0], nD1 = s.nDeliv[1];
     begin_assignment(s, P, dev, dur);
-    DevRing ring{A.st.ring + i, nsim, A.st.hot + i};
+    DevRing ring{A.st.ring + i, nsim, A.st.hot + i, false, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     PendulumPlant<DevVals, DevSrxOut> plant(Q, S, DevVals{A.st.pval + i, nsim}, DevSrxOut{A.st.srx + i, A.st.ntab});
     run_until_assign_plant<MODE_R>(s, P, P.band[0], srx, ring, NoMasks(), NoMemo(), plant);
     // InvertedPendulumInterpreter (inverted_pendulum.py:42-56): the angle is read from the plant
@@ -881,7 +942,7 @@ __global__ void reset_kernel(StatePtrs st, Params P, const long long *env_ids, l
     const long long i = e * st.nb + band;
     Sim<D, NS, NJ> s;
     load_sim(s, st, i, st.now[e]);
-    DevRing ring{st.ring + i, st.nsim, st.hot + i};
+    DevRing ring{st.ring + i, st.nsim, st.hot + i, false, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     reset_sim(s, P.band[band], ring);
     store_sim(s, st, i, true);
     if (obs) obs[i] = (long long)s.latestDiff + kCounterBound;       // counter_traffic.py:144
@@ -1206,6 +1267,9 @@ static void fill_params(const gw_config &cfg, Params &P)
     P.tenLog10BitRate = 10 * std::log10(P.bitRate);
     P.qDen = 1.135 * std::sqrt(2 * 3.141592653589793);
     P.bitsFactor = 2 - 0.75;
+    // GYMWIPE_B200_NO_MACRO=1: every timed event through the generic transition function (A/B tests)
+    finish_params(P);
+    P.noMacro = std::getenv("GYMWIPE_B200_NO_MACRO") ? std::atoi(std::getenv("GYMWIPE_B200_NO_MACRO")) : 0;
     for (int b = 0; b < cfg.n_bands; ++b) {
         const gw_band_config &cb = cfg.band[b];
         BandParams &B = P.band[b];
@@ -1309,6 +1373,7 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
     h->cfg = *cfg;
     h->device = device;
     h->D = D; h->NS = NS; h->NJ = NJ;
+    h->pdl = std::getenv("GYMWIPE_B200_NO_PDL") ? 0 : 1;
     fill_params(*cfg, h->P);
     const long long ntab = cfg->per_env_positions ? cfg->n_envs * cfg->n_bands : 1;
     h->layout = make_layout(cfg->n_envs, cfg->n_bands, ntab, cfg->plant);
@@ -1371,8 +1436,8 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
             unsigned long long want = 32ull * (unsigned long long)nsim;
             while (h->memo_entries < want && h->memo_entries < (1u << 26)) h->memo_entries <<= 1;
         }
-        e = cudaMalloc((void **)&h->memo, 32ull * h->memo_entries);
-        if (e == cudaSuccess) e = cudaMemsetAsync(h->memo, 0, 32ull * h->memo_entries, s);
+        e = cudaMalloc((void **)&h->memo, 32ull * (h->memo_entries + MEMO_L0));      // second + first level
+        if (e == cudaSuccess) e = cudaMemsetAsync(h->memo, 0, 32ull * (h->memo_entries + MEMO_L0), s);
         if (e != cudaSuccess) { cudaFree(stg); gw_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
     }
     h->errflag = (int *)(h->stats + 8);
@@ -1444,6 +1509,8 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     A.masks.mode = h->cfg.mode; A.masks.seed = h->cfg.seed; A.masks.env_offset = h->cfg.env_id_offset;
     A.masks.words = h->masks; A.masks.slots = h->mask_slots > 0 ? h->mask_slots : 1; A.masks.words_per_row = h->mask_words;
     A.memo.tab = h->memo; A.memo.mask = h->memo_entries ? h->memo_entries - 1 : 0;
+    A.memo.l0g = (h->memo && !h->st.per_env) ? h->memo + 2ull * h->memo_entries : nullptr;
+    A.memo.l0s = nullptr;
     SharedTables T;
     std::memset(&T, 0, sizeof T);
     if (!h->st.per_env) {
@@ -1465,8 +1532,8 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
         return GW_OK;
     }
     // one wave: 128-thread blocks, a multiple of the SM count when the batch is large
-    int blocks = grid_for(nsim, 128);
-    const int cap = 148 * 16;
+    int blocks = grid_for(nsim, STEP_BLOCK);
+    const int cap = 148 * GW_STEP_MIN_BLOCKS * 4;
     if (blocks > cap) blocks = cap;
 #define LAUNCH_STEP(KERNEL, DD, SS, JJ)                                                              \
     do {                                                                                             \
@@ -1476,7 +1543,14 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
             CUDA_TRY(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
             configured = true;                                                                       \
         }                                                                                            \
-        KERNEL<<<blocks, STEP_BLOCK, smem, s>>>(A, h->P, T);                                          \
+        cudaLaunchConfig_t lc = {};                                                                  \
+        lc.gridDim = dim3((unsigned)blocks); lc.blockDim = dim3(STEP_BLOCK);                         \
+        lc.dynamicSmemBytes = smem; lc.stream = s;                                                   \
+        cudaLaunchAttribute at[1];                                                                   \
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                               \
+        at[0].val.programmaticStreamSerializationAllowed = 1;                                        \
+        lc.attrs = at; lc.numAttrs = h->pdl ? 1 : 0;                                                 \
+        CUDA_TRY(cudaLaunchKernelEx(&lc, KERNEL, A, h->P, T));                                       \
     } while (0)
 #define CALL_STEP(DD, SS, JJ)                                                                        \
     do {                                                                                             \
@@ -1656,6 +1730,14 @@ int gw_count_bit_errors(const uint32_t *mask_words, int32_t words_per_row, const
     CUDA_TRY(cudaGetLastError());
     return GW_OK;
 }
+
+#ifdef GW_MEMO_STATS
+int gw_debug_memo_stats(unsigned long long *out2)
+{
+    CUDA_TRY(cudaMemcpyFromSymbol(out2, g_memo_stats, sizeof(unsigned long long) * 2));
+    return GW_OK;
+}
+#endif
 
 int gw_philox4x32(const uint32_t *counter, const uint32_t *key, uint32_t *out, int64_t n, void *stream)
 {

@@ -8,6 +8,8 @@
 #include <cstring>
 #include <vector>
 
+static long long g_macro_stat[4] = {0, 0, 0, 0};
+#define GW_STAT_MACRO(i) (++g_macro_stat[i])
 #include "../../gymwipe_b200/csrc/gw_core.cuh"
 #include "../../gymwipe_b200/csrc/gw_pendulum.cuh"
 
@@ -49,9 +51,12 @@ struct HsScenario {
     HsBand band[kMaxBands];
 };
 
+int g_no_macro = 0;     // hs_set_no_macro(1): every event through the generic transition function
+
 void fill_params(const HsScenario &sc, Params &P)
 {
     std::memset(&P, 0, sizeof P);
+    P.noMacro = g_no_macro;
     P.nbands = sc.nbands; P.factor = sc.factor; P.maxDuration = 20; P.mode = sc.mode;
     P.bitRate = 133.33333e3;
     P.dataRate = 0.75 * P.bitRate;
@@ -59,6 +64,7 @@ void fill_params(const HsScenario &sc, Params &P)
     P.tenLog10BitRate = 10 * std::log10(P.bitRate);
     P.qDen = 1.135 * std::sqrt(2 * 3.141592653589793);
     P.bitsFactor = 1.25;
+    finish_params(P);
     for (int b = 0; b < sc.nbands; ++b) {
         BandParams &B = P.band[b];
         const HsBand &h = sc.band[b];
@@ -168,6 +174,14 @@ int hs_run(const HsScenario *sc, int64_t nenv, int nsteps, int do_reset, const d
     return -1;
 }
 
+void hs_set_no_macro(int v) { g_no_macro = v; }
+
+// macro-event statistics since the last call: {isolated transmissions, quiet tails}
+void hs_macro_stats(long long *out2) { out2[0] = g_macro_stat[0]; out2[1] = g_macro_stat[1]; g_macro_stat[0] = g_macro_stat[1] = 0; }
+
+// generic-path statistics since the last call: {non-tick events, tick events} through process_event
+void hs_generic_stats(long long *out2) { out2[0] = g_macro_stat[2]; out2[1] = g_macro_stat[3]; g_macro_stat[2] = g_macro_stat[3] = 0; }
+
 double hs_ber(double S, double N)
 {
     return ber_bpsk_mw(S, N, 10 * std::log10(133.33333e3), 1.135 * std::sqrt(2 * 3.141592653589793));
@@ -185,6 +199,26 @@ void hs_pendulum_advance(const double *params /* M m l g fMax kServo dtMax */, d
     S.ctrlAngleDeg = 0; S.lastError = 0;
     pendulum_advance(Q, S, now);
     state[0] = S.x; state[1] = S.v; state[2] = S.th; state[3] = S.om; state[5] = S.tPlant;
+}
+
+// the decider with the division-free shortcut (1) and with the reference's division (0)
+int hs_within_max_ber(double err_sum, double total_bits, double max_ber, int shortcut)
+{
+    Params P;
+    std::memset(&P, 0, sizeof P);
+    P.bitRate = 133.33333e3; P.dataRate = 0.75 * P.bitRate; P.maxBer = max_ber; P.bitsFactor = 1.25;
+    finish_params(P);
+    if (!shortcut) P.berMult = 0.0;
+    return within_max_ber(P, err_sum, total_bits) ? 1 : 0;
+}
+
+double hs_airtime(int bytes)
+{
+    Params P;
+    std::memset(&P, 0, sizeof P);
+    P.bitRate = 133.33333e3; P.dataRate = 0.75 * P.bitRate; P.maxBer = 0.25; P.bitsFactor = 1.25;
+    finish_params(P);
+    return airtime_of(P, bytes);
 }
 
 double hs_fmod_slot(double t) { return fmod_slot(t); }

@@ -56,6 +56,10 @@ def lib():
         L.hs_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.hs_fmod_slot.restype = C.c_double
         L.hs_fmod_slot.argtypes = [C.c_double]
+        L.hs_within_max_ber.restype = C.c_int
+        L.hs_within_max_ber.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
+        L.hs_airtime.restype = C.c_double
+        L.hs_airtime.argtypes = [C.c_int]
         L.hs_pendulum_advance.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
         L.hs_mask_errors.restype = C.c_int64
         L.hs_mask_errors.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.c_int,
@@ -96,8 +100,9 @@ def scenario_from_dict(d, mode=0, seed=0):
     return sc
 
 
-def run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, mode=0, seed=0, env_offset=0):
+def run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, mode=0, seed=0, env_offset=0, macros=True):
     L = lib()
+    L.hs_set_no_macro(0 if macros else 1)
     sc = scenario_from_dict(scenario, mode, seed) if isinstance(scenario, dict) else scenario
     nb = sc.nbands
     dev_tape = np.ascontiguousarray(dev_tape, dtype=np.int32)
@@ -118,4 +123,6 @@ def run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, mode=0, seed=0, e
         return None if a is None else a.ctypes.data_as(C.c_void_p)
     rc = L.hs_run(C.byref(sc), nenv, nsteps, 1 if do_reset else 0, ptr(pos), ptr(dev_tape), ptr(dur_tape),
                   ptr(obs), ptr(rew), ptr(done), ptr(now), ptr(counts), ptr(power), env_offset)
-    return {"rc": rc, "obs": obs, "reward": rew, "done": done, "now": now, "counts": counts, "power": power}
+    ms = (C.c_longlong * 2)()
+    L.hs_macro_stats(ms)
+    return {"macro_tx": int(ms[0]), "macro_tail": int(ms[1]), "rc": rc, "obs": obs, "reward": rew, "done": done, "now": now, "counts": counts, "power": power}

@@ -152,3 +152,55 @@ def test_philox_known_answers():
         o = np.zeros(4, np.uint32)
         L.hs_philox(c.ctypes.data, k.ctypes.data, o.ctypes.data)
         assert tuple(int(x) for x in o) == want
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_macro_events_equal_the_generic_path(seed):
+    """
+    The macro events (isolated transmissions, quiet step tails; gw_core.cuh) are exact shortcuts:
+    results, event times, transmission / delivery / tie counters and the received-power residue
+    equal those of the generic one-event-at-a-time path, and the shortcuts are actually taken.
+    """
+    from gymwipe_b200.scenario import default_scenario_dict
+    rs = np.random.RandomState(4000 + seed)
+    cases = [(default_scenario_dict(), 96, 140),
+             (random_scenario(rs, jammers=0, spread=2.5), 48, 120),
+             (random_scenario(rs, jammers=1, spread=2.5), 48, 120),
+             (random_scenario(rs, nbands=4, jammers=1, spread=3.0), 12, 60),
+             (random_scenario(rs, nbands=2, jammers=0, spread=3.0), 24, 80)]
+    for sc, nenv, nsteps in cases:
+        nb = len(sc["bands"])
+        dev, dur = random_tapes(rs, nsteps, nenv, nb)
+        a = HS.run(sc, dev, dur, do_reset=bool(seed & 1), macros=True)
+        b = HS.run(sc, dev, dur, do_reset=bool(seed & 1), macros=False)
+        assert a["rc"] == 0 and b["rc"] == 0
+        for k in ("obs", "reward", "done", "now", "counts", "power"):
+            assert (a[k] == b[k]).all(), k
+        assert b["macro_tx"] == 0 and b["macro_tail"] == 0
+        assert a["macro_tx"] > 0
+        if not any(d["role"] == "jammer" for d in sc["bands"][0]["devices"]):
+            # without interferers almost every transmission is isolated
+            assert a["macro_tx"] >= 0.9 * a["counts"][:, :, 0].sum()
+
+
+def test_decider_shortcut_equals_the_division():
+    """round(errSum) / totalBits <= 2^-k  <=>  round(errSum) * 2^k <= totalBits (gw_core.cuh::within_max_ber)."""
+    L = HS.lib()
+    rs = np.random.RandomState(3)
+    for max_ber in (0.25, 0.5, 0.125):
+        for nbytes in list(range(1, 40)) + [100, 1525, 65561] + list(rs.randint(1, 70000, 40)):
+            bits = nbytes * 8 * 1.25
+            edge = bits * max_ber
+            cand = [0.0, 0.4, 0.5, 0.5000001, 1.5, 2.5, edge, edge - 0.5, edge + 0.5, edge - 0.5000001, edge + 0.4999999,
+                    edge + 1, edge - 1, np.nextafter(edge + 0.5, 0), np.nextafter(edge + 0.5, 1e9), 1e9, 1e300,
+                    float("inf"), float("nan")] + list(rs.uniform(0, 2 * edge + 2, 30))
+            for e in cand:
+                assert L.hs_within_max_ber(float(e), bits, max_ber, 1) == L.hs_within_max_ber(float(e), bits, max_ber, 0), (e, bits, max_ber)
+    # a code rate whose bound is not a power of two keeps the division (both calls take the same path)
+    assert L.hs_within_max_ber(10.0, 130.0, 1.0 / 3, 1) == 1 and L.hs_within_max_ber(50.0, 130.0, 1.0 / 3, 1) == 0
+
+
+def test_airtime_table_equals_the_division():
+    L = HS.lib()
+    for k in list(range(0, 64)) + [1525, 65561]:
+        assert L.hs_airtime(k) == (k * 8) / (0.75 * 133.33333e3)
