@@ -367,6 +367,19 @@ GW_HD typename A::value_type get_at(const A &a, int i)
         return r;
     }
 }
+// Received-power table of a band-sim, entry (receiver p, sender d).  Two representations:
+//  * a plain array [D * D] that the compiler keeps in registers (host build, plant envs): a run-time
+//    sender index is resolved by selects;
+//  * SrxView: a table in memory (the step kernels: shared memory for a geometry common to all
+//    envs, global memory for per-env geometries), entry (p, d) at base[(p * kMaxDev + d) * stride]
+//    -- no registers are held for it.
+struct SrxView {
+    const double *base;
+    long long stride;
+};
+template <int D>
+GW_HD double srx_at(const SrxView &x, int p, int d) { return x.base[(long long)(p * kMaxDev + d) * x.stride]; }
+
 // received power of receiver p (compile-time after unrolling) from sender d (run time)
 template <int D>
 GW_HD double srx_at(const double *srx, int p, int d)
@@ -483,8 +496,8 @@ GW_HD Event next_event(Sim<D, NS, NJ, ST> &s, const BandParams &B, double tLimit
 //              then the receive process counts again -- appendix B #4)
 // ---------------------------------------------------------------------------
 
-template <int D, int NS, int NJ, class ST>
-GW_HD void count_set(const Sim<D, NS, NJ, ST> &s, const Event &ev, const double *srx, int &once, int &twice)
+template <int D, int NS, int NJ, class ST, class SRX>
+GW_HD void count_set(const Sim<D, NS, NJ, ST> &s, const Event &ev, const SRX &srx, int &once, int &twice)
 {
     once = 0; twice = 0;
     if (ev.kind != EV_PHY) return;
@@ -723,9 +736,9 @@ GW_HD bool decide_rec(Sim<D, NS, NJ, ST> &s, const Params &P, int p, int section
 // PHYs whose bit error rate must be re-evaluated afterwards (SimplePhy._updateBitErrorRate)
 // ---------------------------------------------------------------------------
 
-template <int D, int NS, int NJ, class ST, class Ring, class Plant>
+template <int D, int NS, int NJ, class ST, class SRX, class Ring, class Plant>
 GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const Event &ev,
-                      double *srx, const Ring &ring, Plant &plant)
+                      SRX srx, const Ring &ring, Plant &plant)
 {
     constexpr int RRM = NS;
     int berMask = 0;
@@ -789,7 +802,7 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
             set_at(s.txSeq, d, get_at(s.txSeq, d) + 1u);
             s.nTx += 1;
             trace_rec(s, REC_TX, s.now, d, stop, (hdrBytes * 8) * P.bitsFactor, (payBytes * 8) * P.bitsFactor, 0.0);
-            if (Plant::active) plant.refresh_links(d, s.now, srx);
+            if constexpr (Plant::active) plant.refresh_links(d, s.now, srx);
             // zero-delay notification: every other PHY registers the received power
             // (simple_stack.py:130-144); a PHY that is receiving re-evaluates its BER
             GW_UNROLL
@@ -939,12 +952,12 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
     return berMask;
 }
 
-template <int D, int NS, int NJ, class ST, class Ring>
+template <int D, int NS, int NJ, class ST, class SRX, class Ring>
 GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const Event &ev,
-                      const double *srx, const Ring &ring)
+                      const SRX &srx, const Ring &ring)
 {
     NoPlant np;
-    return apply_event(s, P, B, ev, const_cast<double *>(srx), ring, np);
+    return apply_event(s, P, B, ev, srx, ring, np);
 }
 
 // BER(S, N) is a pure function and, with static geometry, the same few (S, N) pairs recur in
@@ -956,8 +969,8 @@ struct NoMemo {
 };
 
 // SimplePhy._updateBitErrorRate for the PHYs in berMask (simple_stack.py:161-173)
-template <int D, int NS, int NJ, class ST, class Memo>
-GW_HD void update_bers(Sim<D, NS, NJ, ST> &s, const Params &P, int berMask, const double *srx, const Memo &memo)
+template <int D, int NS, int NJ, class ST, class SRX, class Memo>
+GW_HD void update_bers(Sim<D, NS, NJ, ST> &s, const Params &P, int berMask, const SRX &srx, const Memo &memo)
 {
     GW_UNROLL
     for (int p = 0; p < D; ++p) {
@@ -977,8 +990,8 @@ GW_HD void update_bers(Sim<D, NS, NJ, ST> &s, const Params &P, int berMask, cons
     }
 }
 
-template <int D, int NS, int NJ, class ST>
-GW_HD void update_bers(Sim<D, NS, NJ, ST> &s, const Params &P, int berMask, const double *srx)
+template <int D, int NS, int NJ, class ST, class SRX>
+GW_HD void update_bers(Sim<D, NS, NJ, ST> &s, const Params &P, int berMask, const SRX &srx)
 {
     update_bers(s, P, berMask, srx, NoMemo());
 }
@@ -1018,9 +1031,9 @@ struct NoMasks {
 };
 
 // processes ONE timed event; `masks(receiver, sender, txseq, k0, k1, ber)` supplies mode-M counts
-template <int MODE, int D, int NS, int NJ, class ST, class Ring, class Masks, class Memo, class Plant>
+template <int MODE, int D, int NS, int NJ, class ST, class SRX, class Ring, class Masks, class Memo, class Plant>
 GW_HD void process_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const Event &ev,
-                         double *srx, const Ring &ring, const Masks &masks, const Memo &memo, Plant &plant)
+                         SRX srx, const Ring &ring, const Masks &masks, const Memo &memo, Plant &plant)
 {
     int once, twice;
     GW_STAT_MACRO(2 + (ev.kind == EV_TICK ? 1 : 0));
@@ -1042,12 +1055,12 @@ GW_HD void process_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParam
     update_bers(s, P, berMask, srx, memo);
 }
 
-template <int MODE, int D, int NS, int NJ, class ST, class Ring, class Masks, class Memo>
+template <int MODE, int D, int NS, int NJ, class ST, class SRX, class Ring, class Masks, class Memo>
 GW_HD void process_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const Event &ev,
-                         const double *srx, const Ring &ring, const Masks &masks, const Memo &memo)
+                         const SRX &srx, const Ring &ring, const Masks &masks, const Memo &memo)
 {
     NoPlant np;
-    process_event<MODE>(s, P, B, ev, const_cast<double *>(srx), ring, masks, memo, np);
+    process_event<MODE>(s, P, B, ev, srx, ring, masks, memo, np);
 }
 
 // ---------------------------------------------------------------------------
@@ -1065,191 +1078,196 @@ GW_HD void process_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParam
 // from the generic path's -- it only breaks exact-time ties between a tick and an unrelated event,
 // which are counted in `ties` either way.  Anything unusual (a power table entry that fails the
 // reference's assertions, a completion time that rounds below the stop time -- appendix B #12)
-// declines, and the generic path handles it.
+// declines, and the generic path handles it.  Transmissions that follow back to back -- the
+// grantee's first packet after the announcement, the next packet of the same window -- are CHAINED:
+// the follower's slot-start event is the next event by the same test, so no event selection is
+// needed in between, and the chain keeps the received powers, the links from the sender and the
+// last BER per receiver in registers (the same (S, N) recurs from packet to packet).
 //
 // quiet_tail(): after the announcement (and the data packets) nothing is on air, no MAC waits for a
 // packet or a transmission and only window time-outs and the RRM guard time-out are pending: they
 // cannot create events, so they are applied in (time, seq) order without the selection machinery.
 // ---------------------------------------------------------------------------
 
-template <int D, int NS, int NJ, class ST, class Ring, class Memo>
-GW_HD bool isolated_tx_one(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const int d, const double ts,
-                           const double *srx, const Ring &ring, const Memo &memo, double tLimit)
+template <int D, int NS, int NJ, class ST, class SRX, class Ring, class Memo>
+GW_HD bool isolated_tx(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const Event &ev,
+                       const SRX &srx, const Ring &ring, const Memo &memo, double tLimit)
 {
     static_assert(NS == 2, "the tick logic is written for two senders per band");
     constexpr int RRM = NS;
+    int d = ev.idx;
     if (get_at(s.sphase, d) != S_SLOT) return false;
+    // structural part of the isolation test; it stays true along the chain (nothing but the chained
+    // transmissions happens, and their completion handlers leave every receiver idle)
     bool ok = true;
     GW_UNROLL
     for (int p = 0; p < D; ++p) ok &= (s.rxOf[p] < 0) & ((p == d) | (s.sphase[p] == S_IDLE));
     GW_UNROLL
     for (int k = 0; k < NS; ++k) ok &= s.mac[k] != MAC_WAIT_COND;
     if (!ok) return false;
+    // the earliest OTHER timed event (window time-outs, the RRM guard time-out, jammer wake-ups,
+    // the caller's horizon): a transmission is isolated if it completes strictly before it
+    double tOther = tLimit;
+    GW_UNROLL
+    for (int k = 0; k < NS; ++k) if (s.wPend[k]) tOther = fmin(tOther, s.stopW[k]);
+    if (s.rrmPend) tOther = fmin(tOther, s.tRrm);
+    GW_UNROLL
+    for (int j = 0; j < NJ; ++j) tOther = fmin(tOther, s.tJam[j]);
 
-    // Transmission.__init__ (physical.py:224-279), as in apply_event / S_SLOT
-    const int payBytes = get_at(s.cmdPay, d);
-    const int hdrBytes = (NJ > 0 && d > RRM) ? B.jamHdr[0] : kMacHdr;
-    const double hd = airtime_of(P, hdrBytes);
-    const double pd = airtime_of(P, payBytes);
-    const double duration = hd + pd;
-    const double stop = ts + duration;
-    const double headerStop = ts + hd;
-    const double tH = ts + (headerStop > ts ? headerStop - ts : 0.0);
-    const double tC = ts + (stop > ts ? stop - ts : 0.0);
-    ok = (tH > ts) & (tC > tH) & (tC >= stop) & (tC < tLimit);
+    // state of the chain, in registers: received powers (written back at the end), the links from
+    // the current sender, the last BER evaluated per receiver (the same (S, N) recurs from packet
+    // to packet), transmissions not yet added to txSeq[d]
+    double ts = ev.t;
+    double Pc[D], rp[D], lastN[D], lastBer[D];
     GW_UNROLL
-    for (int k = 0; k < NS; ++k) ok &= (s.wPend[k] == 0) | (s.stopW[k] > tC);
-    ok &= (s.rrmPend == 0) | (s.tRrm > tC);
-    GW_UNROLL
-    for (int j = 0; j < NJ; ++j) ok &= s.tJam[j] > tC;
-    // received powers; the reference's assertions on signal / noise power (simple_stack.py:168-169)
-    double rp[D], Pn[D];
-    GW_UNROLL
-    for (int p = 0; p < D; ++p) {
-        rp[p] = srx_at<D>(srx, p, d);
-        Pn[p] = s.P[p] + rp[p];
-        const double N = Pn[p] - rp[p];
-        ok &= (p == d) | ((rp[p] >= 0) & (N >= 0));
-    }
-    if (!ok) return false;
-
-    GW_STAT_MACRO(0);
-
-    // ---- slot start: the transmission begins, every other PHY registers its power and locks on
-    s.now = ts;
-    s.seq++;                                    // creation number of the header-end event
-    const uint32_t qC = s.seq++;
-    set_at(s.tC, d, tC);
-    set_at(s.sC, d, qC);
-    set_at(s.txStart, d, ts);
-    set_at(s.tStop, d, stop);
-    set_at(s.txSeq, d, get_at(s.txSeq, d) + 1u);
-    s.nTx += 1;
-    const double hdrBits = (hdrBytes * 8) * P.bitsFactor;
-    const double payBits = (payBytes * 8) * P.bitsFactor;
-    trace_rec(s, REC_TX, ts, d, stop, hdrBits, payBits, 0.0);
-    double ber[D];
-    GW_UNROLL
-    for (int p = 0; p < D; ++p) {
-        ber[p] = 0.0;
-        if (p == d) continue;
-        s.P[p] = Pn[p];
-        const double S = rp[p], N = Pn[p] - S;
-        double b;
-        if (!memo.get(S, N, b)) {
-            b = ber_bpsk_mw_cold(S, N, P.tenLog10BitRate, P.qDen);
-            memo.put(S, N, b);
-        }
-        ber[p] = b;
-        trace_rec(s, REC_BER, ts, p, b, 0.0, 0.0, 0.0);
-    }
-
-    // ---- header end (simple_stack.py:241-251).  Ticks are silent here: those up to the completion
-    // are applied in one batch below (nothing observes the queues before the completion handler)
-    s.now = tH;
-    bool locked[D];
-    GW_UNROLL
-    for (int p = 0; p < D; ++p) {
-        locked[p] = false;
-        if (p == d) continue;
-        const double bitErrors = ber[p] * (tH - ts) * P.bitRate;
-        const double e = 0.0 + bitErrors;
-        locked[p] = within_max_ber(P, e, hdrBits);
-        trace_rec(s, REC_DEC, tH, p, 0, e, hdrBits, locked[p] ? 1.0 : 0.0);
-    }
-    if (s.trace != nullptr) {
-        // the BER of a receiver that passed the header is evaluated again: same powers, same value
+    for (int p = 0; p < D; ++p) { Pc[p] = s.P[p]; rp[p] = srx_at<D>(srx, p, d); lastN[p] = -1.0; lastBer[p] = 0.0; }
+    uint32_t txs = 0;
+    bool any = false;
+    NoPlant plant;
+    for (;;) {
+        // Transmission.__init__ (physical.py:224-279), as in apply_event / S_SLOT
+        const int payBytes = get_at(s.cmdPay, d);
+        const int hdrBytes = (NJ > 0 && d > RRM) ? B.jamHdr[0] : kMacHdr;
+        const double hd = airtime_of(P, hdrBytes);
+        const double pd = airtime_of(P, payBytes);
+        const double duration = hd + pd;
+        const double stop = ts + duration;
+        const double headerStop = ts + hd;
+        const double tH = ts + (headerStop > ts ? headerStop - ts : 0.0);
+        const double tC = ts + (stop > ts ? stop - ts : 0.0);
+        bool okT = (tH > ts) & (tC > tH) & (tC >= stop) & (tC < tOther);
+        // received powers; the reference's assertions on signal / noise power (simple_stack.py:168-169)
+        double Pn[D];
         GW_UNROLL
-        for (int p = 0; p < D; ++p) if (p != d && locked[p]) trace_rec(s, REC_BER, tH, p, ber[p], 0.0, 0.0, 0.0);
-    }
-
-    // ---- completion (simple_stack.py:146-157, 253-267)
-    silent_ticks<0>(s, B.mult[0], B.interval[0], tC, qC, true, tLimit);
-    silent_ticks<1>(s, B.mult[1], B.interval[1], tC, qC, true, tLimit);
-    s.now = tC;
-    set_at(s.sphase, d, (int)S_IDLE);
-    set_at(s.tEv, d, tC);
-    set_at(s.sEv, d, qC);
-    int window = -1;
-    GW_UNROLL
-    for (int p = 0; p < D; ++p) {
-        if (p == d) continue;
-        double e = 0.0;
-        if (locked[p]) {
-            // the completion callback counts (if the power changes), then the receive process
-            // counts again -- appendix B #4
-            const double bitErrors = ber[p] * (tC - tH) * P.bitRate;
-            e = 0.0 + bitErrors;
-            if (rp[p] != 0.0) e += bitErrors;
+        for (int p = 0; p < D; ++p) {
+            Pn[p] = Pc[p] + rp[p];
+            const double N = Pn[p] - rp[p];
+            okT &= (p == d) | ((rp[p] >= 0) & (N >= 0));
         }
-        s.P[p] += -rp[p];
-        if (locked[p]) {
-            const bool okP = within_max_ber(P, e, payBits);
-            trace_rec(s, REC_DEC, tC, p, 1, e, payBits, okP ? 1.0 : 0.0);
-            if (okP) {
-                if (p < NS) {
-                    if (d == RRM && s.annDest == p && s.mac[p] == MAC_NONE) window = p;
-                } else if (p == RRM) {
-                    if (d < NS) {
-                        if (d == 0) s.rv0 = kCounterByteLen;
-                        if (d == 1) s.rv1 = kCounterByteLen;
-                        s.latestDiff = s.rv0 - s.rv1;
-                        set_at(s.nDeliv, d, get_at(s.nDeliv, d) + 1u);
+        if (!okT) break;
+        any = true;
+        GW_STAT_MACRO(0);
+
+        // ---- slot start: the transmission begins, every other PHY registers its power and locks on
+        s.seq++;                                    // creation number of the header-end event
+        const uint32_t qC = s.seq++;
+        ++txs;
+        s.nTx += 1;
+        const double hdrBits = (hdrBytes * 8) * P.bitsFactor;
+        const double payBits = (payBytes * 8) * P.bitsFactor;
+        trace_rec(s, REC_TX, ts, d, stop, hdrBits, payBits, 0.0);
+        GW_UNROLL
+        for (int p = 0; p < D; ++p) {
+            if (p == d) continue;
+            const double S = rp[p], N = Pn[p] - S;
+            if (N != lastN[p]) {
+                double b;
+                if (!memo.get(S, N, b)) {
+                    b = ber_bpsk_mw_cold(S, N, P.tenLog10BitRate, P.qDen);
+                    memo.put(S, N, b);
+                }
+                lastN[p] = N; lastBer[p] = b;
+            }
+            trace_rec(s, REC_BER, ts, p, lastBer[p], 0.0, 0.0, 0.0);
+        }
+
+        // ---- header end (simple_stack.py:241-251).  Ticks are silent here: those up to the
+        // completion are applied in one batch below (nothing observes the queues before the
+        // completion handler)
+        bool locked[D];
+        GW_UNROLL
+        for (int p = 0; p < D; ++p) {
+            locked[p] = false;
+            if (p == d) continue;
+            const double bitErrors = lastBer[p] * (tH - ts) * P.bitRate;
+            const double e = 0.0 + bitErrors;
+            locked[p] = within_max_ber(P, e, hdrBits);
+            trace_rec(s, REC_DEC, tH, p, 0, e, hdrBits, locked[p] ? 1.0 : 0.0);
+        }
+        if (s.trace != nullptr) {
+            // the BER of a receiver that passed the header is evaluated again: same powers, same value
+            GW_UNROLL
+            for (int p = 0; p < D; ++p) if (p != d && locked[p]) trace_rec(s, REC_BER, tH, p, lastBer[p], 0.0, 0.0, 0.0);
+        }
+
+        // ---- completion (simple_stack.py:146-157, 253-267)
+        silent_ticks<0>(s, B.mult[0], B.interval[0], tC, qC, true, tLimit);
+        silent_ticks<1>(s, B.mult[1], B.interval[1], tC, qC, true, tLimit);
+        s.now = tC;
+        set_at(s.sphase, d, (int)S_IDLE);
+        int window = -1;
+        GW_UNROLL
+        for (int p = 0; p < D; ++p) {
+            if (p == d) continue;
+            double e = 0.0;
+            if (locked[p]) {
+                // the completion callback counts (if the power changes), then the receive process
+                // counts again -- appendix B #4
+                const double bitErrors = lastBer[p] * (tC - tH) * P.bitRate;
+                e = 0.0 + bitErrors;
+                if (rp[p] != 0.0) e += bitErrors;
+            }
+            Pc[p] = Pn[p] + -rp[p];
+            if (locked[p]) {
+                const bool okP = within_max_ber(P, e, payBits);
+                trace_rec(s, REC_DEC, tC, p, 1, e, payBits, okP ? 1.0 : 0.0);
+                if (okP) {
+                    if (p < NS) {
+                        if (d == RRM && s.annDest == p && s.mac[p] == MAC_NONE) window = p;
+                    } else if (p == RRM) {
+                        if (d < NS) {
+                            if (d == 0) s.rv0 = kCounterByteLen;
+                            if (d == 1) s.rv1 = kCounterByteLen;
+                            s.latestDiff = s.rv0 - s.rv1;
+                            set_at(s.nDeliv, d, get_at(s.nDeliv, d) + 1u);
+                        }
+                        trace_rec(s, REC_RX, tC, d, 0.0, 0.0, 0.0, 0.0);
                     }
-                    trace_rec(s, REC_RX, tC, d, 0.0, 0.0, 0.0, 0.0);
                 }
             }
+            // (the receivers' reception fields -- error sum, BER, reset time, section -- are dead once
+            // rxOf is -1 again: a lock-on rewrites them; they are not maintained along the chain)
         }
-        // end of the reception (rx_clear); rxOf stays -1
-        s.rxSec[p] = locked[p] ? 1 : 0;
-        s.err[p] = 0.0; s.ber[p] = 0.0;
-        s.tReset[p] = locked[p] ? tC : tH;
-        s.segT0[p] = s.tReset[p];
-    }
-    NoPlant plant;
-    if (window >= 0) {
-        const double timeTotal = s.annSlots * kSlot;
-        const double stopW = tC + timeTotal;
-        const uint32_t qW = s.seq++;
-        set_at(s.stopW, window, stopW);
-        set_at(s.sW, window, qW);
-        set_at(s.wPend, window, 1);
-        set_at(s.wDone, window, 0);
-        mac_loop_head(s, P, B, window, ring, plant);
-    }
-    if (d < NS) {
-        mac_loop_head(s, P, B, d, ring, plant);
-    } else if (d == RRM) {
-        s.tRrm = tC + (s.annSlots + 1) * kSlot;
-        s.sRrm = s.seq++;
-        s.rrmPend = 1;
-    } else if (NJ > 0 && s.jamPending[0] > 0) {
-        s.jamPending[0] -= 1;
-        phy_send_init(s, d);
-    }
-    return true;
-}
+        if (window >= 0) {
+            const double timeTotal = s.annSlots * kSlot;
+            const double stopW = tC + timeTotal;
+            const uint32_t qW = s.seq++;
+            set_at(s.stopW, window, stopW);
+            set_at(s.sW, window, qW);
+            set_at(s.wPend, window, 1);
+            set_at(s.wDone, window, 0);
+            tOther = fmin(tOther, stopW);
+            mac_loop_head(s, P, B, window, ring, plant);
+        }
+        if (d < NS) {
+            mac_loop_head(s, P, B, d, ring, plant);
+        } else if (d == RRM) {
+            s.tRrm = tC + (s.annSlots + 1) * kSlot;
+            s.sRrm = s.seq++;
+            s.rrmPend = 1;
+            tOther = fmin(tOther, s.tRrm);
+        } else if (NJ > 0 && s.jamPending[0] > 0) {
+            s.jamPending[0] -= 1;
+            phy_send_init(s, d);
+        }
 
-// The slot-start event `ev` of device ev.idx, and -- chained -- the transmissions that follow it
-// back to back: the grantee's first packet after the announcement, the next packet of the same
-// sender's window.  The follower's slot-start event is the next event by the same isolation test
-// (every other timed event lies after ITS completion), so no event selection is needed in between.
-template <int D, int NS, int NJ, class ST, class Ring, class Memo>
-GW_HD bool isolated_tx(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const Event &ev,
-                       const double *srx, const Ring &ring, const Memo &memo, double tLimit)
-{
-    constexpr int RRM = NS;
-    int d = ev.idx;
-    double ts = ev.t;
-    bool any = false;
-    for (;;) {
-        if (!isolated_tx_one(s, P, B, d, ts, srx, ring, memo, tLimit)) break;
-        any = true;
-        // the only device that can have started a SEND in the completion handler
+        // ---- chain: the only device that can have started a SEND in the completion handler; its
+        // slot-start event is the next event if its transmission completes before tOther
         const int nx = (d == RRM) ? s.annDest : d;
         if (get_at(s.sphase, nx) != S_SLOT) break;
-        d = nx;
+        if (nx != d) {
+            set_at(s.txSeq, d, get_at(s.txSeq, d) + txs);
+            txs = 0;
+            d = nx;
+            GW_UNROLL
+            for (int p = 0; p < D; ++p) { rp[p] = srx_at<D>(srx, p, d); lastN[p] = -1.0; }
+        }
         ts = get_at(s.tEv, d);
+    }
+    if (any) {
+        set_at(s.txSeq, d, get_at(s.txSeq, d) + txs);
+        GW_UNROLL
+        for (int p = 0; p < D; ++p) s.P[p] = Pc[p];
     }
     return any;
 }
@@ -1303,9 +1321,9 @@ GW_HD void run_until_assign_plant(Sim<D, NS, NJ, ST> &s, const Params &P, const 
 }
 
 // SimMan.runSimulation(assignSignal.eProcessed) (counter_traffic.py:155)
-template <int MODE, int D, int NS, int NJ, class ST, class Ring, class Masks, class Memo = NoMemo>
+template <int MODE, int D, int NS, int NJ, class ST, class SRX, class Ring, class Masks, class Memo = NoMemo>
 GW_HD void run_until_assign(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B,
-                            const double *srx, const Ring &ring, const Masks &masks, const Memo &memo = Memo())
+                            const SRX &srx, const Ring &ring, const Masks &masks, const Memo &memo = Memo())
 {
     const bool macros = MODE == MODE_R && !P.noMacro;
     while (!s.assignDone && !s.fault) {
@@ -1318,8 +1336,8 @@ GW_HD void run_until_assign(Sim<D, NS, NJ, ST> &s, const Params &P, const BandPa
 
 // another band of the same env ended its assignment later, at time T: events strictly
 // before T are processed, then the clock is the env's clock
-template <int MODE, int D, int NS, int NJ, class ST, class Ring, class Masks, class Memo = NoMemo>
-GW_HD void run_until_time(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const double *srx,
+template <int MODE, int D, int NS, int NJ, class ST, class SRX, class Ring, class Masks, class Memo = NoMemo>
+GW_HD void run_until_time(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const SRX &srx,
                           const Ring &ring, const Masks &masks, double T, const Memo &memo = Memo())
 {
     while (!s.fault) {

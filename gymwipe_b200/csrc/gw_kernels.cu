@@ -405,22 +405,19 @@ struct DevRing {
     int32_t *base;      // ring + sim index
     long long nsim;
     const uint4 *hot;   // hot chunks + sim index
-    // counter epochs {snapEnd, epochK | epochC << 63} of both senders: the step kernels fetch them
-    // together with the rest of the state (head_size() needs them at every window), the other
-    // kernels read them on demand
-    bool have;
-    uint4 ep0, ep1;
+    // counter epochs {snapEnd, epochK | epochC << 63} of sender k: read where head_size() needs
+    // them (once per window / packet).  The step kernels prefetch both chunks into L2 together with
+    // the state loads, so the first read is an L2 hit and the following ones hit L1 -- without
+    // holding them in registers for the whole step.
     __device__ __forceinline__ int operator()(int k, uint32_t slot) const { return base[(long long)(k * kRingSlots + slot) * nsim]; }
     __device__ __forceinline__ void operator()(int k, uint32_t slot, int v) { base[(long long)(k * kRingSlots + slot) * nsim] = v; }
-    __device__ __forceinline__ uint4 ep(int k) const
-    {
-        if (have) return k == 0 ? ep0 : ep1;
-        return hot[(long long)(H_EP0 + k) * nsim];
-    }
+    __device__ __forceinline__ uint4 ep(int k) const { return hot[(long long)(H_EP0 + k) * nsim]; }
     template <class S> __device__ __forceinline__ unsigned long long snapEnd(const S &, int k) const { return lo_q(ep(k)); }
     template <class S> __device__ __forceinline__ unsigned long long epochK(const S &, int k) const { return hi_q(ep(k)) & ~(1ull << 63); }
     template <class S> __device__ __forceinline__ int epochC(const S &, int k) const { return (int)(hi_q(ep(k)) >> 63); }
 };
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ------------------------------------------------------------------------------------
 // BER memo: direct-mapped table of exact (S, N) -> BER results in device memory (L2 / L1
@@ -454,29 +451,21 @@ struct DevMemo {
         unsigned long long h = a * 0x9E3779B97F4A7C15ull ^ (b + 0xC2B2AE3D27D4EB4Full) * 0xD6E8FEB86659FD93ull;
         return (unsigned)(h >> 40) & mask;
     }
-    // first-level index: a few XORs of mantissa bits (no multiplies on the hot path)
-    __device__ __forceinline__ unsigned slot0(unsigned long long a, unsigned long long b) const
-    {
-        unsigned x = (unsigned)a ^ (unsigned)(a >> 32) ^ ((unsigned)b >> 3) ^ ((unsigned)(b >> 32) << 2);
-        x ^= x >> 16;
-        x ^= x >> 8;
-        return (x ^ (x >> 5)) & (MEMO_L0 - 1);
-    }
     __device__ __forceinline__ bool get(double S, double N, double &ber) const
     {
         if (!tab) return false;
         const unsigned long long a = (unsigned long long)__double_as_longlong(S), b = (unsigned long long)__double_as_longlong(N);
+        const unsigned h = slot(a, b);
         if (l0s) {
-            const unsigned h0 = slot0(a, b);
+            const unsigned h0 = h & (MEMO_L0 - 1);
             const ulonglong2 f0 = l0s[2 * h0], f1 = l0s[2 * h0 + 1];
             if (f0.x == a && f0.y == b && f1.y == (a ^ b ^ f1.x ^ MAGIC)) { ber = __longlong_as_double((long long)f1.x); return true; }
         }
-        const unsigned h = slot(a, b);
         const ulonglong2 e0 = tab[2 * h], e1 = tab[2 * h + 1];
         if (e0.x == a && e0.y == b && e1.y == (a ^ b ^ e1.x ^ MAGIC)) {
             ber = __longlong_as_double((long long)e1.x);
             GW_MEMO_COUNT(1);
-            if (l0g) { const unsigned h0 = slot0(a, b); l0g[2 * h0] = e0; l0g[2 * h0 + 1] = e1; }
+            if (l0g) { const unsigned h0 = h & (MEMO_L0 - 1); l0g[2 * h0] = e0; l0g[2 * h0 + 1] = e1; }
             return true;
         }
         return false;
@@ -491,7 +480,7 @@ struct DevMemo {
         tab[2 * h] = make_ulonglong2(a, b);
         tab[2 * h + 1] = make_ulonglong2(c, a ^ b ^ c ^ MAGIC);
         if (l0g) {
-            const unsigned h0 = slot0(a, b);
+            const unsigned h0 = h & (MEMO_L0 - 1);
             l0g[2 * h0] = make_ulonglong2(a, b);
             l0g[2 * h0 + 1] = make_ulonglong2(c, a ^ b ^ c ^ MAGIC);
         }
@@ -640,6 +629,8 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         for (int t = threadIdx.x; t < 2 * MEMO_L0; t += blockDim.x) memo_l0[t] = memo.l0g[t];
         memo.l0s = memo_l0;
     }
+    __shared__ double srx_s[kMaxBands][16];
+    if (threadIdx.x < kMaxBands * 16) srx_s[threadIdx.x >> 4][threadIdx.x & 15] = T.srx[threadIdx.x >> 4][threadIdx.x & 15];
     // Programmatic dependent launch: this grid may have been scheduled while the previous kernel
     // of the stream (the previous step, or whatever produced the actions) was still draining; its
     // memory is visible from here on.  The next kernel may start launching right away -- it waits
@@ -660,22 +651,17 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         const int band = active ? (int)(i & (nb - 1)) : 0;
 
         SimT s;
-        double srx[D * D];
         const BandParams &B = P.band[band];
-        DevRing ring{A.st.ring + (active ? i : 0), nsim, A.st.hot + (active ? i : 0), false, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        // received-power table: the block's shared copy (one geometry for all envs) or this
+        // band-sim's own table in global memory; no registers are held for it
+        const SrxView srx = A.st.per_env ? SrxView{A.st.srx + (active ? i : 0), A.st.ntab}
+                                         : SrxView{&srx_s[band][0], 1};
+        DevRing ring{A.st.ring + (active ? i : 0), nsim, A.st.hot + (active ? i : 0)};
         int dev = 0, dur = 0;
         if (active) {
             load_sim<false, MODE != MODE_R>(s, A.st, i, A.st.now[env]);
-            ring.ep0 = ld_chunk(A.st.hot, nsim, H_EP0, i);
-            ring.ep1 = ld_chunk(A.st.hot, nsim, H_EP1, i);
-            ring.have = true;
-            if (!A.st.per_env) {
-#pragma unroll
-                for (int k = 0; k < D * D; ++k) srx[k] = T.srx[band][(k / D) * kMaxDev + (k % D)];
-            } else {
-#pragma unroll
-                for (int k = 0; k < D * D; ++k) srx[k] = A.st.srx[(long long)((k / D) * kMaxDev + (k % D)) * A.st.ntab + i];
-            }
+            prefetch_l2(A.st.hot + (long long)H_EP0 * nsim + i);
+            prefetch_l2(A.st.hot + (long long)H_EP1 * nsim + i);
             if (TRACE) { s.trace = A.trace + (long long)i * A.traceCap * 8; s.traceCap = A.traceCap; s.ntrace = 0; }
             dev = A.device[i];
             dur = A.duration[i];
@@ -870,7 +856,7 @@ pendulum_step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__
     }
     const uint32_t nTx0 = s.nTx, nD0 = s.nDeliv[0], nD1 = s.nDeliv[1];
     begin_assignment(s, P, dev, dur);
-    DevRing ring{A.st.ring + i, nsim, A.st.hot + i, false, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    DevRing ring{A.st.ring + i, nsim, A.st.hot + i};
     PendulumPlant<DevVals, DevSrxOut> plant(Q, S, DevVals{A.st.pval + i, nsim}, DevSrxOut{A.st.srx + i, A.st.ntab});
     run_until_assign_plant<MODE_R>(s, P, P.band[0], srx, ring, NoMasks(), NoMemo(), plant);
     // InvertedPendulumInterpreter (inverted_pendulum.py:42-56): the angle is read from the plant
@@ -942,7 +928,7 @@ __global__ void reset_kernel(StatePtrs st, Params P, const long long *env_ids, l
     const long long i = e * st.nb + band;
     Sim<D, NS, NJ> s;
     load_sim(s, st, i, st.now[e]);
-    DevRing ring{st.ring + i, st.nsim, st.hot + i, false, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    DevRing ring{st.ring + i, st.nsim, st.hot + i};
     reset_sim(s, P.band[band], ring);
     store_sim(s, st, i, true);
     if (obs) obs[i] = (long long)s.latestDiff + kCounterBound;       // counter_traffic.py:144
