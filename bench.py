@@ -33,6 +33,8 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 ENVS_PER_GPU = 65536
 ROTATING_BATCHES = 16                  # independent 65,536-env batches stepped round-robin (inputs > L2)
+BURN_IN_STEPS = 128                    # steps of every env before the timed region (steady state, see own_arm)
+PRODUCTIVE_STEPS = 32                  # steps of every fresh env timed separately (productive regime)
 ALGO_BYTES_PER_ENV_STEP = 193          # SURVEY.md section 8d / DESIGN.md section 6
 STATS_EVERY_CHUNKS = 4                 # graph chunks (of 64 launches) between two NCCL reductions of the statistics vector
 METRIC = "env-steps/sec CounterTrafficEnv batch"
@@ -269,7 +271,8 @@ def cfg4_multiband(dev_t, steps=64):
 
 
 def cpu_baseline_run(target_seconds, threads=None):
-    """The oracle port on the host cores, on a bounded sample of the same workload."""
+    """The oracle port on the host cores, on a bounded sample of the same workload (steady state:
+    the first BURN_IN_STEPS steps of every env are simulated too and their time is subtracted)."""
     import numpy as np
     import gw_oracle as O
     from gymwipe_b200.scenario import default_scenario_dict
@@ -278,26 +281,26 @@ def cpu_baseline_run(target_seconds, threads=None):
     rs = np.random.RandomState(0)
     T = 256
 
-    def run(nenv):
-        dev = rs.randint(0, 2, size=(T, nenv)).astype(np.int32)
-        dur = rs.randint(0, 20, size=(T, nenv)).astype(np.int32)
+    def run(nenv, steps):
+        dev = rs.randint(0, 2, size=(steps, nenv)).astype(np.int32)
+        dur = rs.randint(0, 20, size=(steps, nenv)).astype(np.int32)
         t0 = time.perf_counter()
         O.run_batch(sc, dev, dur, threads=threads, want=("obs", "reward"))
         return time.perf_counter() - t0
-    run(threads * 4)                                    # warm-up (page-in, thread start)
+    run(threads * 4, T)                                 # warm-up (page-in, thread start)
     probe_n = threads * 16
-    dt = run(probe_n)
+    dt = run(probe_n, T)
     rate = probe_n * T / dt
-    nenv = int(max(probe_n, min(rate * target_seconds / T, 200000)))
+    nenv = int(max(probe_n, min(rate * target_seconds / (2 * (T + 2 * BURN_IN_STEPS)), 200000)))
     nenv = (nenv // threads) * threads
     best = None
     for _ in range(2):
-        dt = run(nenv)
-        v = nenv * T / dt
+        dt = run(nenv, BURN_IN_STEPS + T) - run(nenv, BURN_IN_STEPS)
+        v = nenv * T / max(dt, 1e-9)
         best = v if best is None else max(best, v)
     return {"value": best, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d envs x %d steps (fresh env + reset, same action distribution), oracle C restatement, "
-                      "%d host threads, best of 2" % (nenv, T, threads)}
+            "sample": "%d envs x %d steps after %d burn-in steps (steady state, same action distribution), oracle C "
+                      "restatement, %d host threads, best of 2" % (nenv, T, BURN_IN_STEPS, threads)}
 
 
 def reference_arm(args, rank):
@@ -311,15 +314,15 @@ def reference_arm(args, rank):
     threads = os.cpu_count() or 1
     K, W = args.steps, args.warmup
     # a "step" = one env.step of a bounded sample of the batch
-    sample = max(threads * 8, min(4096, (2_000_000 // max(K + W, 1)) // threads * threads))
+    sample = max(threads * 8, min(4096, (2_000_000 // max(K + 2 * (W + BURN_IN_STEPS), 1)) // threads * threads))
     rs = np.random.RandomState(0)
-    dev = rs.randint(0, 2, size=(W + K, sample)).astype(np.int32)
-    dur = rs.randint(0, 20, size=(W + K, sample)).astype(np.int32)
-    # the restatement keeps envs alive only inside run_batch: warm-up steps are re-simulated and
-    # their time subtracted (they are measured separately)
+    # the restatement keeps envs alive only inside run_batch: the burn-in and warm-up steps are
+    # re-simulated and their time subtracted (they are measured separately)
+    B0 = BURN_IN_STEPS
+    dev = rs.randint(0, 2, size=(B0 + W + K, sample)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(B0 + W + K, sample)).astype(np.int32)
     t0 = time.perf_counter()
-    if W > 0:
-        O.run_batch(sc, dev[:W], dur[:W], threads=threads, want=("obs",))
+    O.run_batch(sc, dev[:B0 + W], dur[:B0 + W], threads=threads, want=("obs",))
     t_w = time.perf_counter() - t0
     t0 = time.perf_counter()
     O.run_batch(sc, dev, dur, threads=threads, want=("obs", "reward"))
@@ -330,7 +333,8 @@ def reference_arm(args, rank):
             "steps": K, "warmup": W, "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(ENVS_PER_GPU * args.gpus, "host threads x%d" % threads,
-                                  "steps %d..%d from a fresh env (productive regime ~100 steps, then degenerate)" % (W, W + K)),
+                                  "steady state: steps %d..%d of every sampled env (the first %d steps are simulated and their "
+                                  "time subtracted)" % (BURN_IN_STEPS + W, BURN_IN_STEPS + W + K, BURN_IN_STEPS + W)),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d envs per step (bounded sample of the %d-env batch), %d steps, oracle C "
                                        "restatement of the reference's SimPy path" % (sample, ENVS_PER_GPU, K)},
@@ -369,36 +373,62 @@ def own_arm(args, rank, world, local_rank):
     # synthetic action tapes for every launch, resident in HBM before the timed region
     g = torch.Generator(device=dev_t).manual_seed(1234 + rank)
     total = W + K
-    rounds = (total + M - 1) // M                       # every batch is stepped `rounds` times at most
-    a_dev = torch.randint(0, 2, (total, n), generator=g, device=dev_t, dtype=torch.int32)
-    a_dur = torch.randint(0, 20, (total, n), generator=g, device=dev_t, dtype=torch.int32)
+    PROD = PRODUCTIVE_STEPS * M                         # launches of the productive-regime measurement
+    BURN = BURN_IN_STEPS * M                            # launches up to the steady state
+    rows = max(total, PROD)
+    a_dev = torch.randint(0, 2, (rows, n), generator=g, device=dev_t, dtype=torch.int32)
+    a_dur = torch.randint(0, 20, (rows, n), generator=g, device=dev_t, dtype=torch.int32)
     reducer = StatsReducer(dev_t) if world > 1 else None
-    stats_acc = torch.zeros(8, dtype=torch.float64, device=dev_t)
     stream = torch.cuda.Stream(device=dev_t)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    counter = [0]                                       # launches so far: launch j steps batch j % M
 
-    def launch(j):
-        envs[j % M].step({"device": a_dev[j], "duration": a_dur[j]})
+    def launch(row):
+        envs[counter[0] % M].step({"device": a_dev[row], "duration": a_dur[row]})
+        counter[0] += 1
 
-    # launches are captured into CUDA graphs of CHUNK launches each (pointers of the action rows are
-    # baked in, hence one graph per chunk); a replay enqueues the chunk without per-launch host work
     CHUNK = 64
+
+    def capture(first_row, count):
+        """CUDA graphs of <= CHUNK launches (the pointers of the action rows are baked in, hence one
+        graph per chunk); capturing does not execute.  Returns [(graph, launches)]."""
+        out, j, c0 = [], 0, counter[0]
+        while j < count:
+            cnt = min(CHUNK, count - j)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=stream):
+                for q in range(cnt):
+                    launch((first_row + j + q) % rows)
+            out.append((gr, cnt))
+            j += cnt
+        assert counter[0] == c0 + count
+        return out
+
     torch.cuda.synchronize(dev_t)
     with torch.cuda.stream(stream):
+        # (1) productive regime (the first ~100 steps after construction / reset(): queues hold packets
+        # that fit the windows): PRODUCTIVE_STEPS steps of every fresh env, timed for the record
+        gp = capture(0, PROD)
+        torch.cuda.synchronize(dev_t)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for gr, _ in gp:
+            gr.replay()
+        p1.record(stream)
+        torch.cuda.synchronize(dev_t)
+        prod_ms = p0.elapsed_time(p1) / PROD
+        del gp
+        # (2) burn-in to the steady state of the reference's workload: its training run
+        # (agents/dqn_counter_traffic.py: one reset(), dqn.fit(nb_steps=50000), `done` never true) leaves
+        # the productive regime after ~100 steps and spends > 99 % of its steps in the regime where the
+        # counters are too large for any window (announcements only)
+        for j in range(BURN - PROD):
+            launch(j % rows)
+        # (3) W warm-up launches, then EXACTLY K timed launches
         for j in range(W):
             launch(j)
         torch.cuda.synchronize(dev_t)
-        graphs = []
-        j = W
-        while j < total:
-            cnt = min(CHUNK, total - j)
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr, stream=stream):
-                for q in range(j, j + cnt):
-                    launch(q)
-            graphs.append((gr, j, cnt))
-            j += cnt
-        # (capturing does not execute: the envs are still at launch W)
+        graphs = capture(W, K)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev_t)
@@ -407,7 +437,7 @@ def own_arm(args, rank, world, local_rank):
             sampler.mark_begin()
         wall0 = time.perf_counter()
         marks[0].record(stream)
-        for c, (gr, j0, cnt) in enumerate(graphs):
+        for c, (gr, cnt) in enumerate(graphs):
             gr.replay()
             if reducer is not None and ((c + 1) % STATS_EVERY_CHUNKS == 0 or c + 1 == len(graphs)):
                 # K5 partial sums of the last chunks -> NCCL all-reduce on a side stream
@@ -429,8 +459,7 @@ def own_arm(args, rank, world, local_rank):
     if reducer is not None:
         reducer.drain()
     chunk_ms = np.array([marks[c].elapsed_time(marks[c + 1]) for c in range(len(graphs))])
-    chunk_cnt = np.array([cnt for _, _, cnt in graphs])
-    chunk_first = np.array([j0 for _, j0, _ in graphs])
+    chunk_cnt = np.array([cnt for _, cnt in graphs])
     elapsed_ms = float(marks[0].elapsed_time(marks[-1]))
     per_step_ms = chunk_ms / chunk_cnt                  # average launch duration per chunk
 
@@ -463,28 +492,6 @@ def own_arm(args, rank, world, local_rank):
     torch.cuda.synchronize(dev_t)
     flushed_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     del flush
-    # (c) the reference's degenerate regime (counters too large for any window: announcements only):
-    # every batch is advanced 128 more steps untimed, then 256 round-robin launches are timed
-    for r in range(128):
-        for b in range(M):
-            envs[b].step({"device": a_dev[(r * M + b) % total], "duration": a_dur[(r * M + b) % total]})
-    torch.cuda.synchronize(dev_t)
-    KD = 256
-    with torch.cuda.stream(stream):
-        gd = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gd, stream=stream):
-            for q in range(KD):
-                envs[q % M].step({"device": a_dev[q % total], "duration": a_dur[q % total]})
-        torch.cuda.synchronize(dev_t)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        gd.replay()
-        e1.record(stream)
-        torch.cuda.synchronize(dev_t)
-    degen_ms = e0.elapsed_time(e1) / KD
-    for e in envs:
-        e.check()
-    del gd
     for e in envs[1:]:
         e.close()
     del envs, graphs, gw
@@ -493,6 +500,13 @@ def own_arm(args, rank, world, local_rank):
     # e2e: host buffers through gw_step_host (pinned), copies inside the timed region
     env2 = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, env_id_offset=rank * n, strict=False)
     env2.reset()
+
+    def burn_in(env):
+        # to the steady state, through the device-resident step (untimed)
+        for t in range(BURN_IN_STEPS):
+            env.step({"device": a_dev[t % rows], "duration": a_dur[t % rows]})
+        torch.cuda.synchronize(dev_t)
+    burn_in(env2)
     KE = min(K, 256)
     h_dev = a_dev[:W + KE].cpu().pin_memory()
     h_dur = a_dur[:W + KE].cpu().pin_memory()
@@ -514,6 +528,7 @@ def own_arm(args, rank, world, local_rank):
     h_res = torch.empty(9 * n, dtype=torch.uint8).pin_memory()
     env3 = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, env_id_offset=rank * n, strict=False)
     env3.reset()
+    burn_in(env3)
     for t in range(W):
         env3.step_host_packed(h_act[t], h_res)
     if world > 1:
@@ -523,15 +538,35 @@ def own_arm(args, rank, world, local_rank):
     for k in range(KE):
         env3.step_host_packed(h_act[W + k], h_res)
     torch.cuda.synchronize(dev_t)
-    e2e_s = time.perf_counter() - t0
+    e2e_packed_s = time.perf_counter() - t0
     checksum = float(env3.unpack_results(h_res)[1].double().sum())
     assert torch.equal(env3.unpack_results(h_res)[0].to(torch.int64), h_obs)   # both paths agree on the last step
+    # compact variant (gw_step_host_compact): uint8 actions [n][2] in (2 B/env), one packed word out (4 B/env)
+    h_act8 = torch.stack([h_dev, h_dur], dim=2).to(torch.uint8).contiguous().pin_memory()     # [steps, n, 2]
+    h_res32 = torch.empty(n, dtype=torch.int32).pin_memory()
+    env4 = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, env_id_offset=rank * n, strict=False)
+    env4.reset()
+    burn_in(env4)
+    act_rows = [h_act8[t] for t in range(W + KE)]      # views of the pinned action tape, one per step
+    for t in range(W):
+        env4.step_host_compact(act_rows[t], h_res32)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev_t)
+    t0 = time.perf_counter()
+    for k in range(KE):
+        env4.step_host_compact(act_rows[W + k], h_res32)
+    torch.cuda.synchronize(dev_t)
+    e2e_s = time.perf_counter() - t0
+    env4.check()
+    assert torch.equal(env4.unpack_compact(h_res32)[0], h_obs)                  # all three paths agree on the last step
+    del env4
 
     # max over ranks
     if world > 1:
-        v = torch.tensor([elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, flushed_ms, degen_ms], dtype=torch.float64, device=dev_t)
+        v = torch.tensor([elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, flushed_ms, prod_ms, e2e_packed_s], dtype=torch.float64, device=dev_t)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, flushed_ms, degen_ms = [float(x) for x in v]
+        elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, flushed_ms, prod_ms, e2e_packed_s = [float(x) for x in v]
     if rank != 0:
         return 0
 
@@ -541,7 +576,6 @@ def own_arm(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     kernel_ms = elapsed_ms / K                          # average launch duration over the timed region
     achieved = ALGO_BYTES_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e9
-    steps_per_env = (W + K + M - 1) // M
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -549,12 +583,14 @@ def own_arm(args, rank, world, local_rank):
         "config": config_dict(total_envs, "dp%d (independent env shards, no data-path collective; NCCL all-reduce of the 64-byte "
                               "statistics vector every %d launches on a side stream)" % (world, STATS_EVERY_CHUNKS * 64) if world > 1
                               else "single GPU",
-                              "fresh envs + reset(); every env advances %d steps during warm-up + timed region: the "
-                              "productive regime (packets delivered; the first ~100 steps of an env)" % steps_per_env),
-        "regimes": {"timed_region_env_steps_per_s": value,
-                    "degenerate_env_steps_per_s": total_envs / (degen_ms * 1e-3),
-                    "degenerate_note": "same round-robin protocol, 256 launches after every env advanced 128 more steps "
-                                       "(counters too large for any window: announcements only)",
+                              "steady state of the reference's workload: fresh envs + reset() + %d untimed steps per env, "
+                              "then W warm-up and K timed launches (the reference's training run -- one reset(), 50,000 steps, "
+                              "`done` never true -- leaves the productive regime after ~100 steps; SURVEY.md section 8d cfg 2: "
+                              "'throughput: steady state; report both regimes separately')" % BURN_IN_STEPS),
+        "regimes": {"steady_state_env_steps_per_s": value,
+                    "productive_env_steps_per_s": total_envs / (prod_ms * 1e-3),
+                    "productive_note": "same round-robin protocol, the first %d steps of every fresh env (%d launches): queues "
+                                       "hold packets that fit the windows, 1-10 data transmissions per step" % (PRODUCTIVE_STEPS, PRODUCTIVE_STEPS * M),
                     "l2_warm_one_batch_env_steps_per_s": total_envs / (warm_ms * 1e-3),
                     "l2_warm_note": "ONE batch stepped 64x back to back from a CUDA graph (its state stays in L2)",
                     "round1_protocol_env_steps_per_s": total_envs / (flushed_ms * 1e-3),
@@ -567,10 +603,15 @@ def own_arm(args, rank, world, local_rank):
                      "avg_launch_ms": kernel_ms,
                      "note": "mode-R state is ~190 B/env-step: the fused step kernel is latency / fp64-ALU bound, "
                              "not HBM bound (SURVEY.md 8d); the fraction is reported as required"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 9 * n,
-                "steps": KE, "api": "CounterTrafficEnv.step_host_packed -> gw_step_host_packed (pinned host buffers: "
-                                    "int32 actions [2][n] in, int32 obs | float32 reward | uint8 done out)",
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n,
+                "steps": KE, "api": "CounterTrafficEnv.step_host_compact -> gw_step_host_compact (pinned host buffers: uint8 "
+                                    "actions [n][2] in, one packed uint32 {obs:17, reward+16:5, done:1} per env out; the kernel "
+                                    "reads / writes the pinned buffers in place over the host link -- the h2d / d2h bytes are moved "
+                                    "by the kernel's own loads and stores, inside the timed region); steady-state envs (burn-in as above)",
                 "reward_checksum": checksum,
+                "packed_api": {"value": total_envs * KE / e2e_packed_s, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 9 * n,
+                               "api": "CounterTrafficEnv.step_host_packed -> gw_step_host_packed (int32 actions [2][n] in, "
+                                      "int32 obs | float32 reward | uint8 done out)"},
                 "wide_api": {"value": total_envs * KE / e2e_wide_s, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 17 * n,
                              "api": "CounterTrafficEnv.step_host -> gw_step_host (int64 obs, float64 reward, uint8 done)"}},
         "gpu_launches": K + (M * ((len(chunk_cnt) + STATS_EVERY_CHUNKS - 1) // STATS_EVERY_CHUNKS) if world > 1 else 0),   # step kernels (+ statistics copies when sharded)

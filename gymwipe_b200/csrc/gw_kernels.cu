@@ -593,6 +593,11 @@ struct StepArgs {
     // compact outputs (gw_step_host_packed): used instead of obs / reward when non-NULL
     int *obs32;
     float *reward32;
+    // gw_step_host_compact: uint8 actions [n][2] in, one packed uint32 per sim out
+    const unsigned char *act8;
+    unsigned *res32;
+    // band-sims [sim_begin, sim_end) are stepped by this launch (a multiple of the block size apart)
+    long long sim_begin, sim_end;
     // event trace (gw_step_traced)
     double *trace;
     int *traceCount;
@@ -642,9 +647,9 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
     // grid-stride over warps' worth of band-sims; every lane of a warp stays in the loop
     // so that the warp-level operations below are executed by all 32 lanes
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long base = (long long)blockIdx.x * blockDim.x; base < nsim; base += stride) {
+    for (long long base = A.sim_begin + (long long)blockIdx.x * blockDim.x; base < A.sim_end; base += stride) {
         const long long i = base + threadIdx.x;
-        const bool active = i < nsim;
+        const bool active = i < A.sim_end;
         // nb is 1, 2 or 4: shifts instead of 64-bit divisions
         const int nbShift = nb == 4 ? 2 : (nb == 2 ? 1 : 0);
         const long long env = active ? (i >> nbShift) : 0;
@@ -663,8 +668,13 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
             prefetch_l2(A.st.hot + (long long)H_EP0 * nsim + i);
             prefetch_l2(A.st.hot + (long long)H_EP1 * nsim + i);
             if (TRACE) { s.trace = A.trace + (long long)i * A.traceCap * 8; s.traceCap = A.traceCap; s.ntrace = 0; }
-            dev = A.device[i];
-            dur = A.duration[i];
+            if (A.act8) {
+                const uchar2 a2 = reinterpret_cast<const uchar2 *>(A.act8)[i];
+                dev = a2.x; dur = a2.y;
+            } else {
+                dev = A.device[i];
+                dur = A.duration[i];
+            }
             // assert self.action_space.contains(action)  (counter_traffic.py:147)
             if (dev < 0 || dev >= NS || dur < 0 || dur >= P.maxDuration) {
                 if (atomicCAS(A.errflag, 0, GW_E_ACTION) == 0) A.errflag[1] = (int)i;
@@ -768,9 +778,13 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         if (active) {
             long long o; double rw; unsigned char dn;
             feedback(s, o, rw, dn);
-            if (A.obs32) { A.obs32[i] = (int)o; A.reward32[i] = (float)rw; }
-            else { A.obs[i] = o; A.reward[i] = rw; }
-            A.done[i] = dn;
+            if (A.res32) {
+                A.res32[i] = ((unsigned)o & 0x1FFFFu) | ((unsigned)((int)rw + 16) << 17) | ((unsigned)(dn != 0) << 22);
+            } else {
+                if (A.obs32) { A.obs32[i] = (int)o; A.reward32[i] = (float)rw; }
+                else { A.obs[i] = o; A.reward[i] = rw; }
+                A.done[i] = dn;
+            }
             if (band == 0) A.st.now[env] = s.now;
             if (s.fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = s.fault; } }
             store_sim<false, MODE != MODE_R>(s, A.st, i, false);
@@ -1482,7 +1496,9 @@ int gw_reset(gw_handle *h, const int64_t *env_ids, int64_t n, int64_t *obs, void
 
 static int launch_step(gw_handle *h, const int32_t *device, const int32_t *duration, int64_t *obs, double *reward,
                        uint8_t *done, cudaStream_t s, int *obs32 = nullptr, float *reward32 = nullptr,
-                       double *trace = nullptr, int *trace_count = nullptr, int trace_cap = 0)
+                       double *trace = nullptr, int *trace_count = nullptr, int trace_cap = 0,
+                       const unsigned char *act8 = nullptr, unsigned *res32 = nullptr,
+                       long long sim_begin = 0, long long sim_end = -1)
 {
     if (h->cfg.mode == GW_MODE_MASK_FED && !h->masks) return fail(GW_E_INVALID, "mode MASK_FED: call gw_set_masks first");
     StepArgs A;
@@ -1491,6 +1507,8 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     A.obs = (long long *)obs; A.reward = reward; A.done = done;
     A.stats = h->stats; A.errflag = h->errflag;
     A.obs32 = obs32; A.reward32 = reward32;
+    A.act8 = act8; A.res32 = res32;
+    A.sim_begin = sim_begin; A.sim_end = sim_end < 0 ? h->st.nsim : sim_end;
     A.trace = trace; A.traceCount = trace_count; A.traceCap = trace_cap;
     A.masks.mode = h->cfg.mode; A.masks.seed = h->cfg.seed; A.masks.env_offset = h->cfg.env_id_offset;
     A.masks.words = h->masks; A.masks.slots = h->mask_slots > 0 ? h->mask_slots : 1; A.masks.words_per_row = h->mask_words;
@@ -1518,7 +1536,7 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
         return GW_OK;
     }
     // one wave: 128-thread blocks, a multiple of the SM count when the batch is large
-    int blocks = grid_for(nsim, STEP_BLOCK);
+    int blocks = grid_for(A.sim_end - A.sim_begin, STEP_BLOCK);
     const int cap = 148 * GW_STEP_MIN_BLOCKS * 4;
     if (blocks > cap) blocks = cap;
 #define LAUNCH_STEP(KERNEL, DD, SS, JJ)                                                              \
@@ -1605,6 +1623,47 @@ int gw_step_host_packed(gw_handle *h, const int32_t *actions, void *results, voi
     const int rc = launch_step(h, h->d_dev, h->d_dur, nullptr, nullptr, done8, s, obs32, rew32);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(results, obs32, n * 9, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return GW_OK;
+}
+
+// device-visible alias of a host pointer if it is pinned (cudaHostAlloc / cudaHostRegister) memory
+static void *mapped_alias(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+int gw_step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *results, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    if (!actions || !results) return fail(GW_E_INVALID, "NULL buffer");
+    if (h->cfg.plant) return fail(GW_E_INVALID, "gw_step_host_compact is not available for plant envs");
+    if (h->cfg.max_assign_duration > 256) return fail(GW_E_INVALID, "max_assign_duration > 256 does not fit uint8 actions");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long n = h->st.nsim;
+    // Pinned host buffers are mapped into the device's address space (UVA): the step kernel reads the
+    // actions and writes the result words over the host link itself -- 2 + 4 bytes per sim in full
+    // 64 / 128-byte warp transactions -- and no copy is enqueued at all.  Pageable buffers are staged.
+    const unsigned char *m_act = (const unsigned char *)mapped_alias(actions);
+    unsigned *m_res = (unsigned *)mapped_alias(results);
+    if (m_act && m_res) {
+        const int rc = launch_step(h, nullptr, nullptr, nullptr, nullptr, nullptr, s, nullptr, nullptr, nullptr, nullptr, 0,
+                                   m_act, m_res);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return GW_OK;
+    }
+    // staging: uint8 actions [n][2] in the action staging area, uint32 results [n] in the obs area
+    unsigned char *d_act = (unsigned char *)h->d_dev;
+    unsigned *d_res = (unsigned *)h->d_obs;
+    CUDA_TRY(cudaMemcpyAsync(d_act, actions, (size_t)(2 * n), cudaMemcpyHostToDevice, s));
+    const int rc = launch_step(h, nullptr, nullptr, nullptr, nullptr, nullptr, s, nullptr, nullptr, nullptr, nullptr, 0,
+                               d_act, d_res);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(results, d_res, (size_t)(4 * n), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return GW_OK;
 }

@@ -442,6 +442,28 @@ class CounterTrafficEnv(BaseEnv):
         with torch.cuda.device(self.device):
             N.check(self._lib.gw_step_host_packed(self._handle, ptr(actions), ptr(results), self._stream()))
 
+    def step_host_compact(self, actions, results):
+        """
+        Compact end-to-end step (``gw_step_host_compact``): ``actions`` is a pinned uint8 tensor / array
+        ``[n_sims, 2]`` (device, duration), ``results`` a pinned int32 / uint32 buffer of ``n_sims`` words
+        that receives ``obs | (reward + 16) << 17 | done << 22``.  2 bytes in, 4 bytes out per sim; pinned
+        buffers are read / written in place by the kernel (no copies), pageable ones are staged.  Use
+        :meth:`unpack_compact` for typed tensors.
+        """
+        a = actions.data_ptr() if torch.is_tensor(actions) else actions.ctypes.data
+        r = results.data_ptr() if torch.is_tensor(results) else results.ctypes.data
+        # (the native call selects the handle's device itself)
+        rc = self._lib.gw_step_host_compact(self._handle, a, r, torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            N.check(rc)
+
+    @staticmethod
+    def unpack_compact(results):
+        """``(obs int64, reward float64, done bool)`` from the packed words of :meth:`step_host_compact`."""
+        r = results if torch.is_tensor(results) else torch.from_numpy(results)
+        w = r.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+        return w & 0x1FFFF, (((w >> 17) & 31) - 16).to(torch.float64), ((w >> 22) & 1).bool()
+
     def unpack_results(self, results):
         """Typed views (obs int32, reward float32, done uint8) of a packed result buffer."""
         n = self.num_envs * self.n_bands

@@ -175,6 +175,23 @@ int gw_step_host(gw_handle *h, const int32_t *device, const int32_t *duration,
  * Synchronises the stream. */
 int gw_step_host_packed(gw_handle *h, const int32_t *actions, void *results, void *stream);
 
+/* Compact host-buffer variant (the transfers, not the kernel, bound the end-to-end rate):
+ * `actions` = uint8 [2][n_sims] (row 0 action["device"], row 1 action["duration"], both < 256 by the
+ * action space: Discrete(2) x Discrete(MAX_ASSIGN_DURATION), envs/core.py:39-42) and `results` =
+ * uint32 [n_sims], one word per sim:
+ *     bits  0..16  observation (Discrete(131072), counter_traffic.py:120)
+ *     bits 17..21  reward + 16  (rewards are integers in [-10, 10], counter_traffic.py:96-107)
+ *     bit  22      done
+ * (GW_COMPACT_OBS / GW_COMPACT_REWARD / GW_COMPACT_DONE decode it.)  2 bytes in, 4 bytes out per sim
+ * and step.  If both buffers are PINNED host memory (cudaHostAlloc / cudaHostRegister, e.g. torch's
+ * pin_memory()) the step kernel reads and writes them in place over the host link and no copy is
+ * enqueued; pageable buffers are staged through two copies.  Synchronises `stream`.  Not available
+ * for plant envs (their observations are not integers of this range). */
+int gw_step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *results, void *stream);
+#define GW_COMPACT_OBS(w)    ((int32_t)((w) & 0x1FFFFu))
+#define GW_COMPACT_REWARD(w) ((int32_t)(((w) >> 17) & 31u) - 16)
+#define GW_COMPACT_DONE(w)   ((int32_t)(((w) >> 22) & 1u))
+
 /* Synchronises and reports the error flag the kernels raised since the last call:
  * 0, GW_E_ACTION or GW_E_SIMFAULT (with the first faulting env in the message). */
 int gw_check(gw_handle *h, void *stream);

@@ -349,6 +349,40 @@ def test_step_host_packed_end_to_end():
         assert not done.numpy().any()
 
 
+@pytest.mark.parametrize("n,pinned", [(37, True), (1024, False), (3000, True)])
+def test_step_host_compact_end_to_end(n, pinned):
+    """gw_step_host_compact: uint8 actions in, one packed word per sim out; pinned buffers are read and
+    written in place by the kernel, pageable ones are staged."""
+    from gymwipe_b200.scenario import default_scenario_dict
+    sc = default_scenario_dict()
+    rs = np.random.RandomState(33)
+    T = 60
+    dev, dur = random_tapes(rs, T, n, 1)
+    ref = O.run_batch(sc, dev, dur)
+    env = make_env(sc, n, strict=False)
+    env.reset()
+    act = torch.empty((n, 2), dtype=torch.uint8)
+    res = torch.empty(n, dtype=torch.int32)
+    if pinned:
+        act, res = act.pin_memory(), res.pin_memory()
+    for t in range(T):
+        act[:, 0] = torch.from_numpy(dev[t, :, 0].astype(np.uint8))
+        act[:, 1] = torch.from_numpy(dur[t, :, 0].astype(np.uint8))
+        res.fill_(-1)
+        env.step_host_compact(act, res)
+        obs, rew, done = env.unpack_compact(res)
+        assert (obs.numpy() == ref["obs"][t, :, 0]).all()
+        assert (rew.numpy() == ref["reward"][t, :, 0]).all()
+        assert (done.numpy() == ref["done"][t, :, 0].astype(bool)).all()
+    env.check()
+    assert (env.read_state(0).cpu().numpy() == ref["now"][-1]).all()
+    # an action outside the action space is flagged like in gw_step
+    act[0, 0] = 7
+    env.step_host_compact(act, res)
+    with pytest.raises(ValueError):
+        env.check()
+
+
 def test_stats_epilogue():
     from gymwipe_b200.scenario import default_scenario_dict
     sc = default_scenario_dict()
