@@ -462,6 +462,44 @@ GW_HD void silent_ticks(Sim<D, NS, NJ, ST> &s, int mult, double interval, double
     s.sTick[K] = s.seq - 1u;
 }
 
+// Both senders' silent ticks up to (tEnd, qEnd): silent_ticks<0> followed by silent_ticks<1>.  When the
+// two senders tick in lockstep (same pending tick time, same interval -- the reference's senders both
+// start at t = 0 with COUNTER_INTERVAL) the second pass repeats the first one addition for addition, so
+// ONE loop serves both; the creation numbers are assigned as the two passes would (sender 0's batch
+// first).  A pending tick exactly at tEnd takes the general path.
+template <int D, int NS, int NJ, class ST>
+GW_HD void silent_ticks_both(Sim<D, NS, NJ, ST> &s, const BandParams &B, double tEnd, uint32_t qEnd, bool haveEnd,
+                             double tLimit)
+{
+    static_assert(NS == 2, "the tick logic is written for two senders per band");
+    double t = s.tTick[0];
+    const double interval = B.interval[0];
+    if (t == s.tTick[1] && interval == B.interval[1] && !(haveEnd && t == tEnd)) {
+        if (!(t < tLimit)) return;
+        if (haveEnd && !(t < tEnd)) return;
+        const double stop = haveEnd ? (tEnd < tLimit ? tEnd : tLimit) : tLimit;
+        uint32_t c = 0;
+        do {
+            t = t + interval;
+            ++c;
+        } while (t < stop);
+        s.ties += (haveEnd && t == tEnd) ? 2u : 0u;
+        s.tTick[0] = t; s.tTick[1] = t;
+        s.ticks[0] += c; s.ticks[1] += c;
+        const uint32_t n0 = (uint32_t)s.qn[0] + c * (uint32_t)B.mult[0];
+        const uint32_t n1 = (uint32_t)s.qn[1] + c * (uint32_t)B.mult[1];
+        s.qn[0] = n0 > (uint32_t)kQueueCap ? kQueueCap : (int)n0;
+        s.qn[1] = n1 > (uint32_t)kQueueCap ? kQueueCap : (int)n1;
+        s.seq += c;
+        s.sTick[0] = s.seq - 1u;
+        s.seq += c;
+        s.sTick[1] = s.seq - 1u;
+        return;
+    }
+    silent_ticks<0>(s, B.mult[0], B.interval[0], tEnd, qEnd, haveEnd, tLimit);
+    silent_ticks<1>(s, B.mult[1], B.interval[1], tEnd, qEnd, haveEnd, tLimit);
+}
+
 template <bool ALL_TICKS = false, int D, int NS, int NJ, class ST>
 GW_HD Event next_event(Sim<D, NS, NJ, ST> &s, const BandParams &B, double tLimit)
 {
@@ -478,8 +516,12 @@ GW_HD Event next_event(Sim<D, NS, NJ, ST> &s, const BandParams &B, double tLimit
         ev.kind = EV_TICK; ev.idx = 1; ev.t = s.tTick[1]; ev.seq = s.sTick[1];
     }
     const bool have = ev.kind != EV_NONE;
-    if (!wake0) silent_ticks<0>(s, B.mult[0], B.interval[0], ev.t, ev.seq, have, tLimit);
-    if (!wake1) silent_ticks<1>(s, B.mult[1], B.interval[1], ev.t, ev.seq, have, tLimit);
+    if (!wake0 && !wake1) {
+        silent_ticks_both(s, B, ev.t, ev.seq, have, tLimit);
+    } else {
+        if (!wake0) silent_ticks<0>(s, B.mult[0], B.interval[0], ev.t, ev.seq, have, tLimit);
+        if (!wake1) silent_ticks<1>(s, B.mult[1], B.interval[1], ev.t, ev.seq, have, tLimit);
+    }
     if (!have) {
         // nothing but silent ticks is pending: report the earliest one (its time is >= tLimit)
         const bool one = before(s.tTick[1], s.sTick[1], s.tTick[0], s.sTick[0]);
@@ -1086,7 +1128,8 @@ GW_HD void process_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParam
 //
 // quiet_tail(): after the announcement (and the data packets) nothing is on air, no MAC waits for a
 // packet or a transmission and only window time-outs and the RRM guard time-out are pending: they
-// cannot create events, so they are applied in (time, seq) order without the selection machinery.
+// cannot create events (the time-outs only clear flags), so they are applied without the selection
+// machinery and the silent ticks up to the guard time-out in one batch.
 // ---------------------------------------------------------------------------
 
 template <int D, int NS, int NJ, class ST, class SRX, class Ring, class Memo>
@@ -1191,8 +1234,7 @@ GW_HD bool isolated_tx(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams 
         }
 
         // ---- completion (simple_stack.py:146-157, 253-267)
-        silent_ticks<0>(s, B.mult[0], B.interval[0], tC, qC, true, tLimit);
-        silent_ticks<1>(s, B.mult[1], B.interval[1], tC, qC, true, tLimit);
+        silent_ticks_both(s, B, tC, qC, true, tLimit);
         s.now = tC;
         set_at(s.sphase, d, (int)S_IDLE);
         int window = -1;
@@ -1285,24 +1327,18 @@ GW_HD bool quiet_tail(Sim<D, NS, NJ, ST> &s, const BandParams &B)
     for (int j = 0; j < NJ; ++j) ok &= s.tJam[j] > s.tRrm;
     if (!ok) return false;
     GW_STAT_MACRO(1);
-    // window time-outs that precede the guard time-out, in (time, seq) order (simple_stack.py:406-420)
-    for (;;) {
-        int k = -1;
-        if (s.wPend[0] && before(s.stopW[0], s.sW[0], s.tRrm, s.sRrm)) k = 0;
-        if (s.wPend[1] && before(s.stopW[1], s.sW[1], s.tRrm, s.sRrm)
-            && (k < 0 || before(s.stopW[1], s.sW[1], s.stopW[0], s.sW[0]))) k = 1;
-        if (k < 0) break;
-        const double tw = get_at(s.stopW, k);
-        const uint32_t qw = get_at(s.sW, k);
-        silent_ticks<0>(s, B.mult[0], B.interval[0], tw, qw, true, INFINITY);
-        silent_ticks<1>(s, B.mult[1], B.interval[1], tw, qw, true, INFINITY);
-        s.now = tw;
-        set_at(s.wPend, k, 0);
-        set_at(s.mac, k, (int)MAC_NONE);
+    // window time-outs that precede the guard time-out (simple_stack.py:406-420): they only clear
+    // flags of MACs that wait for nothing else, so neither their order nor their position among the
+    // silent ticks matters; the ticks up to the guard time-out are applied in one batch
+    GW_UNROLL
+    for (int k = 0; k < NS; ++k) {
+        if (s.wPend[k] && before(s.stopW[k], s.sW[k], s.tRrm, s.sRrm)) {
+            s.wPend[k] = 0;
+            s.mac[k] = MAC_NONE;
+        }
     }
     // assignMessage.setProcessed() (simple_stack.py:561)
-    silent_ticks<0>(s, B.mult[0], B.interval[0], s.tRrm, s.sRrm, true, INFINITY);
-    silent_ticks<1>(s, B.mult[1], B.interval[1], s.tRrm, s.sRrm, true, INFINITY);
+    silent_ticks_both(s, B, s.tRrm, s.sRrm, true, INFINITY);
     s.now = s.tRrm;
     s.rrmPend = 0;
     s.assignDone = 1;
