@@ -355,6 +355,7 @@ def own_arm(args, rank, world, local_rank):
     from gymwipe_b200.distributed import StatsReducer
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.set_num_threads(1)                            # no idle worker threads spinning next to the stepping thread
     torch.cuda.set_device(local_rank)
     dev_t = torch.device("cuda", local_rank)
     K, W = args.steps, args.warmup

@@ -82,7 +82,7 @@ struct Params {
     double tenLog10BitRate;             // 10*log10(bitRate), host libm
     double qDen;                        // 1.135 * sqrt(2*pi), physical.py:44,58
     double bitsFactor;                  // float(2 - codeRate) = 1.25, physical.py:259-263
-    int noMacro;                        // 1: every timed event goes through the generic transition function
+    int noMacro;                        // macro events: 0 = where they pay (bands without interferers), 1 = never, -1 = always
     double berMult;                     // 1 / maxBer if that is a power of two and bit counts are integers, else 0
     double airtime[32];                 // (k * 8) / dataRate for k < 32 bytes (same IEEE division, done once)
     double rateInv;                     // fl(1 / dataRate) if the multiply-and-correct quotient below was verified, else 0
@@ -1132,6 +1132,22 @@ GW_HD void process_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParam
 // machinery and the silent ticks up to the guard time-out in one batch.
 // ---------------------------------------------------------------------------
 
+// Macro events are exact wherever they apply, but a warp whose lanes split between a macro event and
+// the generic transition function executes both.  With PHY-only interferers on the band a large share
+// of the transmissions is not isolated, and the split costs more than the macro events save
+// (configs[3]: 2.9 ms per step without, 5.8 ms with); they are therefore used on bands without
+// interferers; the host build can force them (P.noMacro = -1: the CPU tests exercise them with
+// interferers too).
+template <int MODE, int NJ>
+GW_HD bool macros_enabled(const Params &P)
+{
+#ifdef __CUDA_ARCH__
+    return MODE == MODE_R && NJ == 0 && P.noMacro == 0;        // kernels with interferers carry no macro code
+#else
+    return MODE == MODE_R && (P.noMacro < 0 || (P.noMacro == 0 && NJ == 0));
+#endif
+}
+
 template <int D, int NS, int NJ, class ST, class SRX, class Ring, class Memo>
 GW_HD bool isolated_tx(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const Event &ev,
                        const SRX &srx, const Ring &ring, const Memo &memo, double tLimit)
@@ -1361,7 +1377,7 @@ template <int MODE, int D, int NS, int NJ, class ST, class SRX, class Ring, clas
 GW_HD void run_until_assign(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B,
                             const SRX &srx, const Ring &ring, const Masks &masks, const Memo &memo = Memo())
 {
-    const bool macros = MODE == MODE_R && !P.noMacro;
+    const bool macros = macros_enabled<MODE, NJ>(P);
     while (!s.assignDone && !s.fault) {
         if (macros && quiet_tail(s, B)) break;
         const Event ev = next_event(s, B, INFINITY);
@@ -1379,7 +1395,7 @@ GW_HD void run_until_time(Sim<D, NS, NJ, ST> &s, const Params &P, const BandPara
     while (!s.fault) {
         const Event ev = next_event(s, B, T);
         if (!(ev.t < T)) break;
-        if (MODE == MODE_R && !P.noMacro && ev.kind == EV_PHY && isolated_tx(s, P, B, ev, srx, ring, memo, T)) continue;
+        if (macros_enabled<MODE, NJ>(P) && ev.kind == EV_PHY && isolated_tx(s, P, B, ev, srx, ring, memo, T)) continue;
         process_event<MODE>(s, P, B, ev, srx, ring, masks, memo);
     }
     s.now = T;

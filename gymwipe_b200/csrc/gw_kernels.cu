@@ -28,6 +28,7 @@
 #include <new>
 
 #include "../../include/gymwipe_b200.h"
+
 #include "gw_core.cuh"
 #include "gw_pendulum.cuh"
 

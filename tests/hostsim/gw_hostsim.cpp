@@ -51,7 +51,7 @@ struct HsScenario {
     HsBand band[kMaxBands];
 };
 
-int g_no_macro = 0;     // hs_set_no_macro(1): every event through the generic transition function
+int g_no_macro = -1;    // hs_set_no_macro: -1 macro events wherever they apply (default here), 1 never, 0 as the kernels do
 
 void fill_params(const HsScenario &sc, Params &P)
 {

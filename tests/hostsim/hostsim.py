@@ -102,7 +102,7 @@ def scenario_from_dict(d, mode=0, seed=0):
 
 def run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, mode=0, seed=0, env_offset=0, macros=True):
     L = lib()
-    L.hs_set_no_macro(0 if macros else 1)
+    L.hs_set_no_macro(-1 if macros else 1)
     sc = scenario_from_dict(scenario, mode, seed) if isinstance(scenario, dict) else scenario
     nb = sc.nbands
     dev_tape = np.ascontiguousarray(dev_tape, dtype=np.int32)
