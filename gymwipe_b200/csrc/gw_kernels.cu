@@ -626,6 +626,21 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0;
 
+    // The first row of this thread is requested into L2 right away: the block-level set-up below (and,
+    // under programmatic dependent launch, the tail of the previous kernel) then overlaps the DRAM
+    // latency of the state loads.  L2 is the point of coherence, so prefetching before the grid
+    // dependency is resolved is safe.
+    {
+        const long long i0 = A.sim_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i0 < A.sim_end) {
+#pragma unroll
+            for (int c = 0; c < HOT_CHUNKS; ++c)
+                if (c != H_EPC && (NJ > 0 || c != H_JAM)) prefetch_l2(A.st.hot + (long long)c * nsim + i0);
+            if (nb == 1) prefetch_l2(A.st.now + i0);
+            if (A.act8) prefetch_l2(A.act8 + 2 * i0);
+            else { prefetch_l2(A.device + i0); prefetch_l2(A.duration + i0); }
+        }
+    }
     // first level of the BER memo: copied into shared memory while the state loads are in flight.
     // (Read before the grid dependency is resolved: entries are checksum-validated, a stale or
     // torn one is a miss.)
@@ -666,8 +681,10 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         int dev = 0, dur = 0;
         if (active) {
             load_sim<false, MODE != MODE_R>(s, A.st, i, A.st.now[env]);
-            prefetch_l2(A.st.hot + (long long)H_EP0 * nsim + i);
-            prefetch_l2(A.st.hot + (long long)H_EP1 * nsim + i);
+            if (base != A.sim_begin + (long long)blockIdx.x * blockDim.x) {     // later rounds of the grid-stride loop
+                prefetch_l2(A.st.hot + (long long)H_EP0 * nsim + i);
+                prefetch_l2(A.st.hot + (long long)H_EP1 * nsim + i);
+            }
             if (TRACE) { s.trace = A.trace + (long long)i * A.traceCap * 8; s.traceCap = A.traceCap; s.ntrace = 0; }
             if (A.act8) {
                 const uchar2 a2 = reinterpret_cast<const uchar2 *>(A.act8)[i];
