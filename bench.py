@@ -567,13 +567,48 @@ def own_arm(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t0
     env4.check()
     assert torch.equal(env4.unpack_compact(h_res32)[0], h_obs)                  # all three paths agree on the last step
-    del env4
+    # pipelined variant: PIPE env batches in flight through gw_step_host_compact_async -- the host waits for
+    # a batch's previous results (event), reads them, then submits that batch's next actions; kernels of
+    # different batches queue behind each other, so launch and synchronisation latencies overlap with compute
+    PIPE = 4
+    penvs = [env4] + [gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t,
+                                        env_id_offset=(rank * PIPE + b) * n, strict=False) for b in range(1, PIPE)]
+    for e in penvs[1:]:
+        e.reset()
+        burn_in(e)
+    pres = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(PIPE)]
+    pres_np = [r.numpy() for r in pres]
+    pev = [torch.cuda.Event() for _ in range(PIPE)]
+    cur = torch.cuda.current_stream(dev_t)
+    nrows = len(act_rows)
+
+    def pipelined(count):
+        acc = 0
+        for k in range(count):
+            b = k % PIPE
+            if k >= PIPE:
+                pev[b].synchronize()
+                acc += int(pres_np[b][k % n])           # the step's results are on the host
+            penvs[b].step_host_compact_async(act_rows[k % nrows], pres[b])
+            pev[b].record(cur)
+        torch.cuda.synchronize(dev_t)
+        return acc
+    pipelined(4 * PIPE)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev_t)
+    t0 = time.perf_counter()
+    pipe_checksum = pipelined(KE * PIPE)
+    e2e_pipe_s = time.perf_counter() - t0
+    for e in penvs:
+        e.check()
+    del env4, penvs
 
     # max over ranks
     if world > 1:
-        v = torch.tensor([elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, flushed_ms, prod_ms, e2e_packed_s], dtype=torch.float64, device=dev_t)
+        v = torch.tensor([elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, flushed_ms, prod_ms, e2e_packed_s, e2e_pipe_s], dtype=torch.float64, device=dev_t)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, flushed_ms, prod_ms, e2e_packed_s = [float(x) for x in v]
+        elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, flushed_ms, prod_ms, e2e_packed_s, e2e_pipe_s = [float(x) for x in v]
     if rank != 0:
         return 0
 
@@ -616,6 +651,11 @@ def own_arm(args, rank, world, local_rank):
                                     "reads / writes the pinned buffers in place over the host link -- the h2d / d2h bytes are moved "
                                     "by the kernel's own loads and stores, inside the timed region); steady-state envs (burn-in as above)",
                 "reward_checksum": checksum,
+                "pipelined": {"value": total_envs * KE * PIPE / e2e_pipe_s, "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n,
+                              "batches_in_flight": PIPE, "checksum": pipe_checksum,
+                              "api": "gw_step_host_compact_async on %d independent env batches (one handle each): the host waits "
+                                     "for a batch's previous results, reads them and submits its next actions while the other "
+                                     "batches' steps run -- the throughput form of the same host-buffer path" % PIPE},
                 "packed_api": {"value": total_envs * KE / e2e_packed_s, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 9 * n,
                                "api": "CounterTrafficEnv.step_host_packed -> gw_step_host_packed (int32 actions [2][n] in, "
                                       "int32 obs | float32 reward | uint8 done out)"},

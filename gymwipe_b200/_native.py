@@ -110,6 +110,7 @@ _SIGNATURES = {
     "gw_step_host": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "gw_step_host_packed": (C.c_int, [_VP, _VP, _VP, _VP]),
     "gw_step_host_compact": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "gw_step_host_compact_async": (C.c_int, [_VP, _VP, _VP, _VP]),
     "gw_check": (C.c_int, [_VP, _VP]),
     "gw_stats": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "gw_read_state": (C.c_int, [_VP, C.c_int, _VP, _VP]),

@@ -1653,7 +1653,19 @@ static void *mapped_alias(const void *p)
     return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
+static int step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *results, void *stream, bool sync);
+
 int gw_step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *results, void *stream)
+{
+    return step_host_compact(h, actions, results, stream, true);
+}
+
+int gw_step_host_compact_async(gw_handle *h, const uint8_t *actions, uint32_t *results, void *stream)
+{
+    return step_host_compact(h, actions, results, stream, false);
+}
+
+static int step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *results, void *stream, bool sync)
 {
     if (!h) return fail(GW_E_INVALID, "handle is NULL");
     if (!actions || !results) return fail(GW_E_INVALID, "NULL buffer");
@@ -1671,9 +1683,10 @@ int gw_step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *results
         const int rc = launch_step(h, nullptr, nullptr, nullptr, nullptr, nullptr, s, nullptr, nullptr, nullptr, nullptr, 0,
                                    m_act, m_res);
         if (rc) return rc;
-        CUDA_TRY(cudaStreamSynchronize(s));
+        if (sync) CUDA_TRY(cudaStreamSynchronize(s));
         return GW_OK;
     }
+    if (!sync) return fail(GW_E_INVALID, "gw_step_host_compact_async needs pinned host buffers");
     // staging: uint8 actions [n][2] in the action staging area, uint32 results [n] in the obs area
     unsigned char *d_act = (unsigned char *)h->d_dev;
     unsigned *d_res = (unsigned *)h->d_obs;

@@ -442,6 +442,18 @@ class CounterTrafficEnv(BaseEnv):
         with torch.cuda.device(self.device):
             N.check(self._lib.gw_step_host_packed(self._handle, ptr(actions), ptr(results), self._stream()))
 
+    def step_host_compact_async(self, actions, results):
+        """
+        :meth:`step_host_compact` without the final synchronisation (``gw_step_host_compact_async``): for
+        callers that keep several env batches in flight.  Pinned buffers only; ``results`` is valid once
+        the current stream (or an event recorded after this call) has completed.
+        """
+        a = actions.data_ptr() if torch.is_tensor(actions) else actions.ctypes.data
+        r = results.data_ptr() if torch.is_tensor(results) else results.ctypes.data
+        rc = self._lib.gw_step_host_compact_async(self._handle, a, r, torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            N.check(rc)
+
     def step_host_compact(self, actions, results):
         """
         Compact end-to-end step (``gw_step_host_compact``): ``actions`` is a pinned uint8 tensor / array

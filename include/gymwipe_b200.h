@@ -188,6 +188,10 @@ int gw_step_host_packed(gw_handle *h, const int32_t *actions, void *results, voi
  * enqueued; pageable buffers are staged through two copies.  Synchronises `stream`.  Not available
  * for plant envs (their observations are not integers of this range). */
 int gw_step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *results, void *stream);
+/* Asynchronous form for callers that keep several env batches in flight (one handle each): enqueues
+ * the step on `stream` and returns; `results` is valid once the stream (or an event recorded after the
+ * call) has completed.  PINNED host buffers only (GW_E_INVALID otherwise). */
+int gw_step_host_compact_async(gw_handle *h, const uint8_t *actions, uint32_t *results, void *stream);
 #define GW_COMPACT_OBS(w)    ((int32_t)((w) & 0x1FFFFu))
 #define GW_COMPACT_REWARD(w) ((int32_t)(((w) >> 17) & 31u) - 16)
 #define GW_COMPACT_DONE(w)   ((int32_t)(((w) >> 22) & 1u))

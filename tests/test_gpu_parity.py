@@ -383,6 +383,39 @@ def test_step_host_compact_end_to_end(n, pinned):
         env.check()
 
 
+def test_step_host_compact_async_two_batches_in_flight():
+    """gw_step_host_compact_async: two env batches in flight on one stream, results valid after their events."""
+    from gymwipe_b200.scenario import default_scenario_dict
+    sc = default_scenario_dict()
+    rs = np.random.RandomState(34)
+    n, T = 777, 40
+    tapes = [random_tapes(rs, T, n, 1) for _ in range(2)]
+    refs = [O.run_batch(sc, d, u) for d, u in tapes]
+    envs = [make_env(sc, n, strict=False) for _ in range(2)]
+    acts = [[torch.from_numpy(np.stack([d[t, :, 0], u[t, :, 0]], axis=1).astype(np.uint8)).pin_memory() for t in range(T)]
+            for d, u in tapes]
+    res = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2)]
+    evs = [torch.cuda.Event() for _ in range(2)]
+    for e in envs:
+        e.reset()
+    for t in range(T):
+        for b in range(2):
+            if t > 0:
+                evs[b].synchronize()
+                obs, rew, done = envs[b].unpack_compact(res[b])
+                assert (obs.numpy() == refs[b]["obs"][t - 1, :, 0]).all()
+                assert (rew.numpy() == refs[b]["reward"][t - 1, :, 0]).all()
+            envs[b].step_host_compact_async(acts[b][t], res[b])
+            evs[b].record()
+    torch.cuda.synchronize()
+    for b in range(2):
+        envs[b].check()
+        assert (envs[b].unpack_compact(res[b])[0].numpy() == refs[b]["obs"][-1, :, 0]).all()
+    # pageable buffers are refused (the asynchronous form never stages)
+    with pytest.raises(Exception):
+        envs[0].step_host_compact_async(np.zeros((n, 2), np.uint8), np.zeros(n, np.int32))
+
+
 def test_stats_epilogue():
     from gymwipe_b200.scenario import default_scenario_dict
     sc = default_scenario_dict()
