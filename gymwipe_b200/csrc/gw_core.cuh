@@ -1401,6 +1401,90 @@ GW_HD void run_until_time(Sim<D, NS, NJ, ST> &s, const Params &P, const BandPara
     s.now = T;
 }
 
+// ---------------------------------------------------------------------------
+// devices moving between steps (the reference's Position.set, devices/core.py:75-84)
+//
+// Position.set -> nChange -> every attenuation model of the device: FsplAttenuation._update
+// (attenuation_models.py:28-36; physical.py:383-386: only below STANDBY_THRESHOLD; equal positions
+// keep the previous value) -> _setAttenuation (physical.py:354-362: only a NEW value triggers) ->
+// SimplePhy._onAttenuationChange (simple_stack.py:119-128) of the PHYs that registered a transmission
+// on that model: the stored received power of the transmission is replaced and the difference goes
+// through _nReceivedPowerChanges -- the PHY's power sum changes, and a PHY that is receiving counts
+// the errors of the segment that ends and, unless its transmission has completed, re-evaluates its bit
+// error rate (simple_stack.py:81-86, 223-233).  Transmissions are registered from the zero-delay
+// notification after their creation to their completion: exactly while the sender is in S_HDR / S_PAY.
+// The models of a device are notified in Python-set order (simtools.py:255); they are visited by
+// ascending partner index here, which only matters for the rounding of the MOVING PHY's own power sum
+// when two or more other devices transmit at that instant.
+//
+// `Tab` gives access to the band-sim's attenuation (dB) and received-power (mW) tables:
+//   att(p, d), set_att(p, d, v), srx(p, d), set_srx(p, d, v), view() -> object for srx_at<D>()
+// ---------------------------------------------------------------------------
+
+template <int MODE, int D, int NS, int NJ, class ST, class SRX, class Masks, class Memo>
+GW_HD void received_power_change(Sim<D, NS, NJ, ST> &s, const Params &P, int p, double delta, const SRX &srx,
+                                 const Masks &masks, const Memo &memo)
+{
+    set_at(s.P, p, get_at(s.P, p) + delta);                 // updateReceivedPower (priority 1)
+    const int e = get_at(s.rxOf, p);
+    if (e < 0 || delta == 0.0) return;                      // onReceivedPowerChange of a running reception
+    if (MODE == MODE_R) {
+        const double duration = s.now - get_at(s.tReset, p);
+        const double bitErrors = get_at(s.ber, p) * duration * P.bitRate;
+        set_at(s.err, p, get_at(s.err, p) + bitErrors);
+    } else {
+        int sender; uint32_t txseq; int64_t k0, k1;
+        mask_range(s, p, P.bitRate, sender, txseq, k0, k1);
+        if (k1 > k0) set_at(s.err, p, get_at(s.err, p) + (double)masks(p, sender, txseq, k0, k1, get_at(s.ber, p)));
+        set_at(s.segT0, p, s.now);
+    }
+    const bool completed = s.now >= get_at(s.tStop, e);
+    if (completed) return;
+    const double S = srx_at<D>(srx, p, e);
+    const double N = get_at(s.P, p) - S;
+    if (!(S >= 0) || !(N >= 0)) { s.fault = FAULT_REF_ASSERT; return; }
+    double ber;
+    if (!memo.get(S, N, ber)) {
+        ber = ber_bpsk_mw_cold(S, N, P.tenLog10BitRate, P.qDen);
+        memo.put(S, N, ber);
+    }
+    set_at(s.ber, p, ber);
+    trace_rec(s, REC_BER, s.now, p, ber, 0.0, 0.0, 0.0);
+}
+
+// `cur` [D][2]: the positions before the call, updated in place; `want` [D][2]: the requested
+// positions.  Devices are moved one after the other by ascending index, like successive
+// Position.set calls.  `powerDbm` [D]: transmission power of each device.
+template <int MODE, int D, int NS, int NJ, class ST, class Tab, class Masks, class Memo>
+GW_HD void move_devices(Sim<D, NS, NJ, ST> &s, const Params &P, const double *powerDbm, double frequency,
+                        double *cur, const double *want, Tab &tab, const Masks &masks, const Memo &memo)
+{
+    for (int m = 0; m < D; ++m) {
+        if (want[2 * m] == cur[2 * m] && want[2 * m + 1] == cur[2 * m + 1]) continue;      // Position.set: no trigger
+        cur[2 * m] = want[2 * m]; cur[2 * m + 1] = want[2 * m + 1];
+        for (int j = 0; j < D; ++j) {
+            if (j == m) continue;
+            const double dx = cur[2 * m] - cur[2 * j], dy = cur[2 * m + 1] - cur[2 * j + 1];
+            const double dist = sqrt(dx * dx + dy * dy);                                    // devices/core.py:88-95
+            if (!(dist < 3000.0)) continue;                                                 // STANDBY_THRESHOLD
+            if (dx == 0.0 && dy == 0.0) continue;                                           // _update returns early
+            const double att = 20 * log10(dist) + 20 * log10(frequency) - 147.55;
+            if (att == tab.att(m, j)) continue;
+            tab.set_att(m, j, att); tab.set_att(j, m, att);
+            // the two directions of the link: (receiver j, sender m) and (receiver m, sender j)
+            for (int dir = 0; dir < 2; ++dir) {
+                const int p = dir == 0 ? j : m, e = dir == 0 ? m : j;
+                const double rp = rx_power_mw(powerDbm[e], att);
+                const int ph = get_at(s.sphase, e);
+                const bool onAir = ph == S_HDR || ph == S_PAY;
+                const double delta = rp - tab.srx(p, e);
+                tab.set_srx(p, e, rp);
+                if (onAir) received_power_change<MODE>(s, P, p, delta, tab.view(), masks, memo);
+            }
+        }
+    }
+}
+
 // CounterTrafficEnv.reset (counter_traffic.py:135-144): sender counters := 0, interpreter
 // reset; time, queues and PHY state stay.  Queued packets keep the sizes they were enqueued
 // with: they are materialised into the snapshot ring (`ringw(sender, slot, size)`) before

@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "../../include/gymwipe_b200.h"
 
@@ -135,6 +136,8 @@ struct gw_handle {
     unsigned memo_entries;
     PendulumParams pend;
     int pdl;                // launch the step kernel with programmatic stream serialization
+    double *pos_cur;        // per-env geometry: current device positions [ntab][GW_MAX_DEVICES][2]
+    int stepped;            // a step has been launched: gw_set_positions moves devices from now on
 };
 
 // ------------------------------------------------------------------------------------
@@ -992,6 +995,66 @@ __global__ void tables_kernel(StatePtrs st, const double *pos /* [ntab][MAXD][2]
     st.srx[(long long)k * st.ntab + tab] = rp;
 }
 
+// tables of one band-sim in global memory, entry (receiver p, sender d) at (p * kMaxDev + d) * stride
+struct DevTab {
+    double *a, *r;
+    long long stride;
+    __device__ __forceinline__ double att(int p, int d) const { return a[(long long)(p * kMaxDev + d) * stride]; }
+    __device__ __forceinline__ void set_att(int p, int d, double v) { a[(long long)(p * kMaxDev + d) * stride] = v; }
+    __device__ __forceinline__ double srx(int p, int d) const { return r[(long long)(p * kMaxDev + d) * stride]; }
+    __device__ __forceinline__ void set_srx(int p, int d, double v) { r[(long long)(p * kMaxDev + d) * stride] = v; }
+    __device__ __forceinline__ SrxView view() const { return SrxView{r, stride}; }
+};
+
+// mode M error counts for one thread (position changes are rare: no warp cooperation)
+struct SerialMasks {
+    MaskSource m;
+    long long env;
+    int band, nb;
+    __device__ long long operator()(int receiver, int sender, uint32_t txseq, long long k0, long long k1, double ber) const
+    {
+        if (m.mode != MODE_M_FED)
+            return mask_errors_serial(m.seed, m.env_offset + env, band, sender, txseq, receiver, k0, k1, ber);
+        const long long row = ((((env * nb + band) * kMaxDev + sender) * m.slots + (long long)(txseq % (uint32_t)m.slots)) * kMaxDev + receiver);
+        const uint32_t *w = m.words + row * m.words_per_row;
+        long long n = 0;
+        for (long long k = k0; k < k1; ++k) n += (w[k >> 5] >> (k & 31)) & 1u;
+        return n;
+    }
+};
+
+// gw_set_positions after the first step: every band-sim moves its devices one after the other
+// (gw_core.cuh::move_devices -- the reference's Position.set with SimplePhy._onAttenuationChange for the
+// transmissions that are on the air), one thread per band-sim
+template <int MODE, int D, int NS, int NJ>
+__global__ void move_kernel(StatePtrs st, Params P, MaskSource masks, const double *want /* [ntab][kMaxDev][2] */,
+                            double *cur /* [ntab][kMaxDev][2] */, SharedTables power, SharedTables freq, int *errflag)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.nsim) return;
+    const long long e = i / st.nb;
+    const int band = (int)(i % st.nb);
+    double c[D * 2], w[D * 2], pw[D];
+    bool moved = false;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        c[2 * d] = cur[(i * kMaxDev + d) * 2]; c[2 * d + 1] = cur[(i * kMaxDev + d) * 2 + 1];
+        w[2 * d] = want[(i * kMaxDev + d) * 2]; w[2 * d + 1] = want[(i * kMaxDev + d) * 2 + 1];
+        pw[d] = power.srx[band][d];
+        moved |= (c[2 * d] != w[2 * d]) | (c[2 * d + 1] != w[2 * d + 1]);
+    }
+    if (!moved) return;
+    Sim<D, NS, NJ> s;
+    load_sim(s, st, i, st.now[e]);
+    DevTab tab{st.att + i, st.srx + i, st.ntab};
+    SerialMasks mk{masks, e, band, st.nb};
+    move_devices<MODE>(s, P, pw, freq.srx[band][0], c, w, tab, mk, NoMemo());
+    if (s.fault) { if (atomicCAS(errflag, 0, GW_E_SIMFAULT) == 0) { errflag[1] = (int)i; errflag[2] = s.fault; } }
+    store_sim(s, st, i, false);
+#pragma unroll
+    for (int d = 0; d < D; ++d) { cur[(i * kMaxDev + d) * 2] = c[2 * d]; cur[(i * kMaxDev + d) * 2 + 1] = c[2 * d + 1]; }
+}
+
 template <int D, int NS, int NJ>
 __global__ void read_kernel(StatePtrs st, Params P, int field, double *out)
 {
@@ -1475,6 +1538,20 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
     if (e != cudaSuccess) { gw_destroy(h); return fail(GW_E_CUDA, "init kernel: %s", cudaGetErrorString(e)); }
     rc = launch_tables(h, nullptr, s);
     if (rc) { gw_destroy(h); return rc; }
+    if (cfg->per_env_positions) {
+        // current positions of every band-sim's devices (gw_set_positions moves them from here)
+        const size_t cnt = (size_t)ntab * kMaxDev * 2;
+        std::vector<double> init(cnt, 0.0);
+        for (long long t = 0; t < ntab; ++t)
+            for (int d = 0; d < kMaxDev; ++d) {
+                init[(t * kMaxDev + d) * 2] = h->default_pos[t % cfg->n_bands][d][0];
+                init[(t * kMaxDev + d) * 2 + 1] = h->default_pos[t % cfg->n_bands][d][1];
+            }
+        e = cudaMalloc((void **)&h->pos_cur, cnt * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h->pos_cur, init.data(), cnt * sizeof(double), cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);         // `init` is a local buffer
+        if (e != cudaSuccess) { gw_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
+    }
     *out = h;
     return GW_OK;
 }
@@ -1487,6 +1564,7 @@ void gw_destroy(gw_handle *h)
     if (h->stats) cudaFree(h->stats);
     if (h->d_obs) cudaFree(h->d_obs);       // base of the staging allocation
     if (h->memo) cudaFree(h->memo);
+    if (h->pos_cur) cudaFree(h->pos_cur);
     delete h;
 }
 
@@ -1495,7 +1573,41 @@ int gw_set_positions(gw_handle *h, const double *positions, void *stream)
     if (!h) return fail(GW_E_INVALID, "handle is NULL");
     if (positions && !h->st.per_env) return fail(GW_E_INVALID, "handle was created with per_env_positions = 0");
     CUDA_TRY(cudaSetDevice(h->device));
-    return launch_tables(h, positions, (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t pos_bytes = sizeof(double) * (size_t)h->st.ntab * kMaxDev * 2;
+    if (!positions || h->cfg.plant || !h->stepped) {
+        // placement: the devices are CREATED at these positions (fresh attenuation models)
+        const int rc = launch_tables(h, positions, s);
+        if (rc) return rc;
+        if (positions && h->pos_cur) CUDA_TRY(cudaMemcpyAsync(h->pos_cur, positions, pos_bytes, cudaMemcpyDeviceToDevice, s));
+        return GW_OK;
+    }
+    // the envs have been stepped: the devices MOVE (Position.set); transmissions on the air see
+    // SimplePhy._onAttenuationChange
+    SharedTables pw, fr;
+    std::memset(&pw, 0, sizeof pw); std::memset(&fr, 0, sizeof fr);
+    for (int b = 0; b < h->cfg.n_bands; ++b) {
+        for (int d = 0; d < kMaxDev; ++d) pw.srx[b][d] = h->power_dbm[b][d];
+        fr.srx[b][0] = h->frequency[b];
+    }
+    MaskSource ms;
+    ms.mode = h->cfg.mode; ms.seed = h->cfg.seed; ms.env_offset = h->cfg.env_id_offset;
+    ms.words = h->masks; ms.slots = h->mask_slots > 0 ? h->mask_slots : 1; ms.words_per_row = h->mask_words;
+    if (h->cfg.mode == GW_MODE_MASK_FED && !h->masks) return fail(GW_E_INVALID, "mode MASK_FED: call gw_set_masks first");
+    const long long nsim = h->st.nsim;
+#define CALL_MOVE(DD, SS, JJ)                                                                                              \
+    do {                                                                                                                   \
+        if (h->cfg.mode == GW_MODE_REFERENCE)                                                                              \
+            move_kernel<MODE_R, DD, SS, JJ><<<grid_for(nsim, 64), 64, 0, s>>>(h->st, h->P, ms, positions, h->pos_cur, pw, fr, h->errflag);        \
+        else if (h->cfg.mode == GW_MODE_MASK_PHILOX)                                                                       \
+            move_kernel<MODE_M_PHILOX, DD, SS, JJ><<<grid_for(nsim, 64), 64, 0, s>>>(h->st, h->P, ms, positions, h->pos_cur, pw, fr, h->errflag); \
+        else                                                                                                               \
+            move_kernel<MODE_M_FED, DD, SS, JJ><<<grid_for(nsim, 64), 64, 0, s>>>(h->st, h->P, ms, positions, h->pos_cur, pw, fr, h->errflag);    \
+    } while (0)
+    DISPATCH_SHAPE(h, CALL_MOVE);
+#undef CALL_MOVE
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
 }
 
 int gw_reset(gw_handle *h, const int64_t *env_ids, int64_t n, int64_t *obs, void *stream)
@@ -1519,6 +1631,7 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
                        long long sim_begin = 0, long long sim_end = -1)
 {
     if (h->cfg.mode == GW_MODE_MASK_FED && !h->masks) return fail(GW_E_INVALID, "mode MASK_FED: call gw_set_masks first");
+    h->stepped = 1;
     StepArgs A;
     A.st = h->st;
     A.device = device; A.duration = duration;

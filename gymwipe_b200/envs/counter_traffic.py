@@ -277,7 +277,12 @@ class CounterTrafficEnv(BaseEnv):
         return out
 
     def set_positions(self, positions):
-        """Per-env device positions ``[num_envs, n_bands, 4, 2]`` (float64, CUDA)."""
+        """
+        Per-env device positions ``[num_envs, n_bands, 4, 2]`` (float64, CUDA).  At construction the
+        devices are created there; once the env has been stepped the call MOVES them (the reference's
+        ``Position.set`` between two ``step`` calls, devices by ascending index): transmissions that
+        are on the air see ``SimplePhy._onAttenuationChange`` (``gw_set_positions``).
+        """
         p = torch.as_tensor(positions, dtype=torch.float64, device=self.device).contiguous()
         assert tuple(p.shape) == (self.num_envs, self.n_bands, N.GW_MAX_DEVICES, 2)
         self._positions = p

@@ -126,9 +126,17 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
 void gw_destroy(gw_handle *h);
 
 /* Per-env device positions, float64 [n_envs][n_bands][GW_MAX_DEVICES][2] on the device
- * (Device / Position, devices/core.py); recomputes the FSPL attenuation and received-
- * power tables (kernel K1; attenuation_models.py:28-36, simple_stack.py:99-111).  With
- * `positions == NULL` the scenario's default positions are applied to every env. */
+ * (Device / Position, devices/core.py).
+ *  - Before the first step: the devices are CREATED there -- the FSPL attenuation and received-
+ *    power tables are computed from scratch (kernel K1; attenuation_models.py:28-36,
+ *    simple_stack.py:99-111).  With `positions == NULL` the scenario's default positions are applied.
+ *  - Afterwards: the devices MOVE, one after the other by ascending index like successive
+ *    Position.set calls (devices/core.py:75-84) between two env.step calls: models beyond
+ *    STANDBY_THRESHOLD or with coinciding devices keep their attenuation (physical.py:383-386,
+ *    attenuation_models.py:31-33), and transmissions that are on the air at that instant see
+ *    SimplePhy._onAttenuationChange (simple_stack.py:119-128): the receivers' power sums change, a
+ *    running reception counts the errors of the segment that ends and re-evaluates its bit error
+ *    rate (all three accounting modes).  Plant envs re-create the tables instead. */
 int gw_set_positions(gw_handle *h, const double *positions, void *stream);
 
 /* Replaces CounterTrafficEnv.reset (counter_traffic.py:135-144): sender counters := 0,

@@ -36,6 +36,7 @@ CASES = {
     "longpacket_seed7": ("long", 7, 12),
     "multiband_seed9": ("multiband", 9, 24),
     "mobility_seed13": ("mobility", 13, 80),
+    "mobility_inflight_seed17": ("mobilityjam", 17, 60),
     "modeM_jammer_seed11": ("maskjammer", 11, 40),
     "modeM_default_seed12": ("maskdefault", 12, 60),
 }
@@ -65,6 +66,11 @@ def make_case(kind, seed, steps):
         tape = [list(x) for x in zip(*tapes)]
     elif kind == "mobility":
         sc, tape = CR.random_scenario(rs, jammers=0, spread=2.0), H.random_actions(steps, seed=seed + 8000)
+    elif kind == "mobilityjam":
+        # a PHY-only sender whose transmissions are regularly on the air at step boundaries, when devices move
+        sc, tape = CR.random_scenario(rs, jammers=1, spread=2.0), H.random_actions(steps, seed=seed + 8500)
+        sc["bands"][0]["devices"][3]["interval"] = 0.0123
+        sc["bands"][0]["devices"][3]["payload"] = 120
     elif kind == "maskjammer":
         sc, tape = CR.random_scenario(rs, jammers=1, spread=2.5), H.random_actions(steps, seed=seed + 6000)
     elif kind == "maskdefault":
@@ -90,6 +96,14 @@ def child(name):
         mrs = np.random.RandomState(seed + 1)
         moves = {t: [(0, int(mrs.randint(3)), float(mrs.uniform(-2.5, 2.5)), float(mrs.uniform(-2.5, 2.5)))]
                  for t in range(2, steps, 3)}
+    if kind == "mobilityjam":
+        # every other step one or two devices (ascending index) jump: SimplePhy._onAttenuationChange for the
+        # transmissions that are on the air at that instant
+        mrs = np.random.RandomState(seed + 1)
+        moves = {}
+        for t in range(1, steps, 2):
+            devs = sorted(set(int(v) for v in mrs.randint(4, size=int(mrs.randint(1, 3)))))
+            moves[t] = [(0, d, float(mrs.uniform(-2.5, 2.5)), float(mrs.uniform(-2.5, 2.5))) for d in devs]
     trace = H.run_tape(env, tape, tr, do_reset=do_reset, moves=moves)
     doc = {"name": name, "kind": kind, "seed": seed, "do_reset": do_reset,
            "mode": "M" if mode_m else "R", "mask_seed": MASK_SEED if mode_m else None,

@@ -1127,10 +1127,20 @@ int gwo_step(gwo_sim *s, const int32_t *device, const int32_t *duration,
 /* Position.set (devices/core.py:75-84) -> FsplAttenuation._positionChanged -> _update
  * (attenuation_models.py:28-39, physical.py:383-386).  Only valid while no transmission that
  * involves the device is on the air (the restatement does not model _onAttenuationChange). */
+/* Position.set (devices/core.py:75-84) -> nChange -> every FsplAttenuation model of the device:
+ * _positionChangedCallback (physical.py:383-386) -> _update (attenuation_models.py:28-36) ->
+ * _setAttenuation (physical.py:354-362) -> nAttenuationChanges -> SimplePhy._onAttenuationChange
+ * (simple_stack.py:119-128) of every PHY that registered a transmission on that model: the stored
+ * received power of the transmission is replaced, the difference goes through
+ * _nReceivedPowerChanges (power bookkeeping; a PHY that is receiving counts the errors of the
+ * segment that ends and re-evaluates its bit error rate).
+ * The models of one device are notified in Python-set order (simtools.py:255); they are visited by
+ * ascending partner index here.  The order only matters for the rounding of the moving PHY's own
+ * received power when two or more OTHER devices are transmitting at that instant. */
 int gwo_set_position(gwo_sim *s, int band, int dev, double x, double y)
 {
     Band *B = &s->band[band];
-    for (int i = 0; i < GWO_MAXTX; i++) if (B->tx[i].used) return -1;
+    if (x == B->dev[dev].x && y == B->dev[dev].y) return 0;      /* Position.set: no change, no trigger */
     B->dev[dev].x = x; B->dev[dev].y = y;
     for (int j = 0; j < B->ndev; j++) {
         if (j == dev) continue;
@@ -1139,7 +1149,23 @@ int gwo_set_position(gwo_sim *s, int band, int dev, double x, double y)
         if (B->dev[dev].x == B->dev[j].x && B->dev[dev].y == B->dev[j].y) continue;   /* _update returns early */
         /* devices[0] / devices[1] order of the model is the frozenset order: the formula is symmetric */
         double att = 20 * log10(d) + 20 * log10(B->frequency) - 147.55;
+        if (att == B->att[dev][j]) continue;                      /* _setAttenuation: only a new value triggers */
         B->att[dev][j] = att; B->att[j][dev] = att;
+        /* transmissions registered on this model: sent by one of the two devices, received by the other */
+        for (int ti = 0; ti < GWO_MAXTX; ti++) {
+            Tx *t = &B->tx[ti];
+            if (!t->used) continue;
+            int p = -1;
+            if (t->sender == dev) p = j; else if (t->sender == j) p = dev;
+            if (p < 0) continue;
+            Dev *P = &B->dev[p];
+            if (!P->hasS[ti]) continue;
+            double rp = dbm_to_mw(t->power - att);
+            double delta = rp - P->S[ti];
+            P->S[ti] = rp;
+            power_change(s, band, p, delta);
+            if (s->fault) return -2;
+        }
     }
     return 0;
 }

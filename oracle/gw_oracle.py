@@ -219,9 +219,10 @@ class Oracle:
         return int(o[0]), float(r[0]), bool(d[0])
 
     def set_position(self, band, dev, x, y):
-        """``device.position.set(x, y)`` between steps (no transmission may be on the air)."""
+        """``device.position.set(x, y)`` between steps; transmissions that are on the air see the
+        reference's ``SimplePhy._onAttenuationChange``."""
         if self.L.gwo_set_position(self.h, band, dev, float(x), float(y)) != 0:
-            raise OracleFault("a transmission is on the air: mid-packet attenuation changes are not modelled")
+            raise OracleFault("the position change hit a condition under which the reference raises")
 
     @property
     def now(self):

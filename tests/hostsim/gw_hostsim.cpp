@@ -45,6 +45,21 @@ struct HsBand {
     int32_t jamHdr, jamPay;
 };
 
+struct HsMove {              // the device `dev` of band `band` jumps to (x, y) before step `step` (all envs)
+    int32_t step, band, dev;
+    double x, y;
+};
+
+template <int D>
+struct HostTab {             // tables of one band-sim, [D * D], entry (receiver p, sender d) at p * D + d
+    double *a, *r;
+    double att(int p, int d) const { return a[p * D + d]; }
+    void set_att(int p, int d, double v) { a[p * D + d] = v; }
+    double srx(int p, int d) const { return r[p * D + d]; }
+    void set_srx(int p, int d, double v) { r[p * D + d] = v; }
+    const double *view() const { return r; }
+};
+
 struct HsScenario {
     int32_t nbands, factor, mode;
     uint64_t seed;
@@ -78,13 +93,16 @@ template <int D, int NS, int NJ>
 struct EnvT {
     Sim<D, NS, NJ> sim[kMaxBands];
     double srx[kMaxBands][D * D];
+    double att[kMaxBands][D * D];
+    double pos[kMaxBands][D * 2];
     int32_t ring[kMaxBands][NS * kRingSlots];
 };
 
 template <int MODE, int D, int NS, int NJ>
 int run_t(const HsScenario &sc, int64_t nenv, int nsteps, int do_reset, const double *pos,
           const int32_t *dev_tape, const int32_t *dur_tape, int64_t *obs, double *reward, uint8_t *done,
-          double *now, int64_t *counts, double *power_out, int64_t env_offset)
+          double *now, int64_t *counts, double *power_out, int64_t env_offset,
+          const HsMove *moves = nullptr, int nmoves = 0)
 {
     Params P;
     fill_params(sc, P);
@@ -104,16 +122,34 @@ int run_t(const HsScenario &sc, int64_t nenv, int nsteps, int do_reset, const do
                 if (pos) { x[d] = pos[((e * nb + b) * kMaxDev + d) * 2]; y[d] = pos[((e * nb + b) * kMaxDev + d) * 2 + 1]; }
                 else { x[d] = h.x[d]; y[d] = h.y[d]; }
             }
+            for (int d = 0; d < D; ++d) { E.pos[b][2 * d] = x[d]; E.pos[b][2 * d + 1] = y[d]; }
             for (int p = 0; p < D; ++p)
-                for (int d = 0; d < D; ++d)
-                    E.srx[b][p * D + d] = (p == d) ? 0.0
-                        : rx_power_mw(h.power[d], fspl_db(x[p], y[p], x[d], y[d], h.frequency));
+                for (int d = 0; d < D; ++d) {
+                    E.att[b][p * D + d] = (p == d) ? 0.0 : fspl_db(x[p], y[p], x[d], y[d], h.frequency);
+                    E.srx[b][p * D + d] = (p == d) ? 0.0 : rx_power_mw(h.power[d], E.att[b][p * D + d]);
+                }
         }
         if (do_reset)
             for (int b = 0; b < nb; ++b) { HostRing r{E.ring[b]}; reset_sim(E.sim[b], P.band[b], r); }
         for (int t = 0; t < nsteps; ++t) {
             const size_t base = ((size_t)t * nenv + e) * nb;
             double T = 0;
+            // devices that move before this step (Position.set between two env.step calls)
+            for (int b = 0; b < nb && nmoves > 0; ++b) {
+                double want[D * 2];
+                bool any = false;
+                for (int k = 0; k < D * 2; ++k) want[k] = E.pos[b][k];
+                for (int k = 0; k < nmoves; ++k)
+                    if (moves[k].step == t && moves[k].band == b && moves[k].dev < D) {
+                        want[2 * moves[k].dev] = moves[k].x; want[2 * moves[k].dev + 1] = moves[k].y; any = true;
+                    }
+                if (!any) continue;
+                HostTab<D> tab{E.att[b], E.srx[b]};
+                HostMasks mk{sc.seed, env_offset + e, b};
+                double power[D];
+                for (int d = 0; d < D; ++d) power[d] = sc.band[b].power[d];
+                move_devices<MODE>(E.sim[b], P, power, sc.band[b].frequency, E.pos[b], want, tab, mk, NoMemo());
+            }
             for (int b = 0; b < nb; ++b) {
                 begin_assignment(E.sim[b], P, dev_tape[base + b], dur_tape[base + b]);
             }
@@ -155,14 +191,26 @@ int run_t(const HsScenario &sc, int64_t nenv, int nsteps, int do_reset, const do
 
 extern "C" {
 
+int hs_run_moves(const HsScenario *sc, int64_t nenv, int nsteps, int do_reset, const double *pos,
+                 const int32_t *dev_tape, const int32_t *dur_tape, int64_t *obs, double *reward, uint8_t *done,
+                 double *now, int64_t *counts, double *power_out, int64_t env_offset, const HsMove *moves, int nmoves);
+
 int hs_run(const HsScenario *sc, int64_t nenv, int nsteps, int do_reset, const double *pos,
            const int32_t *dev_tape, const int32_t *dur_tape, int64_t *obs, double *reward, uint8_t *done,
            double *now, int64_t *counts, double *power_out, int64_t env_offset)
 {
+    return hs_run_moves(sc, nenv, nsteps, do_reset, pos, dev_tape, dur_tape, obs, reward, done, now, counts, power_out,
+                        env_offset, nullptr, 0);
+}
+
+int hs_run_moves(const HsScenario *sc, int64_t nenv, int nsteps, int do_reset, const double *pos,
+                 const int32_t *dev_tape, const int32_t *dur_tape, int64_t *obs, double *reward, uint8_t *done,
+                 double *now, int64_t *counts, double *power_out, int64_t env_offset, const HsMove *moves, int nmoves)
+{
     const int ns = sc->band[0].ns, nj = sc->band[0].nj;
     for (int b = 1; b < sc->nbands; ++b)
         if (sc->band[b].ns != ns || sc->band[b].nj != nj) return -1;
-#define HS_ARGS *sc, nenv, nsteps, do_reset, pos, dev_tape, dur_tape, obs, reward, done, now, counts, power_out, env_offset
+#define HS_ARGS *sc, nenv, nsteps, do_reset, pos, dev_tape, dur_tape, obs, reward, done, now, counts, power_out, env_offset, moves, nmoves
     if (sc->mode == MODE_R) {
         if (ns == 2 && nj == 0) return run_t<MODE_R, 3, 2, 0>(HS_ARGS);
         if (ns == 2 && nj == 1) return run_t<MODE_R, 4, 2, 1>(HS_ARGS);

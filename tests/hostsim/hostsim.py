@@ -27,6 +27,10 @@ class HsBand(C.Structure):
                 ("jamHdr", C.c_int32), ("jamPay", C.c_int32)]
 
 
+class HsMove(C.Structure):
+    _fields_ = [("step", C.c_int32), ("band", C.c_int32), ("dev", C.c_int32), ("x", C.c_double), ("y", C.c_double)]
+
+
 class HsScenario(C.Structure):
     _fields_ = [("nbands", C.c_int32), ("factor", C.c_int32), ("mode", C.c_int32), ("seed", C.c_uint64),
                 ("band", HsBand * MAXBAND)]
@@ -49,6 +53,8 @@ def lib():
         L = C.CDLL(SO)
         L.hs_run.restype = C.c_int
         L.hs_run.argtypes = [C.POINTER(HsScenario), C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int64]
+        L.hs_run_moves.restype = C.c_int
+        L.hs_run_moves.argtypes = [C.POINTER(HsScenario), C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_int64, C.c_void_p, C.c_int]
         L.hs_ber.restype = C.c_double
         L.hs_ber.argtypes = [C.c_double, C.c_double]
         L.hs_fspl.restype = C.c_double
@@ -100,7 +106,7 @@ def scenario_from_dict(d, mode=0, seed=0):
     return sc
 
 
-def run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, mode=0, seed=0, env_offset=0, macros=True):
+def run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, mode=0, seed=0, env_offset=0, macros=True, moves=None):
     L = lib()
     L.hs_set_no_macro(-1 if macros else 1)
     sc = scenario_from_dict(scenario, mode, seed) if isinstance(scenario, dict) else scenario
@@ -121,8 +127,14 @@ def run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, mode=0, seed=0, e
 
     def ptr(a):
         return None if a is None else a.ctypes.data_as(C.c_void_p)
-    rc = L.hs_run(C.byref(sc), nenv, nsteps, 1 if do_reset else 0, ptr(pos), ptr(dev_tape), ptr(dur_tape),
-                  ptr(obs), ptr(rew), ptr(done), ptr(now), ptr(counts), ptr(power), env_offset)
+    # moves: {step: [(band, dev, x, y), ...]} -- devices that jump before that step, in every env
+    mv = [(t, b, d, x, y) for t, lst in sorted((moves or {}).items()) for (b, d, x, y) in lst]
+    arr = (HsMove * max(len(mv), 1))()
+    for k, (t, b, d, x, y) in enumerate(mv):
+        arr[k].step, arr[k].band, arr[k].dev, arr[k].x, arr[k].y = int(t), int(b), int(d), float(x), float(y)
+    rc = L.hs_run_moves(C.byref(sc), nenv, nsteps, 1 if do_reset else 0, ptr(pos), ptr(dev_tape), ptr(dur_tape),
+                        ptr(obs), ptr(rew), ptr(done), ptr(now), ptr(counts), ptr(power), env_offset,
+                        C.cast(arr, C.c_void_p), len(mv))
     ms = (C.c_longlong * 2)()
     L.hs_macro_stats(ms)
     return {"macro_tx": int(ms[0]), "macro_tail": int(ms[1]), "rc": rc, "obs": obs, "reward": rew, "done": done, "now": now, "counts": counts, "power": power}

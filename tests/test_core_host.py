@@ -204,3 +204,43 @@ def test_airtime_table_equals_the_division():
     L = HS.lib()
     for k in list(range(0, 64)) + [1525, 65561]:
         assert L.hs_airtime(k) == (k * 8) / (0.75 * 133.33333e3)
+
+
+@pytest.mark.parametrize("name", ["mobility_seed13", "mobility_inflight_seed17"])
+def test_core_moving_devices_match_reference_golden(name):
+    """Devices move between steps; in the second golden transmissions are on the air at that instant
+    (the reference's SimplePhy._onAttenuationChange): gw_core.cuh::move_devices."""
+    doc = load_golden(name)
+    moves = {int(k): [tuple(m) for m in v] for k, v in doc["moves"].items()}
+    dev, dur = tapes_from_golden(doc)
+    obs, rew, done, now = golden_results(doc)
+    for macros in (True, False):
+        h = HS.run(doc["scenario"], dev, dur, do_reset=doc["do_reset"], moves=moves, macros=macros)
+        assert h["rc"] == 0
+        assert (h["obs"][:, 0, :] == obs).all() and (h["reward"][:, 0, :] == rew).all()
+        assert (h["now"][:, 0] == now).all()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_core_moving_devices_random_vs_oracle(seed):
+    """Random scenarios with a PHY-only sender, devices jumping before every other step (mode R and M)."""
+    rs = np.random.RandomState(7000 + seed)
+    sc = random_scenario(rs, jammers=1, spread=2.5)
+    sc["bands"][0]["devices"][3]["interval"] = float(rs.uniform(0.008, 0.02))
+    nsteps = 70
+    dev, dur = random_tapes(rs, nsteps, 1, 1)
+    moves = {}
+    for t in range(1, nsteps, 2):
+        devs = sorted(set(int(v) for v in rs.randint(4, size=int(rs.randint(1, 4)))))
+        moves[t] = [(0, d, float(rs.uniform(-3, 3)), float(rs.uniform(-3, 3))) for d in devs]
+    acts = [{"device": int(dev[t, 0, 0]), "duration": int(dur[t, 0, 0])} for t in range(nsteps)]
+    for mode, hs_mode in ((O.MODE_R, 0), (O.MODE_M, 1)):
+        ora = O.Oracle(sc, mode=mode)
+        if mode == O.MODE_M:
+            ora.use_philox_masks(77, 5)
+        res = O.run_tape(ora, acts, do_reset=True, moves=moves)
+        h = HS.run(sc, dev, dur, do_reset=True, moves=moves, mode=hs_mode, seed=77, env_offset=5)
+        assert h["rc"] == 0
+        assert [s["obs"] for s in res["steps"]] == list(h["obs"][:, 0, 0])
+        assert [s["reward"] for s in res["steps"]] == list(h["reward"][:, 0, 0])
+        assert [s["now"] for s in res["steps"]] == list(h["now"][:, 0])

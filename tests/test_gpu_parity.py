@@ -205,9 +205,11 @@ def test_cuda_per_env_positions():
                 assert abs(got - want) <= BER_RTOL * abs(want)
 
 
-def test_cuda_moving_devices_match_reference_golden():
-    """gw_set_positions between steps vs the reference's Position.set (golden from the reference)."""
-    doc = load_golden("mobility_seed13")
+@pytest.mark.parametrize("name", ["mobility_seed13", "mobility_inflight_seed17"])
+def test_cuda_moving_devices_match_reference_golden(name):
+    """gw_set_positions between steps vs the reference's Position.set (goldens from the reference); in
+    the second golden transmissions are on the air when devices move (SimplePhy._onAttenuationChange)."""
+    doc = load_golden(name)
     moves = {int(k): [tuple(m) for m in v] for k, v in doc["moves"].items()}
     devs = doc["scenario"]["bands"][0]["devices"]
     pos = torch.zeros((1, 1, 4, 2), dtype=torch.float64)
@@ -226,8 +228,50 @@ def test_cuda_moving_devices_match_reference_golden():
                                 "duration": torch.tensor([a["duration"]], dtype=torch.int32).cuda()})
         assert int(o[0]) == s["obs"] and float(r[0]) == s["reward"], t
         assert float(env.read_state(0)[0]) == s["now"], t
-    n_rx = sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "rx")
+    n_rx = sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "rx" and r[3] < 2)    # the MAC senders' packets
     assert int(env.delivered().sum()) == n_rx and n_rx > 0
+
+
+@pytest.mark.parametrize("mode", ["reference", "mask_philox"])
+def test_cuda_moving_devices_random_vs_oracle(mode):
+    """Per-env random jumps before every other step while a PHY-only sender keeps the band busy."""
+    rs = np.random.RandomState(7100)
+    sc = random_scenario(rs, jammers=1, spread=2.5)
+    sc["bands"][0]["devices"][3]["interval"] = 0.011
+    n, T = 12, 50
+    dev, dur = random_tapes(rs, T, n, 1)
+    devs = sc["bands"][0]["devices"]
+    pos = torch.zeros((n, 1, 4, 2), dtype=torch.float64)
+    for d, dv in enumerate(devs):
+        pos[:, 0, d, 0], pos[:, 0, d, 1] = dv["x"], dv["y"]
+    moves = [{} for _ in range(n)]
+    for e in range(n):
+        for t in range(1, T, 2):
+            ds = sorted(set(int(v) for v in rs.randint(4, size=int(rs.randint(1, 4)))))
+            moves[e][t] = [(0, d, float(rs.uniform(-3, 3)), float(rs.uniform(-3, 3))) for d in ds]
+    kw = {} if mode == "reference" else {"mode": mode, "seed": 91}
+    env = make_env(sc, n, strict=False, positions=pos.cuda(), **kw)
+    env.reset()
+    got_obs = np.zeros((T, n), np.int64)
+    got_now = np.zeros((T, n))
+    for t in range(T):
+        if t % 2 == 1:
+            for e in range(n):
+                for (_, d, x, y) in moves[e][t]:
+                    pos[e, 0, d, 0], pos[e, 0, d, 1] = x, y
+            env.set_positions(pos.cuda())
+        o, r, dn, _ = env.step({"device": torch.as_tensor(dev[t, :, 0]).cuda(), "duration": torch.as_tensor(dur[t, :, 0]).cuda()})
+        got_obs[t] = o.cpu().numpy()
+        got_now[t] = env.read_state(0).cpu().numpy()
+    env.check()
+    for e in range(n):
+        ora = O.Oracle(sc, mode=O.MODE_R if mode == "reference" else O.MODE_M)
+        if mode != "reference":
+            ora.use_philox_masks(91, e)
+        acts = [{"device": int(dev[t, e, 0]), "duration": int(dur[t, e, 0])} for t in range(T)]
+        res = O.run_tape(ora, acts, do_reset=True, moves=moves[e])
+        assert [s["obs"] for s in res["steps"]] == list(got_obs[:, e]), e
+        assert [s["now"] for s in res["steps"]] == list(got_now[:, e]), e
 
 
 def _with_positions(sc, pos_env):

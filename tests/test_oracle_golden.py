@@ -37,15 +37,23 @@ def test_restatement_matches_reference_trace(name):
         assert ora.near_ties == 0          # no decider threshold is within rounding distance
 
 
-def test_restatement_matches_reference_with_moving_devices():
-    """Devices move between steps (Position.set in the reference); goldens from the reference."""
-    doc = load_golden("mobility_seed13")
+@pytest.mark.parametrize("name", ["mobility_seed13", "mobility_inflight_seed17"])
+def test_restatement_matches_reference_with_moving_devices(name):
+    """Devices move between steps (Position.set in the reference); goldens from the reference.  In the
+    second case a PHY-only sender is regularly on the air when devices move: the reference's
+    SimplePhy._onAttenuationChange path (mid-packet power change, error count, BER re-evaluation)."""
+    doc = load_golden(name)
     moves = {int(k): [tuple(m) for m in v] for k, v in doc["moves"].items()}
     ora = O.Oracle(doc["scenario"], trace=True)
     res = O.run_tape(ora, [s["action"] for s in doc["steps"]], do_reset=doc["do_reset"], moves=moves)
     for i, (a, b) in enumerate(zip(doc["steps"], res["steps"])):
         assert a["obs"] == b["obs"] and a["reward"] == b["reward"] and a["now"] == b["now"], i
         assert canonical(a["records"]) == canonical(b["records"]), i
+    if name == "mobility_inflight_seed17":
+        # the case does exercise mid-packet changes: BER records stamped with a step's START time
+        starts = [0.0] + [s["now"] for s in doc["steps"][:-1]]
+        hits = sum(1 for s, t0 in zip(doc["steps"], starts) for r in s["records"] if r[0] == "ber" and r[1] == t0)
+        assert hits >= 10, hits
 
 
 def test_reference_known_answer():
