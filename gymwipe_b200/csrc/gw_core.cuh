@@ -1150,28 +1150,32 @@ GW_HD bool macros_enabled(const Params &P)
 
 template <int D, int NS, int NJ, class ST, class SRX, class Ring, class Memo>
 GW_HD bool isolated_tx(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const Event &ev,
-                       const SRX &srx, const Ring &ring, const Memo &memo, double tLimit)
+                       const SRX &srx, const Ring &ring, const Memo &memo, double tLimit, bool idleStart = false)
 {
     static_assert(NS == 2, "the tick logic is written for two senders per band");
     constexpr int RRM = NS;
     int d = ev.idx;
-    if (get_at(s.sphase, d) != S_SLOT) return false;
-    // structural part of the isolation test; it stays true along the chain (nothing but the chained
-    // transmissions happens, and their completion handlers leave every receiver idle)
-    bool ok = true;
-    GW_UNROLL
-    for (int p = 0; p < D; ++p) ok &= (s.rxOf[p] < 0) & ((p == d) | (s.sphase[p] == S_IDLE));
-    GW_UNROLL
-    for (int k = 0; k < NS; ++k) ok &= s.mac[k] != MAC_WAIT_COND;
-    if (!ok) return false;
-    // the earliest OTHER timed event (window time-outs, the RRM guard time-out, jammer wake-ups,
-    // the caller's horizon): a transmission is isolated if it completes strictly before it
     double tOther = tLimit;
-    GW_UNROLL
-    for (int k = 0; k < NS; ++k) if (s.wPend[k]) tOther = fmin(tOther, s.stopW[k]);
-    if (s.rrmPend) tOther = fmin(tOther, s.tRrm);
-    GW_UNROLL
-    for (int j = 0; j < NJ; ++j) tOther = fmin(tOther, s.tJam[j]);
+    // idleStart: the caller established that `ev` is the slot start of the RRM's announcement in a
+    // band-sim where nothing else is active or pending (run_until_assign): the tests below hold
+    if (!idleStart) {
+        if (get_at(s.sphase, d) != S_SLOT) return false;
+        // structural part of the isolation test; it stays true along the chain (nothing but the chained
+        // transmissions happens, and their completion handlers leave every receiver idle)
+        bool ok = true;
+        GW_UNROLL
+        for (int p = 0; p < D; ++p) ok &= (s.rxOf[p] < 0) & ((p == d) | (s.sphase[p] == S_IDLE));
+        GW_UNROLL
+        for (int k = 0; k < NS; ++k) ok &= s.mac[k] != MAC_WAIT_COND;
+        if (!ok) return false;
+        // the earliest OTHER timed event (window time-outs, the RRM guard time-out, jammer wake-ups,
+        // the caller's horizon): a transmission is isolated if it completes strictly before it
+        GW_UNROLL
+        for (int k = 0; k < NS; ++k) if (s.wPend[k]) tOther = fmin(tOther, s.stopW[k]);
+        if (s.rrmPend) tOther = fmin(tOther, s.tRrm);
+        GW_UNROLL
+        for (int j = 0; j < NJ; ++j) tOther = fmin(tOther, s.tJam[j]);
+    }
 
     // state of the chain, in registers: received powers (written back at the end), the links from
     // the current sender, the last BER evaluated per receiver (the same (S, N) recurs from packet
@@ -1375,13 +1379,40 @@ GW_HD void run_until_assign_plant(Sim<D, NS, NJ, ST> &s, const Params &P, const 
 // SimMan.runSimulation(assignSignal.eProcessed) (counter_traffic.py:155)
 template <int MODE, int D, int NS, int NJ, class ST, class SRX, class Ring, class Masks, class Memo = NoMemo>
 GW_HD void run_until_assign(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B,
-                            const SRX &srx, const Ring &ring, const Masks &masks, const Memo &memo = Memo())
+                            const SRX &srx, const Ring &ring, const Masks &masks, const Memo &memo = Memo(),
+                            int idleAtStart = 0)
 {
     const bool macros = macros_enabled<MODE, NJ>(P);
+    // The common start of a step: begin_assignment() found the band-sim idle -- no PHY active, no
+    // reception, no MAC busy, no window or guard time-out pending (and no interferer on the band).
+    // Then the RRM's slot start is the only non-tick event: it needs no selection, and its
+    // transmission passes the structural isolation test by construction.  `idleAtStart` > 0: the
+    // caller knows (the kernels read it from the packed flags); 0: checked here.
+    bool first = false;
+    if (macros && NJ == 0) {
+        if (idleAtStart > 0) {
+            first = true;
+        } else {
+            bool idle = (s.sphase[NS] == S_SLOT) & (s.rrmPend == 0);
+            GW_UNROLL
+            for (int p = 0; p < D; ++p) idle &= (s.rxOf[p] < 0) & ((p == NS) | (s.sphase[p] == S_IDLE));
+            GW_UNROLL
+            for (int k = 0; k < NS; ++k) idle &= (s.mac[k] == MAC_NONE) & (s.wPend[k] == 0);
+            first = idle;
+        }
+    }
     while (!s.assignDone && !s.fault) {
-        if (macros && quiet_tail(s, B)) break;
-        const Event ev = next_event(s, B, INFINITY);
-        if (macros && ev.kind == EV_PHY && isolated_tx(s, P, B, ev, srx, ring, memo, INFINITY)) continue;
+        Event ev;
+        const bool idleStart = first;
+        if (first) {
+            first = false;
+            ev.kind = EV_PHY; ev.idx = NS; ev.t = s.tEv[NS]; ev.seq = s.sEv[NS];
+            silent_ticks_both(s, B, ev.t, ev.seq, true, INFINITY);
+        } else {
+            if (macros && quiet_tail(s, B)) break;
+            ev = next_event(s, B, INFINITY);
+        }
+        if (macros && ev.kind == EV_PHY && isolated_tx(s, P, B, ev, srx, ring, memo, INFINITY, idleStart)) continue;
         process_event<MODE>(s, P, B, ev, srx, ring, masks, memo);
     }
 }

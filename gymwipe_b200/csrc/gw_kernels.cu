@@ -271,7 +271,7 @@ __device__ __forceinline__ void pack_flags(const Sim<D, NS, NJ, ST> &s, bool bus
 // through DevRing --, mode-M segment starts in mode R, packet values without a plant), which
 // makes them dead in registers
 template <bool FULL = true, bool WITH_SEG = true, int D, int NS, int NJ, class ST>
-__device__ __forceinline__ void load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs &st, long long i, double now)
+__device__ __forceinline__ bool load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs &st, long long i, double now)
 {
     const long long n = st.nsim;
     s.now = now;
@@ -344,6 +344,7 @@ __device__ __forceinline__ void load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs 
     }
     s.annDest = 0; s.annBytes = 0; s.annSlots = 0; s.rrmPend = 0; s.tRrm = 0; s.sRrm = 0; s.assignDone = 0;
     s.trace = nullptr; s.ntrace = 0; s.traceCap = 0;
+    return busy;        // something was in flight across the step boundary (sim_busy at the last store)
 }
 
 template <bool FULL = true, bool WITH_SEG = true, int D, int NS, int NJ, class ST>
@@ -682,8 +683,9 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
                                          : SrxView{&srx_s[band][0], 1};
         DevRing ring{A.st.ring + (active ? i : 0), nsim, A.st.hot + (active ? i : 0)};
         int dev = 0, dur = 0;
+        bool idle0 = false;
         if (active) {
-            load_sim<false, MODE != MODE_R>(s, A.st, i, A.st.now[env]);
+            idle0 = !load_sim<false, MODE != MODE_R>(s, A.st, i, A.st.now[env]);
             if (base != A.sim_begin + (long long)blockIdx.x * blockDim.x) {     // later rounds of the grid-stride loop
                 prefetch_l2(A.st.hot + (long long)H_EP0 * nsim + i);
                 prefetch_l2(A.st.hot + (long long)H_EP1 * nsim + i);
@@ -712,7 +714,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         const uint32_t ties0 = 0;           // the lean load starts the per-step tie counter at 0
 
         if (MODE == MODE_R) {
-            if (active) run_until_assign<MODE_R>(s, P, B, srx, ring, NoMasks(), memo);
+            if (active) run_until_assign<MODE_R>(s, P, B, srx, ring, NoMasks(), memo, idle0 ? 1 : 0);
             if (nb > 1) {
                 // SimMan.runSimulation for every band's ASSIGN message: the env's clock ends
                 // at the latest band; the other bands keep simulating up to that time
