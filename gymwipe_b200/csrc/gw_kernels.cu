@@ -558,6 +558,16 @@ __device__ __forceinline__ int warp_popc_range(const uint32_t *row, int k0, int 
     return n;
 }
 
+// the same count by ONE lane (every lane of a warp scanning a range of its own)
+__device__ __forceinline__ int lane_popc_range(const uint32_t *row, int k0, int k1)
+{
+    int n = 0;
+    const int q0 = k0 >> 7, q1 = (k1 - 1) >> 7;
+    const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
+    for (int q = q0; q <= q1; ++q) n += popc_group(__ldg(row4 + q), q, q0, q1, k0, k1);
+    return n;
+}
+
 // Philox-generated masks: bit k is an error iff word (k & 3) of block (k >> 2) < thr
 __device__ __forceinline__ int warp_philox_range(unsigned long long seed, long long env, int band, int sender,
                                                  uint32_t txseq, int receiver, int k0, int k1, uint32_t thr, int lane)
@@ -753,8 +763,58 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
                     s.now = ev.t;
                     count_set(s, ev, srx, once, twice);
                 }
-                // service the count requests: for every lane with requests, all lanes scan
-                unsigned pending = __ballot_sync(0xFFFFFFFFu, once != 0);
+                // Service the count requests.  Two ways: (a) cooperatively -- for every lane with requests
+                // all 32 lanes scan that lane's range (ballot / shuffle / popc, coalesced 512-byte reads):
+                // right for few, long ranges; (b) every lane scans its own ranges: right when many lanes
+                // have requests at once, which is the rule in this lockstep loop.  The warp picks the
+                // cheaper one from an instruction estimate (warp-uniform, so (a) stays converged).
+                int costLocal = 0, costCoop = 0;
+                if (once != 0) {
+                    int req = once;
+                    while (req) {
+                        const int p = __ffs(req) - 1;
+                        req &= req - 1;
+                        int sender; uint32_t txseq; int64_t k0, k1;
+                        mask_range(s, p, P.bitRate, sender, txseq, k0, k1);
+                        if (k1 > k0) {
+                            if (MODE == MODE_M_FED) {
+                                const int groups = (int)(((k1 - 1) >> 7) - (k0 >> 7)) + 1;       // 16-byte groups
+                                costLocal += 14 * groups + 20;
+                                costCoop += 45 * ((groups + 127) >> 7) + 50;
+                            } else {
+                                const int blocks = (int)(((k1 - 1) >> 2) - (k0 >> 2)) + 1;       // Philox blocks
+                                costLocal += 120 * blocks + 20;
+                                costCoop += 120 * ((blocks + 31) >> 5) + 50;
+                            }
+                        } else {
+                            costLocal += 10; costCoop += 50;
+                        }
+                    }
+                }
+                const bool laneLocal = __reduce_max_sync(0xFFFFFFFFu, costLocal) <= __reduce_add_sync(0xFFFFFFFFu, costCoop);
+                if (laneLocal) {
+                    int req = once;
+                    while (req) {
+                        const int p = __ffs(req) - 1;
+                        req &= req - 1;
+                        int sender; uint32_t txseq; int64_t k0, k1;
+                        mask_range(s, p, P.bitRate, sender, txseq, k0, k1);
+                        long long cnt = 0;
+                        if (k1 > k0) {
+                            if (MODE == MODE_M_FED) {
+                                const long long row = ((((env * nb + band) * kMaxDev + sender) * A.masks.slots
+                                                        + (long long)(txseq % (uint32_t)A.masks.slots)) * kMaxDev + p);
+                                cnt = lane_popc_range(A.masks.words + row * A.masks.words_per_row, (int)k0, (int)k1);
+                            } else {
+                                cnt = mask_errors_serial(A.masks.seed, A.masks.env_offset + env, band, sender, txseq, p,
+                                                         k0, k1, get_at(s.ber, p));
+                            }
+                        }
+                        set_at(s.err, p, get_at(s.err, p) + (double)cnt);
+                        set_at(s.segT0, p, s.now);
+                    }
+                }
+                unsigned pending = laneLocal ? 0u : __ballot_sync(0xFFFFFFFFu, once != 0);
                 while (pending) {
                     const int src = __ffs(pending) - 1;
                     pending &= pending - 1;
