@@ -68,17 +68,17 @@ def compare(ref, ora, label, ber_rtol=0.0):
     return bad
 
 
-def run_case_m(scenario, tape, label, seed=77, env_id=12345):
+def run_case_m(scenario, tape, label, seed=77, env_id=12345, moves=None):
     """mode M: reference + MaskedPhy subclass (numpy Philox) vs the restatement (C Philox)."""
     tr = H.Tracer()
     H.setup_paths()
     H.install_masked_phy(lambda band, sender, seq, receiver, k0, k1, ber:
                          H.philox_mask_errors(seed, env_id, band, sender, seq, receiver, k0, k1, ber), tr)
     env = H.ScenarioEnv(scenario, tr)
-    ref = H.run_tape(env, tape, tr)
+    ref = H.run_tape(env, tape, tr, moves=moves)
     ora_env = O.Oracle(scenario, trace=True, mode=O.MODE_M)
     ora_env.use_philox_masks(seed, env_id)
-    ora = O.run_tape(ora_env, tape)
+    ora = O.run_tape(ora_env, tape, moves=moves)
     bad = compare(ref, ora, label)
     ndec = sum(1 for s in ref["steps"] for r in s["records"] if r[0] == "dec")
     nfail = sum(1 for s in ref["steps"] for r in s["records"] if r[0] == "dec" and not r[7])
@@ -86,14 +86,14 @@ def run_case_m(scenario, tape, label, seed=77, env_id=12345):
     return bad
 
 
-def run_case(scenario, tape, label, do_reset=True, use_default_class=False):
+def run_case(scenario, tape, label, do_reset=True, use_default_class=False, moves=None):
     tr = H.Tracer()
     if use_default_class:
         env = H.make_default_env(tr)
     else:
         env = H.ScenarioEnv(scenario, tr)
-    ref = H.run_tape(env, tape, tr, do_reset=do_reset)
-    ora = O.run_tape(O.Oracle(scenario, trace=True), tape, do_reset=do_reset)
+    ref = H.run_tape(env, tape, tr, do_reset=do_reset, moves=moves)
+    ora = O.run_tape(O.Oracle(scenario, trace=True), tape, do_reset=do_reset, moves=moves)
     bad = compare(ref, ora, label)
     ev_ref = sum(s["events"] for s in ref["steps"])
     ev_ora = sum(s["events"] for s in ora["steps"])
@@ -166,6 +166,20 @@ def child(args):
         sc = random_scenario(rs, jammers=1, fixed_payload=1500, spread=args.spread, factor=10000)
         tape = H.random_actions(args.steps, seed=args.seed + 7000)
         return run_case_m(sc, tape, "mode M long-packet seed %d" % args.seed, seed=args.seed + 79)
+    if args.case in ("mobilityjam", "maskmobilityjam"):
+        # devices jump before every other step while a PHY-only sender keeps the band busy:
+        # SimplePhy._onAttenuationChange for the transmissions that are on the air
+        sc = random_scenario(rs, jammers=1, spread=3.0)
+        sc["bands"][0]["devices"][3]["interval"] = float(rs.uniform(0.008, 0.02))
+        tape = H.random_actions(args.steps, seed=args.seed + 9000)
+        moves = {}
+        for t in range(1, args.steps, 2):
+            devs = sorted(set(int(v) for v in rs.randint(4, size=int(rs.randint(1, 4)))))
+            moves[t] = [(0, d, float(rs.uniform(-3, 3)), float(rs.uniform(-3, 3))) for d in devs]
+        if args.case == "mobilityjam":
+            return run_case(sc, tape, "mobility with transmissions on the air, seed %d" % args.seed, moves=moves)
+        return run_case_m(sc, tape, "mode M mobility with transmissions on the air, seed %d" % args.seed,
+                          seed=args.seed + 80, moves=moves)
     if args.case == "multiband":
         sc = random_scenario(rs, nbands=4, jammers=1, spread=args.spread)
         tapes = [H.random_actions(args.steps, seed=args.seed + 4000 + b) for b in range(4)]
@@ -203,7 +217,8 @@ def main():
     nseeds = 2 if args.quick else 6
     for sd in range(nseeds):
         plan += [("positions", sd, 200), ("jammer", sd, 200), ("long", sd, 40), ("multiband", sd, 80),
-                 ("maskdefault", sd, 120), ("maskjammer", sd, 120), ("masklong", sd, 20)]
+                 ("maskdefault", sd, 120), ("maskjammer", sd, 120), ("masklong", sd, 20),
+                 ("mobilityjam", sd, 120), ("maskmobilityjam", sd, 80)]
     failed = 0
     for case, sd, steps in plan:
         rc = subprocess.call([sys.executable, os.path.abspath(__file__), "--case", case,
