@@ -228,6 +228,7 @@ struct Sim {
 
     double now;
     uint32_t seq;                       // creation counter of timed events (the eid order)
+    int pchg;                           // bit p: PHY p's power sum changed since its BER was last evaluated
     int fault;
     uint32_t ties;                      // exact-time ties between independent events (diagnostic)
 
@@ -313,7 +314,7 @@ struct Event {
 template <int D, int NS, int NJ, class ST>
 GW_HD void init_sim(Sim<D, NS, NJ, ST> &s, double thermal)
 {
-    s.now = 0.0; s.seq = 0; s.fault = 0; s.ties = 0;
+    s.now = 0.0; s.seq = 0; s.fault = 0; s.ties = 0; s.pchg = -1;
     GW_UNROLL
     for (int p = 0; p < D; ++p) {
         s.P[p] = thermal; s.sphase[p] = S_IDLE; s.tEv[p] = 0; s.sEv[p] = 0;
@@ -852,6 +853,7 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
                 if (p == d) continue;
                 const double rp = srx_at<D>(srx, p, d);
                 s.P[p] += rp;
+                if (rp != 0.0) s.pchg |= 1 << p;
                 if (s.rxOf[p] >= 0 && rp != 0.0) {
                     const bool completed = s.now >= get_at(s.tStop, s.rxOf[p]);
                     if (!completed) berMask |= 1 << p;
@@ -875,8 +877,16 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
             for (int p = 0; p < D; ++p) {
                 if (s.rxOf[p] != d || s.rxSec[p] != 0) continue;
                 if (decide_rec(s, P, p, 0, hdrBits)) {
+                    // _resetBitErrorCounter, then _updateBitErrorRate (simple_stack.py:248-250): with the
+                    // power sum unchanged since the last evaluation the same (S, N) gives the same value
+                    const double same = s.ber[p];
                     s.rxSec[p] = 1; s.err[p] = 0; s.ber[p] = 0.0; s.tReset[p] = s.now; s.segT0[p] = s.now;
-                    berMask |= 1 << p;
+                    if ((s.pchg >> p) & 1) {
+                        berMask |= 1 << p;
+                    } else {
+                        s.ber[p] = same;
+                        trace_rec(s, REC_BER, s.now, p, same, 0.0, 0.0, 0.0);
+                    }
                 } else {
                     rx_clear(s, p);
                     if (s.sphase[p] == S_WAITRX) wake |= 1 << p;
@@ -900,6 +910,7 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
                 if (p == d) continue;
                 const double rp = srx_at<D>(srx, p, d);
                 s.P[p] += -rp;
+                if (rp != 0.0) s.pchg |= 1 << p;
                 if (s.rxOf[p] >= 0 && rp != 0.0) {
                     if (s.rxOf[p] == d) {
                         // `if not t.completed: _updateBitErrorRate(t)` with the power entry
@@ -1028,6 +1039,7 @@ GW_HD void update_bers(Sim<D, NS, NJ, ST> &s, const Params &P, int berMask, cons
             memo.put(S, N, ber);
         }
         s.ber[p] = ber;
+        s.pchg &= ~(1 << p);
         trace_rec(s, REC_BER, s.now, p, ber, 0.0, 0.0, 0.0);
     }
 }
@@ -1330,6 +1342,7 @@ GW_HD bool isolated_tx(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams 
         set_at(s.txSeq, d, get_at(s.txSeq, d) + txs);
         GW_UNROLL
         for (int p = 0; p < D; ++p) s.P[p] = Pc[p];
+        s.pchg = -1;
     }
     return any;
 }
@@ -1457,6 +1470,7 @@ GW_HD void received_power_change(Sim<D, NS, NJ, ST> &s, const Params &P, int p, 
                                  const Masks &masks, const Memo &memo)
 {
     set_at(s.P, p, get_at(s.P, p) + delta);                 // updateReceivedPower (priority 1)
+    s.pchg |= 1 << p;
     const int e = get_at(s.rxOf, p);
     if (e < 0 || delta == 0.0) return;                      // onReceivedPowerChange of a running reception
     if (MODE == MODE_R) {
@@ -1480,6 +1494,7 @@ GW_HD void received_power_change(Sim<D, NS, NJ, ST> &s, const Params &P, int p, 
         memo.put(S, N, ber);
     }
     set_at(s.ber, p, ber);
+    s.pchg &= ~(1 << p);
     trace_rec(s, REC_BER, s.now, p, ber, 0.0, 0.0, 0.0);
 }
 

@@ -275,6 +275,7 @@ __device__ __forceinline__ bool load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs 
 {
     const long long n = st.nsim;
     s.now = now;
+    s.pchg = -1;            // not kept across steps: the first BER of a reception in flight is re-evaluated
     uint4 v = ld_chunk(st.hot, n, H_P01, i);
     s.P[0] = lo_d(v); s.P[1] = hi_d(v);
     v = ld_chunk(st.hot, n, H_P23, i);
