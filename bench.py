@@ -270,6 +270,37 @@ def cfg4_multiband(dev_t, steps=64):
             "transmissions_per_env_step": float(st[6]) / steps / n, "deliveries_per_env_step": float(st[1] + st[2]) / steps / n}
 
 
+def cfg5_pendulum(dev_t, steps=32):
+    """
+    BASELINE configs[4] on ONE GPU's share: the networked inverted-pendulum env (sensor / controller
+    band assignment, in-kernel RK4 plant; PARITY UNPINNED), 131 072 envs.
+    """
+    import torch
+    import gymwipe_b200
+    n = 131072
+    env = gymwipe_b200.make('InvertedPendulum-v0', num_envs=n, device=dev_t, strict=False)
+    g = torch.Generator(device=dev_t).manual_seed(5)
+    a_dev = torch.randint(0, 2, (steps + 4, n), generator=g, device=dev_t, dtype=torch.int32)
+    a_dur = torch.randint(1, 20, (steps + 4, n), generator=g, device=dev_t, dtype=torch.int32)
+    stream = torch.cuda.current_stream(dev_t)
+    for t in range(4):
+        env.step({"device": a_dev[t], "duration": a_dur[t]})
+    torch.cuda.synchronize(dev_t)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(4, steps + 4):
+        env.step({"device": a_dev[t], "duration": a_dur[t]})
+    e1.record(stream)
+    torch.cuda.synchronize(dev_t)
+    env.check()
+    ms = e0.elapsed_time(e1) / steps
+    th = env.plant_state()[2]
+    return {"workload": "configs[4] share of one GPU: networked inverted pendulum, %d envs, in-kernel RK4 plant "
+                        "(parity unpinned: the reference env is unconstructible)" % n,
+            "env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms,
+            "mean_abs_angle_deg": float(torch.rad2deg(th).abs().mean())}
+
+
 def cpu_baseline_run(target_seconds, threads=None):
     """The oracle port on the host cores, on a bounded sample of the same workload (steady state:
     the first BURN_IN_STEPS steps of every env are simulated too and their time is subtracted)."""
@@ -681,6 +712,8 @@ def own_arm(args, rank, world, local_rank):
             line["cfg3_long_packet_mode_m"] = cfg3_long_packet(dev_t)
             torch.cuda.empty_cache()
             line["cfg4_multiband"] = cfg4_multiband(dev_t)
+            torch.cuda.empty_cache()
+            line["cfg5_pendulum"] = cfg5_pendulum(dev_t)
         except Exception as exc:                      # extras must never take the headline down
             line["extras_error"] = repr(exc)
     if world == 1 and not args.no_cpu_baseline:
