@@ -401,6 +401,8 @@ def own_arm(args, rank, world, local_rank):
                               env_id_offset=(rank * M + b) * n, strict=False) for b in range(M)]
     for e in envs:
         e.reset()
+    for e in envs[1:]:
+        e.share_stats(envs[0])                          # one statistics vector per GPU (gw_share_stats)
 
     # synthetic action tapes for every launch, resident in HBM before the timed region
     g = torch.Generator(device=dev_t).manual_seed(1234 + rank)
@@ -468,10 +470,7 @@ def own_arm(args, rank, world, local_rank):
         torch.cuda.synchronize(dev_t)
         def reduce_stats():
             # K5 partial sums of all batches -> NCCL all-reduce on a side stream
-            buf = reducer.next_slot()
-            buf.zero_()
-            for e in envs:
-                buf += e.stats()
+            envs[0].stats(out=reducer.next_slot())
             reducer.submit()
         if reducer is not None:
             # first use loads the small kernels and sets up NCCL's channels: not part of stepping
@@ -536,6 +535,7 @@ def own_arm(args, rank, world, local_rank):
     flushed_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     del flush
     for e in envs[1:]:
+        e.share_stats(None)
         e.close()
     del envs, graphs, gw
     torch.cuda.empty_cache()
@@ -697,7 +697,7 @@ def own_arm(args, rank, world, local_rank):
                                       "int32 obs | float32 reward | uint8 done out)"},
                 "wide_api": {"value": total_envs * KE / e2e_wide_s, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 17 * n,
                              "api": "CounterTrafficEnv.step_host -> gw_step_host (int64 obs, float64 reward, uint8 done)"}},
-        "gpu_launches": K + (M * ((len(chunk_cnt) + STATS_EVERY_CHUNKS - 1) // STATS_EVERY_CHUNKS) if world > 1 else 0),   # step kernels (+ statistics copies when sharded)
+        "gpu_launches": K + (((len(chunk_cnt) + STATS_EVERY_CHUNKS - 1) // STATS_EVERY_CHUNKS) if world > 1 else 0),   # step kernels (+ statistics copies when sharded)
         "clocks": clocks,
         "wall_s_timed_loop": wall,
     }

@@ -113,6 +113,7 @@ _SIGNATURES = {
     "gw_step_host_compact_async": (C.c_int, [_VP, _VP, _VP, _VP]),
     "gw_check": (C.c_int, [_VP, _VP]),
     "gw_stats": (C.c_int, [_VP, _VP, C.c_int, _VP]),
+    "gw_share_stats": (C.c_int, [_VP, _VP]),
     "gw_read_state": (C.c_int, [_VP, C.c_int, _VP, _VP]),
     "gw_set_masks": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP]),
     "gw_fspl_attenuation": (C.c_int, [_VP, _VP, _VP, _VP, C.c_double, _VP, C.c_int64, _VP]),

@@ -117,6 +117,7 @@ struct gw_handle {
     Layout layout;
     void *owned_state;
     double *stats;          // device [8]
+    double *stats_use;      // accumulators the step kernels add to: `stats`, or another handle's (gw_share_stats)
     int *errflag;           // device [4]: code, sim, fault, -
     double power_dbm[kMaxBands][kMaxDev];
     double default_pos[kMaxBands][kMaxDev][2];
@@ -1585,6 +1586,7 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
         if (e != cudaSuccess) { cudaFree(stg); gw_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
     }
     h->errflag = (int *)(h->stats + 8);
+    h->stats_use = h->stats;
     h->d_obs = (long long *)stg;                            // base of the staging allocation
     h->d_rew = (double *)(h->d_obs + nsim);
     int32_t *p32 = (int32_t *)(h->d_rew + nsim);
@@ -1699,7 +1701,7 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     A.st = h->st;
     A.device = device; A.duration = duration;
     A.obs = (long long *)obs; A.reward = reward; A.done = done;
-    A.stats = h->stats; A.errflag = h->errflag;
+    A.stats = h->stats_use; A.errflag = h->errflag;
     A.obs32 = obs32; A.reward32 = reward32;
     A.act8 = act8; A.res32 = res32;
     A.sim_begin = sim_begin; A.sim_end = sim_end < 0 ? h->st.nsim : sim_end;
@@ -1898,8 +1900,16 @@ int gw_stats(gw_handle *h, double *out8, int clear, void *stream)
 {
     if (!h || !out8) return fail(GW_E_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    stats_copy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->stats, out8, clear);
+    stats_copy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->stats_use, out8, clear);
     CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_share_stats(gw_handle *h, gw_handle *with)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    if (with && with->device != h->device) return fail(GW_E_INVALID, "handles on different devices cannot share statistics");
+    h->stats_use = with ? with->stats_use : h->stats;
     return GW_OK;
 }
 

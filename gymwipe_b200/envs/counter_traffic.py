@@ -276,6 +276,15 @@ class CounterTrafficEnv(BaseEnv):
             N.check(self._lib.gw_stats(self._handle, out.data_ptr(), 1 if clear else 0, self._stream()))
         return out
 
+    def share_stats(self, other):
+        """
+        Accumulate this env's step statistics into ``other``'s vector (``gw_share_stats``): several env
+        batches on one GPU then need one :meth:`stats` call in front of the all-reduce.  ``None`` restores
+        this env's own accumulators.  Keep ``other`` alive while sharing.
+        """
+        N.check(self._lib.gw_share_stats(self._handle, other._handle if other is not None else None))
+        self._stats_owner = other
+
     def set_positions(self, positions):
         """
         Per-env device positions ``[num_envs, n_bands, 4, 2]`` (float64, CUDA).  At construction the

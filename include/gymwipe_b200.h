@@ -216,6 +216,13 @@ int gw_check(gw_handle *h, void *stream);
  * (agents/dqn_counter_traffic.py:70) -- and the NCCL all-reduce when envs are sharded. */
 int gw_stats(gw_handle *h, double *out8, int clear, void *stream);
 
+/* Several handles on one device (e.g. env batches stepped round-robin) can accumulate into ONE
+ * statistics vector: after gw_share_stats(h, with) the step kernels of `h` add to the accumulators of
+ * `with`, and gw_stats of either handle reads / clears them -- one copy instead of one per handle in
+ * front of the all-reduce.  `with == NULL` restores the handle's own accumulators.  `with` must outlive
+ * the sharing. */
+int gw_share_stats(gw_handle *h, gw_handle *with);
+
 /* Read-back of the structure-of-arrays state (tests, tracing, render()): converts one
  * field to a dense device float64 array (integers are exact below 2^53).  n_sims =
  * n_envs * n_bands, sim index = env * n_bands + band. */

@@ -479,6 +479,31 @@ def test_stats_epilogue():
     assert tot[4] == n * T and tot[6] == o["counts"][:, 0, 0].sum()
 
 
+def test_shared_stats_across_handles():
+    """gw_share_stats: two env batches accumulate into one statistics vector."""
+    from gymwipe_b200.scenario import default_scenario_dict
+    sc = default_scenario_dict()
+    rs = np.random.RandomState(19)
+    n, T = 300, 20
+    tapes = [random_tapes(rs, T, n, 1) for _ in range(2)]
+    refs = [O.run_batch(sc, d, u) for d, u in tapes]
+    envs = [make_env(sc, n, strict=False) for _ in range(2)]
+    for e in envs:
+        e.reset()
+    envs[1].share_stats(envs[0])
+    envs[0].stats()
+    for t in range(T):
+        for e, (d, u) in zip(envs, tapes):
+            e.step({"device": torch.as_tensor(d[t, :, 0]).cuda(), "duration": torch.as_tensor(u[t, :, 0]).cuda()})
+    tot = envs[0].stats().cpu().numpy()
+    assert tot[0] == sum(r["reward"].sum() for r in refs)
+    assert tot[4] == 2 * n * T and tot[6] == sum(r["counts"][:, 0, 0].sum() for r in refs)
+    assert envs[1].stats().cpu().numpy()[4] == 0            # the shared vector was cleared by the read above
+    envs[1].share_stats(None)
+    envs[1].step({"device": torch.as_tensor(tapes[1][0][0, :, 0]).cuda(), "duration": torch.as_tensor(tapes[1][1][0, :, 0]).cuda()})
+    assert envs[1].stats().cpu().numpy()[4] == n and envs[0].stats().cpu().numpy()[4] == 0
+
+
 def test_full_size_properties_65536():
     """BASELINE configs[1]: 65,536 envs.  Size-independent properties + a strided oracle sample."""
     from gymwipe_b200.scenario import default_scenario_dict
