@@ -111,3 +111,21 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "gw_oracle" not in text and "hostsim" not in text.replace("tests/hostsim", ""), f
+
+
+def test_compact_result_word_layout():
+    """The packed result word of gw_step_host_compact (include/gymwipe_b200.h: GW_COMPACT_*) and its
+    Python decoder agree: obs in bits 0..16, reward + 16 in bits 17..21, done in bit 22."""
+    import numpy as np
+    import torch
+    from gymwipe_b200.envs.counter_traffic import CounterTrafficEnv
+    obs = np.array([0, 65534, 65536, 65538, 131071], np.int64)
+    rew = np.array([-10, -2, 0, 2, 10], np.int64)
+    done = np.array([0, 1, 0, 1, 1], np.int64)
+    words = (obs | ((rew + 16) << 17) | (done << 22)).astype(np.uint32).view(np.int32)
+    o, r, d = CounterTrafficEnv.unpack_compact(torch.from_numpy(words.copy()))
+    assert o.tolist() == obs.tolist() and r.tolist() == [float(x) for x in rew] and d.tolist() == [bool(x) for x in done]
+    text = open(os.path.join(ROOT, "include", "gymwipe_b200.h")).read()
+    assert "#define GW_COMPACT_OBS(w)    ((int32_t)((w) & 0x1FFFFu))" in text
+    assert "#define GW_COMPACT_REWARD(w) ((int32_t)(((w) >> 17) & 31u) - 16)" in text
+    assert "#define GW_COMPACT_DONE(w)   ((int32_t)(((w) >> 22) & 1u))" in text
