@@ -1459,7 +1459,9 @@ GW_HD void run_until_time(Sim<D, NS, NJ, ST> &s, const Params &P, const BandPara
 // notification after their creation to their completion: exactly while the sender is in S_HDR / S_PAY.
 // The models of a device are notified in Python-set order (simtools.py:255); they are visited by
 // ascending partner index here, which only matters for the rounding of the MOVING PHY's own power sum
-// when two or more other devices transmit at that instant.
+// when two or more other devices transmit at that instant.  Models are created lazily (see below):
+// a pair neither of whose devices has transmitted yet has no model, its table entry follows the
+// positions without the threshold / coincidence rules.
 //
 // `Tab` gives access to the band-sim's attenuation (dB) and received-power (mW) tables:
 //   att(p, d), set_att(p, d, v), srx(p, d), set_srx(p, d, v), view() -> object for srx_at<D>()
@@ -1512,6 +1514,18 @@ GW_HD void move_devices(Sim<D, NS, NJ, ST> &s, const Params &P, const double *po
             if (j == m) continue;
             const double dx = cur[2 * m] - cur[2 * j], dy = cur[2 * m + 1] - cur[2 * j + 1];
             const double dist = sqrt(dx * dx + dy * dy);                                    // devices/core.py:88-95
+            // The model of a pair is created lazily, at the first transmission one of the two devices
+            // sends (SimplePhy._getAttenuationModelByTransmission -> FrequencyBand.getAttenuationModel,
+            // physical.py:576-594).  Until then nobody listens to position changes and the model will be
+            // computed from the positions of that moment -- without the threshold, 0 dB for coinciding
+            // devices: the table simply follows the positions (fspl_db).
+            if (get_at(s.txSeq, m) == 0u && get_at(s.txSeq, j) == 0u) {
+                const double fresh = (dx == 0.0 && dy == 0.0) ? 0.0 : 20 * log10(dist) + 20 * log10(frequency) - 147.55;
+                tab.set_att(m, j, fresh); tab.set_att(j, m, fresh);
+                tab.set_srx(j, m, rx_power_mw(powerDbm[m], fresh));
+                tab.set_srx(m, j, rx_power_mw(powerDbm[j], fresh));
+                continue;
+            }
             if (!(dist < 3000.0)) continue;                                                 // STANDBY_THRESHOLD
             if (dx == 0.0 && dy == 0.0) continue;                                           // _update returns early
             const double att = 20 * log10(dist) + 20 * log10(frequency) - 147.55;

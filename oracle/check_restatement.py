@@ -180,6 +180,30 @@ def child(args):
             return run_case(sc, tape, "mobility with transmissions on the air, seed %d" % args.seed, moves=moves)
         return run_case_m(sc, tape, "mode M mobility with transmissions on the air, seed %d" % args.seed,
                           seed=args.seed + 80, moves=moves)
+    if args.case == "mobilityquirks":
+        # the corner cases of PositionalAttenuationModel / FsplAttenuation._update: a device jumps beyond
+        # STANDBY_THRESHOLD (the model stops following), onto another device's position (the model keeps its
+        # value) and back, while a PHY-only sender keeps the band busy
+        sc = random_scenario(rs, jammers=1, spread=3.0)
+        sc["bands"][0]["devices"][3]["interval"] = float(rs.uniform(0.008, 0.02))
+        tape = H.random_actions(args.steps, seed=args.seed + 9500)
+        devs = sc["bands"][0]["devices"]
+        moves = {}
+        for t in range(1, args.steps, 2):
+            d = int(rs.randint(4))
+            kind = int(rs.randint(4))
+            if kind == 0:
+                x, y = float(rs.uniform(4000, 6000)), float(rs.uniform(-10, 10))          # far away
+            elif kind == 1:
+                o = int((d + 1 + rs.randint(3)) % 4)                                       # onto another device
+                x, y = float(devs[o]["x"]), float(devs[o]["y"])
+            else:
+                x, y = float(rs.uniform(-3, 3)), float(rs.uniform(-3, 3))
+            devs[d] = dict(devs[d], x=x, y=y)                                               # track for "onto another device"
+            moves[t] = [(0, d, x, y)]
+        sc0 = random_scenario(np.random.RandomState(args.seed), jammers=1, spread=3.0)      # the scenario as constructed
+        sc0["bands"][0]["devices"][3]["interval"] = sc["bands"][0]["devices"][3]["interval"]
+        return run_case(sc0, tape, "mobility corner cases, seed %d" % args.seed, moves=moves)
     if args.case == "multiband":
         sc = random_scenario(rs, nbands=4, jammers=1, spread=args.spread)
         tapes = [H.random_actions(args.steps, seed=args.seed + 4000 + b) for b in range(4)]
@@ -218,7 +242,7 @@ def main():
     for sd in range(nseeds):
         plan += [("positions", sd, 200), ("jammer", sd, 200), ("long", sd, 40), ("multiband", sd, 80),
                  ("maskdefault", sd, 120), ("maskjammer", sd, 120), ("masklong", sd, 20),
-                 ("mobilityjam", sd, 120), ("maskmobilityjam", sd, 80)]
+                 ("mobilityjam", sd, 120), ("maskmobilityjam", sd, 80), ("mobilityquirks", sd, 100)]
     failed = 0
     for case, sd, steps in plan:
         rc = subprocess.call([sys.executable, os.path.abspath(__file__), "--case", case,

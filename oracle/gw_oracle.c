@@ -1145,6 +1145,18 @@ int gwo_set_position(gwo_sim *s, int band, int dev, double x, double y)
     for (int j = 0; j < B->ndev; j++) {
         if (j == dev) continue;
         double d = sqrt(pow(B->dev[dev].x - B->dev[j].x, 2.0) + pow(B->dev[dev].y - B->dev[j].y, 2.0));
+        /* The model of a pair is created lazily, at the first transmission one of the two devices sends
+         * (SimplePhy._getAttenuationModelByTransmission -> FrequencyBand.getAttenuationModel,
+         * physical.py:576-594); until then nobody listens to position changes, and the model will be
+         * computed from the positions of THAT moment -- without the threshold, and with 0 dB for
+         * coinciding devices (AttenuationModel.__init__ + FsplAttenuation._update). */
+        if (B->dev[dev].tx_seq == 0 && B->dev[j].tx_seq == 0) {
+            double fresh = 0.0;
+            if (!(B->dev[dev].x == B->dev[j].x && B->dev[dev].y == B->dev[j].y))
+                fresh = 20 * log10(d) + 20 * log10(B->frequency) - 147.55;
+            B->att[dev][j] = fresh; B->att[j][dev] = fresh;
+            continue;
+        }
         if (!(d < 3000.0)) continue;                              /* STANDBY_THRESHOLD, physical.py:371 */
         if (B->dev[dev].x == B->dev[j].x && B->dev[dev].y == B->dev[j].y) continue;   /* _update returns early */
         /* devices[0] / devices[1] order of the model is the frozenset order: the formula is symmetric */

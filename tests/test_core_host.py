@@ -244,3 +244,35 @@ def test_core_moving_devices_random_vs_oracle(seed):
         assert [s["obs"] for s in res["steps"]] == list(h["obs"][:, 0, 0])
         assert [s["reward"] for s in res["steps"]] == list(h["reward"][:, 0, 0])
         assert [s["now"] for s in res["steps"]] == list(h["now"][:, 0])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_core_moving_devices_corner_cases_vs_oracle(seed):
+    """Jumps beyond STANDBY_THRESHOLD, onto another device's position and back, before and after the pair's
+    attenuation model exists (the reference creates it at the first transmission of either device); the
+    oracle is pinned on these cases by oracle/check_restatement.py --case mobilityquirks."""
+    rs = np.random.RandomState(7300 + seed)
+    sc = random_scenario(rs, jammers=1, spread=3.0)
+    sc["bands"][0]["devices"][3]["interval"] = float(rs.uniform(0.008, 0.02))
+    nsteps = 80
+    dev, dur = random_tapes(rs, nsteps, 1, 1)
+    pos = [(d["x"], d["y"]) for d in sc["bands"][0]["devices"]]
+    moves = {}
+    for t in range(0, nsteps, 2):                      # from before the very first step on
+        d = int(rs.randint(4))
+        kind = int(rs.randint(4))
+        if kind == 0:
+            x, y = float(rs.uniform(4000, 6000)), float(rs.uniform(-10, 10))
+        elif kind == 1:
+            x, y = pos[int((d + 1 + rs.randint(3)) % 4)]
+        else:
+            x, y = float(rs.uniform(-3, 3)), float(rs.uniform(-3, 3))
+        pos[d] = (x, y)
+        moves[t] = [(0, d, x, y)]
+    acts = [{"device": int(dev[t, 0, 0]), "duration": int(dur[t, 0, 0])} for t in range(nsteps)]
+    res = O.run_tape(O.Oracle(sc), acts, do_reset=True, moves=moves)
+    h = HS.run(sc, dev, dur, do_reset=True, moves=moves)
+    assert h["rc"] == 0
+    assert [s["obs"] for s in res["steps"]] == list(h["obs"][:, 0, 0])
+    assert [s["reward"] for s in res["steps"]] == list(h["reward"][:, 0, 0])
+    assert [s["now"] for s in res["steps"]] == list(h["now"][:, 0])

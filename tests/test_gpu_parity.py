@@ -274,6 +274,53 @@ def test_cuda_moving_devices_random_vs_oracle(mode):
         assert [s["now"] for s in res["steps"]] == list(got_now[:, e]), e
 
 
+def test_cuda_moving_devices_corner_cases_vs_oracle():
+    """Jumps beyond STANDBY_THRESHOLD, onto another device's position and back, from the first step on
+    (lazily created attenuation models): move_kernel vs the oracle, one env per random move sequence."""
+    rs = np.random.RandomState(7400)
+    sc = random_scenario(rs, jammers=1, spread=3.0)
+    sc["bands"][0]["devices"][3]["interval"] = 0.0125
+    n, T = 10, 60
+    dev, dur = random_tapes(rs, T, n, 1)
+    devs = sc["bands"][0]["devices"]
+    pos = torch.zeros((n, 1, 4, 2), dtype=torch.float64)
+    for d, dv in enumerate(devs):
+        pos[:, 0, d, 0], pos[:, 0, d, 1] = dv["x"], dv["y"]
+    moves = [{} for _ in range(n)]
+    for e in range(n):
+        cur = [(dv["x"], dv["y"]) for dv in devs]
+        for t in range(1, T, 2):
+            d = int(rs.randint(4))
+            kind = int(rs.randint(4))
+            if kind == 0:
+                x, y = float(rs.uniform(4000, 6000)), float(rs.uniform(-10, 10))
+            elif kind == 1:
+                x, y = cur[int((d + 1 + rs.randint(3)) % 4)]
+            else:
+                x, y = float(rs.uniform(-3, 3)), float(rs.uniform(-3, 3))
+            cur[d] = (x, y)
+            moves[e][t] = [(0, d, x, y)]
+    env = make_env(sc, n, strict=False, positions=pos.cuda())
+    env.reset()
+    got_obs = np.zeros((T, n), np.int64)
+    got_now = np.zeros((T, n))
+    for t in range(T):
+        if t % 2 == 1:
+            for e in range(n):
+                for (_, d, x, y) in moves[e][t]:
+                    pos[e, 0, d, 0], pos[e, 0, d, 1] = x, y
+            env.set_positions(pos.cuda())
+        o, r, dn, _ = env.step({"device": torch.as_tensor(dev[t, :, 0]).cuda(), "duration": torch.as_tensor(dur[t, :, 0]).cuda()})
+        got_obs[t] = o.cpu().numpy()
+        got_now[t] = env.read_state(0).cpu().numpy()
+    env.check()
+    for e in range(n):
+        acts = [{"device": int(dev[t, e, 0]), "duration": int(dur[t, e, 0])} for t in range(T)]
+        res = O.run_tape(O.Oracle(sc), acts, do_reset=True, moves=moves[e])
+        assert [s["obs"] for s in res["steps"]] == list(got_obs[:, e]), e
+        assert [s["now"] for s in res["steps"]] == list(got_now[:, e]), e
+
+
 def _with_positions(sc, pos_env):
     import copy
     sc = copy.deepcopy(sc)
