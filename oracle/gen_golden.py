@@ -37,6 +37,7 @@ CASES = {
     "multiband_seed9": ("multiband", 9, 24),
     "mobility_seed13": ("mobility", 13, 80),
     "mobility_inflight_seed17": ("mobilityjam", 17, 60),
+    "mobility_quirks_seed4": ("mobilityquirks", 4, 70),
     "modeM_jammer_seed11": ("maskjammer", 11, 40),
     "modeM_default_seed12": ("maskdefault", 12, 60),
 }
@@ -71,6 +72,9 @@ def make_case(kind, seed, steps):
         sc, tape = CR.random_scenario(rs, jammers=1, spread=2.0), H.random_actions(steps, seed=seed + 8500)
         sc["bands"][0]["devices"][3]["interval"] = 0.0123
         sc["bands"][0]["devices"][3]["payload"] = 120
+    elif kind == "mobilityquirks":
+        sc, tape = CR.random_scenario(rs, jammers=1, spread=3.0), H.random_actions(steps, seed=seed + 9500)
+        sc["bands"][0]["devices"][3]["interval"] = 0.0131
     elif kind == "maskjammer":
         sc, tape = CR.random_scenario(rs, jammers=1, spread=2.5), H.random_actions(steps, seed=seed + 6000)
     elif kind == "maskdefault":
@@ -104,6 +108,23 @@ def child(name):
         for t in range(1, steps, 2):
             devs = sorted(set(int(v) for v in mrs.randint(4, size=int(mrs.randint(1, 3)))))
             moves[t] = [(0, d, float(mrs.uniform(-2.5, 2.5)), float(mrs.uniform(-2.5, 2.5))) for d in devs]
+    if kind == "mobilityquirks":
+        # jumps beyond STANDBY_THRESHOLD, onto another device's position and back -- from before the first
+        # step on, i.e. also while the pair's attenuation model does not exist yet
+        mrs = np.random.RandomState(seed + 2)
+        cur = [(d["x"], d["y"]) for d in sc["bands"][0]["devices"]]
+        moves = {}
+        for t in range(0, steps, 2):
+            d = int(mrs.randint(4))
+            k = int(mrs.randint(4))
+            if k == 0:
+                x, y = float(mrs.uniform(4000, 6000)), float(mrs.uniform(-10, 10))
+            elif k == 1:
+                x, y = cur[int((d + 1 + mrs.randint(3)) % 4)]
+            else:
+                x, y = float(mrs.uniform(-3, 3)), float(mrs.uniform(-3, 3))
+            cur[d] = (x, y)
+            moves[t] = [(0, d, float(x), float(y))]
     trace = H.run_tape(env, tape, tr, do_reset=do_reset, moves=moves)
     doc = {"name": name, "kind": kind, "seed": seed, "do_reset": do_reset,
            "mode": "M" if mode_m else "R", "mask_seed": MASK_SEED if mode_m else None,

@@ -206,7 +206,7 @@ def test_airtime_table_equals_the_division():
         assert L.hs_airtime(k) == (k * 8) / (0.75 * 133.33333e3)
 
 
-@pytest.mark.parametrize("name", ["mobility_seed13", "mobility_inflight_seed17"])
+@pytest.mark.parametrize("name", ["mobility_seed13", "mobility_inflight_seed17", "mobility_quirks_seed4"])
 def test_core_moving_devices_match_reference_golden(name):
     """Devices move between steps; in the second golden transmissions are on the air at that instant
     (the reference's SimplePhy._onAttenuationChange): gw_core.cuh::move_devices."""

@@ -205,7 +205,7 @@ def test_cuda_per_env_positions():
                 assert abs(got - want) <= BER_RTOL * abs(want)
 
 
-@pytest.mark.parametrize("name", ["mobility_seed13", "mobility_inflight_seed17"])
+@pytest.mark.parametrize("name", ["mobility_seed13", "mobility_inflight_seed17", "mobility_quirks_seed4"])
 def test_cuda_moving_devices_match_reference_golden(name):
     """gw_set_positions between steps vs the reference's Position.set (goldens from the reference); in
     the second golden transmissions are on the air when devices move (SimplePhy._onAttenuationChange)."""

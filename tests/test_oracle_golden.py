@@ -37,7 +37,7 @@ def test_restatement_matches_reference_trace(name):
         assert ora.near_ties == 0          # no decider threshold is within rounding distance
 
 
-@pytest.mark.parametrize("name", ["mobility_seed13", "mobility_inflight_seed17"])
+@pytest.mark.parametrize("name", ["mobility_seed13", "mobility_inflight_seed17", "mobility_quirks_seed4"])
 def test_restatement_matches_reference_with_moving_devices(name):
     """Devices move between steps (Position.set in the reference); goldens from the reference.  In the
     second case a PHY-only sender is regularly on the air when devices move: the reference's
