@@ -49,6 +49,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "gw_oracle.h"
 
@@ -1238,6 +1239,19 @@ int gwo_run_batch_m(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_res
                     uint64_t seed, int64_t env_id_offset, const uint32_t *fed_words, int fed_slots,
                     int fed_words_per_row);
 
+/* Timing support for benchmarks (bench.py): the seconds THIS thread spends in steps t >= time_from of the
+ * envs it simulates are accumulated (the envs are simulated one after the other, so the steps before
+ * time_from -- a burn-in -- are excluded per env). */
+static __thread int g_time_from = -1;
+static __thread double g_timed_seconds = 0.0;
+
+static double mono_seconds(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 int gwo_run_batch(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_reset,
                   const double *pos, const int32_t *dev_tape, const int32_t *dur_tape,
                   int64_t *obs, double *reward, uint8_t *done, double *now, int64_t *counts,
@@ -1305,7 +1319,9 @@ int gwo_run_batch_m(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_res
         }
         if (do_reset) gwo_reset(s, NULL);
         int64_t o[GWO_MAXBAND]; double r[GWO_MAXBAND]; uint8_t dn[GWO_MAXBAND];
+        double t_begin = 0.0;
         for (int t = 0; t < nsteps; t++) {
+            if (t == g_time_from) t_begin = mono_seconds();
             size_t base = ((size_t)t * nenv + e) * nb;
             int rc = gwo_step(s, dev_tape + base, dur_tape + base, o, r, dn);
             if (rc) { rc_all = rc; break; }
@@ -1316,6 +1332,7 @@ int gwo_run_batch_m(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_res
             }
             if (now) now[(size_t)t * nenv + e] = s->now;
         }
+        if (g_time_from >= 0 && g_time_from < nsteps && !rc_all) g_timed_seconds += mono_seconds() - t_begin;
         if (counts) {
             for (int b = 0; b < nb; b++) {
                 int64_t *c = counts + ((size_t)e * nb + b) * (1 + GWO_MAXDEV);
@@ -1326,4 +1343,19 @@ int gwo_run_batch_m(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_res
         if (rc_all) return rc_all;
     }
     return 0;
+}
+
+/* gwo_run_batch (mode R) that also reports the seconds this thread spent in steps t >= time_from */
+int gwo_run_batch_timed(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_reset,
+                        const double *pos, const int32_t *dev_tape, const int32_t *dur_tape,
+                        int64_t *obs, double *reward, uint8_t *done, double *now, int64_t *counts,
+                        int64_t env_begin, int64_t env_end, int time_from, double *seconds_out)
+{
+    g_time_from = time_from;
+    g_timed_seconds = 0.0;
+    int rc = gwo_run_batch_m(sc, nenv, nsteps, do_reset, pos, dev_tape, dur_tape, obs, reward, done, now, counts,
+                             env_begin, env_end, 0, 0, NULL, 0, 0);
+    if (seconds_out) *seconds_out = g_timed_seconds;
+    g_time_from = -1;
+    return rc;
 }

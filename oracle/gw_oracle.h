@@ -97,6 +97,13 @@ int gwo_run_batch(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_reset
 void gwo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void gwo_use_philox_masks(gwo_sim *s, uint64_t seed, int64_t env_id);
 void gwo_use_fed_masks(gwo_sim *s, const uint32_t *words, int slots, int words_per_row, int64_t env_index);
+/* gwo_run_batch (mode R) that also reports the seconds THIS thread spent in steps t >= time_from of the
+ * envs it simulated (benchmarks: a burn-in is excluded per env). */
+int gwo_run_batch_timed(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_reset,
+                        const double *pos, const int32_t *dev_tape, const int32_t *dur_tape,
+                        int64_t *obs, double *reward, uint8_t *done, double *now, int64_t *counts,
+                        int64_t env_begin, int64_t env_end, int time_from, double *seconds_out);
+
 int gwo_run_batch_m(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_reset,
                     const double *pos, const int32_t *dev_tape, const int32_t *dur_tape,
                     int64_t *obs, double *reward, uint8_t *done, double *now, int64_t *counts,

@@ -96,6 +96,9 @@ def lib():
         L.gwo_use_philox_masks.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
         L.gwo_use_fed_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64]
         L.gwo_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gwo_run_batch_timed.restype = C.c_int
+        L.gwo_run_batch_timed.argtypes = [C.POINTER(Scenario), C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 8 + \
+            [C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_double)]
         L.gwo_run_batch_m.restype = C.c_int
         L.gwo_run_batch_m.argtypes = [C.POINTER(Scenario), C.c_int64, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p,
@@ -288,7 +291,7 @@ def run_tape(oracle, actions, do_reset=True, moves=None):
 
 def run_batch(scenario, dev_tape, dur_tape, pos=None, do_reset=True, threads=None,
               want=("obs", "reward", "done", "now", "counts"), mode=MODE_R, seed=0, env_id_offset=0,
-              fed_words=None, fed_slots=0):
+              fed_words=None, fed_slots=0, time_from=None):
     """
     Run ``nenv`` independent envs for ``nsteps`` steps with ``threads`` host threads.
     ``dev_tape`` / ``dur_tape``: int32 ``[nsteps, nenv, nbands]`` (or ``[nsteps, nenv]``).
@@ -332,7 +335,19 @@ def run_batch(scenario, dev_tape, dur_tape, pos=None, do_reset=True, threads=Non
     bounds = np.linspace(0, nenv, threads + 1).astype(np.int64)
     rcs = [0] * threads
 
+    secs = [0.0] * threads
+
     def work(i):
+        if time_from is not None:
+            # mode R only: the seconds each thread spends in steps >= time_from (burn-in excluded per env)
+            out = C.c_double(0.0)
+            rcs[i] = L.gwo_run_batch_timed(C.byref(scenario), nenv, nsteps, 1 if do_reset else 0,
+                                           ptr(pos), ptr(dev_tape), ptr(dur_tape),
+                                           ptr(res.get("obs")), ptr(res.get("reward")), ptr(res.get("done")),
+                                           ptr(res.get("now")), ptr(res.get("counts")),
+                                           int(bounds[i]), int(bounds[i + 1]), int(time_from), C.byref(out))
+            secs[i] = out.value
+            return
         rcs[i] = L.gwo_run_batch_m(C.byref(scenario), nenv, nsteps, 1 if do_reset else 0,
                                    ptr(pos), ptr(dev_tape), ptr(dur_tape),
                                    ptr(res.get("obs")), ptr(res.get("reward")), ptr(res.get("done")),
@@ -351,4 +366,6 @@ def run_batch(scenario, dev_tape, dur_tape, pos=None, do_reset=True, threads=Non
         if rc:
             raise OracleFault(FAULTS.get(rc, str(rc)))
     res["threads"] = threads
+    if time_from is not None:
+        res["seconds"] = max(secs)         # the threads run side by side: the slowest one bounds the batch
     return res

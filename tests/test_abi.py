@@ -129,3 +129,22 @@ def test_compact_result_word_layout():
     assert "#define GW_COMPACT_OBS(w)    ((int32_t)((w) & 0x1FFFFu))" in text
     assert "#define GW_COMPACT_REWARD(w) ((int32_t)(((w) >> 17) & 31u) - 16)" in text
     assert "#define GW_COMPACT_DONE(w)   ((int32_t)(((w) >> 22) & 1u))" in text
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to the GPU arm) prints one JSON line
+    with the contract's keys and a plausible value even for a handful of steps."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "4",
+                          "--warmup", "3"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["steps"] == 4 and line["unit"] == "env-steps/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert 1e4 < line["value"] < 1e9                  # a CPU rate, not a timing artefact
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
