@@ -4,14 +4,16 @@ bench.py -- env-steps/sec of the batched CounterTrafficEnv hot path (BASELINE.js
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Own arm: N ranks (one per GPU; torchrun supplies RANK / LOCAL_RANK / WORLD_SIZE for N > 1), each
-owning an independent shard of 16 batches of 65,536 envs (BASELINE configs[1], weak scaling).  A
-"step" is ONE pass of the hot path over ONE batch (`CounterTrafficEnv.step` of its 65,536 envs = one
-launch of the fused step kernel); the batches are stepped round-robin so that every launch finds its
-inputs in HBM, not in L2 ("inputs larger than L2", no flush).  W warm-up launches, then EXACTLY K timed
-launches replayed from CUDA graphs, one CUDA-event pair around them on the launching stream, barrier +
-synchronize on both sides, max over ranks.  `e2e` is the same metric through `gw_step_host_packed`
-with pinned HOST buffers (H2D actions + D2H obs/reward/done inside the timed region).
+Own arm: N ranks (one per GPU; torchrun supplies RANK / LOCAL_RANK / WORLD_SIZE for N > 1), each owning
+an independent POPULATION of `--batches` (default 272) batches of 65,536 envs (BASELINE configs[1]; weak
+scaling).  One bench "step" is one `env.step` of EVERY env of the population: one launch of the fused step
+kernel per batch, the batches one after the other -- a batch is touched again only after all the others
+(gigabytes of other traffic), so every launch finds its inputs in HBM, not in L2 ("inputs larger than L2",
+no flush).  A step is ~2.5 ms of device time, so even the driver's `--steps 20` times > 50 ms.  W warm-up
+steps, then EXACTLY K timed steps replayed from CUDA graphs (one per step), one CUDA-event pair around them
+on the launching stream, barrier + synchronize on both sides, max over ranks.  `e2e` is the same metric
+through the C ABI with pinned HOST buffers (`gw_step_host_compact_many`: actions read / results written in
+place by the kernels, inside the timed region), timed for >= 60 ms.
 
 Reference arm (`--impl reference`): the reference's algorithm on the box's host cores -- the
 oracle port (plain-C restatement, pinned bit-exactly against the unmodified Python reference;
@@ -32,27 +34,28 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 ENVS_PER_GPU = 65536
-ROTATING_BATCHES = 16                  # independent 65,536-env batches stepped round-robin (inputs > L2)
+POPULATION_BATCHES = 272               # 65,536-env batches per GPU: one bench step = one env.step of all of them (~2.5 ms)
+E2E_BATCHES = 16                       # batches of the population stepped per host-buffer call (gw_step_host_compact_many)
 BURN_IN_STEPS = 128                    # steps of every env before the timed region (steady state, see own_arm)
 PRODUCTIVE_STEPS = 32                  # steps of every fresh env timed separately (productive regime)
 ALGO_BYTES_PER_ENV_STEP = 193          # SURVEY.md section 8d / DESIGN.md section 6
-STATS_EVERY_CHUNKS = 4                 # graph chunks (of 64 launches) between two NCCL reductions of the statistics vector
+STATS_EVERY_STEPS = 4                  # bench steps between two NCCL reductions of the statistics vector
 METRIC = "env-steps/sec CounterTrafficEnv batch"
 UNIT = "env-steps/s"
 
 
-def config_dict(n_envs_total, parallelism, regime):
+def config_dict(n_envs_total, batches, parallelism, regime):
     return {"workload": "CounterTrafficEnv default scenario (2 counter senders + RRM, 1 FrequencyBand, FSPL, BPSK), "
-                        "mode R (reference-exact accounting), batches of %d envs per GPU (BASELINE configs[1]), random "
-                        "actions (device~U{0,1}, duration~U{0..19}); one step = one launch of the fused step kernel over "
-                        "one batch" % ENVS_PER_GPU,
-            "n_envs": n_envs_total * ROTATING_BATCHES, "envs_per_launch": ENVS_PER_GPU,
-            "batches_per_gpu": ROTATING_BATCHES, "parallelism": parallelism,
+                        "mode R (reference-exact accounting), batches of %d envs (BASELINE configs[1]), random "
+                        "actions (device~U{0,1}, duration~U{0..19}); one step = one env.step of the GPU's whole env "
+                        "population = one launch of the fused step kernel per batch" % ENVS_PER_GPU,
+            "n_envs": n_envs_total, "envs_per_launch": ENVS_PER_GPU,
+            "batches_per_gpu": batches, "parallelism": parallelism,
             "regime": regime,
-            "l2": "inputs larger than L2: %d independent %d-env batches per GPU are stepped round-robin, so a batch's "
-                  "state (~13 MB hot), its fresh action rows and outputs are re-touched only after ~%d MB of other "
-                  "traffic (L2 = 126 MB); no flush, launches replayed from CUDA graphs (64 launches each), one "
-                  "CUDA-event pair around the K timed launches" % (ROTATING_BATCHES, ENVS_PER_GPU, 13 * (ROTATING_BATCHES - 1))}
+            "l2": "inputs larger than L2: the %d batches of a GPU are stepped one after the other, so a batch's state "
+                  "(~13 MB hot), its action rows and outputs are re-touched only after ~%.1f GB of other traffic "
+                  "(L2 = 126 MB); no flush, steps replayed from CUDA graphs, one CUDA-event pair around the K timed "
+                  "steps" % (batches, 13e-3 * (batches - 1))}
 
 
 def measured_peak():
@@ -64,12 +67,12 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_launch():
+def ncu_traffic_per_launch(key="dram_bytes_per_launch"):
     """DRAM bytes per step-kernel launch from the committed ncu capture (profiles/), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as f:
             d = json.load(f)
-        return d.get("dram_bytes_per_launch")
+        return d.get(key)
     except Exception:
         return None
 
@@ -184,10 +187,30 @@ def mask_scan_roofline(dev_t, peak, order="random"):
             "checksum_first_1024": check}
 
 
-def cfg3_long_packet(dev_t, steps=24):
+def _time_steps(env, a_dev, a_dur, steps, dev_t, warm=4):
+    """`steps` device-resident env.step calls behind `warm` untimed ones; returns ms per step (CUDA events)."""
+    import torch
+    stream = torch.cuda.current_stream(dev_t)
+    for t in range(warm):
+        env.step({"device": a_dev[t], "duration": a_dur[t]})
+    env.stats()
+    torch.cuda.synchronize(dev_t)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(warm, warm + steps):
+        env.step({"device": a_dev[t], "duration": a_dur[t]})
+    e1.record(stream)
+    torch.cuda.synchronize(dev_t)
+    env.check()
+    return e0.elapsed_time(e1) / steps
+
+
+def cfg3_long_packet(dev_t, peak, rank=0, world=1, steps=48):
     """
-    BASELINE configs[2]: 1500-byte payloads, fed per-bit masks, a PHY-only interferer creating
+    BASELINE configs[2]: 1500-byte payloads, fed per-bit masks (mode M), a PHY-only interferer creating
     mid-packet SINR segments; ASSIGNMENT_DURATION_FACTOR = 10000 so that windows fit 122 ms packets.
+    The mask scan INSIDE the fused step kernel is the HBM-bound part of the path: its roofline entry uses
+    the bytes of mask words the kernel counted (`gw_mask_bytes`) + the 193 B of state per env-step.
     """
     import torch
     import gymwipe_b200
@@ -197,41 +220,43 @@ def cfg3_long_packet(dev_t, steps=24):
         {"role": "sender", "x": 0.0, "y": -2.0, "mult": 3, "payload": 1500, "interval": 0.001, "dest": 0},
         {"role": "rrm", "x": 0.0, "y": 0.0},
         {"role": "jammer", "x": 6.0, "y": 0.0, "interval": 0.05, "delay": 0.003, "power": 0.0, "hdr": 13, "payload": 200}]}]}
-    env = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, scenario=sc, mode="mask_fed", strict=False)
-    # Bernoulli(1/16) masks: 4 GiB, resident before the timed region
+    env = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, scenario=sc, mode="mask_fed",
+                            env_id_offset=rank * n, strict=False)
+    # Bernoulli(1/16) masks: 4 GiB, resident before the timed region (>> L2: every scan streams from HBM)
     shape = (n, 1, 4, slots, 4, words)
-    masks = torch.randint(-2 ** 31, 2 ** 31 - 1, shape, dtype=torch.int32, device=dev_t)
+    g = torch.Generator(device=dev_t).manual_seed(77 + rank)
+    masks = torch.randint(-2 ** 31, 2 ** 31 - 1, shape, dtype=torch.int32, device=dev_t, generator=g)
     for _ in range(3):                                  # AND of 4 random words: bit density 1/16
-        masks &= torch.randint(-2 ** 31, 2 ** 31 - 1, shape, dtype=torch.int32, device=dev_t)
+        masks &= torch.randint(-2 ** 31, 2 ** 31 - 1, shape, dtype=torch.int32, device=dev_t, generator=g)
     env.set_masks(masks, slots)
     env.reset()
-    g = torch.Generator(device=dev_t).manual_seed(7)
     a_dev = torch.randint(0, 2, (steps + 4, n), generator=g, device=dev_t, dtype=torch.int32)
     a_dur = torch.randint(12, 20, (steps + 4, n), generator=g, device=dev_t, dtype=torch.int32)
-    stream = torch.cuda.current_stream(dev_t)
     for t in range(4):
         env.step({"device": a_dev[t], "duration": a_dur[t]})
-    env.stats()
-    torch.cuda.synchronize(dev_t)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for t in range(4, steps + 4):
-        env.step({"device": a_dev[t], "duration": a_dur[t]})
-    e1.record(stream)
-    torch.cuda.synchronize(dev_t)
-    env.check()
+    env.mask_bytes(clear=True)
+    ms = _time_steps(env, a_dev, a_dur, steps, dev_t, warm=0)
+    mask_bytes = env.mask_bytes() / steps
     st = env.stats().cpu().numpy()
-    ms = e0.elapsed_time(e1) / steps
-    return {"workload": "configs[2]: 1500-byte payloads, fed per-bit masks (mode M), PHY-only interferer, %d envs" % n,
-            "env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "transmissions_per_step": float(st[6]) / steps,
-            "deliveries_per_step": float(st[1] + st[2]) / steps, "mask_bytes_resident": int(masks.numel() * 4)}
+    algo = mask_bytes + ALGO_BYTES_PER_ENV_STEP * n
+    achieved = algo / (ms * 1e-3) / 1e9
+    return {"workload": "configs[2]: 1500-byte payloads, fed per-bit masks (mode M), PHY-only interferer, %d envs per GPU" % n,
+            "n_envs": n, "env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "transmissions_per_step": float(st[6]) / steps,
+            "deliveries_per_step": float(st[1] + st[2]) / steps, "mask_bytes_resident": int(masks.numel() * 4),
+            "roofline": {"bound": "hbm", "kernel": "step_kernel<MODE_M_FED,4,2,1> (fused step incl. the in-step mask scan)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "algorithmic_bytes_per_launch": algo, "mask_bytes_per_launch": mask_bytes,
+                         "avg_launch_ms": ms, "traffic": ncu_traffic_per_launch("cfg3_dram_bytes_per_launch"),
+                         "note": "algorithmic bytes = 32-bit mask words holding the on-air bits of every decided "
+                                 "section (counted by the kernel) + 193 B of state per env-step; masks 4 GiB >> L2"}}
 
 
-def cfg4_multiband(dev_t, steps=64):
+def cfg4_multiband(dev_t, rank=0, world=1, steps=64):
     """
-    BASELINE configs[3] on ONE GPU's share: 16 devices over 4 FrequencyBands (per band: RRM + 2 MAC
-    senders + 1 PHY-only interferer), positions ~U(-20, 20) m per env, one action per band; the env's
-    clock ends at the latest band (mode R).  131 072 envs x 4 bands = 524 288 band-sims.
+    BASELINE configs[3], one GPU's share of the 1 M envs: 16 devices over 4 FrequencyBands (per band: RRM + 2 MAC
+    senders + 1 PHY-only interferer), per-env positions (senders and RRM within a few metres of each other so that
+    packets are delivered, the interferer anywhere in a 40 m square), one action per band; the env's clock ends at
+    the latest band (mode R).  131 072 envs x 4 bands = 524 288 band-sims per GPU.
     """
     import torch
     import gymwipe_b200
@@ -245,59 +270,40 @@ def cfg4_multiband(dev_t, steps=64):
             {"role": "jammer", "x": 5.0, "y": 5.0, "interval": 0.013 + 0.002 * b, "delay": 0.001 * b, "power": 10.0,
              "hdr": 13, "payload": 60}]})
     sc = {"assignment_duration_factor": 1000, "bands": bands}
-    g = torch.Generator(device=dev_t).manual_seed(11)
-    pos = (torch.rand((n, 4, 4, 2), generator=g, device=dev_t, dtype=torch.float64) * 40.0 - 20.0)
-    env = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, scenario=sc, positions=pos, strict=False)
+    g = torch.Generator(device=dev_t).manual_seed(11 + rank)
+    pos = torch.rand((n, 4, 4, 2), generator=g, device=dev_t, dtype=torch.float64)
+    pos[:, :, :3, :] = pos[:, :, :3, :] * 3.0 - 1.5    # senders and RRM: ~U(-1.5, 1.5) m
+    pos[:, :, 3, :] = pos[:, :, 3, :] * 40.0 - 20.0    # interferer: ~U(-20, 20) m
+    env = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, scenario=sc, positions=pos,
+                            env_id_offset=rank * n, strict=False)
     env.reset()
     a_dev = torch.randint(0, 2, (steps + 4, n, 4), generator=g, device=dev_t, dtype=torch.int32)
     a_dur = torch.randint(0, 20, (steps + 4, n, 4), generator=g, device=dev_t, dtype=torch.int32)
-    stream = torch.cuda.current_stream(dev_t)
-    for t in range(4):
-        env.step({"device": a_dev[t], "duration": a_dur[t]})
-    env.stats()
-    torch.cuda.synchronize(dev_t)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for t in range(4, steps + 4):
-        env.step({"device": a_dev[t], "duration": a_dur[t]})
-    e1.record(stream)
-    torch.cuda.synchronize(dev_t)
-    env.check()
+    ms = _time_steps(env, a_dev, a_dur, steps, dev_t)
     st = env.stats().cpu().numpy()
-    ms = e0.elapsed_time(e1) / steps
-    return {"workload": "configs[3] share of one GPU: %d envs x 4 bands x 4 devices, per-env positions, mode R" % n,
-            "env_steps_per_s": n / (ms * 1e-3), "band_steps_per_s": 4 * n / (ms * 1e-3), "ms_per_step": ms,
+    return {"workload": "configs[3], share of one GPU: %d envs x 4 bands x 4 devices, per-env positions, mode R; the first "
+                        "%d steps of fresh envs (productive regime)" % (n, steps + 4),
+            "n_envs": n, "env_steps_per_s": n / (ms * 1e-3), "band_steps_per_s": 4 * n / (ms * 1e-3), "ms_per_step": ms,
             "transmissions_per_env_step": float(st[6]) / steps / n, "deliveries_per_env_step": float(st[1] + st[2]) / steps / n}
 
 
-def cfg5_pendulum(dev_t, steps=32):
+def cfg5_pendulum(dev_t, rank=0, world=1, steps=32):
     """
-    BASELINE configs[4] on ONE GPU's share: the networked inverted-pendulum env (sensor / controller
-    band assignment, in-kernel RK4 plant; PARITY UNPINNED), 131 072 envs.
+    BASELINE configs[4], one GPU's share of the 1 M envs: the networked inverted-pendulum env (sensor / controller
+    band assignment, in-kernel RK4 plant; PARITY UNPINNED), 131 072 envs per GPU.
     """
     import torch
     import gymwipe_b200
     n = 131072
     env = gymwipe_b200.make('InvertedPendulum-v0', num_envs=n, device=dev_t, strict=False)
-    g = torch.Generator(device=dev_t).manual_seed(5)
+    g = torch.Generator(device=dev_t).manual_seed(5 + rank)
     a_dev = torch.randint(0, 2, (steps + 4, n), generator=g, device=dev_t, dtype=torch.int32)
     a_dur = torch.randint(1, 20, (steps + 4, n), generator=g, device=dev_t, dtype=torch.int32)
-    stream = torch.cuda.current_stream(dev_t)
-    for t in range(4):
-        env.step({"device": a_dev[t], "duration": a_dur[t]})
-    torch.cuda.synchronize(dev_t)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for t in range(4, steps + 4):
-        env.step({"device": a_dev[t], "duration": a_dur[t]})
-    e1.record(stream)
-    torch.cuda.synchronize(dev_t)
-    env.check()
-    ms = e0.elapsed_time(e1) / steps
+    ms = _time_steps(env, a_dev, a_dur, steps, dev_t)
     th = env.plant_state()[2]
-    return {"workload": "configs[4] share of one GPU: networked inverted pendulum, %d envs, in-kernel RK4 plant "
+    return {"workload": "configs[4], share of one GPU: networked inverted pendulum, %d envs, in-kernel RK4 plant "
                         "(parity unpinned: the reference env is unconstructible)" % n,
-            "env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms,
+            "n_envs": n, "env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms,
             "mean_abs_angle_deg": float(torch.rad2deg(th).abs().mean())}
 
 
@@ -361,7 +367,7 @@ def reference_arm(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": K, "warmup": W, "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(ENVS_PER_GPU * args.gpus, "host threads x%d" % threads,
+            "config": config_dict(ENVS_PER_GPU * args.batches * args.gpus, args.batches, "host threads x%d" % threads,
                                   "steady state: steps %d..%d of every sampled env (the first %d steps are simulated untimed)"
                                   % (BURN_IN_STEPS + W, BURN_IN_STEPS + W + K, BURN_IN_STEPS + W)),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
@@ -383,6 +389,7 @@ def own_arm(args, rank, world, local_rank):
     import torch.distributed as dist
     import gymwipe_b200
     from gymwipe_b200.distributed import StatsReducer
+    from gymwipe_b200.envs import EnvPopulation
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.set_num_threads(1)                            # no idle worker threads spinning next to the stepping thread
@@ -390,86 +397,82 @@ def own_arm(args, rank, world, local_rank):
     dev_t = torch.device("cuda", local_rank)
     K, W = args.steps, args.warmup
     n = ENVS_PER_GPU
-    M = ROTATING_BATCHES
-    # M independent 65,536-env batches stepped round-robin: one "step" = one launch of the fused
-    # step kernel over one batch.  A batch is touched again only after the M - 1 others (M x ~13 MB of
-    # hot state + fresh action rows + outputs > the 126 MB L2), so every launch finds its inputs in
-    # HBM, not in L2 ("inputs larger than L2"); nothing is flushed and nothing sits between two
-    # launches inside the timed region.
-    envs = [gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t,
-                              env_id_offset=(rank * M + b) * n, strict=False) for b in range(M)]
-    for e in envs:
-        e.reset()
-    for e in envs[1:]:
-        e.share_stats(envs[0])                          # one statistics vector per GPU (gw_share_stats)
+    M = args.batches
+    # The rank's env POPULATION: M independent batches of 65,536 envs (BASELINE configs[1]).  One bench
+    # "step" = one env.step of EVERY env of the population = M launches of the fused step kernel, one per
+    # batch.  A batch is touched again only after the M - 1 others (M x ~13 MB of hot state + fresh action
+    # rows + outputs >> the 126 MB L2), so every launch finds its inputs in HBM ("inputs larger than L2");
+    # nothing is flushed and nothing but step kernels sits inside the timed region.
+    pop = EnvPopulation([gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t,
+                                           env_id_offset=(rank * M + b) * n, strict=False) for b in range(M)])
+    envs = pop.envs
+    pop.reset()
 
-    # synthetic action tapes for every launch, resident in HBM before the timed region
+    # synthetic action rows, resident in HBM before the timed region: a pool of ROWS independent rows;
+    # launch j (batch j % M of bench step j // M) reads row j % ROWS
     g = torch.Generator(device=dev_t).manual_seed(1234 + rank)
-    total = W + K
-    PROD = PRODUCTIVE_STEPS * M                         # launches of the productive-regime measurement
-    BURN = BURN_IN_STEPS * M                            # launches up to the steady state
-    rows = max(total, PROD)
-    a_dev = torch.randint(0, 2, (rows, n), generator=g, device=dev_t, dtype=torch.int32)
-    a_dur = torch.randint(0, 20, (rows, n), generator=g, device=dev_t, dtype=torch.int32)
+    ROWS = 1021                                         # prime: successive steps of a batch see different rows
+    a_dev = torch.randint(0, 2, (ROWS, n), generator=g, device=dev_t, dtype=torch.int32)
+    a_dur = torch.randint(0, 20, (ROWS, n), generator=g, device=dev_t, dtype=torch.int32)
     reducer = StatsReducer(dev_t) if world > 1 else None
     stream = torch.cuda.Stream(device=dev_t)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     counter = [0]                                       # launches so far: launch j steps batch j % M
 
-    def launch(row):
-        envs[counter[0] % M].step({"device": a_dev[row], "duration": a_dur[row]})
-        counter[0] += 1
+    def launch():
+        j = counter[0]
+        envs[j % M].step({"device": a_dev[j % ROWS], "duration": a_dur[j % ROWS]})
+        counter[0] = j + 1
 
-    CHUNK = 64
-
-    def capture(first_row, count):
-        """CUDA graphs of <= CHUNK launches (the pointers of the action rows are baked in, hence one
-        graph per chunk); capturing does not execute.  Returns [(graph, launches)]."""
-        out, j, c0 = [], 0, counter[0]
-        while j < count:
-            cnt = min(CHUNK, count - j)
+    def capture_steps(count):
+        """One CUDA graph per bench step (M launches; the action-row pointers are baked in); capturing does
+        not execute."""
+        out = []
+        for _ in range(count):
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr, stream=stream):
-                for q in range(cnt):
-                    launch((first_row + j + q) % rows)
-            out.append((gr, cnt))
-            j += cnt
-        assert counter[0] == c0 + count
+                for _b in range(M):
+                    launch()
+            out.append(gr)
         return out
+
+    def timed(fn):
+        torch.cuda.synchronize(dev_t)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        torch.cuda.synchronize(dev_t)
+        return e0.elapsed_time(e1)
 
     torch.cuda.synchronize(dev_t)
     with torch.cuda.stream(stream):
         # (1) productive regime (the first ~100 steps after construction / reset(): queues hold packets
         # that fit the windows): PRODUCTIVE_STEPS steps of every fresh env, timed for the record
-        gp = capture(0, PROD)
-        torch.cuda.synchronize(dev_t)
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record(stream)
-        for gr, _ in gp:
-            gr.replay()
-        p1.record(stream)
-        torch.cuda.synchronize(dev_t)
-        prod_ms = p0.elapsed_time(p1) / PROD
+        gp = capture_steps(PRODUCTIVE_STEPS)
+        prod_ms = timed(lambda: [gr.replay() for gr in gp]) / (PRODUCTIVE_STEPS * M)
         del gp
         # (2) burn-in to the steady state of the reference's workload: its training run
         # (agents/dqn_counter_traffic.py: one reset(), dqn.fit(nb_steps=50000), `done` never true) leaves
         # the productive regime after ~100 steps and spends > 99 % of its steps in the regime where the
         # counters are too large for any window (announcements only)
-        for j in range(BURN - PROD):
-            launch(j % rows)
-        # (3) W warm-up launches (+ one untimed replay of the K-launch graphs), then EXACTLY K timed launches
-        for j in range(W):
-            launch(j)
+        for _ in range((BURN_IN_STEPS - PRODUCTIVE_STEPS) * M):
+            launch()
+        # (3) W warm-up steps, then EXACTLY K timed steps.  The K steps are replayed from G = min(K, 16)
+        # step graphs used round-robin (each with its own action rows); every graph is replayed once untimed
+        # first (the first launch of an instantiated graph uploads it to the device)
+        for _ in range(W * M):
+            launch()
         torch.cuda.synchronize(dev_t)
-        graphs = capture(W, K)
-        # one untimed replay of every graph: the first launch of an instantiated graph uploads it to the
-        # device (a one-time cost like any warm-up); the envs simply advance K more steps
-        for gr, _ in graphs:
+        G = min(K, 16)
+        graphs = capture_steps(G)
+        for gr in graphs:
             gr.replay()
         torch.cuda.synchronize(dev_t)
+
         def reduce_stats():
-            # K5 partial sums of all batches -> NCCL all-reduce on a side stream
-            envs[0].stats(out=reducer.next_slot())
+            # K5 partial sums of the whole population -> NCCL all-reduce on a side stream
+            pop.stats(out=reducer.next_slot())
             reducer.submit()
         if reducer is not None:
             # first use loads the small kernels and sets up NCCL's channels: not part of stepping
@@ -478,16 +481,18 @@ def own_arm(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev_t)
-        marks = [torch.cuda.Event(enable_timing=True) for _ in range(len(graphs) + 1)]
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        n_reduce = 0
         if sampler is not None:
             sampler.mark_begin()
         wall0 = time.perf_counter()
         marks[0].record(stream)
-        for c, (gr, cnt) in enumerate(graphs):
-            gr.replay()
-            if reducer is not None and ((c + 1) % STATS_EVERY_CHUNKS == 0 or c + 1 == len(graphs)):
+        for k in range(K):
+            graphs[k % G].replay()
+            marks[k + 1].record(stream)                 # the step's end, BEFORE the host enqueues the reduction
+            if reducer is not None and ((k + 1) % STATS_EVERY_STEPS == 0 or k + 1 == K):
                 reduce_stats()
-            marks[c + 1].record(stream)
+                n_reduce += 1
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev_t)
@@ -495,17 +500,13 @@ def own_arm(args, rank, world, local_rank):
     if sampler is not None:
         sampler.mark_end()
     clocks = sampler.stop() if sampler is not None else None
-    for e in envs:
-        e.check()
+    pop.check()
     if reducer is not None:
         reducer.drain()
-    chunk_ms = np.array([marks[c].elapsed_time(marks[c + 1]) for c in range(len(graphs))])
-    chunk_cnt = np.array([cnt for _, cnt in graphs])
+    step_ms = np.array([marks[k].elapsed_time(marks[k + 1]) for k in range(K)])
     elapsed_ms = float(marks[0].elapsed_time(marks[-1]))
-    per_step_ms = chunk_ms / chunk_cnt                  # average launch duration per chunk
 
-    # transparency: (a) one batch stepped back to back from one graph (state stays in L2),
-    # (b) the round-1 protocol: per-launch event pairs with a 256 MiB L2-flush memset before each
+    # transparency: one batch stepped back to back from one graph (its state stays in L2)
     env1 = envs[0]
     KB = 64
     with torch.cuda.stream(stream):
@@ -514,207 +515,165 @@ def own_arm(args, rank, world, local_rank):
             for k in range(KB):
                 env1.step({"device": a_dev[k], "duration": a_dur[k]})
         gw.replay()
-        torch.cuda.synchronize(dev_t)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        gw.replay()
-        e1.record(stream)
-        torch.cuda.synchronize(dev_t)
-    warm_ms = e0.elapsed_time(e1) / KB
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev_t)
-    KF = 64
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KF)]
-    cur = torch.cuda.current_stream(dev_t)
-    for k in range(KF):
-        flush.zero_()
-        evs[k][0].record(cur)
-        env1.step({"device": a_dev[k], "duration": a_dur[k]})
-        evs[k][1].record(cur)
+        warm_ms = timed(gw.replay) / KB
+    del graphs, gw
+
+    # ---- e2e: the same population step through the C ABI with HOST buffers (gw_step_host_compact_many): every
+    # batch reads its pinned uint8 actions and writes its pinned result words in place; one synchronisation per
+    # population step.  Steady-state envs (the population above); KE steps so that the region is >= ~60 ms.
+    PE = min(M, E2E_BATCHES)
+    epop = EnvPopulation(envs[:PE])
+    EROWS = 8
+    h_act = [[torch.stack([a_dev[(r * PE + b) % ROWS], a_dur[(r * PE + b) % ROWS]], dim=1).to(torch.uint8).cpu().pin_memory()
+              for b in range(PE)] for r in range(EROWS)]
+    h_res = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(PE)]
+    act_ptrs = [EnvPopulation.pointer_array(h_act[r]) for r in range(EROWS)]
+    res_ptrs = EnvPopulation.pointer_array(h_res)
+    res_np = [r.numpy() for r in h_res]
+    for r in range(max(W, 3)):
+        epop.step_host_compact(act_ptrs[r % EROWS], res_ptrs)
     torch.cuda.synchronize(dev_t)
-    flushed_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-    del flush
-    for e in envs[1:]:
-        e.share_stats(None)
-        e.close()
-    del envs, graphs, gw
-    torch.cuda.empty_cache()
-
-    # e2e: host buffers through gw_step_host (pinned), copies inside the timed region
-    env2 = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, env_id_offset=rank * n, strict=False)
-    env2.reset()
-
-    def burn_in(env):
-        # to the steady state, through the device-resident step (untimed)
-        for t in range(BURN_IN_STEPS):
-            env.step({"device": a_dev[t % rows], "duration": a_dur[t % rows]})
-        torch.cuda.synchronize(dev_t)
-    burn_in(env2)
-    KE = min(K, 256)
-    h_dev = a_dev[:W + KE].cpu().pin_memory()
-    h_dur = a_dur[:W + KE].cpu().pin_memory()
+    t0 = time.perf_counter()
+    for r in range(8):
+        epop.step_host_compact(act_ptrs[r % EROWS], res_ptrs)
+    est = (time.perf_counter() - t0) / 8
+    KE = max(K, int(0.06 / max(est, 1e-6)) + 1)
+    if world > 1:
+        ke = torch.tensor([KE], dtype=torch.int64, device=dev_t)
+        dist.all_reduce(ke, op=dist.ReduceOp.MAX)
+        KE = int(ke[0])
+        dist.barrier()
+    torch.cuda.synchronize(dev_t)
+    checksum = 0
+    t0 = time.perf_counter()
+    for r in range(KE):
+        epop.step_host_compact(act_ptrs[r % EROWS], res_ptrs)
+        checksum += int(res_np[r % PE][r % n])          # the step's results are on the host
+    torch.cuda.synchronize(dev_t)
+    e2e_s = time.perf_counter() - t0
+    epop.check()
+    reward_checksum = float(sum(env1.unpack_compact(h)[1].sum() for h in h_res))
+    # the single-batch synchronous call (gw_step_host_compact) and the wider-typed variants, for the record
     h_obs = torch.empty(n, dtype=torch.int64).pin_memory()
     h_rew = torch.empty(n, dtype=torch.float64).pin_memory()
     h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
-    for t in range(W):
-        env2.step_host(h_dev[t], h_dur[t], h_obs, h_rew, h_done)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev_t)
-    t0 = time.perf_counter()
-    for k in range(KE):
-        env2.step_host(h_dev[W + k], h_dur[W + k], h_obs, h_rew, h_done)
-    torch.cuda.synchronize(dev_t)
-    e2e_wide_s = time.perf_counter() - t0
-    # packed variant (gw_step_host_packed): one copy in (8 B/env), one copy out (9 B/env)
-    h_act = torch.stack([h_dev, h_dur], dim=1).contiguous().pin_memory()      # [steps, 2, n]
-    h_res = torch.empty(9 * n, dtype=torch.uint8).pin_memory()
-    env3 = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, env_id_offset=rank * n, strict=False)
-    env3.reset()
-    burn_in(env3)
-    for t in range(W):
-        env3.step_host_packed(h_act[t], h_res)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev_t)
-    t0 = time.perf_counter()
-    for k in range(KE):
-        env3.step_host_packed(h_act[W + k], h_res)
-    torch.cuda.synchronize(dev_t)
-    e2e_packed_s = time.perf_counter() - t0
-    checksum = float(env3.unpack_results(h_res)[1].double().sum())
-    assert torch.equal(env3.unpack_results(h_res)[0].to(torch.int64), h_obs)   # both paths agree on the last step
-    # compact variant (gw_step_host_compact): uint8 actions [n][2] in (2 B/env), one packed word out (4 B/env)
-    h_act8 = torch.stack([h_dev, h_dur], dim=2).to(torch.uint8).contiguous().pin_memory()     # [steps, n, 2]
-    h_res32 = torch.empty(n, dtype=torch.int32).pin_memory()
-    env4 = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, env_id_offset=rank * n, strict=False)
-    env4.reset()
-    burn_in(env4)
-    act_rows = [h_act8[t] for t in range(W + KE)]      # views of the pinned action tape, one per step
-    for t in range(W):
-        env4.step_host_compact(act_rows[t], h_res32)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev_t)
-    t0 = time.perf_counter()
-    for k in range(KE):
-        env4.step_host_compact(act_rows[W + k], h_res32)
-    torch.cuda.synchronize(dev_t)
-    e2e_s = time.perf_counter() - t0
-    env4.check()
-    assert torch.equal(env4.unpack_compact(h_res32)[0], h_obs)                  # all three paths agree on the last step
-    # pipelined variant: PIPE env batches in flight through gw_step_host_compact_async -- the host waits for
-    # a batch's previous results (event), reads them, then submits that batch's next actions; kernels of
-    # different batches queue behind each other, so launch and synchronisation latencies overlap with compute
-    PIPE = 4
-    penvs = [env4] + [gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t,
-                                        env_id_offset=(rank * PIPE + b) * n, strict=False) for b in range(1, PIPE)]
-    for e in penvs[1:]:
-        e.reset()
-        burn_in(e)
-    pres = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(PIPE)]
-    pres_np = [r.numpy() for r in pres]
-    pev = [torch.cuda.Event() for _ in range(PIPE)]
-    cur = torch.cuda.current_stream(dev_t)
-    nrows = len(act_rows)
+    h_dev = a_dev[:EROWS].cpu().pin_memory()
+    h_dur = a_dur[:EROWS].cpu().pin_memory()
+    h_pk = torch.stack([h_dev, h_dur], dim=1).contiguous().pin_memory()         # [rows, 2, n]
+    h_res9 = torch.empty(9 * n, dtype=torch.uint8).pin_memory()
+    KS = max(64, min(KE, 2048))
 
-    def pipelined(count):
-        acc = 0
-        for k in range(count):
-            b = k % PIPE
-            if k >= PIPE:
-                pev[b].synchronize()
-                acc += int(pres_np[b][k % n])           # the step's results are on the host
-            penvs[b].step_host_compact_async(act_rows[k % nrows], pres[b])
-            pev[b].record(cur)
+    def time_single(fn):
+        for r in range(3):
+            fn(r)
         torch.cuda.synchronize(dev_t)
-        return acc
-    pipelined(4 * PIPE)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev_t)
-    t0 = time.perf_counter()
-    pipe_checksum = pipelined(KE * PIPE)
-    e2e_pipe_s = time.perf_counter() - t0
-    for e in penvs:
-        e.check()
-    del env4, penvs
+        t0 = time.perf_counter()
+        for r in range(KS):
+            fn(r)
+        torch.cuda.synchronize(dev_t)
+        return time.perf_counter() - t0
+    e2e_single_s = time_single(lambda r: env1.step_host_compact(h_act[r % EROWS][0], h_res[0]))
+    e2e_packed_s = time_single(lambda r: env1.step_host_packed(h_pk[r % EROWS], h_res9))
+    e2e_wide_s = time_single(lambda r: env1.step_host(h_dev[r % EROWS], h_dur[r % EROWS], h_obs, h_rew, h_done))
+    assert torch.equal(env1.unpack_results(h_res9)[0].to(torch.int64), h_obs)
+    env1.check()
 
     # max over ranks
     if world > 1:
-        v = torch.tensor([elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, flushed_ms, prod_ms, e2e_packed_s, e2e_pipe_s], dtype=torch.float64, device=dev_t)
+        v = torch.tensor([elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, prod_ms, e2e_packed_s, e2e_single_s],
+                         dtype=torch.float64, device=dev_t)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, flushed_ms, prod_ms, e2e_packed_s, e2e_pipe_s = [float(x) for x in v]
+        elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, prod_ms, e2e_packed_s, e2e_single_s = [float(x) for x in v]
+    pop.close()
+    del pop, epop, envs
+    torch.cuda.empty_cache()
+
+    extras = {}
+    if not args.no_extras:
+        peak, _ = measured_peak()
+        try:
+            for name, fn in (("cfg3_long_packet_mode_m", lambda: cfg3_long_packet(dev_t, peak, rank, world)),
+                             ("cfg4_multiband", lambda: cfg4_multiband(dev_t, rank, world)),
+                             ("cfg5_pendulum", lambda: cfg5_pendulum(dev_t, rank, world))):
+                r = fn()
+                torch.cuda.empty_cache()
+                if world > 1:                           # every rank its share; the slowest rank bounds the step
+                    t = torch.tensor([r["ms_per_step"]], dtype=torch.float64, device=dev_t)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    scale = r["ms_per_step"] / float(t[0])
+                    r["ms_per_step"] = float(t[0])
+                    for key in ("env_steps_per_s", "band_steps_per_s"):
+                        if key in r:
+                            r[key] = r[key] * scale * world
+                    if "roofline" in r:
+                        r["roofline"]["achieved"] *= scale
+                        r["roofline"]["frac"] *= scale
+                        r["roofline"]["note"] = "per GPU, at the slowest rank's step time"
+                    r["n_envs_total"] = r["n_envs"] * world
+                extras[name] = r
+            if world == 1:
+                extras["mask_scan"] = mask_scan_roofline(dev_t, peak, "random")
+                torch.cuda.empty_cache()
+        except Exception as exc:                          # extras must never take the headline down
+            extras["extras_error"] = repr(exc)
     if rank != 0:
         return 0
 
-    total_envs = n * world
-    value = total_envs * K / (elapsed_ms * 1e-3)
-    e2e_value = total_envs * KE / e2e_s
+    envs_per_step = n * M * world                       # env-steps of one bench step, all ranks
+    value = envs_per_step * K / (elapsed_ms * 1e-3)
+    e2e_value = n * PE * world * KE / e2e_s
     peak, peak_src = measured_peak()
-    kernel_ms = elapsed_ms / K                          # average launch duration over the timed region
+    kernel_ms = elapsed_ms / (K * M)                    # average launch duration over the timed region
     achieved = ALGO_BYTES_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e9
+    traffic = ncu_traffic_per_launch()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": config_dict(total_envs, "dp%d (independent env shards, no data-path collective; NCCL all-reduce of the 64-byte "
-                              "statistics vector every %d launches on a side stream)" % (world, STATS_EVERY_CHUNKS * 64) if world > 1
+        "config": config_dict(n * M * world, M, "dp%d (independent env shards, no data-path collective; NCCL all-reduce of the "
+                              "64-byte statistics vector every %d steps on a side stream)" % (world, STATS_EVERY_STEPS) if world > 1
                               else "single GPU",
                               "steady state of the reference's workload: fresh envs + reset() + %d untimed steps per env, "
-                              "then W warm-up and K timed launches (the reference's training run -- one reset(), 50,000 steps, "
+                              "then W warm-up and K timed steps (the reference's training run -- one reset(), 50,000 steps, "
                               "`done` never true -- leaves the productive regime after ~100 steps; SURVEY.md section 8d cfg 2: "
                               "'throughput: steady state; report both regimes separately')" % BURN_IN_STEPS),
+        "launches_per_step": M, "us_per_launch": 1e3 * kernel_ms,
+        "productive": {"value": n * world / (prod_ms * 1e-3), "unit": UNIT, "us_per_launch": 1e3 * prod_ms,
+                       "note": "same population protocol, the first %d steps of every fresh env (%d launches per GPU): queues "
+                               "hold packets that fit the windows, 1-10 data transmissions per step" % (PRODUCTIVE_STEPS, PRODUCTIVE_STEPS * M)},
         "regimes": {"steady_state_env_steps_per_s": value,
-                    "productive_env_steps_per_s": total_envs / (prod_ms * 1e-3),
-                    "productive_note": "same round-robin protocol, the first %d steps of every fresh env (%d launches): queues "
-                                       "hold packets that fit the windows, 1-10 data transmissions per step" % (PRODUCTIVE_STEPS, PRODUCTIVE_STEPS * M),
-                    "l2_warm_one_batch_env_steps_per_s": total_envs / (warm_ms * 1e-3),
+                    "productive_env_steps_per_s": n * world / (prod_ms * 1e-3),
+                    "l2_warm_one_batch_env_steps_per_s": n * world / (warm_ms * 1e-3),
                     "l2_warm_note": "ONE batch stepped 64x back to back from a CUDA graph (its state stays in L2)",
-                    "round1_protocol_env_steps_per_s": total_envs / (flushed_ms * 1e-3),
-                    "round1_protocol_note": "one batch, 256 MiB memset before every launch, CUDA-event pair around every launch "
-                                            "(includes the launch latency behind the flush)",
-                    "per_chunk_ms_per_launch": [float(x) for x in per_step_ms]},
+                    "per_step_ms": {"min": float(step_ms.min()), "median": float(np.median(step_ms)), "max": float(step_ms.max())}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
+                     "traffic": traffic, "peak_source": peak_src,
                      "kernel": "step_kernel<MODE_R,3,2,0>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
                      "avg_launch_ms": kernel_ms,
-                     "note": "mode-R state is ~190 B/env-step: the fused step kernel is latency / fp64-ALU bound, "
-                             "not HBM bound (SURVEY.md 8d); the fraction is reported as required"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n,
-                "steps": KE, "api": "CounterTrafficEnv.step_host_compact -> gw_step_host_compact (pinned host buffers: uint8 "
-                                    "actions [n][2] in, one packed uint32 {obs:17, reward+16:5, done:1} per env out; the kernel "
-                                    "reads / writes the pinned buffers in place over the host link -- the h2d / d2h bytes are moved "
-                                    "by the kernel's own loads and stores, inside the timed region); steady-state envs (burn-in as above)",
-                "reward_checksum": checksum,
-                "pipelined": {"value": total_envs * KE * PIPE / e2e_pipe_s, "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n,
-                              "batches_in_flight": PIPE, "checksum": pipe_checksum,
-                              "api": "gw_step_host_compact_async on %d independent env batches (one handle each): the host waits "
-                                     "for a batch's previous results, reads them and submits its next actions while the other "
-                                     "batches' steps run -- the throughput form of the same host-buffer path" % PIPE},
-                "packed_api": {"value": total_envs * KE / e2e_packed_s, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 9 * n,
+                     "note": "mode-R state is ~190 B/env-step: the fused step kernel is latency / issue bound, "
+                             "not HBM bound (SURVEY.md 8d); the HBM-bound kernel of the path is the mode-M mask scan "
+                             "inside the step kernel -- see cfg3_long_packet_mode_m.roofline"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * PE, "d2h_bytes_per_step": 4 * n * PE,
+                "steps": KE, "envs_per_step_per_gpu": n * PE, "timed_region_s": e2e_s,
+                "api": "EnvPopulation.step_host_compact -> gw_step_host_compact_many: one env.step of a population of %d "
+                       "batches x %d envs per GPU from PINNED HOST buffers (uint8 actions [n][2] in, one packed uint32 "
+                       "{obs:17, reward+16:5, done:1} per env out; the kernels read / write the pinned buffers in place over "
+                       "the host link -- the h2d / d2h bytes are moved by the kernels' own loads and stores, inside the timed "
+                       "region); one stream synchronisation per population step; steady-state envs" % (PE, n),
+                "reward_checksum": reward_checksum, "result_checksum": checksum,
+                "single_batch_sync": {"value": n * world * KS / e2e_single_s, "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n,
+                                      "api": "CounterTrafficEnv.step_host_compact -> gw_step_host_compact: ONE batch per call, "
+                                             "synchronised every call (launch + kernel + wake-up latency per 65,536 envs)"},
+                "packed_api": {"value": n * world * KS / e2e_packed_s, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 9 * n,
                                "api": "CounterTrafficEnv.step_host_packed -> gw_step_host_packed (int32 actions [2][n] in, "
                                       "int32 obs | float32 reward | uint8 done out)"},
-                "wide_api": {"value": total_envs * KE / e2e_wide_s, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 17 * n,
+                "wide_api": {"value": n * world * KS / e2e_wide_s, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 17 * n,
                              "api": "CounterTrafficEnv.step_host -> gw_step_host (int64 obs, float64 reward, uint8 done)"}},
-        "gpu_launches": K + (((len(chunk_cnt) + STATS_EVERY_CHUNKS - 1) // STATS_EVERY_CHUNKS) if world > 1 else 0),   # step kernels (+ statistics copies when sharded)
+        "gpu_launches": K * M + n_reduce,               # step kernels (+ statistics copies when sharded)
         "clocks": clocks,
         "wall_s_timed_loop": wall,
     }
-    if world == 1 and not args.no_extras:
-        del env2, env3
-        torch.cuda.empty_cache()
-        try:
-            line["mask_scan"] = mask_scan_roofline(dev_t, peak, "random")
-            torch.cuda.empty_cache()
-            line["mask_scan_sequential_rows"] = mask_scan_roofline(dev_t, peak, "sequential")
-            torch.cuda.empty_cache()
-            line["cfg3_long_packet_mode_m"] = cfg3_long_packet(dev_t)
-            torch.cuda.empty_cache()
-            line["cfg4_multiband"] = cfg4_multiband(dev_t)
-            torch.cuda.empty_cache()
-            line["cfg5_pendulum"] = cfg5_pendulum(dev_t)
-        except Exception as exc:                      # extras must never take the headline down
-            line["extras_error"] = repr(exc)
+    line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_run(args.cpu_seconds)
     print(json.dumps(line))
@@ -724,9 +683,11 @@ def own_arm(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=512)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--batches", type=int, default=POPULATION_BATCHES,
+                    help="65,536-env batches per GPU (one bench step = one env.step of all of them)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the mask-scan roofline and the cfg-3 run")

@@ -86,9 +86,25 @@ def build(force=False, verbose=False):
         raise RuntimeError("gymwipe_b200: %s is missing and nvcc is not available to build it; "
                            "there is no CPU fallback" % LIB_PATH)
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH, os.path.join(CSRC, "gw_kernels.cu")]
-    subprocess.check_call(cmd)
+    # several ranks (torchrun) may find the library stale at the same time: one of them compiles, into
+    # a temporary file that is renamed into place, the others wait on the lock and then find it fresh
+    import fcntl
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB_PATH
+            tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+                ["-o", tmp, os.path.join(CSRC, "gw_kernels.cu")]
+            try:
+                subprocess.check_call(cmd)
+                os.replace(tmp, LIB_PATH)
+            finally:
+                if os.path.exists(tmp):
+                    os.unlink(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -111,9 +127,11 @@ _SIGNATURES = {
     "gw_step_host_packed": (C.c_int, [_VP, _VP, _VP, _VP]),
     "gw_step_host_compact": (C.c_int, [_VP, _VP, _VP, _VP]),
     "gw_step_host_compact_async": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "gw_step_host_compact_many": (C.c_int, [C.POINTER(_VP), C.c_int32, C.POINTER(_VP), C.POINTER(_VP), _VP]),
     "gw_check": (C.c_int, [_VP, _VP]),
     "gw_stats": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "gw_share_stats": (C.c_int, [_VP, _VP]),
+    "gw_mask_bytes": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.c_int, _VP]),
     "gw_read_state": (C.c_int, [_VP, C.c_int, _VP, _VP]),
     "gw_set_masks": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP]),
     "gw_fspl_attenuation": (C.c_int, [_VP, _VP, _VP, _VP, C.c_double, _VP, C.c_int64, _VP]),

@@ -38,9 +38,45 @@ class CounterTrafficProcessor:
 
 
 def build_model(nb_actions, hidden=16):
-    """``agents/dqn_counter_traffic.py:46-56``: Dense(16)-ReLU x3, Dense(nb_actions), linear."""
-    return nn.Sequential(nn.Linear(1, hidden), nn.ReLU(), nn.Linear(hidden, hidden), nn.ReLU(),
-                         nn.Linear(hidden, hidden), nn.ReLU(), nn.Linear(hidden, nb_actions))
+    """``agents/dqn_counter_traffic.py:46-56``: Dense(16)-ReLU x3, Dense(nb_actions), linear; Keras' Dense
+    defaults: glorot-uniform kernels, zero biases."""
+    model = nn.Sequential(nn.Linear(1, hidden), nn.ReLU(), nn.Linear(hidden, hidden), nn.ReLU(),
+                          nn.Linear(hidden, hidden), nn.ReLU(), nn.Linear(hidden, nb_actions))
+    for m in model:
+        if isinstance(m, nn.Linear):
+            nn.init.xavier_uniform_(m.weight)
+            nn.init.zeros_(m.bias)
+    return model
+
+
+class KerasAdam(torch.optim.Optimizer):
+    """
+    Adam as Keras 2 applies it (``keras/optimizers.py``, the optimiser ``dqn.compile(Adam(lr=1e-3))`` of
+    ``agents/dqn_counter_traffic.py:66`` uses): ``lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)``,
+    ``p -= lr_t * m / (sqrt(v) + eps)`` with ``eps = 1e-7`` (``K.epsilon()``) -- the epsilon sits outside the
+    bias correction, unlike ``torch.optim.Adam``.
+    """
+
+    def __init__(self, params, lr=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        super().__init__(params, dict(lr=lr, beta_1=beta_1, beta_2=beta_2, epsilon=epsilon))
+        self.iterations = 0
+
+    @torch.no_grad()
+    def step(self):
+        self.iterations += 1
+        t = self.iterations
+        for group in self.param_groups:
+            b1, b2 = group["beta_1"], group["beta_2"]
+            lr_t = group["lr"] * (1.0 - b2 ** t) ** 0.5 / (1.0 - b1 ** t)
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["m"], st["v"] = torch.zeros_like(p), torch.zeros_like(p)
+                st["m"].mul_(b1).add_(p.grad, alpha=1.0 - b1)
+                st["v"].mul_(b2).addcmul_(p.grad, p.grad, value=1.0 - b2)
+                p.addcdiv_(st["m"], st["v"].sqrt().add_(group["epsilon"]), value=-lr_t)
 
 
 class ReplayMemory:
@@ -87,7 +123,7 @@ class DQNLearner:
         self.model = build_model(self.nb_actions, hidden).to(self.device)
         self.target = build_model(self.nb_actions, hidden).to(self.device)
         self.target.load_state_dict(self.model.state_dict())
-        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=lr)
+        self.optimizer = KerasAdam(self.model.parameters(), lr=lr)
         self.gamma, self.tau_update, self.warmup = gamma, target_model_update, nb_steps_warmup
         self.batch_size, self.tau, self.clip = batch_size, tau, clip
         self.obs_center = float(getattr(env, "COUNTER_BOUND", 0)) if normalize_obs else 0.0
@@ -95,27 +131,48 @@ class DQNLearner:
         self.memory = ReplayMemory(max(memory_limit, 4 * n), self.device)
         self.gen = torch.Generator(device=self.device).manual_seed(seed)
         self.step_count = 0
+        self.reset_done = True
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        # warm-up in TRANSITIONS, counted with the smallest shard: shards differ by at most one env
+        # (distributed.shard_range), and every rank must start training -- and with it the gradient
+        # all-reduce -- in the same iteration
+        self.warmup_width = int(n)
+        if self.world > 1:
+            w = torch.tensor([self.warmup_width], dtype=torch.int64, device=self.device)
+            dist.all_reduce(w, op=dist.ReduceOp.MIN)
+            self.warmup_width = int(w[0])
         self.history = {"loss": [], "mean_reward": []}
 
     def _features(self, obs):
+        """Network input of a RAW observation: the only place where the observation is centred."""
         return (obs.to(torch.float32) - self.obs_center).reshape(-1, 1)
 
     @torch.no_grad()
     def select_action(self, obs):
-        """BoltzmannQPolicy (keras-rl): p ~ exp(clip(q / tau))."""
+        """BoltzmannQPolicy (keras-rl): p ~ exp(clip(q / tau)); ``obs`` is the raw observation."""
         q = self.model(self._features(obs)).double()
         logits = torch.clamp(q / self.tau, self.clip[0], self.clip[1])
         probs = torch.softmax(logits, dim=1)
         return torch.multinomial(probs, 1, generator=self.gen).squeeze(1)
 
     def _train_step(self):
-        obs, action, reward, next_obs, done = self.memory.sample(self.batch_size, self.gen)
+        return self.train_on_batch(*self.memory.sample(self.batch_size, self.gen))
+
+    def train_on_batch(self, obs, action, reward, next_obs, done):
+        """
+        One update of keras-rl's ``DQNAgent.backward`` (``rl/agents/dqn.py``; the reference constructs the
+        agent with the defaults: no double DQN, no dueling, ``gamma = .99``, ``delta_clip = inf``):
+        ``y = r + gamma * (1 - terminal) * max_a Q_target(s', a)``; loss = mean over the batch of
+        ``0.5 * (Q(s, a) - y)^2`` (``huber_loss`` with an infinite clip value, masked to the taken action);
+        Keras Adam; then the soft target update ``target = tau * model + (1 - tau) * target``
+        (``get_soft_target_model_updates``, ``target_model_update = 1e-2``) with the UPDATED weights.
+        ``obs`` / ``next_obs`` are network inputs (features), as stored in the replay memory.
+        """
         with torch.no_grad():
             target_q = self.target(next_obs.reshape(-1, 1)).max(dim=1).values
             y = reward + self.gamma * (1.0 - done) * target_q
         q = self.model(obs.reshape(-1, 1)).gather(1, action.reshape(-1, 1)).squeeze(1)
-        loss = torch.mean((q - y) ** 2)
+        loss = torch.mean(0.5 * (q - y) ** 2)
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
         if self.world > 1:                              # data-parallel learner: average the gradients
@@ -137,7 +194,7 @@ class DQNLearner:
         obs = self.env.reset()
         obs = torch.as_tensor(obs, device=self.device).reshape(-1)
         for _ in range(nb_steps):
-            flat = self.select_action(obs - int(self.obs_center) if self.obs_center else obs)
+            flat = self.select_action(obs)
             next_obs, reward, done, _ = self.env.step(self.processor.process_action(flat))
             next_obs = torch.as_tensor(next_obs, device=self.device).reshape(-1)
             reward = torch.as_tensor(reward, device=self.device).reshape(-1)
@@ -145,10 +202,16 @@ class DQNLearner:
             self.memory.append(self._features(obs).squeeze(1), flat, reward.to(torch.float32),
                                self._features(next_obs).squeeze(1), done.to(torch.float32))
             self.step_count += 1
-            if self.step_count * obs.numel() >= self.warmup and self.memory.size >= self.batch_size:
+            if self.step_count * self.warmup_width >= self.warmup and self.memory.size >= self.batch_size:
                 self.history["loss"].append(self._train_step())
             self.history["mean_reward"].append(reward.double().mean())
             obs = next_obs
+            # keras-rl's fit() resets an env whose episode ended (rl/core.py: `if done: ... env.reset()`);
+            # CounterTrafficEnv never ends an episode (app. B #1), plant / custom envs may
+            if self.reset_done and bool(done.any()):
+                ids = done.nonzero().reshape(-1)
+                fresh = torch.as_tensor(self.env.reset(env_ids=ids), device=self.device).reshape(-1)
+                obs = torch.where(done.bool(), fresh, obs)
             if log_interval and self.step_count % log_interval == 0:
                 print("step %d  mean reward %.4f" % (self.step_count, float(self.history["mean_reward"][-1])))
         self.history["loss"] = [float(x) for x in self.history["loss"]]

@@ -591,6 +591,28 @@ GW_HD void mask_range(const Sim<D, NS, NJ, ST> &s, int p, double bitRate, int &s
     k1 = (int64_t)floor((s.now - start) * bitRate);
 }
 
+// Mode M with FED masks: the error flags of a row are data, so the count of a section (header or
+// payload) does not depend on how the section is cut into constant-SINR segments -- the ranges of
+// consecutive segments are contiguous ([k0, k1), [k1, k2), ... with k = floor((t - start) * bitRate) of
+// the SAME boundary time t on both sides) and their counts are integers, added exactly in fp64.  Only
+// the events that DECIDE on a section (header end, completion) therefore need a count: the bits from
+// the start of the running segment (segT0: lock-on, header success, or the last position change) to
+// now.  Power changes in between (other transmissions starting / ending) count nothing and leave
+// segT0 alone.  Returns the receivers that decide at `ev`.
+template <int D, int NS, int NJ, class ST>
+GW_HD int fed_decide_set(const Sim<D, NS, NJ, ST> &s, const Event &ev)
+{
+    if (ev.kind != EV_PHY) return 0;
+    const int d = ev.idx, ph = get_at(s.sphase, d);
+    if (ph != S_HDR && ph != S_PAY) return 0;
+    const int sec = ph == S_HDR ? 0 : 1;
+    int need = 0;
+    GW_UNROLL
+    for (int p = 0; p < D; ++p)
+        if (s.rxOf[p] == d && s.rxSec[p] == sec) need |= 1 << p;
+    return need;
+}
+
 // ---------------------------------------------------------------------------
 // plant hook: envs whose packets carry values of a simulated plant (the networked inverted
 // pendulum, gymwipe/envs/inverted_pendulum.py) plug a plant object into the transition
@@ -1092,7 +1114,8 @@ GW_HD void process_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParam
     int once, twice;
     GW_STAT_MACRO(2 + (ev.kind == EV_TICK ? 1 : 0));
     s.now = ev.t;
-    count_set(s, ev, srx, once, twice);
+    if (MODE == MODE_M_FED) { once = fed_decide_set(s, ev); twice = 0; }
+    else count_set(s, ev, srx, once, twice);
     if (MODE == MODE_R) {
         do_counts_R(s, once, twice, P.bitRate);
     } else {

@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -119,6 +120,7 @@ struct gw_handle {
     double *stats;          // device [8]
     double *stats_use;      // accumulators the step kernels add to: `stats`, or another handle's (gw_share_stats)
     int *errflag;           // device [4]: code, sim, fault, -
+    unsigned long long *mask_bytes;     // device [2]: mask bytes scanned by the mode-M (fed) step kernels, -
     double power_dbm[kMaxBands][kMaxDev];
     double default_pos[kMaxBands][kMaxDev][2];
     double thermal[kMaxBands];
@@ -139,6 +141,10 @@ struct gw_handle {
     int pdl;                // launch the step kernel with programmatic stream serialization
     double *pos_cur;        // per-env geometry: current device positions [ntab][GW_MAX_DEVICES][2]
     int stepped;            // a step has been launched: gw_set_positions moves devices from now on
+    // bit v: the dynamic shared-memory limit of step-kernel variant v (0 traced, 1 mode R, 2 Philox, 3 fed)
+    // has been raised on THIS handle's device (the attribute is per device, and a handle is driven by
+    // one host thread at a time -- include/gymwipe_b200.h)
+    unsigned smem_configured;
 };
 
 // ------------------------------------------------------------------------------------
@@ -513,6 +519,15 @@ struct MaskSource {
 #ifndef GW_MASK_LOAD
 #define GW_MASK_LOAD __ldcs
 #endif
+#ifndef GW_FED_U
+#define GW_FED_U 4
+#endif
+#ifdef GW_FED_NO_PREFETCH
+#define FED_FIRST_PASS 1
+#else
+#define FED_FIRST_PASS 0
+#endif
+constexpr int FED_U = GW_FED_U;         // 128-bit loads per lane and mask row in flight in the cooperative scan
 
 __device__ __forceinline__ int popc4(uint4 v) { return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
 
@@ -561,13 +576,54 @@ __device__ __forceinline__ int warp_popc_range(const uint32_t *row, int k0, int 
 }
 
 // the same count by ONE lane (every lane of a warp scanning a range of its own)
-__device__ __forceinline__ int lane_popc_range(const uint32_t *row, int k0, int k1)
+__device__ __noinline__ int lane_popc_range(const uint32_t *row, int k0, int k1)
 {
     int n = 0;
     const int q0 = k0 >> 7, q1 = (k1 - 1) >> 7;
     const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
     for (int q = q0; q <= q1; ++q) n += popc_group(__ldg(row4 + q), q, q0, q1, k0, k1);
     return n;
+}
+
+// mask of the bits of 16-byte group g that lie inside the bit range [k0, k1) (branch-free: all ones for
+// interior groups, a prefix / suffix for the first / last group, zero outside)
+__device__ __forceinline__ unsigned word_mask(int lo, int hi)     // bits [lo, hi) of a 32-bit word, any ints
+{
+    const unsigned upto_hi = hi >= 32 ? 0xFFFFFFFFu : (hi <= 0 ? 0u : ((1u << hi) - 1u));
+    const unsigned upto_lo = lo >= 32 ? 0xFFFFFFFFu : (lo <= 0 ? 0u : ((1u << lo) - 1u));
+    return upto_hi & ~upto_lo;
+}
+__device__ __forceinline__ uint4 range_mask(int g, int k0, int k1)
+{
+    const int lo = k0 - g * 128, hi = k1 - g * 128;
+    return make_uint4(word_mask(lo, hi), word_mask(lo - 32, hi - 32), word_mask(lo - 64, hi - 64), word_mask(lo - 96, hi - 96));
+}
+__device__ __forceinline__ int popc4_and(uint4 v, uint4 m)
+{
+    return __popc(v.x & m.x) + __popc(v.y & m.y) + __popc(v.z & m.z) + __popc(v.w & m.w);
+}
+
+// the same count for a range of at most FED_TINY 16-byte groups: all loads are issued before the first
+// popcount (headers, announcement payloads)
+constexpr int FED_TINY = 4;
+__device__ __forceinline__ int lane_popc_small(const uint32_t *row, int k0, int k1)
+{
+    const int q0 = k0 >> 7, q1 = (k1 - 1) >> 7;
+    const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
+    uint4 v[FED_TINY];
+#pragma unroll
+    for (int u = 0; u < FED_TINY; ++u) v[u] = (q0 + u <= q1) ? __ldg(row4 + q0 + u) : make_uint4(0, 0, 0, 0);
+    int n = 0;
+#pragma unroll
+    for (int u = 0; u < FED_TINY; ++u) n += popc4_and(v[u], range_mask(q0 + u, k0, k1));
+    return n;
+}
+
+// fire-and-forget request to bring `bytes` (a multiple of 16) at `p` (16-byte aligned) into L2: one
+// instruction per mask row (SASS UBLKPF), no registers or shared memory held while the row is in flight
+__device__ __forceinline__ void prefetch_bulk_l2(const void *p, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(bytes) : "memory");
 }
 
 // Philox-generated masks: bit k is an error iff word (k & 3) of block (k >> 2) < thr
@@ -605,6 +661,7 @@ struct StepArgs {
     unsigned char *done;
     double *stats;
     int *errflag;
+    unsigned long long *maskBytes;      // mode M fed: bytes of mask words the step kernels scanned (statistic)
     MaskSource masks;
     DevMemo memo;
     // compact outputs (gw_step_host_packed): used instead of obs / reward when non-NULL
@@ -734,6 +791,177 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
                 for (int o = 1; o < nb; o <<= 1) Tend = fmax(Tend, __shfl_xor_sync(0xFFFFFFFFu, Tend, o));
                 if (active && s.now < Tend) run_until_time<MODE_R>(s, P, B, srx, ring, NoMasks(), Tend, memo);
             }
+        } else if (MODE == MODE_M_FED) {
+            // Mode M with fed masks.  The count of a section does not depend on the segmentation
+            // (gw_core.cuh::fed_decide_set), so only DECIDING events read mask words.  Two alternating parts:
+            //  (1) serial: every lane runs ahead, at its own pace, through its events (the cheap per-lane
+            //      loop of mode R).  Decisions over a few 16-byte groups (headers, announcements) are
+            //      counted on the spot -- their cache line was requested into L2 when the transmission
+            //      started -- and a lane stops in front of a decision over a LONG range;
+            //  (2) warp-uniform: the pending long ranges of all 32 lanes are counted together, four rows
+            //      at a time (one per group of eight lanes, each reading whole 128-byte lines), in two
+            //      passes: the first only requests every line of every row into L2 (prefetch: nothing is
+            //      held in registers while ALL rows of the warp are in flight), the second loads (L2 hits,
+            //      FED_U 128-bit loads per lane in flight), popcounts and reduces within the eight lanes.
+            //      The event itself is applied at the head of part (1): the transition function has ONE
+            //      call site (code size).
+            double Tend = INFINITY;
+            int phase = 0;      // 0: until the own ASSIGN is processed, 1: until Tend
+            const long long wpr = A.masks.words_per_row;
+            unsigned maskWords = 0;
+            Event ev; ev.kind = EV_NONE; ev.idx = 0; ev.t = 0; ev.seq = 0;
+            int need = 0, k0c = 0, k1c = 0;
+            long long rowbase = 0;
+            int cnt[D];
+#pragma unroll
+            for (int p = 0; p < D; ++p) cnt[p] = 0;
+            for (;;) {
+                if (active) {
+                    while (!s.fault) {
+                        int nd = need;                  // a pending long decision: its counts have arrived
+                        need = 0;
+                        if (!nd) {
+                            if (phase == 0 && s.assignDone) break;
+                            ev = next_event(s, B, phase == 0 ? (double)INFINITY : Tend);
+                            if (phase == 1 && !(ev.t < Tend)) break;
+                            nd = fed_decide_set(s, ev);
+                            if (nd) {
+                                s.now = ev.t;
+                                int sender = 0; uint32_t txseq = 0;
+                                bool first = true, uniform = true;
+#pragma unroll
+                                for (int p = 0; p < D; ++p) {
+                                    if (!((nd >> p) & 1)) continue;
+                                    int64_t a0, a1;
+                                    mask_range(s, p, P.bitRate, sender, txseq, a0, a1);
+                                    if (first) { k0c = (int)a0; k1c = (int)a1; first = false; }
+                                    else uniform &= ((int)a0 == k0c) & ((int)a1 == k1c);
+                                }
+                                rowbase = ((((env * nb + band) * kMaxDev + sender) * A.masks.slots
+                                            + (long long)(txseq % (uint32_t)A.masks.slots)) * kMaxDev) * wpr;
+#pragma unroll
+                                for (int p = 0; p < D; ++p) cnt[p] = 0;
+#ifndef GW_PROBE_NOSCAN
+                                const int groups = k1c > k0c ? ((k1c - 1) >> 7) - (k0c >> 7) + 1 : 0;
+                                if (!uniform) {
+                                    // the receivers' segments differ (a position change cut one of them): rare
+#pragma unroll 1
+                                    for (int p = 0; p < D; ++p) {
+                                        if (!((nd >> p) & 1)) continue;
+                                        int sd; uint32_t tq; int64_t a0, a1;
+                                        mask_range(s, p, P.bitRate, sd, tq, a0, a1);
+                                        if (a1 > a0) {
+                                            const int c = lane_popc_range(A.masks.words + rowbase + p * wpr, (int)a0, (int)a1);
+#pragma unroll
+                                            for (int pp = 0; pp < D; ++pp) cnt[pp] = pp == p ? c : cnt[pp];
+                                            maskWords += (unsigned)((((int)a1 + 31) >> 5) - ((int)a0 >> 5));
+                                        }
+                                    }
+                                } else if (groups > 0) {
+                                    maskWords += (unsigned)__popc(nd) * (unsigned)(((k1c + 31) >> 5) - (k0c >> 5));
+                                    if (groups <= FED_TINY) {
+#pragma unroll
+                                        for (int p = 0; p < D; ++p)
+                                            if ((nd >> p) & 1) cnt[p] = lane_popc_small(A.masks.words + rowbase + p * wpr, k0c, k1c);
+                                    } else {
+                                        need = nd;      // counted by the whole warp below
+                                        break;
+                                    }
+                                }
+#endif
+                            }
+                        }
+                        if (nd) {
+#pragma unroll
+                            for (int p = 0; p < D; ++p)
+                                if ((nd >> p) & 1) { s.err[p] += (double)cnt[p]; s.segT0[p] = ev.t; }
+                        }
+                        const int d = ev.idx;
+                        const bool starts = ev.kind == EV_PHY && get_at(s.sphase, d) == S_SLOT;
+                        s.now = ev.t;
+                        const int berMask = apply_event(s, P, B, ev, srx, ring);
+                        update_bers(s, P, berMask, srx, memo);
+#ifndef GW_FED_NO_PREFETCH
+                        if (starts) {
+                            // the first line of the rows of the receivers that locked on: header (and
+                            // announcement payload) decisions will find it in L2
+                            const uint32_t q = get_at(s.txSeq, d) - 1u;
+                            const long long rb = ((((env * nb + band) * kMaxDev + d) * A.masks.slots
+                                                   + (long long)(q % (uint32_t)A.masks.slots)) * kMaxDev) * wpr;
+#pragma unroll
+                            for (int p = 0; p < D; ++p)
+                                if (p != d && s.rxOf[p] == d) prefetch_l2(A.masks.words + rb + p * wpr);
+                        }
+#endif
+                    }
+                    if (s.fault) need = 0;
+                }
+                const unsigned pend = __ballot_sync(0xFFFFFFFFu, need != 0);
+                if (pend == 0) {
+                    if (phase == 0 && nb > 1) {
+                        double t = active ? s.now : -INFINITY;
+                        for (int o = 1; o < nb; o <<= 1) t = fmax(t, __shfl_xor_sync(0xFFFFFFFFu, t, o));
+                        Tend = t;
+                        phase = 1;
+                        continue;
+                    }
+                    break;
+                }
+                // ---- (2) the long ranges of the pending decisions, four rows at a time
+                const int oct = lane >> 3, sub = lane & 7;
+#pragma unroll 1
+                for (int pass = FED_FIRST_PASS; pass < 2; ++pass) {
+#pragma unroll 1
+                    for (int p = 0; p < D; ++p) {
+                        unsigned M = __ballot_sync(0xFFFFFFFFu, (need >> p) & 1);
+                        while (M) {
+                            const int s0 = __ffs(M) - 1; M &= M - 1;
+                            const int s1 = __ffs(M) - 1; M &= M - 1;        // -1 when M ran empty (0 & x stays 0)
+                            const int s2 = __ffs(M) - 1; M &= M - 1;
+                            const int s3 = __ffs(M) - 1; M &= M - 1;
+                            const int src = oct == 0 ? s0 : (oct == 1 ? s1 : (oct == 2 ? s2 : s3));
+                            const int from = src < 0 ? 0 : src;
+                            const long long rb = __shfl_sync(0xFFFFFFFFu, rowbase, from);
+                            const int a0 = __shfl_sync(0xFFFFFFFFu, k0c, from), a1 = __shfl_sync(0xFFFFFFFFu, k1c, from);
+                            const int q0 = a0 >> 7, q1 = src < 0 ? -1 : ((a1 - 1) >> 7);
+                            const uint4 *row4 = reinterpret_cast<const uint4 *>(A.masks.words + rb + p * wpr);
+                            if (pass == 0) {
+                                // every 128-byte line of the range (row4 is 16-byte aligned: lines by group / 8)
+                                for (int g = (q0 & ~7) + 8 * sub; g <= q1; g += 64) prefetch_l2(row4 + (g < q0 ? q0 : g));
+                                continue;
+                            }
+                            int tot = 0;
+#pragma unroll 1
+                            for (int gb = q0 + sub; gb <= q1; gb += 8 * FED_U) {
+                                uint4 v[FED_U];
+#pragma unroll
+                                for (int u = 0; u < FED_U; ++u)
+                                    v[u] = gb + 8 * u <= q1 ? GW_MASK_LOAD(row4 + gb + 8 * u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                                for (int u = 0; u < FED_U; ++u) {
+                                    const int g = gb + 8 * u;
+                                    int c = popc4(v[u]);
+                                    if (g == q0 || g == q1) c = popc4_and(v[u], range_mask(g, a0, a1));
+                                    tot += c;
+                                }
+                            }
+                            tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 4);
+                            tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 2);
+                            tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 1);
+                            const int rank = lane == s0 ? 0 : (lane == s1 ? 1 : (lane == s2 ? 2 : (lane == s3 ? 3 : -1)));
+                            const int val = __shfl_sync(0xFFFFFFFFu, tot, rank < 0 ? 0 : 8 * rank);
+                            if (rank >= 0) {
+#pragma unroll
+                                for (int pp = 0; pp < D; ++pp) cnt[pp] = pp == p ? val : cnt[pp];
+                            }
+                        }
+                    }
+                }
+            }
+            if (active && nb > 1) s.now = Tend;
+            // statistic: mask bytes scanned by this block
+            maskWords = __reduce_add_sync(0xFFFFFFFFu, maskWords);
+            if (lane == 0 && maskWords != 0 && A.maskBytes != nullptr) atomicAdd(A.maskBytes, 4ull * maskWords);
         } else {
             // warp-synchronous event loop: one timed event per lane and iteration; the error
             // counts of all lanes are serviced cooperatively (ballot / popc / shuffle)
@@ -806,7 +1034,11 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
                             if (MODE == MODE_M_FED) {
                                 const long long row = ((((env * nb + band) * kMaxDev + sender) * A.masks.slots
                                                         + (long long)(txseq % (uint32_t)A.masks.slots)) * kMaxDev + p);
+#ifdef GW_PROBE_NOSCAN
+                                cnt = 0; (void)row;
+#else
                                 cnt = lane_popc_range(A.masks.words + row * A.masks.words_per_row, (int)k0, (int)k1);
+#endif
                             } else {
                                 cnt = mask_errors_serial(A.masks.seed, A.masks.env_offset + env, band, sender, txseq, p,
                                                          k0, k1, get_at(s.ber, p));
@@ -840,7 +1072,11 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
                         if (MODE == MODE_M_FED) {
                             const long long row = ((((senv * nb + sband) * kMaxDev + sender) * A.masks.slots
                                                     + (long long)(txseq % (uint32_t)A.masks.slots)) * kMaxDev + p);
+#ifdef GW_PROBE_NOSCAN
+                            cnt = 0; (void)row;
+#else
                             cnt = warp_popc_range(A.masks.words + row * A.masks.words_per_row, ik0, ik1, lane);
+#endif
                         } else {
                             const uint32_t thr = ber_threshold(__shfl_sync(0xFFFFFFFFu, berp, src));
                             cnt = warp_philox_range(A.masks.seed, A.masks.env_offset + senv, sband, sender, txseq, p,
@@ -1566,7 +1802,7 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
     }
     cudaStream_t s = (cudaStream_t)stream;
     const long long nsim = h->st.nsim;
-    const size_t aux = 8 * sizeof(double) + 4 * sizeof(int);
+    const size_t aux = 8 * sizeof(double) + 4 * sizeof(int) + 2 * sizeof(unsigned long long);
     void *stg = nullptr;
     cudaError_t e = cudaMalloc((void **)&h->stats, aux);
     if (e == cudaSuccess) e = cudaMemsetAsync(h->stats, 0, aux, s);
@@ -1586,6 +1822,7 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
         if (e != cudaSuccess) { cudaFree(stg); gw_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
     }
     h->errflag = (int *)(h->stats + 8);
+    h->mask_bytes = (unsigned long long *)(h->errflag + 4);
     h->stats_use = h->stats;
     h->d_obs = (long long *)stg;                            // base of the staging allocation
     h->d_rew = (double *)(h->d_obs + nsim);
@@ -1701,7 +1938,7 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     A.st = h->st;
     A.device = device; A.duration = duration;
     A.obs = (long long *)obs; A.reward = reward; A.done = done;
-    A.stats = h->stats_use; A.errflag = h->errflag;
+    A.stats = h->stats_use; A.errflag = h->errflag; A.maskBytes = h->mask_bytes;
     A.obs32 = obs32; A.reward32 = reward32;
     A.act8 = act8; A.res32 = res32;
     A.sim_begin = sim_begin; A.sim_end = sim_end < 0 ? h->st.nsim : sim_end;
@@ -1735,13 +1972,12 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     int blocks = grid_for(A.sim_end - A.sim_begin, STEP_BLOCK);
     const int cap = 148 * GW_STEP_MIN_BLOCKS * 4;
     if (blocks > cap) blocks = cap;
-#define LAUNCH_STEP(KERNEL, DD, SS, JJ)                                                              \
+#define LAUNCH_STEP(KERNEL, VARIANT, DD, SS, JJ)                                                     \
     do {                                                                                             \
         constexpr int smem = Sim<DD, SS, JJ, ShStore>::kDirectBytes * STEP_BLOCK;                     \
-        static bool configured = false;                                                              \
-        if (!configured) {                                                                           \
+        if (!(h->smem_configured & (1u << (VARIANT)))) {                                             \
             CUDA_TRY(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-            configured = true;                                                                       \
+            h->smem_configured |= 1u << (VARIANT);                                                   \
         }                                                                                            \
         cudaLaunchConfig_t lc = {};                                                                  \
         lc.gridDim = dim3((unsigned)blocks); lc.blockDim = dim3(STEP_BLOCK);                         \
@@ -1754,10 +1990,10 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     } while (0)
 #define CALL_STEP(DD, SS, JJ)                                                                        \
     do {                                                                                             \
-        if (trace) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ, true>), DD, SS, JJ);                  \
-        else if (h->cfg.mode == GW_MODE_REFERENCE) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ>), DD, SS, JJ);  \
-        else if (h->cfg.mode == GW_MODE_MASK_PHILOX) LAUNCH_STEP((step_kernel<MODE_M_PHILOX, DD, SS, JJ>), DD, SS, JJ); \
-        else LAUNCH_STEP((step_kernel<MODE_M_FED, DD, SS, JJ>), DD, SS, JJ);                          \
+        if (trace) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ, true>), 0, DD, SS, JJ);               \
+        else if (h->cfg.mode == GW_MODE_REFERENCE) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ>), 1, DD, SS, JJ);  \
+        else if (h->cfg.mode == GW_MODE_MASK_PHILOX) LAUNCH_STEP((step_kernel<MODE_M_PHILOX, DD, SS, JJ>), 2, DD, SS, JJ); \
+        else LAUNCH_STEP((step_kernel<MODE_M_FED, DD, SS, JJ>), 3, DD, SS, JJ);                       \
     } while (0)
     DISPATCH_SHAPE(h, CALL_STEP);
 #undef CALL_STEP
@@ -1877,6 +2113,20 @@ static int step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *res
     return GW_OK;
 }
 
+int gw_step_host_compact_many(gw_handle *const *handles, int32_t n_handles, const uint8_t *const *actions,
+                              uint32_t *const *results, void *stream)
+{
+    if (!handles || !actions || !results || n_handles < 1) return fail(GW_E_INVALID, "bad argument");
+    for (int k = 0; k < n_handles; ++k) {
+        if (!handles[k]) return fail(GW_E_INVALID, "handle %d is NULL", k);
+        if (handles[k]->device != handles[0]->device) return fail(GW_E_INVALID, "the handles of one call live on one device");
+        const int rc = step_host_compact(handles[k], actions[k], results[k], stream, false);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return GW_OK;
+}
+
 int gw_check(gw_handle *h, void *stream)
 {
     if (!h) return fail(GW_E_INVALID, "handle is NULL");
@@ -1902,6 +2152,17 @@ int gw_stats(gw_handle *h, double *out8, int clear, void *stream)
     CUDA_TRY(cudaSetDevice(h->device));
     stats_copy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->stats_use, out8, clear);
     CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_mask_bytes(gw_handle *h, uint64_t *out, int clear, void *stream)
+{
+    if (!h || !out) return fail(GW_E_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(out, h->mask_bytes, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (clear) CUDA_TRY(cudaMemsetAsync(h->mask_bytes, 0, sizeof(uint64_t), s));
     return GW_OK;
 }
 
@@ -1966,15 +2227,26 @@ int gw_count_bit_errors(const uint32_t *mask_words, int32_t words_per_row, const
     if (n <= 0) return GW_OK;
     if (words_per_row < 4 || (words_per_row & 3) || ((uintptr_t)mask_words & 15)) return fail(GW_E_INVALID, "bad mask layout");
     cudaStream_t st = (cudaStream_t)stream;
-    static int sms = 0, occ_reg = 0, occ_tma = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_reg, count_bits_kernel, 256, 0) != cudaSuccess || occ_reg < 1) occ_reg = 6;
-        cudaFuncSetAttribute(count_bits_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tma, count_bits_tma_kernel, 256, TMA_SMEM_BYTES) != cudaSuccess || occ_tma < 1) occ_tma = 3;
-        if (sms < 1) sms = 148;
+    // launch geometry per DEVICE (the shared-memory attribute and the occupancy are per device), guarded:
+    // this entry point has no handle, so several host threads may come through here at once
+    struct K3Geometry { int sms, occ_reg, occ_tma; };
+    static K3Geometry geo[64];
+    static std::mutex geo_mutex;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(GW_E_INVALID, "device ordinal %d out of range", dev);
+    int sms, occ_reg, occ_tma;
+    {
+        std::lock_guard<std::mutex> lock(geo_mutex);
+        K3Geometry &g = geo[dev];
+        if (g.sms == 0) {
+            cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, dev);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_reg, count_bits_kernel, 256, 0) != cudaSuccess || g.occ_reg < 1) g.occ_reg = 6;
+            cudaFuncSetAttribute(count_bits_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g.occ_tma, count_bits_tma_kernel, 256, TMA_SMEM_BYTES) != cudaSuccess || g.occ_tma < 1) g.occ_tma = 3;
+            if (g.sms < 1) g.sms = 148;
+        }
+        sms = g.sms; occ_reg = g.occ_reg; occ_tma = g.occ_tma;
     }
     // persistent grid: one full wave (SM count x resident blocks per SM), 8 warps per block.
     // Default: the register-staged kernel (measured 5.97 TB/s = 91 % of the measured HBM peak).

@@ -5,6 +5,7 @@ instantiates them (gym itself is not a dependency).
 from gymwipe_b200.envs.counter_traffic import CounterTrafficEnv
 from gymwipe_b200.envs.core import BaseEnv, Interpreter
 from gymwipe_b200.envs.inverted_pendulum import InvertedPendulumEnv
+from gymwipe_b200.envs.population import EnvPopulation
 
 registry = {
     'CounterTraffic-v0': CounterTrafficEnv,
@@ -23,4 +24,4 @@ def make(id, **kwargs):
     return registry[id](**kwargs)
 
 
-__all__ = ["CounterTrafficEnv", "InvertedPendulumEnv", "BaseEnv", "Interpreter", "make", "register", "registry"]
+__all__ = ["CounterTrafficEnv", "InvertedPendulumEnv", "EnvPopulation", "BaseEnv", "Interpreter", "make", "register", "registry"]

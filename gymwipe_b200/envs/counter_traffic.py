@@ -276,6 +276,14 @@ class CounterTrafficEnv(BaseEnv):
             N.check(self._lib.gw_stats(self._handle, out.data_ptr(), 1 if clear else 0, self._stream()))
         return out
 
+    def mask_bytes(self, clear=True):
+        """Mode ``mask_fed``: bytes of mask words the step kernels scanned since the last clearing call
+        (``gw_mask_bytes``; synchronises)."""
+        out = C.c_uint64(0)
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gw_mask_bytes(self._handle, C.byref(out), 1 if clear else 0, self._stream()))
+        return int(out.value)
+
     def share_stats(self, other):
         """
         Accumulate this env's step statistics into ``other``'s vector (``gw_share_stats``): several env

@@ -184,8 +184,9 @@ int gw_step_host(gw_handle *h, const int32_t *device, const int32_t *duration,
 int gw_step_host_packed(gw_handle *h, const int32_t *actions, void *results, void *stream);
 
 /* Compact host-buffer variant (the transfers, not the kernel, bound the end-to-end rate):
- * `actions` = uint8 [2][n_sims] (row 0 action["device"], row 1 action["duration"], both < 256 by the
- * action space: Discrete(2) x Discrete(MAX_ASSIGN_DURATION), envs/core.py:39-42) and `results` =
+ * `actions` = uint8 [n_sims][2] -- per sim the byte pair { action["device"], action["duration"] }, i.e.
+ * actions[2*i] = device and actions[2*i + 1] = duration of sim i (both < 256 by the action space:
+ * Discrete(2) x Discrete(MAX_ASSIGN_DURATION), envs/core.py:39-42) -- and `results` =
  * uint32 [n_sims], one word per sim:
  *     bits  0..16  observation (Discrete(131072), counter_traffic.py:120)
  *     bits 17..21  reward + 16  (rewards are integers in [-10, 10], counter_traffic.py:96-107)
@@ -200,6 +201,13 @@ int gw_step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *results
  * the step on `stream` and returns; `results` is valid once the stream (or an event recorded after the
  * call) has completed.  PINNED host buffers only (GW_E_INVALID otherwise). */
 int gw_step_host_compact_async(gw_handle *h, const uint8_t *actions, uint32_t *results, void *stream);
+/* One env.step of a POPULATION of env batches held by several handles on one device (a vector env whose
+ * state is split into independently allocated batches): the steps of all handles are enqueued back to
+ * back on `stream` -- each reads its own actions[k] / writes its own results[k], layouts as above, PINNED
+ * host buffers -- and the call synchronises ONCE.  The launch and wake-up latency of a synchronous step
+ * is paid per population, not per batch. */
+int gw_step_host_compact_many(gw_handle *const *handles, int32_t n_handles, const uint8_t *const *actions,
+                              uint32_t *const *results, void *stream);
 #define GW_COMPACT_OBS(w)    ((int32_t)((w) & 0x1FFFFu))
 #define GW_COMPACT_REWARD(w) ((int32_t)(((w) >> 17) & 31u) - 16)
 #define GW_COMPACT_DONE(w)   ((int32_t)(((w) >> 22) & 1u))
@@ -215,6 +223,13 @@ int gw_check(gw_handle *h, void *stream);
  * accumulators are cleared after the copy when `clear` != 0.  Feeds the learner
  * (agents/dqn_counter_traffic.py:70) -- and the NCCL all-reduce when envs are sharded. */
 int gw_stats(gw_handle *h, double *out8, int clear, void *stream);
+
+/* Mode M with fed masks: bytes of mask words the step kernels have read for their error counts since
+ * the last clearing call -- per decided section the 32-bit words that hold its on-air bits
+ * (SimplePhy._countBitErrors with per-bit masks, simple_stack.py:180-188).  This is the algorithmic
+ * traffic of the HBM-bound part of the step (bench.py's roofline of configs[2]).  `out` is a HOST
+ * uint64; synchronises `stream`. */
+int gw_mask_bytes(gw_handle *h, uint64_t *out, int clear, void *stream);
 
 /* Several handles on one device (e.g. env batches stepped round-robin) can accumulate into ONE
  * statistics vector: after gw_share_stats(h, with) the step kernels of `h` add to the accumulators of

@@ -35,6 +35,35 @@ struct HostMasks {
     }
 };
 
+// mode M with FED masks: words laid out [nenv][nbands][4 sender][slots][4 receiver][words_per_row]
+struct HostFedMasks {
+    const uint32_t *words; int slots, wpr; int64_t env; int band, nb;
+    int64_t operator()(int receiver, int sender, uint32_t txseq, int64_t k0, int64_t k1, double) const
+    {
+        const int64_t row = ((((env * nb + band) * kMaxDev + sender) * slots + (int64_t)(txseq % (uint32_t)slots)) * kMaxDev + receiver);
+        const uint32_t *w = words + row * wpr;
+        int64_t n = 0;
+        for (int64_t k = k0; k < k1; ++k) n += (w[k >> 5] >> (k & 31)) & 1u;
+        return n;
+    }
+};
+static const uint32_t *g_fed_words = nullptr;
+static int g_fed_slots = 0, g_fed_wpr = 0;
+
+template <int MODE>
+struct MasksFor {
+    using type = HostMasks;
+    static HostMasks make(uint64_t seed, int64_t env, int64_t, int band, int) { return HostMasks{seed, env, band}; }
+};
+template <>
+struct MasksFor<MODE_M_FED> {
+    using type = HostFedMasks;
+    static HostFedMasks make(uint64_t, int64_t, int64_t local_env, int band, int nb)
+    {
+        return HostFedMasks{g_fed_words, g_fed_slots, g_fed_wpr, local_env, band, nb};
+    }
+};
+
 struct HsBand {
     int32_t ns, nj;
     double frequency, bandwidth;
@@ -145,7 +174,7 @@ int run_t(const HsScenario &sc, int64_t nenv, int nsteps, int do_reset, const do
                     }
                 if (!any) continue;
                 HostTab<D> tab{E.att[b], E.srx[b]};
-                HostMasks mk{sc.seed, env_offset + e, b};
+                auto mk = MasksFor<MODE>::make(sc.seed, env_offset + e, e, b, nb);
                 double power[D];
                 for (int d = 0; d < D; ++d) power[d] = sc.band[b].power[d];
                 move_devices<MODE>(E.sim[b], P, power, sc.band[b].frequency, E.pos[b], want, tab, mk, NoMemo());
@@ -155,13 +184,13 @@ int run_t(const HsScenario &sc, int64_t nenv, int nsteps, int do_reset, const do
             }
             for (int b = 0; b < nb; ++b) {
                 HostRing r{E.ring[b]};
-                HostMasks mk{sc.seed, env_offset + e, b};
+                auto mk = MasksFor<MODE>::make(sc.seed, env_offset + e, e, b, nb);
                 run_until_assign<MODE>(E.sim[b], P, P.band[b], E.srx[b], r, mk);
                 if (E.sim[b].now > T) T = E.sim[b].now;
             }
             for (int b = 0; b < nb; ++b) {
                 HostRing r{E.ring[b]};
-                HostMasks mk{sc.seed, env_offset + e, b};
+                auto mk = MasksFor<MODE>::make(sc.seed, env_offset + e, e, b, nb);
                 if (E.sim[b].now < T) run_until_time<MODE>(E.sim[b], P, P.band[b], E.srx[b], r, mk, T);
                 long long o; double rw; unsigned char dn;
                 feedback(E.sim[b], o, rw, dn);
@@ -214,6 +243,10 @@ int hs_run_moves(const HsScenario *sc, int64_t nenv, int nsteps, int do_reset, c
     if (sc->mode == MODE_R) {
         if (ns == 2 && nj == 0) return run_t<MODE_R, 3, 2, 0>(HS_ARGS);
         if (ns == 2 && nj == 1) return run_t<MODE_R, 4, 2, 1>(HS_ARGS);
+    } else if (sc->mode == MODE_M_FED) {
+        if (!g_fed_words) return -2;
+        if (ns == 2 && nj == 0) return run_t<MODE_M_FED, 3, 2, 0>(HS_ARGS);
+        if (ns == 2 && nj == 1) return run_t<MODE_M_FED, 4, 2, 1>(HS_ARGS);
     } else {
         if (ns == 2 && nj == 0) return run_t<MODE_M_PHILOX, 3, 2, 0>(HS_ARGS);
         if (ns == 2 && nj == 1) return run_t<MODE_M_PHILOX, 4, 2, 1>(HS_ARGS);
@@ -223,6 +256,9 @@ int hs_run_moves(const HsScenario *sc, int64_t nenv, int nsteps, int do_reset, c
 }
 
 void hs_set_no_macro(int v) { g_no_macro = v; }
+
+// mode 2 (fed masks): the mask words of the next hs_run* call
+void hs_set_fed_masks(const uint32_t *words, int slots, int words_per_row) { g_fed_words = words; g_fed_slots = slots; g_fed_wpr = words_per_row; }
 
 // macro-event statistics since the last call: {isolated transmissions, quiet tails}
 void hs_macro_stats(long long *out2) { out2[0] = g_macro_stat[0]; out2[1] = g_macro_stat[1]; g_macro_stat[0] = g_macro_stat[1] = 0; }

@@ -67,6 +67,7 @@ def lib():
         L.hs_airtime.restype = C.c_double
         L.hs_airtime.argtypes = [C.c_int]
         L.hs_pendulum_advance.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+        L.hs_set_fed_masks.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.hs_mask_errors.restype = C.c_int64
         L.hs_mask_errors.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_uint32, C.c_int,
                                      C.c_int64, C.c_int64, C.c_double]
@@ -106,9 +107,13 @@ def scenario_from_dict(d, mode=0, seed=0):
     return sc
 
 
-def run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, mode=0, seed=0, env_offset=0, macros=True, moves=None):
+def run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, mode=0, seed=0, env_offset=0, macros=True, moves=None,
+        fed_words=None, fed_slots=0):
     L = lib()
     L.hs_set_no_macro(-1 if macros else 1)
+    if fed_words is not None:           # mode 2: uint32 [nenv][nbands][4][slots][4][words_per_row]
+        fed_words = np.ascontiguousarray(fed_words, dtype=np.uint32)
+        L.hs_set_fed_masks(fed_words.ctypes.data_as(C.c_void_p), int(fed_slots), int(fed_words.shape[-1]))
     sc = scenario_from_dict(scenario, mode, seed) if isinstance(scenario, dict) else scenario
     nb = sc.nbands
     dev_tape = np.ascontiguousarray(dev_tape, dtype=np.int32)

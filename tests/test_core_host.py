@@ -276,3 +276,59 @@ def test_core_moving_devices_corner_cases_vs_oracle(seed):
     assert [s["obs"] for s in res["steps"]] == list(h["obs"][:, 0, 0])
     assert [s["reward"] for s in res["steps"]] == list(h["reward"][:, 0, 0])
     assert [s["now"] for s in res["steps"]] == list(h["now"][:, 0])
+
+
+def _random_fed_masks(rs, nenv, nb, slots, words):
+    """Bernoulli(p) flags with p per (env, sender, slot, receiver): some sections fail, some pass."""
+    p = rs.uniform(0.02, 0.3, size=(nenv, nb, 4, slots, 4, 1))
+    bits = rs.random_sample((nenv, nb, 4, slots, 4, words * 32)) < p
+    m = np.packbits(bits.reshape(-1, 8)[:, ::-1], axis=1).reshape(nenv, nb, 4, slots, 4, words * 4)
+    return np.ascontiguousarray(m.view("<u4").reshape(nenv, nb, 4, slots, 4, words))
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_core_mode_m_fed_deferred_counts_vs_oracle(seed):
+    """Mode M with FED masks: the core counts a section once, at its decision (fed_decide_set); the oracle
+    counts every constant-SINR segment.  Both see the same mask words: results are identical."""
+    rs = np.random.RandomState(9100 + seed)
+    for sc, nenv, nsteps, words in [(random_scenario(rs, jammers=1, spread=2.5), 12, 60, 64),
+                                    (random_scenario(rs, jammers=1, spread=2.0, fixed_payload=600, factor=10000), 6, 30, 208),
+                                    (random_scenario(rs, jammers=0, spread=2.0), 12, 60, 64)]:
+        slots = 3
+        masks = _random_fed_masks(rs, nenv, 1, slots, words)
+        dev, dur = random_tapes(rs, nsteps, nenv, 1)
+        if sc["bands"][0]["devices"][0]["payload"] == "counter":
+            dur = np.minimum(dur, 9)          # counter payloads: keep packets inside the 64-word rows
+        o = O.run_batch(sc, dev, dur, mode=O.MODE_M, fed_words=masks, fed_slots=slots)
+        h = HS.run(sc, dev, dur, mode=2, fed_words=masks, fed_slots=slots)
+        assert h["rc"] == 0
+        assert (o["obs"] == h["obs"]).all() and (o["reward"] == h["reward"]).all()
+        assert (o["now"] == h["now"]).all()
+        assert (o["counts"][:, :, :3] == h["counts"][:, :, :3]).all()
+        assert o["counts"][:, :, 1:3].sum() > 0
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_core_mode_m_fed_moving_devices_vs_oracle(seed):
+    """Fed masks with devices jumping between steps: a position change cuts the running segment
+    (received_power_change counts it and restarts segT0), the decision counts the rest."""
+    rs = np.random.RandomState(9200 + seed)
+    sc = random_scenario(rs, jammers=1, spread=2.5)
+    sc["bands"][0]["devices"][3]["interval"] = float(rs.uniform(0.008, 0.02))
+    nsteps, slots, words = 70, 3, 64
+    dev, dur = random_tapes(rs, nsteps, 1, 1)
+    dur = np.minimum(dur, 9)
+    masks = _random_fed_masks(rs, 1, 1, slots, words)
+    moves = {}
+    for t in range(1, nsteps, 2):
+        devs = sorted(set(int(v) for v in rs.randint(4, size=int(rs.randint(1, 4)))))
+        moves[t] = [(0, d, float(rs.uniform(-3, 3)), float(rs.uniform(-3, 3))) for d in devs]
+    acts = [{"device": int(dev[t, 0, 0]), "duration": int(dur[t, 0, 0])} for t in range(nsteps)]
+    ora = O.Oracle(sc, mode=O.MODE_M)
+    ora.use_fed_masks(masks, slots)
+    res = O.run_tape(ora, acts, do_reset=True, moves=moves)
+    h = HS.run(sc, dev, dur, do_reset=True, moves=moves, mode=2, fed_words=masks, fed_slots=slots)
+    assert h["rc"] == 0
+    assert [s["obs"] for s in res["steps"]] == list(h["obs"][:, 0, 0])
+    assert [s["reward"] for s in res["steps"]] == list(h["reward"][:, 0, 0])
+    assert [s["now"] for s in res["steps"]] == list(h["now"][:, 0])
