@@ -5,11 +5,11 @@ bench.py -- env-steps/sec of the batched CounterTrafficEnv hot path (BASELINE.js
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Own arm: N ranks (one per GPU; torchrun supplies RANK / LOCAL_RANK / WORLD_SIZE for N > 1), each owning
-an independent POPULATION of `--batches` (default 272) batches of 65,536 envs (BASELINE configs[1]; weak
+an independent POPULATION of `--batches` (default 320) batches of 65,536 envs (BASELINE configs[1]; weak
 scaling).  One bench "step" is one `env.step` of EVERY env of the population: one launch of the fused step
 kernel per batch, the batches one after the other -- a batch is touched again only after all the others
 (gigabytes of other traffic), so every launch finds its inputs in HBM, not in L2 ("inputs larger than L2",
-no flush).  A step is ~2.5 ms of device time, so even the driver's `--steps 20` times > 50 ms.  W warm-up
+no flush).  A step is ~2.9 ms of device time, so even the driver's `--steps 20` times > 50 ms.  W warm-up
 steps, then EXACTLY K timed steps replayed from CUDA graphs (one per step), one CUDA-event pair around them
 on the launching stream, barrier + synchronize on both sides, max over ranks.  `e2e` is the same metric
 through the C ABI with pinned HOST buffers (`gw_step_host_compact_many`: actions read / results written in
@@ -34,7 +34,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 ENVS_PER_GPU = 65536
-POPULATION_BATCHES = 272               # 65,536-env batches per GPU: one bench step = one env.step of all of them (~2.5 ms)
+POPULATION_BATCHES = 320               # 65,536-env batches per GPU: one bench step = one env.step of all of them (~2.5 ms)
 E2E_BATCHES = 16                       # batches of the population stepped per host-buffer call (gw_step_host_compact_many)
 BURN_IN_STEPS = 128                    # steps of every env before the timed region (steady state, see own_arm)
 PRODUCTIVE_STEPS = 32                  # steps of every fresh env timed separately (productive regime)
@@ -591,15 +591,19 @@ def own_arm(args, rank, world, local_rank):
     extras = {}
     if not args.no_extras:
         peak, _ = measured_peak()
-        try:
-            for name, fn in (("cfg3_long_packet_mode_m", lambda: cfg3_long_packet(dev_t, peak, rank, world)),
-                             ("cfg4_multiband", lambda: cfg4_multiband(dev_t, rank, world)),
-                             ("cfg5_pendulum", lambda: cfg5_pendulum(dev_t, rank, world))):
-                r = fn()
-                torch.cuda.empty_cache()
-                if world > 1:                           # every rank its share; the slowest rank bounds the step
-                    t = torch.tensor([r["ms_per_step"]], dtype=torch.float64, device=dev_t)
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        for name, fn in (("cfg3_long_packet_mode_m", lambda: cfg3_long_packet(dev_t, peak, rank, world)),
+                         ("cfg4_multiband", lambda: cfg4_multiband(dev_t, rank, world)),
+                         ("cfg5_pendulum", lambda: cfg5_pendulum(dev_t, rank, world)),
+                         ("mask_scan", lambda: mask_scan_roofline(dev_t, peak, "random") if world == 1 else None)):
+            try:                                          # extras must never take the headline down
+                r, err = fn(), None
+            except Exception as exc:
+                r, err = None, repr(exc)
+            torch.cuda.empty_cache()
+            if world > 1:                               # every rank its share; the slowest rank bounds the step
+                t = torch.tensor([r["ms_per_step"] if r else float("inf")], dtype=torch.float64, device=dev_t)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                if r and float(t[0]) != float("inf"):
                     scale = r["ms_per_step"] / float(t[0])
                     r["ms_per_step"] = float(t[0])
                     for key in ("env_steps_per_s", "band_steps_per_s"):
@@ -608,14 +612,14 @@ def own_arm(args, rank, world, local_rank):
                     if "roofline" in r:
                         r["roofline"]["achieved"] *= scale
                         r["roofline"]["frac"] *= scale
-                        r["roofline"]["note"] = "per GPU, at the slowest rank's step time"
+                        r["roofline"]["note"] += "; per GPU, at the slowest rank's step time"
                     r["n_envs_total"] = r["n_envs"] * world
+                elif r:
+                    r, err = None, "another rank failed"
+            if r is not None:
                 extras[name] = r
-            if world == 1:
-                extras["mask_scan"] = mask_scan_roofline(dev_t, peak, "random")
-                torch.cuda.empty_cache()
-        except Exception as exc:                          # extras must never take the headline down
-            extras["extras_error"] = repr(exc)
+            elif err is not None:
+                extras[name + "_error"] = err
     if rank != 0:
         return 0
 

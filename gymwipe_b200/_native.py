@@ -131,6 +131,7 @@ _SIGNATURES = {
     "gw_check": (C.c_int, [_VP, _VP]),
     "gw_stats": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "gw_share_stats": (C.c_int, [_VP, _VP]),
+    "gw_debug_stamps": (C.c_int, [_VP, _VP, C.c_int64]),
     "gw_mask_bytes": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.c_int, _VP]),
     "gw_read_state": (C.c_int, [_VP, C.c_int, _VP, _VP]),
     "gw_set_masks": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP]),

@@ -256,9 +256,9 @@ struct Sim {
     RegArr<uint32_t, NS> sTick;
     RegArr<uint64_t, NS> ticks;         // ticks fired; packets enqueued = ticks * mult
     RegArr<int, NS> qn;                 // queue length (<= 100)
-    RegArr<uint64_t, NS> epochK;        // counter(tick k) = min(65536, epochC + (k - epochK))
+    RegArr<uint64_t, NS> epochK;        // counter(tick k) = min(65536, epochC + (k - epochK)); packets enqueued before
+                                        // tick epochK (index < epochK * mult) read their size from the snapshot ring
     RegArr<int, NS> epochC;
-    RegArr<uint64_t, NS> snapEnd;       // packets with index < snapEnd read their size from the ring
     Arr<int, NS, O_mac> mac;            // MAC_*
     Arr<int, NS, O_wDone> wDone;
     Arr<int, NS, O_wPend> wPend;
@@ -325,7 +325,7 @@ GW_HD void init_sim(Sim<D, NS, NJ, ST> &s, double thermal)
     GW_UNROLL
     for (int k = 0; k < NS; ++k) {
         s.tTick[k] = 0.0; s.sTick[k] = s.seq++;
-        s.ticks[k] = 0; s.qn[k] = 0; s.epochK[k] = 0; s.epochC[k] = 1; s.snapEnd[k] = 0;
+        s.ticks[k] = 0; s.qn[k] = 0; s.epochK[k] = 0; s.epochC[k] = 1;
         s.mac[k] = MAC_NONE; s.wDone[k] = 0; s.wPend[k] = 0; s.stopW[k] = 0; s.sW[k] = 0;
         s.nDeliv[k] = 0;
     }
@@ -727,7 +727,7 @@ GW_HD int head_size(const Sim<D, NS, NJ, ST> &s, const BandParams &B, int k, con
     const uint32_t qn = (uint32_t)get_at(s.qn, k);
     const uint64_t enq = ticks * m;
     const uint64_t j = enq - (uint64_t)qn;
-    if (j < ring.snapEnd(s, k)) return ring(k, (uint32_t)j & (uint32_t)(kRingSlots - 1));
+    if (j < ring.epochK(s, k) * m) return ring(k, (uint32_t)j & (uint32_t)(kRingSlots - 1));     // predates the last reset()
     // tick of packet j = ticks - ceil(qn / m)
     const uint64_t back = (qn + m - 1u) / m;
     const uint64_t tick = ticks - back;
@@ -1581,14 +1581,13 @@ GW_HD void reset_sim(Sim<D, NS, NJ, ST> &s, const BandParams &B, RingW &ringw)
         const uint64_t enq = s.ticks[k] * m;
         if (B.payloadRule[k] < 0) {
             uint64_t j = enq - (uint64_t)s.qn[k];
-            if (j < s.snapEnd[k]) j = s.snapEnd[k];
+            if (j < s.epochK[k] * m) j = s.epochK[k] * m;           // already materialised by an earlier reset()
             for (; j < enq; ++j) {
                 const uint64_t tick = j / m;
                 const uint64_t c = (uint64_t)s.epochC[k] + (tick - s.epochK[k]);
                 ringw(k, (uint32_t)j & (uint32_t)(kRingSlots - 1), c > (uint64_t)kCounterBound ? kCounterBound : (int)c);
             }
         }
-        s.snapEnd[k] = enq;
         s.epochK[k] = s.ticks[k];
         s.epochC[k] = 0;
     }

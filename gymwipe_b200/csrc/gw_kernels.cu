@@ -63,7 +63,7 @@ static int fail(int code, const char *fmt, ...)
 // ------------------------------------------------------------------------------------
 
 enum : int {
-    H_P01 = 0, H_P23, H_TICK, H_TICKS, H_U0, H_U1, H_U2, H_JAM, H_EP0, H_EP1, H_EPC, HOT_CHUNKS
+    H_P01 = 0, H_P23, H_TICK, H_TICKS, H_U0, H_U1, H_U2, H_JAM, H_EP, H_EPC, HOT_CHUNKS
 };
 // cold: per device 5 chunks, then per sender 1
 enum : int { C_EV = 0, C_TX, C_RX, C_RT, C_U, C_V, C_PER_DEV };
@@ -145,6 +145,8 @@ struct gw_handle {
     // has been raised on THIS handle's device (the attribute is per device, and a handle is driven by
     // one host thread at a time -- include/gymwipe_b200.h)
     unsigned smem_configured;
+    unsigned long long *stamps;         // gw_debug_stamps: device buffer [stamp_cap][4], next slot
+    long long stamp_cap, stamp_next;
 };
 
 // ------------------------------------------------------------------------------------
@@ -278,7 +280,8 @@ __device__ __forceinline__ void pack_flags(const Sim<D, NS, NJ, ST> &s, bool bus
 // through DevRing --, mode-M segment starts in mode R, packet values without a plant), which
 // makes them dead in registers
 template <bool FULL = true, bool WITH_SEG = true, int D, int NS, int NJ, class ST>
-__device__ __forceinline__ bool load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs &st, long long i, double now)
+__device__ __forceinline__ bool load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs &st, long long i, double now,
+                                         bool with_seq = true)
 {
     const long long n = st.nsim;
     s.now = now;
@@ -297,7 +300,9 @@ __device__ __forceinline__ bool load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs 
     unpack_flags(s, u0.y, u0.z);
     v = ld_chunk(st.hot, n, H_U1, i);
     s.sTick[0] = v.x; s.sTick[1] = v.y; s.nDeliv[0] = v.z; s.nDeliv[1] = v.w;
-    v = ld_chunk(st.hot, n, H_U2, i);
+    // per-device transmission numbers: mode-M mask keys and the lazily created attenuation models of
+    // moving devices read them; mode R with one shared geometry does not (with_seq = false: not kept)
+    v = with_seq ? ld_chunk(st.hot, n, H_U2, i) : make_uint4(0, 0, 0, 0);
     s.txSeq[0] = v.x; s.txSeq[1] = v.y; s.txSeq[2] = v.z;
     if (D > 3) s.txSeq[D > 3 ? 3 : 0] = v.w;
     if (NJ > 0) {
@@ -307,17 +312,15 @@ __device__ __forceinline__ bool load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs 
         s.tJam[0] = 0; s.sJam[0] = 0;
     }
     if (FULL) {
-        // per sender one chunk {snapEnd, epochK | epochC << 63}: the counter epoch of sender k
-        // (counter value 0 or 1 at tick epochK) and the end of its snapshot ring
-#pragma unroll
-        for (int k = 0; k < NS; ++k) {
-            v = ld_chunk(st.hot, n, H_EP0 + k, i);
-            s.snapEnd[k] = lo_q(v); s.epochK[k] = hi_q(v) & ~(1ull << 63); s.epochC[k] = (int)(hi_q(v) >> 63);
-        }
+        // one chunk {epochK[0] | epochC[0] << 63, epochK[1] | epochC[1] << 63}: the counter epoch of each sender
+        // (counter value 0 or 1 at tick epochK; packets enqueued before that tick are in the snapshot ring)
+        v = ld_chunk(st.hot, n, H_EP, i);
+        s.epochK[0] = lo_q(v) & ~(1ull << 63); s.epochC[0] = (int)(lo_q(v) >> 63);
+        s.epochK[1] = hi_q(v) & ~(1ull << 63); s.epochC[1] = (int)(hi_q(v) >> 63);
         v = ld_chunk(st.hot, n, H_EPC, i);
         s.fault = (int)v.z; s.ties = v.w;
     } else {
-        s.epochK[0] = s.epochK[1] = 0; s.snapEnd[0] = s.snapEnd[1] = 0; s.epochC[0] = s.epochC[1] = 0;
+        s.epochK[0] = s.epochK[1] = 0; s.epochC[0] = s.epochC[1] = 0;
         s.fault = 0; s.ties = 0;        // a faulted sim stays flagged in memory (store_sim ORs nothing back)
     }
     const bool busy = (u0.z >> 31) & 1;
@@ -356,7 +359,8 @@ __device__ __forceinline__ bool load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs 
 }
 
 template <bool FULL = true, bool WITH_SEG = true, int D, int NS, int NJ, class ST>
-__device__ __forceinline__ void store_sim(const Sim<D, NS, NJ, ST> &s, const StatePtrs &st, long long i, bool epoch_too)
+__device__ __forceinline__ void store_sim(const Sim<D, NS, NJ, ST> &s, const StatePtrs &st, long long i, bool epoch_too,
+                                          bool with_seq = true)
 {
     const long long n = st.nsim;
     st_chunk(st.hot, n, H_P01, i, pack_dd(s.P[0], s.P[1]));
@@ -371,18 +375,18 @@ __device__ __forceinline__ void store_sim(const Sim<D, NS, NJ, ST> &s, const Sta
     uint4 v;
     v.x = s.sTick[0]; v.y = s.sTick[1]; v.z = s.nDeliv[0]; v.w = s.nDeliv[1];
     st_chunk(st.hot, n, H_U1, i, v);
-    v.x = s.txSeq[0]; v.y = s.txSeq[1]; v.z = s.txSeq[2]; v.w = D > 3 ? s.txSeq[D > 3 ? 3 : 0] : 0u;
-    st_chunk(st.hot, n, H_U2, i, v);
+    if (with_seq) {
+        v.x = s.txSeq[0]; v.y = s.txSeq[1]; v.z = s.txSeq[2]; v.w = D > 3 ? s.txSeq[D > 3 ? 3 : 0] : 0u;
+        st_chunk(st.hot, n, H_U2, i, v);
+    }
     if (NJ > 0) {
         v = pack_dd(s.tJam[0], 0.0);
         v.z = s.sJam[0]; v.w = 0;
         st_chunk(st.hot, n, H_JAM, i, v);
     }
-    if (epoch_too) {
-#pragma unroll
-        for (int k = 0; k < NS; ++k)
-            st_chunk(st.hot, n, H_EP0 + k, i, pack_qq(s.snapEnd[k], s.epochK[k] | ((unsigned long long)(s.epochC[k] & 1) << 63)));
-    }
+    if (epoch_too)
+        st_chunk(st.hot, n, H_EP, i, pack_qq(s.epochK[0] | ((unsigned long long)(s.epochC[0] & 1) << 63),
+                                             s.epochK[1] | ((unsigned long long)(s.epochC[1] & 1) << 63)));
     if (FULL) {
         if (epoch_too || s.fault || s.ties) {
             v.x = 0; v.y = 0; v.z = (unsigned)s.fault; v.w = s.ties;
@@ -418,17 +422,26 @@ struct DevRing {
     int32_t *base;      // ring + sim index
     long long nsim;
     const uint4 *hot;   // hot chunks + sim index
-    // counter epochs {snapEnd, epochK | epochC << 63} of sender k: read where head_size() needs
-    // them (once per window / packet).  The step kernels prefetch both chunks into L2 together with
-    // the state loads, so the first read is an L2 hit and the following ones hit L1 -- without
-    // holding them in registers for the whole step.
+    // counter epochs {epochK | epochC << 63} of the two senders, one chunk: read where head_size() needs
+    // them (once per window / packet).  The step kernels prefetch the chunk into L2 together with the
+    // state loads, so the first read is an L2 hit and the following ones hit L1 -- without holding it in
+    // registers for the whole step.
     __device__ __forceinline__ int operator()(int k, uint32_t slot) const { return base[(long long)(k * kRingSlots + slot) * nsim]; }
     __device__ __forceinline__ void operator()(int k, uint32_t slot, int v) { base[(long long)(k * kRingSlots + slot) * nsim] = v; }
-    __device__ __forceinline__ uint4 ep(int k) const { return hot[(long long)(H_EP0 + k) * nsim]; }
-    template <class S> __device__ __forceinline__ unsigned long long snapEnd(const S &, int k) const { return lo_q(ep(k)); }
-    template <class S> __device__ __forceinline__ unsigned long long epochK(const S &, int k) const { return hi_q(ep(k)) & ~(1ull << 63); }
-    template <class S> __device__ __forceinline__ int epochC(const S &, int k) const { return (int)(hi_q(ep(k)) >> 63); }
+    __device__ __forceinline__ unsigned long long ep(int k) const
+    {
+        return reinterpret_cast<const unsigned long long *>(hot + (long long)H_EP * nsim)[k];
+    }
+    template <class S> __device__ __forceinline__ unsigned long long epochK(const S &, int k) const { return ep(k) & ~(1ull << 63); }
+    template <class S> __device__ __forceinline__ int epochC(const S &, int k) const { return (int)(ep(k) >> 63); }
 };
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -522,11 +535,7 @@ struct MaskSource {
 #ifndef GW_FED_U
 #define GW_FED_U 4
 #endif
-#ifdef GW_FED_NO_PREFETCH
-#define FED_FIRST_PASS 1
-#else
-#define FED_FIRST_PASS 0
-#endif
+
 constexpr int FED_U = GW_FED_U;         // 128-bit loads per lane and mask row in flight in the cooperative scan
 
 __device__ __forceinline__ int popc4(uint4 v) { return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
@@ -585,37 +594,43 @@ __device__ __noinline__ int lane_popc_range(const uint32_t *row, int k0, int k1)
     return n;
 }
 
-// mask of the bits of 16-byte group g that lie inside the bit range [k0, k1) (branch-free: all ones for
-// interior groups, a prefix / suffix for the first / last group, zero outside)
-__device__ __forceinline__ unsigned word_mask(int lo, int hi)     // bits [lo, hi) of a 32-bit word, any ints
+// set bits of the 128-bit group `v` at positions < r (any int r: <= 0 gives 0, >= 128 gives all): one
+// BMSK (clamped bit-mask generate) + AND + POPC per word
+__device__ __forceinline__ int popc_below(uint4 v, int r)
 {
-    const unsigned upto_hi = hi >= 32 ? 0xFFFFFFFFu : (hi <= 0 ? 0u : ((1u << hi) - 1u));
-    const unsigned upto_lo = lo >= 32 ? 0xFFFFFFFFu : (lo <= 0 ? 0u : ((1u << lo) - 1u));
-    return upto_hi & ~upto_lo;
-}
-__device__ __forceinline__ uint4 range_mask(int g, int k0, int k1)
-{
-    const int lo = k0 - g * 128, hi = k1 - g * 128;
-    return make_uint4(word_mask(lo, hi), word_mask(lo - 32, hi - 32), word_mask(lo - 64, hi - 64), word_mask(lo - 96, hi - 96));
-}
-__device__ __forceinline__ int popc4_and(uint4 v, uint4 m)
-{
-    return __popc(v.x & m.x) + __popc(v.y & m.y) + __popc(v.z & m.z) + __popc(v.w & m.w);
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int b = max(r - 32 * j, 0);
+        unsigned m;
+        asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(m) : "r"(b));         // low min(b, 32) bits set
+        n += __popc(w[j] & m);
+    }
+    return n;
 }
 
-// the same count for a range of at most FED_TINY 16-byte groups: all loads are issued before the first
-// popcount (headers, announcement payloads)
+// bits of group g (content v) inside the bit range [k0, k1): for the first / last group of a range
+__device__ __forceinline__ int popc_edge(uint4 v, int g, int k0, int k1)
+{
+    return popc_below(v, k1 - g * 128) - popc_below(v, k0 - g * 128);
+}
+
+// the same count by ONE lane for a range of at most FED_TINY 16-byte groups (headers, announcement
+// payloads: one or two groups): whole groups, minus the bits below k0 in the first group and the bits from
+// k1 on in the last one
 constexpr int FED_TINY = 4;
 __device__ __forceinline__ int lane_popc_small(const uint32_t *row, int k0, int k1)
 {
     const int q0 = k0 >> 7, q1 = (k1 - 1) >> 7;
     const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
-    uint4 v[FED_TINY];
-#pragma unroll
-    for (int u = 0; u < FED_TINY; ++u) v[u] = (q0 + u <= q1) ? __ldg(row4 + q0 + u) : make_uint4(0, 0, 0, 0);
-    int n = 0;
-#pragma unroll
-    for (int u = 0; u < FED_TINY; ++u) n += popc4_and(v[u], range_mask(q0 + u, k0, k1));
+    const uint4 first = __ldg(row4 + q0);
+    uint4 last = first;
+    int n = popc4(first);
+#pragma unroll 1
+    for (int q = q0 + 1; q <= q1; ++q) { last = __ldg(row4 + q); n += popc4(last); }
+    n -= popc_below(first, k0 - q0 * 128);
+    n -= popc4(last) - popc_below(last, k1 - q1 * 128);
     return n;
 }
 
@@ -662,6 +677,8 @@ struct StepArgs {
     double *stats;
     int *errflag;
     unsigned long long *maskBytes;      // mode M fed: bytes of mask words the step kernels scanned (statistic)
+    unsigned long long *stamps;         // diagnostics (gw_debug_stamps): this launch's {first block start, first block
+                                        // past the grid dependency, last block end} in globaltimer ns, or NULL
     MaskSource masks;
     DevMemo memo;
     // compact outputs (gw_step_host_packed): used instead of obs / reward when non-NULL
@@ -698,6 +715,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
     int acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0;
+    const bool keepSeq = MODE != MODE_R || A.st.per_env != 0;     // see load_sim
 
     // The first row of this thread is requested into L2 right away: the block-level set-up below (and,
     // under programmatic dependent launch, the tail of the previous kernel) then overlaps the DRAM
@@ -708,12 +726,13 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         if (i0 < A.sim_end) {
 #pragma unroll
             for (int c = 0; c < HOT_CHUNKS; ++c)
-                if (c != H_EPC && (NJ > 0 || c != H_JAM)) prefetch_l2(A.st.hot + (long long)c * nsim + i0);
+                if (c != H_EPC && (NJ > 0 || c != H_JAM) && (keepSeq || c != H_U2)) prefetch_l2(A.st.hot + (long long)c * nsim + i0);
             if (nb == 1) prefetch_l2(A.st.now + i0);
             if (A.act8) prefetch_l2(A.act8 + 2 * i0);
             else { prefetch_l2(A.device + i0); prefetch_l2(A.duration + i0); }
         }
     }
+    if (A.stamps != nullptr && threadIdx.x == 0) atomicMin(A.stamps + 0, globaltimer_ns());
     // first level of the BER memo: copied into shared memory while the state loads are in flight.
     // (Read before the grid dependency is resolved: entries are checksum-validated, a stale or
     // torn one is a miss.)
@@ -731,6 +750,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
     // at the same point for this grid to complete.
     cudaGridDependencySynchronize();
     cudaTriggerProgrammaticLaunchCompletion();
+    if (A.stamps != nullptr && threadIdx.x == 0) atomicMin(A.stamps + 1, globaltimer_ns());
     __syncthreads();
 
     // grid-stride over warps' worth of band-sims; every lane of a warp stays in the loop
@@ -754,10 +774,9 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         int dev = 0, dur = 0;
         bool idle0 = false;
         if (active) {
-            idle0 = !load_sim<false, MODE != MODE_R>(s, A.st, i, A.st.now[env]);
+            idle0 = !load_sim<false, MODE != MODE_R>(s, A.st, i, A.st.now[env], keepSeq);
             if (base != A.sim_begin + (long long)blockIdx.x * blockDim.x) {     // later rounds of the grid-stride loop
-                prefetch_l2(A.st.hot + (long long)H_EP0 * nsim + i);
-                prefetch_l2(A.st.hot + (long long)H_EP1 * nsim + i);
+                prefetch_l2(A.st.hot + (long long)H_EP * nsim + i);
             }
             if (TRACE) { s.trace = A.trace + (long long)i * A.traceCap * 8; s.traceCap = A.traceCap; s.ntrace = 0; }
             if (A.act8) {
@@ -796,15 +815,15 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
             // (gw_core.cuh::fed_decide_set), so only DECIDING events read mask words.  Two alternating parts:
             //  (1) serial: every lane runs ahead, at its own pace, through its events (the cheap per-lane
             //      loop of mode R).  Decisions over a few 16-byte groups (headers, announcements) are
-            //      counted on the spot -- their cache line was requested into L2 when the transmission
-            //      started -- and a lane stops in front of a decision over a LONG range;
+            //      counted on the spot by their own lane; a lane stops in front of a decision over a LONG
+            //      range;
             //  (2) warp-uniform: the pending long ranges of all 32 lanes are counted together, four rows
-            //      at a time (one per group of eight lanes, each reading whole 128-byte lines), in two
-            //      passes: the first only requests every line of every row into L2 (prefetch: nothing is
-            //      held in registers while ALL rows of the warp are in flight), the second loads (L2 hits,
-            //      FED_U 128-bit loads per lane in flight), popcounts and reduces within the eight lanes.
-            //      The event itself is applied at the head of part (1): the transition function has ONE
-            //      call site (code size).
+            //      at a time: one row per group of eight lanes, each lane reading every eighth 16-byte
+            //      group (whole 128-byte lines per octet and load instruction, FED_U loads per lane in
+            //      flight), popc, reduction within the eight lanes.  The event itself is applied at the
+            //      head of part (1): the transition function has ONE call site (code size).
+            // (Measured alternatives, profiles/README.md: the round-1 lockstep loop, 32 lanes per row, L2
+            // prefetch passes -- bulk and per line --, and a vote on the most common event kind were all slower.)
             double Tend = INFINITY;
             int phase = 0;      // 0: until the own ASSIGN is processed, 1: until Tend
             const long long wpr = A.masks.words_per_row;
@@ -876,23 +895,9 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
                             for (int p = 0; p < D; ++p)
                                 if ((nd >> p) & 1) { s.err[p] += (double)cnt[p]; s.segT0[p] = ev.t; }
                         }
-                        const int d = ev.idx;
-                        const bool starts = ev.kind == EV_PHY && get_at(s.sphase, d) == S_SLOT;
                         s.now = ev.t;
                         const int berMask = apply_event(s, P, B, ev, srx, ring);
                         update_bers(s, P, berMask, srx, memo);
-#ifndef GW_FED_NO_PREFETCH
-                        if (starts) {
-                            // the first line of the rows of the receivers that locked on: header (and
-                            // announcement payload) decisions will find it in L2
-                            const uint32_t q = get_at(s.txSeq, d) - 1u;
-                            const long long rb = ((((env * nb + band) * kMaxDev + d) * A.masks.slots
-                                                   + (long long)(q % (uint32_t)A.masks.slots)) * kMaxDev) * wpr;
-#pragma unroll
-                            for (int p = 0; p < D; ++p)
-                                if (p != d && s.rxOf[p] == d) prefetch_l2(A.masks.words + rb + p * wpr);
-                        }
-#endif
                     }
                     if (s.fault) need = 0;
                 }
@@ -910,50 +915,45 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
                 // ---- (2) the long ranges of the pending decisions, four rows at a time
                 const int oct = lane >> 3, sub = lane & 7;
 #pragma unroll 1
-                for (int pass = FED_FIRST_PASS; pass < 2; ++pass) {
+                for (int p = 0; p < D; ++p) {
+                    unsigned M = __ballot_sync(0xFFFFFFFFu, (need >> p) & 1);
+                    while (M) {
+                        const int s0 = __ffs(M) - 1; M &= M - 1;
+                        const int s1 = __ffs(M) - 1; M &= M - 1;        // -1 when M ran empty (0 & x stays 0)
+                        const int s2 = __ffs(M) - 1; M &= M - 1;
+                        const int s3 = __ffs(M) - 1; M &= M - 1;
+                        const int src = oct == 0 ? s0 : (oct == 1 ? s1 : (oct == 2 ? s2 : s3));
+                        const int from = src < 0 ? 0 : src;
+                        const long long rb = __shfl_sync(0xFFFFFFFFu, rowbase, from);
+                        const int a0 = __shfl_sync(0xFFFFFFFFu, k0c, from), a1 = __shfl_sync(0xFFFFFFFFu, k1c, from);
+                        const int q0 = a0 >> 7, q1 = src < 0 ? -1 : ((a1 - 1) >> 7);
+                        const uint4 *row4 = reinterpret_cast<const uint4 *>(A.masks.words + rb + p * wpr);
+                        int tot = 0;
 #pragma unroll 1
-                    for (int p = 0; p < D; ++p) {
-                        unsigned M = __ballot_sync(0xFFFFFFFFu, (need >> p) & 1);
-                        while (M) {
-                            const int s0 = __ffs(M) - 1; M &= M - 1;
-                            const int s1 = __ffs(M) - 1; M &= M - 1;        // -1 when M ran empty (0 & x stays 0)
-                            const int s2 = __ffs(M) - 1; M &= M - 1;
-                            const int s3 = __ffs(M) - 1; M &= M - 1;
-                            const int src = oct == 0 ? s0 : (oct == 1 ? s1 : (oct == 2 ? s2 : s3));
-                            const int from = src < 0 ? 0 : src;
-                            const long long rb = __shfl_sync(0xFFFFFFFFu, rowbase, from);
-                            const int a0 = __shfl_sync(0xFFFFFFFFu, k0c, from), a1 = __shfl_sync(0xFFFFFFFFu, k1c, from);
-                            const int q0 = a0 >> 7, q1 = src < 0 ? -1 : ((a1 - 1) >> 7);
-                            const uint4 *row4 = reinterpret_cast<const uint4 *>(A.masks.words + rb + p * wpr);
-                            if (pass == 0) {
-                                // every 128-byte line of the range (row4 is 16-byte aligned: lines by group / 8)
-                                for (int g = (q0 & ~7) + 8 * sub; g <= q1; g += 64) prefetch_l2(row4 + (g < q0 ? q0 : g));
-                                continue;
-                            }
-                            int tot = 0;
-#pragma unroll 1
-                            for (int gb = q0 + sub; gb <= q1; gb += 8 * FED_U) {
-                                uint4 v[FED_U];
+                        for (int gb = q0 + sub; gb <= q1; gb += 8 * FED_U) {
+                            uint4 v[FED_U];
 #pragma unroll
-                                for (int u = 0; u < FED_U; ++u)
-                                    v[u] = gb + 8 * u <= q1 ? GW_MASK_LOAD(row4 + gb + 8 * u) : make_uint4(0, 0, 0, 0);
+                            for (int u = 0; u < FED_U; ++u)
+                                v[u] = gb + 8 * u <= q1 ? GW_MASK_LOAD(row4 + gb + 8 * u) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-                                for (int u = 0; u < FED_U; ++u) {
-                                    const int g = gb + 8 * u;
-                                    int c = popc4(v[u]);
-                                    if (g == q0 || g == q1) c = popc4_and(v[u], range_mask(g, a0, a1));
-                                    tot += c;
+                            for (int u = 0; u < FED_U; ++u) {
+                                const int g = gb + 8 * u;
+                                if (g == q0 || g == q1) {
+                                    asm volatile("");           // keep this a (rare, two lanes per row) branch
+                                    tot += popc_edge(v[u], g, a0, a1);
+                                } else {
+                                    tot += popc4(v[u]);
                                 }
                             }
-                            tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 4);
-                            tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 2);
-                            tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 1);
-                            const int rank = lane == s0 ? 0 : (lane == s1 ? 1 : (lane == s2 ? 2 : (lane == s3 ? 3 : -1)));
-                            const int val = __shfl_sync(0xFFFFFFFFu, tot, rank < 0 ? 0 : 8 * rank);
-                            if (rank >= 0) {
+                        }
+                        tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 4);
+                        tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 2);
+                        tot += __shfl_xor_sync(0xFFFFFFFFu, tot, 1);
+                        const int rank = lane == s0 ? 0 : (lane == s1 ? 1 : (lane == s2 ? 2 : (lane == s3 ? 3 : -1)));
+                        const int val = __shfl_sync(0xFFFFFFFFu, tot, rank < 0 ? 0 : 8 * rank);
+                        if (rank >= 0) {
 #pragma unroll
-                                for (int pp = 0; pp < D; ++pp) cnt[pp] = pp == p ? val : cnt[pp];
-                            }
+                            for (int pp = 0; pp < D; ++pp) cnt[pp] = pp == p ? val : cnt[pp];
                         }
                     }
                 }
@@ -1108,7 +1108,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
             }
             if (band == 0) A.st.now[env] = s.now;
             if (s.fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = s.fault; } }
-            store_sim<false, MODE != MODE_R>(s, A.st, i, false);
+            store_sim<false, MODE != MODE_R>(s, A.st, i, false, keepSeq);
             if (TRACE) A.traceCount[i] = s.ntrace;
             acc[0] += (int)rw;                  // rewards are integers in [-10, 10] (counter_traffic.py:96-107)
             acc[1] += (int)(s.nDeliv[0] - nD0);
@@ -1135,6 +1135,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
         if (v != 0) atomicAdd(A.stats + threadIdx.x, (double)v);
     }
+    if (A.stamps != nullptr && threadIdx.x == 0) atomicMax(A.stamps + 2, globaltimer_ns());
 }
 
 // ------------------------------------------------------------------------------------
@@ -1939,6 +1940,7 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     A.device = device; A.duration = duration;
     A.obs = (long long *)obs; A.reward = reward; A.done = done;
     A.stats = h->stats_use; A.errflag = h->errflag; A.maskBytes = h->mask_bytes;
+    A.stamps = (h->stamps && h->stamp_next < h->stamp_cap) ? h->stamps + 4 * h->stamp_next++ : nullptr;
     A.obs32 = obs32; A.reward32 = reward32;
     A.act8 = act8; A.res32 = res32;
     A.sim_begin = sim_begin; A.sim_end = sim_end < 0 ? h->st.nsim : sim_end;
@@ -2113,6 +2115,17 @@ static int step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *res
     return GW_OK;
 }
 
+// side streams of gw_step_host_compact_many, per device (created on first use, never destroyed: they live
+// as long as the library)
+constexpr int MANY_STREAMS = 4;
+struct ManyStreams {
+    cudaStream_t s[MANY_STREAMS];
+    cudaEvent_t fork, join[MANY_STREAMS];
+    bool ready;
+};
+static ManyStreams g_many[64];
+static std::mutex g_many_mutex;
+
 int gw_step_host_compact_many(gw_handle *const *handles, int32_t n_handles, const uint8_t *const *actions,
                               uint32_t *const *results, void *stream)
 {
@@ -2120,10 +2133,40 @@ int gw_step_host_compact_many(gw_handle *const *handles, int32_t n_handles, cons
     for (int k = 0; k < n_handles; ++k) {
         if (!handles[k]) return fail(GW_E_INVALID, "handle %d is NULL", k);
         if (handles[k]->device != handles[0]->device) return fail(GW_E_INVALID, "the handles of one call live on one device");
-        const int rc = step_host_compact(handles[k], actions[k], results[k], stream, false);
+    }
+    const int dev = handles[0]->device;
+    if (dev < 0 || dev >= 64) return fail(GW_E_INVALID, "device ordinal %d out of range", dev);
+    CUDA_TRY(cudaSetDevice(dev));
+    cudaStream_t s = (cudaStream_t)stream;
+    // The batches are independent (own state, own pinned buffers): their steps are spread over a few side
+    // streams, so that one batch's result words drain over the host link while the next batch computes --
+    // on one stream every kernel would wait for its predecessor's posted writes.  Fork from / join into
+    // the caller's stream with events; ONE synchronisation at the end.
+    ManyStreams *ms;
+    {
+        std::lock_guard<std::mutex> lock(g_many_mutex);
+        ms = &g_many[dev];
+        if (!ms->ready) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ms->fork, cudaEventDisableTiming));
+            for (int k = 0; k < MANY_STREAMS; ++k) {
+                CUDA_TRY(cudaStreamCreateWithFlags(&ms->s[k], cudaStreamNonBlocking));
+                CUDA_TRY(cudaEventCreateWithFlags(&ms->join[k], cudaEventDisableTiming));
+            }
+            ms->ready = true;
+        }
+    }
+    const int lanes = n_handles < MANY_STREAMS ? n_handles : MANY_STREAMS;
+    CUDA_TRY(cudaEventRecord(ms->fork, s));
+    for (int k = 0; k < lanes; ++k) CUDA_TRY(cudaStreamWaitEvent(ms->s[k], ms->fork, 0));
+    for (int k = 0; k < n_handles; ++k) {
+        const int rc = step_host_compact(handles[k], actions[k], results[k], (void *)ms->s[k % lanes], false);
         if (rc) return rc;
     }
-    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int k = 0; k < lanes; ++k) {
+        CUDA_TRY(cudaEventRecord(ms->join[k], ms->s[k]));
+        CUDA_TRY(cudaStreamWaitEvent(s, ms->join[k], 0));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
     return GW_OK;
 }
 
@@ -2163,6 +2206,15 @@ int gw_mask_bytes(gw_handle *h, uint64_t *out, int clear, void *stream)
     CUDA_TRY(cudaMemcpyAsync(out, h->mask_bytes, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     if (clear) CUDA_TRY(cudaMemsetAsync(h->mask_bytes, 0, sizeof(uint64_t), s));
+    return GW_OK;
+}
+
+int gw_debug_stamps(gw_handle *h, uint64_t *stamps, int64_t capacity)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    h->stamps = (unsigned long long *)stamps;
+    h->stamp_cap = stamps ? capacity : 0;
+    h->stamp_next = 0;
     return GW_OK;
 }
 

@@ -67,6 +67,7 @@ class SimpleNetworkDevice(NetworkDevice):
         self.macAddr = SimpleMac.macAddress(macIndex)
         self._phy = SimplePhy("phy", self, frequencyBand)
         self._mac = SimpleMac("mac", self, frequencyBand.spec, self.macAddr)
+        self._mac.ports["phy"].biConnectWith(self._phy.ports["mac"])            # devices.py:58
 
 
 class SimpleRrmDevice(NetworkDevice):
@@ -81,6 +82,7 @@ class SimpleRrmDevice(NetworkDevice):
         self.macToDeviceIndexDict = {mac: index for index, mac in deviceIndexToMacDict.items()}
         self._phy = SimplePhy("phy", self, frequencyBand)
         self._mac = SimpleRrmMac("mac", self, frequencyBand.spec)
+        self._mac.ports["phy"].biConnectWith(self._phy.ports["mac"])            # devices.py:131
 
     @property
     def macAddr(self):

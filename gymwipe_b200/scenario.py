@@ -87,3 +87,91 @@ def dict_from_bands(bands, assignment_duration_factor=1000):
         out["bands"].append({"frequency": band.spec.frequency, "bandwidth": band.spec.bandwidth,
                              "devices": entries})
     return out
+
+
+def compile_stack(bands, assignment_duration_factor=1000):
+    """
+    Traces wired network stacks into the scenario table.
+
+    ``bands``: ``FrequencyBand`` descriptors whose registered devices own ``Module`` s wired with the
+    reference's plumbing (``gymwipe_b200.networking.construction``).  The ROLE of a device is read from its
+    wiring, not from its class: the device's ``SimplePhy`` on the band is located, its ``"mac"`` port is
+    followed through ``Gate.connectTo`` connections (proxy ports in between are passed through, as in
+    ``tests/networking/test_stack.py:134-158``) to the first ``SimpleMac`` (a sender with a MAC queue), or
+    ``SimpleRrmMac`` (the band's RRM); a PHY whose ``"mac"`` port leads to no MAC is a PHY-only periodic
+    sender (``tests/test_benchmark.py:20-50``).  Traffic parameters are the device's attributes
+    (``packetMultiplicity`` / ``interval`` / ``payloadRule``; ``sendInterval`` / ``initialDelay`` / ``power`` /
+    ``headerBytes`` / ``payloadBytes``).  Raises ``ValueError`` for stacks the step kernel has no table for.
+    """
+    from gymwipe_b200.networking.construction import Module, Port
+    from gymwipe_b200.networking.simple_stack import SimpleMac, SimplePhy, SimpleRrmMac
+
+    def modules_of(device):
+        found = []
+        for value in vars(device).values():
+            if isinstance(value, Module):
+                found.append(value)
+        return found
+
+    def mac_behind(phy):
+        """Breadth-first along the connections leaving the PHY's mac port."""
+        seen, frontier = set(), [phy.ports["mac"].output]
+        while frontier:
+            gate = frontier.pop(0)
+            if id(gate) in seen:
+                continue
+            seen.add(id(gate))
+            port = gate._owner if isinstance(gate._owner, Port) else None
+            module = port._owner if port is not None else gate._owner
+            if isinstance(module, (SimpleMac, SimpleRrmMac)) and module is not phy:
+                back = module.ports["phy"].output
+                if not _reaches(back, phy.ports["mac"].input):
+                    raise ValueError("%r: the MAC's phy port is not connected back to the PHY" % (module,))
+                return module
+            frontier.extend(gate.connections)
+        return None
+
+    out = {"assignment_duration_factor": assignment_duration_factor, "bands": []}
+    for band in bands:
+        senders, rrms, jammers = [], [], []
+        for dv in band.devices:
+            phys = [m for m in modules_of(dv) if isinstance(m, SimplePhy) and m.frequencyBand is band]
+            if len(phys) != 1:
+                raise ValueError("%r needs exactly one SimplePhy on the band (found %d)" % (dv, len(phys)))
+            mac = mac_behind(phys[0])
+            if isinstance(mac, SimpleRrmMac):
+                rrms.append(dv)
+            elif isinstance(mac, SimpleMac):
+                senders.append(dv)
+            else:
+                jammers.append(dv)
+        if len(rrms) != 1:
+            raise ValueError("a band needs exactly one RRM stack (SimplePhy <-> SimpleRrmMac), found %d" % len(rrms))
+        if len(senders) != 2 or len(jammers) > N.GW_MAX_JAMMERS:
+            raise ValueError("step-kernel tables exist for 2 MAC senders + RRM + up to %d PHY-only sender(s) per band; "
+                             "got %d / %d" % (N.GW_MAX_JAMMERS, len(senders), len(jammers)))
+        entries = []
+        for i, dv in enumerate(senders):
+            entries.append({"role": "sender", "x": dv.position.x, "y": dv.position.y,
+                            "mult": getattr(dv, "packetMultiplicity", 1), "payload": getattr(dv, "payloadRule", "counter"),
+                            "interval": getattr(dv, "interval", 0.001), "dest": 1 - i})
+        entries.append({"role": "rrm", "x": rrms[0].position.x, "y": rrms[0].position.y})
+        for dv in jammers:
+            for attr in ("sendInterval", "initialDelay", "payloadBytes"):
+                if not hasattr(dv, attr):
+                    raise ValueError("%r is a PHY-only sender: it needs the attribute %r" % (dv, attr))
+            entries.append({"role": "jammer", "x": dv.position.x, "y": dv.position.y, "interval": dv.sendInterval,
+                            "delay": dv.initialDelay, "power": getattr(dv, "power", 0.0),
+                            "hdr": getattr(dv, "headerBytes", 13), "payload": dv.payloadBytes})
+        out["bands"].append({"frequency": band.spec.frequency, "bandwidth": band.spec.bandwidth, "devices": entries})
+    return out
+
+
+def _reaches(gate, target, _seen=None):
+    _seen = set() if _seen is None else _seen
+    if gate is target:
+        return True
+    if id(gate) in _seen:
+        return False
+    _seen.add(id(gate))
+    return any(_reaches(g, target, _seen) for g in gate.connections)

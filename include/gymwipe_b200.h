@@ -205,7 +205,9 @@ int gw_step_host_compact_async(gw_handle *h, const uint8_t *actions, uint32_t *r
  * state is split into independently allocated batches): the steps of all handles are enqueued back to
  * back on `stream` -- each reads its own actions[k] / writes its own results[k], layouts as above, PINNED
  * host buffers -- and the call synchronises ONCE.  The launch and wake-up latency of a synchronous step
- * is paid per population, not per batch. */
+ * is paid per population, not per batch; internally the (independent) batches are spread over a few
+ * side streams forked from / joined into `stream`, so that one batch's result words cross the host link
+ * while the next batch computes.  From the caller's point of view everything is ordered on `stream`. */
 int gw_step_host_compact_many(gw_handle *const *handles, int32_t n_handles, const uint8_t *const *actions,
                               uint32_t *const *results, void *stream);
 #define GW_COMPACT_OBS(w)    ((int32_t)((w) & 0x1FFFFu))
@@ -231,6 +233,14 @@ int gw_stats(gw_handle *h, double *out8, int clear, void *stream);
  * uint64; synchronises `stream`. */
 int gw_mask_bytes(gw_handle *h, uint64_t *out, int clear, void *stream);
 
+/* Diagnostics: from now on the k-th step launch of this handle (k = 0, 1, ... < capacity, counted at
+ * ENQUEUE / graph-capture time) records into stamps[4*k .. 4*k+2] the globaltimer (ns) at which its first
+ * block started, its first block passed the grid dependency (programmatic dependent launch: the previous
+ * kernel of the stream has completed), and its last block finished.  `stamps` is a device uint64 buffer of
+ * 4 * capacity entries that the caller initialises to {~0, ~0, 0, 0} per launch; NULL switches it off.
+ * Shows per-kernel start / end inside a CUDA-graph replay (profiles/scripts/kernel_stamps.py). */
+int gw_debug_stamps(gw_handle *h, uint64_t *stamps, int64_t capacity);
+
 /* Several handles on one device (e.g. env batches stepped round-robin) can accumulate into ONE
  * statistics vector: after gw_share_stats(h, with) the step kernels of `h` add to the accumulators of
  * `with`, and gw_stats of either handle reads / clears them -- one copy instead of one per handle in
@@ -253,7 +263,8 @@ int gw_share_stats(gw_handle *h, gw_handle *with);
 #define GW_FIELD_RX_POWER_MW 9      /* [GW_MAX_DEVICES^2][n_sims] 10**((P_tx - att)/10) */
 #define GW_FIELD_FAULT 10           /* [n_sims]                0 or the condition under which the reference raises */
 #define GW_FIELD_TIES 11            /* [n_sims]                exact-time ties seen by the event selector */
-#define GW_FIELD_TX_SEQ 12          /* [GW_MAX_DEVICES][n_sims] transmissions started per device */
+#define GW_FIELD_TX_SEQ 12          /* [GW_MAX_DEVICES][n_sims] transmissions started per device (kept in mode M and with
+                                       per-env positions -- the only users; 0 in mode R with one shared geometry) */
 #define GW_FIELD_PLANT 13           /* [8][n_sims] x, v, theta, omega, motor target velocity, plant time,
                                        controller's angle estimate (deg), PID memory (plant envs) */
 int gw_read_state(gw_handle *h, int field, double *out, void *stream);

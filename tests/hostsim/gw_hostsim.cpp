@@ -22,7 +22,6 @@ struct HostRing {
     int operator()(int k, uint32_t slot) const { return data[k * kRingSlots + slot]; }
     void operator()(int k, uint32_t slot, int v) { data[k * kRingSlots + slot] = v; }
     // counter epochs (the device reads them from global memory on demand)
-    template <class S> uint64_t snapEnd(const S &s, int k) const { return get_at(s.snapEnd, k); }
     template <class S> uint64_t epochK(const S &s, int k) const { return get_at(s.epochK, k); }
     template <class S> int epochC(const S &s, int k) const { return get_at(s.epochC, k); }
 };

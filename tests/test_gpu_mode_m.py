@@ -143,3 +143,40 @@ def test_philox_known_answers_device():
     out = torch.zeros((3, 4), dtype=torch.int32, device="cuda")
     N.check(N.lib().gw_philox4x32(c.data_ptr(), k.data_ptr(), out.data_ptr(), 3, torch.cuda.current_stream().cuda_stream))
     assert (out.cpu().numpy().view(np.uint32) == want).all()
+
+
+def test_mode_m_fed_moving_devices_match_oracle():
+    """Fed masks with devices jumping between steps: a position change cuts the running segment
+    (move_kernel counts it and restarts the segment), the decision counts the rest -- the receivers of one
+    transmission then decide over DIFFERENT ranges (the kernel's 'own scans' path)."""
+    rs = np.random.RandomState(9300)
+    sc = random_scenario(rs, jammers=1, spread=2.5)
+    sc["bands"][0]["devices"][3]["interval"] = float(rs.uniform(0.008, 0.02))
+    nenv, nsteps, slots, words = 1, 70, 3, 64
+    dev, dur = random_tapes(rs, nsteps, nenv, 1)
+    dur = np.minimum(dur, 9)
+    p = rs.uniform(0.02, 0.3, size=(nenv, 1, 4, slots, 4, 1))
+    bits = rs.random_sample((nenv, 1, 4, slots, 4, words * 32)) < p
+    masks = np.packbits(bits.reshape(-1, 8)[:, ::-1], axis=1).reshape(nenv, 1, 4, slots, 4, words * 4)
+    masks = np.ascontiguousarray(masks.view("<u4").reshape(nenv, 1, 4, slots, 4, words))
+    moves = {}
+    for t in range(1, nsteps, 2):
+        devs = sorted(set(int(v) for v in rs.randint(4, size=int(rs.randint(1, 4)))))
+        moves[t] = [(0, d, float(rs.uniform(-3, 3)), float(rs.uniform(-3, 3))) for d in devs]
+    acts = [{"device": int(dev[t, 0, 0]), "duration": int(dur[t, 0, 0])} for t in range(nsteps)]
+    ora = O.Oracle(sc, mode=O.MODE_M)
+    ora.use_fed_masks(masks, slots)
+    res = O.run_tape(ora, acts, do_reset=True, moves=moves)
+    pos = np.array([[[[d["x"], d["y"]] for d in sc["bands"][0]["devices"]]]], np.float64)      # [1, 1, 4, 2]
+    env = make_env(sc, nenv, mode="mask_fed", positions=torch.as_tensor(pos).cuda())
+    env.set_masks(torch.as_tensor(masks.view(np.int32)).cuda(), slots)
+    env.reset()
+    for t in range(nsteps):
+        if t in moves:
+            for (b, d, x, y) in moves[t]:
+                pos[0, b, d] = (x, y)
+            env.set_positions(torch.as_tensor(pos).cuda())
+        o, r, dn, _ = env.step({"device": torch.as_tensor(dev[t, :, 0]).cuda(), "duration": torch.as_tensor(dur[t, :, 0]).cuda()})
+        assert int(o[0]) == res["steps"][t]["obs"] and float(r[0]) == res["steps"][t]["reward"]
+        assert float(env.read_state(0)[0]) == res["steps"][t]["now"]
+    env.check()
