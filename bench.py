@@ -5,11 +5,11 @@ bench.py -- env-steps/sec of the batched CounterTrafficEnv hot path (BASELINE.js
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Own arm: N ranks (one per GPU; torchrun supplies RANK / LOCAL_RANK / WORLD_SIZE for N > 1), each owning
-an independent POPULATION of `--batches` (default 320) batches of 65,536 envs (BASELINE configs[1]; weak
+an independent POPULATION of `--batches` (default 384) batches of 65,536 envs (BASELINE configs[1]; weak
 scaling).  One bench "step" is one `env.step` of EVERY env of the population: one launch of the fused step
 kernel per batch, the batches one after the other -- a batch is touched again only after all the others
 (gigabytes of other traffic), so every launch finds its inputs in HBM, not in L2 ("inputs larger than L2",
-no flush).  A step is ~2.9 ms of device time, so even the driver's `--steps 20` times > 50 ms.  W warm-up
+no flush).  A step is ~2.8 ms of device time, so even the driver's `--steps 20` times > 50 ms.  W warm-up
 steps, then EXACTLY K timed steps replayed from CUDA graphs (one per step), one CUDA-event pair around them
 on the launching stream, barrier + synchronize on both sides, max over ranks.  `e2e` is the same metric
 through the C ABI with pinned HOST buffers (`gw_step_host_compact_many`: actions read / results written in
@@ -34,7 +34,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
 
 ENVS_PER_GPU = 65536
-POPULATION_BATCHES = 320               # 65,536-env batches per GPU: one bench step = one env.step of all of them (~2.5 ms)
+POPULATION_BATCHES = 384               # 65,536-env batches per GPU: one bench step = one env.step of all of them (~2.5 ms)
 E2E_BATCHES = 16                       # batches of the population stepped per host-buffer call (gw_step_host_compact_many)
 BURN_IN_STEPS = 128                    # steps of every env before the timed region (steady state, see own_arm)
 PRODUCTIVE_STEPS = 32                  # steps of every fresh env timed separately (productive regime)
@@ -55,7 +55,7 @@ def config_dict(n_envs_total, batches, parallelism, regime):
             "l2": "inputs larger than L2: the %d batches of a GPU are stepped one after the other, so a batch's state "
                   "(~13 MB hot), its action rows and outputs are re-touched only after ~%.1f GB of other traffic "
                   "(L2 = 126 MB); no flush, steps replayed from CUDA graphs, one CUDA-event pair around the K timed "
-                  "steps" % (batches, 13e-3 * (batches - 1))}
+                  "steps; EnvPopulation.step spreads the (independent) batches of a step over a few streams" % (batches, 13e-3 * (batches - 1))}
 
 
 def measured_peak():
@@ -418,11 +418,13 @@ def own_arm(args, rank, world, local_rank):
     stream = torch.cuda.Stream(device=dev_t)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     counter = [0]                                       # launches so far: launch j steps batch j % M
+    pop.streams = args.streams
 
-    def launch():
+    def pop_step():
+        """One env.step of the whole population through EnvPopulation.step (its batches spread over a few streams)."""
         j = counter[0]
-        envs[j % M].step({"device": a_dev[j % ROWS], "duration": a_dur[j % ROWS]})
-        counter[0] = j + 1
+        pop.step([{"device": a_dev[(j + b) % ROWS], "duration": a_dur[(j + b) % ROWS]} for b in range(M)])
+        counter[0] = j + M
 
     def capture_steps(count):
         """One CUDA graph per bench step (M launches; the action-row pointers are baked in); capturing does
@@ -431,8 +433,7 @@ def own_arm(args, rank, world, local_rank):
         for _ in range(count):
             gr = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gr, stream=stream):
-                for _b in range(M):
-                    launch()
+                pop_step()
             out.append(gr)
         return out
 
@@ -456,13 +457,13 @@ def own_arm(args, rank, world, local_rank):
         # (agents/dqn_counter_traffic.py: one reset(), dqn.fit(nb_steps=50000), `done` never true) leaves
         # the productive regime after ~100 steps and spends > 99 % of its steps in the regime where the
         # counters are too large for any window (announcements only)
-        for _ in range((BURN_IN_STEPS - PRODUCTIVE_STEPS) * M):
-            launch()
+        for _ in range(BURN_IN_STEPS - PRODUCTIVE_STEPS):
+            pop_step()
         # (3) W warm-up steps, then EXACTLY K timed steps.  The K steps are replayed from G = min(K, 16)
         # step graphs used round-robin (each with its own action rows); every graph is replayed once untimed
         # first (the first launch of an instantiated graph uploads it to the device)
-        for _ in range(W * M):
-            launch()
+        for _ in range(W):
+            pop_step()
         torch.cuda.synchronize(dev_t)
         G = min(K, 16)
         graphs = capture_steps(G)
@@ -692,6 +693,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--batches", type=int, default=POPULATION_BATCHES,
                     help="65,536-env batches per GPU (one bench step = one env.step of all of them)")
+    ap.add_argument("--streams", type=int, default=3,
+                    help="side streams EnvPopulation.step spreads the batches of a population step over")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the mask-scan roofline and the cfg-3 run")

@@ -139,6 +139,8 @@ _SIGNATURES = {
     "gw_ber_bpsk": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),
     "gw_count_bit_errors": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP, _VP, C.c_int64, _VP]),
     "gw_philox4x32": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),
+    "gw_policy_boltzmann": (C.c_int, [_VP, C.c_int32, C.c_int32, _VP, C.c_int64, C.c_float, C.c_double, C.c_double, C.c_double,
+                                      C.c_uint64, C.c_uint64, C.c_int64, _VP, _VP, _VP, _VP, _VP]),
     "gw_max_correctable_ber": (C.c_double, [C.c_int, C.c_int]),
 }
 

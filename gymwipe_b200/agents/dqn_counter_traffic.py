@@ -132,6 +132,8 @@ class DQNLearner:
         self.gen = torch.Generator(device=self.device).manual_seed(seed)
         self.step_count = 0
         self.reset_done = True
+        self.seed = seed
+        self.fused_policy = True        # CUDA envs: action selection through gw_policy_boltzmann (one kernel)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         # warm-up in TRANSITIONS, counted with the smallest shard: shards differ by at most one env
         # (distributed.shard_range), and every rank must start training -- and with it the gradient
@@ -146,6 +148,51 @@ class DQNLearner:
     def _features(self, obs):
         """Network input of a RAW observation: the only place where the observation is centred."""
         return (obs.to(torch.float32) - self.obs_center).reshape(-1, 1)
+
+    def _flat_weights(self):
+        """The model's parameters as views into ONE float32 buffer (the layout ``gw_policy_boltzmann`` reads)."""
+        if getattr(self, "_flat", None) is None:
+            params = list(self.model.parameters())
+            flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+            off = 0
+            for p in params:
+                p.data = flat[off:off + p.numel()].view(p.shape)
+                off += p.numel()
+            self._flat = flat
+        return self._flat
+
+    @torch.no_grad()
+    def select_action_fused(self, obs, want_probs=False):
+        """
+        Action selection in ONE kernel (``gw_policy_boltzmann``): MLP forward, Boltzmann probabilities in float64,
+        draw -- instead of ~8 eager launches.  Returns ``(flat int64, {"device", "duration"} int32 action dict[, probs])``;
+        the dict is what ``env.step`` takes without further conversion.  CUDA envs with the reference's 3x16 network.
+        """
+        from gymwipe_b200 import _native as N
+        obs = obs.to(torch.int64).contiguous()
+        n = obs.numel()
+        flat = torch.empty(n, dtype=torch.int64, device=obs.device)
+        dev = torch.empty(n, dtype=torch.int32, device=obs.device)
+        dur = torch.empty(n, dtype=torch.int32, device=obs.device)
+        probs = torch.empty((n, self.nb_actions), dtype=torch.float64, device=obs.device) if want_probs else None
+        self._draws = getattr(self, "_draws", 0) + 1
+        with torch.cuda.device(obs.device):
+            N.check(N.lib().gw_policy_boltzmann(
+                self._flat_weights().data_ptr(), self.nb_actions, self.nb_durations, obs.data_ptr(), n,
+                float(self.obs_center), float(self.tau), float(self.clip[0]), float(self.clip[1]),
+                int(self.seed) & (2 ** 64 - 1), self._draws, int(getattr(getattr(self.env, "_cfg", None), "env_id_offset", 0)),
+                flat.data_ptr(), dev.data_ptr(), dur.data_ptr(), probs.data_ptr() if want_probs else None,
+                torch.cuda.current_stream(obs.device).cuda_stream))
+        shape = getattr(self.env, "_shape", (n,))
+        if n != int(torch.Size(shape).numel()):
+            shape = (n,)
+        action = {"device": dev.reshape(shape), "duration": dur.reshape(shape)}
+        return (flat, action, probs) if want_probs else (flat, action)
+
+    def _fused_ok(self):
+        return (self.device.type == "cuda" and self.nb_actions in (8, 20, 40)
+                and [tuple(p.shape) for p in self.model.parameters()] ==
+                [(16, 1), (16,), (16, 16), (16,), (16, 16), (16,), (self.nb_actions, 16), (self.nb_actions,)])
 
     @torch.no_grad()
     def select_action(self, obs):
@@ -193,9 +240,14 @@ class DQNLearner:
         """Runs ``nb_steps`` batched env steps; returns the history dict."""
         obs = self.env.reset()
         obs = torch.as_tensor(obs, device=self.device).reshape(-1)
+        fused = self.fused_policy and self._fused_ok()
         for _ in range(nb_steps):
-            flat = self.select_action(obs)
-            next_obs, reward, done, _ = self.env.step(self.processor.process_action(flat))
+            if fused:
+                flat, action = self.select_action_fused(obs)
+            else:
+                flat = self.select_action(obs)
+                action = self.processor.process_action(flat)
+            next_obs, reward, done, _ = self.env.step(action)
             next_obs = torch.as_tensor(next_obs, device=self.device).reshape(-1)
             reward = torch.as_tensor(reward, device=self.device).reshape(-1)
             done = torch.as_tensor(done, device=self.device).reshape(-1)

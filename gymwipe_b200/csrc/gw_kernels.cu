@@ -360,11 +360,13 @@ __device__ __forceinline__ bool load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs 
 
 template <bool FULL = true, bool WITH_SEG = true, int D, int NS, int NJ, class ST>
 __device__ __forceinline__ void store_sim(const Sim<D, NS, NJ, ST> &s, const StatePtrs &st, long long i, bool epoch_too,
-                                          bool with_seq = true)
+                                          bool with_seq = true, int keep_p = 0)
 {
     const long long n = st.nsim;
-    st_chunk(st.hot, n, H_P01, i, pack_dd(s.P[0], s.P[1]));
-    st_chunk(st.hot, n, H_P23, i, pack_dd(s.P[2], D > 3 ? s.P[D > 3 ? 3 : 0] : 0.0));
+    // keep_p bit 0 / 1: the received powers of chunk P01 / P23 equal what the step loaded (the usual case:
+    // every transmission adds and removes its power, and the rounding residue settles) -- not written back
+    if (!(keep_p & 1)) st_chunk(st.hot, n, H_P01, i, pack_dd(s.P[0], s.P[1]));
+    if (!(keep_p & 2)) st_chunk(st.hot, n, H_P23, i, pack_dd(s.P[2], D > 3 ? s.P[D > 3 ? 3 : 0] : 0.0));
     st_chunk(st.hot, n, H_TICK, i, pack_dd(s.tTick[0], s.tTick[1]));
     st_chunk(st.hot, n, H_TICKS, i, pack_qq(s.ticks[0], s.ticks[1]));
     const bool busy = sim_busy(s);
@@ -743,6 +745,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         memo.l0s = memo_l0;
     }
     __shared__ double srx_s[kMaxBands][16];
+    __shared__ double p_loaded[NJ == 0 ? 3 : 1][NJ == 0 ? STEP_BLOCK : 1];     // see store_sim / keep_p
     if (threadIdx.x < kMaxBands * 16) srx_s[threadIdx.x >> 4][threadIdx.x & 15] = T.srx[threadIdx.x >> 4][threadIdx.x & 15];
     // Programmatic dependent launch: this grid may have been scheduled while the previous kernel
     // of the stream (the previous step, or whatever produced the actions) was still draining; its
@@ -775,6 +778,10 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         bool idle0 = false;
         if (active) {
             idle0 = !load_sim<false, MODE != MODE_R>(s, A.st, i, A.st.now[env], keepSeq);
+            if (NJ == 0) {
+#pragma unroll
+                for (int p = 0; p < 3; ++p) p_loaded[p][threadIdx.x] = s.P[p];
+            }
             if (base != A.sim_begin + (long long)blockIdx.x * blockDim.x) {     // later rounds of the grid-stride loop
                 prefetch_l2(A.st.hot + (long long)H_EP * nsim + i);
             }
@@ -1108,7 +1115,15 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
             }
             if (band == 0) A.st.now[env] = s.now;
             if (s.fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = s.fault; } }
-            store_sim<false, MODE != MODE_R>(s, A.st, i, false, keepSeq);
+            int keepP = 0;
+            if (NJ == 0) {
+                // bitwise comparison with the loaded values (kept in shared memory: no registers held)
+                const bool e0 = __double_as_longlong(s.P[0]) == __double_as_longlong(p_loaded[0][threadIdx.x]);
+                const bool e1 = __double_as_longlong(s.P[1]) == __double_as_longlong(p_loaded[1][threadIdx.x]);
+                const bool e2 = __double_as_longlong(s.P[2]) == __double_as_longlong(p_loaded[2][threadIdx.x]);
+                keepP = ((e0 && e1) ? 1 : 0) | (e2 ? 2 : 0);
+            }
+            store_sim<false, MODE != MODE_R>(s, A.st, i, false, keepSeq, keepP);
             if (TRACE) A.traceCount[i] = s.ntrace;
             acc[0] += (int)rw;                  // rewards are integers in [-10, 10] (counter_traffic.py:96-107)
             acc[1] += (int)(s.nDeliv[0] - nD0);
@@ -1560,6 +1575,82 @@ __global__ void philox_kernel(const uint32_t *ctr, const uint32_t *key, uint32_t
     uint32_t o[4];
     philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1], o);
     out[4 * i] = o[0]; out[4 * i + 1] = o[1]; out[4 * i + 2] = o[2]; out[4 * i + 3] = o[3];
+}
+
+// Action selection of the DQN learner (agents/dqn_counter_traffic.py:46-63), fused: the 1-16-16-16-A ReLU MLP on the
+// centred scalar observation, keras-rl's BoltzmannQPolicy (rl/policy.py: p ~ exp(clip(q / tau, lo, hi)), float64) and
+// the draw, one thread per env.  The ~1.3 k weights sit in shared memory; the A q-values of an env in registers.
+// The uniform variate of (env, draw counter) is Philox4x32-10 keyed by the seed, so the sample does not depend on
+// the batch size or the sharding.  weights: float32, the order of torch's model.parameters() -- W1[16][1], b1[16],
+// W2[16][16], b2[16], W3[16][16], b3[16], W4[A][16], b4[A].
+constexpr int POLICY_HIDDEN = 16;
+constexpr int POLICY_MAX_ACTIONS = 64;
+
+template <int A>
+__global__ void __launch_bounds__(128)
+policy_kernel(const float *weights, const long long *obs, long long n, float obs_center, double tau, double clip_lo,
+              double clip_hi, unsigned long long seed, unsigned long long counter, long long env_offset, int n_durations,
+              long long *flat, int *device, int *duration, double *probs)
+{
+    constexpr int H = POLICY_HIDDEN;
+    constexpr int NW = H + H + H * H + H + H * H + H + A * H + A;
+    __shared__ float w[NW];
+    for (int t = threadIdx.x; t < NW; t += blockDim.x) w[t] = weights[t];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *W1 = w, *b1 = W1 + H, *W2 = b1 + H, *b2 = W2 + H * H, *W3 = b2 + H, *b3 = W3 + H * H, *W4 = b3 + H,
+                *b4 = W4 + A * H;
+    const float x = (float)obs[i] - obs_center;
+    float h1[H], h2[H], h3[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) h1[j] = fmaxf(__fmaf_rn(W1[j], x, b1[j]), 0.f);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float a = b2[j];
+#pragma unroll
+        for (int k = 0; k < H; ++k) a = __fmaf_rn(W2[j * H + k], h1[k], a);
+        h2[j] = fmaxf(a, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float a = b3[j];
+#pragma unroll
+        for (int k = 0; k < H; ++k) a = __fmaf_rn(W3[j * H + k], h2[k], a);
+        h3[j] = fmaxf(a, 0.f);
+    }
+    double e[A];
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+        float q = b4[j];
+#pragma unroll
+        for (int k = 0; k < H; ++k) q = __fmaf_rn(W4[j * H + k], h3[k], q);
+        const double z = fmin(fmax((double)q / tau, clip_lo), clip_hi);
+        e[j] = exp(z);
+        sum += e[j];
+    }
+    // inverse CDF with u in (0, 1): the first action whose cumulative probability exceeds u
+    uint32_t r[4];
+    const unsigned long long env = (unsigned long long)(env_offset + i);
+    philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), (uint32_t)counter, (uint32_t)(counter >> 32),
+                  (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u = ((double)r[0] * 4294967296.0 + (double)r[1] + 0.5) * (1.0 / 18446744073709551616.0);
+    const double target = u * sum;
+    double acc = 0.0;
+    int a = A - 1;
+    bool found = false;
+#pragma unroll
+    for (int j = 0; j < A; ++j) {
+        acc += e[j];
+        if (!found && acc > target) { a = j; found = true; }
+    }
+    if (flat) flat[i] = a;
+    if (device) { device[i] = a / n_durations; duration[i] = a % n_durations; }       // CounterTrafficProcessor, :25-33
+    if (probs) {
+#pragma unroll
+        for (int j = 0; j < A; ++j) probs[i * A + j] = e[j] / sum;
+    }
 }
 
 __global__ void stats_copy_kernel(double *stats, double *out, int clear)
@@ -2324,6 +2415,28 @@ int gw_debug_memo_stats(unsigned long long *out2)
     return GW_OK;
 }
 #endif
+
+int gw_policy_boltzmann(const float *weights, int32_t n_actions, int32_t n_durations, const int64_t *obs, int64_t n,
+                        float obs_center, double tau, double clip_lo, double clip_hi, uint64_t seed, uint64_t counter,
+                        int64_t env_id_offset, int64_t *flat_action, int32_t *device, int32_t *duration, double *probs,
+                        void *stream)
+{
+    if (n <= 0) return GW_OK;
+    if (!weights || !obs) return fail(GW_E_INVALID, "NULL buffer");
+    if ((device == nullptr) != (duration == nullptr)) return fail(GW_E_INVALID, "device and duration come together");
+    if (n_durations < 1 || !(tau > 0)) return fail(GW_E_INVALID, "bad policy parameters");
+    const int grid = grid_for(n, 128);
+    cudaStream_t s = (cudaStream_t)stream;
+#define CALL_POLICY(AA) policy_kernel<AA><<<grid, 128, 0, s>>>(weights, (const long long *)obs, n, obs_center, tau, clip_lo, clip_hi, \
+        seed, counter, env_id_offset, n_durations, (long long *)flat_action, device, duration, probs)
+    if (n_actions == 40) CALL_POLICY(40);               // 2 devices x 20 durations (envs/core.py:39-42)
+    else if (n_actions == 20) CALL_POLICY(20);
+    else if (n_actions == 8) CALL_POLICY(8);
+    else return fail(GW_E_INVALID, "policy kernels are instantiated for 8, 20 and 40 actions, not %d", n_actions);
+#undef CALL_POLICY
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
 
 int gw_philox4x32(const uint32_t *counter, const uint32_t *key, uint32_t *out, int64_t n, void *stream)
 {

@@ -297,6 +297,20 @@ int gw_count_bit_errors(const uint32_t *mask_words, int32_t words_per_row,
                         const int64_t *rows, const int32_t *k0, const int32_t *k1,
                         int32_t *counts, int64_t n, void *stream);
 
+/* Action selection of the learner that consumes the env (agents/dqn_counter_traffic.py:46-63), fused into one
+ * kernel over obs[n]: the 1-16-16-16-n_actions ReLU MLP on (obs - obs_center), keras-rl's BoltzmannQPolicy
+ * (p ~ exp(clip(q / tau, clip_lo, clip_hi)) in float64; the reference uses tau 1, clip +-500) and the draw -- the
+ * uniform variate of (env_id_offset + i, counter) comes from Philox4x32-10 keyed by `seed`, so samples do not
+ * depend on batch size or sharding.  `weights`: device float32 in the order of torch's model.parameters()
+ * (W1[16][1], b1[16], W2[16][16], b2[16], W3[16][16], b3[16], W4[n_actions][16], b4[n_actions]); `obs`: device
+ * int64 [n].  Outputs (device, each may be NULL): flat_action int64 [n]; device / duration int32 [n]
+ * (flat // n_durations, flat % n_durations: CounterTrafficProcessor.process_action, :25-33 -- directly usable
+ * as gw_step's action arrays); probs float64 [n][n_actions] (tests).  n_actions in {8, 20, 40}. */
+int gw_policy_boltzmann(const float *weights, int32_t n_actions, int32_t n_durations, const int64_t *obs, int64_t n,
+                        float obs_center, double tau, double clip_lo, double clip_hi, uint64_t seed, uint64_t counter,
+                        int64_t env_id_offset, int64_t *flat_action, int32_t *device, int32_t *duration, double *probs,
+                        void *stream);
+
 /* Philox4x32-10 (Random123) block function, for known-answer tests: out[4*i..] =
  * philox(counter[4*i..], key[2*i..]).  Device uint32 arrays. */
 int gw_philox4x32(const uint32_t *counter, const uint32_t *key, uint32_t *out, int64_t n,

@@ -88,7 +88,10 @@ enum {
     K_RRM_ANN_INIT,   /* Initialize of SimpleRrmMac._sendAnnouncement */
     K_RRM_TIMEOUT,    /* (duration+1)*TIME_SLOT_LENGTH timeout (simple_stack.py:558) */
     K_ASSIGN_DONE,    /* ASSIGN message eProcessed (simple_stack.py:561) */
-    K_RRM_ANN_END     /* _sendAnnouncement process event -> executeNext */
+    K_RRM_ANN_END,    /* _sendAnnouncement process event -> executeNext */
+    K_STOP,           /* env.run(until=number): StopSimulation event, URGENT (simpy core.py run()) */
+    K_MOVE_INIT,      /* Initialize of a mobility process (tests/test_benchmark.py:73-85) */
+    K_MOVE            /* its timeout: Position.set, then the next timeout */
 };
 
 enum { MAC_NONE = 0, MAC_WAIT_COND, MAC_WAIT_TX, MAC_IDLE };
@@ -168,6 +171,10 @@ typedef struct {
     /* traffic */
     int counter;
     int jam_stage;
+    /* mobility process (gwo_add_mover) */
+    double mv_x0, mv_y0, mv_first, mv_interval;
+    const double *mv_offsets;
+    int mv_n, mv_k;
 } Dev;
 
 typedef struct {
@@ -189,7 +196,7 @@ typedef struct {
     int64_t n_tx, n_deliv[GWO_MAXDEV];
 } Band;
 
-#define HEAP_CAP 512
+#define HEAP_CAP 4096
 
 struct gwo_sim {
     int nbands;
@@ -910,6 +917,25 @@ static void dispatch(gwo_sim *s, Ev e)
             B->ann_running = 0;
         }
         break;
+    case K_STOP:
+        break;
+    case K_MOVE_INIT:
+        /* yield SimMan.timeout(random.uniform(0, MOVE_INTERVAL)) */
+        schedule(s, K_MOVE, PRIO_NORMAL, B->dev[e.a].mv_first, b, e.a, 0);
+        break;
+    case K_MOVE: {
+        Dev *D = &B->dev[e.a];
+        if (D->mv_k < D->mv_n) {
+            /* d.position.set(initialPos.x + xOffset, initialPos.y + yOffset); yield SimMan.timeout(MOVE_INTERVAL).
+             * `initialPos = d.position` (tests/test_benchmark.py:77) is the Position OBJECT that moves, not a copy:
+             * the offsets accumulate -- a random walk, not a jitter around the start position */
+            const double x = D->x + D->mv_offsets[2 * D->mv_k], y = D->y + D->mv_offsets[2 * D->mv_k + 1];
+            D->mv_k++;
+            if (gwo_set_position(s, b, e.a, x, y) < 0 && !s->fault) s->fault = GWO_FAULT_INTERNAL;
+            schedule(s, K_MOVE, PRIO_NORMAL, D->mv_interval, b, e.a, 0);
+        }
+        break;
+    }
     default:
         s->fault = GWO_FAULT_INTERNAL;
     }
@@ -930,6 +956,37 @@ static int run_until_assign(gwo_sim *s, int b, uint32_t seq)
     }
     s->fault = GWO_FAULT_EMPTY;
     return s->fault;
+}
+
+/* env.run(until=number): a StopSimulation event is scheduled URGENT at that time (simpy core.py) */
+int gwo_run_for(gwo_sim *s, double duration)
+{
+    if (s->fault) return s->fault;
+    if (!(duration > 0)) return -1;                 /* simpy: until must be > now */
+    const uint64_t stop_eid = s->eid;
+    schedule(s, K_STOP, PRIO_URGENT, duration, 0, 0, 0);
+    while (s->heap_n > 0) {
+        Ev e = heap_pop(s);
+        s->now = e.t;
+        s->popped++;
+        if (e.kind == K_STOP && e.eid == stop_eid) return 0;
+        dispatch(s, e);
+        if (s->fault) return s->fault;
+    }
+    s->fault = GWO_FAULT_EMPTY;
+    return s->fault;
+}
+
+int gwo_add_mover(gwo_sim *s, int band, int dev, double first_delay, double interval, const double *offsets,
+                  int n_offsets)
+{
+    if (band < 0 || band >= s->nbands || dev < 0 || dev >= s->band[band].ndev) return -1;
+    Dev *D = &s->band[band].dev[dev];
+    D->mv_x0 = D->x; D->mv_y0 = D->y;
+    D->mv_first = first_delay; D->mv_interval = interval;
+    D->mv_offsets = offsets; D->mv_n = n_offsets; D->mv_k = 0;
+    schedule(s, K_MOVE_INIT, PRIO_URGENT, 0, band, dev, 0);
+    return 0;
 }
 
 /* ---------------------------------------------------------------------- */
@@ -1229,7 +1286,7 @@ void gwo_default_scenario(gwo_scenario *sc)        /* counter_traffic.py:114-133
  * independent envs of the same scenario, optional per-env positions
  * pos[env][band][dev][2], action tapes dev_tape/dur_tape[step][env][band].
  * Outputs (any may be NULL): obs/reward/done [step][env][band], now[step][env],
- * counts[env][band][1 + GWO_MAXDEV] (n_tx, deliveries per device) after the last step.
+ * counts[env][band][1 + GWO_BATCH_DEV] (n_tx, deliveries per device) after the last step.
  * Envs [env_begin, env_end) are processed -- the caller shards threads.
  */
 int gwo_run_batch_m(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_reset,
@@ -1275,7 +1332,7 @@ int gwo_run_batch_m(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_res
         if (pos) {
             for (int b = 0; b < nb; b++)
                 for (int d = 0; d < sc->band[b].ndev; d++) {
-                    const double *p = pos + (((size_t)e * nb + b) * GWO_MAXDEV + d) * 2;
+                    const double *p = pos + (((size_t)e * nb + b) * GWO_BATCH_DEV + d) * 2;
                     local.band[b].dev[d].x = p[0];
                     local.band[b].dev[d].y = p[1];
                 }
@@ -1309,8 +1366,8 @@ int gwo_run_batch_m(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_res
             }
             if (counts) {
                 for (int b = 0; b < nb; b++) {
-                    int64_t *c = counts + ((size_t)e * nb + b) * (1 + GWO_MAXDEV);
-                    gwo_counts(s, b, c, c + 1);
+                    int64_t *c = counts + ((size_t)e * nb + b) * (1 + GWO_BATCH_DEV);
+                    { int64_t nd_[GWO_MAXDEV]; gwo_counts(s, b, c, nd_); for (int d_ = 0; d_ < GWO_BATCH_DEV; d_++) c[1 + d_] = nd_[d_]; }
                 }
             }
             gwo_destroy(s);
@@ -1335,8 +1392,8 @@ int gwo_run_batch_m(const gwo_scenario *sc, int64_t nenv, int nsteps, int do_res
         if (g_time_from >= 0 && g_time_from < nsteps && !rc_all) g_timed_seconds += mono_seconds() - t_begin;
         if (counts) {
             for (int b = 0; b < nb; b++) {
-                int64_t *c = counts + ((size_t)e * nb + b) * (1 + GWO_MAXDEV);
-                gwo_counts(s, b, c, c + 1);
+                int64_t *c = counts + ((size_t)e * nb + b) * (1 + GWO_BATCH_DEV);
+                { int64_t nd_[GWO_MAXDEV]; gwo_counts(s, b, c, nd_); for (int d_ = 0; d_ < GWO_BATCH_DEV; d_++) c[1 + d_] = nd_[d_]; }
             }
         }
         gwo_destroy(s);

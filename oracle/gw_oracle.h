@@ -12,9 +12,10 @@
 extern "C" {
 #endif
 
-#define GWO_MAXDEV 8
+#define GWO_MAXDEV 24              /* devices per band held by the model (grids of PHY-only senders: up to 20 + ...) */
+#define GWO_BATCH_DEV 8            /* device stride of the batch API's pos / counts arrays (kept from round 1) */
 #define GWO_MAXBAND 4
-#define GWO_MAXTX 8
+#define GWO_MAXTX 24
 
 #define GWO_ROLE_SENDER 1   /* SimpleNetworkDevice + traffic process (counter_traffic.py:37-61) */
 #define GWO_ROLE_RRM 2      /* SimpleRrmDevice (devices.py:113) */
@@ -78,6 +79,16 @@ void gwo_reset(gwo_sim *s, int64_t *obs);
 int gwo_step(gwo_sim *s, const int32_t *device, const int32_t *duration,
              int64_t *obs, double *reward, uint8_t *done);
 int gwo_set_position(gwo_sim *s, int band, int dev, double x, double y);
+/* SimMan.runSimulation(duration) (simtools.py:77-88 -> simpy env.run(until = now + duration)): every event
+ * strictly before that time and the URGENT ones at it; the clock ends at now + duration. */
+int gwo_run_for(gwo_sim *s, double duration);
+/* A mobility process of device `dev` as in tests/test_benchmark.py:73-85: created now (its Initialize event is
+ * URGENT at the current time), waits `first_delay`, then every `interval` moves the device by
+ * offsets[2*k .. 2*k+1] for k = 0, 1, ... -- the reference's `initialPos` is the moving Position object itself
+ * (:77), so the offsets ACCUMULATE (a random walk); stops after n_offsets jumps.
+ * The offsets array must stay alive. */
+int gwo_add_mover(gwo_sim *s, int band, int dev, double first_delay, double interval, const double *offsets,
+                  int n_offsets);
 double gwo_now(const gwo_sim *s);
 int64_t gwo_popped(const gwo_sim *s);
 int gwo_fault(const gwo_sim *s);

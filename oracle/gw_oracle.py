@@ -15,7 +15,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libgw_oracle.so")
 
-MAXDEV, MAXBAND, MAXTX = 8, 4, 8
+MAXDEV, MAXBAND, MAXTX = 24, 4, 24
+BATCH_DEV = 8           # device stride of the batch API's pos / counts arrays
 ROLE = {"sender": 1, "rrm": 2, "jammer": 3}
 MODE_R, MODE_M = 0, 1
 REC_TX, REC_BER, REC_DEC, REC_RX = 1, 2, 3, 4
@@ -71,6 +72,10 @@ def lib():
         L.gwo_step.restype = C.c_int
         L.gwo_step.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_uint8)]
+        L.gwo_run_for.restype = C.c_int
+        L.gwo_run_for.argtypes = [C.c_void_p, C.c_double]
+        L.gwo_add_mover.restype = C.c_int
+        L.gwo_add_mover.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.c_int]
         L.gwo_set_position.restype = C.c_int
         L.gwo_set_position.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
         L.gwo_now.restype = C.c_double
@@ -129,7 +134,7 @@ def scenario_from_dict(d, mode=MODE_R):
         bs.bandwidth = float(bd.get("bandwidth", 22e6))
         order = [ROLE[x["role"]] for x in bd["devices"]]
         assert order == sorted(order), "canonical device order is senders, rrm, jammers"
-        assert order.count(2) == 1
+        assert order.count(2) <= 1            # grids of PHY-only senders have no RRM (they are run with run_for)
         for i, x in enumerate(bd["devices"]):
             ds = bs.dev[i]
             ds.role = ROLE[x["role"]]
@@ -221,6 +226,21 @@ class Oracle:
             return [(int(o[i]), float(r[i]), bool(d[i])) for i in range(self.nb)]
         return int(o[0]), float(r[0]), bool(d[0])
 
+    def run_for(self, duration):
+        """``SimMan.runSimulation(duration)``: advances simulated time by ``duration`` seconds."""
+        rc = self.L.gwo_run_for(self.h, float(duration))
+        if rc != 0:
+            raise OracleFault("gwo_run_for failed (%d)" % rc)
+
+    def add_mover(self, band, dev, first_delay, interval, offsets):
+        """Mobility process of ``tests/test_benchmark.py:73-85``; ``offsets`` float64 ``[k, 2]`` (accumulating)."""
+        arr = np.ascontiguousarray(offsets, dtype=np.float64).reshape(-1, 2)
+        self._keep = getattr(self, "_keep", []) + [arr]
+        rc = self.L.gwo_add_mover(self.h, band, dev, float(first_delay), float(interval),
+                                  arr.ctypes.data_as(C.POINTER(C.c_double)), int(arr.shape[0]))
+        if rc != 0:
+            raise OracleFault("gwo_add_mover failed")
+
     def set_position(self, band, dev, x, y):
         """``device.position.set(x, y)`` between steps; transmissions that are on the air see the
         reference's ``SimplePhy._onAttenuationChange``."""
@@ -295,7 +315,7 @@ def run_batch(scenario, dev_tape, dur_tape, pos=None, do_reset=True, threads=Non
     """
     Run ``nenv`` independent envs for ``nsteps`` steps with ``threads`` host threads.
     ``dev_tape`` / ``dur_tape``: int32 ``[nsteps, nenv, nbands]`` (or ``[nsteps, nenv]``).
-    ``pos``: optional float64 ``[nenv, nbands, MAXDEV, 2]``.
+    ``pos``: optional float64 ``[nenv, nbands, BATCH_DEV, 2]``.
     Returns a dict of numpy arrays.
     """
     L = lib()
@@ -314,7 +334,7 @@ def run_batch(scenario, dev_tape, dur_tape, pos=None, do_reset=True, threads=Non
     assert nb2 == nb
     if pos is not None:
         pos = np.ascontiguousarray(pos, dtype=np.float64)
-        assert pos.shape == (nenv, nb, MAXDEV, 2)
+        assert pos.shape == (nenv, nb, BATCH_DEV, 2)
     res = {}
     if "obs" in want:
         res["obs"] = np.zeros((nsteps, nenv, nb), dtype=np.int64)
@@ -325,7 +345,7 @@ def run_batch(scenario, dev_tape, dur_tape, pos=None, do_reset=True, threads=Non
     if "now" in want:
         res["now"] = np.zeros((nsteps, nenv), dtype=np.float64)
     if "counts" in want:
-        res["counts"] = np.zeros((nenv, nb, 1 + MAXDEV), dtype=np.int64)
+        res["counts"] = np.zeros((nenv, nb, 1 + BATCH_DEV), dtype=np.int64)
 
     def ptr(a):
         return None if a is None else a.ctypes.data_as(C.c_void_p)
