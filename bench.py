@@ -307,6 +307,42 @@ def cfg5_pendulum(dev_t, rank=0, world=1, steps=32):
             "mean_abs_angle_deg": float(torch.rad2deg(th).abs().mean())}
 
 
+def grid_benchmark(dev_t, rank=0, world=1, n_envs=4096, n_devices=20):
+    """
+    The reference's own benchmark (tests/test_benchmark.py:52-91, `make benchmark`): a grid of 20 PHY-only
+    SendingDevices, static and with the mobility processes, advanced by ONE simulated second -- here for
+    `n_envs` independent grids at once.  BASELINE.md (session-measured, one core): 1.44 s / 4.68 s of wall time
+    per simulated second and grid for the static / mobile variant of the Python reference.
+    """
+    import torch
+    from gymwipe_b200.envs import SendingDeviceGrid
+    out = {"workload": "reference benchmark grid: %d independent grids x %d PHY-only senders (40 dBm, 10 ms send "
+                       "interval), runSimulation(1.0)" % (n_envs, n_devices), "n_envs": n_envs}
+    stream = torch.cuda.current_stream(dev_t)
+    for label, mobile in (("static", False), ("mobile", True)):
+        grid = SendingDeviceGrid(n_envs, n_devices, device=dev_t, mobile=mobile, max_moves=1002, seed=100 + rank)
+        grid.runSimulation(0.01)                        # warm-up (module load, first touch)
+        torch.cuda.synchronize(dev_t)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        grid.runSimulation(0.99)
+        e1.record(stream)
+        torch.cuda.synchronize(dev_t)
+        grid.check()
+        ms = e0.elapsed_time(e1)
+        st = grid.stats()
+        out[label] = {"device_seconds_per_simulated_second": ms * 1e-3 / 0.99,
+                      "grid_seconds_per_second": n_envs * 0.99 / (ms * 1e-3),
+                      "transmissions_per_grid": float(st[0].sum()) / n_envs,
+                      "payloads_decoded_per_grid": float(st[3].sum()) / n_envs,
+                      "reference_seconds_per_simulated_second_one_grid": 4.68 if mobile else 1.44}
+        grid.close()
+        del grid
+        torch.cuda.empty_cache()
+    out["ms_per_step"] = 1e3 * out["mobile"]["device_seconds_per_simulated_second"]
+    return out
+
+
 def cpu_baseline_run(target_seconds, threads=None):
     """The oracle port on the host cores, on a bounded sample of the same workload (steady state: every
     env is burnt in for BURN_IN_STEPS steps first; only the steps after that are timed, per thread)."""
@@ -595,6 +631,7 @@ def own_arm(args, rank, world, local_rank):
         for name, fn in (("cfg3_long_packet_mode_m", lambda: cfg3_long_packet(dev_t, peak, rank, world)),
                          ("cfg4_multiband", lambda: cfg4_multiband(dev_t, rank, world)),
                          ("cfg5_pendulum", lambda: cfg5_pendulum(dev_t, rank, world)),
+                         ("reference_benchmark_grid", lambda: grid_benchmark(dev_t, rank, world)),
                          ("mask_scan", lambda: mask_scan_roofline(dev_t, peak, "random") if world == 1 else None)):
             try:                                          # extras must never take the headline down
                 r, err = fn(), None

@@ -58,6 +58,18 @@ class Config(C.Structure):
                 ("plant", C.c_int32), ("pendulum", PendulumConfig)]
 
 
+GW_GRID_MAX_DEVICES = 24
+GW_GRID_FIELD_NOW, GW_GRID_FIELD_STATS, GW_GRID_FIELD_POSITIONS, GW_GRID_FIELD_RECEIVED_POWER = range(4)
+
+
+class GridConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("n_envs", C.c_int64), ("n_devices", C.c_int32),
+                ("frequency_hz", C.c_double), ("bandwidth_hz", C.c_double),
+                ("power_dbm", C.c_double * GW_GRID_MAX_DEVICES), ("send_interval", C.c_double * GW_GRID_MAX_DEVICES),
+                ("header_bytes", C.c_int32 * GW_GRID_MAX_DEVICES), ("payload_bytes", C.c_int32 * GW_GRID_MAX_DEVICES),
+                ("move_interval", C.c_double), ("max_moves", C.c_int32)]
+
+
 class NativeError(RuntimeError):
     def __init__(self, code, message):
         super().__init__("gymwipe_b200 native error %d: %s" % (code, message))
@@ -65,7 +77,7 @@ class NativeError(RuntimeError):
 
 
 def _sources():
-    return [os.path.join(CSRC, f) for f in ("gw_kernels.cu", "gw_core.cuh", "gw_pendulum.cuh")] + [INCLUDE]
+    return [os.path.join(CSRC, f) for f in ("gw_kernels.cu", "gw_core.cuh", "gw_pendulum.cuh", "gw_grid.cuh")] + [INCLUDE]
 
 
 def needs_build():
@@ -139,6 +151,12 @@ _SIGNATURES = {
     "gw_ber_bpsk": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),
     "gw_count_bit_errors": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP, _VP, C.c_int64, _VP]),
     "gw_philox4x32": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),
+    "gw_grid_create": (C.c_int, [C.POINTER(GridConfig), C.c_int, _VP, _VP, _VP, _VP, _VP, C.POINTER(_VP)]),
+    "gw_grid_destroy": (None, [_VP]),
+    "gw_grid_run": (C.c_int, [_VP, C.c_double, _VP]),
+    "gw_grid_run_traced": (C.c_int, [_VP, C.c_double, _VP, _VP, C.c_int32, _VP]),
+    "gw_grid_read": (C.c_int, [_VP, C.c_int, _VP, _VP]),
+    "gw_grid_check": (C.c_int, [_VP, _VP]),
     "gw_policy_boltzmann": (C.c_int, [_VP, C.c_int32, C.c_int32, _VP, C.c_int64, C.c_float, C.c_double, C.c_double, C.c_double,
                                       C.c_uint64, C.c_uint64, C.c_int64, _VP, _VP, _VP, _VP, _VP]),
     "gw_max_correctable_ber": (C.c_double, [C.c_int, C.c_int]),

@@ -33,6 +33,7 @@
 
 #include "gw_core.cuh"
 #include "gw_pendulum.cuh"
+#include "gw_grid.cuh"
 
 using namespace gw;
 
@@ -1660,6 +1661,71 @@ __global__ void stats_copy_kernel(double *stats, double *out, int clear)
 }
 
 // ------------------------------------------------------------------------------------
+// grids of PHY-only senders with in-step mobility (gw_grid.cuh): one band-sim per thread, its state block in
+// global memory
+// ------------------------------------------------------------------------------------
+
+struct GridArgs {
+    char *state;                // [n_envs] blocks of `block_bytes`
+    size_t block_bytes;
+    long long n_envs;
+    const double *offsets;      // [n_envs][n_dev][max_moves][2] or NULL
+    double *trace;              // [n_envs][cap][8] or NULL
+    int *trace_count;
+    int trace_cap;
+    int *errflag;
+};
+
+__global__ void grid_init_kernel(GridArgs A, GridParams G, const double *pos, const double *delays, const double *move_delays)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_envs) return;
+    GridView v = grid_view(A.state + (size_t)i * A.block_bytes, G.ndev);
+    grid_init(v, G, pos + i * G.ndev * 2, delays + i * G.ndev, move_delays ? move_delays + i * G.ndev : nullptr);
+}
+
+__global__ void __launch_bounds__(64)
+grid_run_kernel(GridArgs A, GridParams G, double duration)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_envs) return;
+    GridView v = grid_view(A.state + (size_t)i * A.block_bytes, G.ndev);
+    if (A.trace) { v.trace = A.trace + (long long)i * A.trace_cap * 8; v.traceCap = A.trace_cap; v.ntrace = 0; }
+    const double *off = A.offsets ? A.offsets + (long long)i * G.ndev * G.maxMoves * 2 : nullptr;
+    grid_run(v, G, duration, off);
+    if (A.trace) A.trace_count[i] = v.ntrace;
+    if (v.h->fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = v.h->fault; } }
+}
+
+__global__ void grid_read_kernel(GridArgs A, GridParams G, int field, double *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_envs) return;
+    const GridView v = grid_view(A.state + (size_t)i * A.block_bytes, G.ndev);
+    const long long n = A.n_envs;
+    if (field == GW_GRID_FIELD_NOW) { out[i] = v.h->now; return; }
+    for (int d = 0; d < G.ndev; ++d) {
+        const GridDev &D = v.dev[d];
+        if (field == GW_GRID_FIELD_STATS) {
+            const unsigned st[6] = {D.nTx, D.nHdrOk, D.nHdrFail, D.nPayOk, D.nPayFail, D.nBer};
+            for (int k = 0; k < 6; ++k) out[((long long)k * G.ndev + d) * n + i] = st[k];
+        } else if (field == GW_GRID_FIELD_POSITIONS) {
+            out[((long long)0 * G.ndev + d) * n + i] = D.x; out[((long long)1 * G.ndev + d) * n + i] = D.y;
+        } else if (field == GW_GRID_FIELD_RECEIVED_POWER) {
+            out[(long long)d * n + i] = D.P;
+        }
+    }
+}
+
+struct gw_grid_handle {
+    gw_grid_config cfg;
+    int device;
+    GridParams G;
+    GridArgs A;
+    int *errflag;
+};
+
+// ------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------
 
@@ -2436,6 +2502,110 @@ int gw_policy_boltzmann(const float *weights, int32_t n_actions, int32_t n_durat
 #undef CALL_POLICY
     CUDA_TRY(cudaGetLastError());
     return GW_OK;
+}
+
+int gw_grid_create(const gw_grid_config *cfg, int device, const double *positions, const double *delays,
+                   const double *move_delays, const double *offsets, void *stream, gw_grid_handle **out)
+{
+    if (!cfg || !out || !positions || !delays) return fail(GW_E_INVALID, "NULL argument");
+    if (cfg->abi_version != GW_ABI_VERSION) return fail(GW_E_INVALID, "abi_version %d != %d", cfg->abi_version, GW_ABI_VERSION);
+    if (cfg->n_envs < 1) return fail(GW_E_INVALID, "n_envs must be >= 1");
+    if (cfg->n_devices < 1 || cfg->n_devices > GW_GRID_MAX_DEVICES) return fail(GW_E_INVALID, "n_devices must be in 1..%d", GW_GRID_MAX_DEVICES);
+    if (cfg->max_moves < 0 || (cfg->max_moves > 0 && (!move_delays || !offsets || !(cfg->move_interval > 0))))
+        return fail(GW_E_INVALID, "mobility needs move_delays, offsets and move_interval > 0");
+    for (int d = 0; d < cfg->n_devices; ++d) {
+        if (!(cfg->send_interval[d] > 0)) return fail(GW_E_INVALID, "send_interval must be > 0");
+        if (cfg->header_bytes[d] < 1 || cfg->payload_bytes[d] < 1) return fail(GW_E_INVALID, "bad packet size");
+    }
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return fail(GW_E_CUDA, "no CUDA device: gymwipe_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(GW_E_INVALID, "device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    gw_grid_handle *h = new (std::nothrow) gw_grid_handle();
+    if (!h) return fail(GW_E_INVALID, "out of host memory");
+    std::memset(h, 0, sizeof *h);
+    h->cfg = *cfg;
+    h->device = device;
+    GridParams &G = h->G;
+    G.ndev = cfg->n_devices; G.maxMoves = cfg->max_moves; G.moveInterval = cfg->move_interval;
+    G.bitRate = 133.33333e3; G.dataRate = 0.75 * G.bitRate; G.maxBer = gw_max_correctable_ber(3, 4);
+    G.tenLog10BitRate = 10 * std::log10(G.bitRate); G.qDen = 1.135 * std::sqrt(2 * 3.141592653589793);
+    G.bitsFactor = 2 - 0.75; G.frequency = cfg->frequency_hz;
+    G.thermal = 1.38e-23 * (20.0 + 273.15) * cfg->bandwidth_hz * 1000;
+    for (int d = 0; d < cfg->n_devices; ++d) {
+        G.power[d] = cfg->power_dbm[d]; G.interval[d] = cfg->send_interval[d];
+        G.hdrBytes[d] = cfg->header_bytes[d]; G.payBytes[d] = cfg->payload_bytes[d];
+    }
+    h->A.block_bytes = (grid_state_bytes(cfg->n_devices) + 15) / 16 * 16;
+    h->A.n_envs = cfg->n_envs;
+    h->A.offsets = cfg->max_moves > 0 ? offsets : nullptr;
+    cudaError_t e = cudaMalloc((void **)&h->A.state, h->A.block_bytes * (size_t)cfg->n_envs);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->errflag, 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->errflag, 0, 4 * sizeof(int), (cudaStream_t)stream);
+    if (e != cudaSuccess) { gw_grid_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
+    h->A.errflag = h->errflag;
+    grid_init_kernel<<<grid_for(cfg->n_envs, 64), 64, 0, (cudaStream_t)stream>>>(h->A, h->G, positions, delays,
+                                                                                 cfg->max_moves > 0 ? move_delays : nullptr);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { gw_grid_destroy(h); return fail(GW_E_CUDA, "init kernel: %s", cudaGetErrorString(e)); }
+    *out = h;
+    return GW_OK;
+}
+
+void gw_grid_destroy(gw_grid_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->A.state) cudaFree(h->A.state);
+    if (h->errflag) cudaFree(h->errflag);
+    delete h;
+}
+
+static int grid_launch(gw_grid_handle *h, double duration, double *trace, int32_t *trace_count, int32_t cap, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    if (!(duration > 0)) return fail(GW_E_INVALID, "duration must be > 0 (simpy: until must be greater than now)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    GridArgs A = h->A;
+    A.trace = trace; A.trace_count = trace_count; A.trace_cap = cap;
+    grid_run_kernel<<<grid_for(A.n_envs, 64), 64, 0, (cudaStream_t)stream>>>(A, h->G, duration);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_grid_run(gw_grid_handle *h, double duration, void *stream)
+{
+    return grid_launch(h, duration, nullptr, nullptr, 0, stream);
+}
+
+int gw_grid_run_traced(gw_grid_handle *h, double duration, double *trace, int32_t *trace_count, int32_t cap, void *stream)
+{
+    if (!trace || !trace_count || cap < 1) return fail(GW_E_INVALID, "bad trace buffer");
+    return grid_launch(h, duration, trace, trace_count, cap, stream);
+}
+
+int gw_grid_read(gw_grid_handle *h, int field, double *out, void *stream)
+{
+    if (!h || !out) return fail(GW_E_INVALID, "NULL argument");
+    if (field < GW_GRID_FIELD_NOW || field > GW_GRID_FIELD_RECEIVED_POWER) return fail(GW_E_INVALID, "unknown field %d", field);
+    CUDA_TRY(cudaSetDevice(h->device));
+    grid_read_kernel<<<grid_for(h->A.n_envs, 64), 64, 0, (cudaStream_t)stream>>>(h->A, h->G, field, out);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_grid_check(gw_grid_handle *h, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int flag[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(flag, h->errflag, sizeof flag, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (flag[0] == 0) return GW_OK;
+    CUDA_TRY(cudaMemsetAsync(h->errflag, 0, sizeof flag, s));
+    return fail(GW_E_SIMFAULT, "grid env %d hit a condition under which the reference raises (fault %d)", flag[1], flag[2]);
 }
 
 int gw_philox4x32(const uint32_t *counter, const uint32_t *key, uint32_t *out, int64_t n, void *stream)

@@ -6,6 +6,7 @@ from gymwipe_b200.envs.counter_traffic import CounterTrafficEnv
 from gymwipe_b200.envs.core import BaseEnv, Interpreter
 from gymwipe_b200.envs.inverted_pendulum import InvertedPendulumEnv
 from gymwipe_b200.envs.population import EnvPopulation
+from gymwipe_b200.envs.sending_grid import SendingDeviceGrid
 
 registry = {
     'CounterTraffic-v0': CounterTrafficEnv,
@@ -24,4 +25,4 @@ def make(id, **kwargs):
     return registry[id](**kwargs)
 
 
-__all__ = ["CounterTrafficEnv", "InvertedPendulumEnv", "EnvPopulation", "BaseEnv", "Interpreter", "make", "register", "registry"]
+__all__ = ["CounterTrafficEnv", "InvertedPendulumEnv", "EnvPopulation", "SendingDeviceGrid", "BaseEnv", "Interpreter", "make", "register", "registry"]

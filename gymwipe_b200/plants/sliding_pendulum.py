@@ -1,5 +1,5 @@
 """
-Mirror of ``gymwipe/plants/sliding_pendulum.py`` (and ``plants/core.py``): the sliding inverted
+Declarative descriptor (a parameter holder, by design: SURVEY.md section 8b) with the names of ``gymwipe/plants/sliding_pendulum.py`` (and ``plants/core.py``): the sliding inverted
 pendulum as a parameter set.  The reference builds an ODE world (py3ode) of two spheres, a slider
 joint with a velocity motor and a hinge (``sliding_pendulum.py:24-55``); here the same mechanical
 system is integrated by the step kernel (``gymwipe_b200/csrc/gw_pendulum.cuh``).

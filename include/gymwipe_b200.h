@@ -276,6 +276,59 @@ int gw_read_state(gw_handle *h, int field, double *out, void *stream);
 int gw_set_masks(gw_handle *h, const uint32_t *mask_words, int32_t slots, int32_t words_per_row,
                  void *stream);
 
+/* ---- grids of PHY-only senders with in-step mobility ---------------------
+ *
+ * The reference's own benchmark scenario (tests/test_benchmark.py:20-91): n_devices devices on one frequency
+ * band, each a SimplePhy driven by a sender process -- timeout(initial delay), then one SEND of a
+ * header_bytes + payload_bytes packet at power_dbm every send_interval (:31-48) -- and every PHY receiving what
+ * the others send (simple_stack.py:77-286, mode R accounting); optionally one mobility process per device
+ * (:73-85): timeout(move delay), then every move_interval the device moves by the next offset of its tape
+ * (the reference's `initialPos` is the moving Position object: offsets accumulate), transmissions on the air
+ * seeing SimplePhy._onAttenuationChange (simple_stack.py:119-128).  No RRM, no MAC, no gym step: the envs are
+ * advanced with gw_grid_run = SimMan.runSimulation(duration) (simtools.py:77-88).  n_envs independent grids,
+ * one GPU thread each; the device count is a run-time value. */
+#define GW_GRID_MAX_DEVICES 24
+
+typedef struct {
+    int32_t abi_version;            /* GW_ABI_VERSION */
+    int64_t n_envs;
+    int32_t n_devices;
+    double frequency_hz, bandwidth_hz;                  /* FrequencyBandSpec, physical.py:293-306 */
+    double power_dbm[GW_GRID_MAX_DEVICES];              /* 40.0 in the reference's benchmark (:45) */
+    double send_interval[GW_GRID_MAX_DEVICES];          /* SEND_INTERVAL = 1e-2 (:17) */
+    int32_t header_bytes[GW_GRID_MAX_DEVICES];          /* SimpleMacHeader: 13 */
+    int32_t payload_bytes[GW_GRID_MAX_DEVICES];         /* Transmittable("A message to all my homies"): 26 */
+    double move_interval;                               /* MOVE_INTERVAL = 1e-3 (:18) */
+    int32_t max_moves;              /* jumps per device in the offset tape; 0: no mobility processes */
+} gw_grid_config;
+
+typedef struct gw_grid_handle gw_grid_handle;
+
+/* Replaces the device_grid / mobile_device_grid fixtures (:52-85).  Device buffers (float64): positions
+ * [n_envs][n_devices][2]; delays [n_envs][n_devices] (the fixtures draw random.uniform(0, SEND_INTERVAL));
+ * with max_moves > 0: move_delays [n_envs][n_devices] (random.uniform(0, MOVE_INTERVAL)) and offsets
+ * [n_envs][n_devices][max_moves][2] (random.uniform(-.2, .2)), which must stay alive as long as the handle (a
+ * device stops moving when its tape is exhausted).  The other buffers are consumed on `stream`. */
+int gw_grid_create(const gw_grid_config *cfg, int device, const double *positions, const double *delays,
+                   const double *move_delays, const double *offsets, void *stream, gw_grid_handle **out);
+void gw_grid_destroy(gw_grid_handle *h);
+
+/* SimMan.runSimulation(duration) for every env: all events strictly before now + duration. */
+int gw_grid_run(gw_grid_handle *h, double duration, void *stream);
+/* The same with an event trace (record format of gw_step_traced, kinds 1-3): trace [n_envs][cap][8],
+ * trace_count [n_envs]. */
+int gw_grid_run_traced(gw_grid_handle *h, double duration, double *trace, int32_t *trace_count, int32_t cap,
+                       void *stream);
+
+#define GW_GRID_FIELD_NOW 0             /* [n_envs] */
+#define GW_GRID_FIELD_STATS 1           /* [6][n_devices][n_envs]: transmissions started; headers decoded / failed;
+                                           payloads decoded / failed (as a receiver); BER evaluations */
+#define GW_GRID_FIELD_POSITIONS 2       /* [2][n_devices][n_envs] */
+#define GW_GRID_FIELD_RECEIVED_POWER 3  /* [n_devices][n_envs] SimplePhy._receivedPower (mW) */
+int gw_grid_read(gw_grid_handle *h, int field, double *out, void *stream);
+/* Synchronises; GW_E_SIMFAULT if an env hit a condition under which the reference raises. */
+int gw_grid_check(gw_grid_handle *h, void *stream);
+
 /* ---- standalone kernels (numeric parity tests, roofline measurements) ------------- */
 
 /* K1: FSPL attenuation in dB, FsplAttenuation._update (attenuation_models.py:28-36) with

@@ -12,6 +12,7 @@ static long long g_macro_stat[4] = {0, 0, 0, 0};
 #define GW_STAT_MACRO(i) (++g_macro_stat[i])
 #include "../../gymwipe_b200/csrc/gw_core.cuh"
 #include "../../gymwipe_b200/csrc/gw_pendulum.cuh"
+#include "../../gymwipe_b200/csrc/gw_grid.cuh"
 
 using namespace gw;
 
@@ -252,6 +253,42 @@ int hs_run_moves(const HsScenario *sc, int64_t nenv, int nsteps, int do_reset, c
     }
 #undef HS_ARGS
     return -1;
+}
+
+// grid of PHY-only senders (gw_grid.cuh) on the host: one band-sim, `ndur` successive runSimulation(duration)
+// calls; per call the clock and the trace records are returned.  Returns the fault code.
+int hs_grid_run(int n, double frequency, double bandwidth, const double *power, const double *interval,
+                const int32_t *hdr, const int32_t *pay, const double *pos, const double *delays,
+                const double *move_delays, const double *offsets, int max_moves, double move_interval,
+                const double *durations, int ndur, double *now_out, double *trace, int trace_cap, int32_t *trace_counts,
+                uint32_t *stats /* [n][6] */)
+{
+    GridParams G;
+    std::memset(&G, 0, sizeof G);
+    G.ndev = n; G.maxMoves = max_moves; G.moveInterval = move_interval;
+    G.bitRate = 133.33333e3; G.dataRate = 0.75 * G.bitRate; G.maxBer = 0.25;
+    G.tenLog10BitRate = 10 * std::log10(G.bitRate); G.qDen = 1.135 * std::sqrt(2 * 3.141592653589793);
+    G.bitsFactor = 1.25; G.frequency = frequency; G.thermal = 1.38e-23 * (20.0 + 273.15) * bandwidth * 1000;
+    for (int d = 0; d < n; ++d) { G.power[d] = power[d]; G.interval[d] = interval[d]; G.hdrBytes[d] = hdr[d]; G.payBytes[d] = pay[d]; }
+    std::vector<char> block(grid_state_bytes(n));
+    GridView v = grid_view(block.data(), n);
+    grid_init(v, G, pos, delays, max_moves > 0 ? move_delays : nullptr);
+    int used = 0;
+    for (int k = 0; k < ndur; ++k) {
+        v.trace = trace ? trace + (size_t)used * 8 : nullptr;
+        v.traceCap = trace_cap - used; v.ntrace = 0;
+        grid_run(v, G, durations[k], offsets);
+        now_out[k] = v.h->now;
+        trace_counts[k] = v.ntrace;
+        used += v.ntrace < v.traceCap ? v.ntrace : v.traceCap;
+        if (v.h->fault) return v.h->fault;
+    }
+    for (int d = 0; d < n; ++d) {
+        const GridDev &D = v.dev[d];
+        stats[d * 6 + 0] = D.nTx; stats[d * 6 + 1] = D.nHdrOk; stats[d * 6 + 2] = D.nHdrFail;
+        stats[d * 6 + 3] = D.nPayOk; stats[d * 6 + 4] = D.nPayFail; stats[d * 6 + 5] = D.nBer;
+    }
+    return 0;
 }
 
 void hs_set_no_macro(int v) { g_no_macro = v; }

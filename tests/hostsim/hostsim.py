@@ -14,6 +14,7 @@ SO = os.path.join(HERE, "_hostsim.so")
 SRC = os.path.join(HERE, "gw_hostsim.cpp")
 CORE = os.path.join(HERE, "..", "..", "gymwipe_b200", "csrc", "gw_core.cuh")
 PEND = os.path.join(HERE, "..", "..", "gymwipe_b200", "csrc", "gw_pendulum.cuh")
+GRID = os.path.join(HERE, "..", "..", "gymwipe_b200", "csrc", "gw_grid.cuh")
 
 MAXDEV, MAXSEND, MAXBAND = 4, 2, 4
 
@@ -40,7 +41,7 @@ _lib = None
 
 
 def build(force=False):
-    if force or not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(PEND)):
+    if force or not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(PEND), os.path.getmtime(GRID)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared",
                                "-o", SO, SRC])
     return SO
@@ -143,3 +144,50 @@ def run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, mode=0, seed=0, e
     ms = (C.c_longlong * 2)()
     L.hs_macro_stats(ms)
     return {"macro_tx": int(ms[0]), "macro_tail": int(ms[1]), "rc": rc, "obs": obs, "reward": rew, "done": done, "now": now, "counts": counts, "power": power}
+
+
+def grid_run(scenario, durations, move_delays=None, offsets=None, move_interval=1e-3, trace_cap=400000):
+    """Grid of PHY-only senders (``gw_grid.cuh``) on the host: ``scenario`` is a one-band scenario dict of
+    ``jammer`` devices; ``offsets`` float64 ``[n, k, 2]`` (accumulating jumps) switches the mobility processes on.
+    Returns ``{"now": [...], "records": [[...], ...], "stats": uint32 [n, 6]}`` (records in Tracer tuple format)."""
+    L = lib()
+    devs = scenario["bands"][0]["devices"]
+    assert all(d["role"] == "jammer" for d in devs)
+    n = len(devs)
+    f64 = lambda xs: np.ascontiguousarray(xs, dtype=np.float64)
+    power, interval = f64([d.get("power", 0.0) for d in devs]), f64([d["interval"] for d in devs])
+    hdr = np.ascontiguousarray([d.get("hdr", 13) for d in devs], dtype=np.int32)
+    pay = np.ascontiguousarray([d["payload"] for d in devs], dtype=np.int32)
+    pos = f64([[d["x"], d["y"]] for d in devs])
+    delays = f64([d["delay"] for d in devs])
+    mobile = offsets is not None
+    off = f64(offsets) if mobile else np.zeros((n, 1, 2))
+    md = f64(move_delays) if mobile else np.zeros(n)
+    dur = f64(durations)
+    now = np.zeros(len(dur))
+    trace = np.zeros((trace_cap, 8))
+    counts = np.zeros(len(dur), np.int32)
+    stats = np.zeros((n, 6), np.uint32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    L.hs_grid_run.restype = C.c_int
+    L.hs_grid_run.argtypes = [C.c_int, C.c_double, C.c_double] + [C.c_void_p] * 8 + [C.c_int, C.c_double, C.c_void_p, C.c_int,
+                                                                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    band = scenario["bands"][0]
+    rc = L.hs_grid_run(n, float(band.get("frequency", 2.4e9)), float(band.get("bandwidth", 22e6)), ptr(power), ptr(interval),
+                       ptr(hdr), ptr(pay), ptr(pos), ptr(delays), ptr(md), ptr(off), off.shape[1] if mobile else 0,
+                       float(move_interval), ptr(dur), len(dur), ptr(now), ptr(trace), trace_cap, ptr(counts), ptr(stats))
+    assert int(counts.sum()) <= trace_cap, "raise trace_cap"
+    records, at = [], 0
+    for k in range(len(dur)):
+        recs = []
+        for r in trace[at:at + counts[k]]:
+            kind = int(r[0])
+            if kind == 1:
+                recs.append(("tx", float(r[1]), 0, int(r[2]), float(r[3]), float(r[4]), float(r[5])))
+            elif kind == 2:
+                recs.append(("ber", float(r[1]), 0, int(r[2]), float(r[3])))
+            elif kind == 3:
+                recs.append(("dec", float(r[1]), 0, int(r[2]), int(r[3]), float(r[4]), float(r[5]), bool(r[6])))
+        at += counts[k]
+        records.append(recs)
+    return {"rc": rc, "now": list(now), "records": records, "stats": stats}
