@@ -17,14 +17,14 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.environ.get("GYMWIPE_B200_LIB") or os.path.join(LIB_DIR, "libgymwipe_b200.so")
 INCLUDE = os.path.join(HERE, "..", "include", "gymwipe_b200.h")
 
-GW_ABI_VERSION = 1
+GW_ABI_VERSION = 2
 GW_MAX_BANDS, GW_MAX_DEVICES, GW_MAX_SENDERS, GW_MAX_JAMMERS = 4, 4, 2, 1
 GW_OK, GW_E_INVALID, GW_E_CUDA, GW_E_STATE, GW_E_ACTION, GW_E_SIMFAULT = 0, -1, -2, -3, -4, -5
 GW_MODE_REFERENCE, GW_MODE_MASK_PHILOX, GW_MODE_MASK_FED = 0, 1, 2
 GW_ROLE_SENDER, GW_ROLE_RRM, GW_ROLE_JAMMER = 1, 2, 3
 (GW_FIELD_NOW, GW_FIELD_RECEIVED_POWER, GW_FIELD_NEXT_TICK, GW_FIELD_COUNTER, GW_FIELD_QUEUE_LEN,
  GW_FIELD_N_TRANSMISSIONS, GW_FIELD_N_DELIVERED, GW_FIELD_RECEIVED_VALUES, GW_FIELD_ATTENUATION_DB,
- GW_FIELD_RX_POWER_MW, GW_FIELD_FAULT, GW_FIELD_TIES, GW_FIELD_TX_SEQ, GW_FIELD_PLANT) = range(14)
+ GW_FIELD_RX_POWER_MW, GW_FIELD_FAULT, GW_FIELD_TIES, GW_FIELD_TX_SEQ, GW_FIELD_PLANT, GW_FIELD_N_RECEIVED) = range(15)
 GW_PLANT_NONE, GW_PLANT_SLIDING_PENDULUM = 0, 1
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-fmad=false",
@@ -34,6 +34,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 class DeviceConfig(C.Structure):
     _fields_ = [("role", C.c_int32), ("x", C.c_double), ("y", C.c_double),
                 ("multiplicity", C.c_int32), ("payload_bytes", C.c_int32), ("interval", C.c_double),
+                ("max_ticks", C.c_int32), ("receive", C.c_int32),
                 ("jam_interval", C.c_double), ("jam_delay", C.c_double), ("jam_power_dbm", C.c_double),
                 ("jam_header_bytes", C.c_int32), ("jam_payload_bytes", C.c_int32)]
 
@@ -59,7 +60,7 @@ class Config(C.Structure):
 
 
 GW_GRID_MAX_DEVICES = 24
-GW_GRID_FIELD_NOW, GW_GRID_FIELD_STATS, GW_GRID_FIELD_POSITIONS, GW_GRID_FIELD_RECEIVED_POWER = range(4)
+GW_GRID_FIELD_NOW, GW_GRID_FIELD_STATS, GW_GRID_FIELD_POSITIONS, GW_GRID_FIELD_RECEIVED_POWER, GW_GRID_FIELD_FAULT = range(5)
 
 
 class GridConfig(C.Structure):

@@ -57,7 +57,8 @@ constexpr int kMaxAirBytes = 70000;     // largest packet on the path: 13 + 12 +
 
 enum : int { S_IDLE = 0, S_WAITRX = 1, S_SLOT = 2, S_HDR = 3, S_PAY = 4 };
 enum : int { MAC_NONE = 0, MAC_WAIT_COND = 1, MAC_WAIT_TX = 2, MAC_IDLE = 3 };
-enum : int { EV_NONE = 0, EV_TICK = 1, EV_JAM = 2, EV_PHY = 3, EV_W = 4, EV_RRM = 5 };
+enum : int { EV_NONE = 0, EV_TICK = 1, EV_JAM = 2, EV_PHY = 3, EV_W = 4, EV_RRM = 5, EV_RXTO = 6 };
+constexpr double kReceiveTimeout = 100.0;      // SimpleNetworkDevice.RECEIVE_TIMEOUT (s), devices.py:66
 enum : int { MODE_R = 0, MODE_M_PHILOX = 1, MODE_M_FED = 2 };
 enum : int { FAULT_NONE = 0, FAULT_REF_KEYERROR = 2, FAULT_REF_ASSERT = 3, FAULT_SENDQ = 4,
              FAULT_EMPTY = 6 };
@@ -70,6 +71,8 @@ struct BandParams {
     int mult[kMaxSend];
     int payloadRule[kMaxSend];          // -1: byteSize = counter
     double interval[kMaxSend];
+    int maxTicks[kMaxSend];             // 0: the traffic process runs forever (reference); n: a burst of n ticks
+    int recv[kMaxSend];                 // 1: MAC receive mode (SimpleNetworkDevice.receiving = True, devices.py:70-97)
     double jamInterval[kMaxJam], jamDelay[kMaxJam];
     int jamHdr[kMaxJam], jamPay[kMaxJam];
 };
@@ -264,6 +267,11 @@ struct Sim {
     Arr<int, NS, O_wPend> wPend;
     Arr<double, NS, O_stopW> stopW;
     Arr<uint32_t, NS, O_sW> sW;
+    // (MAC receive mode, simple_stack.py:436-460 / devices.py:88-97: the current RECEIVE command's timeout and the
+    // count of packets handed to onReceive live behind the `ring` accessor -- rxT / rxS / set_rx / add_received --,
+    // i.e. in memory, not in this struct: bands without receive mode hold no registers for them.  A MAC in
+    // receive mode is receiving at every event boundary: a delivery or a timeout ends the command and the
+    // device's receive loop re-issues it within the same instant.)
 
     // jammers
     RegArr<double, NJa> tJam;
@@ -291,7 +299,7 @@ struct Sim {
     int ntrace, traceCap;
 };
 
-enum : int { REC_TX = 1, REC_BER = 2, REC_DEC = 3, REC_RX = 4 };
+enum : int { REC_TX = 1, REC_BER = 2, REC_DEC = 3, REC_RX = 4, REC_MRX = 5 };
 
 template <int D, int NS, int NJ, class ST>
 GW_HD void trace_rec(Sim<D, NS, NJ, ST> &s, int kind, double t, int dev, double x0, double x1, double x2, double x3)
@@ -337,6 +345,19 @@ GW_HD void init_sim(Sim<D, NS, NJ, ST> &s, double thermal)
     s.rv0 = s.rv1 = 0; s.latestDiff = 0; s.lastAbsDiff = 0; s.done = 0;
     s.nTx = 0;
     s.trace = nullptr; s.ntrace = 0; s.traceCap = 0;
+}
+
+// `device.receiving = True` after construction (devices.py:77-84), senders in index order: each starts its receive
+// loop as a process (Initialize, t = 0); the loop's first pass issues the RECEIVE command like every later one,
+// so it is modelled as a time-out slot at t = 0 (EV_RXTO)
+template <int D, int NS, int NJ, class ST, class Ring>
+GW_HD void init_receive(Sim<D, NS, NJ, ST> &s, const BandParams &B, Ring &ring)
+{
+    GW_UNROLL
+    for (int k = 0; k < NS; ++k) {
+        if (B.recv[k]) ring.set_rx(k, 0.0, s.seq++);
+        else ring.set_rx(k, (double)INFINITY, 0u);
+    }
 }
 
 GW_HD bool seq_before(uint32_t a, uint32_t b) { return (int32_t)(a - b) < 0; }
@@ -405,8 +426,8 @@ GW_HD bool before(double ta, uint32_t qa, double tb, uint32_t qb)
     return ta < tb || (ta == tb && seq_before(qa, qb));
 }
 
-template <int D, int NS, int NJ, class ST>
-GW_HD Event select_nontick(const Sim<D, NS, NJ, ST> &s)
+template <int D, int NS, int NJ, class ST, class Ring>
+GW_HD Event select_nontick(const Sim<D, NS, NJ, ST> &s, const BandParams &B, const Ring &ring)
 {
     Event e;
     e.kind = EV_NONE; e.idx = 0; e.t = INFINITY; e.seq = 0;
@@ -427,6 +448,9 @@ GW_HD Event select_nontick(const Sim<D, NS, NJ, ST> &s)
     for (int k = 0; k < NS; ++k)
         if (s.wPend[k]) GW_CONSIDER(s.stopW[k], s.sW[k], EV_W, k);
     if (s.rrmPend) GW_CONSIDER(s.tRrm, s.sRrm, EV_RRM, 0);
+    GW_UNROLL
+    for (int k = 0; k < NS; ++k)
+        if (B.recv[k]) GW_CONSIDER(ring.rxT(k), ring.rxS(k), EV_RXTO, k);
 #undef GW_CONSIDER
     return e;
 }
@@ -501,15 +525,16 @@ GW_HD void silent_ticks_both(Sim<D, NS, NJ, ST> &s, const BandParams &B, double 
     silent_ticks<1>(s, B.mult[1], B.interval[1], tEnd, qEnd, haveEnd, tLimit);
 }
 
-template <bool ALL_TICKS = false, int D, int NS, int NJ, class ST>
-GW_HD Event next_event(Sim<D, NS, NJ, ST> &s, const BandParams &B, double tLimit)
+template <bool ALL_TICKS = false, int D, int NS, int NJ, class ST, class Ring>
+GW_HD Event next_event(Sim<D, NS, NJ, ST> &s, const BandParams &B, double tLimit, const Ring &ring)
 {
     static_assert(NS == 2, "the tick logic is written for two senders per band");
-    Event ev = select_nontick(s);
+    Event ev = select_nontick(s, B, ring);
     // ticks that must go through the transition function: every tick of a plant env, otherwise
     // the ticks of a sender whose MAC waits for a packet
-    const bool wake0 = ALL_TICKS || s.mac[0] == MAC_WAIT_COND;
-    const bool wake1 = ALL_TICKS || s.mac[1] == MAC_WAIT_COND;
+    // (finite traffic bursts: every tick goes through the transition function, which ends the process)
+    const bool wake0 = ALL_TICKS || B.maxTicks[0] != 0 || s.mac[0] == MAC_WAIT_COND;
+    const bool wake1 = ALL_TICKS || B.maxTicks[kMaxSend - 1] != 0 || s.mac[1] == MAC_WAIT_COND;
     if (wake0 && (ev.kind == EV_NONE || before(s.tTick[0], s.sTick[0], ev.t, ev.seq))) {
         ev.kind = EV_TICK; ev.idx = 0; ev.t = s.tTick[0]; ev.seq = s.sTick[0];
     }
@@ -815,6 +840,13 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
         const int k = ev.idx;
         const int mult = k == 0 ? B.mult[0] : B.mult[kMaxSend - 1];
         const double interval = k == 0 ? B.interval[0] : B.interval[kMaxSend - 1];
+        const int maxTicks = k == 0 ? B.maxTicks[0] : B.maxTicks[kMaxSend - 1];
+        if (maxTicks != 0 && get_at(s.ticks, k) >= (uint64_t)maxTicks) {
+            // the burst is over: this wake-up only ends the traffic process (its process event takes a number)
+            set_at(s.tTick, k, (double)INFINITY);
+            s.seq++;
+            break;
+        }
         const int n = get_at(s.qn, k) + mult;
         set_at(s.qn, k, n > kQueueCap ? kQueueCap : n);             // drop-oldest
         set_at(s.ticks, k, get_at(s.ticks, k) + 1);
@@ -945,18 +977,21 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
                 }
             }
             // 3. receivers that passed the header decide on the payload and deliver
-            int window = -1, wake = 0;
+            int window = -1, wake = 0, received = 0;
             GW_UNROLL
             for (int p = 0; p < D; ++p) {
                 if (s.rxOf[p] != d || s.rxSec[p] != 1) continue;
                 if (decide_rec(s, P, p, 1, payBits)) {
                     if (Plant::active && d != RRM) plant.delivered(d, p, get_at(s.txVal, d), s.now);
                     if (p < NS) {
-                        // SimpleMac.phyInHandler (blocking, not queued): only an announcement
-                        // addressed to an idle MAC has an effect (simple_stack.py:386-448)
+                        // SimpleMac.phyInHandler (blocking, not queued): an announcement addressed to an idle
+                        // MAC opens its window (simple_stack.py:386-434); a data packet addressed to an idle MAC
+                        // in receive mode goes to the network layer (:436-444)
+                        const bool idle = get_at(s.mac, p) == MAC_NONE;
                         if (d == RRM && s.annDest == p) {
-                            const bool idle = get_at(s.mac, p) == MAC_NONE;
                             if (idle) window = p;
+                        } else if (d < NS && idle && (p == 0 ? B.recv[0] : B.recv[kMaxSend - 1])) {
+                            received |= 1 << p;         // the two senders of a band address each other
                         }
                     } else if (p == RRM) {
                         // SimpleRrmMac.phyInHandler -> interpreter.onPacketReceived
@@ -1005,7 +1040,22 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
             // d. _nReceivingFinished.event of the receivers that finished
             GW_UNROLL
             for (int p = 0; p < D; ++p) if ((wake >> p) & 1) begin_slot_wait(s, p);
+            // e. RECEIVE.eProcessed: the device's receive loop hands the packet to onReceive and issues the
+            // next RECEIVE command with a fresh timeout (devices.py:88-95, simple_stack.py:452-460)
+            GW_UNROLL
+            for (int k = 0; k < NS; ++k) {
+                if (!((received >> k) & 1)) continue;
+                ring.add_received(k);
+                trace_rec(s, REC_MRX, s.now, k, 0.0, 0.0, 0.0, 0.0);
+                ring.set_rx(k, s.now + kReceiveTimeout, s.seq++);
+            }
         }
+        break;
+    }
+    case EV_RXTO: {
+        // the current RECEIVE command timed out (or the receive loop starts): setProcessed() without a result,
+        // the loop issues the next command (simple_stack.py:473-478, devices.py:88-93)
+        ring.set_rx(ev.idx, s.now + kReceiveTimeout, s.seq++);
         break;
     }
     case EV_W: {
@@ -1407,7 +1457,7 @@ GW_HD void run_until_assign_plant(Sim<D, NS, NJ, ST> &s, const Params &P, const 
                                   const Ring &ring, const Masks &masks, const Memo &memo, Plant &plant)
 {
     while (!s.assignDone && !s.fault) {
-        const Event ev = next_event<true>(s, B, INFINITY);
+        const Event ev = next_event<true>(s, B, INFINITY, ring);
         process_event<MODE>(s, P, B, ev, srx, ring, masks, memo, plant);
     }
 }
@@ -1446,7 +1496,7 @@ GW_HD void run_until_assign(Sim<D, NS, NJ, ST> &s, const Params &P, const BandPa
             silent_ticks_both(s, B, ev.t, ev.seq, true, INFINITY);
         } else {
             if (macros && quiet_tail(s, B)) break;
-            ev = next_event(s, B, INFINITY);
+            ev = next_event(s, B, INFINITY, ring);
         }
         if (macros && ev.kind == EV_PHY && isolated_tx(s, P, B, ev, srx, ring, memo, INFINITY, idleStart)) continue;
         process_event<MODE>(s, P, B, ev, srx, ring, masks, memo);
@@ -1460,7 +1510,7 @@ GW_HD void run_until_time(Sim<D, NS, NJ, ST> &s, const Params &P, const BandPara
                           const Ring &ring, const Masks &masks, double T, const Memo &memo = Memo())
 {
     while (!s.fault) {
-        const Event ev = next_event(s, B, T);
+        const Event ev = next_event(s, B, T, ring);
         if (!(ev.t < T)) break;
         if (macros_enabled<MODE, NJ>(P) && ev.kind == EV_PHY && isolated_tx(s, P, B, ev, srx, ring, memo, T)) continue;
         process_event<MODE>(s, P, B, ev, srx, ring, masks, memo);

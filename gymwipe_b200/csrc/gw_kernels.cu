@@ -64,7 +64,7 @@ static int fail(int code, const char *fmt, ...)
 // ------------------------------------------------------------------------------------
 
 enum : int {
-    H_P01 = 0, H_P23, H_TICK, H_TICKS, H_U0, H_U1, H_U2, H_JAM, H_EP, H_EPC, HOT_CHUNKS
+    H_P01 = 0, H_P23, H_TICK, H_TICKS, H_U0, H_U1, H_U2, H_JAM, H_EP, H_EPC, H_RCV0, H_RCV1, HOT_CHUNKS
 };
 // cold: per device 5 chunks, then per sender 1
 enum : int { C_EV = 0, C_TX, C_RX, C_RT, C_U, C_V, C_PER_DEV };
@@ -437,6 +437,20 @@ struct DevRing {
     }
     template <class S> __device__ __forceinline__ unsigned long long epochK(const S &, int k) const { return ep(k) & ~(1ull << 63); }
     template <class S> __device__ __forceinline__ int epochC(const S &, int k) const { return (int)(ep(k) >> 63); }
+    // MAC receive mode: chunk H_RCV0 = {time-out of sender 0's RECEIVE command, of sender 1's}, chunk H_RCV1 =
+    // {their creation numbers, packets handed to onReceive per sender}; touched only by bands in receive mode
+    __device__ __forceinline__ double rxT(int k) const { return reinterpret_cast<const double *>(hot + (long long)H_RCV0 * nsim)[k]; }
+    __device__ __forceinline__ uint32_t rxS(int k) const { return reinterpret_cast<const uint32_t *>(hot + (long long)H_RCV1 * nsim)[k]; }
+    __device__ __forceinline__ void set_rx(int k, double t, uint32_t q) const
+    {
+        const_cast<double *>(reinterpret_cast<const double *>(hot + (long long)H_RCV0 * nsim))[k] = t;
+        const_cast<uint32_t *>(reinterpret_cast<const uint32_t *>(hot + (long long)H_RCV1 * nsim))[k] = q;
+    }
+    __device__ __forceinline__ void add_received(int k) const
+    {
+        const_cast<uint32_t *>(reinterpret_cast<const uint32_t *>(hot + (long long)H_RCV1 * nsim))[2 + k] += 1u;
+    }
+    __device__ __forceinline__ uint32_t received(int k) const { return reinterpret_cast<const uint32_t *>(hot + (long long)H_RCV1 * nsim)[2 + k]; }
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns()
@@ -849,7 +863,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
                         need = 0;
                         if (!nd) {
                             if (phase == 0 && s.assignDone) break;
-                            ev = next_event(s, B, phase == 0 ? (double)INFINITY : Tend);
+                            ev = next_event(s, B, phase == 0 ? (double)INFINITY : Tend, ring);
                             if (phase == 1 && !(ev.t < Tend)) break;
                             nd = fed_decide_set(s, ev);
                             if (nd) {
@@ -981,7 +995,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
                 if (run) {
                     if (phase == 0) run = !s.assignDone;
                     if (run || phase == 1) {
-                        ev = next_event(s, B, phase == 0 ? (double)INFINITY : Tend);
+                        ev = next_event(s, B, phase == 0 ? (double)INFINITY : Tend, ring);
                         run = phase == 0 ? true : (ev.t < Tend);
                     }
                 }
@@ -1253,7 +1267,7 @@ __global__ void plant_read_kernel(StatePtrs st, double *out)
 // ------------------------------------------------------------------------------------
 
 template <int D, int NS, int NJ>
-__global__ void init_kernel(StatePtrs st, SharedTables thermal /* srx[b][0] = thermal noise */)
+__global__ void init_kernel(StatePtrs st, Params P, SharedTables thermal /* srx[b][0] = thermal noise */)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= st.nsim) return;
@@ -1265,6 +1279,8 @@ __global__ void init_kernel(StatePtrs st, SharedTables thermal /* srx[b][0] = th
     const long long n = st.nsim;
     for (int c = 0; c < COLD_CHUNKS; ++c) st_chunk(st.cold, n, c, i, make_uint4(0, 0, 0, 0));
     for (int c = 0; c < HOT_CHUNKS; ++c) st_chunk(st.hot, n, c, i, make_uint4(0, 0, 0, 0));
+    DevRing ring{st.ring + i, st.nsim, st.hot + i};
+    init_receive(s, P.band[band], ring);            // the receive loops' first time-outs take creation numbers
     store_sim(s, st, i, true);
 }
 
@@ -1404,6 +1420,11 @@ __global__ void read_kernel(StatePtrs st, Params P, int field, double *out)
         break;
     case GW_FIELD_FAULT: out[i] = s.fault; break;
     case GW_FIELD_TIES: out[i] = s.ties; break;
+    case GW_FIELD_N_RECEIVED: {
+        DevRing ring{st.ring + i, st.nsim, st.hot + i};
+        for (int k = 0; k < NS; ++k) out[k * n + i] = ring.received(k);
+        break;
+    }
     case GW_FIELD_TX_SEQ: for (int d = 0; d < kMaxDev; ++d) out[d * n + i] = d < D ? s.txSeq[d < D ? d : 0] : 0.0; break;
     default: break;
     }
@@ -1704,6 +1725,7 @@ __global__ void grid_read_kernel(GridArgs A, GridParams G, int field, double *ou
     const GridView v = grid_view(A.state + (size_t)i * A.block_bytes, G.ndev);
     const long long n = A.n_envs;
     if (field == GW_GRID_FIELD_NOW) { out[i] = v.h->now; return; }
+    if (field == GW_GRID_FIELD_FAULT) { out[i] = v.h->fault; return; }
     for (int d = 0; d < G.ndev; ++d) {
         const GridDev &D = v.dev[d];
         if (field == GW_GRID_FIELD_STATS) {
@@ -1746,6 +1768,8 @@ double gw_max_correctable_ber(int k, int n)        // Mcs.maxCorrectableBer, phy
     return (double)t / n;
 }
 
+static_assert(sizeof(gw_config) <= 2048, "INTEGRATION.md tells binders to reserve 2048 bytes for gw_config");
+
 static int validate(const gw_config *cfg, int &D, int &NS, int &NJ)
 {
     if (!cfg) return fail(GW_E_INVALID, "cfg is NULL");
@@ -1774,6 +1798,9 @@ static int validate(const gw_config *cfg, int &D, int &NS, int &NJ)
             if (B.device[k].multiplicity < 1 || B.device[k].multiplicity > 16) return fail(GW_E_INVALID, "multiplicity out of range");
             if (!(B.device[k].interval > 0)) return fail(GW_E_INVALID, "interval must be > 0");
             if (B.device[k].payload_bytes > 60000) return fail(GW_E_INVALID, "payload_bytes too large");
+            if (B.device[k].max_ticks < 0) return fail(GW_E_INVALID, "max_ticks must be >= 0");
+            if ((B.device[k].max_ticks != 0 || B.device[k].receive) && cfg->plant != GW_PLANT_NONE)
+                return fail(GW_E_INVALID, "plant envs define their own traffic and reception");
         }
         for (int d = ns + 1; d < B.n_devices; ++d) {
             if (!(B.device[d].jam_interval > 0) || B.device[d].jam_delay < 0) return fail(GW_E_INVALID, "bad jammer timing");
@@ -1809,6 +1836,7 @@ static void fill_params(const gw_config &cfg, Params &P)
     // GYMWIPE_B200_NO_MACRO=1: every timed event through the generic transition function (A/B tests)
     finish_params(P);
     P.noMacro = std::getenv("GYMWIPE_B200_NO_MACRO") ? std::atoi(std::getenv("GYMWIPE_B200_NO_MACRO")) : 0;
+    if (P.noMacro < 0) P.noMacro = 0;
     for (int b = 0; b < cfg.n_bands; ++b) {
         const gw_band_config &cb = cfg.band[b];
         BandParams &B = P.band[b];
@@ -1817,7 +1845,9 @@ static void fill_params(const gw_config &cfg, Params &P)
             const gw_device_config &dc = cb.device[d];
             if (dc.role == GW_ROLE_SENDER) {
                 B.mult[B.ns] = dc.multiplicity; B.payloadRule[B.ns] = dc.payload_bytes < 0 ? -1 : dc.payload_bytes;
-                B.interval[B.ns] = dc.interval; B.ns++;
+                B.interval[B.ns] = dc.interval; B.maxTicks[B.ns] = dc.max_ticks; B.recv[B.ns] = dc.receive ? 1 : 0;
+                if (dc.max_ticks != 0 || dc.receive) P.noMacro = 1;      // finite bursts / receive mode: generic path
+                B.ns++;
             } else if (dc.role == GW_ROLE_JAMMER) {
                 B.jamInterval[B.nj] = dc.jam_interval; B.jamDelay[B.nj] = dc.jam_delay;
                 B.jamHdr[B.nj] = dc.jam_header_bytes; B.jamPay[B.nj] = dc.jam_payload_bytes; B.nj++;
@@ -1990,7 +2020,7 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
     SharedTables th;
     std::memset(&th, 0, sizeof th);
     for (int b = 0; b < cfg->n_bands; ++b) th.srx[b][0] = h->thermal[b];
-#define CALL_INIT(DD, SS, JJ) init_kernel<DD, SS, JJ><<<grid_for(nsim, 128), 128, 0, s>>>(h->st, th)
+#define CALL_INIT(DD, SS, JJ) init_kernel<DD, SS, JJ><<<grid_for(nsim, 128), 128, 0, s>>>(h->st, h->P, th)
     DISPATCH_SHAPE(h, CALL_INIT);
 #undef CALL_INIT
     if (cfg->plant) pendulum_init_kernel<<<grid_for(nsim, 128), 128, 0, s>>>(h->st, h->pend);
@@ -2386,7 +2416,7 @@ int gw_share_stats(gw_handle *h, gw_handle *with)
 int gw_read_state(gw_handle *h, int field, double *out, void *stream)
 {
     if (!h || !out) return fail(GW_E_INVALID, "NULL argument");
-    if (field < GW_FIELD_NOW || field > GW_FIELD_PLANT) return fail(GW_E_INVALID, "unknown field %d", field);
+    if (field < GW_FIELD_NOW || field > GW_FIELD_N_RECEIVED) return fail(GW_E_INVALID, "unknown field %d", field);
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     const long long nsim = h->st.nsim;
@@ -2588,7 +2618,7 @@ int gw_grid_run_traced(gw_grid_handle *h, double duration, double *trace, int32_
 int gw_grid_read(gw_grid_handle *h, int field, double *out, void *stream)
 {
     if (!h || !out) return fail(GW_E_INVALID, "NULL argument");
-    if (field < GW_GRID_FIELD_NOW || field > GW_GRID_FIELD_RECEIVED_POWER) return fail(GW_E_INVALID, "unknown field %d", field);
+    if (field < GW_GRID_FIELD_NOW || field > GW_GRID_FIELD_FAULT) return fail(GW_E_INVALID, "unknown field %d", field);
     CUDA_TRY(cudaSetDevice(h->device));
     grid_read_kernel<<<grid_for(h->A.n_envs, 64), 64, 0, (cudaStream_t)stream>>>(h->A, h->G, field, out);
     CUDA_TRY(cudaGetLastError());

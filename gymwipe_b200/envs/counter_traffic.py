@@ -239,7 +239,8 @@ class CounterTrafficEnv(BaseEnv):
         rows = {N.GW_FIELD_NOW: None, N.GW_FIELD_RECEIVED_POWER: 4, N.GW_FIELD_NEXT_TICK: 2, N.GW_FIELD_COUNTER: 2,
                 N.GW_FIELD_QUEUE_LEN: 2, N.GW_FIELD_N_TRANSMISSIONS: 1, N.GW_FIELD_N_DELIVERED: 2,
                 N.GW_FIELD_RECEIVED_VALUES: 2, N.GW_FIELD_ATTENUATION_DB: 16, N.GW_FIELD_RX_POWER_MW: 16,
-                N.GW_FIELD_FAULT: 1, N.GW_FIELD_TIES: 1, N.GW_FIELD_TX_SEQ: 4, N.GW_FIELD_PLANT: 8}[field]
+                N.GW_FIELD_FAULT: 1, N.GW_FIELD_TIES: 1, N.GW_FIELD_TX_SEQ: 4, N.GW_FIELD_PLANT: 8,
+                N.GW_FIELD_N_RECEIVED: 2}[field]
         if rows is None:
             out = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
         else:
@@ -261,6 +262,11 @@ class CounterTrafficEnv(BaseEnv):
     def delivered(self):
         """Packets the RRM decoded per sender, int64 ``[n_sims, 2]``."""
         return self.read_state(N.GW_FIELD_N_DELIVERED).t().to(torch.int64)
+
+    def received(self):
+        """MAC receive mode (scenario key ``"receive": True`` of a sender = ``SimpleNetworkDevice.receiving = True``):
+        packets handed to ``onReceive`` per sender, int64 ``[n_sims, 2]``."""
+        return self.read_state(N.GW_FIELD_N_RECEIVED).t().to(torch.int64)
 
     def transmissions(self):
         return self.read_state(N.GW_FIELD_N_TRANSMISSIONS)[0].to(torch.int64)
@@ -437,6 +443,8 @@ class CounterTrafficEnv(BaseEnv):
                     out.append(("dec", float(r[1]), band, int(r[2]), int(r[3]), float(r[4]), float(r[5]), bool(r[6])))
                 elif k == 4:
                     out.append(("rx", float(r[1]), band, int(r[2])))
+                elif k == 5:
+                    out.append(("mrx", float(r[1]), band, int(r[2])))
             records.append(out)
         return obs, reward, done.bool(), records
 

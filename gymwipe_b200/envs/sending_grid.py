@@ -159,5 +159,10 @@ class SendingDeviceGrid:
         """Current device positions ``[2, n_devices, num_envs]``."""
         return self._read(N.GW_GRID_FIELD_POSITIONS, (2, self.n_devices, self.num_envs))
 
+    def faults(self):
+        """int64 ``[num_envs]``: 0, or the condition under which the reference raises for that grid (3: the
+        reference's ``assert noisePower >= 0``; 2: ``KeyError``, SURVEY app. B #12); a faulted grid stops simulating."""
+        return self._read(N.GW_GRID_FIELD_FAULT, (self.num_envs,)).to(torch.int64)
+
     def received_power(self):
         return self._read(N.GW_GRID_FIELD_RECEIVED_POWER, (self.n_devices, self.num_envs))

@@ -56,6 +56,8 @@ def config_from_dict(d, n_envs, mode="reference", seed=0, env_id_offset=0, per_e
                 p = x.get("payload", "counter")
                 dc.payload_bytes = -1 if p == "counter" else int(p)
                 dc.interval = float(x.get("interval", 0.001))
+                dc.max_ticks = int(x.get("max_ticks", 0))
+                dc.receive = 1 if x.get("receive") else 0
                 if "dest" in x and int(x["dest"]) != 1 - i:
                     raise ValueError("the two senders of a band address each other")
             elif x["role"] == "jammer":

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GW_ABI_VERSION 1
+#define GW_ABI_VERSION 2
 
 #define GW_MAX_BANDS 4
 #define GW_MAX_DEVICES 4            /* per frequency band */
@@ -62,6 +62,11 @@ typedef struct {
     int32_t multiplicity;           /* packets per tick, counter_traffic.py:44 */
     int32_t payload_bytes;          /* -1: byteSize = counter (reference behaviour, app. B #1); >=0 fixed */
     double interval;                /* COUNTER_INTERVAL, counter_traffic.py:31 */
+    int32_t max_ticks;              /* 0: the traffic process runs forever (reference); n: a burst of n ticks (finite
+                                       sources as in tests/networking/test_stack.py:186-191) */
+    int32_t receive;                /* 1: MAC receive mode -- SimpleNetworkDevice.receiving = True (devices.py:70-97):
+                                       the device loops RECEIVE commands (RECEIVE_TIMEOUT 100 s), data packets addressed
+                                       to its idle MAC are handed to onReceive (simple_stack.py:436-460); GW_FIELD_N_RECEIVED */
     /* GW_ROLE_JAMMER */
     double jam_interval, jam_delay, jam_power_dbm;
     int32_t jam_header_bytes, jam_payload_bytes;
@@ -165,7 +170,8 @@ int gw_step(gw_handle *h, const int32_t *device, const int32_t *duration,
  *   kind 2 SimplePhy._updateBitErrorRate (simple_stack.py:161-173): device = receiver, x0 = BER
  *   kind 3 SimplePhy._decide (simple_stack.py:269-286): device = receiver, x0 = section (0 header,
  *          1 payload), x1 = bit error sum, x2 = total bits, x3 = verdict
- *   kind 4 interpreter.onPacketReceived (devices.py:163-168): device = sender index */
+ *   kind 4 interpreter.onPacketReceived (devices.py:163-168): device = sender index
+ *   kind 5 SimpleNetworkDevice.onReceive (devices.py:88-97, MAC receive mode): device = receiving device */
 int gw_step_traced(gw_handle *h, const int32_t *device, const int32_t *duration,
                    int64_t *obs, double *reward, uint8_t *done,
                    double *trace, int32_t *trace_count, int32_t cap, void *stream);
@@ -267,6 +273,7 @@ int gw_share_stats(gw_handle *h, gw_handle *with);
                                        per-env positions -- the only users; 0 in mode R with one shared geometry) */
 #define GW_FIELD_PLANT 13           /* [8][n_sims] x, v, theta, omega, motor target velocity, plant time,
                                        controller's angle estimate (deg), PID memory (plant envs) */
+#define GW_FIELD_N_RECEIVED 14      /* [GW_MAX_SENDERS][n_sims] packets handed to onReceive (MAC receive mode) */
 int gw_read_state(gw_handle *h, int field, double *out, void *stream);
 
 /* Mode M, fed masks: `mask_words` is a device uint32 buffer laid out
@@ -325,6 +332,10 @@ int gw_grid_run_traced(gw_grid_handle *h, double duration, double *trace, int32_
                                            payloads decoded / failed (as a receiver); BER evaluations */
 #define GW_GRID_FIELD_POSITIONS 2       /* [2][n_devices][n_envs] */
 #define GW_GRID_FIELD_RECEIVED_POWER 3  /* [n_devices][n_envs] SimplePhy._receivedPower (mW) */
+#define GW_GRID_FIELD_FAULT 4           /* [n_envs] 0, or the condition under which the reference raises (3: `assert
+                                           noisePower >= 0`, simple_stack.py:168-169 -- the incrementally kept power
+                                           sum of a PHY can round below the signal power; 2: KeyError, app. B #12);
+                                           a faulted env stops simulating */
 int gw_grid_read(gw_grid_handle *h, int field, double *out, void *stream);
 /* Synchronises; GW_E_SIMFAULT if an env hit a condition under which the reference raises. */
 int gw_grid_check(gw_grid_handle *h, void *stream);

@@ -29,7 +29,7 @@ import ref_harness as H  # noqa: E402
 
 
 def canonical(records):
-    glob = [r for r in records if r[0] in ("tx", "rx")]
+    glob = [r for r in records if r[0] in ("tx", "rx", "mrx")]
     per = {}
     for r in records:
         if r[0] in ("ber", "dec"):

@@ -40,6 +40,8 @@ CASES = {
     "mobility_quirks_seed4": ("mobilityquirks", 4, 70),
     "modeM_jammer_seed11": ("maskjammer", 11, 40),
     "modeM_default_seed12": ("maskdefault", 12, 60),
+    "mac_receive_kat": ("mackat", 0, 10),
+    "receive_bursts_seed21": ("receive", 21, 60),
 }
 
 MASK_SEED, MASK_ENV = 20261018, 4242
@@ -79,6 +81,20 @@ def make_case(kind, seed, steps):
         sc, tape = CR.random_scenario(rs, jammers=1, spread=2.5), H.random_actions(steps, seed=seed + 6000)
     elif kind == "maskdefault":
         sc, tape = H.default_scenario(), H.random_actions(steps, seed=seed + 5000)
+    elif kind == "mackat":
+        # the reference's MAC known-answer test (tests/networking/test_stack.py:134-235) through the env API: devices at
+        # (0,0) / (1,1), RRM at (2,2); each sender hands 10 packets to its MAC, one every 1e-4 s (1- / 2-byte payloads),
+        # both MACs in receive mode, ten 10 ms assignments alternately: onReceive counts 4/4/8/8/10/10
+        sc = {"assignment_duration_factor": 1000, "bands": [{"frequency": 2.4e9, "bandwidth": 22e6, "devices": [
+            {"role": "sender", "x": 0.0, "y": 0.0, "mult": 1, "payload": 1, "interval": 1e-4, "dest": 1, "max_ticks": 10, "receive": True},
+            {"role": "sender", "x": 1.0, "y": 1.0, "mult": 1, "payload": 2, "interval": 1e-4, "dest": 0, "max_ticks": 10, "receive": True},
+            {"role": "rrm", "x": 2.0, "y": 2.0}]}]}
+        tape, do_reset = [{"device": t % 2, "duration": 10} for t in range(steps)], False
+    elif kind == "receive":
+        sc, tape = CR.random_scenario(rs, jammers=1, spread=2.0), H.random_actions(steps, seed=seed + 7000)
+        sc["bands"][0]["devices"][0]["receive"] = True
+        sc["bands"][0]["devices"][1]["receive"] = True
+        sc["bands"][0]["devices"][1]["max_ticks"] = 45
     else:
         raise SystemExit(kind)
     return sc, tape, do_reset, use_default

@@ -91,8 +91,13 @@ enum {
     K_RRM_ANN_END,    /* _sendAnnouncement process event -> executeNext */
     K_STOP,           /* env.run(until=number): StopSimulation event, URGENT (simpy core.py run()) */
     K_MOVE_INIT,      /* Initialize of a mobility process (tests/test_benchmark.py:73-85) */
-    K_MOVE            /* its timeout: Position.set, then the next timeout */
+    K_MOVE,           /* its timeout: Position.set, then the next timeout */
+    K_RECV_INIT,      /* Initialize of SimpleNetworkDevice._receiver (devices.py:88-97) */
+    K_RECV_TIMEOUT,   /* SimpleMac._receiveTimeout (simple_stack.py:458-459, 473-478) */
+    K_RECV_DONE       /* RECEIVE message eProcessed: the receiver loop resumes */
 };
+
+#define RECEIVE_TIMEOUT 100.0       /* SimpleNetworkDevice.RECEIVE_TIMEOUT, devices.py:66 */
 
 enum { MAC_NONE = 0, MAC_WAIT_COND, MAC_WAIT_TX, MAC_IDLE };
 enum { PKT_ANNOUNCE = 1, PKT_DATA, PKT_JAM };
@@ -171,6 +176,11 @@ typedef struct {
     /* traffic */
     int counter;
     int jam_stage;
+    /* finite traffic bursts and MAC receive mode */
+    int max_ticks, ticks_done;
+    int recv_mode, mac_receiving;
+    uint32_t recv_gen;
+    int64_t n_received;
     /* mobility process (gwo_add_mover) */
     double mv_x0, mv_y0, mv_first, mv_interval;
     const double *mv_offsets;
@@ -738,7 +748,12 @@ static void on_mac_rx_init(gwo_sim *s, int b, int d)   /* simple_stack.py:386-44
         schedule(s, K_W, PRIO_NORMAL, timeTotal, b, d, 0);
         mac_loop(s, b, d, 0);
     } else {
-        /* not for us / not from the RRM and not in receive mode: ignored */
+        /* a packet from another device, addressed to us (simple_stack.py:436-444): in receive mode its payload goes
+         * to the network layer -- setProcessed(payload), _stopReceiving(); otherwise ignored */
+        if (p->type == PKT_DATA && p->dst == d && D->mac_receiving) {
+            D->mac_receiving = 0;
+            schedule(s, K_RECV_DONE, PRIO_NORMAL, 0, b, d, 1);
+        }
         mac_end(s, b, d);
     }
 }
@@ -765,13 +780,46 @@ static void rrm_assign(gwo_sim *s, int b, int dev, double slots, int nbytes)
     }
 }
 
+/* one pass of `while self._receiving:` in SimpleNetworkDevice._receiver (devices.py:88-93): a RECEIVE message goes
+ * to the MAC's networkIn gate (callback): _receiving = True and a fresh timeout (simple_stack.py:452-460) */
+static void receiver_issue(gwo_sim *s, int b, int d)
+{
+    Dev *D = &s->band[b].dev[d];
+    D->mac_receiving = 1;
+    D->recv_gen++;
+    schedule(s, K_RECV_TIMEOUT, PRIO_NORMAL, RECEIVE_TIMEOUT, b, d, (int)D->recv_gen);
+}
+
 static void dispatch(gwo_sim *s, Ev e)
 {
     int b = e.band;
     Band *B = &s->band[b];
     switch (e.kind) {
+    case K_RECV_INIT:
+        receiver_issue(s, b, e.a);
+        break;
+    case K_RECV_TIMEOUT: {
+        /* _receiveTimeoutCallback: only the CURRENT receive command's timeout has an effect */
+        Dev *D = &B->dev[e.a];
+        if (D->mac_receiving && (uint32_t)e.b == D->recv_gen) {
+            D->mac_receiving = 0;                                 /* setProcessed() without a result, _stopReceiving() */
+            schedule(s, K_RECV_DONE, PRIO_NORMAL, 0, b, e.a, 0);
+        }
+        break;
+    }
+    case K_RECV_DONE: {
+        Dev *D = &B->dev[e.a];
+        if (e.b) {                                                /* `if result: self.onReceive(result)` */
+            D->n_received++;
+            rec_push(s, GWO_REC_MRX, s->now, b, e.a, 0, 0, 0, 0);
+        }
+        receiver_issue(s, b, e.a);                                /* the device-level flag stays set: next RECEIVE */
+        break;
+    }
     case K_TICK: {
         Dev *D = &B->dev[e.a];
+        if (D->max_ticks > 0 && D->ticks_done >= D->max_ticks) { schedule_unobserved(s); break; }   /* the process ends */
+        D->ticks_done++;
         for (int i = 0; i < D->mult; i++) {
             int bytes = D->payload_rule < 0 ? D->counter : D->payload_rule;
             mac_enqueue(s, b, e.a, bytes);
@@ -1029,6 +1077,7 @@ gwo_sim *gwo_create(const gwo_scenario *sc)
             D->interval = ds->interval;
             D->jam_interval = ds->jam_interval; D->jam_delay = ds->jam_delay;
             D->jam_power = ds->jam_power; D->jam_hdr = ds->jam_hdr; D->jam_payload = ds->jam_payload;
+            D->max_ticks = ds->max_ticks; D->recv_mode = ds->receive;
             D->P = B->thermal;
             D->counter = 1;                        /* counter_traffic.py:48 */
             D->cur_tx = -1;
@@ -1049,6 +1098,13 @@ gwo_sim *gwo_create(const gwo_scenario *sc)
         for (int d = 0; d < B->ndev; d++)
             if (B->dev[d].role == GWO_ROLE_JAMMER)
                 schedule(s, K_JAM_WAKE, PRIO_URGENT, 0, b, d, 0);
+    }
+    /* receive mode is switched on after construction, band by band in device order (the harness does the same) */
+    for (int b = 0; b < sc->nbands; b++) {
+        Band *B = &s->band[b];
+        for (int d = 0; d < B->ndev; d++)
+            if (B->dev[d].role == GWO_ROLE_SENDER && B->dev[d].recv_mode)
+                schedule(s, K_RECV_INIT, PRIO_URGENT, 0, b, d, 0);
     }
     return s;
 }
@@ -1250,6 +1306,11 @@ void gwo_counts(const gwo_sim *s, int band, int64_t *n_tx, int64_t *n_deliv /* [
     const Band *B = &s->band[band];
     *n_tx = B->n_tx;
     for (int d = 0; d < GWO_MAXDEV; d++) n_deliv[d] = B->n_deliv[d];
+}
+
+void gwo_received(const gwo_sim *s, int band, int64_t *n_received)
+{
+    for (int d = 0; d < GWO_MAXDEV; d++) n_received[d] = s->band[band].dev[d].n_received;
 }
 
 double gwo_attenuation(const gwo_sim *s, int band, int i, int j) { return s->band[band].att[i][j]; }

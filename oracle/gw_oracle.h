@@ -28,6 +28,7 @@ extern "C" {
 #define GWO_REC_BER 2       /* t, dev=receiver, x0=BER */
 #define GWO_REC_DEC 3       /* t, dev=receiver, x0=section(0 header,1 payload), x1=errSum, x2=totalBits, x3=ok */
 #define GWO_REC_RX 4        /* t, dev=sender index of a packet the RRM decoded */
+#define GWO_REC_MRX 5       /* t, dev=device whose MAC handed a received packet to onReceive (receive mode) */
 
 #define GWO_FAULT_HEAP 1
 #define GWO_FAULT_REF_KEYERROR 2   /* the reference would raise KeyError */
@@ -45,6 +46,8 @@ typedef struct {
     int32_t payload_rule;   /* -1: byteSize = counter (reference), else fixed byteSize */
     int32_t dest;           /* destination device index */
     double interval;        /* COUNTER_INTERVAL */
+    int32_t max_ticks;      /* 0: the traffic process runs forever (reference); n: a burst of n ticks */
+    int32_t receive;        /* 1: MAC receive mode (SimpleNetworkDevice.receiving = True, devices.py:70-97) */
     /* jammer */
     double jam_interval, jam_delay, jam_power;
     int32_t jam_hdr, jam_payload;
@@ -94,6 +97,8 @@ int64_t gwo_popped(const gwo_sim *s);
 int gwo_fault(const gwo_sim *s);
 int64_t gwo_near_ties(const gwo_sim *s);
 void gwo_counts(const gwo_sim *s, int band, int64_t *n_tx, int64_t *n_deliv);
+/* packets handed to SimpleNetworkDevice.onReceive per device (receive mode) */
+void gwo_received(const gwo_sim *s, int band, int64_t *n_received /* [GWO_MAXDEV] */);
 double gwo_attenuation(const gwo_sim *s, int band, int i, int j);
 size_t gwo_trace_take(gwo_sim *s, double *out, size_t cap_doubles);
 size_t gwo_trace_size(const gwo_sim *s);

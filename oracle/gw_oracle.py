@@ -27,7 +27,7 @@ FAULTS = {1: "heap overflow", 2: "reference would raise KeyError", 3: "reference
 class DevSpec(C.Structure):
     _fields_ = [("role", C.c_int32), ("x", C.c_double), ("y", C.c_double),
                 ("mult", C.c_int32), ("payload_rule", C.c_int32), ("dest", C.c_int32),
-                ("interval", C.c_double),
+                ("interval", C.c_double), ("max_ticks", C.c_int32), ("receive", C.c_int32),
                 ("jam_interval", C.c_double), ("jam_delay", C.c_double), ("jam_power", C.c_double),
                 ("jam_hdr", C.c_int32), ("jam_payload", C.c_int32)]
 
@@ -87,6 +87,7 @@ def lib():
         L.gwo_near_ties.restype = C.c_int64
         L.gwo_near_ties.argtypes = [C.c_void_p]
         L.gwo_counts.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.gwo_received.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
         L.gwo_attenuation.restype = C.c_double
         L.gwo_attenuation.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.gwo_trace_take.restype = C.c_size_t
@@ -145,6 +146,8 @@ def scenario_from_dict(d, mode=MODE_R):
                 ds.payload_rule = -1 if p == "counter" else int(p)
                 ds.dest = int(x["dest"])
                 ds.interval = float(x.get("interval", 0.001))
+                ds.max_ticks = int(x.get("max_ticks", 0))
+                ds.receive = 1 if x.get("receive") else 0
             elif x["role"] == "jammer":
                 ds.jam_interval = float(x["interval"])
                 ds.jam_delay = float(x["delay"])
@@ -265,6 +268,12 @@ class Oracle:
         self.L.gwo_counts(self.h, band, C.byref(n_tx), nd)
         return int(n_tx.value), [int(x) for x in nd]
 
+    def received(self, band=0):
+        """Packets handed to ``onReceive`` per device (MAC receive mode)."""
+        nr = (C.c_int64 * MAXDEV)()
+        self.L.gwo_received(self.h, band, nr)
+        return [int(x) for x in nr]
+
     def attenuation(self, band, i, j):
         return float(self.L.gwo_attenuation(self.h, band, i, j))
 
@@ -285,6 +294,8 @@ class Oracle:
                             float(r[6]), bool(r[7])))
             elif k == REC_RX:
                 out.append(("rx", float(r[1]), int(r[2]), int(r[3])))
+            elif k == 5:
+                out.append(("mrx", float(r[1]), int(r[2]), int(r[3])))
         return out
 
 

@@ -301,18 +301,26 @@ class ScenarioEnv:
         class Sender(SimpleNetworkDevice):
             # mirrors CounterTrafficEnv.SenderDevice (counter_traffic.py:37-61) with
             # the interval / payload rule as parameters
-            def __init__(self, name, x, y, band, mult, payload, interval):
+            def __init__(self, name, x, y, band, mult, payload, interval, max_ticks=0):
                 super().__init__(name, x, y, band)
                 self.packetMultiplicity = mult
                 self.payloadRule = payload
                 self.interval = interval
+                self.maxTicks = max_ticks       # 0: forever (the reference's SenderDevice); n: a burst of n ticks
                 self.counter = 1
                 SimMan.process(self.senderProcess())
                 self.destinationMac = None
 
+            def onReceive(self, packet):        # devices.py:99-111: invoked by the receiver loop in receive mode
+                if outer.tracer is not None and outer.tracer.enabled:
+                    band, dev = outer.tracer.device_index[self]
+                    outer.tracer.records.append(("mrx", SimMan.now, band, dev))
+
             def senderProcess(self):
                 assert self.destinationMac is not None
-                while True:
+                ticks = 0
+                while self.maxTicks == 0 or ticks < self.maxTicks:
+                    ticks += 1
                     for _ in range(self.packetMultiplicity):
                         if self.payloadRule == "counter":
                             data = Transmittable(outer.COUNTER_BYTE_LENGTH, self.counter)
@@ -359,7 +367,7 @@ class ScenarioEnv:
             for i, d in enumerate(devs):
                 if d["role"] == "sender":
                     s = Sender("Sender %d.%d" % (b, i), d["x"], d["y"], band, d["mult"],
-                               d.get("payload", "counter"), d.get("interval", 0.001))
+                               d.get("payload", "counter"), d.get("interval", 0.001), int(d.get("max_ticks", 0)))
                     senders.append((i, s))
                     dest.append(d.get("dest"))
                     dev_objs[i] = s
@@ -402,6 +410,12 @@ class ScenarioEnv:
                 tracer.wrap_interpreter(interp, b)
             self.bands.append({"band": band, "senders": sender_objs, "rrm": rrm,
                                "devices": dev_objs, "interp": interp})
+        # MAC receive mode (devices.py:70-97): switched on after the whole scenario has been constructed, band by
+        # band in device order -- each starts its blocking receive loop as a process
+        for b, bspec in enumerate(scenario["bands"]):
+            for i, d in enumerate(bspec["devices"]):
+                if d["role"] == "sender" and d.get("receive"):
+                    self.bands[b]["devices"][i].receiving = True
 
     # gym-like API --------------------------------------------------------
     def reset(self):

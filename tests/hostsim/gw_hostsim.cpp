@@ -20,6 +20,12 @@ namespace {
 
 struct HostRing {
     int32_t *data;      // [NS][100]
+    // MAC receive mode: {time-out, creation number, packets handed to onReceive} per sender
+    double *rxt; uint32_t *rxs; uint32_t *rxn;
+    double rxT(int k) const { return rxt[k]; }
+    uint32_t rxS(int k) const { return rxs[k]; }
+    void set_rx(int k, double t, uint32_t q) const { rxt[k] = t; rxs[k] = q; }
+    void add_received(int k) const { rxn[k] += 1u; }
     int operator()(int k, uint32_t slot) const { return data[k * kRingSlots + slot]; }
     void operator()(int k, uint32_t slot, int v) { data[k * kRingSlots + slot] = v; }
     // counter epochs (the device reads them from global memory on demand)
@@ -70,6 +76,7 @@ struct HsBand {
     double x[kMaxDev], y[kMaxDev], power[kMaxDev];
     int32_t mult[kMaxSend], payloadRule[kMaxSend];
     double interval[kMaxSend];
+    int32_t maxTicks[kMaxSend], recv[kMaxSend];
     double jamInterval, jamDelay;
     int32_t jamHdr, jamPay;
 };
@@ -113,7 +120,11 @@ void fill_params(const HsScenario &sc, Params &P)
         BandParams &B = P.band[b];
         const HsBand &h = sc.band[b];
         B.ns = h.ns; B.nj = h.nj; B.ndev = h.ns + 1 + h.nj;
-        for (int k = 0; k < kMaxSend; ++k) { B.mult[k] = h.mult[k]; B.payloadRule[k] = h.payloadRule[k]; B.interval[k] = h.interval[k]; }
+        for (int k = 0; k < kMaxSend; ++k) {
+            B.mult[k] = h.mult[k]; B.payloadRule[k] = h.payloadRule[k]; B.interval[k] = h.interval[k];
+            B.maxTicks[k] = h.maxTicks[k]; B.recv[k] = h.recv[k];
+            if (h.maxTicks[k] != 0 || h.recv[k]) P.noMacro = 1;       // as gw_kernels.cu::fill_params
+        }
         B.jamInterval[0] = h.jamInterval; B.jamDelay[0] = h.jamDelay; B.jamHdr[0] = h.jamHdr; B.jamPay[0] = h.jamPay;
     }
 }
@@ -125,6 +136,8 @@ struct EnvT {
     double att[kMaxBands][D * D];
     double pos[kMaxBands][D * 2];
     int32_t ring[kMaxBands][NS * kRingSlots];
+    double rxt[kMaxBands][NS];
+    uint32_t rxs[kMaxBands][NS], rxn[kMaxBands][NS];
 };
 
 template <int MODE, int D, int NS, int NJ>
@@ -146,6 +159,7 @@ int run_t(const HsScenario &sc, int64_t nenv, int nsteps, int do_reset, const do
             const double npd = 1.38e-23 * (20.0 + 273.15);
             const double thermal = npd * h.bandwidth * 1000;
             init_sim(E.sim[b], thermal);
+            { HostRing r0{E.ring[b], E.rxt[b], E.rxs[b], E.rxn[b]}; init_receive(E.sim[b], P.band[b], r0); }
             double x[D], y[D];
             for (int d = 0; d < D; ++d) {
                 if (pos) { x[d] = pos[((e * nb + b) * kMaxDev + d) * 2]; y[d] = pos[((e * nb + b) * kMaxDev + d) * 2 + 1]; }
@@ -159,7 +173,7 @@ int run_t(const HsScenario &sc, int64_t nenv, int nsteps, int do_reset, const do
                 }
         }
         if (do_reset)
-            for (int b = 0; b < nb; ++b) { HostRing r{E.ring[b]}; reset_sim(E.sim[b], P.band[b], r); }
+            for (int b = 0; b < nb; ++b) { HostRing r{E.ring[b], E.rxt[b], E.rxs[b], E.rxn[b]}; reset_sim(E.sim[b], P.band[b], r); }
         for (int t = 0; t < nsteps; ++t) {
             const size_t base = ((size_t)t * nenv + e) * nb;
             double T = 0;
@@ -183,13 +197,13 @@ int run_t(const HsScenario &sc, int64_t nenv, int nsteps, int do_reset, const do
                 begin_assignment(E.sim[b], P, dev_tape[base + b], dur_tape[base + b]);
             }
             for (int b = 0; b < nb; ++b) {
-                HostRing r{E.ring[b]};
+                HostRing r{E.ring[b], E.rxt[b], E.rxs[b], E.rxn[b]};
                 auto mk = MasksFor<MODE>::make(sc.seed, env_offset + e, e, b, nb);
                 run_until_assign<MODE>(E.sim[b], P, P.band[b], E.srx[b], r, mk);
                 if (E.sim[b].now > T) T = E.sim[b].now;
             }
             for (int b = 0; b < nb; ++b) {
-                HostRing r{E.ring[b]};
+                HostRing r{E.ring[b], E.rxt[b], E.rxs[b], E.rxn[b]};
                 auto mk = MasksFor<MODE>::make(sc.seed, env_offset + e, e, b, nb);
                 if (E.sim[b].now < T) run_until_time<MODE>(E.sim[b], P, P.band[b], E.srx[b], r, mk, T);
                 long long o; double rw; unsigned char dn;
@@ -207,6 +221,7 @@ int run_t(const HsScenario &sc, int64_t nenv, int nsteps, int do_reset, const do
                 int64_t *c = counts + ((size_t)e * nb + b) * 9;
                 c[0] = E.sim[b].nTx;
                 for (int k = 0; k < NS; ++k) c[1 + k] = E.sim[b].nDeliv[k];
+                for (int k = 0; k < NS; ++k) c[3 + k] = E.rxn[b][k];      // packets handed to onReceive
                 c[8] = E.sim[b].ties;
             }
             if (power_out)

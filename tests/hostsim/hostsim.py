@@ -24,6 +24,7 @@ class HsBand(C.Structure):
                 ("x", C.c_double * MAXDEV), ("y", C.c_double * MAXDEV), ("power", C.c_double * MAXDEV),
                 ("mult", C.c_int32 * MAXSEND), ("payloadRule", C.c_int32 * MAXSEND),
                 ("interval", C.c_double * MAXSEND),
+                ("maxTicks", C.c_int32 * MAXSEND), ("recv", C.c_int32 * MAXSEND),
                 ("jamInterval", C.c_double), ("jamDelay", C.c_double),
                 ("jamHdr", C.c_int32), ("jamPay", C.c_int32)]
 
@@ -99,6 +100,8 @@ def scenario_from_dict(d, mode=0, seed=0):
                 p = x.get("payload", "counter")
                 hb.payloadRule[i] = -1 if p == "counter" else int(p)
                 hb.interval[i] = float(x.get("interval", 0.001))
+                hb.maxTicks[i] = int(x.get("max_ticks", 0))
+                hb.recv[i] = 1 if x.get("receive") else 0
                 assert int(x["dest"]) == 1 - i
             elif x["role"] == "jammer":
                 hb.jamInterval = float(x["interval"])

@@ -332,3 +332,62 @@ def test_core_mode_m_fed_moving_devices_vs_oracle(seed):
     assert [s["obs"] for s in res["steps"]] == list(h["obs"][:, 0, 0])
     assert [s["reward"] for s in res["steps"]] == list(h["reward"][:, 0, 0])
     assert [s["now"] for s in res["steps"]] == list(h["now"][:, 0])
+
+
+def mac_kat_scenario():
+    """The reference's MAC known-answer test (tests/networking/test_stack.py:134-235) through the env API: devices at
+    (0,0) and (1,1), the RRM at (2,2); each sender hands 10 packets to its MAC, one every 1e-4 s (payloads
+    Transmittable(i): 1 byte for i < 10, 2 bytes for 10..19), both MACs in receive mode; the RRM assigns the band
+    for 10 ms alternately."""
+    return {"assignment_duration_factor": 1000, "bands": [{"frequency": 2.4e9, "bandwidth": 22e6, "devices": [
+        {"role": "sender", "x": 0.0, "y": 0.0, "mult": 1, "payload": 1, "interval": 1e-4, "dest": 1, "max_ticks": 10, "receive": True},
+        {"role": "sender", "x": 1.0, "y": 1.0, "mult": 1, "payload": 2, "interval": 1e-4, "dest": 0, "max_ticks": 10, "receive": True},
+        {"role": "rrm", "x": 2.0, "y": 2.0}]}]}
+
+
+MAC_KAT_RECEIVED = [(0, 4), (4, 4), (4, 8), (8, 8), (8, 10), (10, 10), (10, 10), (10, 10), (10, 10), (10, 10)]
+
+
+def test_core_mac_receive_known_answers():
+    """`assert len(receivedPackets2) == 4 ... 4 ... 8 ... 8 ... 10 ... 10` (test_stack.py:218-235): packets handed to
+    onReceive after every assignment round, oracle and core."""
+    sc = mac_kat_scenario()
+    ora = O.Oracle(sc)
+    for t in range(10):
+        ora.step({"device": t % 2, "duration": 10})
+        assert tuple(ora.received()[:2]) == MAC_KAT_RECEIVED[t]
+    dev = np.array([[t % 2] for t in range(10)], np.int32)
+    dur = np.full((10, 1), 10, np.int32)
+    for t in range(1, 11):
+        h = HS.run(sc, dev[:t], dur[:t], do_reset=False)
+        assert h["rc"] == 0 and tuple(h["counts"][0, 0, 3:5]) == MAC_KAT_RECEIVED[t - 1]
+    assert h["now"][-1, 0] == ora.now
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_core_receive_mode_and_bursts_random_vs_oracle(seed):
+    """Random scenarios with MACs in receive mode and finite traffic bursts, with and without an interferer,
+    modes R and M: step results, clocks, transmissions, RRM deliveries and onReceive counts equal the oracle's."""
+    rs = np.random.RandomState(8800 + seed)
+    for jam in (0, 1):
+        sc = random_scenario(rs, jammers=jam, spread=2.0)
+        for k in range(2):
+            sc["bands"][0]["devices"][k]["receive"] = bool(rs.randint(2)) or k == seed % 2
+        if seed % 2:
+            sc["bands"][0]["devices"][int(rs.randint(2))]["max_ticks"] = int(rs.randint(5, 60))
+        nenv, nsteps = 6, 70
+        dev, dur = random_tapes(rs, nsteps, nenv, 1)
+        for mode, hs_mode in ((O.MODE_R, 0), (O.MODE_M, 1)):
+            o = O.run_batch(sc, dev, dur, mode=mode, seed=11, env_id_offset=3)
+            h = HS.run(sc, dev, dur, mode=hs_mode, seed=11, env_offset=3)
+            assert h["rc"] == 0
+            assert (o["obs"] == h["obs"]).all() and (o["reward"] == h["reward"]).all() and (o["now"] == h["now"]).all()
+            assert (o["counts"][:, :, :3] == h["counts"][:, :, :3]).all()
+            ora = O.Oracle(sc, mode=mode)
+            if mode == O.MODE_M:
+                ora.use_philox_masks(11, 3)
+            ora.reset()
+            for t in range(nsteps):
+                ora.step({"device": int(dev[t, 0, 0]), "duration": int(dur[t, 0, 0])})
+            assert tuple(ora.received()[:2]) == tuple(h["counts"][0, 0, 3:5])
+            assert sum(ora.received()[:2]) > 0

@@ -636,3 +636,48 @@ def test_send_queue_overflow_is_reported():
         for _ in range(400):
             env.step(a)
         env.check()
+
+
+def test_cuda_mac_receive_known_answers():
+    """The reference's MAC known-answer test (tests/networking/test_stack.py:218-235: 4 / 4 / 8 / 8 / 10 / 10 packets
+    received after successive assignment rounds) on the GPU, through the env API: both MACs in receive mode, two
+    finite 10-packet bursts, ten alternating 10 ms assignments."""
+    from test_core_host import MAC_KAT_RECEIVED, mac_kat_scenario
+    import gymwipe_b200
+    n = 64
+    env = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, scenario=mac_kat_scenario(), strict=False)
+    ora = O.Oracle(mac_kat_scenario())
+    for t in range(10):
+        env.step({"device": torch.full((n,), t % 2, dtype=torch.int32, device="cuda"),
+                  "duration": torch.full((n,), 10, dtype=torch.int32, device="cuda")})
+        ora.step({"device": t % 2, "duration": 10})
+        got = env.received().cpu().numpy()
+        assert (got == np.array(MAC_KAT_RECEIVED[t])).all()
+        assert (env.read_state(0).cpu().numpy() == ora.now).all()
+    env.check()
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_cuda_receive_mode_and_bursts_match_oracle(seed):
+    rs = np.random.RandomState(8900 + seed)
+    for jam in (0, 1):
+        sc = random_scenario(rs, jammers=jam, spread=2.0)
+        sc["bands"][0]["devices"][seed % 2]["receive"] = True
+        sc["bands"][0]["devices"][1 - seed % 2]["receive"] = bool(rs.randint(2))
+        sc["bands"][0]["devices"][int(rs.randint(2))]["max_ticks"] = int(rs.randint(5, 60))
+        nenv, nsteps = 128, 70
+        dev, dur = random_tapes(rs, nsteps, nenv, 1)
+        o = O.run_batch(sc, dev, dur)
+        import gymwipe_b200
+        env = gymwipe_b200.make('CounterTraffic-v0', num_envs=nenv, scenario=sc, strict=False)
+        env.reset()
+        for t in range(nsteps):
+            ob, rw, dn, _ = env.step({"device": torch.as_tensor(dev[t, :, 0]).cuda(), "duration": torch.as_tensor(dur[t, :, 0]).cuda()})
+            assert (ob.cpu().numpy() == o["obs"][t, :, 0]).all() and (rw.cpu().numpy() == o["reward"][t, :, 0]).all()
+        env.check()
+        assert (env.read_state(0).cpu().numpy() == o["now"][-1]).all()
+        ora = O.Oracle(sc)
+        ora.reset()
+        for t in range(nsteps):
+            ora.step({"device": int(dev[t, 0, 0]), "duration": int(dur[t, 0, 0])})
+        assert tuple(env.received()[0].tolist()) == tuple(ora.received()[:2])

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 GOLDEN_CASES = ["kat_reference_test", "default_reset_seed0", "default_noreset_seed1", "positions_seed3",
-                "jammer_seed5", "longpacket_seed7", "multiband_seed9"]
+                "jammer_seed5", "longpacket_seed7", "multiband_seed9", "mac_receive_kat", "receive_bursts_seed21"]
 
 
 GOLDEN_CASES_M = ["modeM_jammer_seed11", "modeM_default_seed12"]
@@ -26,7 +26,7 @@ def canonical(records):
     (band, device) subsequence and tx/rx records as one global subsequence.
     """
     records = [tuple(r) for r in records]
-    glob = [r for r in records if r[0] in ("tx", "rx")]
+    glob = [r for r in records if r[0] in ("tx", "rx", "mrx")]
     per = {}
     for r in records:
         if r[0] in ("ber", "dec"):
