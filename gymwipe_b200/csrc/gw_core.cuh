@@ -355,7 +355,7 @@ GW_HD void init_receive(Sim<D, NS, NJ, ST> &s, const BandParams &B, Ring &ring)
 {
     GW_UNROLL
     for (int k = 0; k < NS; ++k) {
-        if (B.recv[k]) ring.set_rx(k, 0.0, s.seq++);
+        if (Ring::ext && B.recv[k]) ring.set_rx(k, 0.0, s.seq++);
         else ring.set_rx(k, (double)INFINITY, 0u);
     }
 }
@@ -450,7 +450,7 @@ GW_HD Event select_nontick(const Sim<D, NS, NJ, ST> &s, const BandParams &B, con
     if (s.rrmPend) GW_CONSIDER(s.tRrm, s.sRrm, EV_RRM, 0);
     GW_UNROLL
     for (int k = 0; k < NS; ++k)
-        if (B.recv[k]) GW_CONSIDER(ring.rxT(k), ring.rxS(k), EV_RXTO, k);
+        if (Ring::ext && B.recv[k]) GW_CONSIDER(ring.rxT(k), ring.rxS(k), EV_RXTO, k);
 #undef GW_CONSIDER
     return e;
 }
@@ -533,8 +533,10 @@ GW_HD Event next_event(Sim<D, NS, NJ, ST> &s, const BandParams &B, double tLimit
     // ticks that must go through the transition function: every tick of a plant env, otherwise
     // the ticks of a sender whose MAC waits for a packet
     // (finite traffic bursts: every tick goes through the transition function, which ends the process)
-    const bool wake0 = ALL_TICKS || B.maxTicks[0] != 0 || s.mac[0] == MAC_WAIT_COND;
-    const bool wake1 = ALL_TICKS || B.maxTicks[kMaxSend - 1] != 0 || s.mac[1] == MAC_WAIT_COND;
+    // (`Ring::ext`: compile-time switch of the kernels for bands with receive mode / bursts -- everybody else
+    // carries no code for them)
+    const bool wake0 = ALL_TICKS || (Ring::ext && B.maxTicks[0] != 0) || s.mac[0] == MAC_WAIT_COND;
+    const bool wake1 = ALL_TICKS || (Ring::ext && B.maxTicks[kMaxSend - 1] != 0) || s.mac[1] == MAC_WAIT_COND;
     if (wake0 && (ev.kind == EV_NONE || before(s.tTick[0], s.sTick[0], ev.t, ev.seq))) {
         ev.kind = EV_TICK; ev.idx = 0; ev.t = s.tTick[0]; ev.seq = s.sTick[0];
     }
@@ -841,7 +843,7 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
         const int mult = k == 0 ? B.mult[0] : B.mult[kMaxSend - 1];
         const double interval = k == 0 ? B.interval[0] : B.interval[kMaxSend - 1];
         const int maxTicks = k == 0 ? B.maxTicks[0] : B.maxTicks[kMaxSend - 1];
-        if (maxTicks != 0 && get_at(s.ticks, k) >= (uint64_t)maxTicks) {
+        if (Ring::ext && maxTicks != 0 && get_at(s.ticks, k) >= (uint64_t)maxTicks) {
             // the burst is over: this wake-up only ends the traffic process (its process event takes a number)
             set_at(s.tTick, k, (double)INFINITY);
             s.seq++;
@@ -990,7 +992,7 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
                         const bool idle = get_at(s.mac, p) == MAC_NONE;
                         if (d == RRM && s.annDest == p) {
                             if (idle) window = p;
-                        } else if (d < NS && idle && (p == 0 ? B.recv[0] : B.recv[kMaxSend - 1])) {
+                        } else if (Ring::ext && d < NS && idle && (p == 0 ? B.recv[0] : B.recv[kMaxSend - 1])) {
                             received |= 1 << p;         // the two senders of a band address each other
                         }
                     } else if (p == RRM) {
@@ -1044,7 +1046,7 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
             // next RECEIVE command with a fresh timeout (devices.py:88-95, simple_stack.py:452-460)
             GW_UNROLL
             for (int k = 0; k < NS; ++k) {
-                if (!((received >> k) & 1)) continue;
+                if (!Ring::ext || !((received >> k) & 1)) continue;
                 ring.add_received(k);
                 trace_rec(s, REC_MRX, s.now, k, 0.0, 0.0, 0.0, 0.0);
                 ring.set_rx(k, s.now + kReceiveTimeout, s.seq++);

@@ -146,6 +146,7 @@ struct gw_handle {
     // has been raised on THIS handle's device (the attribute is per device, and a handle is driven by
     // one host thread at a time -- include/gymwipe_b200.h)
     unsigned smem_configured;
+    int ext;                // some band uses MAC receive mode / finite bursts: the EXT kernels step this handle
     unsigned long long *stamps;         // gw_debug_stamps: device buffer [stamp_cap][4], next slot
     long long stamp_cap, stamp_next;
 };
@@ -421,7 +422,11 @@ __device__ __forceinline__ void store_sim(const Sim<D, NS, NJ, ST> &s, const Sta
     }
 }
 
-struct DevRing {
+// EXT: the band-sims of this handle may use MAC receive mode / finite traffic bursts (gw_device_config.receive /
+// max_ticks); the kernels of everybody else are compiled without that code (gw_core.cuh tests `Ring::ext`)
+template <bool EXT>
+struct DevRingT {
+    static constexpr bool ext = EXT;
     int32_t *base;      // ring + sim index
     long long nsim;
     const uint4 *hot;   // hot chunks + sim index
@@ -452,6 +457,7 @@ struct DevRing {
     }
     __device__ __forceinline__ uint32_t received(int k) const { return reinterpret_cast<const uint32_t *>(hot + (long long)H_RCV1 * nsim)[2 + k]; }
 };
+using DevRing = DevRingT<true>;
 
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
@@ -720,7 +726,7 @@ struct SharedTables {
 #define GW_STEP_MIN_BLOCKS 4
 #endif
 
-template <int MODE, int D, int NS, int NJ, bool TRACE = false>
+template <int MODE, int D, int NS, int NJ, bool TRACE = false, bool EXT = false>
 __global__ void __launch_bounds__(STEP_BLOCK, GW_STEP_MIN_BLOCKS)
 step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P,
             const __grid_constant__ SharedTables T)
@@ -788,7 +794,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         // band-sim's own table in global memory; no registers are held for it
         const SrxView srx = A.st.per_env ? SrxView{A.st.srx + (active ? i : 0), A.st.ntab}
                                          : SrxView{&srx_s[band][0], 1};
-        DevRing ring{A.st.ring + (active ? i : 0), nsim, A.st.hot + (active ? i : 0)};
+        DevRingT<EXT> ring{A.st.ring + (active ? i : 0), nsim, A.st.hot + (active ? i : 0)};
         int dev = 0, dur = 0;
         bool idle0 = false;
         if (active) {
@@ -1222,7 +1228,7 @@ pendulum_step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__
     }
     const uint32_t nTx0 = s.nTx, nD0 = s.nDeliv[0], nD1 = s.nDeliv[1];
     begin_assignment(s, P, dev, dur);
-    DevRing ring{A.st.ring + i, nsim, A.st.hot + i};
+    DevRingT<false> ring{A.st.ring + i, nsim, A.st.hot + i};
     PendulumPlant<DevVals, DevSrxOut> plant(Q, S, DevVals{A.st.pval + i, nsim}, DevSrxOut{A.st.srx + i, A.st.ntab});
     run_until_assign_plant<MODE_R>(s, P, P.band[0], srx, ring, NoMasks(), NoMemo(), plant);
     // InvertedPendulumInterpreter (inverted_pendulum.py:42-56): the angle is read from the plant
@@ -1944,6 +1950,10 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
     h->D = D; h->NS = NS; h->NJ = NJ;
     h->pdl = std::getenv("GYMWIPE_B200_NO_PDL") ? 0 : 1;
     fill_params(*cfg, h->P);
+    for (int b = 0; b < cfg->n_bands; ++b)
+        for (int d = 0; d < cfg->band[b].n_devices; ++d)
+            if (cfg->band[b].device[d].role == GW_ROLE_SENDER && (cfg->band[b].device[d].receive || cfg->band[b].device[d].max_ticks != 0))
+                h->ext = 1;
     const long long ntab = cfg->per_env_positions ? cfg->n_envs * cfg->n_bands : 1;
     h->layout = make_layout(cfg->n_envs, cfg->n_bands, ntab, cfg->plant);
     if (state) {
@@ -2179,7 +2189,12 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     } while (0)
 #define CALL_STEP(DD, SS, JJ)                                                                        \
     do {                                                                                             \
-        if (trace) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ, true>), 0, DD, SS, JJ);               \
+        if (h->ext) {                                                                                \
+            if (trace) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ, true, true>), 4, DD, SS, JJ);     \
+            else if (h->cfg.mode == GW_MODE_REFERENCE) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ, false, true>), 5, DD, SS, JJ);  \
+            else if (h->cfg.mode == GW_MODE_MASK_PHILOX) LAUNCH_STEP((step_kernel<MODE_M_PHILOX, DD, SS, JJ, false, true>), 6, DD, SS, JJ); \
+            else LAUNCH_STEP((step_kernel<MODE_M_FED, DD, SS, JJ, false, true>), 7, DD, SS, JJ);      \
+        } else if (trace) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ, true>), 0, DD, SS, JJ);        \
         else if (h->cfg.mode == GW_MODE_REFERENCE) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ>), 1, DD, SS, JJ);  \
         else if (h->cfg.mode == GW_MODE_MASK_PHILOX) LAUNCH_STEP((step_kernel<MODE_M_PHILOX, DD, SS, JJ>), 2, DD, SS, JJ); \
         else LAUNCH_STEP((step_kernel<MODE_M_FED, DD, SS, JJ>), 3, DD, SS, JJ);                       \

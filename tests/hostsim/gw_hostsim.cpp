@@ -19,6 +19,7 @@ using namespace gw;
 namespace {
 
 struct HostRing {
+    static constexpr bool ext = true;       // receive mode / bursts compiled in
     int32_t *data;      // [NS][100]
     // MAC receive mode: {time-out, creation number, packets handed to onReceive} per sender
     double *rxt; uint32_t *rxs; uint32_t *rxn;

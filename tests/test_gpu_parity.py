@@ -139,7 +139,7 @@ def test_cuda_event_trace_matches_reference_golden(name):
             if g[0] == "tx":
                 assert tuple(g[4:]) == tuple(w[4:]), (name, t, g, w)
             elif g[0] == "ber":
-                rel = abs(g[4] - w[4]) / abs(w[4])
+                rel = abs(g[4] - w[4]) / max(abs(w[4]), 1e-300)      # the BER underflows to exactly 0 on very strong links
                 worst = max(worst, rel)
                 assert rel <= BER_RTOL, (name, t, g, w)
             elif g[0] == "dec":
