@@ -209,8 +209,11 @@ def cfg3_long_packet(dev_t, peak, rank=0, world=1, steps=48):
     """
     BASELINE configs[2]: 1500-byte payloads, fed per-bit masks (mode M), a PHY-only interferer creating
     mid-packet SINR segments; ASSIGNMENT_DURATION_FACTOR = 10000 so that windows fit 122 ms packets.
-    The mask scan INSIDE the fused step kernel is the HBM-bound part of the path: its roofline entry uses
-    the bytes of mask words the kernel counted (`gw_mask_bytes`) + the 193 B of state per env-step.
+    The HBM-bound part of the path is the popcount over the mask words.  `gw_set_masks` does it in ONE streaming
+    pass over the fed buffer (`mask_index_kernel`: per-row prefix counts) -- that kernel's roofline is the
+    `roofline` entry; the fused step kernel then takes every section's count from two index entries and at most
+    two 16-byte groups per row (`step`), instead of scanning ~6 KB of mask words per env-step inside the event
+    loop (`GW_FED_INDEX=0`: the in-step scan of the previous rounds, reported by `profiles/`).
     """
     import torch
     import gymwipe_b200
@@ -222,13 +225,27 @@ def cfg3_long_packet(dev_t, peak, rank=0, world=1, steps=48):
         {"role": "jammer", "x": 6.0, "y": 0.0, "interval": 0.05, "delay": 0.003, "power": 0.0, "hdr": 13, "payload": 200}]}]}
     env = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, scenario=sc, mode="mask_fed",
                             env_id_offset=rank * n, strict=False)
-    # Bernoulli(1/16) masks: 4 GiB, resident before the timed region (>> L2: every scan streams from HBM)
+    # Bernoulli(1/16) masks: 4 GiB, resident before the timed region (>> L2: every pass streams from HBM)
     shape = (n, 1, 4, slots, 4, words)
     g = torch.Generator(device=dev_t).manual_seed(77 + rank)
     masks = torch.randint(-2 ** 31, 2 ** 31 - 1, shape, dtype=torch.int32, device=dev_t, generator=g)
     for _ in range(3):                                  # AND of 4 random words: bit density 1/16
         masks &= torch.randint(-2 ** 31, 2 ** 31 - 1, shape, dtype=torch.int32, device=dev_t, generator=g)
-    env.set_masks(masks, slots)
+    stream = torch.cuda.current_stream(dev_t)
+    env.set_masks(masks, slots)                         # allocates the index; untimed
+    torch.cuda.synchronize(dev_t)
+    indexed = os.environ.get("GW_FED_INDEX", "1")[:1] != "0"
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        env.set_masks(masks, slots)                     # one launch of mask_index_kernel over the 4 GiB
+    e1.record(stream)
+    torch.cuda.synchronize(dev_t)
+    idx_ms = e0.elapsed_time(e1) / reps
+    rows = n * 4 * slots * 4
+    idx_read = int(masks.numel() * 4)
+    idx_write = rows * (((words // 4) + 1 + 7) // 8 * 8) * 2
     env.reset()
     a_dev = torch.randint(0, 2, (steps + 4, n), generator=g, device=dev_t, dtype=torch.int32)
     a_dur = torch.randint(12, 20, (steps + 4, n), generator=g, device=dev_t, dtype=torch.int32)
@@ -239,16 +256,36 @@ def cfg3_long_packet(dev_t, peak, rank=0, world=1, steps=48):
     mask_bytes = env.mask_bytes() / steps
     st = env.stats().cpu().numpy()
     algo = mask_bytes + ALGO_BYTES_PER_ENV_STEP * n
-    achieved = algo / (ms * 1e-3) / 1e9
-    return {"workload": "configs[2]: 1500-byte payloads, fed per-bit masks (mode M), PHY-only interferer, %d envs per GPU" % n,
-            "n_envs": n, "env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "transmissions_per_step": float(st[6]) / steps,
-            "deliveries_per_step": float(st[1] + st[2]) / steps, "mask_bytes_resident": int(masks.numel() * 4),
-            "roofline": {"bound": "hbm", "kernel": "step_kernel<MODE_M_FED,4,2,1> (fused step incl. the in-step mask scan)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "algorithmic_bytes_per_launch": algo, "mask_bytes_per_launch": mask_bytes,
-                         "avg_launch_ms": ms, "traffic": ncu_traffic_per_launch("cfg3_dram_bytes_per_launch"),
-                         "note": "algorithmic bytes = 32-bit mask words holding the on-air bits of every decided "
-                                 "section (counted by the kernel) + 193 B of state per env-step; masks 4 GiB >> L2"}}
+    out = {"workload": "configs[2]: 1500-byte payloads, fed per-bit masks (mode M), PHY-only interferer, %d envs per GPU" % n,
+           "n_envs": n, "env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms, "transmissions_per_step": float(st[6]) / steps,
+           "deliveries_per_step": float(st[1] + st[2]) / steps, "mask_bytes_resident": idx_read}
+    if indexed:
+        achieved = (idx_read + idx_write) / (idx_ms * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "kernel": "mask_index_kernel (gw_set_masks): the popcount over the fed mask words, one "
+                                                      "streaming pass per feed, per-row prefix counts out",
+                           "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                           "algorithmic_bytes_per_launch": idx_read + idx_write, "bytes_read": idx_read,
+                           "bytes_written": idx_write, "avg_launch_ms": idx_ms,
+                           "traffic": ncu_traffic_per_launch("mask_index_dram_bytes_per_launch"),
+                           "note": "every mask word is read once per gw_set_masks; the step kernels read two index "
+                                   "entries and at most two 16-byte groups per receiver and decided section"}
+        out["step"] = {"kernel": "step_kernel<MODE_M_FEDX,4,2,1> (event loop + index look-ups)", "ms_per_step": ms,
+                       "decided_mask_bytes_per_step": mask_bytes,
+                       "decided_mask_gbs": algo / (ms * 1e-3) / 1e9,
+                       "traffic": ncu_traffic_per_launch("cfg3_dram_bytes_per_launch"),
+                       "steps_amortising_one_feed": idx_ms / ms,
+                       "note": "decided_mask_bytes = the 32-bit mask words that hold the on-air bits of every decided section "
+                               "(what an in-step scan has to read; rounds 1-2 read them at 780 GB/s, 0.54 ms per step); "
+                               "decided_mask_gbs is that figure over the step time -- an equivalent rate, not traffic"}
+    else:
+        achieved = algo / (ms * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "kernel": "step_kernel<MODE_M_FED,4,2,1> (fused step incl. the in-step mask scan)",
+                           "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                           "algorithmic_bytes_per_launch": algo, "mask_bytes_per_launch": mask_bytes,
+                           "avg_launch_ms": ms, "traffic": ncu_traffic_per_launch("cfg3_scan_dram_bytes_per_launch"),
+                           "note": "algorithmic bytes = 32-bit mask words holding the on-air bits of every decided "
+                                   "section (counted by the kernel) + 193 B of state per env-step; masks 4 GiB >> L2"}
+    return out
 
 
 def cfg4_multiband(dev_t, rank=0, world=1, steps=64):

@@ -148,6 +148,7 @@ _SIGNATURES = {
     "gw_mask_bytes": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.c_int, _VP]),
     "gw_read_state": (C.c_int, [_VP, C.c_int, _VP, _VP]),
     "gw_set_masks": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP]),
+    "gw_mask_index_count": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int64, _VP]),
     "gw_fspl_attenuation": (C.c_int, [_VP, _VP, _VP, _VP, C.c_double, _VP, C.c_int64, _VP]),
     "gw_ber_bpsk": (C.c_int, [_VP, _VP, _VP, C.c_int64, _VP]),
     "gw_count_bit_errors": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP, _VP, C.c_int64, _VP]),

@@ -135,6 +135,11 @@ struct gw_handle {
     // mode M fed masks
     const uint32_t *masks;
     int mask_slots, mask_words;
+    // prefix-count index of the fed masks (gw_set_masks; see mask_index_kernel)
+    uint16_t *mask_t16;
+    uint32_t *mask_s32;
+    int mask_gt, mask_nsb;
+    size_t mask_idx_bytes;
     // BER memo
     ulonglong2 *memo;
     unsigned memo_entries;
@@ -546,6 +551,10 @@ struct MaskSource {
     long long env_offset;
     const uint32_t *words;      // fed masks
     int slots, words_per_row;
+    // prefix-count index of the fed masks (mask_index_kernel), or NULL
+    const uint16_t *t16;        // [rows][gt]: set bits of groups [first group of g's superblock, g) of the row
+    const uint32_t *s32;        // [rows][nsb]: set bits before superblock sb (512 groups); NULL when rows have one superblock
+    int gt, nsb;
 };
 
 // number of set bits among bits [k0, k1) of a row of 32-bit words; all 32 lanes cooperate,
@@ -664,6 +673,83 @@ __device__ __forceinline__ void prefetch_bulk_l2(const void *p, unsigned bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(bytes) : "memory");
 }
 
+// ------------------------------------------------------------------------------------
+// K3i: prefix-count index of the fed masks.
+//
+// A section's error count is the number of set bits among bits [k0, k1) of a mask row (SimplePhy._countBitErrors
+// with per-bit masks, simple_stack.py:180-188).  The rows are DATA handed over with gw_set_masks, so the counting
+// is hoisted out of the event loop: ONE streaming pass over the whole mask buffer -- this kernel, HBM-bound,
+// every mask word read exactly once -- leaves per row the number of set bits in front of every 128-bit group
+// (uint16, relative to the group's 512-group superblock; uint32 totals per superblock for rows longer than
+// 64 Kibit), and a count in the step kernel is  before(k1) - before(k0)  with
+//     before(k) = s32[row][k >> 16] + t16[row][k >> 7] + popc(bits of group k >> 7 below k & 127):
+// two index entries and at most two 16-byte groups per row and decision, whatever the length of the section
+// and however the section was cut into SINR segments.  One warp per row, four consecutive groups per lane
+// (64 contiguous bytes), one warp scan per 128 groups.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mask_index_kernel(const uint32_t *words, int words_per_row, long long rows, uint16_t *t16, uint32_t *s32, int gt, int nsb)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int G = words_per_row >> 2;
+    for (long long r = warp; r < rows; r += nwarps) {
+        const uint4 *row4 = reinterpret_cast<const uint4 *>(words + r * words_per_row);
+        uint16_t *trow = t16 + r * gt;
+        unsigned total = 0, sbBase = 0;
+        for (int start = 0; start <= G; start += 128) {
+            const int g = start + 4 * lane;
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = g + u < G ? __ldcs(row4 + g + u) : make_uint4(0, 0, 0, 0);
+            const int c0 = popc4(v[0]), c1 = popc4(v[1]), c2 = popc4(v[2]), c3 = popc4(v[3]);
+            const int mine = c0 + c1 + c2 + c3;
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if ((start & 511) == 0) {
+                sbBase = total;
+                if (s32 != nullptr && lane == 0) s32[r * nsb + (start >> 9)] = total;
+            }
+            const unsigned b0 = total + (unsigned)(incl - mine) - sbBase;      // set bits of this superblock in front of group g
+            if (g < gt) {
+                const unsigned e0 = b0, e1 = b0 + c0, e2 = e1 + c1, e3 = e2 + c2;
+                *reinterpret_cast<uint2 *>(trow + g) = make_uint2(e0 | (e1 << 16), e2 | (e3 << 16));
+            }
+            total += (unsigned)__shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+    }
+}
+
+// set bits among bits [k0, k1) of mask row `row` = before(k1) - before(k0): the (up to) two index entries per end
+// and the (up to) two edge groups are independent read-only loads, issued together
+__device__ __forceinline__ int fed_count(const MaskSource &m, long long row, int k0, int k1)
+{
+    const int g0 = k0 >> 7, r0 = k0 & 127, g1 = k1 >> 7, r1 = k1 & 127;
+    const uint16_t *t = m.t16 + row * m.gt;
+    const uint4 *row4 = reinterpret_cast<const uint4 *>(m.words + row * m.words_per_row);
+    const int t1 = __ldg(t + g1);
+    const int t0 = k0 ? (int)__ldg(t + g0) : 0;
+    uint4 v1 = make_uint4(0, 0, 0, 0), v0 = make_uint4(0, 0, 0, 0);
+    if (r1) v1 = __ldg(row4 + g1);
+    if (r0) v0 = __ldg(row4 + g0);
+    int c = t1 - t0;
+    if (m.s32 != nullptr) c += (int)(__ldg(m.s32 + row * m.nsb + (g1 >> 9)) - __ldg(m.s32 + row * m.nsb + (g0 >> 9)));
+    return c + popc_below(v1, r1) - popc_below(v0, r0);
+}
+
+// the index look-up on its own (gw_mask_index_count: numeric tests of the index against plain popcounts)
+__global__ void mask_index_count_kernel(MaskSource m, const long long *rows, const int *k0, const int *k1, int *counts, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    counts[i] = k1[i] > k0[i] ? fed_count(m, rows[i], k0[i], k1[i]) : 0;
+}
+
 // Philox-generated masks: bit k is an error iff word (k & 3) of block (k >> 2) < thr
 __device__ __forceinline__ int warp_philox_range(unsigned long long seed, long long env, int band, int sender,
                                                  uint32_t txseq, int receiver, int k0, int k1, uint32_t thr, int lane)
@@ -689,6 +775,9 @@ __device__ __forceinline__ int warp_philox_range(unsigned long long seed, long l
 // ------------------------------------------------------------------------------------
 // K4: fused event-ordered step kernel (+ K5 epilogue)
 // ------------------------------------------------------------------------------------
+
+// kernel-level variant of MODE_M_FED: the handle holds a prefix-count index of its masks (mask_index_kernel)
+constexpr int MODE_M_FEDX = 3;
 
 struct StepArgs {
     StatePtrs st;
@@ -838,6 +927,59 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
                 for (int o = 1; o < nb; o <<= 1) Tend = fmax(Tend, __shfl_xor_sync(0xFFFFFFFFu, Tend, o));
                 if (active && s.now < Tend) run_until_time<MODE_R>(s, P, B, srx, ring, NoMasks(), Tend, memo);
             }
+        } else if (MODE == MODE_M_FEDX) {
+            // Mode M with fed masks and a prefix-count index (mask_index_kernel): the count of a decision is two
+            // index look-ups per receiver, done by the deciding lane on the spot -- the per-lane event loop of
+            // mode R, no warp-level service of count requests.  (fed_decide_set: only DECIDING events count.)
+            double Tend = INFINITY;
+            int phase = 0;      // 0: until the own ASSIGN is processed, 1: until Tend
+            unsigned maskWords = 0;
+            for (;;) {
+                if (active) {
+                    while (!s.fault) {
+                        if (phase == 0 && s.assignDone) break;
+                        const Event ev = next_event(s, B, phase == 0 ? (double)INFINITY : Tend, ring);
+                        if (phase == 1 && !(ev.t < Tend)) break;
+                        const int nd = fed_decide_set(s, ev);
+                        s.now = ev.t;
+                        if (nd) {
+                            // all receivers' look-ups are issued before the first count is used
+                            int cnt[D];
+#pragma unroll
+                            for (int p = 0; p < D; ++p) {
+                                cnt[p] = 0;
+                                if (!((nd >> p) & 1)) continue;
+                                int sender; uint32_t txseq; int64_t a0, a1;
+                                mask_range(s, p, P.bitRate, sender, txseq, a0, a1);
+                                if (a1 > a0) {
+                                    const long long row = ((((env * nb + band) * kMaxDev + sender) * A.masks.slots
+                                                            + (long long)(txseq % (uint32_t)A.masks.slots)) * kMaxDev + p);
+                                    cnt[p] = fed_count(A.masks, row, (int)a0, (int)a1);
+                                    maskWords += (unsigned)((((int)a1 + 31) >> 5) - ((int)a0 >> 5));
+                                }
+                            }
+#pragma unroll
+                            for (int p = 0; p < D; ++p)
+                                if ((nd >> p) & 1) { s.err[p] += (double)cnt[p]; s.segT0[p] = ev.t; }
+                        }
+                        const int berMask = apply_event(s, P, B, ev, srx, ring);
+                        update_bers(s, P, berMask, srx, memo);
+                    }
+                }
+                if (phase == 0 && nb > 1) {
+                    __syncwarp();
+                    double t = active ? s.now : -INFINITY;
+                    for (int o = 1; o < nb; o <<= 1) t = fmax(t, __shfl_xor_sync(0xFFFFFFFFu, t, o));
+                    Tend = t;
+                    phase = 1;
+                    continue;
+                }
+                break;
+            }
+            if (active && nb > 1) s.now = Tend;
+            // statistic: the mask words that hold the on-air bits of the decided sections (algorithmic bytes)
+            maskWords = __reduce_add_sync(0xFFFFFFFFu, maskWords);
+            if (lane == 0 && maskWords != 0 && A.maskBytes != nullptr) atomicAdd(A.maskBytes, 4ull * maskWords);
         } else if (MODE == MODE_M_FED) {
             // Mode M with fed masks.  The count of a section does not depend on the segmentation
             // (gw_core.cuh::fed_decide_set), so only DECIDING events read mask words.  Two alternating parts:
@@ -2065,6 +2207,7 @@ void gw_destroy(gw_handle *h)
     if (h->d_obs) cudaFree(h->d_obs);       // base of the staging allocation
     if (h->memo) cudaFree(h->memo);
     if (h->pos_cur) cudaFree(h->pos_cur);
+    if (h->mask_t16) cudaFree(h->mask_t16);
     delete h;
 }
 
@@ -2093,6 +2236,7 @@ int gw_set_positions(gw_handle *h, const double *positions, void *stream)
     MaskSource ms;
     ms.mode = h->cfg.mode; ms.seed = h->cfg.seed; ms.env_offset = h->cfg.env_id_offset;
     ms.words = h->masks; ms.slots = h->mask_slots > 0 ? h->mask_slots : 1; ms.words_per_row = h->mask_words;
+    ms.t16 = nullptr; ms.s32 = nullptr; ms.gt = 0; ms.nsb = 0;
     if (h->cfg.mode == GW_MODE_MASK_FED && !h->masks) return fail(GW_E_INVALID, "mode MASK_FED: call gw_set_masks first");
     const long long nsim = h->st.nsim;
 #define CALL_MOVE(DD, SS, JJ)                                                                                              \
@@ -2144,6 +2288,7 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     A.trace = trace; A.traceCount = trace_count; A.traceCap = trace_cap;
     A.masks.mode = h->cfg.mode; A.masks.seed = h->cfg.seed; A.masks.env_offset = h->cfg.env_id_offset;
     A.masks.words = h->masks; A.masks.slots = h->mask_slots > 0 ? h->mask_slots : 1; A.masks.words_per_row = h->mask_words;
+    A.masks.t16 = h->mask_t16; A.masks.s32 = h->mask_s32; A.masks.gt = h->mask_gt; A.masks.nsb = h->mask_nsb;
     A.memo.tab = h->memo; A.memo.mask = h->memo_entries ? h->memo_entries - 1 : 0;
     A.memo.l0g = (h->memo && !h->st.per_env) ? h->memo + 2ull * h->memo_entries : nullptr;
     A.memo.l0s = nullptr;
@@ -2193,10 +2338,12 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
             if (trace) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ, true, true>), 4, DD, SS, JJ);     \
             else if (h->cfg.mode == GW_MODE_REFERENCE) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ, false, true>), 5, DD, SS, JJ);  \
             else if (h->cfg.mode == GW_MODE_MASK_PHILOX) LAUNCH_STEP((step_kernel<MODE_M_PHILOX, DD, SS, JJ, false, true>), 6, DD, SS, JJ); \
+            else if (h->mask_t16) LAUNCH_STEP((step_kernel<MODE_M_FEDX, DD, SS, JJ, false, true>), 9, DD, SS, JJ); \
             else LAUNCH_STEP((step_kernel<MODE_M_FED, DD, SS, JJ, false, true>), 7, DD, SS, JJ);      \
         } else if (trace) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ, true>), 0, DD, SS, JJ);        \
         else if (h->cfg.mode == GW_MODE_REFERENCE) LAUNCH_STEP((step_kernel<MODE_R, DD, SS, JJ>), 1, DD, SS, JJ);  \
         else if (h->cfg.mode == GW_MODE_MASK_PHILOX) LAUNCH_STEP((step_kernel<MODE_M_PHILOX, DD, SS, JJ>), 2, DD, SS, JJ); \
+        else if (h->mask_t16) LAUNCH_STEP((step_kernel<MODE_M_FEDX, DD, SS, JJ>), 8, DD, SS, JJ);    \
         else LAUNCH_STEP((step_kernel<MODE_M_FED, DD, SS, JJ>), 3, DD, SS, JJ);                       \
     } while (0)
     DISPATCH_SHAPE(h, CALL_STEP);
@@ -2454,6 +2601,52 @@ int gw_set_masks(gw_handle *h, const uint32_t *mask_words, int32_t slots, int32_
     if (!mask_words || slots < 1 || words_per_row < 4 || (words_per_row & 3)) return fail(GW_E_INVALID, "bad mask layout (words_per_row must be a multiple of 4)");
     if (((uintptr_t)mask_words & 15) != 0) return fail(GW_E_INVALID, "mask buffer must be 16-byte aligned");
     h->masks = mask_words; h->mask_slots = slots; h->mask_words = words_per_row;
+    // prefix-count index (mask_index_kernel): one streaming pass over the buffer on `stream`; GW_FED_INDEX=0 in the
+    // environment keeps the step kernels scanning the mask words themselves (step_kernel<MODE_M_FED>)
+    const char *no_index = std::getenv("GW_FED_INDEX");
+    const bool want_index = !(no_index && no_index[0] == '0');
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!want_index || h->cfg.mode != GW_MODE_MASK_FED) {
+        if (h->mask_t16) { CUDA_TRY(cudaFree(h->mask_t16)); h->mask_t16 = nullptr; h->mask_s32 = nullptr; h->mask_idx_bytes = 0; }
+        return GW_OK;
+    }
+    const long long rows = h->st.nsim * kMaxDev * (long long)slots * kMaxDev;
+    const int G = words_per_row >> 2;
+    const int gt = (G + 1 + 7) & ~7;                // entries per row: G + 1, padded to 16 bytes
+    const int nsb = (G >> 9) + 1;
+    const size_t t16_bytes = align_up((size_t)rows * gt * sizeof(uint16_t), 256);
+    const size_t s32_bytes = nsb > 1 ? (size_t)rows * nsb * sizeof(uint32_t) : 0;
+    if (h->mask_idx_bytes != t16_bytes + s32_bytes || !h->mask_t16) {
+        if (h->mask_t16) { CUDA_TRY(cudaFree(h->mask_t16)); h->mask_t16 = nullptr; h->mask_s32 = nullptr; h->mask_idx_bytes = 0; }
+        void *p = nullptr;
+        CUDA_TRY(cudaMalloc(&p, t16_bytes + s32_bytes));
+        h->mask_t16 = (uint16_t *)p;
+        h->mask_idx_bytes = t16_bytes + s32_bytes;
+    }
+    h->mask_s32 = nsb > 1 ? (uint32_t *)((char *)h->mask_t16 + t16_bytes) : nullptr;
+    h->mask_gt = gt; h->mask_nsb = nsb;
+    long long blocks = (rows + 7) / 8;              // 8 warps per block, one row per warp and pass
+    const long long cap = 148ll * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    mask_index_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(mask_words, words_per_row, rows, h->mask_t16, h->mask_s32, gt, nsb);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_mask_index_count(gw_handle *h, const int64_t *rows, const int32_t *k0, const int32_t *k1, int32_t *counts, int64_t n,
+                        void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    if (!h->mask_t16) return fail(GW_E_INVALID, "no mask index: mode MASK_FED and gw_set_masks first (GW_FED_INDEX=0 disables it)");
+    if (n <= 0) return GW_OK;
+    if (!rows || !k0 || !k1 || !counts) return fail(GW_E_INVALID, "NULL buffer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    MaskSource m;
+    m.mode = MODE_M_FED; m.seed = 0; m.env_offset = 0;
+    m.words = h->masks; m.slots = h->mask_slots; m.words_per_row = h->mask_words;
+    m.t16 = h->mask_t16; m.s32 = h->mask_s32; m.gt = h->mask_gt; m.nsb = h->mask_nsb;
+    mask_index_count_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(m, (const long long *)rows, k0, k1, counts, n);
+    CUDA_TRY(cudaGetLastError());
     return GW_OK;
 }
 

@@ -279,9 +279,22 @@ int gw_read_state(gw_handle *h, int field, double *out, void *stream);
 /* Mode M, fed masks: `mask_words` is a device uint32 buffer laid out
  * [n_envs][n_bands][GW_MAX_DEVICES sender][slots][GW_MAX_DEVICES receiver][words_per_row];
  * transmission number q of a sender uses slot q % slots; bit k of a row is the error
- * flag of on-air bit k (bit k%32 of word k/32).  The buffer stays caller-owned. */
+ * flag of on-air bit k (bit k%32 of word k/32).  The buffer stays caller-owned.
+ *
+ * The call makes ONE streaming pass over the buffer on `stream` and keeps a prefix-count index of it in the
+ * handle (per row the set bits in front of every 128-bit group: 2 bytes per 16 bytes of mask, allocated on the
+ * first call / when the layout changes): SimplePhy._countBitErrors over a section (simple_stack.py:180-188)
+ * is then two index look-ups per receiver in the step kernel instead of a scan of the section's mask words
+ * inside the event loop.  Call it again after changing mask words in place.  GW_FED_INDEX=0 in the environment
+ * (read by this call) skips the index; the step kernels then scan the words themselves. */
 int gw_set_masks(gw_handle *h, const uint32_t *mask_words, int32_t slots, int32_t words_per_row,
                  void *stream);
+
+/* The index look-up on its own (numeric tests): counts[i] = set bits among bits [k0[i], k1[i]) of mask row
+ * rows[i] (row = (((env * n_bands + band) * GW_MAX_DEVICES + sender) * slots + slot) * GW_MAX_DEVICES + receiver),
+ * evaluated through the index built by gw_set_masks.  Device arrays: rows int64 [n], k0 / k1 / counts int32 [n]. */
+int gw_mask_index_count(gw_handle *h, const int64_t *rows, const int32_t *k0, const int32_t *k1, int32_t *counts,
+                        int64_t n, void *stream);
 
 /* ---- grids of PHY-only senders with in-step mobility ---------------------
  *

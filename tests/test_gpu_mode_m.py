@@ -90,16 +90,24 @@ def test_mode_m_sharding_invariance():
         assert (gp["counts"] == g["counts"][128 * k:128 * (k + 1)]).all()
 
 
-def test_mode_m_fed_masks_match_oracle():
-    """Both sides are fed the SAME mask words; long packets (1500-byte payloads) with a jammer."""
-    rs = np.random.RandomState(55)
-    sc = random_scenario(rs, jammers=1, spread=2.0, fixed_payload=1500, factor=10000)
-    nenv, nsteps, slots, words = 48, 24, 4, 512
+def _bernoulli_masks(rs, nenv, slots, words):
     # Bernoulli(p) bits, p different per receiver so that some packets fail and some pass
     p = rs.uniform(0.02, 0.3, size=(nenv, 1, 4, slots, 4, 1))
     bits = rs.random_sample((nenv, 1, 4, slots, 4, words * 32)) < p
     masks = np.packbits(bits.reshape(-1, 8)[:, ::-1], axis=1).reshape(nenv, 1, 4, slots, 4, words * 4)
-    masks = masks.view("<u4").reshape(nenv, 1, 4, slots, 4, words)
+    return np.ascontiguousarray(masks.view("<u4").reshape(nenv, 1, 4, slots, 4, words))
+
+
+@pytest.mark.parametrize("index", ["1", "0"])
+def test_mode_m_fed_masks_match_oracle(index, monkeypatch):
+    """Both sides are fed the SAME mask words; long packets (1500-byte payloads) with a jammer.  index = 1: the
+    counts come from the prefix-count index gw_set_masks builds (step_kernel<MODE_M_FEDX>); 0: the step kernel
+    scans the mask words itself (step_kernel<MODE_M_FED>, GW_FED_INDEX=0)."""
+    monkeypatch.setenv("GW_FED_INDEX", index)
+    rs = np.random.RandomState(55)
+    sc = random_scenario(rs, jammers=1, spread=2.0, fixed_payload=1500, factor=10000)
+    nenv, nsteps, slots, words = 48, 24, 4, 512
+    masks = _bernoulli_masks(rs, nenv, slots, words)
     dev, dur = random_tapes(rs, nsteps, nenv, 1)
     o = O.run_batch(sc, dev, dur, mode=O.MODE_M, fed_words=masks, fed_slots=slots)
     env = make_env(sc, nenv, mode="mask_fed")
@@ -108,6 +116,56 @@ def test_mode_m_fed_masks_match_oracle():
     g = run_gpu(env, dev, dur)
     assert_same(o, g)
     assert 0 < o["counts"][:, :, 1:3].sum() < o["counts"][:, :, 0].sum()
+
+
+def test_mode_m_fed_rows_longer_than_a_superblock():
+    """8000-byte payloads: 85,461 on-air bits per packet = 668 groups of 128 bits, more than one 512-group
+    superblock of the prefix-count index (its uint32 level), windows of up to 0.95 s."""
+    rs = np.random.RandomState(77)
+    sc = random_scenario(rs, jammers=1, spread=2.0, fixed_payload=8000, factor=50000)
+    nenv, nsteps, slots, words = 6, 10, 2, 2688
+    masks = _bernoulli_masks(rs, nenv, slots, words)
+    dev, dur = random_tapes(rs, nsteps, nenv, 1)
+    dur = np.maximum(dur, 14)
+    o = O.run_batch(sc, dev, dur, mode=O.MODE_M, fed_words=masks, fed_slots=slots)
+    env = make_env(sc, nenv, mode="mask_fed")
+    env.set_masks(torch.as_tensor(masks.view(np.int32)).cuda(), slots)
+    env.reset()
+    assert_same(o, run_gpu(env, dev, dur))
+    assert o["counts"][:, :, 0].sum() > 0
+
+
+@pytest.mark.parametrize("words", [64, 512, 2052, 4096])
+def test_mask_index_counts_match_numpy(words):
+    """gw_mask_index_count (the look-up the step kernel does) against numpy popcounts over arbitrary bit ranges:
+    rows shorter than, equal to and longer than one 512-group superblock (2048 words)."""
+    from gymwipe_b200 import _native as N
+    from gymwipe_b200.scenario import default_scenario_dict
+    rs = np.random.RandomState(words)
+    nenv, slots = 3, 2
+    rows = nenv * 4 * slots * 4
+    m = rs.randint(0, 2 ** 32, size=(rows, words), dtype=np.uint64).astype(np.uint32)
+    m &= rs.randint(0, 2 ** 32, size=(rows, words), dtype=np.uint64).astype(np.uint32)
+    m[1] = 0xFFFFFFFF                    # a full row: the largest counts
+    env = make_env(default_scenario_dict(), nenv, mode="mask_fed")
+    env.set_masks(torch.as_tensor(m.view(np.int32).reshape(nenv, 1, 4, slots, 4, words)).cuda(), slots)
+    n = 6000
+    ridx = rs.randint(0, rows, n).astype(np.int64)
+    k0 = rs.randint(0, words * 32, n).astype(np.int32)
+    k1 = np.minimum(words * 32, k0 + rs.randint(0, 2 * words * 32, n)).astype(np.int32)
+    k1[:50] = k0[:50]                     # empty ranges
+    k0[50:80], k1[50:80] = 0, words * 32  # whole rows
+    k0[80:110] = (k0[80:110] >> 7) << 7   # group-aligned starts
+    k1[110:140] = np.maximum(k0[110:140], (k1[110:140] >> 7) << 7)
+    ridx[140:150] = 1
+    bits = np.unpackbits(m.view(np.uint8).reshape(rows, -1), axis=1, bitorder="little")
+    cs = np.concatenate([np.zeros((rows, 1), np.int64), np.cumsum(bits, axis=1)], axis=1)
+    want = cs[ridx, k1] - cs[ridx, k0]
+    out = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_rows, d_k0, d_k1 = torch.as_tensor(ridx).cuda(), torch.as_tensor(k0).cuda(), torch.as_tensor(k1).cuda()
+    N.check(N.lib().gw_mask_index_count(env._handle, d_rows.data_ptr(), d_k0.data_ptr(), d_k1.data_ptr(),
+                                        out.data_ptr(), n, torch.cuda.current_stream().cuda_stream))
+    assert (out.cpu().numpy().astype(np.int64) == want.astype(np.int64)).all()
 
 
 def test_k3_count_bit_errors_kernel():
