@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -42,6 +43,10 @@ using namespace gw;
 // ------------------------------------------------------------------------------------
 
 static thread_local char g_err[512] = "";
+// handle generations (gw_handle::generation) are unique over all handles and calls of the process: a handle
+// allocated at the address of a destroyed one never matches a cached launch graph of its predecessor
+static std::atomic<unsigned long long> g_generation{1};
+static unsigned long long next_generation() { return g_generation.fetch_add(1); }
 
 static int fail(int code, const char *fmt, ...)
 {
@@ -154,6 +159,8 @@ struct gw_handle {
     int ext;                // some band uses MAC receive mode / finite bursts: the EXT kernels step this handle
     unsigned long long *stamps;         // gw_debug_stamps: device buffer [stamp_cap][4], next slot
     long long stamp_cap, stamp_next;
+    unsigned long long generation;      // bumped by every call that changes what a step launch is given (masks, shared
+                                        // statistics, positions, stamps): cached launch graphs are keyed by it
 };
 
 // ------------------------------------------------------------------------------------
@@ -2087,6 +2094,7 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
     gw_handle *h = new (std::nothrow) gw_handle();
     if (!h) return fail(GW_E_INVALID, "out of host memory");
     std::memset(h, 0, sizeof *h);
+    h->generation = next_generation();
     h->cfg = *cfg;
     h->device = device;
     h->D = D; h->NS = NS; h->NJ = NJ;
@@ -2215,6 +2223,7 @@ int gw_set_positions(gw_handle *h, const double *positions, void *stream)
 {
     if (!h) return fail(GW_E_INVALID, "handle is NULL");
     if (positions && !h->st.per_env) return fail(GW_E_INVALID, "handle was created with per_env_positions = 0");
+    h->generation = next_generation();
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     const size_t pos_bytes = sizeof(double) * (size_t)h->st.ntab * kMaxDev * 2;
@@ -2467,10 +2476,18 @@ static int step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *res
 // side streams of gw_step_host_compact_many, per device (created on first use, never destroyed: they live
 // as long as the library)
 constexpr int MANY_STREAMS = 4;
+struct ManyGraph {
+    unsigned long long key;
+    cudaGraphExec_t exec;
+    unsigned long long used;
+};
 struct ManyStreams {
     cudaStream_t s[MANY_STREAMS];
-    cudaEvent_t fork, join[MANY_STREAMS];
+    cudaStream_t main;                  // stands in for the legacy default stream (which cannot be captured)
+    cudaEvent_t fork, join[MANY_STREAMS], enter;
     bool ready;
+    std::vector<ManyGraph> graphs;      // captured population steps (gw_step_host_compact_many), keyed by the call
+    unsigned long long clock;
 };
 static ManyStreams g_many[64];
 static std::mutex g_many_mutex;
@@ -2497,6 +2514,8 @@ int gw_step_host_compact_many(gw_handle *const *handles, int32_t n_handles, cons
         ms = &g_many[dev];
         if (!ms->ready) {
             CUDA_TRY(cudaEventCreateWithFlags(&ms->fork, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ms->enter, cudaEventDisableTiming));
+            CUDA_TRY(cudaStreamCreateWithFlags(&ms->main, cudaStreamNonBlocking));
             for (int k = 0; k < MANY_STREAMS; ++k) {
                 CUDA_TRY(cudaStreamCreateWithFlags(&ms->s[k], cudaStreamNonBlocking));
                 CUDA_TRY(cudaEventCreateWithFlags(&ms->join[k], cudaEventDisableTiming));
@@ -2505,16 +2524,82 @@ int gw_step_host_compact_many(gw_handle *const *handles, int32_t n_handles, cons
         }
     }
     const int lanes = n_handles < MANY_STREAMS ? n_handles : MANY_STREAMS;
-    CUDA_TRY(cudaEventRecord(ms->fork, s));
-    for (int k = 0; k < lanes; ++k) CUDA_TRY(cudaStreamWaitEvent(ms->s[k], ms->fork, 0));
+    if (s == nullptr) {
+        // the legacy default stream: the call runs on a stream of the library's own, ordered behind what the
+        // default stream holds; it returns synchronised, so later work on the default stream is ordered behind it
+        CUDA_TRY(cudaEventRecord(ms->enter, nullptr));
+        CUDA_TRY(cudaStreamWaitEvent(ms->main, ms->enter, 0));
+        s = ms->main;
+    }
+    // enqueues the fork / per-batch launches / join on `s` and the side streams
+    auto enqueue = [&]() -> int {
+        CUDA_TRY(cudaEventRecord(ms->fork, s));
+        for (int k = 0; k < lanes; ++k) CUDA_TRY(cudaStreamWaitEvent(ms->s[k], ms->fork, 0));
+        for (int k = 0; k < n_handles; ++k) {
+            const int rc = step_host_compact(handles[k], actions[k], results[k], (void *)ms->s[k % lanes], false);
+            if (rc) return rc;
+        }
+        for (int k = 0; k < lanes; ++k) {
+            CUDA_TRY(cudaEventRecord(ms->join[k], ms->s[k]));
+            CUDA_TRY(cudaStreamWaitEvent(s, ms->join[k], 0));
+        }
+        return GW_OK;
+    };
+    // The same call (same handles, same pinned buffers, nothing about the handles changed) is usually repeated
+    // step after step: its ~16 kernel launches and event operations are captured ONCE into a CUDA graph and
+    // replayed with one cudaGraphLaunch -- the host-side launch cost per population step drops from ~16 launches
+    // to one.  GW_MANY_GRAPH=0 in the environment: plain launches.  Handles with launch stamps are not cached.
+    static const bool use_graph = [] { const char *e = std::getenv("GW_MANY_GRAPH"); return !(e && e[0] == '0'); }();
+    bool cacheable = use_graph;
+    unsigned long long key = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
+    mix((unsigned long long)n_handles); mix((unsigned long long)(uintptr_t)s);
     for (int k = 0; k < n_handles; ++k) {
-        const int rc = step_host_compact(handles[k], actions[k], results[k], (void *)ms->s[k % lanes], false);
-        if (rc) return rc;
+        if (handles[k]->stamps) cacheable = false;
+        mix((unsigned long long)(uintptr_t)handles[k]); mix(handles[k]->generation);
+        mix((unsigned long long)(uintptr_t)actions[k]); mix((unsigned long long)(uintptr_t)results[k]);
     }
-    for (int k = 0; k < lanes; ++k) {
-        CUDA_TRY(cudaEventRecord(ms->join[k], ms->s[k]));
-        CUDA_TRY(cudaStreamWaitEvent(s, ms->join[k], 0));
+    if (cacheable) {
+        cudaGraphExec_t exec = nullptr;
+        {
+            std::lock_guard<std::mutex> lock(g_many_mutex);
+            for (auto &g : ms->graphs) if (g.key == key) { exec = g.exec; g.used = ++ms->clock; break; }
+        }
+        if (!exec) {
+            for (int k = 0; k < n_handles; ++k) {
+                // validation and the one-time shared-memory attribute happen outside the capture
+                if (!actions[k] || !results[k]) return fail(GW_E_INVALID, "NULL buffer");
+                if (!mapped_alias(actions[k]) || !mapped_alias(results[k])) { cacheable = false; break; }
+            }
+        }
+        if (cacheable && !exec) {
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+            const int rc = enqueue();
+            const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            CUDA_TRY(ce);
+            const cudaError_t ci = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            CUDA_TRY(ci);
+            std::lock_guard<std::mutex> lock(g_many_mutex);
+            if (ms->graphs.size() >= 32) {             // evict the least recently used entry
+                size_t victim = 0;
+                for (size_t q = 1; q < ms->graphs.size(); ++q) if (ms->graphs[q].used < ms->graphs[victim].used) victim = q;
+                cudaGraphExecDestroy(ms->graphs[victim].exec);
+                ms->graphs.erase(ms->graphs.begin() + (long)victim);
+            }
+            ms->graphs.push_back(ManyGraph{key, exec, ++ms->clock});
+        }
+        if (cacheable) {
+            for (int k = 0; k < n_handles; ++k) handles[k]->stepped = 1;
+            CUDA_TRY(cudaGraphLaunch(exec, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            return GW_OK;
+        }
     }
+    const int rc = enqueue();
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(s));
     return GW_OK;
 }
@@ -2560,6 +2645,7 @@ int gw_mask_bytes(gw_handle *h, uint64_t *out, int clear, void *stream)
 
 int gw_debug_stamps(gw_handle *h, uint64_t *stamps, int64_t capacity)
 {
+    if (h) h->generation = next_generation();
     if (!h) return fail(GW_E_INVALID, "handle is NULL");
     h->stamps = (unsigned long long *)stamps;
     h->stamp_cap = stamps ? capacity : 0;
@@ -2572,6 +2658,7 @@ int gw_share_stats(gw_handle *h, gw_handle *with)
     if (!h) return fail(GW_E_INVALID, "handle is NULL");
     if (with && with->device != h->device) return fail(GW_E_INVALID, "handles on different devices cannot share statistics");
     h->stats_use = with ? with->stats_use : h->stats;
+    h->generation = next_generation();
     return GW_OK;
 }
 
@@ -2601,6 +2688,7 @@ int gw_set_masks(gw_handle *h, const uint32_t *mask_words, int32_t slots, int32_
     if (!mask_words || slots < 1 || words_per_row < 4 || (words_per_row & 3)) return fail(GW_E_INVALID, "bad mask layout (words_per_row must be a multiple of 4)");
     if (((uintptr_t)mask_words & 15) != 0) return fail(GW_E_INVALID, "mask buffer must be 16-byte aligned");
     h->masks = mask_words; h->mask_slots = slots; h->mask_words = words_per_row;
+    h->generation = next_generation();
     // prefix-count index (mask_index_kernel): one streaming pass over the buffer on `stream`; GW_FED_INDEX=0 in the
     // environment keeps the step kernels scanning the mask words themselves (step_kernel<MODE_M_FED>)
     const char *no_index = std::getenv("GW_FED_INDEX");

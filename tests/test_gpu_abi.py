@@ -127,6 +127,46 @@ def test_population_host_step_equals_single_batch_steps():
     pop.close()
 
 
+def test_population_host_step_replays_its_cached_graph():
+    """The same call (same handles, same pinned buffers) is captured once and replayed: the replay reads the
+    buffers' NEW contents; a change of the handles (gw_share_stats) or of the buffers takes a fresh capture; more
+    distinct calls than the cache holds are evicted and re-captured."""
+    import gymwipe_b200
+    from gymwipe_b200.envs import EnvPopulation
+    n, nb, T = 384, 3, 48
+    rs = np.random.RandomState(18)
+    pop = EnvPopulation([gymwipe_b200.make('CounterTraffic-v0', num_envs=n, env_id_offset=k * n, strict=False) for k in range(nb)])
+    ref = [gymwipe_b200.make('CounterTraffic-v0', num_envs=n, env_id_offset=k * n, strict=False) for k in range(nb)]
+    pop.reset()
+    for e in ref:
+        e.reset()
+    res = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(nb)]
+    res_ptrs = EnvPopulation.pointer_array(res)
+    fixed = [torch.zeros((n, 2), dtype=torch.uint8).pin_memory() for _ in range(nb)]
+    fixed_ptrs = EnvPopulation.pointer_array(fixed)
+    for t in range(T):
+        acts = [np.stack([rs.randint(0, 2, n), rs.randint(0, 20, n)], axis=1).astype(np.uint8) for _ in range(nb)]
+        if t % 40 < 4:
+            pinned = [torch.as_tensor(a).pin_memory() for a in acts]       # new buffers: a new capture (40 > cache size)
+            pop.step_host_compact(EnvPopulation.pointer_array(pinned), res_ptrs)
+        else:
+            for k in range(nb):
+                fixed[k].copy_(torch.as_tensor(acts[k]))                    # same buffers, new contents: a replay
+            pop.step_host_compact(fixed_ptrs, res_ptrs)
+        if t == 20:
+            pop.stats()                                                     # (clears) ... and the handles change:
+            pop.envs[1].share_stats(None)                                   # env 1 counts on its own again
+        for k in range(nb):
+            o, r, d, _ = ref[k].step({"device": torch.as_tensor(acts[k][:, 0].astype(np.int32)).cuda(),
+                                      "duration": torch.as_tensor(acts[k][:, 1].astype(np.int32)).cuda()})
+            oo, rr, dd = ref[k].unpack_compact(res[k])
+            assert torch.equal(oo, o.cpu()) and torch.equal(rr, r.cpu()), t
+    pop.check()
+    own = pop.envs[1].stats().cpu().numpy()
+    assert own[4] == n * (T - 21)                                            # steps 21 .. T-1 went to its own accumulators
+    pop.close()
+
+
 @pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_handles_on_two_devices_in_one_process():
     """A jammer scenario needs > 48 KB of dynamic shared memory: the attribute is per device and must be set
