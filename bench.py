@@ -676,7 +676,8 @@ def own_arm(args, rank, world, local_rank):
                 r, err = None, repr(exc)
             torch.cuda.empty_cache()
             if world > 1:                               # every rank its share; the slowest rank bounds the step
-                t = torch.tensor([r["ms_per_step"] if r else float("inf")], dtype=torch.float64, device=dev_t)
+                rl_ms = r["roofline"]["avg_launch_ms"] if r and "roofline" in r else 0.0
+                t = torch.tensor([r["ms_per_step"] if r else float("inf"), rl_ms], dtype=torch.float64, device=dev_t)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 if r and float(t[0]) != float("inf"):
                     scale = r["ms_per_step"] / float(t[0])
@@ -684,10 +685,15 @@ def own_arm(args, rank, world, local_rank):
                     for key in ("env_steps_per_s", "band_steps_per_s"):
                         if key in r:
                             r[key] = r[key] * scale * world
-                    if "roofline" in r:
-                        r["roofline"]["achieved"] *= scale
-                        r["roofline"]["frac"] *= scale
-                        r["roofline"]["note"] += "; per GPU, at the slowest rank's step time"
+                    if "roofline" in r:                  # the roofline kernel's own launch time, slowest rank
+                        rs = rl_ms / float(t[1]) if float(t[1]) > 0 else 1.0
+                        r["roofline"]["achieved"] *= rs
+                        r["roofline"]["frac"] *= rs
+                        r["roofline"]["avg_launch_ms"] = float(t[1])
+                        r["roofline"]["note"] += "; per GPU, at the slowest rank's launch time"
+                    if "step" in r:
+                        r["step"]["ms_per_step"] = float(t[0])
+                        r["step"]["decided_mask_gbs"] *= scale
                     r["n_envs_total"] = r["n_envs"] * world
                 elif r:
                     r, err = None, "another rank failed"
@@ -730,15 +736,17 @@ def own_arm(args, rank, world, local_rank):
                      "kernel": "step_kernel<MODE_R,3,2,0>", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
                      "avg_launch_ms": kernel_ms,
                      "note": "mode-R state is ~190 B/env-step: the fused step kernel is latency / issue bound, "
-                             "not HBM bound (SURVEY.md 8d); the HBM-bound kernel of the path is the mode-M mask scan "
-                             "inside the step kernel -- see cfg3_long_packet_mode_m.roofline"},
+                             "not HBM bound (SURVEY.md 8d); the HBM-bound kernel of the path is the popcount over the fed "
+                             "mode-M mask words (mask_index_kernel, one streaming pass per gw_set_masks) -- see "
+                             "cfg3_long_packet_mode_m.roofline"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * PE, "d2h_bytes_per_step": 4 * n * PE,
                 "steps": KE, "envs_per_step_per_gpu": n * PE, "timed_region_s": e2e_s,
                 "api": "EnvPopulation.step_host_compact -> gw_step_host_compact_many: one env.step of a population of %d "
                        "batches x %d envs per GPU from PINNED HOST buffers (uint8 actions [n][2] in, one packed uint32 "
                        "{obs:17, reward+16:5, done:1} per env out; the kernels read / write the pinned buffers in place over "
                        "the host link -- the h2d / d2h bytes are moved by the kernels' own loads and stores, inside the timed "
-                       "region); one stream synchronisation per population step; steady-state envs" % (PE, n),
+                       "region); the call's launches are captured once into a CUDA graph and replayed; one stream synchronisation "
+                       "per population step; steady-state envs" % (PE, n),
                 "reward_checksum": reward_checksum, "result_checksum": checksum,
                 "single_batch_sync": {"value": n * world * KS / e2e_single_s, "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n,
                                       "api": "CounterTrafficEnv.step_host_compact -> gw_step_host_compact: ONE batch per call, "

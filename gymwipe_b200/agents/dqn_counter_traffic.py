@@ -241,13 +241,23 @@ class DQNLearner:
         obs = self.env.reset()
         obs = torch.as_tensor(obs, device=self.device).reshape(-1)
         fused = self.fused_policy and self._fused_ok()
-        for _ in range(nb_steps):
+        # two result triples used alternately (obs of step t is still needed while step t + 1 writes its own):
+        # the loop allocates nothing per step
+        bufs = None
+        if hasattr(self.env, "_shape_t"):
+            bufs = [(torch.empty(self.env._shape_t, dtype=torch.int64, device=self.device),
+                     torch.empty(self.env._shape_t, dtype=torch.float64, device=self.device),
+                     torch.empty(self.env._shape_t, dtype=torch.bool, device=self.device)) for _ in range(2)]
+        for it in range(nb_steps):
             if fused:
                 flat, action = self.select_action_fused(obs)
             else:
                 flat = self.select_action(obs)
                 action = self.processor.process_action(flat)
-            next_obs, reward, done, _ = self.env.step(action)
+            if bufs is not None:
+                next_obs, reward, done, _ = self.env.step(action, out=bufs[it & 1])
+            else:
+                next_obs, reward, done, _ = self.env.step(action)
             next_obs = torch.as_tensor(next_obs, device=self.device).reshape(-1)
             reward = torch.as_tensor(reward, device=self.device).reshape(-1)
             done = torch.as_tensor(done, device=self.device).reshape(-1)

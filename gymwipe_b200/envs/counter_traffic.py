@@ -368,11 +368,13 @@ class CounterTrafficEnv(BaseEnv):
                 return dev, dur
         return None
 
-    def step(self, action):
+    def step(self, action, out=None):
         """
         ``counter_traffic.py:146-158``: assigns the band (``action["device"]``) for
         ``action["duration"] * ASSIGNMENT_DURATION_FACTOR`` slots in every env and simulates
-        until the assignment ends.  Returns ``(obs, reward, done, info)``.
+        until the assignment ends.  Returns ``(obs, reward, done, info)``.  ``out``: an optional
+        ``(obs int64, reward float64, done bool)`` triple of CUDA tensors of the batch shape that receives the
+        results (a loop that steps many times re-uses one triple instead of allocating three tensors per call).
         """
         fast = self._fast_action(action)
         scalar = False
@@ -384,9 +386,15 @@ class CounterTrafficEnv(BaseEnv):
             if scalar:
                 assert self.action_space.contains(action)
             dev, dur = self._prepare_action(action)
-        obs = torch.empty(self._shape, dtype=torch.int64, device=self.device)
-        reward = torch.empty(self._shape, dtype=torch.float64, device=self.device)
-        done = torch.empty(self._shape, dtype=torch.bool, device=self.device)
+        if out is not None:
+            obs, reward, done = out
+            assert obs.dtype == torch.int64 and reward.dtype == torch.float64 and done.dtype == torch.bool
+            assert obs.shape == self._shape_t and reward.shape == self._shape_t and done.shape == self._shape_t
+            assert obs.is_contiguous() and reward.is_contiguous() and done.is_contiguous() and obs.device == self.device
+        else:
+            obs = torch.empty(self._shape, dtype=torch.int64, device=self.device)
+            reward = torch.empty(self._shape, dtype=torch.float64, device=self.device)
+            done = torch.empty(self._shape, dtype=torch.bool, device=self.device)
         if torch.cuda.current_device() == self.device.index:
             rc = self._lib.gw_step(self._handle, dev.data_ptr(), dur.data_ptr(), obs.data_ptr(),
                                    reward.data_ptr(), done.data_ptr(), torch.cuda.current_stream().cuda_stream)
