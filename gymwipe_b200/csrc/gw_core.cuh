@@ -33,10 +33,19 @@
 #define GW_HD __host__ __device__ __forceinline__
 #define GW_HD_COLD __host__ __device__ __noinline__
 #define GW_UNROLL _Pragma("unroll")
+// Loops over the devices of a band inside the generic transition function.  Fully unrolled where the per-device
+// arrays live in registers (host build, plant kernel: a run-time index would push them to local memory); ROLLED
+// (unroll factor 1) in the step kernels, whose per-device arrays are in shared memory.  The kernels of bands with
+// interferers diverge into every branch of the transition function, and their unrolled code (8 k SASS instructions
+// = 125 KB against a 32 KB instruction cache) left the warps waiting for instruction fetch 65 % of the time (ncu:
+// stall_no_instruction 17.6 per issued instruction on configs[3]): rolled, configs[3] runs 1.77x faster
+// (2.77 -> 1.57 ms), configs[2] 1.10x, the default kernel 1.02x.  Needs D, NS, NJ, ST in scope.
+#define GW_UNROLL_D _Pragma("unroll (Sim<D, NS, NJ, ST>::kUnrollD)")
 #else
 #define GW_HD inline
 #define GW_HD_COLD inline
 #define GW_UNROLL
+#define GW_UNROLL_D
 #endif
 
 // test hook of the host build (tests/hostsim): counts how often each macro event applies
@@ -218,6 +227,7 @@ struct RegArr {
 };
 
 struct RegStore {
+    static constexpr bool roll = false;                     // arrays in registers: device loops stay unrolled
     template <class T, int N, int OFF> using Arr = RegArr<T, N>;
     template <class T, int N> using Aux = RegArr<T, N>;     // mode-M / plant-only arrays
 };
@@ -229,6 +239,11 @@ struct RegStore {
 template <int D, int NS, int NJ, class ST = RegStore>
 struct Sim {
     static constexpr int kD = D, kNS = NS, kNJ = NJ, kRrm = NS;
+#if !defined(GW_NO_ROLL)
+    static constexpr int kUnrollD = ST::roll ? 1 : D;                   // see GW_UNROLL_D
+#else
+    static constexpr int kUnrollD = D;
+#endif
     static constexpr int NJa = NJ > 0 ? NJ : 1;
     // byte offsets (per thread) of the arrays inside a direct storage
     enum : int {
@@ -454,7 +469,7 @@ GW_HD Event select_nontick(const Sim<D, NS, NJ, ST> &s, const BandParams &B, con
     } while (0)
     GW_UNROLL
     for (int j = 0; j < NJ; ++j) GW_CONSIDER(s.tJam[j], s.sJam[j], EV_JAM, j);
-    GW_UNROLL
+    GW_UNROLL_D
     for (int d = 0; d < D; ++d)
         if (s.sphase[d] >= S_SLOT) GW_CONSIDER(s.tEv[d], s.sEv[d], EV_PHY, d);
     GW_UNROLL
@@ -585,7 +600,7 @@ GW_HD void count_set(const Sim<D, NS, NJ, ST> &s, const Event &ev, const SRX &sr
     once = 0; twice = 0;
     if (ev.kind != EV_PHY) return;
     const int d = ev.idx, ph = get_at(s.sphase, d);
-    GW_UNROLL
+    GW_UNROLL_D
     for (int p = 0; p < D; ++p) {
         const int rx = s.rxOf[p];
         if (rx < 0) continue;
@@ -607,7 +622,7 @@ GW_HD void count_set(const Sim<D, NS, NJ, ST> &s, const Event &ev, const SRX &sr
 template <int D, int NS, int NJ, class ST>
 GW_HD void do_counts_R(Sim<D, NS, NJ, ST> &s, int once, int twice, double bitRate)
 {
-    GW_UNROLL
+    GW_UNROLL_D
     for (int p = 0; p < D; ++p) {
         if (!((once >> p) & 1)) continue;
         const double duration = s.now - s.tReset[p];
@@ -647,7 +662,7 @@ GW_HD int fed_decide_set(const Sim<D, NS, NJ, ST> &s, const Event &ev)
     if (ph != S_HDR && ph != S_PAY) return 0;
     const int sec = ph == S_HDR ? 0 : 1;
     int need = 0;
-    GW_UNROLL
+    GW_UNROLL_D
     for (int p = 0; p < D; ++p)
         if (s.rxOf[p] == d && s.rxSec[p] == sec) need |= 1 << p;
     return need;
@@ -917,7 +932,7 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
             if constexpr (Plant::active) plant.refresh_links(d, s.now, srx);
             // zero-delay notification: every other PHY registers the received power
             // (simple_stack.py:130-144); a PHY that is receiving re-evaluates its BER
-            GW_UNROLL
+            GW_UNROLL_D
             for (int p = 0; p < D; ++p) {
                 if (p == d) continue;
                 const double rp = srx_at<D>(srx, p, d);
@@ -930,11 +945,11 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
             }
             // receive processes in PHY construction order: idle, non-transmitting PHYs lock on
             // (simple_stack.py:214-235)
-            GW_UNROLL
+            GW_UNROLL_D
             for (int p = 0; p < D; ++p) {
                 if (p == d || s.rxOf[p] >= 0 || s.sphase[p] >= S_SLOT) continue;
                 s.rxOf[p] = d; s.rxSec[p] = 0;
-                s.err[p] = 0; s.ber[p] = 0.0; s.tReset[p] = s.now; s.segT0[p] = s.now;
+                s.err[p] = 0; s.ber[p] = 0.0; s.tReset[p] = s.now; set_at(s.segT0, p, s.now);
                 berMask |= 1 << p;
             }
         } else if (ph == S_HDR) {
@@ -942,14 +957,14 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
             const int hdrBytes = (NJ > 0 && d > RRM) ? B.jamHdr[0] : kMacHdr;
             const double hdrBits = (hdrBytes * 8) * P.bitsFactor;
             int wake = 0;
-            GW_UNROLL
+            GW_UNROLL_D
             for (int p = 0; p < D; ++p) {
                 if (s.rxOf[p] != d || s.rxSec[p] != 0) continue;
                 if (decide_rec(s, P, p, 0, hdrBits)) {
                     // _resetBitErrorCounter, then _updateBitErrorRate (simple_stack.py:248-250): with the
                     // power sum unchanged since the last evaluation the same (S, N) gives the same value
                     const double same = s.ber[p];
-                    s.rxSec[p] = 1; s.err[p] = 0; s.ber[p] = 0.0; s.tReset[p] = s.now; s.segT0[p] = s.now;
+                    s.rxSec[p] = 1; s.err[p] = 0; s.ber[p] = 0.0; s.tReset[p] = s.now; set_at(s.segT0, p, s.now);
                     if ((s.pchg >> p) & 1) {
                         berMask |= 1 << p;
                     } else {
@@ -964,7 +979,7 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
             set_at(s.sphase, d, (int)S_PAY);
             set_at(s.tEv, d, get_at(s.tC, d));
             set_at(s.sEv, d, get_at(s.sC, d));
-            GW_UNROLL
+            GW_UNROLL_D
             for (int p = 0; p < D; ++p) if ((wake >> p) & 1) begin_slot_wait(s, p);   // _nReceivingFinished.event
         } else {
             // eCompletes, callbacks in registration order:
@@ -974,7 +989,7 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
             set_at(s.sphase, d, (int)S_IDLE);
             const double payBits = (payBytes * 8) * P.bitsFactor;
             // 2. _onCompletingTransmission of every other PHY (simple_stack.py:146-157)
-            GW_UNROLL
+            GW_UNROLL_D
             for (int p = 0; p < D; ++p) {
                 if (p == d) continue;
                 const double rp = srx_at<D>(srx, p, d);
@@ -993,7 +1008,7 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
             }
             // 3. receivers that passed the header decide on the payload and deliver
             int window = -1, wake = 0, received = 0;
-            GW_UNROLL
+            GW_UNROLL_D
             for (int p = 0; p < D; ++p) {
                 if (s.rxOf[p] != d || s.rxSec[p] != 1) continue;
                 if (decide_rec(s, P, p, 1, payBits)) {
@@ -1053,7 +1068,7 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
                 }
             }
             // d. _nReceivingFinished.event of the receivers that finished
-            GW_UNROLL
+            GW_UNROLL_D
             for (int p = 0; p < D; ++p) if ((wake >> p) & 1) begin_slot_wait(s, p);
             // e. RECEIVE.eProcessed: the device's receive loop hands the packet to onReceive and issues the
             // next RECEIVE command with a fresh timeout (devices.py:88-95, simple_stack.py:452-460)
@@ -1112,7 +1127,7 @@ struct NoMemo {
 template <int D, int NS, int NJ, class ST, class SRX, class Memo>
 GW_HD void update_bers(Sim<D, NS, NJ, ST> &s, const Params &P, int berMask, const SRX &srx, const Memo &memo)
 {
-    GW_UNROLL
+    GW_UNROLL_D
     for (int p = 0; p < D; ++p) {
         if (!((berMask >> p) & 1)) continue;
         const int e = s.rxOf[p];
@@ -1184,13 +1199,13 @@ GW_HD void process_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParam
     if (MODE == MODE_R) {
         do_counts_R(s, once, twice, P.bitRate);
     } else {
-        GW_UNROLL
+        GW_UNROLL_D
         for (int p = 0; p < D; ++p) {
             if (!((once >> p) & 1)) continue;
             int sender; uint32_t txseq; int64_t k0, k1;
             mask_range(s, p, P.bitRate, sender, txseq, k0, k1);
             if (k1 > k0) s.err[p] += (double)masks(p, sender, txseq, k0, k1, s.ber[p]);
-            s.segT0[p] = s.now;
+            set_at(s.segT0, p, s.now);
         }
     }
     const int berMask = apply_event(s, P, B, ev, srx, ring, plant);

@@ -194,6 +194,7 @@ struct ShArr {
 };
 
 struct ShStore {
+    static constexpr bool roll = true;                      // arrays in shared memory: a run-time index is an address
     template <class T, int N, int OFF> using Arr = ShArr<T, N, OFF>;
     template <class T, int N> using Aux = RegArr<T, N>;     // dead (mode R) or few (mode M) registers
 };
@@ -2156,15 +2157,12 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
     if (e == cudaSuccess) e = cudaMemsetAsync(h->stats, 0, aux, s);
     if (e == cudaSuccess) e = cudaMalloc(&stg, nsim * (4 + 4 + 8 + 8 + 1) + 64);
     if (e != cudaSuccess) { gw_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
-    if (!std::getenv("GYMWIPE_B200_NO_MEMO")) {
-        // identical geometry in every env: a small table holds every (S, N) pair that occurs;
-        // per-env geometries: ~20 recurring pairs per band-sim, so the table scales with the batch
-        // (32 entries per band-sim, 32 B each, capped at 2 GiB)
+    if (!std::getenv("GYMWIPE_B200_NO_MEMO") && !cfg->per_env_positions) {
+        // identical geometry in every env: a small table holds every (S, N) pair that occurs.  Per-env geometries
+        // evaluate: a table that holds their ~20 recurring pairs per band-sim has to scale with the batch (512 MB
+        // for configs[3]) and its random DRAM probes cost more than the evaluation (configs[3]: 1.56 ms per step
+        // with it, 1.51 ms without)
         h->memo_entries = 1u << 14;
-        if (cfg->per_env_positions) {
-            unsigned long long want = 32ull * (unsigned long long)nsim;
-            while (h->memo_entries < want && h->memo_entries < (1u << 26)) h->memo_entries <<= 1;
-        }
         e = cudaMalloc((void **)&h->memo, 32ull * (h->memo_entries + MEMO_L0));      // second + first level
         if (e == cudaSuccess) e = cudaMemsetAsync(h->memo, 0, 32ull * (h->memo_entries + MEMO_L0), s);
         if (e != cudaSuccess) { cudaFree(stg); gw_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
