@@ -681,7 +681,7 @@ struct NoPlant {
     static constexpr bool active = false;
     GW_HD double tick_value(int, double) { return 0.0; }
     GW_HD void delivered(int, int, double, double) {}
-    GW_HD void refresh_links(int, double, double *) {}
+    template <class SRX> GW_HD void refresh_links(int, double, const SRX &) {}
     GW_HD void put_value(int, uint64_t, double) {}
     GW_HD double get_value(int, uint64_t) { return 0.0; }
 };
@@ -1482,8 +1482,8 @@ GW_HD bool quiet_tail(Sim<D, NS, NJ, ST> &s, const BandParams &B)
 }
 
 // SimMan.runSimulation(assignSignal.eProcessed) for an env with a plant: every tick is an event
-template <int MODE, int D, int NS, int NJ, class ST, class Ring, class Masks, class Memo, class Plant>
-GW_HD void run_until_assign_plant(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, double *srx,
+template <int MODE, int D, int NS, int NJ, class ST, class SRX, class Ring, class Masks, class Memo, class Plant>
+GW_HD void run_until_assign_plant(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &B, const SRX &srx,
                                   const Ring &ring, const Masks &masks, const Memo &memo, Plant &plant)
 {
     while (!s.assignDone && !s.fault) {

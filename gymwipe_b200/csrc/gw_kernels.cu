@@ -1328,6 +1328,10 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
 // config 5: networked inverted pendulum -- the same transition function with a plant plugged in
 // ------------------------------------------------------------------------------------
 
+#ifndef GW_PEND_MIN_BLOCKS
+#define GW_PEND_MIN_BLOCKS 4
+#endif
+
 struct DevVals {
     double *base;       // pval + sim index
     long long nsim;
@@ -1355,21 +1359,22 @@ __device__ __forceinline__ void store_plant(const PendulumState &S, const StateP
     st.plant[7 * n + i] = S.lastError;
 }
 
-__global__ void __launch_bounds__(128)
+// Same layout as the step kernels: the per-device arrays of the band-sim in dynamic shared memory
+// ([field][index][thread], rolled device loops), the received-power table read from / written to the band-sim's
+// own table in global memory (the links follow the wagon).
+__global__ void __launch_bounds__(STEP_BLOCK, GW_PEND_MIN_BLOCKS)
 pendulum_step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P,
                      const __grid_constant__ PendulumParams Q)
 {
-    using SimT = Sim<4, 2, 1>;
+    using SimT = Sim<4, 2, 1, ShStore>;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nsim = A.st.nsim;
     if (i >= nsim) return;
     SimT s;
     PendulumState S;
-    double srx[16];
+    const SrxView srx{A.st.srx + i, A.st.ntab};
     load_sim(s, A.st, i, A.st.now[i]);
     load_plant(S, A.st, i);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) srx[k] = A.st.srx[(long long)k * A.st.ntab + i];
     int dev = A.device[i], dur = A.duration[i];
     if (dev < 0 || dev >= 2 || dur < 0 || dur >= P.maxDuration) {
         if (atomicCAS(A.errflag, 0, GW_E_ACTION) == 0) A.errflag[1] = (int)i;
@@ -2315,7 +2320,12 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     }
     const long long nsim = h->st.nsim;
     if (h->cfg.plant) {
-        pendulum_step_kernel<<<grid_for(nsim, 128), 128, 0, s>>>(A, h->P, h->pend);
+        constexpr int psmem = Sim<4, 2, 1, ShStore>::kDirectBytes * STEP_BLOCK;
+        if (!(h->smem_configured & (1u << 10))) {
+            CUDA_TRY(cudaFuncSetAttribute(pendulum_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem));
+            h->smem_configured |= 1u << 10;
+        }
+        pendulum_step_kernel<<<grid_for(nsim, STEP_BLOCK), STEP_BLOCK, psmem, s>>>(A, h->P, h->pend);
         CUDA_TRY(cudaGetLastError());
         return GW_OK;
     }
