@@ -1119,9 +1119,19 @@ GW_HD int apply_event(Sim<D, NS, NJ, ST> &s, const Params &P, const BandParams &
 // every env and step: a memo (exact fp64 results keyed by the exact bit patterns of S and N)
 // replaces ~10^3 dependent fp64 instructions by one table probe.  NoMemo = always evaluate.
 struct NoMemo {
-    GW_HD bool get(double, double, double &) const { return false; }
-    GW_HD void put(double, double, double) const {}
+    GW_HD bool get(double, double, double &, int = 0) const { return false; }
+    GW_HD void put(double, double, double, int = 0) const {}
 };
+
+// slot of a (receiver p, sender e) link in a per-band-sim BER cache: two ways per link -- with / without the band's
+// PHY-only interferer on the air, the two noise levels a link usually sees
+template <int D, int NS, int NJ, class ST>
+GW_HD int memo_slot(const Sim<D, NS, NJ, ST> &s, int p, int e)
+{
+    int way = 0;
+    if (NJ > 0) way = s.sphase[D - 1] >= S_HDR ? 1 : 0;
+    return ((p * kMaxDev + e) << 1) | way;
+}
 
 // SimplePhy._updateBitErrorRate for the PHYs in berMask (simple_stack.py:161-173)
 template <int D, int NS, int NJ, class ST, class SRX, class Memo>
@@ -1136,9 +1146,10 @@ GW_HD void update_bers(Sim<D, NS, NJ, ST> &s, const Params &P, int berMask, cons
         const double N = s.P[p] - S;
         if (!(S >= 0) || !(N >= 0)) { s.fault = FAULT_REF_ASSERT; continue; }   // simple_stack.py:168-169
         double ber;
-        if (!memo.get(S, N, ber)) {
+        const int slot = memo_slot(s, p, e);
+        if (!memo.get(S, N, ber, slot)) {
             ber = ber_bpsk_mw_cold(S, N, P.tenLog10BitRate, P.qDen);
-            memo.put(S, N, ber);
+            memo.put(S, N, ber, slot);
         }
         s.ber[p] = ber;
         s.pchg &= ~(1 << p);
@@ -1594,9 +1605,10 @@ GW_HD void received_power_change(Sim<D, NS, NJ, ST> &s, const Params &P, int p, 
     const double N = get_at(s.P, p) - S;
     if (!(S >= 0) || !(N >= 0)) { s.fault = FAULT_REF_ASSERT; return; }
     double ber;
-    if (!memo.get(S, N, ber)) {
+    const int slot = memo_slot(s, p, e);
+    if (!memo.get(S, N, ber, slot)) {
         ber = ber_bpsk_mw_cold(S, N, P.tenLog10BitRate, P.qDen);
-        memo.put(S, N, ber);
+        memo.put(S, N, ber, slot);
     }
     set_at(s.ber, p, ber);
     s.pchg &= ~(1 << p);

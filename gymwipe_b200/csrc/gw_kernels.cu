@@ -148,6 +148,7 @@ struct gw_handle {
     // BER memo
     ulonglong2 *memo;
     unsigned memo_entries;
+    ulonglong2 *memo_sim;   // per-env geometries: [64][n_sims] per-band-sim BER cache (DevMemo::sim)
     PendulumParams pend;
     int pdl;                // launch the step kernel with programmatic stream serialization
     double *pos_cur;        // per-env geometry: current device positions [ntab][GW_MAX_DEVICES][2]
@@ -507,14 +508,27 @@ struct DevMemo {
     // shared-memory reads instead of a trip to L2 / DRAM.  Filled from the second level.
     ulonglong2 *l0g;
     const ulonglong2 *l0s;
+    // per-env geometries: a cache of the band-sim's own -- [64][n_sims] x 16 B = {S, N} and {BER, -} for each of
+    // the 16 links x 2 ways (gw_core.cuh::memo_slot); `sim` points at this thread's band-sim, entries `stride`
+    // apart.  Only the owning thread reads and writes it: no validation beyond the exact (S, N) match.
+    ulonglong2 *sim;
+    long long stride;
     static constexpr unsigned long long MAGIC = 0x9E3779B97F4A7C15ull;
     __device__ __forceinline__ unsigned slot(unsigned long long a, unsigned long long b) const
     {
         unsigned long long h = a * 0x9E3779B97F4A7C15ull ^ (b + 0xC2B2AE3D27D4EB4Full) * 0xD6E8FEB86659FD93ull;
         return (unsigned)(h >> 40) & mask;
     }
-    __device__ __forceinline__ bool get(double S, double N, double &ber) const
+    __device__ __forceinline__ bool get(double S, double N, double &ber, int link = 0) const
     {
+        if (sim) {
+            const ulonglong2 k = sim[(long long)(2 * link) * stride];
+            if (k.x == (unsigned long long)__double_as_longlong(S) && k.y == (unsigned long long)__double_as_longlong(N)) {
+                ber = __longlong_as_double((long long)sim[(long long)(2 * link + 1) * stride].x);
+                return true;
+            }
+            return false;
+        }
         if (!tab) return false;
         const unsigned long long a = (unsigned long long)__double_as_longlong(S), b = (unsigned long long)__double_as_longlong(N);
         const unsigned h = slot(a, b);
@@ -532,8 +546,13 @@ struct DevMemo {
         }
         return false;
     }
-    __device__ __forceinline__ void put(double S, double N, double ber) const
+    __device__ __forceinline__ void put(double S, double N, double ber, int link = 0) const
     {
+        if (sim) {
+            sim[(long long)(2 * link) * stride] = make_ulonglong2((unsigned long long)__double_as_longlong(S), (unsigned long long)__double_as_longlong(N));
+            sim[(long long)(2 * link + 1) * stride] = make_ulonglong2((unsigned long long)__double_as_longlong(ber), 0ull);
+            return;
+        }
         if (!tab) return;
         const unsigned long long a = (unsigned long long)__double_as_longlong(S), b = (unsigned long long)__double_as_longlong(N);
         const unsigned long long c = (unsigned long long)__double_as_longlong(ber);
@@ -892,6 +911,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         const SrxView srx = A.st.per_env ? SrxView{A.st.srx + (active ? i : 0), A.st.ntab}
                                          : SrxView{&srx_s[band][0], 1};
         DevRingT<EXT> ring{A.st.ring + (active ? i : 0), nsim, A.st.hot + (active ? i : 0)};
+        if (A.memo.sim != nullptr) memo.sim = A.memo.sim + (active ? i : 0);
         int dev = 0, dur = 0;
         bool idle0 = false;
         if (active) {
@@ -2172,6 +2192,12 @@ int gw_create(const gw_config *cfg, int device, void *state, size_t state_bytes,
         if (e == cudaSuccess) e = cudaMemsetAsync(h->memo, 0, 32ull * (h->memo_entries + MEMO_L0), s);
         if (e != cudaSuccess) { cudaFree(stg); gw_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
     }
+    if (!std::getenv("GYMWIPE_B200_NO_MEMO") && cfg->per_env_positions && !cfg->plant) {
+        // per-env geometries: every band-sim caches the BER of its own links (1 KB per band-sim)
+        e = cudaMalloc((void **)&h->memo_sim, 64ull * sizeof(ulonglong2) * (size_t)nsim);
+        if (e == cudaSuccess) e = cudaMemsetAsync(h->memo_sim, 0, 64ull * sizeof(ulonglong2) * (size_t)nsim, s);
+        if (e != cudaSuccess) { cudaFree(stg); gw_destroy(h); return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e)); }
+    }
     h->errflag = (int *)(h->stats + 8);
     h->mask_bytes = (unsigned long long *)(h->errflag + 4);
     h->stats_use = h->stats;
@@ -2217,6 +2243,7 @@ void gw_destroy(gw_handle *h)
     if (h->stats) cudaFree(h->stats);
     if (h->d_obs) cudaFree(h->d_obs);       // base of the staging allocation
     if (h->memo) cudaFree(h->memo);
+    if (h->memo_sim) cudaFree(h->memo_sim);
     if (h->pos_cur) cudaFree(h->pos_cur);
     if (h->mask_t16) cudaFree(h->mask_t16);
     delete h;
@@ -2304,6 +2331,7 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     A.memo.tab = h->memo; A.memo.mask = h->memo_entries ? h->memo_entries - 1 : 0;
     A.memo.l0g = (h->memo && !h->st.per_env) ? h->memo + 2ull * h->memo_entries : nullptr;
     A.memo.l0s = nullptr;
+    A.memo.sim = h->memo_sim; A.memo.stride = h->st.nsim;
     SharedTables T;
     std::memset(&T, 0, sizeof T);
     if (!h->st.per_env) {
