@@ -877,6 +877,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
     // torn one is a miss.)
     __shared__ ulonglong2 memo_l0[2 * MEMO_L0];
     DevMemo memo = A.memo;
+    memo.sim = nullptr;
     if (memo.l0g != nullptr) {
         for (int t = threadIdx.x; t < 2 * MEMO_L0; t += blockDim.x) memo_l0[t] = memo.l0g[t];
         memo.l0s = memo_l0;
@@ -911,7 +912,9 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
         const SrxView srx = A.st.per_env ? SrxView{A.st.srx + (active ? i : 0), A.st.ntab}
                                          : SrxView{&srx_s[band][0], 1};
         DevRingT<EXT> ring{A.st.ring + (active ? i : 0), nsim, A.st.hot + (active ? i : 0)};
-        if (A.memo.sim != nullptr) memo.sim = A.memo.sim + (active ? i : 0);
+        // (compile-time off in the kernels of bands without interferers: the default kernel sits at its register
+        // limit, and the extra pointer + branch cost its productive regime 7 %)
+        if (NJ > 0 && A.memo.sim != nullptr) memo.sim = A.memo.sim + (active ? i : 0);
         int dev = 0, dur = 0;
         bool idle0 = false;
         if (active) {
