@@ -35,7 +35,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 ENVS_PER_GPU = 65536
 POPULATION_BATCHES = 384               # 65,536-env batches per GPU: one bench step = one env.step of all of them (~2.5 ms)
-E2E_BATCHES = 16                       # batches of the population stepped per host-buffer call (gw_step_host_compact_many)
+E2E_BATCHES = 64                       # batches of the population stepped per host-buffer call (gw_step_host_compact_many)
 BURN_IN_STEPS = 128                    # steps of every env before the timed region (steady state, see own_arm)
 PRODUCTIVE_STEPS = 32                  # steps of every fresh env timed separately (productive regime)
 ALGO_BYTES_PER_ENV_STEP = 193          # SURVEY.md section 8d / DESIGN.md section 6
@@ -595,7 +595,7 @@ def own_arm(args, rank, world, local_rank):
     # ---- e2e: the same population step through the C ABI with HOST buffers (gw_step_host_compact_many): every
     # batch reads its pinned uint8 actions and writes its pinned result words in place; one synchronisation per
     # population step.  Steady-state envs (the population above); KE steps so that the region is >= ~60 ms.
-    PE = min(M, E2E_BATCHES)
+    PE = min(M, args.e2e_batches)
     epop = EnvPopulation(envs[:PE])
     EROWS = 8
     h_act = [[torch.stack([a_dev[(r * PE + b) % ROWS], a_dur[(r * PE + b) % ROWS]], dim=1).to(torch.uint8).cpu().pin_memory()
@@ -777,6 +777,8 @@ def main():
                     help="65,536-env batches per GPU (one bench step = one env.step of all of them)")
     ap.add_argument("--streams", type=int, default=3,
                     help="side streams EnvPopulation.step spreads the batches of a population step over")
+    ap.add_argument("--e2e-batches", type=int, default=E2E_BATCHES,
+                    help="batches stepped per host-buffer call of the e2e leg (gw_step_host_compact_many)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the mask-scan roofline and the cfg-3 run")
