@@ -603,30 +603,41 @@ def own_arm(args, rank, world, local_rank):
     h_res = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(PE)]
     act_ptrs = [EnvPopulation.pointer_array(h_act[r]) for r in range(EROWS)]
     res_ptrs = EnvPopulation.pointer_array(h_res)
-    res_np = [r.numpy() for r in h_res]
-    for r in range(max(W, 3)):
-        epop.step_host_compact(act_ptrs[r % EROWS], res_ptrs)
-    torch.cuda.synchronize(dev_t)
-    t0 = time.perf_counter()
-    for r in range(8):
-        epop.step_host_compact(act_ptrs[r % EROWS], res_ptrs)
-    est = (time.perf_counter() - t0) / 8
-    KE = max(K, int(0.06 / max(est, 1e-6)) + 1)
-    if world > 1:
-        ke = torch.tensor([KE], dtype=torch.int64, device=dev_t)
-        dist.all_reduce(ke, op=dist.ReduceOp.MAX)
-        KE = int(ke[0])
-        dist.barrier()
-    torch.cuda.synchronize(dev_t)
-    checksum = 0
-    t0 = time.perf_counter()
-    for r in range(KE):
-        epop.step_host_compact(act_ptrs[r % EROWS], res_ptrs)
-        checksum += int(res_np[r % PE][r % n])          # the step's results are on the host
-    torch.cuda.synchronize(dev_t)
-    e2e_s = time.perf_counter() - t0
+    # the smallest wire format (gw_step_host_tiny_many): one action byte in, one 16-bit result word out per env
+    t_act = [[((a_dev[(r * PE + b) % ROWS] << 7) | a_dur[(r * PE + b) % ROWS]).to(torch.uint8).cpu().pin_memory()
+              for b in range(PE)] for r in range(EROWS)]
+    t_res = [torch.empty(n, dtype=torch.int16).pin_memory() for _ in range(PE)]
+    tact_ptrs = [EnvPopulation.pointer_array(t_act[r]) for r in range(EROWS)]
+    tres_ptrs = EnvPopulation.pointer_array(t_res)
+    res_np = [r.numpy() for r in t_res]
+
+    def e2e_leg(step_fn, a_ptrs, r_ptrs, rnp):
+        for r in range(max(W, 3) + EROWS):
+            step_fn(a_ptrs[r % EROWS], r_ptrs)
+        torch.cuda.synchronize(dev_t)
+        t0 = time.perf_counter()
+        for r in range(8):
+            step_fn(a_ptrs[r % EROWS], r_ptrs)
+        est = (time.perf_counter() - t0) / 8
+        ke = max(K, int(0.06 / max(est, 1e-6)) + 1)
+        if world > 1:
+            kt = torch.tensor([ke], dtype=torch.int64, device=dev_t)
+            dist.all_reduce(kt, op=dist.ReduceOp.MAX)
+            ke = int(kt[0])
+            dist.barrier()
+        torch.cuda.synchronize(dev_t)
+        chk = 0
+        t0 = time.perf_counter()
+        for r in range(ke):
+            step_fn(a_ptrs[r % EROWS], r_ptrs)
+            chk += int(rnp[r % PE][r % n])              # the step's results are on the host
+        torch.cuda.synchronize(dev_t)
+        return ke, time.perf_counter() - t0, chk
+
+    KC, e2e_compact_s, _ = e2e_leg(epop.step_host_compact, act_ptrs, res_ptrs, [r.numpy() for r in h_res])
+    KE, e2e_s, checksum = e2e_leg(epop.step_host_tiny, tact_ptrs, tres_ptrs, res_np)
     epop.check()
-    reward_checksum = float(sum(env1.unpack_compact(h)[1].sum() for h in h_res))
+    reward_checksum = float(sum(env1.unpack_tiny(h)[1].sum() for h in t_res))
     # the single-batch synchronous call (gw_step_host_compact) and the wider-typed variants, for the record
     h_obs = torch.empty(n, dtype=torch.int64).pin_memory()
     h_rew = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -654,10 +665,10 @@ def own_arm(args, rank, world, local_rank):
 
     # max over ranks
     if world > 1:
-        v = torch.tensor([elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, prod_ms, e2e_packed_s, e2e_single_s],
+        v = torch.tensor([elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, prod_ms, e2e_packed_s, e2e_single_s, e2e_compact_s],
                          dtype=torch.float64, device=dev_t)
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, prod_ms, e2e_packed_s, e2e_single_s = [float(x) for x in v]
+        elapsed_ms, e2e_s, warm_ms, wall, e2e_wide_s, prod_ms, e2e_packed_s, e2e_single_s, e2e_compact_s = [float(x) for x in v]
     pop.close()
     del pop, epop, envs
     torch.cuda.empty_cache()
@@ -739,15 +750,20 @@ def own_arm(args, rank, world, local_rank):
                              "not HBM bound (SURVEY.md 8d); the HBM-bound kernel of the path is the popcount over the fed "
                              "mode-M mask words (mask_index_kernel, one streaming pass per gw_set_masks) -- see "
                              "cfg3_long_packet_mode_m.roofline"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n * PE, "d2h_bytes_per_step": 4 * n * PE,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * PE, "d2h_bytes_per_step": 2 * n * PE,
                 "steps": KE, "envs_per_step_per_gpu": n * PE, "timed_region_s": e2e_s,
-                "api": "EnvPopulation.step_host_compact -> gw_step_host_compact_many: one env.step of a population of %d "
-                       "batches x %d envs per GPU from PINNED HOST buffers (uint8 actions [n][2] in, one packed uint32 "
-                       "{obs:17, reward+16:5, done:1} per env out; the kernels read / write the pinned buffers in place over "
-                       "the host link -- the h2d / d2h bytes are moved by the kernels' own loads and stores, inside the timed "
-                       "region); the call's launches are captured once into a CUDA graph and replayed; one stream synchronisation "
-                       "per population step; steady-state envs" % (PE, n),
+                "api": "EnvPopulation.step_host_tiny -> gw_step_host_tiny_many: one env.step of a population of %d "
+                       "batches x %d envs per GPU from PINNED HOST buffers (one action byte `device << 7 | duration` in, one "
+                       "16-bit result word {obs - COUNTER_BOUND: 8, reward+16: 5, done: 1} per env out -- lossless: the "
+                       "interpreter's observation is COUNTER_BOUND + a difference of at most +-COUNTER_BYTE_LENGTH; the kernels "
+                       "read / write the pinned buffers in place over the host link -- the h2d / d2h bytes are moved by the "
+                       "kernels' own loads and stores, inside the timed region); the call's launches are captured once into a "
+                       "CUDA graph and replayed; one stream synchronisation per population step; steady-state envs" % (PE, n),
                 "reward_checksum": reward_checksum, "result_checksum": checksum,
+                "compact_api": {"value": n * PE * world * KC / e2e_compact_s, "h2d_bytes_per_step": 2 * n * PE,
+                                "d2h_bytes_per_step": 4 * n * PE, "steps": KC,
+                                "api": "EnvPopulation.step_host_compact -> gw_step_host_compact_many: the same call with uint8 "
+                                       "actions [n][2] in and one packed uint32 {obs:17, reward+16:5, done:1} per env out"},
                 "single_batch_sync": {"value": n * world * KS / e2e_single_s, "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * n,
                                       "api": "CounterTrafficEnv.step_host_compact -> gw_step_host_compact: ONE batch per call, "
                                              "synchronised every call (launch + kernel + wake-up latency per 65,536 envs)"},

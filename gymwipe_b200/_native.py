@@ -141,6 +141,8 @@ _SIGNATURES = {
     "gw_step_host_compact": (C.c_int, [_VP, _VP, _VP, _VP]),
     "gw_step_host_compact_async": (C.c_int, [_VP, _VP, _VP, _VP]),
     "gw_step_host_compact_many": (C.c_int, [C.POINTER(_VP), C.c_int32, C.POINTER(_VP), C.POINTER(_VP), _VP]),
+    "gw_step_host_tiny": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "gw_step_host_tiny_many": (C.c_int, [C.POINTER(_VP), C.c_int32, C.POINTER(_VP), C.POINTER(_VP), _VP]),
     "gw_check": (C.c_int, [_VP, _VP]),
     "gw_stats": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "gw_share_stats": (C.c_int, [_VP, _VP]),

@@ -826,6 +826,7 @@ struct StepArgs {
     // gw_step_host_compact: uint8 actions [n][2] in, one packed uint32 per sim out
     const unsigned char *act8;
     unsigned *res32;
+    int tiny;                           // gw_step_host_tiny: act8 = uint8 [n] (device << 7 | duration), res32 = uint16 [n]
     // band-sims [sim_begin, sim_end) are stepped by this launch (a multiple of the block size apart)
     long long sim_begin, sim_end;
     // event trace (gw_step_traced)
@@ -867,7 +868,7 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
             for (int c = 0; c < HOT_CHUNKS; ++c)
                 if (c != H_EPC && (NJ > 0 || c != H_JAM) && (keepSeq || c != H_U2)) prefetch_l2(A.st.hot + (long long)c * nsim + i0);
             if (nb == 1) prefetch_l2(A.st.now + i0);
-            if (A.act8) prefetch_l2(A.act8 + 2 * i0);
+            if (A.act8) prefetch_l2(A.act8 + (A.tiny ? i0 : 2 * i0));
             else { prefetch_l2(A.device + i0); prefetch_l2(A.duration + i0); }
         }
     }
@@ -928,8 +929,13 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
             }
             if (TRACE) { s.trace = A.trace + (long long)i * A.traceCap * 8; s.traceCap = A.traceCap; s.ntrace = 0; }
             if (A.act8) {
-                const uchar2 a2 = reinterpret_cast<const uchar2 *>(A.act8)[i];
-                dev = a2.x; dur = a2.y;
+                if (A.tiny) {
+                    const unsigned a1 = A.act8[i];
+                    dev = (int)(a1 >> 7); dur = (int)(a1 & 127u);
+                } else {
+                    const uchar2 a2 = reinterpret_cast<const uchar2 *>(A.act8)[i];
+                    dev = a2.x; dur = a2.y;
+                }
             } else {
                 dev = A.device[i];
                 dur = A.duration[i];
@@ -1301,7 +1307,16 @@ step_kernel(const __grid_constant__ StepArgs A, const __grid_constant__ Params P
             long long o; double rw; unsigned char dn;
             feedback(s, o, rw, dn);
             if (A.res32) {
-                A.res32[i] = ((unsigned)o & 0x1FFFFu) | ((unsigned)((int)rw + 16) << 17) | ((unsigned)(dn != 0) << 22);
+                if (A.tiny) {
+                    // obs as the signed difference obs - COUNTER_BOUND (the interpreter's latestDifference,
+                    // counter_traffic.py:85-94: +-COUNTER_BYTE_LENGTH at most); bit 15: it did not fit 8 bits
+                    const int diff = (int)(o - kCounterBound);
+                    reinterpret_cast<unsigned short *>(A.res32)[i] = (unsigned short)(
+                        ((unsigned)diff & 0xFFu) | ((unsigned)((int)rw + 16) << 8) | ((unsigned)(dn != 0) << 13)
+                        | ((diff < -128 || diff > 127) ? 0x8000u : 0u));
+                } else {
+                    A.res32[i] = ((unsigned)o & 0x1FFFFu) | ((unsigned)((int)rw + 16) << 17) | ((unsigned)(dn != 0) << 22);
+                }
             } else {
                 if (A.obs32) { A.obs32[i] = (int)o; A.reward32[i] = (float)rw; }
                 else { A.obs[i] = o; A.reward[i] = rw; }
@@ -2314,7 +2329,7 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
                        uint8_t *done, cudaStream_t s, int *obs32 = nullptr, float *reward32 = nullptr,
                        double *trace = nullptr, int *trace_count = nullptr, int trace_cap = 0,
                        const unsigned char *act8 = nullptr, unsigned *res32 = nullptr,
-                       long long sim_begin = 0, long long sim_end = -1)
+                       long long sim_begin = 0, long long sim_end = -1, int tiny = 0)
 {
     if (h->cfg.mode == GW_MODE_MASK_FED && !h->masks) return fail(GW_E_INVALID, "mode MASK_FED: call gw_set_masks first");
     h->stepped = 1;
@@ -2325,7 +2340,7 @@ static int launch_step(gw_handle *h, const int32_t *device, const int32_t *durat
     A.stats = h->stats_use; A.errflag = h->errflag; A.maskBytes = h->mask_bytes;
     A.stamps = (h->stamps && h->stamp_next < h->stamp_cap) ? h->stamps + 4 * h->stamp_next++ : nullptr;
     A.obs32 = obs32; A.reward32 = reward32;
-    A.act8 = act8; A.res32 = res32;
+    A.act8 = act8; A.res32 = res32; A.tiny = tiny;
     A.sim_begin = sim_begin; A.sim_end = sim_end < 0 ? h->st.nsim : sim_end;
     A.trace = trace; A.traceCount = trace_count; A.traceCap = trace_cap;
     A.masks.mode = h->cfg.mode; A.masks.seed = h->cfg.seed; A.masks.env_offset = h->cfg.env_id_offset;
@@ -2466,7 +2481,7 @@ static void *mapped_alias(const void *p)
     return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
-static int step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *results, void *stream, bool sync);
+static int step_host_compact(gw_handle *h, const uint8_t *actions, void *results, void *stream, bool sync, int tiny = 0);
 
 int gw_step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *results, void *stream)
 {
@@ -2478,36 +2493,38 @@ int gw_step_host_compact_async(gw_handle *h, const uint8_t *actions, uint32_t *r
     return step_host_compact(h, actions, results, stream, false);
 }
 
-static int step_host_compact(gw_handle *h, const uint8_t *actions, uint32_t *results, void *stream, bool sync)
+static int step_host_compact(gw_handle *h, const uint8_t *actions, void *results, void *stream, bool sync, int tiny)
 {
     if (!h) return fail(GW_E_INVALID, "handle is NULL");
     if (!actions || !results) return fail(GW_E_INVALID, "NULL buffer");
     if (h->cfg.plant) return fail(GW_E_INVALID, "gw_step_host_compact is not available for plant envs");
-    if (h->cfg.max_assign_duration > 256) return fail(GW_E_INVALID, "max_assign_duration > 256 does not fit uint8 actions");
+    if (h->cfg.max_assign_duration > (tiny ? 128 : 256))
+        return fail(GW_E_INVALID, "max_assign_duration does not fit the %s action format", tiny ? "1-byte" : "uint8");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     const long long n = h->st.nsim;
+    const size_t abytes = (size_t)(tiny ? n : 2 * n), rbytes = (size_t)(tiny ? 2 * n : 4 * n);
     // Pinned host buffers are mapped into the device's address space (UVA): the step kernel reads the
-    // actions and writes the result words over the host link itself -- 2 + 4 bytes per sim in full
-    // 64 / 128-byte warp transactions -- and no copy is enqueued at all.  Pageable buffers are staged.
+    // actions and writes the result words over the host link itself -- 2 + 4 (tiny: 1 + 2) bytes per sim in
+    // full 64 / 128-byte warp transactions -- and no copy is enqueued at all.  Pageable buffers are staged.
     const unsigned char *m_act = (const unsigned char *)mapped_alias(actions);
     unsigned *m_res = (unsigned *)mapped_alias(results);
     if (m_act && m_res) {
         const int rc = launch_step(h, nullptr, nullptr, nullptr, nullptr, nullptr, s, nullptr, nullptr, nullptr, nullptr, 0,
-                                   m_act, m_res);
+                                   m_act, m_res, 0, -1, tiny);
         if (rc) return rc;
         if (sync) CUDA_TRY(cudaStreamSynchronize(s));
         return GW_OK;
     }
-    if (!sync) return fail(GW_E_INVALID, "gw_step_host_compact_async needs pinned host buffers");
-    // staging: uint8 actions [n][2] in the action staging area, uint32 results [n] in the obs area
+    if (!sync) return fail(GW_E_INVALID, "the asynchronous / population calls need pinned host buffers");
+    // staging: the actions in the action staging area, the result words in the obs area
     unsigned char *d_act = (unsigned char *)h->d_dev;
     unsigned *d_res = (unsigned *)h->d_obs;
-    CUDA_TRY(cudaMemcpyAsync(d_act, actions, (size_t)(2 * n), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_act, actions, abytes, cudaMemcpyHostToDevice, s));
     const int rc = launch_step(h, nullptr, nullptr, nullptr, nullptr, nullptr, s, nullptr, nullptr, nullptr, nullptr, 0,
-                               d_act, d_res);
+                               d_act, d_res, 0, -1, tiny);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(results, d_res, (size_t)(4 * n), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(results, d_res, rbytes, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return GW_OK;
 }
@@ -2531,8 +2548,28 @@ struct ManyStreams {
 static ManyStreams g_many[64];
 static std::mutex g_many_mutex;
 
+static int step_host_many(gw_handle *const *handles, int32_t n_handles, const uint8_t *const *actions,
+                          void *const *results, void *stream, int tiny);
+
 int gw_step_host_compact_many(gw_handle *const *handles, int32_t n_handles, const uint8_t *const *actions,
                               uint32_t *const *results, void *stream)
+{
+    return step_host_many(handles, n_handles, actions, (void *const *)results, stream, 0);
+}
+
+int gw_step_host_tiny(gw_handle *h, const uint8_t *actions, uint16_t *results, void *stream)
+{
+    return step_host_compact(h, actions, results, stream, true, 1);
+}
+
+int gw_step_host_tiny_many(gw_handle *const *handles, int32_t n_handles, const uint8_t *const *actions,
+                           uint16_t *const *results, void *stream)
+{
+    return step_host_many(handles, n_handles, actions, (void *const *)results, stream, 1);
+}
+
+static int step_host_many(gw_handle *const *handles, int32_t n_handles, const uint8_t *const *actions,
+                          void *const *results, void *stream, int tiny)
 {
     if (!handles || !actions || !results || n_handles < 1) return fail(GW_E_INVALID, "bad argument");
     for (int k = 0; k < n_handles; ++k) {
@@ -2575,7 +2612,7 @@ int gw_step_host_compact_many(gw_handle *const *handles, int32_t n_handles, cons
         CUDA_TRY(cudaEventRecord(ms->fork, s));
         for (int k = 0; k < lanes; ++k) CUDA_TRY(cudaStreamWaitEvent(ms->s[k], ms->fork, 0));
         for (int k = 0; k < n_handles; ++k) {
-            const int rc = step_host_compact(handles[k], actions[k], results[k], (void *)ms->s[k % lanes], false);
+            const int rc = step_host_compact(handles[k], actions[k], results[k], (void *)ms->s[k % lanes], false, tiny);
             if (rc) return rc;
         }
         for (int k = 0; k < lanes; ++k) {
@@ -2592,7 +2629,7 @@ int gw_step_host_compact_many(gw_handle *const *handles, int32_t n_handles, cons
     bool cacheable = use_graph;
     unsigned long long key = 1469598103934665603ull;
     auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
-    mix((unsigned long long)n_handles); mix((unsigned long long)(uintptr_t)s);
+    mix((unsigned long long)n_handles); mix((unsigned long long)(uintptr_t)s); mix((unsigned long long)tiny);
     for (int k = 0; k < n_handles; ++k) {
         if (handles[k]->stamps) cacheable = false;
         mix((unsigned long long)(uintptr_t)handles[k]); mix(handles[k]->generation);

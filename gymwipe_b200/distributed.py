@@ -22,6 +22,38 @@ def shard_range(total_envs, rank, world_size):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def bind_to_gpu_numa(device_index):
+    """
+    Restricts this process to the CPUs next to its GPU (NVML's CPU affinity of the device, intersected with the
+    CPUs the process may use): host buffers pinned AFTER the call are first touched -- hence allocated -- on the
+    GPU's own NUMA node, so the kernels' in-place reads / writes of host memory (``gw_step_host_compact*``) do not
+    cross the socket interconnect.  Matters when several ranks of one box drive the host link at once.  Returns the
+    CPU list, or None if NVML / the affinity is unavailable (nothing is changed then).  ``GYMWIPE_B200_NO_BIND=1``
+    switches it off.
+    """
+    if os.environ.get("GYMWIPE_B200_NO_BIND") or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + uuid)
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        near = {c for c in range(ncpu) if (mask[c // 64] >> (c % 64)) & 1}
+        cpus = sorted(near & os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def init_from_env(backend=None):
     """Initialise ``torch.distributed`` from torchrun's environment; returns (rank, world, local_rank)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))

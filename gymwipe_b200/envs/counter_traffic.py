@@ -507,6 +507,34 @@ class CounterTrafficEnv(BaseEnv):
         if rc:
             N.check(rc)
 
+    def step_host_tiny(self, actions, results):
+        """
+        The smallest wire format (``gw_step_host_tiny``): ``actions`` a pinned uint8 tensor / array ``[n_sims]``
+        with ``device << 7 | duration`` (:meth:`pack_tiny_actions`), ``results`` a pinned int16 / uint16 buffer of
+        ``n_sims`` words that receives ``(obs - COUNTER_BOUND) & 0xFF | (reward + 16) << 8 | done << 13``.
+        1 byte in, 2 bytes out per sim; :meth:`unpack_tiny` for typed tensors.
+        """
+        a = actions.data_ptr() if torch.is_tensor(actions) else actions.ctypes.data
+        r = results.data_ptr() if torch.is_tensor(results) else results.ctypes.data
+        rc = self._lib.gw_step_host_tiny(self._handle, a, r, torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            N.check(rc)
+
+    @staticmethod
+    def pack_tiny_actions(device, duration):
+        """uint8 ``device << 7 | duration`` from integer tensors / arrays (device in {0, 1}, duration < 128)."""
+        d = torch.as_tensor(device).to(torch.int32)
+        return ((d << 7) | torch.as_tensor(duration).to(torch.int32)).to(torch.uint8)
+
+    @staticmethod
+    def unpack_tiny(results):
+        """``(obs int64, reward float64, done bool)`` from the 16-bit words of :meth:`step_host_tiny`."""
+        r = results if torch.is_tensor(results) else torch.from_numpy(results)
+        w = r.view(torch.int16).to(torch.int64) & 0xFFFF
+        diff = ((w & 0xFF) ^ 0x80) - 0x80                       # sign-extend the low byte
+        assert not bool(((w >> 15) & 1).any()), "an observation did not fit the 8-bit difference"
+        return diff + 65536, (((w >> 8) & 31) - 16).to(torch.float64), ((w >> 13) & 1).bool()
+
     @staticmethod
     def unpack_compact(results):
         """``(obs int64, reward float64, done bool)`` from the packed words of :meth:`step_host_compact`."""

@@ -87,6 +87,15 @@ class EnvPopulation:
         if rc:
             N.check(rc)
 
+    def step_host_tiny(self, action_ptrs, result_ptrs):
+        """:meth:`step_host_compact` in the smallest wire format (``gw_step_host_tiny_many``): pinned uint8 ``[n]``
+        action bytes (``device << 7 | duration``) and uint16 ``[n]`` result words per batch
+        (``CounterTrafficEnv.unpack_tiny``)."""
+        rc = self._lib.gw_step_host_tiny_many(self._handles, len(self.envs), action_ptrs, result_ptrs,
+                                              torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            N.check(rc)
+
     def close(self):
         for e in self.envs[1:]:
             e.share_stats(None)

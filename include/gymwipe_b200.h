@@ -216,6 +216,24 @@ int gw_step_host_compact_async(gw_handle *h, const uint8_t *actions, uint32_t *r
  * while the next batch computes.  From the caller's point of view everything is ordered on `stream`. */
 int gw_step_host_compact_many(gw_handle *const *handles, int32_t n_handles, const uint8_t *const *actions,
                               uint32_t *const *results, void *stream);
+/* The smallest wire format of a CounterTrafficEnv step, for callers bound by the host link (several GPUs of one
+ * box stepping from host-resident actors share it): `actions` = uint8 [n_sims], one byte per sim = device << 7 |
+ * duration (Discrete(2) x Discrete(MAX_ASSIGN_DURATION <= 128), envs/core.py:39-42); `results` = uint16 [n_sims]:
+ *     bits  0..7   observation - COUNTER_BOUND as a signed byte: the interpreter's latestDifference
+ *                  (counter_traffic.py:85-94: receivedValues[0] - receivedValues[1], each 0 or COUNTER_BYTE_LENGTH)
+ *     bits  8..12  reward + 16
+ *     bit  13      done
+ *     bit  15      the difference did not fit a signed byte (cannot happen with the reference's value 2)
+ * 1 byte in, 2 bytes out per sim and step; same in-place access of pinned buffers, same staging of pageable
+ * ones, same restrictions as gw_step_host_compact; gw_step_host_tiny_many = gw_step_host_compact_many with
+ * these layouts. */
+int gw_step_host_tiny(gw_handle *h, const uint8_t *actions, uint16_t *results, void *stream);
+int gw_step_host_tiny_many(gw_handle *const *handles, int32_t n_handles, const uint8_t *const *actions,
+                           uint16_t *const *results, void *stream);
+#define GW_TINY_ACTION(device, duration) ((uint8_t)(((device) << 7) | (duration)))
+#define GW_TINY_OBS(w)    ((int32_t)(int8_t)((w) & 0xFFu) + 65536)
+#define GW_TINY_REWARD(w) ((int32_t)(((w) >> 8) & 31u) - 16)
+#define GW_TINY_DONE(w)   ((int32_t)(((w) >> 13) & 1u))
 #define GW_COMPACT_OBS(w)    ((int32_t)((w) & 0x1FFFFu))
 #define GW_COMPACT_REWARD(w) ((int32_t)(((w) >> 17) & 31u) - 16)
 #define GW_COMPACT_DONE(w)   ((int32_t)(((w) >> 22) & 1u))

@@ -127,6 +127,46 @@ def test_population_host_step_equals_single_batch_steps():
     pop.close()
 
 
+def test_tiny_wire_format_equals_the_device_step():
+    """gw_step_host_tiny / gw_step_host_tiny_many: 1 action byte in (device << 7 | duration), one 16-bit result word
+    out -- the same observations, rewards and done flags as the device-resident step; pinned and pageable buffers."""
+    import gymwipe_b200
+    from gymwipe_b200.envs import EnvPopulation
+    from gymwipe_b200.envs.counter_traffic import CounterTrafficEnv
+    n, nb, T = 640, 3, 40
+    rs = np.random.RandomState(31)
+    pop = EnvPopulation([gymwipe_b200.make('CounterTraffic-v0', num_envs=n, env_id_offset=k * n, strict=False) for k in range(nb)])
+    one = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, strict=False)
+    ref = [gymwipe_b200.make('CounterTraffic-v0', num_envs=n, env_id_offset=k * n, strict=False) for k in range(nb)]
+    pop.reset(); one.reset()
+    for e in ref:
+        e.reset()
+    acts = [torch.zeros(n, dtype=torch.uint8).pin_memory() for _ in range(nb)]
+    res = [torch.empty(n, dtype=torch.int16).pin_memory() for _ in range(nb)]
+    a_ptrs, r_ptrs = EnvPopulation.pointer_array(acts), EnvPopulation.pointer_array(res)
+    pageable_res = np.empty(n, dtype=np.uint16)
+    seen = set()
+    for t in range(T):
+        dev = [rs.randint(0, 2, n) for _ in range(nb)]
+        dur = [rs.randint(0, 20, n) for _ in range(nb)]
+        for k in range(nb):
+            acts[k].copy_(CounterTrafficEnv.pack_tiny_actions(dev[k], dur[k]))
+        pop.step_host_tiny(a_ptrs, r_ptrs)
+        one.step_host_tiny(acts[0].numpy().copy(), pageable_res)           # pageable buffers: staged copies
+        for k in range(nb):
+            o, r, d, _ = ref[k].step({"device": torch.as_tensor(dev[k].astype(np.int32)).cuda(),
+                                      "duration": torch.as_tensor(dur[k].astype(np.int32)).cuda()})
+            oo, rr, dd = CounterTrafficEnv.unpack_tiny(res[k])
+            assert torch.equal(oo, o.cpu()) and torch.equal(rr, r.cpu()) and torch.equal(dd, d.cpu()), (t, k)
+            seen.update(int(v) for v in oo.unique())
+            if k == 0:
+                po, pr, pd = CounterTrafficEnv.unpack_tiny(pageable_res.view(np.int16))
+                assert torch.equal(po, o.cpu()) and torch.equal(pr, r.cpu())
+    assert seen == {65534, 65536, 65538}                                    # both signs of the difference occurred
+    pop.check(); one.check()
+    pop.close()
+
+
 def test_population_host_step_replays_its_cached_graph():
     """The same call (same handles, same pinned buffers) is captured once and replayed: the replay reads the
     buffers' NEW contents; a change of the handles (gw_share_stats) or of the buffers takes a fresh capture; more
