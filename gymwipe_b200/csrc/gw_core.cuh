@@ -726,6 +726,10 @@ inline void finish_params(Params &P)
     }
 }
 
+// the fp64 divisions that the verified shortcuts replace: out of line, so that their ~60 instructions each do not
+// sit between the hot instructions of every call site (the kernels are instruction-fetch bound)
+GW_HD_COLD double div_cold(double x, double y) { return x / y; }
+
 // duration of `bytes` bytes on air at the data rate (physical.py:244-250): (bytes * 8) / dataRate
 GW_HD double airtime_of(const Params &P, int bytes)
 {
@@ -735,7 +739,7 @@ GW_HD double airtime_of(const Params &P, int bytes)
         const double q0 = x * P.rateInv;
         return fma(fma(-q0, P.dataRate, x), P.rateInv, q0);     // == x / dataRate, verified in finish_params
     }
-    return x / P.dataRate;
+    return div_cold(x, P.dataRate);
 }
 
 // SimplePhy._decide: round(bitErrorSum) / totalBits <= maxCorrectableBer (simple_stack.py:274-277).
@@ -747,7 +751,7 @@ GW_HD bool within_max_ber(const Params &P, double errSum, double totalBits)
 {
     const double x = rint(errSum);
     if (P.berMult != 0.0) return x * P.berMult <= totalBits;
-    return x / totalBits <= P.maxBer;
+    return div_cold(x, totalBits) <= P.maxBer;
 }
 
 template <int D, int NS, int NJ, class ST>

@@ -2544,6 +2544,9 @@ struct ManyStreams {
     bool ready;
     std::vector<ManyGraph> graphs;      // captured population steps (gw_step_host_compact_many), keyed by the call
     unsigned long long clock;
+    std::mutex call;                    // one population call per device at a time: the side streams, the fork / join
+                                        // events and the graph cache are per device (concurrent callers would
+                                        // contend for the same GPU anyway)
 };
 static ManyStreams g_many[64];
 static std::mutex g_many_mutex;
@@ -2600,6 +2603,7 @@ static int step_host_many(gw_handle *const *handles, int32_t n_handles, const ui
         }
     }
     const int lanes = n_handles < MANY_STREAMS ? n_handles : MANY_STREAMS;
+    std::lock_guard<std::mutex> call_lock(ms->call);
     if (s == nullptr) {
         // the legacy default stream: the call runs on a stream of the library's own, ordered behind what the
         // default stream holds; it returns synchronised, so later work on the default stream is ordered behind it
