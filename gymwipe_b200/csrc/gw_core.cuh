@@ -241,7 +241,9 @@ struct Sim {
     static constexpr int kD = D, kNS = NS, kNJ = NJ, kRrm = NS;
 #if !defined(GW_NO_ROLL)
     static constexpr int kUnrollD = ST::roll ? 1 : D;                   // see GW_UNROLL_D
+    static constexpr int kUnrollIO = (ST::roll && NJ > 0) ? 1 : D;      // state load / store / flag loops of the kernels
 #else
+    static constexpr int kUnrollIO = D;
     static constexpr int kUnrollD = D;
 #endif
     static constexpr int NJa = NJ > 0 ? NJ : 1;

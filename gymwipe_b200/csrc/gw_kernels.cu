@@ -233,7 +233,7 @@ __device__ __forceinline__ unsigned long long hi_q(uint4 v) { return ((unsigned 
 template <int D, int NS, int NJ, class ST>
 __device__ __forceinline__ void unpack_flags(Sim<D, NS, NJ, ST> &s, unsigned a, unsigned b)
 {
-#pragma unroll
+#pragma unroll (Sim<D, NS, NJ, ST>::kUnrollIO)
     for (int d = 0; d < D; ++d) {
         s.sphase[d] = (a >> (3 * d)) & 7;
         s.rxOf[d] = (int)((a >> (12 + 3 * d)) & 7) - 1;
@@ -259,7 +259,7 @@ template <int D, int NS, int NJ, class ST>
 __device__ __forceinline__ bool sim_busy(const Sim<D, NS, NJ, ST> &s)
 {
     bool busy = false;
-#pragma unroll
+#pragma unroll (Sim<D, NS, NJ, ST>::kUnrollIO)
     for (int d = 0; d < D; ++d) busy |= (s.sphase[d] != S_IDLE) | (s.rxOf[d] >= 0);
 #pragma unroll
     for (int k = 0; k < NS; ++k) busy |= (s.mac[k] != MAC_NONE) | (s.wPend[k] != 0);
@@ -270,7 +270,7 @@ template <int D, int NS, int NJ, class ST>
 __device__ __forceinline__ void pack_flags(const Sim<D, NS, NJ, ST> &s, bool busy, unsigned &a, unsigned &b)
 {
     a = 0; b = 0;
-#pragma unroll
+#pragma unroll (Sim<D, NS, NJ, ST>::kUnrollIO)
     for (int d = 0; d < D; ++d) {
         a |= (unsigned)s.sphase[d] << (3 * d);
         a |= (unsigned)(s.rxOf[d] + 1) << (12 + 3 * d);
@@ -341,7 +341,7 @@ __device__ __forceinline__ bool load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs 
     }
     const bool busy = (u0.z >> 31) & 1;
     if (busy) {
-#pragma unroll
+#pragma unroll (Sim<D, NS, NJ, ST>::kUnrollIO)
         for (int d = 0; d < D; ++d) {
             uint4 c = ld_chunk(st.cold, n, d * C_PER_DEV + C_EV, i);
             s.tEv[d] = lo_d(c); s.tC[d] = hi_d(c);
@@ -350,10 +350,10 @@ __device__ __forceinline__ bool load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs 
             c = ld_chunk(st.cold, n, d * C_PER_DEV + C_RX, i);
             s.ber[d] = lo_d(c); s.err[d] = hi_d(c);
             c = ld_chunk(st.cold, n, d * C_PER_DEV + C_RT, i);
-            s.tReset[d] = lo_d(c); s.segT0[d] = WITH_SEG ? hi_d(c) : 0.0;
+            s.tReset[d] = lo_d(c); set_at(s.segT0, d, WITH_SEG ? hi_d(c) : 0.0);
             c = ld_chunk(st.cold, n, d * C_PER_DEV + C_U, i);
             s.sEv[d] = c.x; s.sC[d] = c.y; s.cmdPay[d] = (int)c.z;
-            if (FULL && st.plant) { c = ld_chunk(st.cold, n, d * C_PER_DEV + C_V, i); s.txVal[d] = lo_d(c); } else s.txVal[d] = 0;
+            if (FULL && st.plant) { c = ld_chunk(st.cold, n, d * C_PER_DEV + C_V, i); set_at(s.txVal, d, lo_d(c)); } else set_at(s.txVal, d, 0.0);
         }
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
@@ -361,10 +361,10 @@ __device__ __forceinline__ bool load_sim(Sim<D, NS, NJ, ST> &s, const StatePtrs 
             s.stopW[k] = lo_d(c); s.sW[k] = c.z;
         }
     } else {
-#pragma unroll
+#pragma unroll (Sim<D, NS, NJ, ST>::kUnrollIO)
         for (int d = 0; d < D; ++d) {
             s.tEv[d] = 0; s.tC[d] = 0; s.txStart[d] = 0; s.tStop[d] = 0; s.ber[d] = 0; s.err[d] = 0;
-            s.tReset[d] = 0; s.segT0[d] = 0; s.sEv[d] = 0; s.sC[d] = 0; s.cmdPay[d] = 0; s.txVal[d] = 0;
+            s.tReset[d] = 0; set_at(s.segT0, d, 0.0); s.sEv[d] = 0; s.sC[d] = 0; s.cmdPay[d] = 0; set_at(s.txVal, d, 0.0);
         }
 #pragma unroll
         for (int k = 0; k < NS; ++k) { s.stopW[k] = 0; s.sW[k] = 0; }
@@ -417,15 +417,15 @@ __device__ __forceinline__ void store_sim(const Sim<D, NS, NJ, ST> &s, const Sta
         w[3] += s.ties;
     }
     if (busy) {
-#pragma unroll
+#pragma unroll (Sim<D, NS, NJ, ST>::kUnrollIO)
         for (int d = 0; d < D; ++d) {
             st_chunk(st.cold, n, d * C_PER_DEV + C_EV, i, pack_dd(s.tEv[d], s.tC[d]));
             st_chunk(st.cold, n, d * C_PER_DEV + C_TX, i, pack_dd(s.txStart[d], s.tStop[d]));
             st_chunk(st.cold, n, d * C_PER_DEV + C_RX, i, pack_dd(s.ber[d], s.err[d]));
-            st_chunk(st.cold, n, d * C_PER_DEV + C_RT, i, pack_dd(s.tReset[d], WITH_SEG ? s.segT0[d] : 0.0));
+            st_chunk(st.cold, n, d * C_PER_DEV + C_RT, i, pack_dd(s.tReset[d], WITH_SEG ? get_at(s.segT0, d) : 0.0));
             uint4 c; c.x = s.sEv[d]; c.y = s.sC[d]; c.z = (unsigned)s.cmdPay[d]; c.w = 0;
             st_chunk(st.cold, n, d * C_PER_DEV + C_U, i, c);
-            if (FULL && st.plant) st_chunk(st.cold, n, d * C_PER_DEV + C_V, i, pack_dd(s.txVal[d], 0.0));
+            if (FULL && st.plant) st_chunk(st.cold, n, d * C_PER_DEV + C_V, i, pack_dd(get_at(s.txVal, d), 0.0));
         }
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
