@@ -71,6 +71,26 @@ class GridConfig(C.Structure):
                 ("move_interval", C.c_double), ("max_moves", C.c_int32)]
 
 
+GW_GENBAND_MAX_SENDERS, GW_GENBAND_MAX_PHY_SENDERS = 8, 16
+GW_GENBAND_MAX_DEVICES = GW_GENBAND_MAX_SENDERS + 1 + GW_GENBAND_MAX_PHY_SENDERS
+(GW_GENBAND_FIELD_NOW, GW_GENBAND_FIELD_DELIVERED, GW_GENBAND_FIELD_RECEIVED, GW_GENBAND_FIELD_TRANSMISSIONS,
+ GW_GENBAND_FIELD_FAULT, GW_GENBAND_FIELD_RECEIVED_POWER, GW_GENBAND_FIELD_QUEUE_LENGTH, GW_GENBAND_FIELD_COUNTER,
+ GW_GENBAND_FIELD_TIES) = range(9)
+
+
+class GenBandConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("n_envs", C.c_int64), ("n_senders", C.c_int32), ("n_phy_senders", C.c_int32),
+                ("assignment_duration_factor", C.c_int32), ("max_assign_duration", C.c_int32),
+                ("per_env_positions", C.c_int32), ("frequency_hz", C.c_double), ("bandwidth_hz", C.c_double),
+                ("multiplicity", C.c_int32 * GW_GENBAND_MAX_SENDERS), ("payload_bytes", C.c_int32 * GW_GENBAND_MAX_SENDERS),
+                ("destination", C.c_int32 * GW_GENBAND_MAX_SENDERS), ("max_ticks", C.c_int32 * GW_GENBAND_MAX_SENDERS),
+                ("receive", C.c_int32 * GW_GENBAND_MAX_SENDERS), ("interval", C.c_double * GW_GENBAND_MAX_SENDERS),
+                ("phy_interval", C.c_double * GW_GENBAND_MAX_PHY_SENDERS), ("phy_delay", C.c_double * GW_GENBAND_MAX_PHY_SENDERS),
+                ("phy_power_dbm", C.c_double * GW_GENBAND_MAX_PHY_SENDERS),
+                ("phy_header_bytes", C.c_int32 * GW_GENBAND_MAX_PHY_SENDERS),
+                ("phy_payload_bytes", C.c_int32 * GW_GENBAND_MAX_PHY_SENDERS)]
+
+
 class NativeError(RuntimeError):
     def __init__(self, code, message):
         super().__init__("gymwipe_b200 native error %d: %s" % (code, message))
@@ -78,7 +98,7 @@ class NativeError(RuntimeError):
 
 
 def _sources():
-    return [os.path.join(CSRC, f) for f in ("gw_kernels.cu", "gw_core.cuh", "gw_pendulum.cuh", "gw_grid.cuh")] + [INCLUDE]
+    return [os.path.join(CSRC, f) for f in ("gw_kernels.cu", "gw_core.cuh", "gw_pendulum.cuh", "gw_grid.cuh", "gw_band.cuh")] + [INCLUDE]
 
 
 def needs_build():
@@ -161,6 +181,13 @@ _SIGNATURES = {
     "gw_grid_run_traced": (C.c_int, [_VP, C.c_double, _VP, _VP, C.c_int32, _VP]),
     "gw_grid_read": (C.c_int, [_VP, C.c_int, _VP, _VP]),
     "gw_grid_check": (C.c_int, [_VP, _VP]),
+    "gw_genband_create": (C.c_int, [C.POINTER(GenBandConfig), C.c_int, _VP, _VP, C.POINTER(_VP)]),
+    "gw_genband_destroy": (None, [_VP]),
+    "gw_genband_reset": (C.c_int, [_VP, _VP, _VP]),
+    "gw_genband_step": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "gw_genband_step_traced": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),
+    "gw_genband_read": (C.c_int, [_VP, C.c_int, _VP, _VP]),
+    "gw_genband_check": (C.c_int, [_VP, _VP]),
     "gw_policy_boltzmann": (C.c_int, [_VP, C.c_int32, C.c_int32, _VP, C.c_int64, C.c_float, C.c_double, C.c_double, C.c_double,
                                       C.c_uint64, C.c_uint64, C.c_int64, _VP, _VP, _VP, _VP, _VP]),
     "gw_max_correctable_ber": (C.c_double, [C.c_int, C.c_int]),

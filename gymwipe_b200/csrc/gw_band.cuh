@@ -1,0 +1,568 @@
+// gymwipe_b200 -- general band engine: bands beyond CounterTrafficEnv's 2 senders + RRM (+ 1 PHY-only sender)
+// template (the generalised scenario compiler).
+//
+// A band of up to kGenMaxSend MAC senders (SimpleNetworkDevice + a traffic process, any of them in MAC receive
+// mode or with a finite burst), ONE RRM (SimpleRrmDevice + CounterTrafficInterpreter) and up to kGenMaxJam PHY-only
+// periodic senders, all as RUN-TIME counts, stepped like the env: assignFrequencyBand(device, duration), then
+// runSimulation(assignSignal.eProcessed), then the interpreter's feedback (reference accounting, "mode R").
+//
+// Same method as the step kernel's core (gw_core.cuh): one band-sim per thread, the SimPy heap replaced by timed
+// event slots ordered by (time, creation number) -- per sender a traffic tick, a window time-out and a RECEIVE
+// time-out, per device one PHY event (slot start -> header end -> completion), per PHY-only sender a wake-up, the
+// RRM's guard time-out -- with the zero-delay event chains executed inline in SimPy's pop order.  Unlike the step
+// kernel nothing is unrolled or held in registers: every per-device array lives in the band-sim's state in global
+// memory ([field][index][sim]: consecutive threads touch consecutive words) and is indexed directly, queued packets
+// keep their sizes in an explicit ring, and the received-power changes are counted where they happen.  This is the
+// general engine, not the tuned one: the 2-sender + RRM template keeps its own kernels.
+//
+// Reference semantics (file:line under /root/reference):
+//   SimplePhy  (power bookkeeping, BER accounting, decider)  networking/simple_stack.py:77-286
+//   SimpleMac  (queue, assignment-window loop, receive mode)  networking/simple_stack.py:386-484
+//   SimpleRrmMac (announcement, guard slot)                   networking/simple_stack.py:527-561
+//   SimpleNetworkDevice receive loop / SimpleRrmDevice        networking/devices.py:66-111, 113-203
+//   Transmission / FrequencyBand.transmit                     networking/physical.py:224-290, 576-608
+//   SenderDevice.senderProcess, CounterTrafficInterpreter     envs/counter_traffic.py:53-61, 63-112 (the interpreter
+//       keeps one received value per device; its observation is receivedValues[0] - receivedValues[1])
+//   PHY-only periodic sender                                  tests/test_benchmark.py:20-50
+//
+// Plain C++ (no CUDA intrinsics): gw_kernels.cu includes it for the device, tests/hostsim for the host.
+#pragma once
+
+#include "gw_core.cuh"
+
+namespace gw {
+
+constexpr int kGenMaxSend = 8, kGenMaxJam = 16, kGenMaxDev = kGenMaxSend + 1 + kGenMaxJam;
+
+// band configuration, common to all band-sims of a handle; device order: senders, RRM, PHY-only senders
+struct GenBand {
+    int ns, nj, nd;
+    int maxDuration;                    // action space: duration in [0, maxDuration)
+    double thermal;
+    int mult[kGenMaxSend];
+    int payloadRule[kGenMaxSend];       // -1: byteSize = counter
+    int dest[kGenMaxSend];              // device index of the sender its packets are addressed to
+    int maxTicks[kGenMaxSend];          // 0: the traffic process runs forever; n: a burst of n ticks
+    int recv[kGenMaxSend];              // 1: MAC receive mode (SimpleNetworkDevice.receiving = True)
+    double interval[kGenMaxSend];
+    double jamInterval[kGenMaxJam], jamDelay[kGenMaxJam];
+    int jamHdr[kGenMaxJam], jamPay[kGenMaxJam];
+};
+
+// words of one band-sim's state
+GW_HD int gen_f64_words(int ns, int nj) { return 3 + 7 * (ns + 1 + nj) + 3 * ns + nj; }
+GW_HD int gen_i32_words(int ns, int nj) { return 14 + 7 * (ns + 1 + nj) + 12 * ns + 3 * nj + kQueueCap * ns; }
+
+// view of one band-sim: word w of the fp64 / int32 state at f[w * stride] / i[w * stride]
+struct GenView {
+    double *f;
+    int32_t *i;
+    long long stride;
+    const double *srx;                  // received power (mW), entry (receiver p, sender d) at srx[(p * nd + d) * srxStride]
+    long long srxStride;
+    int ns, nj, nd;
+    double *trace;                      // optional event trace (records of 8 doubles, as gw_core.cuh::trace_rec)
+    int ntrace, traceCap;
+
+#define GEN_F(name, base) GW_HD double &name(int k) const { return f[(long long)((base) + k) * stride]; }
+#define GEN_I(name, base) GW_HD int32_t &name(int k) const { return i[(long long)((base) + k) * stride]; }
+#define GEN_U(name, base) GW_HD uint32_t &name(int k) const { return ((uint32_t *)i)[(long long)((base) + k) * stride]; }
+    // scalars
+    GW_HD double &now() const { return f[0]; }
+    GW_HD double &tRrm() const { return f[stride]; }
+    GW_HD double &annSlots() const { return f[2 * stride]; }
+    // PHY, per device (names as in gw_core.cuh::Sim)
+    GEN_F(P, 3) GEN_F(tEv, 3 + nd) GEN_F(tStop, 3 + 2 * nd) GEN_F(tC, 3 + 3 * nd) GEN_F(ber, 3 + 4 * nd)
+    GEN_F(err, 3 + 5 * nd) GEN_F(tReset, 3 + 6 * nd)
+    // senders
+    GEN_F(tTick, 3 + 7 * nd) GEN_F(stopW, 3 + 7 * nd + ns) GEN_F(rxT, 3 + 7 * nd + 2 * ns)
+    // PHY-only senders
+    GEN_F(tJam, 3 + 7 * nd + 3 * ns)
+
+    enum : int { I_seq = 0, I_fault, I_ties, I_annDest, I_rrmPend, I_sRrm, I_assignDone, I_rv0, I_rv1, I_latestDiff,
+                 I_lastAbsDiff, I_done, I_nTx, I_pad, kScalars };
+    GW_HD int32_t &sc(int w) const { return i[(long long)w * stride]; }
+    GW_HD uint32_t &seq() const { return ((uint32_t *)i)[(long long)I_seq * stride]; }
+    GEN_I(sphase, 14) GEN_U(sEv, 14 + nd) GEN_U(sC, 14 + 2 * nd) GEN_I(cmdPay, 14 + 3 * nd) GEN_I(rxOf, 14 + 4 * nd)
+    GEN_I(rxSec, 14 + 5 * nd) GEN_U(txSeq, 14 + 6 * nd)
+    GEN_U(sTick, 14 + 7 * nd) GEN_I(qh, 14 + 7 * nd + ns) GEN_I(qn, 14 + 7 * nd + 2 * ns) GEN_I(mac, 14 + 7 * nd + 3 * ns)
+    GEN_I(wDone, 14 + 7 * nd + 4 * ns) GEN_I(wPend, 14 + 7 * nd + 5 * ns) GEN_U(sW, 14 + 7 * nd + 6 * ns)
+    GEN_U(rxS, 14 + 7 * nd + 7 * ns) GEN_U(nDeliv, 14 + 7 * nd + 8 * ns) GEN_U(nRecv, 14 + 7 * nd + 9 * ns)
+    GEN_I(counter, 14 + 7 * nd + 10 * ns) GEN_U(ticksDone, 14 + 7 * nd + 11 * ns)
+    GEN_U(sJam, 14 + 7 * nd + 12 * ns) GEN_I(jamStage, 14 + 7 * nd + 12 * ns + nj) GEN_I(jamPending, 14 + 7 * nd + 12 * ns + 2 * nj)
+    GW_HD int32_t &ring(int k, int slot) const { return i[(long long)(14 + 7 * nd + 12 * ns + 3 * nj + k * kQueueCap + slot) * stride]; }
+#undef GEN_F
+#undef GEN_I
+#undef GEN_U
+    GW_HD double rp(int p, int d) const { return srx[(long long)(p * nd + d) * srxStride]; }
+};
+
+static_assert(GenView::kScalars == 14, "scalar block of the int32 state");
+
+GW_HD void gen_rec(GenView &v, int kind, double t, int dev, double x0, double x1, double x2, double x3)
+{
+    if (v.trace == nullptr) return;
+    if (v.ntrace < v.traceCap) {
+        double *r = v.trace + (long long)v.ntrace * 8;
+        r[0] = kind; r[1] = t; r[2] = dev; r[3] = x0; r[4] = x1; r[5] = x2; r[6] = x3; r[7] = 0;
+    }
+    v.ntrace += 1;
+}
+
+// received-power table of a geometry: pos [nd][2], power [nd] (dBm) -> srx [nd * nd] with the given stride
+// (FsplAttenuation._update, attenuation_models.py:28-36; dbmToMilliwatts(power - attenuation), simple_stack.py:111)
+GW_HD void gen_power_table(int nd, const double *pos, const double *power, double frequency, double *srx, long long stride)
+{
+    for (int p = 0; p < nd; ++p)
+        for (int d = 0; d < nd; ++d) {
+            double rp = 0.0;
+            if (p != d) rp = rx_power_mw(power[d], fspl_db(pos[2 * p], pos[2 * p + 1], pos[2 * d], pos[2 * d + 1], frequency));
+            srx[(long long)(p * nd + d) * stride] = rp;
+        }
+}
+
+// construction-time state (counter_traffic.py:114-133; the harness scenario of N senders): process Initialize events
+// in construction order -- senders, then PHY-only senders --, then `receiving = True` in sender order (devices.py:77-84)
+GW_HD void gen_init(GenView &v, const GenBand &B)
+{
+    const int ns = v.ns, nj = v.nj, nd = v.nd;
+    v.now() = 0.0; v.tRrm() = 0.0; v.annSlots() = 0.0;
+    for (int w = 0; w < GenView::kScalars; ++w) v.sc(w) = 0;
+    for (int p = 0; p < nd; ++p) {
+        v.P(p) = B.thermal; v.tEv(p) = 0; v.tStop(p) = 0; v.tC(p) = 0; v.ber(p) = 0; v.err(p) = 0; v.tReset(p) = 0;
+        v.sphase(p) = S_IDLE; v.sEv(p) = 0; v.sC(p) = 0; v.cmdPay(p) = 0; v.rxOf(p) = -1; v.rxSec(p) = 0; v.txSeq(p) = 0;
+    }
+    for (int k = 0; k < ns; ++k) {
+        v.tTick(k) = 0.0; v.sTick(k) = v.seq()++;
+        v.stopW(k) = 0; v.qh(k) = 0; v.qn(k) = 0; v.mac(k) = MAC_NONE; v.wDone(k) = 0; v.wPend(k) = 0; v.sW(k) = 0;
+        v.nDeliv(k) = 0; v.nRecv(k) = 0; v.counter(k) = 1; v.ticksDone(k) = 0;
+        for (int q = 0; q < kQueueCap; ++q) v.ring(k, q) = 0;
+    }
+    for (int j = 0; j < nj; ++j) { v.tJam(j) = 0.0; v.sJam(j) = v.seq()++; v.jamStage(j) = 0; v.jamPending(j) = 0; }
+    for (int k = 0; k < ns; ++k) {
+        if (B.recv[k]) { v.rxT(k) = 0.0; v.rxS(k) = v.seq()++; }
+        else { v.rxT(k) = (double)INFINITY; v.rxS(k) = 0; }
+    }
+}
+
+// CounterTrafficEnv.reset (counter_traffic.py:135-144): sender counters := 0, interpreter reset; time, queues
+// (with the sizes their packets were enqueued with) and PHY state stay
+GW_HD void gen_reset(GenView &v)
+{
+    for (int k = 0; k < v.ns; ++k) v.counter(k) = 0;
+    v.sc(GenView::I_latestDiff) = 0; v.sc(GenView::I_lastAbsDiff) = 0; v.sc(GenView::I_rv0) = 0; v.sc(GenView::I_rv1) = 0;
+    v.sc(GenView::I_done) = 0;
+}
+
+// SimpleMac.networkInHandler for a Packet (simple_stack.py:463-471): deque(maxlen = 100) drops the oldest
+GW_HD void gen_enqueue(GenView &v, int k, int size)
+{
+    int h = v.qh(k), n = v.qn(k);
+    if (n == kQueueCap) { h = h + 1 == kQueueCap ? 0 : h + 1; n -= 1; }
+    int slot = h + n; if (slot >= kQueueCap) slot -= kQueueCap;
+    v.ring(k, slot) = size;
+    v.qh(k) = h; v.qn(k) = n + 1;
+}
+
+// `c` ticks of sender k's traffic process at once (SenderDevice.senderProcess, counter_traffic.py:53-61): per tick
+// `mult` packets of byteSize = counter (or the fixed size), counter += 1 up to COUNTER_BOUND; only the last 100
+// packets of the batch can survive in the queue
+GW_HD void gen_ticks(GenView &v, const GenBand &B, int k, uint32_t c)
+{
+    const int mult = B.mult[k], rule = B.payloadRule[k];
+    const int c0 = v.counter(k);
+    const long long M = (long long)c * mult;
+    long long j = M > kQueueCap ? M - kQueueCap : 0;
+    long long tick = j / mult;
+    int inTick = (int)(j - tick * mult);
+    for (; j < M; ++j) {
+        const long long cv = (long long)c0 + tick;
+        const int size = rule >= 0 ? rule : (cv > kCounterBound ? kCounterBound : (int)cv);
+        gen_enqueue(v, k, size);
+        if (++inTick == mult) { inTick = 0; ++tick; }
+    }
+    const long long c1 = (long long)c0 + c;
+    v.counter(k) = c1 > kCounterBound ? kCounterBound : (int)c1;
+    v.ticksDone(k) += c;
+}
+
+// Silent ticks of sender k strictly before (tEnd, qEnd): the tick times are accumulated with the reference's fp64
+// additions, one per tick (counter_traffic.py:61); see gw_core.cuh::silent_ticks
+GW_HD void gen_silent_ticks(GenView &v, const GenBand &B, int k, double tEnd, uint32_t qEnd)
+{
+    double t = v.tTick(k);
+    if (!before(t, v.sTick(k), tEnd, qEnd)) return;
+    const double interval = B.interval[k];
+    uint32_t c = 0;
+    do {
+        t = t + interval;
+        ++c;
+    } while (t < tEnd);
+    v.sc(GenView::I_ties) += (t == tEnd) ? 1 : 0;       // exact tie of independent events (diagnostic)
+    v.tTick(k) = t;
+    gen_ticks(v, B, k, c);
+    v.seq() += c;
+    v.sTick(k) = v.seq() - 1u;
+}
+
+// does sender k's tick go through the transition function?  (a MAC that waits for a packet wakes up; the last tick
+// of a burst ends the process)
+GW_HD bool gen_tick_wakes(const GenView &v, const GenBand &B, int k)
+{
+    return B.maxTicks[k] != 0 || v.mac(k) == MAC_WAIT_COND;
+}
+
+// earliest (time, creation number) among the timed slots; silent ticks in front of it are applied on the way
+GW_HD Event gen_next_event(GenView &v, const GenBand &B)
+{
+    const int ns = v.ns, nj = v.nj, nd = v.nd;
+    Event e;
+    e.kind = EV_NONE; e.idx = 0; e.t = INFINITY; e.seq = 0;
+#define GEN_CONSIDER(T, SQ, K, I)                                                       \
+    do {                                                                                \
+        const double t_ = (T);                                                          \
+        const uint32_t q_ = (SQ);                                                       \
+        if (e.kind == EV_NONE || before(t_, q_, e.t, e.seq)) {                          \
+            e.t = t_; e.seq = q_; e.kind = (K); e.idx = (I);                            \
+        }                                                                               \
+    } while (0)
+    for (int j = 0; j < nj; ++j) GEN_CONSIDER(v.tJam(j), v.sJam(j), EV_JAM, j);
+    for (int d = 0; d < nd; ++d)
+        if (v.sphase(d) >= S_SLOT) GEN_CONSIDER(v.tEv(d), v.sEv(d), EV_PHY, d);
+    for (int k = 0; k < ns; ++k) {
+        if (v.wPend(k)) GEN_CONSIDER(v.stopW(k), v.sW(k), EV_W, k);
+        if (B.recv[k]) GEN_CONSIDER(v.rxT(k), v.rxS(k), EV_RXTO, k);
+        if (gen_tick_wakes(v, B, k) && v.tTick(k) < (double)INFINITY) GEN_CONSIDER(v.tTick(k), v.sTick(k), EV_TICK, k);
+    }
+    if (v.sc(GenView::I_rrmPend)) GEN_CONSIDER(v.tRrm(), (uint32_t)v.sc(GenView::I_sRrm), EV_RRM, 0);
+#undef GEN_CONSIDER
+    if (e.kind == EV_NONE) return e;
+    // ticks of different senders touch only their own sender's queue, so the senders are advanced one after the other
+    for (int k = 0; k < ns; ++k)
+        if (!gen_tick_wakes(v, B, k)) gen_silent_ticks(v, B, k, e.t, e.seq);
+    return e;
+}
+
+// SimplePhy._updateBitErrorRate (simple_stack.py:161-173)
+GW_HD void gen_update_ber(GenView &v, const Params &P, int p)
+{
+    const int e = v.rxOf(p);
+    if (e < 0) return;
+    const double S = v.rp(p, e);
+    const double N = v.P(p) - S;
+    if (!(S >= 0) || !(N >= 0)) { v.sc(GenView::I_fault) = FAULT_REF_ASSERT; return; }     // simple_stack.py:168-169
+    const double b = ber_bpsk_mw_cold(S, N, P.tenLog10BitRate, P.qDen);
+    v.ber(p) = b;
+    gen_rec(v, REC_BER, v.now(), p, b, 0.0, 0.0, 0.0);
+}
+
+// SimplePhy._countBitErrors (simple_stack.py:180-188): duration from the last RESET (appendix B #5)
+GW_HD void gen_count(GenView &v, const Params &P, int p)
+{
+    const double duration = v.now() - v.tReset(p);
+    const double bitErrors = v.ber(p) * duration * P.bitRate;
+    v.err(p) += bitErrors;
+}
+
+// _nReceivedPowerChanges.trigger(delta): the power sum, then the running reception (simple_stack.py:81-86, 223-233)
+GW_HD void gen_power_change(GenView &v, const Params &P, int p, double delta, bool completingOwn)
+{
+    v.P(p) += delta;
+    const int e = v.rxOf(p);
+    if (e < 0 || delta == 0.0) return;
+    gen_count(v, P, p);
+    const bool completed = v.now() >= v.tStop(e);
+    if (completed) return;
+    // `if not t.completed: _updateBitErrorRate(t)` with the power entry of its own transmission already popped:
+    // the reference raises KeyError (appendix B #12)
+    if (completingOwn) { v.sc(GenView::I_fault) = FAULT_REF_KEYERROR; return; }
+    gen_update_ber(v, P, p);
+}
+
+GW_HD void gen_rx_clear(GenView &v, int p)
+{
+    v.rxOf(p) = -1; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = v.now();
+}
+
+GW_HD bool gen_decide(GenView &v, const Params &P, int p, int section, double totalBits)
+{
+    const bool ok = within_max_ber(P, v.err(p), totalBits);         // simple_stack.py:274-277
+    gen_rec(v, REC_DEC, v.now(), p, section, v.err(p), totalBits, ok ? 1.0 : 0.0);
+    return ok;
+}
+
+GW_HD void gen_begin_slot_wait(GenView &v, int d)
+{
+    // self._transmitting = True; yield SimMan.nextTimeSlot(TIME_SLOT_LENGTH)  (simple_stack.py:202-204, simtools.py:53)
+    v.tEv(d) = v.now() + (kSlot - fmod_slot(v.now()));
+    v.sEv(d) = v.seq()++;
+    v.sphase(d) = S_SLOT;
+}
+
+GW_HD void gen_phy_send_init(GenView &v, int d)
+{
+    if (v.rxOf(d) >= 0) v.sphase(d) = S_WAITRX;                     // yield self._nReceivingFinished.event
+    else gen_begin_slot_wait(v, d);
+}
+
+// one pass of the SimpleMac window loop body with a non-empty queue (simple_stack.py:417-434)
+GW_HD void gen_mac_try_send(GenView &v, const Params &P, int k)
+{
+    const int size = v.ring(k, v.qh(k));
+    const double timeLeft = v.stopW(k) - v.now();
+    const double txTime = airtime_of(P, kMacHdr + kNetHdr + size);
+    if (!(timeLeft > txTime)) { v.mac(k) = MAC_IDLE; return; }      // yield timeoutEvent
+    const int h = v.qh(k) + 1;
+    v.qh(k) = h == kQueueCap ? 0 : h;
+    v.qn(k) -= 1;
+    v.mac(k) = MAC_WAIT_TX;
+    v.cmdPay(k) = kNetHdr + size;
+    gen_phy_send_init(v, k);
+}
+
+// loop head of the window loop (simple_stack.py:408-416)
+GW_HD void gen_mac_loop_head(GenView &v, const Params &P, int k)
+{
+    if (v.wDone(k)) { v.mac(k) = MAC_NONE; return; }
+    if (v.qn(k) == 0) { v.mac(k) = MAC_WAIT_COND; return; }
+    gen_mac_try_send(v, P, k);
+}
+
+GW_HD int gen_hdr_bytes(const GenView &v, const GenBand &B, int d) { return d > v.ns ? B.jamHdr[d - v.ns - 1] : kMacHdr; }
+
+// transition function: one timed event (the structure of gw_core.cuh::apply_event with run-time device counts)
+GW_HD void gen_apply(GenView &v, const Params &P, const GenBand &B, const Event &ev)
+{
+    const int ns = v.ns, nd = v.nd, RRM = v.ns;
+    v.now() = ev.t;
+    switch (ev.kind) {
+    case EV_TICK: {
+        const int k = ev.idx;
+        if (B.maxTicks[k] != 0 && v.ticksDone(k) >= (uint32_t)B.maxTicks[k]) {
+            // the burst is over: this wake-up only ends the traffic process (its process event takes a number)
+            v.tTick(k) = (double)INFINITY;
+            v.seq()++;
+            break;
+        }
+        gen_ticks(v, B, k, 1u);
+        v.tTick(k) = v.now() + B.interval[k];
+        v.sTick(k) = v.seq()++;
+        if (v.mac(k) == MAC_WAIT_COND) gen_mac_try_send(v, P, k);   // _packetAddedEvent wakes the window loop
+        break;
+    }
+    case EV_JAM: {
+        const int j = ev.idx, d = RRM + 1 + j;
+        if (v.jamStage(j) == 0) {                                   // yield timeout(initialDelay)
+            v.jamStage(j) = 1; v.tJam(j) = v.now() + B.jamDelay[j]; v.sJam(j) = v.seq()++;
+        } else if (v.jamStage(j) == 1) {                            // first yield timeout(sendInterval)
+            v.jamStage(j) = 2; v.tJam(j) = v.now() + B.jamInterval[j]; v.sJam(j) = v.seq()++;
+        } else {
+            // macIn.send(SEND) -> queued executor; then yield timeout(sendInterval)
+            v.tJam(j) = v.now() + B.jamInterval[j]; v.sJam(j) = v.seq()++;
+            if (v.sphase(d) != S_IDLE) { v.jamPending(j) += 1; if (v.jamPending(j) > 60) v.sc(GenView::I_fault) = FAULT_SENDQ; }
+            else { v.cmdPay(d) = B.jamPay[j]; gen_phy_send_init(v, d); }
+        }
+        break;
+    }
+    case EV_PHY: {
+        const int d = ev.idx;
+        const int ph = v.sphase(d);
+        if (ph == S_SLOT) {
+            // FrequencyBand.transmit -> Transmission.__init__ (physical.py:224-279, 596-608)
+            const int payBytes = v.cmdPay(d), hdrBytes = gen_hdr_bytes(v, B, d);
+            const double now = v.now();
+            const double hd = airtime_of(P, hdrBytes);
+            const double pd = airtime_of(P, payBytes);
+            const double duration = hd + pd;
+            const double stop = now + duration;
+            const double headerStop = now + hd;
+            const double tH = now + (headerStop > now ? headerStop - now : 0.0);       // timeoutUntil
+            const double tC = now + (stop > now ? stop - now : 0.0);
+            const uint32_t qH = v.seq()++, qC = v.seq()++;
+            v.sphase(d) = S_HDR; v.tEv(d) = tH; v.sEv(d) = qH; v.tC(d) = tC; v.sC(d) = qC; v.tStop(d) = stop;
+            v.txSeq(d) += 1u;
+            v.sc(GenView::I_nTx) += 1;
+            gen_rec(v, REC_TX, now, d, stop, (hdrBytes * 8) * P.bitsFactor, (payBytes * 8) * P.bitsFactor, 0.0);
+            // zero-delay notification: every other PHY registers the received power (simple_stack.py:130-144)
+            for (int p = 0; p < nd; ++p) {
+                if (p == d) continue;
+                gen_power_change(v, P, p, v.rp(p, d), false);
+            }
+            // receive processes in PHY construction order: idle, non-transmitting PHYs lock on (simple_stack.py:214-235)
+            for (int p = 0; p < nd; ++p) {
+                if (p == d || v.rxOf(p) >= 0 || v.sphase(p) >= S_SLOT) continue;
+                v.rxOf(p) = d; v.rxSec(p) = 0; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = now;
+                gen_update_ber(v, P, p);
+            }
+        } else if (ph == S_HDR) {
+            // eHeaderCompletes: receivers decide on the header (simple_stack.py:241-251)
+            const double hdrBits = (gen_hdr_bytes(v, B, d) * 8) * P.bitsFactor;
+            uint32_t wake = 0;
+            for (int p = 0; p < nd; ++p) {
+                if (v.rxOf(p) != d || v.rxSec(p) != 0) continue;
+                gen_count(v, P, p);
+                if (gen_decide(v, P, p, 0, hdrBits)) {
+                    v.rxSec(p) = 1; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = v.now();  // _resetBitErrorCounter
+                    gen_update_ber(v, P, p);
+                } else {
+                    gen_rx_clear(v, p);
+                    if (v.sphase(p) == S_WAITRX) wake |= 1u << p;
+                }
+            }
+            v.sphase(d) = S_PAY; v.tEv(d) = v.tC(d); v.sEv(d) = v.sC(d);
+            for (int p = 0; p < nd; ++p) if ((wake >> p) & 1u) gen_begin_slot_wait(v, p);   // _nReceivingFinished.event
+        } else {
+            // eCompletes, callbacks in registration order:
+            // 1. the sender's macInHandler resumes: _transmitting = False (simple_stack.py:210)
+            const double payBits = (v.cmdPay(d) * 8) * P.bitsFactor;
+            v.sphase(d) = S_IDLE;
+            // 2. _onCompletingTransmission of every other PHY (simple_stack.py:146-157)
+            for (int p = 0; p < nd; ++p) {
+                if (p == d) continue;
+                gen_power_change(v, P, p, -v.rp(p, d), v.rxOf(p) == d);
+            }
+            // 3. receivers that passed the header count again (appendix B #4), decide on the payload and deliver
+            int window = -1;
+            uint32_t wake = 0, received = 0;
+            for (int p = 0; p < nd; ++p) {
+                if (v.rxOf(p) != d || v.rxSec(p) != 1) continue;
+                gen_count(v, P, p);
+                if (gen_decide(v, P, p, 1, payBits)) {
+                    if (p < ns) {
+                        // SimpleMac.phyInHandler (blocking, not queued): an announcement addressed to an idle MAC
+                        // opens its window (simple_stack.py:386-434); a data packet addressed to an idle MAC in
+                        // receive mode goes to the network layer (:436-444)
+                        const bool idle = v.mac(p) == MAC_NONE;
+                        if (d == RRM) {
+                            if (idle && v.sc(GenView::I_annDest) == p) window = p;
+                        } else if (d < ns && idle && B.recv[p] && B.dest[d] == p) {
+                            received |= 1u << p;
+                        }
+                    } else if (p == RRM) {
+                        // SimpleRrmMac.phyInHandler -> interpreter.onPacketReceived (devices.py:163-168,
+                        // counter_traffic.py:75-80): receivedValues[sender] = payload.value (= 2, appendix B #1)
+                        if (d < ns) {
+                            if (d == 0) v.sc(GenView::I_rv0) = kCounterByteLen;
+                            if (d == 1) v.sc(GenView::I_rv1) = kCounterByteLen;
+                            v.sc(GenView::I_latestDiff) = v.sc(GenView::I_rv0) - v.sc(GenView::I_rv1);
+                            v.nDeliv(d) += 1u;
+                        }
+                        gen_rec(v, REC_RX, v.now(), d, 0.0, 0.0, 0.0, 0.0);
+                    }
+                }
+                gen_rx_clear(v, p);
+                if (v.sphase(p) == S_WAITRX) wake |= 1u << p;
+            }
+            // zero-delay children in SimPy's pop order:
+            // a. URGENT: phyInHandler of the grantee opens its window (simple_stack.py:399-406)
+            if (window >= 0) {
+                const double timeTotal = v.annSlots() * kSlot;
+                v.stopW(window) = v.now() + timeTotal;
+                v.sW(window) = v.seq()++;
+                v.wPend(window) = 1;
+                v.wDone(window) = 0;
+                gen_mac_loop_head(v, P, window);
+            }
+            // b. SEND eProcessed: the sender's upper layer resumes
+            if (d < ns) {
+                gen_mac_loop_head(v, P, d);                         // `yield message.eProcessed` returns
+            } else if (d == RRM) {
+                v.tRrm() = v.now() + (v.annSlots() + 1) * kSlot;    // simple_stack.py:558
+                v.sc(GenView::I_sRrm) = (int32_t)(v.seq()++);
+                v.sc(GenView::I_rrmPend) = 1;
+            } else {
+                // c. executeNext of the queued macIn executor: a PHY-only sender's pending SEND starts
+                const int j = d - RRM - 1;
+                if (v.jamPending(j) > 0) { v.jamPending(j) -= 1; gen_phy_send_init(v, d); }
+            }
+            // d. _nReceivingFinished.event of the receivers that finished
+            for (int p = 0; p < nd; ++p) if ((wake >> p) & 1u) gen_begin_slot_wait(v, p);
+            // e. RECEIVE.eProcessed: the device's receive loop hands the packet to onReceive and issues the next
+            // RECEIVE command with a fresh timeout (devices.py:88-95, simple_stack.py:452-460)
+            for (int k = 0; k < ns; ++k) {
+                if (!((received >> k) & 1u)) continue;
+                v.nRecv(k) += 1u;
+                gen_rec(v, REC_MRX, v.now(), k, 0.0, 0.0, 0.0, 0.0);
+                v.rxT(k) = v.now() + kReceiveTimeout; v.rxS(k) = v.seq()++;
+            }
+        }
+        break;
+    }
+    case EV_RXTO:
+        // the current RECEIVE command timed out (or the receive loop starts): the loop issues the next command
+        // (simple_stack.py:473-478, devices.py:88-93)
+        v.rxT(ev.idx) = v.now() + kReceiveTimeout; v.rxS(ev.idx) = v.seq()++;
+        break;
+    case EV_W: {
+        // window timeoutEvent processed (simple_stack.py:406-420)
+        const int k = ev.idx;
+        v.wPend(k) = 0;
+        if (v.mac(k) == MAC_WAIT_TX) v.wDone(k) = 1;
+        else v.mac(k) = MAC_NONE;
+        break;
+    }
+    case EV_RRM:
+        // assignMessage.setProcessed() (simple_stack.py:561): the step ends here
+        v.sc(GenView::I_rrmPend) = 0;
+        v.sc(GenView::I_assignDone) = 1;
+        break;
+    default:
+        v.sc(GenView::I_fault) = FAULT_EMPTY;
+    }
+}
+
+// SimpleRrmDevice.assignFrequencyBand + SimpleRrmMac._sendAnnouncement start (devices.py:178-203,
+// simple_stack.py:536-556): the RRM PHY receives a SEND command for the announcement
+GW_HD void gen_begin_assignment(GenView &v, const Params &P, int device, int duration)
+{
+    const long long slots = (long long)duration * P.factor;         // counter_traffic.py:149
+    int nbytes = 1;                                                  // len(str(slots)), messages.py:62-64
+    for (long long lim = 10; lim <= slots && nbytes < 18; lim *= 10) ++nbytes;
+    v.sc(GenView::I_annDest) = device;
+    v.annSlots() = (double)slots;
+    v.sc(GenView::I_assignDone) = 0;
+    // the RRM PHY's queued macIn executor is idle here: its previous SEND completed before the previous
+    // assignment's guard time-out (simple_stack.py:557-558)
+    if (v.sphase(v.ns) != S_IDLE) v.sc(GenView::I_fault) = FAULT_SENDQ;
+    v.cmdPay(v.ns) = nbytes;
+    gen_phy_send_init(v, v.ns);
+}
+
+// Interpreter.getFeedback (envs/core.py:142-153, counter_traffic.py:85-107)
+GW_HD void gen_feedback(GenView &v, long long &obs, double &reward, unsigned char &done)
+{
+    const int diff = v.sc(GenView::I_latestDiff);
+    obs = (long long)diff + kCounterBound;
+    const int absd = diff < 0 ? -diff : diff;
+    int r = v.sc(GenView::I_lastAbsDiff) - absd;
+    v.sc(GenView::I_lastAbsDiff) = absd;
+    if (r > 10) r = 10; else if (r < -10) r = -10;
+    reward = (double)r;
+    done = (unsigned char)v.sc(GenView::I_done);
+}
+
+// env.step(action): assign, run until the ASSIGN message is processed (counter_traffic.py:146-158), feedback.
+// An action outside the action space (the reference asserts) leaves the band-sim untouched and reports a fault.
+GW_HD void gen_step(GenView &v, const Params &P, const GenBand &B, int device, int duration, long long &obs,
+                    double &reward, unsigned char &done)
+{
+    if (v.sc(GenView::I_fault) == 0) {
+        if (device < 0 || device >= v.ns || duration < 0 || duration >= B.maxDuration) {
+            v.sc(GenView::I_fault) = FAULT_EMPTY + 1;              // FAULT_ACTION of the C ABI
+        } else {
+            gen_begin_assignment(v, P, device, duration);
+            while (!v.sc(GenView::I_assignDone) && !v.sc(GenView::I_fault)) {
+                const Event ev = gen_next_event(v, B);
+                gen_apply(v, P, B, ev);
+            }
+        }
+    }
+    if (v.sc(GenView::I_fault)) {
+        // a rejected action or a faulted band-sim: nothing happened, the interpreter is not consulted
+        obs = (long long)v.sc(GenView::I_latestDiff) + kCounterBound; reward = 0.0; done = (unsigned char)v.sc(GenView::I_done);
+        return;
+    }
+    gen_feedback(v, obs, reward, done);
+}
+
+}  // namespace gw

@@ -35,6 +35,7 @@
 #include "gw_core.cuh"
 #include "gw_pendulum.cuh"
 #include "gw_grid.cuh"
+#include "gw_band.cuh"
 
 using namespace gw;
 
@@ -1938,6 +1939,106 @@ __global__ void grid_read_kernel(GridArgs A, GridParams G, int field, double *ou
     }
 }
 
+// ------------------------------------------------------------------------------------
+// general band engine (gw_band.cuh): run-time device counts, one band-sim per thread, state in global memory
+// laid out [word][env] so that a warp's accesses to one field are contiguous
+// ------------------------------------------------------------------------------------
+
+struct GenArgs {
+    double *f64;                // [gen_f64_words][n_envs]
+    int32_t *i32;               // [gen_i32_words][n_envs]
+    double *srx;                // [nd * nd][n_envs] or [nd * nd]
+    long long n_envs;
+    int per_env;
+    double *trace;              // [n_envs][cap][8] or NULL
+    int *trace_count;
+    int trace_cap;
+    int *errflag;
+};
+
+__device__ __forceinline__ GenView gen_view_of(const GenArgs &A, const GenBand &B, long long i)
+{
+    GenView v;
+    v.f = A.f64 + i; v.i = A.i32 + i; v.stride = A.n_envs;
+    v.srx = A.per_env ? A.srx + i : A.srx; v.srxStride = A.per_env ? A.n_envs : 1;
+    v.ns = B.ns; v.nj = B.nj; v.nd = B.nd;
+    v.trace = nullptr; v.ntrace = 0; v.traceCap = 0;
+    return v;
+}
+
+__global__ void genband_init_kernel(GenArgs A, GenBand B, const double *pos, const double *power, double frequency)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_envs) return;
+    if (A.per_env) gen_power_table(B.nd, pos + i * B.nd * 2, power, frequency, A.srx + i, A.n_envs);
+    else if (i == 0) gen_power_table(B.nd, pos, power, frequency, A.srx, 1);
+    GenView v = gen_view_of(A, B, i);
+    gen_init(v, B);
+}
+
+__global__ void genband_reset_kernel(GenArgs A, GenBand B, long long *obs)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_envs) return;
+    GenView v = gen_view_of(A, B, i);
+    gen_reset(v);
+    if (obs) obs[i] = (long long)kCounterBound;
+}
+
+__global__ void __launch_bounds__(64)
+genband_step_kernel(GenArgs A, Params P, GenBand B, const int32_t *device, const int32_t *duration, long long *obs,
+                    double *reward, unsigned char *done)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_envs) return;
+    GenView v = gen_view_of(A, B, i);
+    if (A.trace) { v.trace = A.trace + i * A.trace_cap * 8; v.traceCap = A.trace_cap; }
+    const int before = v.sc(GenView::I_fault);
+    long long o; double r; unsigned char d;
+    gen_step(v, P, B, device[i], duration[i], o, r, d);
+    obs[i] = o; reward[i] = r; done[i] = d;
+    if (A.trace) A.trace_count[i] = v.ntrace;
+    const int fault = v.sc(GenView::I_fault);
+    if (fault && !before) {
+        const int code = fault == FAULT_EMPTY + 1 ? GW_E_ACTION : GW_E_SIMFAULT;
+        if (fault == FAULT_EMPTY + 1) v.sc(GenView::I_fault) = 0;      // a rejected action leaves the env as it was
+        if (atomicCAS(A.errflag, 0, code) == 0) { A.errflag[1] = (int)i; A.errflag[2] = fault; }
+    }
+}
+
+__global__ void genband_read_kernel(GenArgs A, GenBand B, int field, double *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_envs) return;
+    const GenView v = gen_view_of(A, B, i);
+    const long long n = A.n_envs;
+    switch (field) {
+    case GW_GENBAND_FIELD_NOW: out[i] = v.now(); break;
+    case GW_GENBAND_FIELD_TRANSMISSIONS: out[i] = v.sc(GenView::I_nTx); break;
+    case GW_GENBAND_FIELD_FAULT: out[i] = v.sc(GenView::I_fault); break;
+    case GW_GENBAND_FIELD_TIES: out[i] = v.sc(GenView::I_ties); break;
+    case GW_GENBAND_FIELD_RECEIVED_POWER: for (int p = 0; p < B.nd; ++p) out[p * n + i] = v.P(p); break;
+    default:
+        for (int k = 0; k < B.ns; ++k) {
+            double x = 0;
+            if (field == GW_GENBAND_FIELD_DELIVERED) x = v.nDeliv(k);
+            else if (field == GW_GENBAND_FIELD_RECEIVED) x = v.nRecv(k);
+            else if (field == GW_GENBAND_FIELD_QUEUE_LENGTH) x = v.qn(k);
+            else if (field == GW_GENBAND_FIELD_COUNTER) x = v.counter(k);
+            out[k * n + i] = x;
+        }
+    }
+}
+
+struct gw_genband_handle {
+    gw_genband_config cfg;
+    int device;
+    Params P;
+    GenBand B;
+    GenArgs A;
+    int *errflag;
+};
+
 struct gw_grid_handle {
     gw_grid_config cfg;
     int device;
@@ -3012,6 +3113,155 @@ int gw_grid_check(gw_grid_handle *h, void *stream)
     if (flag[0] == 0) return GW_OK;
     CUDA_TRY(cudaMemsetAsync(h->errflag, 0, sizeof flag, s));
     return fail(GW_E_SIMFAULT, "grid env %d hit a condition under which the reference raises (fault %d)", flag[1], flag[2]);
+}
+
+int gw_genband_create(const gw_genband_config *cfg, int device, const double *positions, void *stream, gw_genband_handle **out)
+{
+    if (!cfg || !out || !positions) return fail(GW_E_INVALID, "NULL argument");
+    if (cfg->abi_version != GW_ABI_VERSION) return fail(GW_E_INVALID, "abi_version %d != %d", cfg->abi_version, GW_ABI_VERSION);
+    if (cfg->n_envs < 1) return fail(GW_E_INVALID, "n_envs must be >= 1");
+    const int ns = cfg->n_senders, nj = cfg->n_phy_senders;
+    if (ns < 2 || ns > GW_GENBAND_MAX_SENDERS) return fail(GW_E_INVALID, "n_senders must be in 2..%d", GW_GENBAND_MAX_SENDERS);
+    if (nj < 0 || nj > GW_GENBAND_MAX_PHY_SENDERS) return fail(GW_E_INVALID, "n_phy_senders must be in 0..%d", GW_GENBAND_MAX_PHY_SENDERS);
+    if (cfg->assignment_duration_factor < 1 || cfg->max_assign_duration < 1) return fail(GW_E_INVALID, "bad duration parameters");
+    if (!(cfg->frequency_hz > 0) || !(cfg->bandwidth_hz > 0)) return fail(GW_E_INVALID, "bad frequency band");
+    for (int k = 0; k < ns; ++k) {
+        if (cfg->multiplicity[k] < 1 || cfg->multiplicity[k] > 1000) return fail(GW_E_INVALID, "sender %d: multiplicity must be in 1..1000", k);
+        if (!(cfg->interval[k] > 0)) return fail(GW_E_INVALID, "sender %d: interval must be > 0", k);
+        if (cfg->payload_bytes[k] > 60000) return fail(GW_E_INVALID, "sender %d: payload_bytes must be <= 60000", k);
+        if (cfg->destination[k] < 0 || cfg->destination[k] >= ns || cfg->destination[k] == k)
+            return fail(GW_E_INVALID, "sender %d: destination must be another sender", k);
+        if (cfg->max_ticks[k] < 0) return fail(GW_E_INVALID, "sender %d: max_ticks must be >= 0", k);
+    }
+    for (int j = 0; j < nj; ++j) {
+        if (!(cfg->phy_interval[j] > 0) || !(cfg->phy_delay[j] >= 0)) return fail(GW_E_INVALID, "PHY-only sender %d: bad interval / delay", j);
+        if (cfg->phy_header_bytes[j] < 1 || cfg->phy_payload_bytes[j] < 1 || cfg->phy_header_bytes[j] + cfg->phy_payload_bytes[j] > 60000)
+            return fail(GW_E_INVALID, "PHY-only sender %d: bad packet size", j);
+    }
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) return fail(GW_E_CUDA, "no CUDA device: gymwipe_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(GW_E_INVALID, "device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    gw_genband_handle *h = new (std::nothrow) gw_genband_handle();
+    if (!h) return fail(GW_E_INVALID, "out of host memory");
+    std::memset(h, 0, sizeof *h);
+    h->cfg = *cfg;
+    h->device = device;
+    Params &P = h->P;
+    P.nbands = 1; P.factor = cfg->assignment_duration_factor; P.maxDuration = cfg->max_assign_duration; P.mode = MODE_R;
+    P.bitRate = 133.33333e3; P.dataRate = 0.75 * P.bitRate; P.maxBer = gw_max_correctable_ber(3, 4);
+    P.tenLog10BitRate = 10 * std::log10(P.bitRate); P.qDen = 1.135 * std::sqrt(2 * 3.141592653589793);
+    P.bitsFactor = 2 - 0.75;
+    finish_params(P);
+    GenBand &B = h->B;
+    B.ns = ns; B.nj = nj; B.nd = ns + 1 + nj; B.maxDuration = cfg->max_assign_duration;
+    B.thermal = 1.38e-23 * (20.0 + 273.15) * cfg->bandwidth_hz * 1000;        // simple_stack.py:57, physical.py:61-78
+    double power[GW_GENBAND_MAX_DEVICES];
+    for (int d = 0; d < B.nd; ++d) power[d] = 0.0;                              // MACs and the RRM send at 0 dBm
+    for (int k = 0; k < ns; ++k) {
+        B.mult[k] = cfg->multiplicity[k]; B.payloadRule[k] = cfg->payload_bytes[k] < 0 ? -1 : cfg->payload_bytes[k];
+        B.dest[k] = cfg->destination[k]; B.maxTicks[k] = cfg->max_ticks[k]; B.recv[k] = cfg->receive[k] ? 1 : 0;
+        B.interval[k] = cfg->interval[k];
+    }
+    for (int j = 0; j < nj; ++j) {
+        B.jamInterval[j] = cfg->phy_interval[j]; B.jamDelay[j] = cfg->phy_delay[j];
+        B.jamHdr[j] = cfg->phy_header_bytes[j]; B.jamPay[j] = cfg->phy_payload_bytes[j];
+        power[ns + 1 + j] = cfg->phy_power_dbm[j];
+    }
+    GenArgs &A = h->A;
+    A.n_envs = cfg->n_envs; A.per_env = cfg->per_env_positions ? 1 : 0;
+    const size_t n = (size_t)cfg->n_envs;
+    double *dpower = nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMalloc((void **)&A.f64, sizeof(double) * gen_f64_words(ns, nj) * n);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&A.i32, sizeof(int32_t) * gen_i32_words(ns, nj) * n);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&A.srx, sizeof(double) * B.nd * B.nd * (A.per_env ? n : 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->errflag, 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(h->errflag, 0, 4 * sizeof(int), s);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dpower, sizeof power);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dpower, power, sizeof power, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        A.errflag = h->errflag;
+        genband_init_kernel<<<grid_for(cfg->n_envs, 64), 64, 0, s>>>(A, B, positions, dpower, cfg->frequency_hz);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);                         // `power` is a stack array
+    if (dpower) cudaFree(dpower);
+    if (e != cudaSuccess) { gw_genband_destroy(h); return fail(GW_E_CUDA, "general band engine: %s", cudaGetErrorString(e)); }
+    *out = h;
+    return GW_OK;
+}
+
+void gw_genband_destroy(gw_genband_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->A.f64) cudaFree(h->A.f64);
+    if (h->A.i32) cudaFree(h->A.i32);
+    if (h->A.srx) cudaFree(h->A.srx);
+    if (h->errflag) cudaFree(h->errflag);
+    delete h;
+}
+
+int gw_genband_reset(gw_genband_handle *h, int64_t *obs, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    genband_reset_kernel<<<grid_for(h->A.n_envs, 64), 64, 0, (cudaStream_t)stream>>>(h->A, h->B, (long long *)obs);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+static int genband_launch(gw_genband_handle *h, const int32_t *device, const int32_t *duration, int64_t *obs, double *reward,
+                          uint8_t *done, double *trace, int32_t *trace_count, int32_t cap, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    if (!device || !duration || !obs || !reward || !done) return fail(GW_E_INVALID, "NULL buffer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    GenArgs A = h->A;
+    A.trace = trace; A.trace_count = trace_count; A.trace_cap = cap;
+    genband_step_kernel<<<grid_for(A.n_envs, 64), 64, 0, (cudaStream_t)stream>>>(A, h->P, h->B, device, duration, (long long *)obs,
+                                                                               reward, done);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_genband_step(gw_genband_handle *h, const int32_t *device, const int32_t *duration, int64_t *obs, double *reward,
+                    uint8_t *done, void *stream)
+{
+    return genband_launch(h, device, duration, obs, reward, done, nullptr, nullptr, 0, stream);
+}
+
+int gw_genband_step_traced(gw_genband_handle *h, const int32_t *device, const int32_t *duration, int64_t *obs, double *reward,
+                           uint8_t *done, double *trace, int32_t *trace_count, int32_t cap, void *stream)
+{
+    if (!trace || !trace_count || cap < 1) return fail(GW_E_INVALID, "bad trace buffer");
+    return genband_launch(h, device, duration, obs, reward, done, trace, trace_count, cap, stream);
+}
+
+int gw_genband_read(gw_genband_handle *h, int field, double *out, void *stream)
+{
+    if (!h || !out) return fail(GW_E_INVALID, "NULL argument");
+    if (field < GW_GENBAND_FIELD_NOW || field > GW_GENBAND_FIELD_TIES) return fail(GW_E_INVALID, "unknown field %d", field);
+    CUDA_TRY(cudaSetDevice(h->device));
+    genband_read_kernel<<<grid_for(h->A.n_envs, 64), 64, 0, (cudaStream_t)stream>>>(h->A, h->B, field, out);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_genband_check(gw_genband_handle *h, void *stream)
+{
+    if (!h) return fail(GW_E_INVALID, "handle is NULL");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    int flag[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(flag, h->errflag, sizeof flag, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (flag[0] == 0) return GW_OK;
+    CUDA_TRY(cudaMemsetAsync(h->errflag, 0, sizeof flag, s));
+    if (flag[0] == GW_E_ACTION) return fail(GW_E_ACTION, "env %d: action outside the action space", flag[1]);
+    return fail(GW_E_SIMFAULT, "env %d hit a condition under which the reference raises (fault %d)", flag[1], flag[2]);
 }
 
 int gw_philox4x32(const uint32_t *counter, const uint32_t *key, uint32_t *out, int64_t n, void *stream)

@@ -4,6 +4,7 @@ instantiates them (gym itself is not a dependency).
 """
 from gymwipe_b200.envs.counter_traffic import CounterTrafficEnv
 from gymwipe_b200.envs.core import BaseEnv, Interpreter
+from gymwipe_b200.envs.general_band import GeneralBandEnv, fits_step_kernel_template
 from gymwipe_b200.envs.inverted_pendulum import InvertedPendulumEnv
 from gymwipe_b200.envs.population import EnvPopulation
 from gymwipe_b200.envs.sending_grid import SendingDeviceGrid
@@ -22,7 +23,14 @@ def make(id, **kwargs):
     """``gym.make(id)`` for the ids this package registers; keyword arguments reach the env."""
     if id not in registry:
         raise KeyError("No registered env with id: {}".format(id))
-    return registry[id](**kwargs)
+    cls = registry[id]
+    # a CounterTraffic scenario beyond the step kernel's 2 senders + RRM (+ 1 PHY-only sender) template -- more MAC
+    # senders, more PHY-only senders -- is stepped by the general band engine behind the same gym surface
+    sc = kwargs.get("scenario")
+    if cls is CounterTrafficEnv and sc is not None and len(sc["bands"]) == 1 and not fits_step_kernel_template(sc):
+        drop = [k for k in ("seed", "env_id_offset") if k in kwargs]
+        return GeneralBandEnv(**{k: v for k, v in kwargs.items() if k not in drop})
+    return cls(**kwargs)
 
 
-__all__ = ["CounterTrafficEnv", "InvertedPendulumEnv", "EnvPopulation", "SendingDeviceGrid", "BaseEnv", "Interpreter", "make", "register", "registry"]
+__all__ = ["CounterTrafficEnv", "InvertedPendulumEnv", "EnvPopulation", "SendingDeviceGrid", "GeneralBandEnv", "BaseEnv", "Interpreter", "make", "register", "registry"]

@@ -371,6 +371,73 @@ int gw_grid_read(gw_grid_handle *h, int field, double *out, void *stream);
 /* Synchronises; GW_E_SIMFAULT if an env hit a condition under which the reference raises. */
 int gw_grid_check(gw_grid_handle *h, void *stream);
 
+/* ---- general band engine: more than two MAC senders / one PHY-only sender per band --
+ *
+ * CounterTrafficEnv wires exactly two SenderDevices and one RRM (counter_traffic.py:114-133) and gw_create's
+ * kernels are specialised for that template (+ at most one PHY-only sender).  The reference's building blocks
+ * compose to larger bands: any number of SimpleNetworkDevices with a traffic process, one SimpleRrmDevice whose
+ * CounterTrafficInterpreter keeps one received value per device (counter_traffic.py:69-80: the observation
+ * stays receivedValues[0] - receivedValues[1]) and PHY-only periodic senders (tests/test_benchmark.py:20-50).
+ * This engine steps such bands -- n_senders <= 8, n_phy_senders <= 16 as RUN-TIME values -- exactly like the env:
+ * assignFrequencyBand(device, duration) (devices.py:178-203), runSimulation(assignSignal.eProcessed), then
+ * Interpreter.getFeedback; reference accounting (mode R).  Device order: senders, RRM, PHY-only senders.
+ * One GPU thread per env, state in global memory ([field][index][env]); gymwipe_b200/csrc/gw_band.cuh. */
+#define GW_GENBAND_MAX_SENDERS 8
+#define GW_GENBAND_MAX_PHY_SENDERS 16
+#define GW_GENBAND_MAX_DEVICES (GW_GENBAND_MAX_SENDERS + 1 + GW_GENBAND_MAX_PHY_SENDERS)
+
+typedef struct {
+    int32_t abi_version;            /* GW_ABI_VERSION */
+    int64_t n_envs;
+    int32_t n_senders, n_phy_senders;
+    int32_t assignment_duration_factor;     /* ASSIGNMENT_DURATION_FACTOR = 1000, envs/core.py:36 */
+    int32_t max_assign_duration;            /* MAX_ASSIGN_DURATION = 20, envs/core.py:31: duration in [0, 20) */
+    int32_t per_env_positions;              /* 0: one geometry for all envs; 1: positions per env */
+    double frequency_hz, bandwidth_hz;      /* FrequencyBandSpec, physical.py:293-306 */
+    /* senders (SenderDevice, counter_traffic.py:37-61) */
+    int32_t multiplicity[GW_GENBAND_MAX_SENDERS];       /* packets per tick */
+    int32_t payload_bytes[GW_GENBAND_MAX_SENDERS];      /* < 0: byteSize = counter (the reference's rule) */
+    int32_t destination[GW_GENBAND_MAX_SENDERS];        /* sender index the packets are addressed to */
+    int32_t max_ticks[GW_GENBAND_MAX_SENDERS];          /* 0: forever; n: a burst of n ticks */
+    int32_t receive[GW_GENBAND_MAX_SENDERS];            /* 1: SimpleNetworkDevice.receiving = True */
+    double interval[GW_GENBAND_MAX_SENDERS];            /* COUNTER_INTERVAL = 1e-3 */
+    /* PHY-only periodic senders (tests/test_benchmark.py:31-48) */
+    double phy_interval[GW_GENBAND_MAX_PHY_SENDERS], phy_delay[GW_GENBAND_MAX_PHY_SENDERS];
+    double phy_power_dbm[GW_GENBAND_MAX_PHY_SENDERS];
+    int32_t phy_header_bytes[GW_GENBAND_MAX_PHY_SENDERS], phy_payload_bytes[GW_GENBAND_MAX_PHY_SENDERS];
+} gw_genband_config;
+
+typedef struct gw_genband_handle gw_genband_handle;
+
+/* `positions`: device float64 [n_devices][2], or [n_envs][n_devices][2] with per_env_positions (consumed on
+ * `stream`).  The envs start in the state after construction (CounterTrafficEnv.__init__); state is owned by the
+ * handle. */
+int gw_genband_create(const gw_genband_config *cfg, int device, const double *positions, void *stream,
+                      gw_genband_handle **out);
+void gw_genband_destroy(gw_genband_handle *h);
+/* CounterTrafficEnv.reset (counter_traffic.py:135-144) of every env; obs (device int64 [n_envs]) may be NULL. */
+int gw_genband_reset(gw_genband_handle *h, int64_t *obs, void *stream);
+/* CounterTrafficEnv.step (counter_traffic.py:146-158).  Device arrays [n_envs]: device in [0, n_senders),
+ * duration in [0, max_assign_duration); obs int64, reward float64, done uint8. */
+int gw_genband_step(gw_genband_handle *h, const int32_t *device, const int32_t *duration, int64_t *obs, double *reward,
+                    uint8_t *done, void *stream);
+/* The same with an event trace (record format of gw_step_traced): trace [n_envs][cap][8], trace_count [n_envs]. */
+int gw_genband_step_traced(gw_genband_handle *h, const int32_t *device, const int32_t *duration, int64_t *obs,
+                           double *reward, uint8_t *done, double *trace, int32_t *trace_count, int32_t cap, void *stream);
+
+#define GW_GENBAND_FIELD_NOW 0              /* [n_envs] */
+#define GW_GENBAND_FIELD_DELIVERED 1        /* [n_senders][n_envs] data packets of each sender decoded by the RRM */
+#define GW_GENBAND_FIELD_RECEIVED 2         /* [n_senders][n_envs] packets handed to onReceive (receive mode) */
+#define GW_GENBAND_FIELD_TRANSMISSIONS 3    /* [n_envs] */
+#define GW_GENBAND_FIELD_FAULT 4            /* [n_envs] 0, or the condition under which the reference raises */
+#define GW_GENBAND_FIELD_RECEIVED_POWER 5   /* [n_devices][n_envs] SimplePhy._receivedPower (mW) */
+#define GW_GENBAND_FIELD_QUEUE_LENGTH 6     /* [n_senders][n_envs] */
+#define GW_GENBAND_FIELD_COUNTER 7          /* [n_senders][n_envs] */
+#define GW_GENBAND_FIELD_TIES 8             /* [n_envs] exact-time ties between independent events (diagnostic) */
+int gw_genband_read(gw_genband_handle *h, int field, double *out, void *stream);
+/* Synchronises; GW_E_ACTION / GW_E_SIMFAULT like gw_check. */
+int gw_genband_check(gw_genband_handle *h, void *stream);
+
 /* ---- standalone kernels (numeric parity tests, roofline measurements) ------------- */
 
 /* K1: FSPL attenuation in dB, FsplAttenuation._update (attenuation_models.py:28-36) with

@@ -127,6 +127,31 @@ def random_scenario(rs, nbands=1, jammers=1, fixed_payload=None, spread=20.0, fa
     return {"assignment_duration_factor": factor, "bands": bands}
 
 
+def random_scenario_n(rs, ns, nj, spread=2.5, factor=1000, receive=False, bursts=False):
+    """One band with `ns` MAC senders (every sender addresses another one), the RRM and `nj` PHY-only senders --
+    beyond CounterTrafficEnv's 2 + 1 template; the interpreter's observation still follows senders 0 and 1
+    (counter_traffic.py:75-80: `receivedValues[0] - receivedValues[1]`)."""
+    devs = []
+    for k in range(ns):
+        dest = int((k + 1 + rs.randint(ns - 1)) % ns)
+        d = {"role": "sender", "x": float(rs.uniform(-spread, spread)), "y": float(rs.uniform(-spread, spread)),
+             "mult": int(rs.randint(1, 4)), "payload": "counter" if rs.rand() < 0.6 else int(rs.randint(1, 60)),
+             "interval": float(rs.choice([0.001, 0.001, 0.0007, 0.0013])), "dest": dest}
+        if receive and rs.rand() < 0.6:
+            d["receive"] = True
+        if bursts and rs.rand() < 0.3:
+            d["max_ticks"] = int(rs.randint(5, 60))
+        devs.append(d)
+    devs.append({"role": "rrm", "x": float(rs.uniform(-spread, spread)), "y": float(rs.uniform(-spread, spread))})
+    for j in range(nj):
+        payload = int(rs.randint(12, 120))
+        airtime = (13 + payload) * 8 / 99999.9975
+        devs.append({"role": "jammer", "x": float(rs.uniform(-spread, spread)), "y": float(rs.uniform(-spread, spread)),
+                     "interval": float(airtime * rs.uniform(2.0, 9.0) * max(1, nj)), "delay": float(rs.uniform(0, 1e-2)),
+                     "power": float(rs.choice([0.0, 10.0, 20.0])), "hdr": 13, "payload": payload})
+    return {"assignment_duration_factor": factor, "bands": [{"frequency": 2.4e9, "bandwidth": 22e6, "devices": devs}]}
+
+
 def child(args):
     """One case per process: the reference allows one env per process."""
     rs = np.random.RandomState(args.seed)
@@ -204,6 +229,12 @@ def child(args):
         sc0 = random_scenario(np.random.RandomState(args.seed), jammers=1, spread=3.0)      # the scenario as constructed
         sc0["bands"][0]["devices"][3]["interval"] = sc["bands"][0]["devices"][3]["interval"]
         return run_case(sc0, tape, "mobility corner cases, seed %d" % args.seed, moves=moves)
+    if args.case == "nsenders":
+        # bands beyond the 2 + 1 template: 3..8 MAC senders, 0..6 PHY-only senders, receive mode and bursts
+        ns, nj = int(rs.randint(3, 9)), int(rs.randint(0, 7))
+        sc = random_scenario_n(rs, ns, nj, spread=args.spread, receive=bool(args.seed % 2), bursts=bool(args.seed % 3 == 0))
+        tape = H.random_actions(args.steps, seed=args.seed + 11000, devices=ns)
+        return run_case(sc, tape, "%d senders + RRM + %d PHY-only senders, seed %d" % (ns, nj, args.seed))
     if args.case == "multiband":
         sc = random_scenario(rs, nbands=4, jammers=1, spread=args.spread)
         tapes = [H.random_actions(args.steps, seed=args.seed + 4000 + b) for b in range(4)]
@@ -242,7 +273,8 @@ def main():
     for sd in range(nseeds):
         plan += [("positions", sd, 200), ("jammer", sd, 200), ("long", sd, 40), ("multiband", sd, 80),
                  ("maskdefault", sd, 120), ("maskjammer", sd, 120), ("masklong", sd, 20),
-                 ("mobilityjam", sd, 120), ("maskmobilityjam", sd, 80), ("mobilityquirks", sd, 100)]
+                 ("mobilityjam", sd, 120), ("maskmobilityjam", sd, 80), ("mobilityquirks", sd, 100),
+                 ("nsenders", sd, 120)]
     failed = 0
     for case, sd, steps in plan:
         rc = subprocess.call([sys.executable, os.path.abspath(__file__), "--case", case,

@@ -42,6 +42,10 @@ CASES = {
     "modeM_default_seed12": ("maskdefault", 12, 60),
     "mac_receive_kat": ("mackat", 0, 10),
     "receive_bursts_seed21": ("receive", 21, 60),
+    # bands beyond CounterTrafficEnv's 2 senders + RRM template (general band engine)
+    "nsenders_5s_3p_seed31": ("nsenders:5:3:1:0", 31, 80),
+    "nsenders_8s_6p_seed32": ("nsenders:8:6:1:1", 32, 60),
+    "nsenders_3s_16p_seed33": ("nsenders:3:16:0:0", 33, 40),
 }
 
 MASK_SEED, MASK_ENV = 20261018, 4242
@@ -95,6 +99,11 @@ def make_case(kind, seed, steps):
         sc["bands"][0]["devices"][0]["receive"] = True
         sc["bands"][0]["devices"][1]["receive"] = True
         sc["bands"][0]["devices"][1]["max_ticks"] = 45
+    elif kind.startswith("nsenders:"):
+        # ns MAC senders + RRM + nj PHY-only senders, with / without receive mode and finite bursts
+        _, ns, nj, rcv, bursts = kind.split(":")
+        sc = CR.random_scenario_n(rs, int(ns), int(nj), spread=2.5, receive=bool(int(rcv)), bursts=bool(int(bursts)))
+        tape = H.random_actions(steps, seed=seed + 11000, devices=int(ns))
     else:
         raise SystemExit(kind)
     return sc, tape, do_reset, use_default

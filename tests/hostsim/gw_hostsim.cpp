@@ -13,6 +13,7 @@ static long long g_macro_stat[4] = {0, 0, 0, 0};
 #include "../../gymwipe_b200/csrc/gw_core.cuh"
 #include "../../gymwipe_b200/csrc/gw_pendulum.cuh"
 #include "../../gymwipe_b200/csrc/gw_grid.cuh"
+#include "../../gymwipe_b200/csrc/gw_band.cuh"
 
 using namespace gw;
 
@@ -305,6 +306,73 @@ int hs_grid_run(int n, double frequency, double bandwidth, const double *power, 
         stats[d * 6 + 3] = D.nPayOk; stats[d * 6 + 4] = D.nPayFail; stats[d * 6 + 5] = D.nBer;
     }
     return 0;
+}
+
+// general band engine (gw_band.cuh) on the host: `nenv` band-sims of one band with ns senders + RRM + nj PHY-only
+// senders stepped through an action tape [nsteps][nenv]; state laid out as on the device ([word][sim]).
+// cfg_i [6][8]: mult, payloadRule, dest, maxTicks, recv per sender (rows 0-4); cfg_jam_i [2][16]: hdr, payload;
+// cfg_d: interval [8], jamInterval [16], jamDelay [16]; pos [nenv or 1][nd][2]; power [nd].
+// Outputs per step and env: obs / reward / done / now; after the last step counts [nenv][1 + 8 + 8]
+// (transmissions, deliveries per sender, packets handed to onReceive per sender).  The trace of env 0 is returned
+// per step (records of 8 doubles).  `reset_at` >= 0: env.reset() before that step (0: before the first one).
+int hs_gen_run(int ns, int nj, int factor, double frequency, double bandwidth, const int32_t *cfg_i, const int32_t *cfg_jam_i,
+               const double *cfg_d, const double *pos, int per_env_pos, const double *power, int64_t nenv, int nsteps,
+               int reset_at, const int32_t *dev_tape, const int32_t *dur_tape, int64_t *obs, double *reward, uint8_t *done,
+               double *now_out, int64_t *counts, double *trace, int trace_cap, int32_t *trace_counts)
+{
+    Params P;
+    std::memset(&P, 0, sizeof P);
+    P.nbands = 1; P.factor = factor; P.maxDuration = 20; P.mode = MODE_R;
+    P.bitRate = 133.33333e3; P.dataRate = 0.75 * P.bitRate; P.maxBer = 0.25;
+    P.tenLog10BitRate = 10 * std::log10(P.bitRate); P.qDen = 1.135 * std::sqrt(2 * 3.141592653589793);
+    P.bitsFactor = 1.25;
+    finish_params(P);
+    GenBand B;
+    std::memset(&B, 0, sizeof B);
+    B.ns = ns; B.nj = nj; B.nd = ns + 1 + nj; B.maxDuration = 20;
+    B.thermal = 1.38e-23 * (20.0 + 273.15) * bandwidth * 1000;
+    for (int k = 0; k < ns; ++k) {
+        B.mult[k] = cfg_i[0 * 8 + k]; B.payloadRule[k] = cfg_i[1 * 8 + k]; B.dest[k] = cfg_i[2 * 8 + k];
+        B.maxTicks[k] = cfg_i[3 * 8 + k]; B.recv[k] = cfg_i[4 * 8 + k]; B.interval[k] = cfg_d[k];
+    }
+    for (int j = 0; j < nj; ++j) {
+        B.jamHdr[j] = cfg_jam_i[j]; B.jamPay[j] = cfg_jam_i[16 + j];
+        B.jamInterval[j] = cfg_d[8 + j]; B.jamDelay[j] = cfg_d[24 + j];
+    }
+    const int nd = B.nd, fw = gen_f64_words(ns, nj), iw = gen_i32_words(ns, nj);
+    std::vector<double> f((size_t)fw * nenv), srx((size_t)nd * nd * (per_env_pos ? nenv : 1));
+    std::vector<int32_t> iv((size_t)iw * nenv);
+    auto view = [&](int64_t e) {
+        GenView v;
+        v.f = f.data() + e; v.i = iv.data() + e; v.stride = nenv;
+        v.srx = per_env_pos ? srx.data() + e : srx.data(); v.srxStride = per_env_pos ? nenv : 1;
+        v.ns = ns; v.nj = nj; v.nd = nd; v.trace = nullptr; v.ntrace = 0; v.traceCap = 0;
+        return v;
+    };
+    if (per_env_pos) for (int64_t e = 0; e < nenv; ++e) gen_power_table(nd, pos + (size_t)e * nd * 2, power, frequency, srx.data() + e, nenv);
+    else gen_power_table(nd, pos, power, frequency, srx.data(), 1);
+    for (int64_t e = 0; e < nenv; ++e) { GenView v = view(e); gen_init(v, B); }
+    int used = 0, fault = 0;
+    for (int t = 0; t < nsteps; ++t) {
+        for (int64_t e = 0; e < nenv; ++e) {
+            GenView v = view(e);
+            if (t == reset_at) gen_reset(v);
+            if (e == 0 && trace) { v.trace = trace + (size_t)used * 8; v.traceCap = trace_cap - used; }
+            long long o; double r; unsigned char d;
+            gen_step(v, P, B, dev_tape[(size_t)t * nenv + e], dur_tape[(size_t)t * nenv + e], o, r, d);
+            obs[(size_t)t * nenv + e] = o; reward[(size_t)t * nenv + e] = r; done[(size_t)t * nenv + e] = d;
+            now_out[(size_t)t * nenv + e] = v.now();
+            if (e == 0 && trace) { trace_counts[t] = v.ntrace; used += v.ntrace < v.traceCap ? v.ntrace : v.traceCap; }
+            if (v.sc(GenView::I_fault) && !fault) fault = v.sc(GenView::I_fault);
+        }
+    }
+    for (int64_t e = 0; e < nenv; ++e) {
+        GenView v = view(e);
+        int64_t *c = counts + (size_t)e * 17;
+        c[0] = v.sc(GenView::I_nTx);
+        for (int k = 0; k < 8; ++k) { c[1 + k] = k < ns ? v.nDeliv(k) : 0; c[9 + k] = k < ns ? v.nRecv(k) : 0; }
+    }
+    return fault;
 }
 
 void hs_set_no_macro(int v) { g_no_macro = v; }

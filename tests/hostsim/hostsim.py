@@ -15,6 +15,7 @@ SRC = os.path.join(HERE, "gw_hostsim.cpp")
 CORE = os.path.join(HERE, "..", "..", "gymwipe_b200", "csrc", "gw_core.cuh")
 PEND = os.path.join(HERE, "..", "..", "gymwipe_b200", "csrc", "gw_pendulum.cuh")
 GRID = os.path.join(HERE, "..", "..", "gymwipe_b200", "csrc", "gw_grid.cuh")
+BAND = os.path.join(HERE, "..", "..", "gymwipe_b200", "csrc", "gw_band.cuh")
 
 MAXDEV, MAXSEND, MAXBAND = 4, 2, 4
 
@@ -42,7 +43,7 @@ _lib = None
 
 
 def build(force=False):
-    if force or not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(PEND), os.path.getmtime(GRID)):
+    if force or not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(PEND), os.path.getmtime(GRID), os.path.getmtime(BAND)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared",
                                "-o", SO, SRC])
     return SO
@@ -194,3 +195,75 @@ def grid_run(scenario, durations, move_delays=None, offsets=None, move_interval=
         at += counts[k]
         records.append(recs)
     return {"rc": rc, "now": list(now), "records": records, "stats": stats}
+
+
+def gen_run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, reset_at=None, trace_cap=400000):
+    """General band engine (``gw_band.cuh``) on the host: a one-band scenario dict with any number of senders
+    (<= 8), the RRM and PHY-only senders (<= 16); ``dev_tape`` / ``dur_tape`` int32 ``[nsteps, nenv]``; ``pos``
+    optional float64 ``[nenv, nd, 2]``.  Returns obs / reward / done / now ``[nsteps, nenv]``, ``counts``
+    ``[nenv, 17]`` (transmissions, deliveries per sender, onReceive calls per sender) and the trace records of
+    env 0 per step (Tracer tuple format)."""
+    L = lib()
+    band = scenario["bands"][0]
+    devs = band["devices"]
+    roles = [d["role"] for d in devs]
+    ns, nj = roles.count("sender"), roles.count("jammer")
+    assert len(scenario["bands"]) == 1 and roles == ["sender"] * ns + ["rrm"] + ["jammer"] * nj
+    nd = ns + 1 + nj
+    ci, cj, cd = np.zeros((6, 8), np.int32), np.zeros((2, 16), np.int32), np.zeros(40, np.float64)
+    for k, d in enumerate(devs[:ns]):
+        p = d.get("payload", "counter")
+        ci[:5, k] = [int(d["mult"]), -1 if p == "counter" else int(p), int(d["dest"]), int(d.get("max_ticks", 0)),
+                     1 if d.get("receive") else 0]
+        cd[k] = float(d.get("interval", 0.001))
+    for j, d in enumerate(devs[ns + 1:]):
+        cj[0, j], cj[1, j] = int(d.get("hdr", 13)), int(d["payload"])
+        cd[8 + j], cd[24 + j] = float(d["interval"]), float(d["delay"])
+    power = np.array([float(d.get("power", 0.0)) if d["role"] == "jammer" else 0.0 for d in devs], np.float64)
+    dev_tape = np.ascontiguousarray(dev_tape, dtype=np.int32)
+    dur_tape = np.ascontiguousarray(dur_tape, dtype=np.int32)
+    nsteps, nenv = dev_tape.shape
+    if pos is None:
+        p = np.ascontiguousarray([[d["x"], d["y"]] for d in devs], dtype=np.float64)
+    else:
+        p = np.ascontiguousarray(pos, dtype=np.float64)
+        assert p.shape == (nenv, nd, 2)
+    obs, rew = np.zeros((nsteps, nenv), np.int64), np.zeros((nsteps, nenv), np.float64)
+    done, now = np.zeros((nsteps, nenv), np.uint8), np.zeros((nsteps, nenv), np.float64)
+    counts = np.zeros((nenv, 17), np.int64)
+    trace, tc = np.zeros((trace_cap, 8)), np.zeros(nsteps, np.int32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    L.hs_gen_run.restype = C.c_int
+    L.hs_gen_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int64,
+                             C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_void_p]
+    if reset_at is None:
+        reset_at = 0 if do_reset else -1
+    rc = L.hs_gen_run(ns, nj, int(scenario.get("assignment_duration_factor", 1000)), float(band.get("frequency", 2.4e9)),
+                      float(band.get("bandwidth", 22e6)), ptr(ci), ptr(cj), ptr(cd), ptr(p), 0 if pos is None else 1, ptr(power),
+                      nenv, nsteps, int(reset_at), ptr(dev_tape), ptr(dur_tape), ptr(obs), ptr(rew), ptr(done), ptr(now),
+                      ptr(counts), ptr(trace), trace_cap, ptr(tc))
+    assert int(tc.sum()) <= trace_cap, "raise trace_cap"
+    return {"rc": rc, "obs": obs, "reward": rew, "done": done, "now": now, "counts": counts,
+            "records": records_from_trace(trace, tc)}
+
+
+def records_from_trace(trace, counts, band=0):
+    """Trace records (8 doubles each, ``gw_core.cuh::trace_rec``) per step -> Tracer tuples."""
+    out, at = [], 0
+    for n in counts:
+        recs = []
+        for r in trace[at:at + n]:
+            kind = int(r[0])
+            if kind == 1:
+                recs.append(("tx", float(r[1]), band, int(r[2]), float(r[3]), float(r[4]), float(r[5])))
+            elif kind == 2:
+                recs.append(("ber", float(r[1]), band, int(r[2]), float(r[3])))
+            elif kind == 3:
+                recs.append(("dec", float(r[1]), band, int(r[2]), int(r[3]), float(r[4]), float(r[5]), bool(r[6])))
+            elif kind == 4:
+                recs.append(("rx", float(r[1]), band, int(r[2])))
+            elif kind == 5:
+                recs.append(("mrx", float(r[1]), band, int(r[2])))
+        at += n
+        out.append(recs)
+    return out

@@ -1,0 +1,126 @@
+"""
+General band engine (``gymwipe_b200/csrc/gw_band.cuh``): bands beyond ``CounterTrafficEnv``'s 2 senders + RRM
+template -- 3..8 MAC senders, the RRM, 0..16 PHY-only senders.
+
+CPU: the oracle's C restatement and the host build of the CUDA engine against golden vectors produced by the
+UNMODIFIED reference (``oracle/gen_golden.py``, cases ``nsenders_*``: the reference's own ``SimpleNetworkDevice`` /
+``SimpleRrmDevice`` / ``CounterTrafficInterpreter`` classes composed to larger bands by ``oracle/ref_harness.py``), and
+against each other on random scenarios.  GPU: the CUDA engine through the C ABI (``gw_genband_*``) against the
+goldens and, at batch sizes the reference could never run, against the oracle.  Integer results, event times and
+event order: bit-exact; BER values / expected error sums: 1e-9 relative (stated tolerance 1e-6).
+"""
+import numpy as np
+import pytest
+
+import gw_oracle as O
+import hostsim as HS
+from util import GOLDEN_NSENDERS, assert_step_records, load_golden, random_scenario_n
+
+
+def _tapes(doc):
+    dev = np.array([[s["action"]["device"]] for s in doc["steps"]], np.int32)
+    dur = np.array([[s["action"]["duration"]] for s in doc["steps"]], np.int32)
+    return dev, dur
+
+
+def _oracle_tape(sc, dev, dur, do_reset=True, reset_at=None):
+    ora = O.Oracle(sc, trace=True)
+    if do_reset and reset_at is None:
+        ora.reset()
+    ora.take_records()
+    steps = []
+    for t in range(dev.shape[0]):
+        if reset_at is not None and t == reset_at:
+            ora.reset()
+        obs, rew, done = ora.step({"device": int(dev[t, 0]), "duration": int(dur[t, 0])})
+        steps.append({"obs": obs, "reward": rew, "done": done, "now": ora.now, "records": ora.take_records()})
+    ntx, nd = ora.counts()
+    return steps, ntx, nd, ora.received(), ora.near_ties
+
+
+def _assert_host_equals(h, steps, ntx, nd, nrecv, ns, label):
+    assert h["rc"] == 0, label
+    for t, s in enumerate(steps):
+        assert h["obs"][t, 0] == s["obs"] and h["reward"][t, 0] == s["reward"] and bool(h["done"][t, 0]) == s["done"], (label, t)
+        assert h["now"][t, 0] == s["now"], (label, t, h["now"][t, 0], s["now"])
+        assert_step_records(h["records"][t], s["records"], "%s step %d" % (label, t))
+    assert h["counts"][0, 0] == ntx, label
+    assert list(h["counts"][0, 1:1 + ns]) == list(nd[:ns]), label
+    assert list(h["counts"][0, 9:9 + ns]) == list(nrecv[:ns]), label
+
+
+@pytest.mark.parametrize("name", GOLDEN_NSENDERS)
+def test_oracle_and_core_match_reference_golden_nsenders(name):
+    doc = load_golden(name)
+    sc = doc["scenario"]
+    ns = sum(1 for d in sc["bands"][0]["devices"] if d["role"] == "sender")
+    dev, dur = _tapes(doc)
+    steps, ntx, nd, nrecv, _ = _oracle_tape(sc, dev, dur, do_reset=doc["do_reset"])
+    h = HS.gen_run(sc, dev, dur, do_reset=doc["do_reset"])
+    assert h["rc"] == 0
+    for t, g in enumerate(doc["steps"]):
+        # the restatement: every record identical (as in tests/test_oracle_golden.py)
+        o = steps[t]
+        assert (o["obs"], o["reward"], o["done"], o["now"]) == (g["obs"], g["reward"], g["done"], g["now"]), (name, t)
+        assert_step_records(o["records"], g["records"], "oracle %s step %d" % (name, t))
+        # the engine
+        assert (h["obs"][t, 0], h["reward"][t, 0], bool(h["done"][t, 0]), h["now"][t, 0]) == (g["obs"], g["reward"], g["done"], g["now"]), (name, t)
+        assert_step_records(h["records"][t], g["records"], "core %s step %d" % (name, t))
+    n_rx = [sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "rx" and r[3] == k) for k in range(ns)]
+    n_mrx = [sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "mrx" and r[3] == k) for k in range(ns)]
+    assert list(h["counts"][0, 1:1 + ns]) == n_rx and list(h["counts"][0, 9:9 + ns]) == n_mrx
+    assert sum(n_rx) > 0
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_core_general_random_vs_oracle(seed):
+    rs = np.random.RandomState(4000 + seed)
+    ns, nj = int(rs.randint(3, 9)), int(rs.randint(0, 17))
+    sc = random_scenario_n(rs, ns, nj, spread=float(rs.choice([1.5, 2.5, 6.0])), receive=bool(seed % 2), bursts=bool(seed % 3 == 0))
+    T = 70
+    dev = rs.randint(0, ns, size=(T, 1)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, 1)).astype(np.int32)
+    reset_at = None if seed % 4 else 25                  # env.reset() in the middle of a run: queued packets keep their sizes
+    steps, ntx, nd, nrecv, near = _oracle_tape(sc, dev, dur, do_reset=seed % 4 != 1, reset_at=reset_at)
+    h = HS.gen_run(sc, dev, dur, do_reset=seed % 4 != 1, reset_at=reset_at)
+    _assert_host_equals(h, steps, ntx, nd, nrecv, ns, "seed %d (%d senders, %d PHY-only)" % (seed, ns, nj))
+
+
+def test_core_general_default_scenario_equals_counter_traffic_env_golden():
+    """With two senders the general engine is CounterTrafficEnv: the golden of the reference's own class."""
+    doc = load_golden("default_reset_seed0")
+    dev, dur = _tapes(doc)
+    h = HS.gen_run(doc["scenario"], dev, dur, do_reset=True)
+    assert h["rc"] == 0
+    for t, g in enumerate(doc["steps"]):
+        assert (h["obs"][t, 0], h["reward"][t, 0], bool(h["done"][t, 0]), h["now"][t, 0]) == (g["obs"], g["reward"], g["done"], g["now"]), t
+        assert_step_records(h["records"][t], g["records"], "default step %d" % t)
+
+
+def test_core_general_batch_with_per_env_positions():
+    """Several band-sims side by side in the device layout ([word][sim]) with per-env geometries."""
+    rs = np.random.RandomState(77)
+    ns, nj, nenv, T = 4, 3, 6, 40
+    sc = random_scenario_n(rs, ns, nj, spread=2.0, receive=True)
+    nd = ns + 1 + nj
+    pos = rs.uniform(-2.5, 2.5, size=(nenv, nd, 2))
+    dev = rs.randint(0, ns, size=(T, nenv)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, nenv)).astype(np.int32)
+    h = HS.gen_run(sc, dev, dur, pos=pos)
+    assert h["rc"] == 0
+    for e in range(nenv):
+        sce = {"assignment_duration_factor": 1000, "bands": [dict(sc["bands"][0], devices=[dict(d, x=float(pos[e, i, 0]), y=float(pos[e, i, 1]))
+                                                                                           for i, d in enumerate(sc["bands"][0]["devices"])])]}
+        steps, ntx, ndl, nrecv, _ = _oracle_tape(sce, dev[:, e:e + 1], dur[:, e:e + 1])
+        for t, s in enumerate(steps):
+            assert h["obs"][t, e] == s["obs"] and h["reward"][t, e] == s["reward"] and h["now"][t, e] == s["now"], (e, t)
+        assert h["counts"][e, 0] == ntx and list(h["counts"][e, 1:1 + ns]) == list(ndl[:ns]) and list(h["counts"][e, 9:9 + ns]) == list(nrecv[:ns])
+
+
+def test_core_general_rejects_actions_outside_the_action_space():
+    rs = np.random.RandomState(5)
+    sc = random_scenario_n(rs, 3, 0)
+    h = HS.gen_run(sc, np.array([[3]], np.int32), np.array([[1]], np.int32))
+    assert h["rc"] != 0
+    h = HS.gen_run(sc, np.array([[1]], np.int32), np.array([[20]], np.int32))
+    assert h["rc"] != 0

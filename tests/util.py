@@ -101,6 +101,58 @@ def random_tapes(rs, nsteps, nenv, nb):
     return dev, dur
 
 
+GOLDEN_NSENDERS = ["nsenders_5s_3p_seed31", "nsenders_8s_6p_seed32", "nsenders_3s_16p_seed33"]
+
+BER_RTOL = 1e-9          # north star: 1e-6 relative in fp64; observed ~1e-15 (libm / libdevice pow, log10 differ by <= 2 ulp)
+
+
+def assert_step_records(got, want, label=""):
+    """Trace records of one step against the reference's (or the oracle's): same records in the same canonical
+    order; transmissions, deliveries, decider inputs (section, bit count) and verdicts bit-exact, BER values and
+    expected error sums within ``BER_RTOL`` relative.  Returns the largest relative deviation seen."""
+    got, want = canonical(got), canonical(want)
+    assert len(got) == len(want), (label, len(got), len(want))
+    worst = 0.0
+    for g, w in zip(got, want):
+        assert g[:4] == w[:4], (label, g, w)
+        if g[0] == "tx":
+            assert tuple(g[4:]) == tuple(w[4:]), (label, g, w)
+        elif g[0] == "ber":
+            rel = abs(g[4] - w[4]) / max(abs(w[4]), 1e-300)
+            worst = max(worst, rel)
+            assert rel <= BER_RTOL, (label, g, w)
+        elif g[0] == "dec":
+            assert g[4] == w[4] and g[6] == w[6] and g[7] == w[7], (label, g, w)
+            rel = abs(g[5] - w[5]) / max(abs(w[5]), 1e-300) if w[5] != 0 else abs(g[5])
+            worst = max(worst, rel)
+            assert rel <= BER_RTOL, (label, g, w)
+    return worst
+
+
+def random_scenario_n(rs, ns, nj, spread=2.5, factor=1000, receive=False, bursts=False):
+    """One band with ``ns`` MAC senders, the RRM and ``nj`` PHY-only senders (same generator as
+    ``oracle/check_restatement.py::random_scenario_n``, which pins the oracle against the live reference on it)."""
+    devs = []
+    for k in range(ns):
+        dest = int((k + 1 + rs.randint(ns - 1)) % ns)
+        d = {"role": "sender", "x": float(rs.uniform(-spread, spread)), "y": float(rs.uniform(-spread, spread)),
+             "mult": int(rs.randint(1, 4)), "payload": "counter" if rs.rand() < 0.6 else int(rs.randint(1, 60)),
+             "interval": float(rs.choice([0.001, 0.001, 0.0007, 0.0013])), "dest": dest}
+        if receive and rs.rand() < 0.6:
+            d["receive"] = True
+        if bursts and rs.rand() < 0.3:
+            d["max_ticks"] = int(rs.randint(5, 60))
+        devs.append(d)
+    devs.append({"role": "rrm", "x": float(rs.uniform(-spread, spread)), "y": float(rs.uniform(-spread, spread))})
+    for j in range(nj):
+        payload = int(rs.randint(12, 120))
+        airtime = (13 + payload) * 8 / 99999.9975
+        devs.append({"role": "jammer", "x": float(rs.uniform(-spread, spread)), "y": float(rs.uniform(-spread, spread)),
+                     "interval": float(airtime * rs.uniform(2.0, 9.0) * max(1, nj)), "delay": float(rs.uniform(0, 1e-2)),
+                     "power": float(rs.choice([0.0, 10.0, 20.0])), "hdr": 13, "payload": payload})
+    return {"assignment_duration_factor": factor, "bands": [{"frequency": 2.4e9, "bandwidth": 22e6, "devices": devs}]}
+
+
 GOLDEN_GRIDS = ["grid_static_n8", "grid_static_n20", "grid_mobile_n8", "grid_mobile_n20"]
 
 
