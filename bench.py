@@ -344,6 +344,52 @@ def cfg5_pendulum(dev_t, rank=0, world=1, steps=32):
             "mean_abs_angle_deg": float(torch.rad2deg(th).abs().mean())}
 
 
+def general_band(dev_t, rank=0, world=1, steps=24, n=65536, ns=8, nj=4):
+    """
+    The general band engine (gw_band.cuh): bands beyond CounterTrafficEnv's template --
+    8 MAC senders on a circle of 2 m around the RRM, each addressing its neighbour, 4 PHY-only interferers at 5 m,
+    run-time device counts, state in global memory.  65 536 envs per GPU, the first steps of fresh envs.
+    """
+    import math
+    import torch
+    import gymwipe_b200
+    devs = []
+    for k in range(ns):
+        a = 2 * math.pi * k / ns
+        devs.append({"role": "sender", "x": 2.0 * math.cos(a), "y": 2.0 * math.sin(a), "mult": 1 + k % 3, "payload": "counter",
+                     "interval": 0.001, "dest": (k + 1) % ns})
+    devs.append({"role": "rrm", "x": 0.0, "y": 0.0})
+    for j in range(nj):
+        a = 2 * math.pi * (j + 0.5) / nj
+        devs.append({"role": "jammer", "x": 5.0 * math.cos(a), "y": 5.0 * math.sin(a), "interval": 0.011 + 0.003 * j,
+                     "delay": 0.001 * j, "power": 10.0, "hdr": 13, "payload": 60})
+    sc = {"assignment_duration_factor": 1000, "bands": [{"frequency": 2.4e9, "bandwidth": 22e6, "devices": devs}]}
+    env = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, scenario=sc, strict=False)
+    env.reset()
+    g = torch.Generator(device=dev_t).manual_seed(17 + rank)
+    a_dev = torch.randint(0, ns, (steps + 4, n), generator=g, device=dev_t, dtype=torch.int32)
+    a_dur = torch.randint(0, 20, (steps + 4, n), generator=g, device=dev_t, dtype=torch.int32)
+    stream = torch.cuda.current_stream(dev_t)
+    for t in range(4):
+        env.step({"device": a_dev[t], "duration": a_dur[t]})
+    torch.cuda.synchronize(dev_t)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(4, 4 + steps):
+        env.step({"device": a_dev[t], "duration": a_dur[t]})
+    e1.record(stream)
+    torch.cuda.synchronize(dev_t)
+    env.check()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"workload": "general band engine: %d envs x (%d MAC senders + RRM + %d PHY-only senders), mode R, the first %d steps of "
+                       "fresh envs" % (n, ns, nj, steps + 4),
+           "n_envs": n, "env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms,
+           "transmissions_per_env_step": float(env.transmissions().sum()) / (steps + 4) / n,
+           "deliveries_per_env_step": float(env.delivered().sum()) / (steps + 4) / n}
+    env.close()
+    return out
+
+
 def grid_benchmark(dev_t, rank=0, world=1, n_envs=4096, n_devices=20):
     """
     The reference's own benchmark (tests/test_benchmark.py:52-91, `make benchmark`): a grid of 20 PHY-only
@@ -679,6 +725,7 @@ def own_arm(args, rank, world, local_rank):
         for name, fn in (("cfg3_long_packet_mode_m", lambda: cfg3_long_packet(dev_t, peak, rank, world)),
                          ("cfg4_multiband", lambda: cfg4_multiband(dev_t, rank, world)),
                          ("cfg5_pendulum", lambda: cfg5_pendulum(dev_t, rank, world)),
+                         ("general_band_8_senders", lambda: general_band(dev_t, rank, world)),
                          ("reference_benchmark_grid", lambda: grid_benchmark(dev_t, rank, world)),
                          ("mask_scan", lambda: mask_scan_roofline(dev_t, peak, "random") if world == 1 else None)):
             try:                                          # extras must never take the headline down

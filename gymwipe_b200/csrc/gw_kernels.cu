@@ -1970,8 +1970,9 @@ __global__ void genband_init_kernel(GenArgs A, GenBand B, const double *pos, con
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n_envs) return;
+    // per-env geometries: the table is evaluated here (libdevice log10 / pow: within 2 ulp of the host's); a geometry
+    // common to all envs is evaluated once on the host, with the C library the reference's Python runs on
     if (A.per_env) gen_power_table(B.nd, pos + i * B.nd * 2, power, frequency, A.srx + i, A.n_envs);
-    else if (i == 0) gen_power_table(B.nd, pos, power, frequency, A.srx, 1);
     GenView v = gen_view_of(A, B, i);
     gen_init(v, B);
 }
@@ -3181,6 +3182,19 @@ int gw_genband_create(const gw_genband_config *cfg, int device, const double *po
     if (e == cudaSuccess) e = cudaMemsetAsync(h->errflag, 0, 4 * sizeof(int), s);
     if (e == cudaSuccess) e = cudaMalloc((void **)&dpower, sizeof power);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dpower, power, sizeof power, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && !A.per_env) {
+        // The incrementally kept power sum of a PHY leaves residues of the size of an ulp of the STRONGEST signal it
+        // has seen, so a 1-ulp difference in one table entry moves a later noise power -- and the
+        // BER of a weak link -- by up to 1e-7 relative: the shared table is computed with the host's libm.
+        double hpos[2 * GW_GENBAND_MAX_DEVICES], tab[GW_GENBAND_MAX_DEVICES * GW_GENBAND_MAX_DEVICES];
+        e = cudaMemcpyAsync(hpos, positions, sizeof(double) * 2 * B.nd, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) {
+            gen_power_table(B.nd, hpos, power, cfg->frequency_hz, tab, 1);
+            e = cudaMemcpyAsync(A.srx, tab, sizeof(double) * B.nd * B.nd, cudaMemcpyHostToDevice, s);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);                     // `tab` is a stack array
+    }
     if (e == cudaSuccess) {
         A.errflag = h->errflag;
         genband_init_kernel<<<grid_for(cfg->n_envs, 64), 64, 0, s>>>(A, B, positions, dpower, cfg->frequency_hz);

@@ -124,3 +124,137 @@ def test_core_general_rejects_actions_outside_the_action_space():
     assert h["rc"] != 0
     h = HS.gen_run(sc, np.array([[1]], np.int32), np.array([[20]], np.int32))
     assert h["rc"] != 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU: the CUDA engine through the C ABI
+# ------------------------------------------------------------------------------------------------------------
+
+def _gpu_env(sc, n, **kw):
+    import gymwipe_b200
+    return gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device="cuda:0", scenario=sc, strict=False, **kw)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GOLDEN_NSENDERS)
+def test_cuda_general_band_matches_reference_golden(name):
+    import torch
+    from gymwipe_b200.envs import GeneralBandEnv
+    doc = load_golden(name)
+    sc = doc["scenario"]
+    ns = sum(1 for d in sc["bands"][0]["devices"] if d["role"] == "sender")
+    env = _gpu_env(sc, 1)
+    assert isinstance(env, GeneralBandEnv) and env.n_senders == ns
+    if doc["do_reset"]:
+        assert env.reset() == doc["reset_obs"]
+    worst = 0.0
+    for t, g in enumerate(doc["steps"]):
+        obs, rew, done, recs = env.step_traced({"device": g["action"]["device"], "duration": g["action"]["duration"]})
+        assert (obs, rew, done) == (g["obs"], g["reward"], g["done"]), (name, t)
+        assert float(env.now[0]) == g["now"], (name, t)
+        worst = max(worst, assert_step_records(recs, g["records"], "%s step %d" % (name, t)))
+    n_rx = [sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "rx" and r[3] == k) for k in range(ns)]
+    n_mrx = [sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "mrx" and r[3] == k) for k in range(ns)]
+    assert env.delivered()[0].tolist() == n_rx and env.received()[0].tolist() == n_mrx
+    print("%s: max relative BER / error-sum deviation vs reference %.3e" % (name, worst))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+def test_cuda_general_band_matches_oracle_batch(seed):
+    """2048 envs x 48 steps of a random N-sender band against the oracle: obs / reward / done / step end times and
+    the delivery counts per sender bit-exact."""
+    import torch
+    rs = np.random.RandomState(5200 + seed)
+    ns, nj = int(rs.randint(3, 9)), int(rs.randint(0, 17))
+    sc = random_scenario_n(rs, ns, nj, spread=float(rs.choice([1.5, 2.5])), receive=bool(seed % 2), bursts=bool(seed == 3))
+    nenv, T = 2048, 48
+    dev = rs.randint(0, ns, size=(T, nenv)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, nenv)).astype(np.int32)
+    o = O.run_batch(sc, dev, dur, do_reset=seed != 2)
+    env = _gpu_env(sc, nenv)
+    if seed != 2:
+        env.reset()
+    for t in range(T):
+        obs, rew, done, _ = env.step({"device": torch.as_tensor(dev[t]).cuda(), "duration": torch.as_tensor(dur[t]).cuda()})
+        assert (obs.cpu().numpy() == o["obs"][t, :, 0]).all(), (seed, t)
+        assert (rew.cpu().numpy() == o["reward"][t, :, 0]).all(), (seed, t)
+        assert (done.cpu().numpy() == o["done"][t, :, 0].astype(bool)).all(), (seed, t)
+        assert (env.now.cpu().numpy() == o["now"][t]).all(), (seed, t)
+    env.check()
+    assert (env.transmissions().cpu().numpy() == o["counts"][:, 0, 0]).all()
+    assert (env.delivered().cpu().numpy() == o["counts"][:, 0, 1:1 + ns]).all()
+    assert o["counts"][:, 0, 1:1 + ns].sum() > 1000
+
+
+@pytest.mark.gpu
+def test_cuda_general_band_per_env_positions_and_reset():
+    import torch
+    rs = np.random.RandomState(91)
+    ns, nj, nenv, T = 5, 4, 8, 30
+    sc = random_scenario_n(rs, ns, nj, spread=2.0, receive=True)
+    nd = ns + 1 + nj
+    pos = rs.uniform(-2.5, 2.5, size=(nenv, nd, 2))
+    dev = rs.randint(0, ns, size=(T, nenv)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, nenv)).astype(np.int32)
+    env = _gpu_env(sc, nenv, positions=torch.as_tensor(pos))
+    got = {k: [] for k in ("obs", "reward", "now")}
+    for t in range(T):
+        if t == 12:
+            env.reset()
+        obs, rew, done, _ = env.step({"device": torch.as_tensor(dev[t]).cuda(), "duration": torch.as_tensor(dur[t]).cuda()})
+        got["obs"].append(obs.cpu().numpy().copy()); got["reward"].append(rew.cpu().numpy().copy()); got["now"].append(env.now.cpu().numpy())
+    env.check()
+    deliv, recvd = env.delivered().cpu().numpy(), env.received().cpu().numpy()
+    for e in range(nenv):
+        sce = {"assignment_duration_factor": 1000, "bands": [dict(sc["bands"][0], devices=[dict(d, x=float(pos[e, i, 0]), y=float(pos[e, i, 1]))
+                                                                                           for i, d in enumerate(sc["bands"][0]["devices"])])]}
+        steps, ntx, ndl, nrecv, _ = _oracle_tape(sce, dev[:, e:e + 1], dur[:, e:e + 1], do_reset=False, reset_at=12)
+        for t, s in enumerate(steps):
+            assert got["obs"][t][e] == s["obs"] and got["reward"][t][e] == s["reward"] and got["now"][t][e] == s["now"], (e, t)
+        assert list(deliv[e]) == list(ndl[:ns]) and list(recvd[e]) == list(nrecv[:ns])
+
+
+@pytest.mark.gpu
+def test_cuda_general_band_two_senders_equal_the_step_kernel():
+    """ns = 2: the general engine and CounterTrafficEnv's fused step kernel are two implementations of the same env."""
+    import torch
+    import gymwipe_b200
+    from gymwipe_b200.envs import GeneralBandEnv
+    from gymwipe_b200.scenario import default_scenario_dict
+    sc = default_scenario_dict()
+    rs = np.random.RandomState(3)
+    nenv, T = 1024, 40
+    a = gymwipe_b200.make('CounterTraffic-v0', num_envs=nenv, device="cuda:0", strict=False)
+    b = GeneralBandEnv(num_envs=nenv, device="cuda:0", scenario=sc, strict=False)
+    a.reset(); b.reset()
+    for t in range(T):
+        act = {"device": torch.as_tensor(rs.randint(0, 2, nenv).astype(np.int32)).cuda(),
+               "duration": torch.as_tensor(rs.randint(0, 20, nenv).astype(np.int32)).cuda()}
+        oa, ra, da, _ = a.step(act)
+        ob, rb, db, _ = b.step(act)
+        assert torch.equal(oa.reshape(-1), ob) and torch.equal(ra.reshape(-1), rb), t
+    assert torch.equal(a.read_state(0).reshape(-1), b.now)
+    assert torch.equal(a.delivered().reshape(nenv, 2), b.delivered())
+
+
+@pytest.mark.gpu
+def test_cuda_general_band_rejects_bad_actions_and_bad_configs():
+    import torch
+    from gymwipe_b200 import _native as N
+    from gymwipe_b200.envs import GeneralBandEnv
+    rs = np.random.RandomState(5)
+    sc = random_scenario_n(rs, 3, 1)
+    env = GeneralBandEnv(num_envs=4, device="cuda:0", scenario=sc, strict=True)
+    env.reset()
+    ok = {"device": torch.tensor([0, 1, 2, 0], dtype=torch.int32).cuda(), "duration": torch.tensor([1, 2, 3, 4], dtype=torch.int32).cuda()}
+    env.step(ok)
+    now = env.now.clone()
+    with pytest.raises(N.NativeError) as e:
+        env.step({"device": torch.tensor([0, 3, 2, 0], dtype=torch.int32).cuda(), "duration": ok["duration"]})
+    assert e.value.code == N.GW_E_ACTION
+    assert env.now[1] == now[1] and env.faults().tolist() == [0, 0, 0, 0]      # the rejected env was not stepped
+    env.step(ok)                                                                 # and the batch goes on
+    bad = dict(sc, bands=[dict(sc["bands"][0], devices=[dict(d, dest=0) if d["role"] == "sender" else d for d in sc["bands"][0]["devices"]])])
+    with pytest.raises(N.NativeError):
+        GeneralBandEnv(num_envs=1, device="cuda:0", scenario=bad)
