@@ -11,8 +11,8 @@
 // time-out, per device one PHY event (slot start -> header end -> completion), per PHY-only sender a wake-up, the
 // RRM's guard time-out -- with the zero-delay event chains executed inline in SimPy's pop order.  Unlike the step
 // kernel nothing is unrolled or held in registers: every per-device array lives in the band-sim's state in global
-// memory ([field][index][sim]: consecutive threads touch consecutive words) and is indexed directly, queued packets
-// keep their sizes in an explicit ring, and the received-power changes are counted where they happen.  This is the
+// memory ([field][index][sim]: consecutive threads touch consecutive words) and is indexed directly, and the
+// received-power changes are counted where they happen.  This is the
 // general engine, not the tuned one: the 2-sender + RRM template keeps its own kernels.
 //
 // Reference semantics (file:line under /root/reference):
@@ -85,10 +85,10 @@ struct GenView {
     GW_HD uint32_t &seq() const { return ((uint32_t *)i)[(long long)I_seq * stride]; }
     GEN_I(sphase, 14) GEN_U(sEv, 14 + nd) GEN_U(sC, 14 + 2 * nd) GEN_I(cmdPay, 14 + 3 * nd) GEN_I(rxOf, 14 + 4 * nd)
     GEN_I(rxSec, 14 + 5 * nd) GEN_U(txSeq, 14 + 6 * nd)
-    GEN_U(sTick, 14 + 7 * nd) GEN_I(qh, 14 + 7 * nd + ns) GEN_I(qn, 14 + 7 * nd + 2 * ns) GEN_I(mac, 14 + 7 * nd + 3 * ns)
+    GEN_U(sTick, 14 + 7 * nd) GEN_U(epochK, 14 + 7 * nd + ns) GEN_I(qn, 14 + 7 * nd + 2 * ns) GEN_I(mac, 14 + 7 * nd + 3 * ns)
     GEN_I(wDone, 14 + 7 * nd + 4 * ns) GEN_I(wPend, 14 + 7 * nd + 5 * ns) GEN_U(sW, 14 + 7 * nd + 6 * ns)
     GEN_U(rxS, 14 + 7 * nd + 7 * ns) GEN_U(nDeliv, 14 + 7 * nd + 8 * ns) GEN_U(nRecv, 14 + 7 * nd + 9 * ns)
-    GEN_I(counter, 14 + 7 * nd + 10 * ns) GEN_U(ticksDone, 14 + 7 * nd + 11 * ns)
+    GEN_I(epochC, 14 + 7 * nd + 10 * ns) GEN_U(ticks, 14 + 7 * nd + 11 * ns)
     GEN_U(sJam, 14 + 7 * nd + 12 * ns) GEN_I(jamStage, 14 + 7 * nd + 12 * ns + nj) GEN_I(jamPending, 14 + 7 * nd + 12 * ns + 2 * nj)
     GW_HD int32_t &ring(int k, int slot) const { return i[(long long)(14 + 7 * nd + 12 * ns + 3 * nj + k * kQueueCap + slot) * stride]; }
 #undef GEN_F
@@ -134,8 +134,8 @@ GW_HD void gen_init(GenView &v, const GenBand &B)
     }
     for (int k = 0; k < ns; ++k) {
         v.tTick(k) = 0.0; v.sTick(k) = v.seq()++;
-        v.stopW(k) = 0; v.qh(k) = 0; v.qn(k) = 0; v.mac(k) = MAC_NONE; v.wDone(k) = 0; v.wPend(k) = 0; v.sW(k) = 0;
-        v.nDeliv(k) = 0; v.nRecv(k) = 0; v.counter(k) = 1; v.ticksDone(k) = 0;
+        v.stopW(k) = 0; v.epochK(k) = 0; v.qn(k) = 0; v.mac(k) = MAC_NONE; v.wDone(k) = 0; v.wPend(k) = 0; v.sW(k) = 0;
+        v.nDeliv(k) = 0; v.nRecv(k) = 0; v.epochC(k) = 1; v.ticks(k) = 0;
         for (int q = 0; q < kQueueCap; ++q) v.ring(k, q) = 0;
     }
     for (int j = 0; j < nj; ++j) { v.tJam(j) = 0.0; v.sJam(j) = v.seq()++; v.jamStage(j) = 0; v.jamPending(j) = 0; }
@@ -145,45 +145,56 @@ GW_HD void gen_init(GenView &v, const GenBand &B)
     }
 }
 
+// The sender queues are not stored: sender k enqueues `mult` packets per tick into a drop-oldest deque(maxlen = 100)
+// (SenderDevice.senderProcess, counter_traffic.py:53-61; SimpleMac.networkInHandler, simple_stack.py:463-471), so
+// after `ticks` ticks the queue holds the LAST qn of the ticks * mult packets enqueued so far, and packet j was
+// enqueued at tick j / mult with byteSize = the counter of that tick: min(COUNTER_BOUND, epochC + (tick - epochK)),
+// where (epochK, epochC) is the counter epoch -- (0, 1) after construction, (ticks at reset, 0) after a reset().
+// Packets that predate the last reset() keep the sizes they were enqueued with: reset materialises them into the
+// ring (slot j % 100: the queue holds at most 100 consecutive packets).  As in gw_core.cuh::head_size.
+// `ticks` is a 32-bit count: 2^32 ticks of 1 ms are 49 simulated days.
+GW_HD int gen_counter_at(const GenView &v, int k, uint32_t tick)
+{
+    const long long c = (long long)v.epochC(k) + (long long)(tick - v.epochK(k));
+    return c > kCounterBound ? kCounterBound : (int)c;
+}
+
+GW_HD int gen_head_size(const GenView &v, const GenBand &B, int k)
+{
+    const int rule = B.payloadRule[k];
+    if (rule >= 0) return rule;
+    const unsigned long long m = (unsigned long long)B.mult[k];
+    const unsigned long long enq = (unsigned long long)v.ticks(k) * m;
+    const unsigned long long j = enq - (unsigned long long)v.qn(k);
+    if (j < (unsigned long long)v.epochK(k) * m) return v.ring(k, (int)(j % kQueueCap));      // predates the last reset()
+    return gen_counter_at(v, k, (uint32_t)(j / m));
+}
+
 // CounterTrafficEnv.reset (counter_traffic.py:135-144): sender counters := 0, interpreter reset; time, queues
 // (with the sizes their packets were enqueued with) and PHY state stay
-GW_HD void gen_reset(GenView &v)
+GW_HD void gen_reset(GenView &v, const GenBand &B)
 {
-    for (int k = 0; k < v.ns; ++k) v.counter(k) = 0;
+    for (int k = 0; k < v.ns; ++k) {
+        const unsigned long long m = (unsigned long long)B.mult[k];
+        const unsigned long long enq = (unsigned long long)v.ticks(k) * m;
+        if (B.payloadRule[k] < 0) {
+            unsigned long long j = enq - (unsigned long long)v.qn(k);
+            if (j < (unsigned long long)v.epochK(k) * m) j = (unsigned long long)v.epochK(k) * m;   // materialised by an earlier reset()
+            for (; j < enq; ++j) v.ring(k, (int)(j % kQueueCap)) = gen_counter_at(v, k, (uint32_t)(j / m));
+        }
+        v.epochK(k) = v.ticks(k);
+        v.epochC(k) = 0;
+    }
     v.sc(GenView::I_latestDiff) = 0; v.sc(GenView::I_lastAbsDiff) = 0; v.sc(GenView::I_rv0) = 0; v.sc(GenView::I_rv1) = 0;
     v.sc(GenView::I_done) = 0;
 }
 
-// SimpleMac.networkInHandler for a Packet (simple_stack.py:463-471): deque(maxlen = 100) drops the oldest
-GW_HD void gen_enqueue(GenView &v, int k, int size)
-{
-    int h = v.qh(k), n = v.qn(k);
-    if (n == kQueueCap) { h = h + 1 == kQueueCap ? 0 : h + 1; n -= 1; }
-    int slot = h + n; if (slot >= kQueueCap) slot -= kQueueCap;
-    v.ring(k, slot) = size;
-    v.qh(k) = h; v.qn(k) = n + 1;
-}
-
-// `c` ticks of sender k's traffic process at once (SenderDevice.senderProcess, counter_traffic.py:53-61): per tick
-// `mult` packets of byteSize = counter (or the fixed size), counter += 1 up to COUNTER_BOUND; only the last 100
-// packets of the batch can survive in the queue
+// `c` ticks of sender k's traffic process at once
 GW_HD void gen_ticks(GenView &v, const GenBand &B, int k, uint32_t c)
 {
-    const int mult = B.mult[k], rule = B.payloadRule[k];
-    const int c0 = v.counter(k);
-    const long long M = (long long)c * mult;
-    long long j = M > kQueueCap ? M - kQueueCap : 0;
-    long long tick = j / mult;
-    int inTick = (int)(j - tick * mult);
-    for (; j < M; ++j) {
-        const long long cv = (long long)c0 + tick;
-        const int size = rule >= 0 ? rule : (cv > kCounterBound ? kCounterBound : (int)cv);
-        gen_enqueue(v, k, size);
-        if (++inTick == mult) { inTick = 0; ++tick; }
-    }
-    const long long c1 = (long long)c0 + c;
-    v.counter(k) = c1 > kCounterBound ? kCounterBound : (int)c1;
-    v.ticksDone(k) += c;
+    const unsigned long long n = (unsigned long long)v.qn(k) + (unsigned long long)c * (unsigned long long)B.mult[k];
+    v.qn(k) = n > (unsigned long long)kQueueCap ? kQueueCap : (int)n;         // drop-oldest
+    v.ticks(k) += c;
 }
 
 // Silent ticks of sender k strictly before (tEnd, qEnd): the tick times are accumulated with the reference's fp64
@@ -265,18 +276,28 @@ GW_HD void gen_count(GenView &v, const Params &P, int p)
 }
 
 // _nReceivedPowerChanges.trigger(delta): the power sum, then the running reception (simple_stack.py:81-86, 223-233)
-GW_HD void gen_power_change(GenView &v, const Params &P, int p, double delta, bool completingOwn)
+// Returns true if the PHY's bit error rate must be re-evaluated (the caller collects these PHYs: the evaluations
+// of an event read nothing that the rest of the event writes, so they are done after it -- by the warp as a whole
+// in the kernel, see gw_kernels.cu::genband_step_kernel).
+GW_HD bool gen_power_change(GenView &v, const Params &P, int p, double delta, bool completingOwn)
 {
     v.P(p) += delta;
     const int e = v.rxOf(p);
-    if (e < 0 || delta == 0.0) return;
+    if (e < 0 || delta == 0.0) return false;
     gen_count(v, P, p);
     const bool completed = v.now() >= v.tStop(e);
-    if (completed) return;
+    if (completed) return false;
     // `if not t.completed: _updateBitErrorRate(t)` with the power entry of its own transmission already popped:
     // the reference raises KeyError (appendix B #12)
-    if (completingOwn) { v.sc(GenView::I_fault) = FAULT_REF_KEYERROR; return; }
-    gen_update_ber(v, P, p);
+    if (completingOwn) { v.sc(GenView::I_fault) = FAULT_REF_KEYERROR; return false; }
+    return true;
+}
+
+// SimplePhy._updateBitErrorRate for the PHYs in berMask
+GW_HD void gen_update_bers(GenView &v, const Params &P, uint32_t berMask)
+{
+    for (int p = 0; p < v.nd; ++p)
+        if ((berMask >> p) & 1u) gen_update_ber(v, P, p);
 }
 
 GW_HD void gen_rx_clear(GenView &v, int p)
@@ -306,14 +327,12 @@ GW_HD void gen_phy_send_init(GenView &v, int d)
 }
 
 // one pass of the SimpleMac window loop body with a non-empty queue (simple_stack.py:417-434)
-GW_HD void gen_mac_try_send(GenView &v, const Params &P, int k)
+GW_HD void gen_mac_try_send(GenView &v, const Params &P, const GenBand &B, int k)
 {
-    const int size = v.ring(k, v.qh(k));
+    const int size = gen_head_size(v, B, k);
     const double timeLeft = v.stopW(k) - v.now();
     const double txTime = airtime_of(P, kMacHdr + kNetHdr + size);
     if (!(timeLeft > txTime)) { v.mac(k) = MAC_IDLE; return; }      // yield timeoutEvent
-    const int h = v.qh(k) + 1;
-    v.qh(k) = h == kQueueCap ? 0 : h;
     v.qn(k) -= 1;
     v.mac(k) = MAC_WAIT_TX;
     v.cmdPay(k) = kNetHdr + size;
@@ -321,24 +340,26 @@ GW_HD void gen_mac_try_send(GenView &v, const Params &P, int k)
 }
 
 // loop head of the window loop (simple_stack.py:408-416)
-GW_HD void gen_mac_loop_head(GenView &v, const Params &P, int k)
+GW_HD void gen_mac_loop_head(GenView &v, const Params &P, const GenBand &B, int k)
 {
     if (v.wDone(k)) { v.mac(k) = MAC_NONE; return; }
     if (v.qn(k) == 0) { v.mac(k) = MAC_WAIT_COND; return; }
-    gen_mac_try_send(v, P, k);
+    gen_mac_try_send(v, P, B, k);
 }
 
 GW_HD int gen_hdr_bytes(const GenView &v, const GenBand &B, int d) { return d > v.ns ? B.jamHdr[d - v.ns - 1] : kMacHdr; }
 
-// transition function: one timed event (the structure of gw_core.cuh::apply_event with run-time device counts)
-GW_HD void gen_apply(GenView &v, const Params &P, const GenBand &B, const Event &ev)
+// transition function: one timed event (the structure of gw_core.cuh::apply_event with run-time device counts);
+// returns the set of PHYs whose bit error rate must be re-evaluated afterwards (SimplePhy._updateBitErrorRate)
+GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Event &ev)
 {
     const int ns = v.ns, nd = v.nd, RRM = v.ns;
+    uint32_t berMask = 0;
     v.now() = ev.t;
     switch (ev.kind) {
     case EV_TICK: {
         const int k = ev.idx;
-        if (B.maxTicks[k] != 0 && v.ticksDone(k) >= (uint32_t)B.maxTicks[k]) {
+        if (B.maxTicks[k] != 0 && v.ticks(k) >= (uint32_t)B.maxTicks[k]) {
             // the burst is over: this wake-up only ends the traffic process (its process event takes a number)
             v.tTick(k) = (double)INFINITY;
             v.seq()++;
@@ -347,7 +368,7 @@ GW_HD void gen_apply(GenView &v, const Params &P, const GenBand &B, const Event 
         gen_ticks(v, B, k, 1u);
         v.tTick(k) = v.now() + B.interval[k];
         v.sTick(k) = v.seq()++;
-        if (v.mac(k) == MAC_WAIT_COND) gen_mac_try_send(v, P, k);   // _packetAddedEvent wakes the window loop
+        if (v.mac(k) == MAC_WAIT_COND) gen_mac_try_send(v, P, B, k);   // _packetAddedEvent wakes the window loop
         break;
     }
     case EV_JAM: {
@@ -386,13 +407,13 @@ GW_HD void gen_apply(GenView &v, const Params &P, const GenBand &B, const Event 
             // zero-delay notification: every other PHY registers the received power (simple_stack.py:130-144)
             for (int p = 0; p < nd; ++p) {
                 if (p == d) continue;
-                gen_power_change(v, P, p, v.rp(p, d), false);
+                if (gen_power_change(v, P, p, v.rp(p, d), false)) berMask |= 1u << p;
             }
             // receive processes in PHY construction order: idle, non-transmitting PHYs lock on (simple_stack.py:214-235)
             for (int p = 0; p < nd; ++p) {
                 if (p == d || v.rxOf(p) >= 0 || v.sphase(p) >= S_SLOT) continue;
                 v.rxOf(p) = d; v.rxSec(p) = 0; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = now;
-                gen_update_ber(v, P, p);
+                berMask |= 1u << p;
             }
         } else if (ph == S_HDR) {
             // eHeaderCompletes: receivers decide on the header (simple_stack.py:241-251)
@@ -403,7 +424,7 @@ GW_HD void gen_apply(GenView &v, const Params &P, const GenBand &B, const Event 
                 gen_count(v, P, p);
                 if (gen_decide(v, P, p, 0, hdrBits)) {
                     v.rxSec(p) = 1; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = v.now();  // _resetBitErrorCounter
-                    gen_update_ber(v, P, p);
+                    berMask |= 1u << p;
                 } else {
                     gen_rx_clear(v, p);
                     if (v.sphase(p) == S_WAITRX) wake |= 1u << p;
@@ -419,7 +440,7 @@ GW_HD void gen_apply(GenView &v, const Params &P, const GenBand &B, const Event 
             // 2. _onCompletingTransmission of every other PHY (simple_stack.py:146-157)
             for (int p = 0; p < nd; ++p) {
                 if (p == d) continue;
-                gen_power_change(v, P, p, -v.rp(p, d), v.rxOf(p) == d);
+                if (gen_power_change(v, P, p, -v.rp(p, d), v.rxOf(p) == d)) berMask |= 1u << p;
             }
             // 3. receivers that passed the header count again (appendix B #4), decide on the payload and deliver
             int window = -1;
@@ -461,11 +482,11 @@ GW_HD void gen_apply(GenView &v, const Params &P, const GenBand &B, const Event 
                 v.sW(window) = v.seq()++;
                 v.wPend(window) = 1;
                 v.wDone(window) = 0;
-                gen_mac_loop_head(v, P, window);
+                gen_mac_loop_head(v, P, B, window);
             }
             // b. SEND eProcessed: the sender's upper layer resumes
             if (d < ns) {
-                gen_mac_loop_head(v, P, d);                         // `yield message.eProcessed` returns
+                gen_mac_loop_head(v, P, B, d);                       // `yield message.eProcessed` returns
             } else if (d == RRM) {
                 v.tRrm() = v.now() + (v.annSlots() + 1) * kSlot;    // simple_stack.py:558
                 v.sc(GenView::I_sRrm) = (int32_t)(v.seq()++);
@@ -509,6 +530,7 @@ GW_HD void gen_apply(GenView &v, const Params &P, const GenBand &B, const Event 
     default:
         v.sc(GenView::I_fault) = FAULT_EMPTY;
     }
+    return berMask;
 }
 
 // SimpleRrmDevice.assignFrequencyBand + SimpleRrmMac._sendAnnouncement start (devices.py:178-203,
@@ -541,28 +563,45 @@ GW_HD void gen_feedback(GenView &v, long long &obs, double &reward, unsigned cha
     done = (unsigned char)v.sc(GenView::I_done);
 }
 
-// env.step(action): assign, run until the ASSIGN message is processed (counter_traffic.py:146-158), feedback.
+// env.step(action) in three pieces (counter_traffic.py:146-158): assign; run until the ASSIGN message is processed --
+// one timed event per call, each followed by the BER evaluations it asks for --; the interpreter's feedback.
 // An action outside the action space (the reference asserts) leaves the band-sim untouched and reports a fault.
-GW_HD void gen_step(GenView &v, const Params &P, const GenBand &B, int device, int duration, long long &obs,
-                    double &reward, unsigned char &done)
+GW_HD bool gen_step_begin(GenView &v, const Params &P, const GenBand &B, int device, int duration)
 {
-    if (v.sc(GenView::I_fault) == 0) {
-        if (device < 0 || device >= v.ns || duration < 0 || duration >= B.maxDuration) {
-            v.sc(GenView::I_fault) = FAULT_EMPTY + 1;              // FAULT_ACTION of the C ABI
-        } else {
-            gen_begin_assignment(v, P, device, duration);
-            while (!v.sc(GenView::I_assignDone) && !v.sc(GenView::I_fault)) {
-                const Event ev = gen_next_event(v, B);
-                gen_apply(v, P, B, ev);
-            }
-        }
+    if (v.sc(GenView::I_fault) != 0) return false;
+    if (device < 0 || device >= v.ns || duration < 0 || duration >= B.maxDuration) {
+        v.sc(GenView::I_fault) = FAULT_EMPTY + 1;                  // FAULT_ACTION of the C ABI
+        return false;
     }
+    gen_begin_assignment(v, P, device, duration);
+    return v.sc(GenView::I_fault) == 0;
+}
+
+GW_HD bool gen_step_running(const GenView &v) { return !v.sc(GenView::I_assignDone) && !v.sc(GenView::I_fault); }
+
+GW_HD uint32_t gen_step_event(GenView &v, const Params &P, const GenBand &B)
+{
+    const Event ev = gen_next_event(v, B);
+    return gen_apply(v, P, B, ev);
+}
+
+GW_HD void gen_step_end(GenView &v, long long &obs, double &reward, unsigned char &done)
+{
     if (v.sc(GenView::I_fault)) {
         // a rejected action or a faulted band-sim: nothing happened, the interpreter is not consulted
         obs = (long long)v.sc(GenView::I_latestDiff) + kCounterBound; reward = 0.0; done = (unsigned char)v.sc(GenView::I_done);
         return;
     }
     gen_feedback(v, obs, reward, done);
+}
+
+// the serial driver (host build, traced kernel)
+GW_HD void gen_step(GenView &v, const Params &P, const GenBand &B, int device, int duration, long long &obs,
+                    double &reward, unsigned char &done)
+{
+    if (gen_step_begin(v, P, B, device, duration))
+        while (gen_step_running(v)) gen_update_bers(v, P, gen_step_event(v, P, B));
+    gen_step_end(v, obs, reward, done);
 }
 
 }  // namespace gw

@@ -1982,21 +1982,89 @@ __global__ void genband_reset_kernel(GenArgs A, GenBand B, long long *obs)
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n_envs) return;
     GenView v = gen_view_of(A, B, i);
-    gen_reset(v);
+    gen_reset(v, B);
     if (obs) obs[i] = (long long)kCounterBound;
 }
 
-__global__ void __launch_bounds__(64)
+// launch configuration (profiles/README.md, r4e): 128 threads x 4 blocks per SM = 128 registers, 16 resident warps per
+// SM -- 2.57 ms per step of the 8 + 1 + 4 band against 3.72 ms with 64-thread blocks at 152 registers
+#ifndef GW_GEN_BLOCK
+#define GW_GEN_BLOCK 128
+#endif
+#ifndef GW_GEN_MINB
+#define GW_GEN_MINB 4
+#endif
+// One band-sim per thread; the lanes of a warp sit at different events of different kinds (ncu: 4 of 32 lanes active
+// per instruction), and what most of them execute most of the time is SimplePhy._updateBitErrorRate -- on a band with
+// a dozen PHYs every transmission that starts or ends makes every receiving PHY re-evaluate its BER (2 log10, exp10,
+// sqrt, 2 exp, a division: ~600 fp64-heavy instructions each, 90 % of the kernel's instructions when each lane
+// evaluates its own).  The evaluations of an event read nothing the rest of the event writes, so the transition
+// function only COLLECTS them (gen_apply's berMask) and the WARP evaluates the collected (env, PHY) pairs of all
+// its lanes together, one pair per lane, 32 at a time: any lane can evaluate any env's pair because the state lives
+// in global memory.  Lanes whose step has ended keep helping until the whole warp is done.
+__global__ void __launch_bounds__(GW_GEN_BLOCK, GW_GEN_MINB)
 genband_step_kernel(GenArgs A, Params P, GenBand B, const int32_t *device, const int32_t *duration, long long *obs,
                     double *reward, unsigned char *done)
 {
+    constexpr unsigned FULL = 0xffffffffu;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.n_envs) return;
-    GenView v = gen_view_of(A, B, i);
-    if (A.trace) { v.trace = A.trace + i * A.trace_cap * 8; v.traceCap = A.trace_cap; }
-    const int before = v.sc(GenView::I_fault);
+    const bool valid = i < A.n_envs;
+    const unsigned lane = threadIdx.x & 31u;
+    const long long warpEnv0 = i - lane;
+    GenView v = gen_view_of(A, B, valid ? i : A.n_envs - 1);
+    if (A.trace) { v.trace = A.trace + (valid ? i : 0) * A.trace_cap * 8; v.traceCap = A.trace_cap; }
+    int before = 0;
+    bool run = false;
+    if (valid) {
+        before = v.sc(GenView::I_fault);
+        run = gen_step_begin(v, P, B, device[i], duration[i]);
+    }
+    const bool serial = A.trace != nullptr;             // the traced variant keeps the BER records in event order
+    for (;;) {
+        uint32_t mask = 0;
+        if (run) {
+            if (gen_step_running(v)) mask = gen_step_event(v, P, B);
+            else run = false;
+        }
+        if (serial) {
+            if (run) gen_update_bers(v, P, mask);
+            if (!__any_sync(FULL, run)) break;
+            continue;
+        }
+        __syncwarp();                                   // the owners' state updates are visible to the helpers
+        const int cnt = __popc(mask);
+        int pre = cnt;                                  // inclusive prefix sum of the lanes' counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, pre, o);
+            if ((int)lane >= o) pre += t;
+        }
+        const int total = __shfl_sync(FULL, pre, 31);
+        const int excl = pre - cnt;
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = t0 + (int)lane;
+            // owner of item t: the number of lanes whose inclusive prefix is <= t
+            int owner = 0;
+#pragma unroll
+            for (int stepw = 16; stepw >= 1; stepw >>= 1) {
+                const int q = __shfl_sync(FULL, pre, owner + stepw - 1);
+                if (q <= t) owner += stepw;
+            }
+            const int ol = owner < 32 ? owner : 31;
+            const int oExcl = __shfl_sync(FULL, excl, ol);
+            const uint32_t oMask = __shfl_sync(FULL, mask, ol);
+            if (t < total) {
+                const int p = (int)__fns(oMask, 0u, t - oExcl + 1);
+                GenView w = gen_view_of(A, B, warpEnv0 + ol);
+                gen_update_ber(w, P, p);
+            }
+        }
+        __syncwarp();                                   // the evaluated rates are visible to their owners
+        if (!__any_sync(FULL, run)) break;
+    }
+    if (!valid) return;
     long long o; double r; unsigned char d;
-    gen_step(v, P, B, device[i], duration[i], o, r, d);
+    gen_step_end(v, o, r, d);
     obs[i] = o; reward[i] = r; done[i] = d;
     if (A.trace) A.trace_count[i] = v.ntrace;
     const int fault = v.sc(GenView::I_fault);
@@ -2025,7 +2093,7 @@ __global__ void genband_read_kernel(GenArgs A, GenBand B, int field, double *out
             if (field == GW_GENBAND_FIELD_DELIVERED) x = v.nDeliv(k);
             else if (field == GW_GENBAND_FIELD_RECEIVED) x = v.nRecv(k);
             else if (field == GW_GENBAND_FIELD_QUEUE_LENGTH) x = v.qn(k);
-            else if (field == GW_GENBAND_FIELD_COUNTER) x = v.counter(k);
+            else if (field == GW_GENBAND_FIELD_COUNTER) x = gen_counter_at(v, k, v.ticks(k));
             out[k * n + i] = x;
         }
     }
@@ -3235,7 +3303,7 @@ static int genband_launch(gw_genband_handle *h, const int32_t *device, const int
     CUDA_TRY(cudaSetDevice(h->device));
     GenArgs A = h->A;
     A.trace = trace; A.trace_count = trace_count; A.trace_cap = cap;
-    genband_step_kernel<<<grid_for(A.n_envs, 64), 64, 0, (cudaStream_t)stream>>>(A, h->P, h->B, device, duration, (long long *)obs,
+    genband_step_kernel<<<grid_for(A.n_envs, GW_GEN_BLOCK), GW_GEN_BLOCK, 0, (cudaStream_t)stream>>>(A, h->P, h->B, device, duration, (long long *)obs,
                                                                                reward, done);
     CUDA_TRY(cudaGetLastError());
     return GW_OK;

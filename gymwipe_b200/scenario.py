@@ -103,7 +103,10 @@ def compile_stack(bands, assignment_duration_factor=1000):
     ``SimpleRrmMac`` (the band's RRM); a PHY whose ``"mac"`` port leads to no MAC is a PHY-only periodic
     sender (``tests/test_benchmark.py:20-50``).  Traffic parameters are the device's attributes
     (``packetMultiplicity`` / ``interval`` / ``payloadRule``; ``sendInterval`` / ``initialDelay`` / ``power`` /
-    ``headerBytes`` / ``payloadBytes``).  Raises ``ValueError`` for stacks the step kernel has no table for.
+    ``headerBytes`` / ``payloadBytes``; with more than two senders ``destination``: the addressed sender).  Bands of 2
+    senders + RRM (+ 1 PHY-only sender) compile to the step kernels' template, larger ones (up to 8 senders and 16
+    PHY-only senders) to the general band engine -- ``gymwipe_b200.make('CounterTraffic-v0', scenario=...)`` picks the
+    engine.  Raises ``ValueError`` for stacks neither has a table for.
     """
     from gymwipe_b200.networking.construction import Module, Port
     from gymwipe_b200.networking.simple_stack import SimpleMac, SimplePhy, SimpleRrmMac
@@ -149,14 +152,25 @@ def compile_stack(bands, assignment_duration_factor=1000):
                 jammers.append(dv)
         if len(rrms) != 1:
             raise ValueError("a band needs exactly one RRM stack (SimplePhy <-> SimpleRrmMac), found %d" % len(rrms))
-        if len(senders) != 2 or len(jammers) > N.GW_MAX_JAMMERS:
-            raise ValueError("step-kernel tables exist for 2 MAC senders + RRM + up to %d PHY-only sender(s) per band; "
-                             "got %d / %d" % (N.GW_MAX_JAMMERS, len(senders), len(jammers)))
+        # 2 MAC senders + RRM + up to GW_MAX_JAMMERS PHY-only sender(s): the step kernels' template; up to
+        # GW_GENBAND_MAX_SENDERS / GW_GENBAND_MAX_PHY_SENDERS: the general band engine (envs/general_band.py)
+        if not 2 <= len(senders) <= N.GW_GENBAND_MAX_SENDERS or len(jammers) > N.GW_GENBAND_MAX_PHY_SENDERS:
+            raise ValueError("a band holds 2..%d MAC senders + RRM + up to %d PHY-only senders; got %d / %d"
+                             % (N.GW_GENBAND_MAX_SENDERS, N.GW_GENBAND_MAX_PHY_SENDERS, len(senders), len(jammers)))
         entries = []
         for i, dv in enumerate(senders):
+            if len(senders) == 2:
+                dest = 1 - i                        # counter_traffic.py:128-129: the two senders address each other
+            else:
+                target = getattr(dv, "destination", None)       # the addressed sender: a device object or its index
+                if target is None:
+                    raise ValueError("%r: with more than two senders every sender needs a `destination`" % (dv,))
+                dest = target if isinstance(target, int) else next((k for k, o in enumerate(senders) if o is target), -1)
+                if not 0 <= dest < len(senders) or dest == i:
+                    raise ValueError("%r: `destination` must be another sender of the band" % (dv,))
             entries.append({"role": "sender", "x": dv.position.x, "y": dv.position.y,
                             "mult": getattr(dv, "packetMultiplicity", 1), "payload": getattr(dv, "payloadRule", "counter"),
-                            "interval": getattr(dv, "interval", 0.001), "dest": 1 - i})
+                            "interval": getattr(dv, "interval", 0.001), "dest": dest})
         entries.append({"role": "rrm", "x": rrms[0].position.x, "y": rrms[0].position.y})
         for dv in jammers:
             for attr in ("sendInterval", "initialDelay", "payloadBytes"):

@@ -356,7 +356,7 @@ int hs_gen_run(int ns, int nj, int factor, double frequency, double bandwidth, c
     for (int t = 0; t < nsteps; ++t) {
         for (int64_t e = 0; e < nenv; ++e) {
             GenView v = view(e);
-            if (t == reset_at) gen_reset(v);
+            if (t == reset_at) gen_reset(v, B);
             if (e == 0 && trace) { v.trace = trace + (size_t)used * 8; v.traceCap = trace_cap - used; }
             long long o; double r; unsigned char d;
             gen_step(v, P, B, dev_tape[(size_t)t * nenv + e], dur_tape[(size_t)t * nenv + e], o, r, d);

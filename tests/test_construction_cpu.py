@@ -331,3 +331,84 @@ def test_compiled_stack_runs_on_the_step_kernel():
     assert obs - env.COUNTER_BOUND == 2 and reward == -2
     obs, reward, done, info = env.step({"device": 1, "duration": 12})
     assert obs - env.COUNTER_BOUND == 0 and reward == 2
+
+
+def _wired_band_n(n_senders=4, n_phy_only=2):
+    """A band beyond CounterTrafficEnv's template, wired by hand: n MAC senders on a circle, each addressing the
+    next one, the RRM in the middle, PHY-only senders outside."""
+    import math
+    from gymwipe_b200.networking.attenuation_models import FsplAttenuation
+    from gymwipe_b200.networking.devices import NetworkDevice, PhySenderDevice
+    from gymwipe_b200.networking.physical import FrequencyBand
+    from gymwipe_b200.networking.simple_stack import SimpleMac, SimplePhy, SimpleRrmMac
+    band = FrequencyBand([FsplAttenuation])
+
+    class Sender(NetworkDevice):
+        def __init__(self, k):
+            a = 2 * math.pi * k / n_senders
+            super().__init__("Sender %d" % k, 2 * math.cos(a), 2 * math.sin(a), band)
+            self.packetMultiplicity = 1 + k % 3
+            self.phy = SimplePhy("phy", self, band)
+            self.mac = SimpleMac("mac", self, band.spec, SimpleMac.macAddress(k + 1))
+            self.mac.ports["phy"].biConnectWith(self.phy.ports["mac"])
+
+    class Rrm(NetworkDevice):
+        def __init__(self):
+            super().__init__("RRM", 0.0, 0.0, band)
+            self.phy = SimplePhy("phy", self, band)
+            self.mac = SimpleRrmMac("mac", self, band.spec)
+            self.mac.ports["phy"].biConnectWith(self.phy.ports["mac"])
+
+    senders = [Sender(k) for k in range(n_senders)]
+    for k, s in enumerate(senders):
+        s.destination = senders[(k + 1) % n_senders]
+    rrm = Rrm()
+    for j in range(n_phy_only):
+        PhySenderDevice("Interferer %d" % j, 6.0 + j, 0.0, band, sendInterval=0.02 + 0.005 * j, initialDelay=0.001 * j, power=10.0,
+                        payloadBytes=40)
+    return band, senders, rrm
+
+
+def test_compile_stack_bands_beyond_the_template():
+    from gymwipe_b200.envs import fits_step_kernel_template
+    from gymwipe_b200.scenario import compile_stack
+    band, senders, rrm = _wired_band_n(4, 2)
+    sc = compile_stack([band])
+    devs = sc["bands"][0]["devices"]
+    assert [d["role"] for d in devs] == ["sender"] * 4 + ["rrm"] + ["jammer"] * 2
+    assert [d["dest"] for d in devs[:4]] == [1, 2, 3, 0] and [d["mult"] for d in devs[:4]] == [1, 2, 3, 1]
+    assert not fits_step_kernel_template(sc)
+    del senders[2].destination
+    with pytest.raises(ValueError, match="destination"):
+        compile_stack([band])
+    band9, _, _ = _wired_band_n(9, 0)
+    with pytest.raises(ValueError, match="2..8 MAC senders"):
+        compile_stack([band9])
+
+
+@pytest.mark.gpu
+def test_compiled_stack_beyond_the_template_runs_on_the_general_band_engine():
+    """A hand-wired band of 4 senders + RRM + 2 PHY-only senders compiles to a table that `make` hands to the general
+    band engine; its steps equal the oracle's."""
+    import numpy as np
+    import torch
+    import gymwipe_b200
+    import gw_oracle as O
+    from gymwipe_b200.envs import GeneralBandEnv
+    from gymwipe_b200.scenario import compile_stack
+    band, _, _ = _wired_band_n(4, 2)
+    sc = compile_stack([band])
+    nenv, T = 64, 30
+    rs = np.random.RandomState(12)
+    dev = rs.randint(0, 4, size=(T, nenv)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, nenv)).astype(np.int32)
+    o = O.run_batch(sc, dev, dur)
+    env = gymwipe_b200.make('CounterTraffic-v0', num_envs=nenv, scenario=sc, strict=False)
+    assert isinstance(env, GeneralBandEnv)
+    env.reset()
+    for t in range(T):
+        obs, rew, done, _ = env.step({"device": torch.as_tensor(dev[t]).cuda(), "duration": torch.as_tensor(dur[t]).cuda()})
+        assert (obs.cpu().numpy() == o["obs"][t, :, 0]).all() and (rew.cpu().numpy() == o["reward"][t, :, 0]).all()
+        assert (env.now.cpu().numpy() == o["now"][t]).all()
+    env.check()
+    assert (env.delivered().cpu().numpy() == o["counts"][:, 0, 1:5]).all() and o["counts"][:, 0, 1:5].sum() > 0
