@@ -344,7 +344,7 @@ def cfg5_pendulum(dev_t, rank=0, world=1, steps=32):
             "mean_abs_angle_deg": float(torch.rad2deg(th).abs().mean())}
 
 
-def general_band(dev_t, rank=0, world=1, steps=24, n=65536, ns=8, nj=4):
+def general_band(dev_t, rank=0, world=1, steps=24, n=65536, ns=8, nj=4, mode="reference", with_mode_m=True):
     """
     The general band engine (gw_band.cuh): bands beyond CounterTrafficEnv's template --
     8 MAC senders on a circle of 2 m around the RRM, each addressing its neighbour, 4 PHY-only interferers at 5 m,
@@ -364,7 +364,8 @@ def general_band(dev_t, rank=0, world=1, steps=24, n=65536, ns=8, nj=4):
         devs.append({"role": "jammer", "x": 5.0 * math.cos(a), "y": 5.0 * math.sin(a), "interval": 0.011 + 0.003 * j,
                      "delay": 0.001 * j, "power": 10.0, "hdr": 13, "payload": 60})
     sc = {"assignment_duration_factor": 1000, "bands": [{"frequency": 2.4e9, "bandwidth": 22e6, "devices": devs}]}
-    env = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, scenario=sc, strict=False)
+    env = gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, scenario=sc, strict=False, mode=mode, seed=99,
+                            env_id_offset=rank * n)
     env.reset()
     g = torch.Generator(device=dev_t).manual_seed(17 + rank)
     a_dev = torch.randint(0, ns, (steps + 4, n), generator=g, device=dev_t, dtype=torch.int32)
@@ -381,12 +382,17 @@ def general_band(dev_t, rank=0, world=1, steps=24, n=65536, ns=8, nj=4):
     torch.cuda.synchronize(dev_t)
     env.check()
     ms = e0.elapsed_time(e1) / steps
-    out = {"workload": "general band engine: %d envs x (%d MAC senders + RRM + %d PHY-only senders), mode R, the first %d steps of "
-                       "fresh envs" % (n, ns, nj, steps + 4),
+    out = {"workload": "general band engine: %d envs x (%d MAC senders + RRM + %d PHY-only senders), mode %s, the first %d steps of "
+                       "fresh envs" % (n, ns, nj, "R" if mode == "reference" else "M (Philox masks)", steps + 4),
            "n_envs": n, "env_steps_per_s": n / (ms * 1e-3), "ms_per_step": ms,
            "transmissions_per_env_step": float(env.transmissions().sum()) / (steps + 4) / n,
            "deliveries_per_env_step": float(env.delivered().sum()) / (steps + 4) / n}
     env.close()
+    del env
+    torch.cuda.empty_cache()
+    if with_mode_m and mode == "reference":
+        m = general_band(dev_t, rank, world, steps=8, n=n, ns=ns, nj=nj, mode="mask_philox")
+        out["mode_m_philox"] = {k: m[k] for k in ("env_steps_per_s", "ms_per_step", "deliveries_per_env_step")}
     return out
 
 

@@ -81,7 +81,8 @@ GW_GENBAND_MAX_DEVICES = GW_GENBAND_MAX_SENDERS + 1 + GW_GENBAND_MAX_PHY_SENDERS
 class GenBandConfig(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("n_envs", C.c_int64), ("n_senders", C.c_int32), ("n_phy_senders", C.c_int32),
                 ("assignment_duration_factor", C.c_int32), ("max_assign_duration", C.c_int32),
-                ("per_env_positions", C.c_int32), ("frequency_hz", C.c_double), ("bandwidth_hz", C.c_double),
+                ("per_env_positions", C.c_int32), ("mode", C.c_int32), ("seed", C.c_uint64), ("env_id_offset", C.c_int64),
+                ("frequency_hz", C.c_double), ("bandwidth_hz", C.c_double),
                 ("multiplicity", C.c_int32 * GW_GENBAND_MAX_SENDERS), ("payload_bytes", C.c_int32 * GW_GENBAND_MAX_SENDERS),
                 ("destination", C.c_int32 * GW_GENBAND_MAX_SENDERS), ("max_ticks", C.c_int32 * GW_GENBAND_MAX_SENDERS),
                 ("receive", C.c_int32 * GW_GENBAND_MAX_SENDERS), ("interval", C.c_double * GW_GENBAND_MAX_SENDERS),

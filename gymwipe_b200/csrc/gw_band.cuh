@@ -38,6 +38,9 @@ constexpr int kGenMaxSend = 8, kGenMaxJam = 16, kGenMaxDev = kGenMaxSend + 1 + k
 struct GenBand {
     int ns, nj, nd;
     int maxDuration;                    // action space: duration in [0, maxDuration)
+    int mode;                           // MODE_R (reference accounting) or MODE_M_PHILOX (per-bit Philox error masks)
+    unsigned long long seed;            // mode M: Philox seed
+    long long envOffset;                // mode M: global id of env 0 (sharding keeps results invariant)
     double thermal;
     int mult[kGenMaxSend];
     int payloadRule[kGenMaxSend];       // -1: byteSize = counter
@@ -50,7 +53,7 @@ struct GenBand {
 };
 
 // words of one band-sim's state
-GW_HD int gen_f64_words(int ns, int nj) { return 3 + 7 * (ns + 1 + nj) + 3 * ns + nj; }
+GW_HD int gen_f64_words(int ns, int nj) { return 3 + 9 * (ns + 1 + nj) + 3 * ns + nj; }
 GW_HD int gen_i32_words(int ns, int nj) { return 14 + 7 * (ns + 1 + nj) + 12 * ns + 3 * nj + kQueueCap * ns; }
 
 // view of one band-sim: word w of the fp64 / int32 state at f[w * stride] / i[w * stride]
@@ -61,6 +64,7 @@ struct GenView {
     const double *srx;                  // received power (mW), entry (receiver p, sender d) at srx[(p * nd + d) * srxStride]
     long long srxStride;
     int ns, nj, nd;
+    long long env;                      // global env id (mode M: key of the error masks)
     double *trace;                      // optional event trace (records of 8 doubles, as gw_core.cuh::trace_rec)
     int ntrace, traceCap;
 
@@ -74,10 +78,11 @@ struct GenView {
     // PHY, per device (names as in gw_core.cuh::Sim)
     GEN_F(P, 3) GEN_F(tEv, 3 + nd) GEN_F(tStop, 3 + 2 * nd) GEN_F(tC, 3 + 3 * nd) GEN_F(ber, 3 + 4 * nd)
     GEN_F(err, 3 + 5 * nd) GEN_F(tReset, 3 + 6 * nd)
+    GEN_F(txStart, 3 + 7 * nd) GEN_F(segT0, 3 + 8 * nd)        // mode M: Transmission.startTime; start of the running segment
     // senders
-    GEN_F(tTick, 3 + 7 * nd) GEN_F(stopW, 3 + 7 * nd + ns) GEN_F(rxT, 3 + 7 * nd + 2 * ns)
+    GEN_F(tTick, 3 + 9 * nd) GEN_F(stopW, 3 + 9 * nd + ns) GEN_F(rxT, 3 + 9 * nd + 2 * ns)
     // PHY-only senders
-    GEN_F(tJam, 3 + 7 * nd + 3 * ns)
+    GEN_F(tJam, 3 + 9 * nd + 3 * ns)
 
     enum : int { I_seq = 0, I_fault, I_ties, I_annDest, I_rrmPend, I_sRrm, I_assignDone, I_rv0, I_rv1, I_latestDiff,
                  I_lastAbsDiff, I_done, I_nTx, I_pad, kScalars };
@@ -130,6 +135,7 @@ GW_HD void gen_init(GenView &v, const GenBand &B)
     for (int w = 0; w < GenView::kScalars; ++w) v.sc(w) = 0;
     for (int p = 0; p < nd; ++p) {
         v.P(p) = B.thermal; v.tEv(p) = 0; v.tStop(p) = 0; v.tC(p) = 0; v.ber(p) = 0; v.err(p) = 0; v.tReset(p) = 0;
+        v.txStart(p) = 0; v.segT0(p) = 0;
         v.sphase(p) = S_IDLE; v.sEv(p) = 0; v.sC(p) = 0; v.cmdPay(p) = 0; v.rxOf(p) = -1; v.rxSec(p) = 0; v.txSeq(p) = 0;
     }
     for (int k = 0; k < ns; ++k) {
@@ -267,24 +273,45 @@ GW_HD void gen_update_ber(GenView &v, const Params &P, int p)
     gen_rec(v, REC_BER, v.now(), p, b, 0.0, 0.0, 0.0);
 }
 
-// SimplePhy._countBitErrors (simple_stack.py:180-188): duration from the last RESET (appendix B #5)
-GW_HD void gen_count(GenView &v, const Params &P, int p)
+// mode M: the on-air bits [k0, k1) of the segment of PHY p's reception that ends now, and what keys their error flags
+GW_HD void gen_mask_range(const GenView &v, const Params &P, int p, int &sender, uint32_t &txseq, long long &k0, long long &k1)
 {
-    const double duration = v.now() - v.tReset(p);
-    const double bitErrors = v.ber(p) * duration * P.bitRate;
-    v.err(p) += bitErrors;
+    const int e = v.rxOf(p);
+    const double start = v.txStart(e);
+    sender = e; txseq = v.txSeq(e) - 1u;
+    k0 = (long long)floor((v.segT0(p) - start) * P.bitRate);
+    k1 = (long long)floor((v.now() - start) * P.bitRate);
+}
+
+// SimplePhy._countBitErrors (simple_stack.py:180-188).  Mode R: expected-value accounting, duration from the last
+// RESET (appendix B #5).  Mode M: the error flags of the on-air bits since the last count -- bit k of transmission
+// `txseq` of device `sender` as seen by `p` in GLOBAL env `env` is an error iff its Philox word is below
+// floor(ber * 2^32) (gw_core.cuh::mask_words4) --, counted here bit by bit; the kernel counts the ranges of an event
+// with the whole warp BEFORE the transition function runs (gen_count_set), which then finds them empty.
+GW_HD void gen_count(GenView &v, const Params &P, const GenBand &B, int p)
+{
+    if (B.mode == MODE_R) {
+        const double duration = v.now() - v.tReset(p);
+        const double bitErrors = v.ber(p) * duration * P.bitRate;
+        v.err(p) += bitErrors;
+        return;
+    }
+    int sender; uint32_t txseq; long long k0, k1;
+    gen_mask_range(v, P, p, sender, txseq, k0, k1);
+    if (k1 > k0) v.err(p) += (double)mask_errors_serial(B.seed, v.env, 0, sender, txseq, p, k0, k1, v.ber(p));
+    v.segT0(p) = v.now();
 }
 
 // _nReceivedPowerChanges.trigger(delta): the power sum, then the running reception (simple_stack.py:81-86, 223-233)
 // Returns true if the PHY's bit error rate must be re-evaluated (the caller collects these PHYs: the evaluations
 // of an event read nothing that the rest of the event writes, so they are done after it -- by the warp as a whole
 // in the kernel, see gw_kernels.cu::genband_step_kernel).
-GW_HD bool gen_power_change(GenView &v, const Params &P, int p, double delta, bool completingOwn)
+GW_HD bool gen_power_change(GenView &v, const Params &P, const GenBand &B, int p, double delta, bool completingOwn)
 {
     v.P(p) += delta;
     const int e = v.rxOf(p);
     if (e < 0 || delta == 0.0) return false;
-    gen_count(v, P, p);
+    gen_count(v, P, B, p);
     const bool completed = v.now() >= v.tStop(e);
     if (completed) return false;
     // `if not t.completed: _updateBitErrorRate(t)` with the power entry of its own transmission already popped:
@@ -302,7 +329,7 @@ GW_HD void gen_update_bers(GenView &v, const Params &P, uint32_t berMask)
 
 GW_HD void gen_rx_clear(GenView &v, int p)
 {
-    v.rxOf(p) = -1; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = v.now();
+    v.rxOf(p) = -1; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = v.now(); v.segT0(p) = v.now();
 }
 
 GW_HD bool gen_decide(GenView &v, const Params &P, int p, int section, double totalBits)
@@ -400,19 +427,19 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
             const double tH = now + (headerStop > now ? headerStop - now : 0.0);       // timeoutUntil
             const double tC = now + (stop > now ? stop - now : 0.0);
             const uint32_t qH = v.seq()++, qC = v.seq()++;
-            v.sphase(d) = S_HDR; v.tEv(d) = tH; v.sEv(d) = qH; v.tC(d) = tC; v.sC(d) = qC; v.tStop(d) = stop;
+            v.sphase(d) = S_HDR; v.tEv(d) = tH; v.sEv(d) = qH; v.tC(d) = tC; v.sC(d) = qC; v.tStop(d) = stop; v.txStart(d) = now;
             v.txSeq(d) += 1u;
             v.sc(GenView::I_nTx) += 1;
             gen_rec(v, REC_TX, now, d, stop, (hdrBytes * 8) * P.bitsFactor, (payBytes * 8) * P.bitsFactor, 0.0);
             // zero-delay notification: every other PHY registers the received power (simple_stack.py:130-144)
             for (int p = 0; p < nd; ++p) {
                 if (p == d) continue;
-                if (gen_power_change(v, P, p, v.rp(p, d), false)) berMask |= 1u << p;
+                if (gen_power_change(v, P, B, p, v.rp(p, d), false)) berMask |= 1u << p;
             }
             // receive processes in PHY construction order: idle, non-transmitting PHYs lock on (simple_stack.py:214-235)
             for (int p = 0; p < nd; ++p) {
                 if (p == d || v.rxOf(p) >= 0 || v.sphase(p) >= S_SLOT) continue;
-                v.rxOf(p) = d; v.rxSec(p) = 0; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = now;
+                v.rxOf(p) = d; v.rxSec(p) = 0; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = now; v.segT0(p) = now;
                 berMask |= 1u << p;
             }
         } else if (ph == S_HDR) {
@@ -421,9 +448,9 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
             uint32_t wake = 0;
             for (int p = 0; p < nd; ++p) {
                 if (v.rxOf(p) != d || v.rxSec(p) != 0) continue;
-                gen_count(v, P, p);
+                gen_count(v, P, B, p);
                 if (gen_decide(v, P, p, 0, hdrBits)) {
-                    v.rxSec(p) = 1; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = v.now();  // _resetBitErrorCounter
+                    v.rxSec(p) = 1; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = v.now(); v.segT0(p) = v.now();  // _resetBitErrorCounter
                     berMask |= 1u << p;
                 } else {
                     gen_rx_clear(v, p);
@@ -440,14 +467,14 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
             // 2. _onCompletingTransmission of every other PHY (simple_stack.py:146-157)
             for (int p = 0; p < nd; ++p) {
                 if (p == d) continue;
-                if (gen_power_change(v, P, p, -v.rp(p, d), v.rxOf(p) == d)) berMask |= 1u << p;
+                if (gen_power_change(v, P, B, p, -v.rp(p, d), v.rxOf(p) == d)) berMask |= 1u << p;
             }
             // 3. receivers that passed the header count again (appendix B #4), decide on the payload and deliver
             int window = -1;
             uint32_t wake = 0, received = 0;
             for (int p = 0; p < nd; ++p) {
                 if (v.rxOf(p) != d || v.rxSec(p) != 1) continue;
-                gen_count(v, P, p);
+                gen_count(v, P, B, p);
                 if (gen_decide(v, P, p, 1, payBits)) {
                     if (p < ns) {
                         // SimpleMac.phyInHandler (blocking, not queued): an announcement addressed to an idle MAC
@@ -583,6 +610,29 @@ GW_HD uint32_t gen_step_event(GenView &v, const Params &P, const GenBand &B)
 {
     const Event ev = gen_next_event(v, B);
     return gen_apply(v, P, B, ev);
+}
+
+// Mode M in the kernel: the PHYs that run SimplePhy._countBitErrors at event `ev` (the set of gw_core.cuh::count_set,
+// which depends only on the state BEFORE the event): every receiving PHY whose power sum changes when a transmission
+// starts or ends (a zero change counts nothing, simple_stack.py:224), the receivers of the header that ends, the
+// receivers of the payload that ends (their second count finds an empty range).  The warp counts these ranges
+// together, then gen_apply runs and finds them counted (segT0 == now).
+GW_HD uint32_t gen_count_set(const GenView &v, const Event &ev)
+{
+    if (ev.kind != EV_PHY) return 0;
+    const int d = ev.idx, ph = v.sphase(d);
+    uint32_t set = 0;
+    for (int p = 0; p < v.nd; ++p) {
+        const int rx = v.rxOf(p);
+        if (rx < 0) continue;
+        if (ph == S_HDR) {
+            if (rx == d && v.rxSec(p) == 0) set |= 1u << p;
+        } else {
+            if (p != d && v.rp(p, d) != 0.0) set |= 1u << p;
+            if (ph == S_PAY && rx == d && v.rxSec(p) == 1) set |= 1u << p;
+        }
+    }
+    return set;
 }
 
 GW_HD void gen_step_end(GenView &v, long long &obs, double &reward, unsigned char &done)

@@ -1961,7 +1961,7 @@ __device__ __forceinline__ GenView gen_view_of(const GenArgs &A, const GenBand &
     GenView v;
     v.f = A.f64 + i; v.i = A.i32 + i; v.stride = A.n_envs;
     v.srx = A.per_env ? A.srx + i : A.srx; v.srxStride = A.per_env ? A.n_envs : 1;
-    v.ns = B.ns; v.nj = B.nj; v.nd = B.nd;
+    v.ns = B.ns; v.nj = B.nj; v.nd = B.nd; v.env = B.envOffset + i;
     v.trace = nullptr; v.ntrace = 0; v.traceCap = 0;
     return v;
 }
@@ -2002,6 +2002,7 @@ __global__ void genband_reset_kernel(GenArgs A, GenBand B, long long *obs)
 // function only COLLECTS them (gen_apply's berMask) and the WARP evaluates the collected (env, PHY) pairs of all
 // its lanes together, one pair per lane, 32 at a time: any lane can evaluate any env's pair because the state lives
 // in global memory.  Lanes whose step has ended keep helping until the whole warp is done.
+template <bool MODE_M>
 __global__ void __launch_bounds__(GW_GEN_BLOCK, GW_GEN_MINB)
 genband_step_kernel(GenArgs A, Params P, GenBand B, const int32_t *device, const int32_t *duration, long long *obs,
                     double *reward, unsigned char *done)
@@ -2020,9 +2021,40 @@ genband_step_kernel(GenArgs A, Params P, GenBand B, const int32_t *device, const
         run = gen_step_begin(v, P, B, device[i], duration[i]);
     }
     const bool serial = A.trace != nullptr;             // the traced variant keeps the BER records in event order
+    constexpr bool modeM = MODE_M;
     for (;;) {
         uint32_t mask = 0;
-        if (run) {
+        if (modeM && !serial) {
+            // mode M: the event is selected first; the bit ranges its PHYs count (gen_count_set) are counted by the
+            // warp, one range after the other, 32 Philox blocks (128 bits) per pass; the transition function then finds
+            // them counted.  The ranges of a section are ~10^2..10^4 bits per receiver against ~10^2 instructions per
+            // Philox block: counted by the owning lane alone they would dwarf everything else.
+            Event ev;
+            uint32_t cset = 0;
+            ev.kind = EV_NONE; ev.idx = 0; ev.t = 0; ev.seq = 0;
+            if (run) {
+                if (gen_step_running(v)) { ev = gen_next_event(v, B); v.now() = ev.t; cset = gen_count_set(v, ev); }
+                else run = false;
+            }
+            __syncwarp();
+            unsigned owners = __ballot_sync(FULL, cset != 0);
+            while (owners) {
+                const int ol = __ffs(owners) - 1;
+                owners &= owners - 1;
+                uint32_t m = __shfl_sync(FULL, cset, ol);
+                GenView w = gen_view_of(A, B, warpEnv0 + ol);
+                while (m) {
+                    const int p = __ffs(m) - 1;
+                    m &= m - 1;
+                    int sender; uint32_t txseq; long long k0, k1;
+                    gen_mask_range(w, P, p, sender, txseq, k0, k1);
+                    const int c = warp_philox_range(B.seed, w.env, 0, sender, txseq, p, (int)k0, (int)k1, ber_threshold(w.ber(p)), (int)lane);
+                    if ((int)lane == ol) { w.err(p) += (double)c; w.segT0(p) = w.now(); }
+                }
+            }
+            __syncwarp();
+            if (run) mask = gen_apply(v, P, B, ev);
+        } else if (run) {
             if (gen_step_running(v)) mask = gen_step_event(v, P, B);
             else run = false;
         }
@@ -3193,6 +3225,8 @@ int gw_genband_create(const gw_genband_config *cfg, int device, const double *po
     if (ns < 2 || ns > GW_GENBAND_MAX_SENDERS) return fail(GW_E_INVALID, "n_senders must be in 2..%d", GW_GENBAND_MAX_SENDERS);
     if (nj < 0 || nj > GW_GENBAND_MAX_PHY_SENDERS) return fail(GW_E_INVALID, "n_phy_senders must be in 0..%d", GW_GENBAND_MAX_PHY_SENDERS);
     if (cfg->assignment_duration_factor < 1 || cfg->max_assign_duration < 1) return fail(GW_E_INVALID, "bad duration parameters");
+    if (cfg->mode != GW_MODE_REFERENCE && cfg->mode != GW_MODE_MASK_PHILOX)
+        return fail(GW_E_INVALID, "the general band engine offers GW_MODE_REFERENCE and GW_MODE_MASK_PHILOX");
     if (!(cfg->frequency_hz > 0) || !(cfg->bandwidth_hz > 0)) return fail(GW_E_INVALID, "bad frequency band");
     for (int k = 0; k < ns; ++k) {
         if (cfg->multiplicity[k] < 1 || cfg->multiplicity[k] > 1000) return fail(GW_E_INVALID, "sender %d: multiplicity must be in 1..1000", k);
@@ -3218,13 +3252,14 @@ int gw_genband_create(const gw_genband_config *cfg, int device, const double *po
     h->cfg = *cfg;
     h->device = device;
     Params &P = h->P;
-    P.nbands = 1; P.factor = cfg->assignment_duration_factor; P.maxDuration = cfg->max_assign_duration; P.mode = MODE_R;
+    P.nbands = 1; P.factor = cfg->assignment_duration_factor; P.maxDuration = cfg->max_assign_duration; P.mode = cfg->mode;
     P.bitRate = 133.33333e3; P.dataRate = 0.75 * P.bitRate; P.maxBer = gw_max_correctable_ber(3, 4);
     P.tenLog10BitRate = 10 * std::log10(P.bitRate); P.qDen = 1.135 * std::sqrt(2 * 3.141592653589793);
     P.bitsFactor = 2 - 0.75;
     finish_params(P);
     GenBand &B = h->B;
     B.ns = ns; B.nj = nj; B.nd = ns + 1 + nj; B.maxDuration = cfg->max_assign_duration;
+    B.mode = cfg->mode == GW_MODE_MASK_PHILOX ? MODE_M_PHILOX : MODE_R; B.seed = cfg->seed; B.envOffset = cfg->env_id_offset;
     B.thermal = 1.38e-23 * (20.0 + 273.15) * cfg->bandwidth_hz * 1000;        // simple_stack.py:57, physical.py:61-78
     double power[GW_GENBAND_MAX_DEVICES];
     for (int d = 0; d < B.nd; ++d) power[d] = 0.0;                              // MACs and the RRM send at 0 dBm
@@ -3303,8 +3338,11 @@ static int genband_launch(gw_genband_handle *h, const int32_t *device, const int
     CUDA_TRY(cudaSetDevice(h->device));
     GenArgs A = h->A;
     A.trace = trace; A.trace_count = trace_count; A.trace_cap = cap;
-    genband_step_kernel<<<grid_for(A.n_envs, GW_GEN_BLOCK), GW_GEN_BLOCK, 0, (cudaStream_t)stream>>>(A, h->P, h->B, device, duration, (long long *)obs,
-                                                                               reward, done);
+    const int grid = grid_for(A.n_envs, GW_GEN_BLOCK);
+    if (h->B.mode == MODE_R)
+        genband_step_kernel<false><<<grid, GW_GEN_BLOCK, 0, (cudaStream_t)stream>>>(A, h->P, h->B, device, duration, (long long *)obs, reward, done);
+    else
+        genband_step_kernel<true><<<grid, GW_GEN_BLOCK, 0, (cudaStream_t)stream>>>(A, h->P, h->B, device, duration, (long long *)obs, reward, done);
     CUDA_TRY(cudaGetLastError());
     return GW_OK;
 }

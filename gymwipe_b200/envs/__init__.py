@@ -28,8 +28,7 @@ def make(id, **kwargs):
     # senders, more PHY-only senders -- is stepped by the general band engine behind the same gym surface
     sc = kwargs.get("scenario")
     if cls is CounterTrafficEnv and sc is not None and len(sc["bands"]) == 1 and not fits_step_kernel_template(sc):
-        drop = [k for k in ("seed", "env_id_offset") if k in kwargs]
-        return GeneralBandEnv(**{k: v for k, v in kwargs.items() if k not in drop})
+        return GeneralBandEnv(**kwargs)
     return cls(**kwargs)
 
 

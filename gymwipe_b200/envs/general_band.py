@@ -61,19 +61,24 @@ class GeneralBandEnv(BaseEnv):
             senders (``role: "jammer"``: ``interval``, ``delay``, ``power``, ``hdr``, ``payload``).
         positions: optional float64 tensor ``[num_envs, n_devices, 2]`` of per-env positions.
         strict: validate actions / faults after every step (costs a device sync); default: ``num_envs == 1``.
+        mode: ``"reference"`` (mode R: the reference's expected-value error accounting) or ``"mask_philox"`` (mode M:
+            per-bit Philox4x32-10 error masks keyed by ``seed`` and the global env id ``env_id_offset + env`` --
+            results do not depend on batch size or sharding).
     """
 
     COUNTER_INTERVAL = 0.001
     COUNTER_BYTE_LENGTH = 2
     COUNTER_BOUND = 2 ** (8 * COUNTER_BYTE_LENGTH)
 
-    def __init__(self, num_envs=1, device="cuda", scenario=None, positions=None, strict=None, mode="reference"):
+    def __init__(self, num_envs=1, device="cuda", scenario=None, positions=None, strict=None, mode="reference", seed=0,
+                 env_id_offset=0):
         if not torch.cuda.is_available():
             raise RuntimeError("gymwipe_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if scenario is None or len(scenario["bands"]) != 1:
             raise ValueError("GeneralBandEnv takes a scenario with exactly one band")
-        if mode not in ("reference", "R"):
-            raise ValueError("the general band engine implements the reference's accounting (mode 'reference') only")
+        if mode not in ("reference", "R", "mask_philox", "M"):
+            raise ValueError("the general band engine offers the modes 'reference' and 'mask_philox'")
+        self.mode = "reference" if mode in ("reference", "R") else "mask_philox"
         dev = torch.device(device)
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self.num_envs = int(num_envs)
@@ -100,6 +105,8 @@ class GeneralBandEnv(BaseEnv):
         cfg.assignment_duration_factor = self.ASSIGNMENT_DURATION_FACTOR
         cfg.max_assign_duration = self.MAX_ASSIGN_DURATION
         cfg.per_env_positions = 0 if positions is None else 1
+        cfg.mode = N.GW_MODE_REFERENCE if self.mode == "reference" else N.GW_MODE_MASK_PHILOX
+        cfg.seed, cfg.env_id_offset = int(seed), int(env_id_offset)
         cfg.frequency_hz, cfg.bandwidth_hz = float(band.get("frequency", 2.4e9)), float(band.get("bandwidth", 22e6))
         for k, d in enumerate(devs[:ns]):
             p = d.get("payload", "counter")

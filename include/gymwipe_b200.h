@@ -380,7 +380,8 @@ int gw_grid_check(gw_grid_handle *h, void *stream);
  * stays receivedValues[0] - receivedValues[1]) and PHY-only periodic senders (tests/test_benchmark.py:20-50).
  * This engine steps such bands -- n_senders <= 8, n_phy_senders <= 16 as RUN-TIME values -- exactly like the env:
  * assignFrequencyBand(device, duration) (devices.py:178-203), runSimulation(assignSignal.eProcessed), then
- * Interpreter.getFeedback; reference accounting (mode R).  Device order: senders, RRM, PHY-only senders.
+ * Interpreter.getFeedback; reference accounting (mode R) or per-bit Philox error masks (mode M).  Device order:
+ * senders, RRM, PHY-only senders.
  * One GPU thread per env, state in global memory ([field][index][env]); gymwipe_b200/csrc/gw_band.cuh. */
 #define GW_GENBAND_MAX_SENDERS 8
 #define GW_GENBAND_MAX_PHY_SENDERS 16
@@ -393,6 +394,9 @@ typedef struct {
     int32_t assignment_duration_factor;     /* ASSIGNMENT_DURATION_FACTOR = 1000, envs/core.py:36 */
     int32_t max_assign_duration;            /* MAX_ASSIGN_DURATION = 20, envs/core.py:31: duration in [0, 20) */
     int32_t per_env_positions;              /* 0: one geometry for all envs; 1: positions per env */
+    int32_t mode;                           /* GW_MODE_REFERENCE, or GW_MODE_MASK_PHILOX: per-bit error masks keyed */
+    uint64_t seed;                          /*   by (seed; env_id_offset + env, sender, transmission, receiver, bit) */
+    int64_t env_id_offset;                  /*   exactly as in gw_config (GW_MODE_MASK_FED is not offered here) */
     double frequency_hz, bandwidth_hz;      /* FrequencyBandSpec, physical.py:293-306 */
     /* senders (SenderDevice, counter_traffic.py:37-61) */
     int32_t multiplicity[GW_GENBAND_MAX_SENDERS];       /* packets per tick */

@@ -235,6 +235,11 @@ def child(args):
         sc = random_scenario_n(rs, ns, nj, spread=args.spread, receive=bool(args.seed % 2), bursts=bool(args.seed % 3 == 0))
         tape = H.random_actions(args.steps, seed=args.seed + 11000, devices=ns)
         return run_case(sc, tape, "%d senders + RRM + %d PHY-only senders, seed %d" % (ns, nj, args.seed))
+    if args.case == "masknsenders":
+        ns, nj = int(rs.randint(3, 7)), int(rs.randint(0, 4))
+        sc = random_scenario_n(rs, ns, nj, spread=args.spread, receive=bool(args.seed % 2))
+        tape = H.random_actions(args.steps, seed=args.seed + 12000, devices=ns)
+        return run_case_m(sc, tape, "mode M, %d senders + RRM + %d PHY-only senders, seed %d" % (ns, nj, args.seed), seed=args.seed + 81)
     if args.case == "multiband":
         sc = random_scenario(rs, nbands=4, jammers=1, spread=args.spread)
         tapes = [H.random_actions(args.steps, seed=args.seed + 4000 + b) for b in range(4)]
@@ -274,7 +279,7 @@ def main():
         plan += [("positions", sd, 200), ("jammer", sd, 200), ("long", sd, 40), ("multiband", sd, 80),
                  ("maskdefault", sd, 120), ("maskjammer", sd, 120), ("masklong", sd, 20),
                  ("mobilityjam", sd, 120), ("maskmobilityjam", sd, 80), ("mobilityquirks", sd, 100),
-                 ("nsenders", sd, 120)]
+                 ("nsenders", sd, 120), ("masknsenders", sd, 40)]
     failed = 0
     for case, sd, steps in plan:
         rc = subprocess.call([sys.executable, os.path.abspath(__file__), "--case", case,

@@ -46,6 +46,7 @@ CASES = {
     "nsenders_5s_3p_seed31": ("nsenders:5:3:1:0", 31, 80),
     "nsenders_8s_6p_seed32": ("nsenders:8:6:1:1", 32, 60),
     "nsenders_3s_16p_seed33": ("nsenders:3:16:0:0", 33, 40),
+    "modeM_nsenders_4s_2p_seed34": ("masknsenders:4:2:1:0", 34, 40),
 }
 
 MASK_SEED, MASK_ENV = 20261018, 4242
@@ -99,7 +100,7 @@ def make_case(kind, seed, steps):
         sc["bands"][0]["devices"][0]["receive"] = True
         sc["bands"][0]["devices"][1]["receive"] = True
         sc["bands"][0]["devices"][1]["max_ticks"] = 45
-    elif kind.startswith("nsenders:"):
+    elif kind.startswith("nsenders:") or kind.startswith("masknsenders:"):
         # ns MAC senders + RRM + nj PHY-only senders, with / without receive mode and finite bursts
         _, ns, nj, rcv, bursts = kind.split(":")
         sc = CR.random_scenario_n(rs, int(ns), int(nj), spread=2.5, receive=bool(int(rcv)), bursts=bool(int(bursts)))

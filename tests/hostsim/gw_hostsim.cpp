@@ -312,11 +312,13 @@ int hs_grid_run(int n, double frequency, double bandwidth, const double *power, 
 // senders stepped through an action tape [nsteps][nenv]; state laid out as on the device ([word][sim]).
 // cfg_i [6][8]: mult, payloadRule, dest, maxTicks, recv per sender (rows 0-4); cfg_jam_i [2][16]: hdr, payload;
 // cfg_d: interval [8], jamInterval [16], jamDelay [16]; pos [nenv or 1][nd][2]; power [nd].
+// mode 0: reference accounting; 1: Philox error masks keyed by (seed; env_offset + env, ...).
 // Outputs per step and env: obs / reward / done / now; after the last step counts [nenv][1 + 8 + 8]
 // (transmissions, deliveries per sender, packets handed to onReceive per sender).  The trace of env 0 is returned
 // per step (records of 8 doubles).  `reset_at` >= 0: env.reset() before that step (0: before the first one).
 int hs_gen_run(int ns, int nj, int factor, double frequency, double bandwidth, const int32_t *cfg_i, const int32_t *cfg_jam_i,
-               const double *cfg_d, const double *pos, int per_env_pos, const double *power, int64_t nenv, int nsteps,
+               const double *cfg_d, const double *pos, int per_env_pos, const double *power, int mode, uint64_t seed,
+               int64_t env_offset, int64_t nenv, int nsteps,
                int reset_at, const int32_t *dev_tape, const int32_t *dur_tape, int64_t *obs, double *reward, uint8_t *done,
                double *now_out, int64_t *counts, double *trace, int trace_cap, int32_t *trace_counts)
 {
@@ -330,6 +332,7 @@ int hs_gen_run(int ns, int nj, int factor, double frequency, double bandwidth, c
     GenBand B;
     std::memset(&B, 0, sizeof B);
     B.ns = ns; B.nj = nj; B.nd = ns + 1 + nj; B.maxDuration = 20;
+    B.mode = mode; B.seed = seed; B.envOffset = env_offset;
     B.thermal = 1.38e-23 * (20.0 + 273.15) * bandwidth * 1000;
     for (int k = 0; k < ns; ++k) {
         B.mult[k] = cfg_i[0 * 8 + k]; B.payloadRule[k] = cfg_i[1 * 8 + k]; B.dest[k] = cfg_i[2 * 8 + k];
@@ -346,7 +349,7 @@ int hs_gen_run(int ns, int nj, int factor, double frequency, double bandwidth, c
         GenView v;
         v.f = f.data() + e; v.i = iv.data() + e; v.stride = nenv;
         v.srx = per_env_pos ? srx.data() + e : srx.data(); v.srxStride = per_env_pos ? nenv : 1;
-        v.ns = ns; v.nj = nj; v.nd = nd; v.trace = nullptr; v.ntrace = 0; v.traceCap = 0;
+        v.ns = ns; v.nj = nj; v.nd = nd; v.env = env_offset + e; v.trace = nullptr; v.ntrace = 0; v.traceCap = 0;
         return v;
     };
     if (per_env_pos) for (int64_t e = 0; e < nenv; ++e) gen_power_table(nd, pos + (size_t)e * nd * 2, power, frequency, srx.data() + e, nenv);

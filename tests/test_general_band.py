@@ -258,3 +258,97 @@ def test_cuda_general_band_rejects_bad_actions_and_bad_configs():
     bad = dict(sc, bands=[dict(sc["bands"][0], devices=[dict(d, dest=0) if d["role"] == "sender" else d for d in sc["bands"][0]["devices"]])])
     with pytest.raises(N.NativeError):
         GeneralBandEnv(num_envs=1, device="cuda:0", scenario=bad)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# mode M: per-bit Philox error masks keyed by (seed; env, sender, transmission, receiver, bit)
+# ------------------------------------------------------------------------------------------------------------
+
+GOLDEN_NSENDERS_M = "modeM_nsenders_4s_2p_seed34"
+
+
+def _oracle_tape_m(sc, dev, dur, seed, env_id):
+    ora = O.Oracle(sc, trace=True, mode=O.MODE_M)
+    ora.use_philox_masks(seed, env_id)
+    ora.reset()
+    ora.take_records()
+    steps = []
+    for t in range(dev.shape[0]):
+        obs, rew, done = ora.step({"device": int(dev[t, 0]), "duration": int(dur[t, 0])})
+        steps.append({"obs": obs, "reward": rew, "done": done, "now": ora.now, "records": ora.take_records()})
+    ntx, nd = ora.counts()
+    return steps, ntx, nd, ora.received(), ora.near_ties
+
+
+def test_oracle_and_core_match_reference_golden_nsenders_mode_m():
+    """Reference + MaskedPhy (a SimplePhy subclass that replaces only the error bookkeeping by Philox masks) on a
+    band of 4 senders + RRM + 2 PHY-only senders: integer error counts, verdicts, deliveries bit-exact."""
+    doc = load_golden(GOLDEN_NSENDERS_M)
+    sc, seed, env_id = doc["scenario"], doc["mask_seed"], doc["mask_env_id"]
+    dev, dur = _tapes(doc)
+    steps, _, _, _, _ = _oracle_tape_m(sc, dev, dur, seed, env_id)
+    h = HS.gen_run(sc, dev, dur, mode=1, seed=seed, env_offset=env_id)
+    assert h["rc"] == 0
+    nfail = 0
+    for t, g in enumerate(doc["steps"]):
+        o = steps[t]
+        assert (o["obs"], o["reward"], o["done"], o["now"]) == (g["obs"], g["reward"], g["done"], g["now"]), t
+        assert_step_records(o["records"], g["records"], "oracle step %d" % t)
+        assert (h["obs"][t, 0], h["reward"][t, 0], bool(h["done"][t, 0]), h["now"][t, 0]) == (g["obs"], g["reward"], g["done"], g["now"]), t
+        assert_step_records(h["records"][t], g["records"], "core step %d" % t)
+        nfail += sum(1 for r in g["records"] if r[0] == "dec" and not r[7])
+    assert nfail > 10
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_core_general_mode_m_random_vs_oracle(seed):
+    rs = np.random.RandomState(6000 + seed)
+    ns, nj = int(rs.randint(3, 9)), int(rs.randint(0, 7))
+    sc = random_scenario_n(rs, ns, nj, spread=2.5, receive=bool(seed % 2), bursts=bool(seed % 3 == 0))
+    T = 40
+    dev = rs.randint(0, ns, size=(T, 1)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, 1)).astype(np.int32)
+    steps, ntx, nd, nrecv, _ = _oracle_tape_m(sc, dev, dur, 900 + seed, 31337 + seed)
+    h = HS.gen_run(sc, dev, dur, mode=1, seed=900 + seed, env_offset=31337 + seed)
+    _assert_host_equals(h, steps, ntx, nd, nrecv, ns, "mode M seed %d (%d senders, %d PHY-only)" % (seed, ns, nj))
+
+
+@pytest.mark.gpu
+def test_cuda_general_band_mode_m_matches_reference_golden():
+    doc = load_golden(GOLDEN_NSENDERS_M)
+    sc = doc["scenario"]
+    env = _gpu_env(sc, 1, mode="mask_philox", seed=doc["mask_seed"], env_id_offset=doc["mask_env_id"])
+    assert env.reset() == doc["reset_obs"]
+    for t, g in enumerate(doc["steps"]):
+        obs, rew, done, recs = env.step_traced({"device": g["action"]["device"], "duration": g["action"]["duration"]})
+        assert (obs, rew, done) == (g["obs"], g["reward"], g["done"]), t
+        assert float(env.now[0]) == g["now"], t
+        assert_step_records(recs, g["records"], "step %d" % t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(3))
+def test_cuda_general_band_mode_m_matches_oracle_and_is_sharding_invariant(seed):
+    """1024 envs x 32 steps in mode M (the warp counts the Philox ranges of its lanes' events together) against the
+    oracle with the same keys; the second half of the envs stepped as a separate shard gives the same results."""
+    import torch
+    rs = np.random.RandomState(6400 + seed)
+    ns, nj = int(rs.randint(3, 9)), int(rs.randint(0, 9))
+    sc = random_scenario_n(rs, ns, nj, spread=2.0, receive=bool(seed % 2))
+    nenv, T, mseed, off = 1024, 32, 4242 + seed, 1000003
+    dev = rs.randint(0, ns, size=(T, nenv)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, nenv)).astype(np.int32)
+    o = O.run_batch(sc, dev, dur, mode=O.MODE_M, seed=mseed, env_id_offset=off)
+    env = _gpu_env(sc, nenv, mode="mask_philox", seed=mseed, env_id_offset=off)
+    shard = _gpu_env(sc, nenv // 2, mode="mask_philox", seed=mseed, env_id_offset=off + nenv // 2)
+    env.reset(); shard.reset()
+    for t in range(T):
+        a = {"device": torch.as_tensor(dev[t]).cuda(), "duration": torch.as_tensor(dur[t]).cuda()}
+        obs, rew, done, _ = env.step(a)
+        assert (obs.cpu().numpy() == o["obs"][t, :, 0]).all() and (rew.cpu().numpy() == o["reward"][t, :, 0]).all(), (seed, t)
+        assert (env.now.cpu().numpy() == o["now"][t]).all(), (seed, t)
+        obs2, rew2, _, _ = shard.step({"device": a["device"][nenv // 2:].contiguous(), "duration": a["duration"][nenv // 2:].contiguous()})
+        assert torch.equal(obs2, obs[nenv // 2:]) and torch.equal(rew2, rew[nenv // 2:])
+    env.check()
+    assert (env.delivered().cpu().numpy() == o["counts"][:, 0, 1:1 + ns]).all()
+    assert torch.equal(shard.delivered(), env.delivered()[nenv // 2:])
