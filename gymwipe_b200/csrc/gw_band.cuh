@@ -65,6 +65,7 @@ struct GenView {
     long long srxStride;
     int ns, nj, nd;
     long long env;                      // global env id (mode M: key of the error masks)
+    int mode;                           // MODE_R / MODE_M_PHILOX: a compile-time constant in the kernels (no mode-M code or stores in mode R)
     double *trace;                      // optional event trace (records of 8 doubles, as gw_core.cuh::trace_rec)
     int ntrace, traceCap;
 
@@ -290,7 +291,7 @@ GW_HD void gen_mask_range(const GenView &v, const Params &P, int p, int &sender,
 // with the whole warp BEFORE the transition function runs (gen_count_set), which then finds them empty.
 GW_HD void gen_count(GenView &v, const Params &P, const GenBand &B, int p)
 {
-    if (B.mode == MODE_R) {
+    if (v.mode == MODE_R) {
         const double duration = v.now() - v.tReset(p);
         const double bitErrors = v.ber(p) * duration * P.bitRate;
         v.err(p) += bitErrors;
@@ -329,7 +330,8 @@ GW_HD void gen_update_bers(GenView &v, const Params &P, uint32_t berMask)
 
 GW_HD void gen_rx_clear(GenView &v, int p)
 {
-    v.rxOf(p) = -1; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = v.now(); v.segT0(p) = v.now();
+    v.rxOf(p) = -1; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = v.now();
+    if (v.mode != MODE_R) v.segT0(p) = v.now();
 }
 
 GW_HD bool gen_decide(GenView &v, const Params &P, int p, int section, double totalBits)
@@ -427,7 +429,8 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
             const double tH = now + (headerStop > now ? headerStop - now : 0.0);       // timeoutUntil
             const double tC = now + (stop > now ? stop - now : 0.0);
             const uint32_t qH = v.seq()++, qC = v.seq()++;
-            v.sphase(d) = S_HDR; v.tEv(d) = tH; v.sEv(d) = qH; v.tC(d) = tC; v.sC(d) = qC; v.tStop(d) = stop; v.txStart(d) = now;
+            v.sphase(d) = S_HDR; v.tEv(d) = tH; v.sEv(d) = qH; v.tC(d) = tC; v.sC(d) = qC; v.tStop(d) = stop;
+            if (v.mode != MODE_R) v.txStart(d) = now;
             v.txSeq(d) += 1u;
             v.sc(GenView::I_nTx) += 1;
             gen_rec(v, REC_TX, now, d, stop, (hdrBytes * 8) * P.bitsFactor, (payBytes * 8) * P.bitsFactor, 0.0);
@@ -439,7 +442,8 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
             // receive processes in PHY construction order: idle, non-transmitting PHYs lock on (simple_stack.py:214-235)
             for (int p = 0; p < nd; ++p) {
                 if (p == d || v.rxOf(p) >= 0 || v.sphase(p) >= S_SLOT) continue;
-                v.rxOf(p) = d; v.rxSec(p) = 0; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = now; v.segT0(p) = now;
+                v.rxOf(p) = d; v.rxSec(p) = 0; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = now;
+                if (v.mode != MODE_R) v.segT0(p) = now;
                 berMask |= 1u << p;
             }
         } else if (ph == S_HDR) {
@@ -450,7 +454,8 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
                 if (v.rxOf(p) != d || v.rxSec(p) != 0) continue;
                 gen_count(v, P, B, p);
                 if (gen_decide(v, P, p, 0, hdrBits)) {
-                    v.rxSec(p) = 1; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = v.now(); v.segT0(p) = v.now();  // _resetBitErrorCounter
+                    v.rxSec(p) = 1; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = v.now();  // _resetBitErrorCounter
+                    if (v.mode != MODE_R) v.segT0(p) = v.now();
                     berMask |= 1u << p;
                 } else {
                     gen_rx_clear(v, p);

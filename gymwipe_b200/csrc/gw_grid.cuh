@@ -162,7 +162,9 @@ GW_HD void grid_count(GridView &v, const GridParams &G, int p)
 }
 
 // _nReceivedPowerChanges.trigger(delta): power sum, then the running reception (simple_stack.py:81-86, 223-233)
-GW_HD void grid_power_change(GridView &v, const GridParams &G, int p, double delta, bool completing_own)
+// `defer`: if given, the PHY is only marked for a BER evaluation after the event (the evaluations of a PHY event
+// read nothing the rest of the event writes; the kernel evaluates the marked PHYs of all lanes of a warp together)
+GW_HD void grid_power_change(GridView &v, const GridParams &G, int p, double delta, bool completing_own, uint32_t *defer = nullptr)
 {
     GridDev &R = v.dev[p];
     R.P += delta;
@@ -173,8 +175,14 @@ GW_HD void grid_power_change(GridView &v, const GridParams &G, int p, double del
         // `if not t.completed: _updateBitErrorRate(t)` with the power entry of its own transmission already
         // popped: the reference raises KeyError (appendix B #12)
         if (completing_own) { v.h->fault = FAULT_REF_KEYERROR; return; }
-        grid_update_ber(v, G, p);
+        if (defer) *defer |= 1u << p; else grid_update_ber(v, G, p);
     }
+}
+
+GW_HD void grid_update_bers(GridView &v, const GridParams &G, uint32_t mask)
+{
+    for (int p = 0; p < v.n; ++p)
+        if ((mask >> p) & 1u) grid_update_ber(v, G, p);
 }
 
 GW_HD void grid_rx_clear(GridView &v, int p)
@@ -243,7 +251,9 @@ GW_HD void grid_move(GridView &v, const GridParams &G, int m, double x, double y
 }
 
 // one timed event; `offsets` [n][maxMoves][2] position offsets of the mobility processes
-GW_HD void grid_apply(GridView &v, const GridParams &G, int kind, int d, const double *offsets)
+// `defer`: see grid_power_change (PHY events only: a moving device's PHY can see several power changes in one event,
+// each counted with the rate the previous one left)
+GW_HD void grid_apply(GridView &v, const GridParams &G, int kind, int d, const double *offsets, uint32_t *defer = nullptr)
 {
     const int n = v.n;
     GridDev &D = v.dev[d];
@@ -291,7 +301,7 @@ GW_HD void grid_apply(GridView &v, const GridParams &G, int kind, int d, const d
         // zero-delay notification: every other PHY registers the received power (simple_stack.py:130-144)
         for (int p = 0; p < n; ++p) {
             if (p == d) continue;
-            grid_power_change(v, G, p, v.srx[p * n + d], false);
+            grid_power_change(v, G, p, v.srx[p * n + d], false, defer);
             if (v.h->fault) return;
         }
         // receive processes in construction order: idle, non-transmitting PHYs lock on (simple_stack.py:214-235)
@@ -299,7 +309,7 @@ GW_HD void grid_apply(GridView &v, const GridParams &G, int kind, int d, const d
             GridDev &R = v.dev[p];
             if (p == d || R.rxOf >= 0 || R.sphase >= S_SLOT) continue;
             R.rxOf = d; R.rxSec = 0; R.err = 0.0; R.ber = 0.0; R.tReset = now;
-            grid_update_ber(v, G, p);
+            if (defer) *defer |= 1u << p; else grid_update_ber(v, G, p);
         }
     } else if (D.sphase == S_HDR) {
         // eHeaderCompletes (simple_stack.py:241-251)
@@ -311,7 +321,7 @@ GW_HD void grid_apply(GridView &v, const GridParams &G, int kind, int d, const d
             if (grid_decide(v, G, p, 0, hdrBits)) {
                 R.nHdrOk += 1;
                 R.rxSec = 1; R.err = 0.0; R.ber = 0.0; R.tReset = v.h->now;
-                grid_update_ber(v, G, p);
+                if (defer) *defer |= 1u << p; else grid_update_ber(v, G, p);
             } else {
                 R.nHdrFail += 1;
                 grid_rx_clear(v, p);
@@ -332,7 +342,7 @@ GW_HD void grid_apply(GridView &v, const GridParams &G, int kind, int d, const d
         // 2. _onCompletingTransmission of every other PHY (simple_stack.py:146-157)
         for (int p = 0; p < n; ++p) {
             if (p == d) continue;
-            grid_power_change(v, G, p, -v.srx[p * n + d], v.dev[p].rxOf == d);
+            grid_power_change(v, G, p, -v.srx[p * n + d], v.dev[p].rxOf == d, defer);
             if (v.h->fault) return;
         }
         // 3. receivers that passed the header decide on the payload (second count: appendix B #4)
@@ -355,24 +365,35 @@ GW_HD void grid_apply(GridView &v, const GridParams &G, int kind, int d, const d
 }
 
 // SimMan.runSimulation(duration): every event strictly before now + duration, then the clock is set
-GW_HD void grid_run(GridView &v, const GridParams &G, double duration, const double *offsets)
+// one timed event strictly before T; returns false when there is none (or the env has faulted).  `berMask`: the PHYs
+// whose bit error rate the caller evaluates afterwards (grid_update_bers)
+GW_HD bool grid_run_event(GridView &v, const GridParams &G, double T, const double *offsets, uint32_t &berMask)
 {
     const int n = v.n;
-    const double T = v.h->now + duration;
-    while (!v.h->fault) {
-        int kind = EV_NONE, idx = 0;
-        double t = INFINITY;
-        uint32_t q = 0;
-        for (int d = 0; d < n; ++d) {
-            const GridDev &D = v.dev[d];
-            if (kind == EV_NONE || before(D.tJam, D.sJam, t, q)) { kind = EV_JAM; idx = d; t = D.tJam; q = D.sJam; }
-            if (D.sphase >= S_SLOT && before(D.tEv, D.sEv, t, q)) { kind = EV_PHY; idx = d; t = D.tEv; q = D.sEv; }
-            if (D.moveStage < 2 && before(D.tMove, D.sMove, t, q)) { kind = EV_W; idx = d; t = D.tMove; q = D.sMove; }
-        }
-        if (kind == EV_NONE || !(t < T)) break;
-        v.h->now = t;
-        grid_apply(v, G, kind, idx, offsets);
+    berMask = 0;
+    if (v.h->fault) return false;
+    int kind = EV_NONE, idx = 0;
+    double t = INFINITY;
+    uint32_t q = 0;
+    for (int d = 0; d < n; ++d) {
+        const GridDev &D = v.dev[d];
+        if (kind == EV_NONE || before(D.tJam, D.sJam, t, q)) { kind = EV_JAM; idx = d; t = D.tJam; q = D.sJam; }
+        if (D.sphase >= S_SLOT && before(D.tEv, D.sEv, t, q)) { kind = EV_PHY; idx = d; t = D.tEv; q = D.sEv; }
+        if (D.moveStage < 2 && before(D.tMove, D.sMove, t, q)) { kind = EV_W; idx = d; t = D.tMove; q = D.sMove; }
     }
+    if (kind == EV_NONE || !(t < T)) return false;
+    v.h->now = t;
+    grid_apply(v, G, kind, idx, offsets, kind == EV_PHY ? &berMask : nullptr);
+    return true;
+}
+
+// SimMan.runSimulation(duration): every event strictly before now + duration, then the clock is set (serial driver:
+// host build, traced kernel)
+GW_HD void grid_run(GridView &v, const GridParams &G, double duration, const double *offsets)
+{
+    const double T = v.h->now + duration;
+    uint32_t m;
+    while (grid_run_event(v, G, T, offsets, m)) grid_update_bers(v, G, m);
     v.h->now = T;
 }
 

@@ -1905,15 +1905,74 @@ __global__ void grid_init_kernel(GridArgs A, GridParams G, const double *pos, co
     grid_init(v, G, pos + i * G.ndev * 2, delays + i * G.ndev, move_delays ? move_delays + i * G.ndev : nullptr);
 }
 
+// Work items collected by the lanes of a warp -- lane l holds the set bits of `mask` -- spread over the whole warp:
+// f(owner lane, bit) is called once per item, 32 items at a time, each by a different lane.  All 32 lanes must call.
+// Used for SimplePhy._updateBitErrorRate in the general engines: one band-sim per thread, the lanes of a warp sit at
+// different events of different kinds (ncu: 4 of 32 lanes active per instruction), and what most of them execute
+// most of the time is the BER evaluation (2 log10, exp10, sqrt, 2 exp, a division: ~600 fp64-heavy instructions) --
+// on a band with a dozen PHYs every transmission that starts or ends makes every receiving PHY re-evaluate.  The
+// evaluations of an event read nothing the rest of the event writes, so the transition functions only COLLECT them
+// and the warp evaluates the (env, PHY) pairs of all its lanes together: any lane can serve any env because the
+// state lives in global memory.
+template <class F>
+__device__ __forceinline__ void warp_spread(uint32_t mask, unsigned lane, F &&f)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int cnt = __popc(mask);
+    int pre = cnt;                                      // inclusive prefix sum of the lanes' counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, pre, o);
+        if ((int)lane >= o) pre += t;
+    }
+    const int total = __shfl_sync(FULL, pre, 31);
+    const int excl = pre - cnt;
+    for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + (int)lane;
+        int owner = 0;                                  // owner of item t: the number of lanes whose inclusive prefix is <= t
+#pragma unroll
+        for (int stepw = 16; stepw >= 1; stepw >>= 1) {
+            const int q = __shfl_sync(FULL, pre, owner + stepw - 1);
+            if (q <= t) owner += stepw;
+        }
+        const int ol = owner < 32 ? owner : 31;
+        const int oExcl = __shfl_sync(FULL, excl, ol);
+        const uint32_t oMask = __shfl_sync(FULL, mask, ol);
+        if (t < total) f(ol, (int)__fns(oMask, 0u, t - oExcl + 1));
+    }
+}
+
 __global__ void __launch_bounds__(64)
 grid_run_kernel(GridArgs A, GridParams G, double duration)
 {
+    constexpr unsigned FULL = 0xffffffffu;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.n_envs) return;
-    GridView v = grid_view(A.state + (size_t)i * A.block_bytes, G.ndev);
-    if (A.trace) { v.trace = A.trace + (long long)i * A.trace_cap * 8; v.traceCap = A.trace_cap; v.ntrace = 0; }
-    const double *off = A.offsets ? A.offsets + (long long)i * G.ndev * G.maxMoves * 2 : nullptr;
-    grid_run(v, G, duration, off);
+    const bool valid = i < A.n_envs;
+    const unsigned lane = threadIdx.x & 31u;
+    const long long warpEnv0 = i - lane;
+    GridView v = grid_view(A.state + (size_t)(valid ? i : A.n_envs - 1) * A.block_bytes, G.ndev);
+    if (A.trace && valid) { v.trace = A.trace + i * A.trace_cap * 8; v.traceCap = A.trace_cap; v.ntrace = 0; }
+    const double *off = A.offsets ? A.offsets + (valid ? i : 0) * G.ndev * G.maxMoves * 2 : nullptr;
+    const double T = v.h->now + duration;
+    const bool serial = A.trace != nullptr;             // the traced variant keeps the BER records in event order
+    bool run = valid;
+    for (;;) {
+        uint32_t mask = 0;
+        if (run) run = grid_run_event(v, G, T, off, mask);
+        if (serial) {
+            if (run) grid_update_bers(v, G, mask);
+        } else {
+            __syncwarp();                               // the owners' state updates are visible to the helpers
+            warp_spread(mask, lane, [&](int ol, int p) {
+                GridView w = grid_view(A.state + (size_t)(warpEnv0 + ol) * A.block_bytes, G.ndev);
+                grid_update_ber(w, G, p);
+            });
+            __syncwarp();                               // the evaluated rates are visible to their owners
+        }
+        if (!__any_sync(FULL, run)) break;
+    }
+    if (!valid) return;
+    v.h->now = T;
     if (A.trace) A.trace_count[i] = v.ntrace;
     if (v.h->fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = v.h->fault; } }
 }
@@ -1956,9 +2015,10 @@ struct GenArgs {
     int *errflag;
 };
 
-__device__ __forceinline__ GenView gen_view_of(const GenArgs &A, const GenBand &B, long long i)
+__device__ __forceinline__ GenView gen_view_of(const GenArgs &A, const GenBand &B, long long i, int mode = -1)
 {
     GenView v;
+    v.mode = mode < 0 ? B.mode : mode;
     v.f = A.f64 + i; v.i = A.i32 + i; v.stride = A.n_envs;
     v.srx = A.per_env ? A.srx + i : A.srx; v.srxStride = A.per_env ? A.n_envs : 1;
     v.ns = B.ns; v.nj = B.nj; v.nd = B.nd; v.env = B.envOffset + i;
@@ -1994,14 +2054,8 @@ __global__ void genband_reset_kernel(GenArgs A, GenBand B, long long *obs)
 #ifndef GW_GEN_MINB
 #define GW_GEN_MINB 4
 #endif
-// One band-sim per thread; the lanes of a warp sit at different events of different kinds (ncu: 4 of 32 lanes active
-// per instruction), and what most of them execute most of the time is SimplePhy._updateBitErrorRate -- on a band with
-// a dozen PHYs every transmission that starts or ends makes every receiving PHY re-evaluate its BER (2 log10, exp10,
-// sqrt, 2 exp, a division: ~600 fp64-heavy instructions each, 90 % of the kernel's instructions when each lane
-// evaluates its own).  The evaluations of an event read nothing the rest of the event writes, so the transition
-// function only COLLECTS them (gen_apply's berMask) and the WARP evaluates the collected (env, PHY) pairs of all
-// its lanes together, one pair per lane, 32 at a time: any lane can evaluate any env's pair because the state lives
-// in global memory.  Lanes whose step has ended keep helping until the whole warp is done.
+// One band-sim per thread.  The BER evaluations an event asks for are collected (gen_apply's berMask) and evaluated by
+// the warp as a whole (warp_spread); lanes whose step has ended keep helping until the whole warp is done.
 template <bool MODE_M>
 __global__ void __launch_bounds__(GW_GEN_BLOCK, GW_GEN_MINB)
 genband_step_kernel(GenArgs A, Params P, GenBand B, const int32_t *device, const int32_t *duration, long long *obs,
@@ -2012,7 +2066,8 @@ genband_step_kernel(GenArgs A, Params P, GenBand B, const int32_t *device, const
     const bool valid = i < A.n_envs;
     const unsigned lane = threadIdx.x & 31u;
     const long long warpEnv0 = i - lane;
-    GenView v = gen_view_of(A, B, valid ? i : A.n_envs - 1);
+    constexpr int kMode = MODE_M ? MODE_M_PHILOX : MODE_R;
+    GenView v = gen_view_of(A, B, valid ? i : A.n_envs - 1, kMode);
     if (A.trace) { v.trace = A.trace + (valid ? i : 0) * A.trace_cap * 8; v.traceCap = A.trace_cap; }
     int before = 0;
     bool run = false;
@@ -2042,7 +2097,7 @@ genband_step_kernel(GenArgs A, Params P, GenBand B, const int32_t *device, const
                 const int ol = __ffs(owners) - 1;
                 owners &= owners - 1;
                 uint32_t m = __shfl_sync(FULL, cset, ol);
-                GenView w = gen_view_of(A, B, warpEnv0 + ol);
+                GenView w = gen_view_of(A, B, warpEnv0 + ol, kMode);
                 while (m) {
                     const int p = __ffs(m) - 1;
                     m &= m - 1;
@@ -2064,33 +2119,10 @@ genband_step_kernel(GenArgs A, Params P, GenBand B, const int32_t *device, const
             continue;
         }
         __syncwarp();                                   // the owners' state updates are visible to the helpers
-        const int cnt = __popc(mask);
-        int pre = cnt;                                  // inclusive prefix sum of the lanes' counts
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(FULL, pre, o);
-            if ((int)lane >= o) pre += t;
-        }
-        const int total = __shfl_sync(FULL, pre, 31);
-        const int excl = pre - cnt;
-        for (int t0 = 0; t0 < total; t0 += 32) {
-            const int t = t0 + (int)lane;
-            // owner of item t: the number of lanes whose inclusive prefix is <= t
-            int owner = 0;
-#pragma unroll
-            for (int stepw = 16; stepw >= 1; stepw >>= 1) {
-                const int q = __shfl_sync(FULL, pre, owner + stepw - 1);
-                if (q <= t) owner += stepw;
-            }
-            const int ol = owner < 32 ? owner : 31;
-            const int oExcl = __shfl_sync(FULL, excl, ol);
-            const uint32_t oMask = __shfl_sync(FULL, mask, ol);
-            if (t < total) {
-                const int p = (int)__fns(oMask, 0u, t - oExcl + 1);
-                GenView w = gen_view_of(A, B, warpEnv0 + ol);
-                gen_update_ber(w, P, p);
-            }
-        }
+        warp_spread(mask, lane, [&](int ol, int p) {
+            GenView w = gen_view_of(A, B, warpEnv0 + ol, kMode);
+            gen_update_ber(w, P, p);
+        });
         __syncwarp();                                   // the evaluated rates are visible to their owners
         if (!__any_sync(FULL, run)) break;
     }
@@ -3177,7 +3209,9 @@ static int grid_launch(gw_grid_handle *h, double duration, double *trace, int32_
     CUDA_TRY(cudaSetDevice(h->device));
     GridArgs A = h->A;
     A.trace = trace; A.trace_count = trace_count; A.trace_cap = cap;
-    grid_run_kernel<<<grid_for(A.n_envs, 64), 64, 0, (cudaStream_t)stream>>>(A, h->G, duration);
+    // small batches: one warp per block, so that the warps spread over more SMs (4,096 grids = 128 warps)
+    const int block = A.n_envs <= 148LL * 64 ? 32 : 64;
+    grid_run_kernel<<<grid_for(A.n_envs, block), block, 0, (cudaStream_t)stream>>>(A, h->G, duration);
     CUDA_TRY(cudaGetLastError());
     return GW_OK;
 }

@@ -349,7 +349,7 @@ int hs_gen_run(int ns, int nj, int factor, double frequency, double bandwidth, c
         GenView v;
         v.f = f.data() + e; v.i = iv.data() + e; v.stride = nenv;
         v.srx = per_env_pos ? srx.data() + e : srx.data(); v.srxStride = per_env_pos ? nenv : 1;
-        v.ns = ns; v.nj = nj; v.nd = nd; v.env = env_offset + e; v.trace = nullptr; v.ntrace = 0; v.traceCap = 0;
+        v.ns = ns; v.nj = nj; v.nd = nd; v.env = env_offset + e; v.mode = mode; v.trace = nullptr; v.ntrace = 0; v.traceCap = 0;
         return v;
     };
     if (per_env_pos) for (int64_t e = 0; e < nenv; ++e) gen_power_table(nd, pos + (size_t)e * nd * 2, power, frequency, srx.data() + e, nenv);
