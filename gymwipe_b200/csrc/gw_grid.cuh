@@ -37,6 +37,8 @@ struct GridParams {
     int maxMoves;                       // jumps per device in the offset tape (0: no mobility processes)
     double bitRate, dataRate, maxBer, tenLog10BitRate, qDen, bitsFactor;
     double frequency, thermal;
+    double fsplConst;                   // 20 * log10(frequency), evaluated once on the host (a move evaluates the FSPL towards
+                                        // every partner: one log10 less each)
     double moveInterval;
     double power[kGridMaxDev];          // dBm
     double interval[kGridMaxDev];       // send interval
@@ -227,25 +229,27 @@ GW_HD void grid_move(GridView &v, const GridParams &G, int m, double x, double y
         const double dist = sqrt(dx * dx + dy * dy);
         if (M.txSeq == 0u && v.dev[j].txSeq == 0u) {
             // no model yet (created at the first transmission of either device): the table follows the positions
-            const double fresh = (dx == 0.0 && dy == 0.0) ? 0.0 : 20 * log10(dist) + 20 * log10(G.frequency) - 147.55;
-            v.att[m * n + j] = fresh; v.att[j * n + m] = fresh;
-            v.srx[j * n + m] = rx_power_mw(G.power[m], fresh);
-            v.srx[m * n + j] = rx_power_mw(G.power[j], fresh);
+            const double fresh = (dx == 0.0 && dy == 0.0) ? 0.0 : 20 * log10(dist) + G.fsplConst - 147.55;
+            v.att[m * n + j] = fresh; v.att[j * n + m] = fresh;     // (received powers: evaluated at the next transmission start)
             continue;
         }
         if (!(dist < 3000.0)) continue;                         // STANDBY_THRESHOLD, physical.py:371
         if (dx == 0.0 && dy == 0.0) continue;                   // FsplAttenuation._update returns early
-        const double att = 20 * log10(dist) + 20 * log10(G.frequency) - 147.55;
+        const double att = 20 * log10(dist) + G.fsplConst - 147.55;
         if (att == v.att[m * n + j]) continue;                  // only a NEW value triggers
         v.att[m * n + j] = att; v.att[j * n + m] = att;
+        // SimplePhy._onAttenuationChange (simple_stack.py:119-128) exists only for transmissions that are on the air; the
+        // received power of a later transmission is evaluated from the attenuation of that moment at its start
+        // (simple_stack.py:130-144) -- so a move evaluates dbmToMilliwatts only for the links whose sender is sending
+        // (2 pow() per partner and move otherwise: with the FSPL's log10 most of what a mobile grid costs)
         for (int dir = 0; dir < 2; ++dir) {
             const int p = dir == 0 ? j : m, e = dir == 0 ? m : j;
-            const double rp = rx_power_mw(G.power[e], att);
             const int ph = v.dev[e].sphase;
-            const bool onAir = ph == S_HDR || ph == S_PAY;
+            if (ph != S_HDR && ph != S_PAY) continue;
+            const double rp = rx_power_mw(G.power[e], att);
             const double delta = rp - v.srx[p * n + e];
             v.srx[p * n + e] = rp;
-            if (onAir) grid_power_change(v, G, p, delta, false);
+            grid_power_change(v, G, p, delta, false);
         }
     }
 }
@@ -298,9 +302,11 @@ GW_HD void grid_apply(GridView &v, const GridParams &G, int kind, int d, const d
         D.sphase = S_HDR; D.tEv = tH; D.sEv = qH; D.tC = tC; D.sC = qC; D.txStart = now; D.tStop = stop;
         D.txSeq += 1; D.nTx += 1;
         grid_rec(v, REC_TX, now, d, stop, (G.hdrBytes[d] * 8) * G.bitsFactor, (G.payBytes[d] * 8) * G.bitsFactor, 0.0);
-        // zero-delay notification: every other PHY registers the received power (simple_stack.py:130-144)
+        // zero-delay notification: every other PHY registers the received power (simple_stack.py:130-144); with
+        // mobility processes it is evaluated here, from the attenuation of this moment (see grid_move)
         for (int p = 0; p < n; ++p) {
             if (p == d) continue;
+            if (G.maxMoves > 0) v.srx[p * n + d] = rx_power_mw(G.power[d], v.att[p * n + d]);
             grid_power_change(v, G, p, v.srx[p * n + d], false, defer);
             if (v.h->fault) return;
         }

@@ -3171,7 +3171,7 @@ int gw_grid_create(const gw_grid_config *cfg, int device, const double *position
     G.ndev = cfg->n_devices; G.maxMoves = cfg->max_moves; G.moveInterval = cfg->move_interval;
     G.bitRate = 133.33333e3; G.dataRate = 0.75 * G.bitRate; G.maxBer = gw_max_correctable_ber(3, 4);
     G.tenLog10BitRate = 10 * std::log10(G.bitRate); G.qDen = 1.135 * std::sqrt(2 * 3.141592653589793);
-    G.bitsFactor = 2 - 0.75; G.frequency = cfg->frequency_hz;
+    G.bitsFactor = 2 - 0.75; G.frequency = cfg->frequency_hz; G.fsplConst = 20 * std::log10(cfg->frequency_hz);
     G.thermal = 1.38e-23 * (20.0 + 273.15) * cfg->bandwidth_hz * 1000;
     for (int d = 0; d < cfg->n_devices; ++d) {
         G.power[d] = cfg->power_dbm[d]; G.interval[d] = cfg->send_interval[d];

@@ -285,7 +285,7 @@ int hs_grid_run(int n, double frequency, double bandwidth, const double *power, 
     G.ndev = n; G.maxMoves = max_moves; G.moveInterval = move_interval;
     G.bitRate = 133.33333e3; G.dataRate = 0.75 * G.bitRate; G.maxBer = 0.25;
     G.tenLog10BitRate = 10 * std::log10(G.bitRate); G.qDen = 1.135 * std::sqrt(2 * 3.141592653589793);
-    G.bitsFactor = 1.25; G.frequency = frequency; G.thermal = 1.38e-23 * (20.0 + 273.15) * bandwidth * 1000;
+    G.bitsFactor = 1.25; G.frequency = frequency; G.fsplConst = 20 * std::log10(frequency); G.thermal = 1.38e-23 * (20.0 + 273.15) * bandwidth * 1000;
     for (int d = 0; d < n; ++d) { G.power[d] = power[d]; G.interval[d] = interval[d]; G.hdrBytes[d] = hdr[d]; G.payBytes[d] = pay[d]; }
     std::vector<char> block(grid_state_bytes(n));
     GridView v = grid_view(block.data(), n);
