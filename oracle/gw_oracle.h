@@ -12,10 +12,10 @@
 extern "C" {
 #endif
 
-#define GWO_MAXDEV 24              /* devices per band held by the model (grids of PHY-only senders: up to 20 + ...) */
+#define GWO_MAXDEV 28              /* devices per band held by the model (grids of PHY-only senders: up to 24; bands: 8 senders + RRM + 16 PHY-only senders) */
 #define GWO_BATCH_DEV 8            /* device stride of the batch API's pos / counts arrays (kept from round 1) */
 #define GWO_MAXBAND 4
-#define GWO_MAXTX 24
+#define GWO_MAXTX 28
 
 #define GWO_ROLE_SENDER 1   /* SimpleNetworkDevice + traffic process (counter_traffic.py:37-61) */
 #define GWO_ROLE_RRM 2      /* SimpleRrmDevice (devices.py:113) */

@@ -15,7 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_build", "libgw_oracle.so")
 
-MAXDEV, MAXBAND, MAXTX = 24, 4, 24
+MAXDEV, MAXBAND, MAXTX = 28, 4, 28
 BATCH_DEV = 8           # device stride of the batch API's pos / counts arrays
 ROLE = {"sender": 1, "rrm": 2, "jammer": 3}
 MODE_R, MODE_M = 0, 1

@@ -352,3 +352,43 @@ def test_cuda_general_band_mode_m_matches_oracle_and_is_sharding_invariant(seed)
     env.check()
     assert (env.delivered().cpu().numpy() == o["counts"][:, 0, 1:1 + ns]).all()
     assert torch.equal(shard.delivered(), env.delivered()[nenv // 2:])
+
+
+def _max_band(rs):
+    """The largest band the engine holds: 8 MAC senders + RRM + 16 PHY-only senders (25 devices)."""
+    return random_scenario_n(rs, 8, 16, spread=3.0, receive=True, bursts=True)
+
+
+def test_core_general_maximum_configuration_vs_oracle():
+    rs = np.random.RandomState(8816)
+    sc = _max_band(rs)
+    T = 40
+    dev = rs.randint(0, 8, size=(T, 1)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, 1)).astype(np.int32)
+    steps, ntx, nd, nrecv, _ = _oracle_tape(sc, dev, dur)
+    h = HS.gen_run(sc, dev, dur)
+    _assert_host_equals(h, steps, ntx, nd, nrecv, 8, "8 senders + RRM + 16 PHY-only senders")
+    assert ntx > 50
+
+
+@pytest.mark.gpu
+def test_cuda_general_maximum_configuration_ragged_batch_vs_oracle():
+    """25 devices per band, 77 envs (two full warps and a ragged one: the idle lanes of the last warp still take part in
+    the warp-wide BER evaluations), modes R and M."""
+    import torch
+    rs = np.random.RandomState(8817)
+    sc = _max_band(rs)
+    nenv, T = 77, 24
+    dev = rs.randint(0, 8, size=(T, nenv)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, nenv)).astype(np.int32)
+    for mode, omode in (("reference", O.MODE_R), ("mask_philox", O.MODE_M)):
+        o = O.run_batch(sc, dev, dur, mode=omode, seed=5, env_id_offset=900)
+        env = _gpu_env(sc, nenv, mode=mode, seed=5, env_id_offset=900)
+        env.reset()
+        for t in range(T):
+            obs, rew, done, _ = env.step({"device": torch.as_tensor(dev[t]).cuda(), "duration": torch.as_tensor(dur[t]).cuda()})
+            assert (obs.cpu().numpy() == o["obs"][t, :, 0]).all() and (rew.cpu().numpy() == o["reward"][t, :, 0]).all(), (mode, t)
+            assert (env.now.cpu().numpy() == o["now"][t]).all(), (mode, t)
+        env.check()
+        assert (env.transmissions().cpu().numpy() == o["counts"][:, 0, 0]).all()
+        assert (env.delivered().cpu().numpy() == o["counts"][:, 0, 1:9]).all()
