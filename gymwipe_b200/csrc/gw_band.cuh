@@ -61,8 +61,10 @@ struct GenView {
     double *f;
     int32_t *i;
     long long stride;
-    const double *srx;                  // received power (mW), entry (receiver p, sender d) at srx[(p * nd + d) * srxStride]
+    double *srx;                        // received power (mW), entry (receiver p, sender d) at srx[(p * nd + d) * srxStride]
     long long srxStride;
+    double *att;                        // attenuation (dB), same layout, and current positions [nd][2] at pos[(2 * d + c) * srxStride]:
+    double *pos;                        //   held for per-env geometries only (devices that move between steps), else null
     int ns, nj, nd;
     long long env;                      // global env id (mode M: key of the error masks)
     int mode;                           // MODE_R / MODE_M_PHILOX: a compile-time constant in the kernels (no mode-M code or stores in mode R)
@@ -101,6 +103,9 @@ struct GenView {
 #undef GEN_I
 #undef GEN_U
     GW_HD double rp(int p, int d) const { return srx[(long long)(p * nd + d) * srxStride]; }
+    GW_HD double &rpw(int p, int d) const { return srx[(long long)(p * nd + d) * srxStride]; }
+    GW_HD double &attw(int p, int d) const { return att[(long long)(p * nd + d) * srxStride]; }
+    GW_HD double &posw(int d, int c) const { return pos[(long long)(2 * d + c) * srxStride]; }
 };
 
 static_assert(GenView::kScalars == 14, "scalar block of the int32 state");
@@ -117,14 +122,17 @@ GW_HD void gen_rec(GenView &v, int kind, double t, int dev, double x0, double x1
 
 // received-power table of a geometry: pos [nd][2], power [nd] (dBm) -> srx [nd * nd] with the given stride
 // (FsplAttenuation._update, attenuation_models.py:28-36; dbmToMilliwatts(power - attenuation), simple_stack.py:111)
-GW_HD void gen_power_table(int nd, const double *pos, const double *power, double frequency, double *srx, long long stride)
+GW_HD void gen_power_table(int nd, const double *pos, const double *power, double frequency, double *srx, long long stride,
+                           double *att = nullptr, double *posOut = nullptr)
 {
     for (int p = 0; p < nd; ++p)
         for (int d = 0; d < nd; ++d) {
-            double rp = 0.0;
-            if (p != d) rp = rx_power_mw(power[d], fspl_db(pos[2 * p], pos[2 * p + 1], pos[2 * d], pos[2 * d + 1], frequency));
+            double a = 0.0, rp = 0.0;
+            if (p != d) { a = fspl_db(pos[2 * p], pos[2 * p + 1], pos[2 * d], pos[2 * d + 1], frequency); rp = rx_power_mw(power[d], a); }
             srx[(long long)(p * nd + d) * stride] = rp;
+            if (att) att[(long long)(p * nd + d) * stride] = a;
         }
+    if (posOut) for (int k = 0; k < 2 * nd; ++k) posOut[(long long)k * stride] = pos[k];
 }
 
 // construction-time state (counter_traffic.py:114-133; the harness scenario of N senders): process Initialize events
@@ -563,6 +571,50 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
         v.sc(GenView::I_fault) = FAULT_EMPTY;
     }
     return berMask;
+}
+
+// Devices moving between steps (Position.set, devices/core.py:75-84): `want` [nd][2] are the requested positions, the
+// devices are moved one after the other by ascending index.  The run-time-count form of gw_core.cuh::move_devices --
+// see the comments there: models beyond STANDBY_THRESHOLD or with coinciding devices keep their value
+// (physical.py:383-386, attenuation_models.py:31-33), only a NEW value triggers (physical.py:354-362), a pair
+// neither of whose devices has transmitted yet has no model (its table entry follows the positions), and
+// transmissions that are on the air go through SimplePhy._onAttenuationChange (simple_stack.py:119-128): the PHY's
+// power sum changes, a running reception counts the segment that ends and re-evaluates its bit error rate.
+GW_HD void gen_move_devices(GenView &v, const Params &P, const GenBand &B, const double *power, double frequency, const double *want)
+{
+    const int nd = v.nd;
+    for (int m = 0; m < nd; ++m) {
+        const double x = want[2 * m], y = want[2 * m + 1];
+        if (x == v.posw(m, 0) && y == v.posw(m, 1)) continue;               // Position.set: no trigger
+        v.posw(m, 0) = x; v.posw(m, 1) = y;
+        for (int j = 0; j < nd; ++j) {
+            if (j == m) continue;
+            const double dx = x - v.posw(j, 0), dy = y - v.posw(j, 1);
+            const double dist = sqrt(dx * dx + dy * dy);                    // devices/core.py:88-95
+            if (v.txSeq(m) == 0u && v.txSeq(j) == 0u) {
+                const double fresh = (dx == 0.0 && dy == 0.0) ? 0.0 : 20 * log10(dist) + 20 * log10(frequency) - 147.55;
+                v.attw(m, j) = fresh; v.attw(j, m) = fresh;
+                v.rpw(j, m) = rx_power_mw(power[m], fresh);
+                v.rpw(m, j) = rx_power_mw(power[j], fresh);
+                continue;
+            }
+            if (!(dist < 3000.0)) continue;                                 // STANDBY_THRESHOLD
+            if (dx == 0.0 && dy == 0.0) continue;                           // _update returns early
+            const double att = 20 * log10(dist) + 20 * log10(frequency) - 147.55;
+            if (att == v.attw(m, j)) continue;
+            v.attw(m, j) = att; v.attw(j, m) = att;
+            for (int dir = 0; dir < 2; ++dir) {                             // (receiver j, sender m), (receiver m, sender j)
+                const int p = dir == 0 ? j : m, e = dir == 0 ? m : j;
+                const double rp = rx_power_mw(power[e], att);
+                const int ph = v.sphase(e);
+                const double delta = rp - v.rp(p, e);
+                v.rpw(p, e) = rp;
+                if (ph == S_HDR || ph == S_PAY) {
+                    if (gen_power_change(v, P, B, p, delta, false)) gen_update_ber(v, P, p);
+                }
+            }
+        }
+    }
 }
 
 // SimpleRrmDevice.assignFrequencyBand + SimpleRrmMac._sendAnnouncement start (devices.py:178-203,

@@ -2007,6 +2007,8 @@ struct GenArgs {
     double *f64;                // [gen_f64_words][n_envs]
     int32_t *i32;               // [gen_i32_words][n_envs]
     double *srx;                // [nd * nd][n_envs] or [nd * nd]
+    double *att;                // [nd * nd][n_envs] attenuation (dB) and
+    double *pos;                // [nd * 2][n_envs] current positions: per-env geometries only (devices may move)
     long long n_envs;
     int per_env;
     double *trace;              // [n_envs][cap][8] or NULL
@@ -2021,6 +2023,7 @@ __device__ __forceinline__ GenView gen_view_of(const GenArgs &A, const GenBand &
     v.mode = mode < 0 ? B.mode : mode;
     v.f = A.f64 + i; v.i = A.i32 + i; v.stride = A.n_envs;
     v.srx = A.per_env ? A.srx + i : A.srx; v.srxStride = A.per_env ? A.n_envs : 1;
+    v.att = A.per_env ? A.att + i : nullptr; v.pos = A.per_env ? A.pos + i : nullptr;
     v.ns = B.ns; v.nj = B.nj; v.nd = B.nd; v.env = B.envOffset + i;
     v.trace = nullptr; v.ntrace = 0; v.traceCap = 0;
     return v;
@@ -2032,9 +2035,21 @@ __global__ void genband_init_kernel(GenArgs A, GenBand B, const double *pos, con
     if (i >= A.n_envs) return;
     // per-env geometries: the table is evaluated here (libdevice log10 / pow: within 2 ulp of the host's); a geometry
     // common to all envs is evaluated once on the host, with the C library the reference's Python runs on
-    if (A.per_env) gen_power_table(B.nd, pos + i * B.nd * 2, power, frequency, A.srx + i, A.n_envs);
+    if (A.per_env) gen_power_table(B.nd, pos + i * B.nd * 2, power, frequency, A.srx + i, A.n_envs, A.att + i, A.pos + i);
     GenView v = gen_view_of(A, B, i);
     gen_init(v, B);
+}
+
+// gw_genband_set_positions: every env moves its devices one after the other (gw_band.cuh::gen_move_devices)
+__global__ void genband_move_kernel(GenArgs A, Params P, GenBand B, const double *power, double frequency, const double *want)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_envs) return;
+    GenView v = gen_view_of(A, B, i);
+    if (v.sc(GenView::I_fault)) return;
+    gen_move_devices(v, P, B, power, frequency, want + i * B.nd * 2);
+    const int fault = v.sc(GenView::I_fault);
+    if (fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = fault; } }
 }
 
 __global__ void genband_reset_kernel(GenArgs A, GenBand B, long long *obs)
@@ -2166,6 +2181,7 @@ __global__ void genband_read_kernel(GenArgs A, GenBand B, int field, double *out
 struct gw_genband_handle {
     gw_genband_config cfg;
     int device;
+    double *dpower;             // transmission powers (dBm) per device
     Params P;
     GenBand B;
     GenArgs A;
@@ -3310,11 +3326,13 @@ int gw_genband_create(const gw_genband_config *cfg, int device, const double *po
     GenArgs &A = h->A;
     A.n_envs = cfg->n_envs; A.per_env = cfg->per_env_positions ? 1 : 0;
     const size_t n = (size_t)cfg->n_envs;
-    double *dpower = nullptr;
+    double *&dpower = h->dpower;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMalloc((void **)&A.f64, sizeof(double) * gen_f64_words(ns, nj) * n);
     if (e == cudaSuccess) e = cudaMalloc((void **)&A.i32, sizeof(int32_t) * gen_i32_words(ns, nj) * n);
     if (e == cudaSuccess) e = cudaMalloc((void **)&A.srx, sizeof(double) * B.nd * B.nd * (A.per_env ? n : 1));
+    if (e == cudaSuccess && A.per_env) e = cudaMalloc((void **)&A.att, sizeof(double) * B.nd * B.nd * n);
+    if (e == cudaSuccess && A.per_env) e = cudaMalloc((void **)&A.pos, sizeof(double) * 2 * B.nd * n);
     if (e == cudaSuccess) e = cudaMalloc((void **)&h->errflag, 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemsetAsync(h->errflag, 0, 4 * sizeof(int), s);
     if (e == cudaSuccess) e = cudaMalloc((void **)&dpower, sizeof power);
@@ -3338,7 +3356,6 @@ int gw_genband_create(const gw_genband_config *cfg, int device, const double *po
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);                         // `power` is a stack array
-    if (dpower) cudaFree(dpower);
     if (e != cudaSuccess) { gw_genband_destroy(h); return fail(GW_E_CUDA, "general band engine: %s", cudaGetErrorString(e)); }
     *out = h;
     return GW_OK;
@@ -3351,8 +3368,21 @@ void gw_genband_destroy(gw_genband_handle *h)
     if (h->A.f64) cudaFree(h->A.f64);
     if (h->A.i32) cudaFree(h->A.i32);
     if (h->A.srx) cudaFree(h->A.srx);
+    if (h->A.att) cudaFree(h->A.att);
+    if (h->A.pos) cudaFree(h->A.pos);
+    if (h->dpower) cudaFree(h->dpower);
     if (h->errflag) cudaFree(h->errflag);
     delete h;
+}
+
+int gw_genband_set_positions(gw_genband_handle *h, const double *positions, void *stream)
+{
+    if (!h || !positions) return fail(GW_E_INVALID, "NULL argument");
+    if (!h->A.per_env) return fail(GW_E_INVALID, "handle was created with per_env_positions = 0");
+    CUDA_TRY(cudaSetDevice(h->device));
+    genband_move_kernel<<<grid_for(h->A.n_envs, 64), 64, 0, (cudaStream_t)stream>>>(h->A, h->P, h->B, h->dpower, h->cfg.frequency_hz, positions);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
 }
 
 int gw_genband_reset(gw_genband_handle *h, int64_t *obs, void *stream)

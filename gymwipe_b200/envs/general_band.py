@@ -198,6 +198,19 @@ class GeneralBandEnv(BaseEnv):
             return int(self._obs[0]), float(self._reward[0]), bool(self._done[0]), recs[0]
         return self._obs, self._reward, self._done.to(torch.bool), recs
 
+    def set_positions(self, positions):
+        """Devices moving between steps: float64 ``[num_envs, n_devices, 2]``; every env moves its devices one after the
+        other by ascending index like successive ``device.position.set(x, y)`` calls (``devices/core.py:75-84``) --
+        transmissions that are on the air see ``SimplePhy._onAttenuationChange``.  Needs an env created with
+        ``positions=`` (per-env geometries)."""
+        pos = torch.as_tensor(positions, dtype=torch.float64, device=self.device).contiguous()
+        if tuple(pos.shape) != (self.num_envs, self.n_devices, 2):
+            raise ValueError("positions must have shape [num_envs, n_devices, 2]")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gw_genband_set_positions(self._handle, pos.data_ptr(), self._stream()))
+        if self.strict:
+            self.check()
+
     def check(self):
         """Synchronises and raises if an action was outside the action space or an env hit a condition under
         which the reference raises."""

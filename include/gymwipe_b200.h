@@ -419,6 +419,13 @@ typedef struct gw_genband_handle gw_genband_handle;
 int gw_genband_create(const gw_genband_config *cfg, int device, const double *positions, void *stream,
                       gw_genband_handle **out);
 void gw_genband_destroy(gw_genband_handle *h);
+/* Devices moving between steps, for handles with per_env_positions: positions device float64 [n_envs][n_devices][2].
+ * Every env moves its devices one after the other by ascending index like successive Position.set calls
+ * (devices/core.py:75-84) with the semantics of gw_set_positions on a stepped handle: attenuation models beyond
+ * STANDBY_THRESHOLD or with coinciding devices keep their value, only a new value triggers, pairs that have not
+ * transmitted yet follow the positions, and transmissions that are on the air go through
+ * SimplePhy._onAttenuationChange (simple_stack.py:119-128). */
+int gw_genband_set_positions(gw_genband_handle *h, const double *positions, void *stream);
 /* CounterTrafficEnv.reset (counter_traffic.py:135-144) of every env; obs (device int64 [n_envs]) may be NULL. */
 int gw_genband_reset(gw_genband_handle *h, int64_t *obs, void *stream);
 /* CounterTrafficEnv.step (counter_traffic.py:146-158).  Device arrays [n_envs]: device in [0, n_senders),

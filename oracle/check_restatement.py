@@ -68,6 +68,45 @@ def compare(ref, ora, label, ber_rtol=0.0):
     return bad
 
 
+def compare_mobile(ref, ora, label, err_rtol=2e-2, ber_rtol=1e-4):
+    """
+    Comparison for devices that move while SEVERAL transmissions are on the air.  A moving device's attenuation models
+    are notified in Python-set order in the reference (simtools.py:255: by object hash -- two runs of the reference
+    itself differ), every notification charges the running reception with the errors since the last RESET (appendix
+    B #5) at the rate of that moment, so error sums (and the rates in between) depend on that order at the 1e-3 level,
+    the final rate of an instant through the rounding of the power sum at the 1e-8 level (times the exponent of
+    exp(-Eb/N0) for rates that are astronomically small: observed 6e-6 at rates of 1e-58).  Compared: step results,
+    transmissions, deliveries exactly; decisions: time / device / section / bit count / verdict exactly, error sum
+    within `err_rtol`; rates: per (device, instant) the same number of evaluations, the last one within `ber_rtol`.
+    """
+    bad = 0
+    assert ref["reset_obs"] == ora["reset_obs"]
+    for i, (a, b) in enumerate(zip(ref["steps"], ora["steps"])):
+        ok = (a["obs"], a["reward"], a["done"], a["now"]) == (b["obs"], b["reward"], b["done"], b["now"])
+        ra, rb = [tuple(r) for r in a["records"]], [tuple(r) for r in b["records"]]
+        ok = ok and [r for r in ra if r[0] in ("tx", "rx", "mrx")] == [r for r in rb if r[0] in ("tx", "rx", "mrx")]
+        key = lambda r: (r[3], r[1], r[4])
+        da, db = sorted([r for r in ra if r[0] == "dec"], key=key), sorted([r for r in rb if r[0] == "dec"], key=key)
+        ok = ok and len(da) == len(db)
+        for x, y in zip(da, db):
+            ok = ok and x[:5] == y[:5] and x[6:] == y[6:] and abs(x[5] - y[5]) <= err_rtol * max(abs(x[5]), abs(y[5]), 1e-300)
+        ga, gb = {}, {}
+        for recs, g in ((ra, ga), (rb, gb)):
+            for r in recs:
+                if r[0] == "ber":
+                    g.setdefault((r[3], r[1]), []).append(r[4])
+        ok = ok and sorted(ga) == sorted(gb)
+        if ok:
+            for k in ga:
+                x, y = ga[k][-1], gb[k][-1]
+                ok = ok and len(ga[k]) == len(gb[k]) and abs(x - y) <= ber_rtol * max(abs(x), abs(y), 1e-30)
+        if not ok:
+            bad += 1
+            if bad == 1:
+                print("[%s] MISMATCH at step %d action %s" % (label, i, a["action"]))
+    return bad
+
+
 def run_case_m(scenario, tape, label, seed=77, env_id=12345, moves=None):
     """mode M: reference + MaskedPhy subclass (numpy Philox) vs the restatement (C Philox)."""
     tr = H.Tracer()
@@ -86,7 +125,7 @@ def run_case_m(scenario, tape, label, seed=77, env_id=12345, moves=None):
     return bad
 
 
-def run_case(scenario, tape, label, do_reset=True, use_default_class=False, moves=None):
+def run_case(scenario, tape, label, do_reset=True, use_default_class=False, moves=None, mobile=False):
     tr = H.Tracer()
     if use_default_class:
         env = H.make_default_env(tr)
@@ -94,7 +133,7 @@ def run_case(scenario, tape, label, do_reset=True, use_default_class=False, move
         env = H.ScenarioEnv(scenario, tr)
     ref = H.run_tape(env, tape, tr, do_reset=do_reset, moves=moves)
     ora = O.run_tape(O.Oracle(scenario, trace=True), tape, do_reset=do_reset, moves=moves)
-    bad = compare(ref, ora, label)
+    bad = compare_mobile(ref, ora, label) if mobile else compare(ref, ora, label)
     ev_ref = sum(s["events"] for s in ref["steps"])
     ev_ora = sum(s["events"] for s in ora["steps"])
     print("[%s] steps %d mismatching %d ; heap pops ref %d / restatement %d" %
@@ -150,6 +189,32 @@ def random_scenario_n(rs, ns, nj, spread=2.5, factor=1000, receive=False, bursts
                      "interval": float(airtime * rs.uniform(2.0, 9.0) * max(1, nj)), "delay": float(rs.uniform(0, 1e-2)),
                      "power": float(rs.choice([0.0, 10.0, 20.0])), "hdr": 13, "payload": payload})
     return {"assignment_duration_factor": factor, "bands": [{"frequency": 2.4e9, "bandwidth": 22e6, "devices": devs}]}
+
+
+def nsender_moves(rs, sc, steps, start=1):
+    """Before every other step one to three devices (ascending index) jump -- within the band's area or far beyond
+    STANDBY_THRESHOLD --; the PHY-only senders are made busy so that transmissions are on the air at step boundaries
+    (SimplePhy._onAttenuationChange).  (Jumps ONTO another device's position are pinned on the four-device band of
+    --case mobilityquirks: with several equal-power signals from one spot on the air the noise power is signal-minus-
+    signal residue, and whether a rate is 0.5 or 0.49 depends on the reference's own set iteration order.)"""
+    devs = sc["bands"][0]["devices"]
+    nd = len(devs)
+    for d in devs:
+        if d["role"] == "jammer":
+            d["interval"] = float(rs.uniform(0.008, 0.02))
+    cur = [(d["x"], d["y"]) for d in devs]
+    moves = {}
+    for t in range(start, steps, 2):
+        lst = []
+        for d in sorted(set(int(v) for v in rs.randint(nd, size=int(rs.randint(1, 4))))):
+            if int(rs.randint(5)) == 0:
+                x, y = float(rs.uniform(4000, 6000)), float(rs.uniform(-10, 10))
+            else:
+                x, y = float(rs.uniform(-3, 3)), float(rs.uniform(-3, 3))
+            cur[d] = (x, y)
+            lst.append((0, d, float(x), float(y)))
+        moves[t] = lst
+    return moves
 
 
 def child(args):
@@ -235,6 +300,15 @@ def child(args):
         sc = random_scenario_n(rs, ns, nj, spread=args.spread, receive=bool(args.seed % 2), bursts=bool(args.seed % 3 == 0))
         tape = H.random_actions(args.steps, seed=args.seed + 11000, devices=ns)
         return run_case(sc, tape, "%d senders + RRM + %d PHY-only senders, seed %d" % (ns, nj, args.seed))
+    if args.case in ("nsendersmobility", "masknsendersmobility"):
+        ns, nj = int(rs.randint(3, 7)), int(rs.randint(1, 5))
+        sc = random_scenario_n(rs, ns, nj, spread=args.spread, receive=bool(args.seed % 2))
+        tape = H.random_actions(args.steps, seed=args.seed + 13000, devices=ns)
+        moves = nsender_moves(rs, sc, args.steps, start=args.seed % 2)
+        label = "%d senders + RRM + %d PHY-only senders moving between steps, seed %d" % (ns, nj, args.seed)
+        if args.case == "nsendersmobility":
+            return run_case(sc, tape, label, moves=moves, mobile=True)
+        return run_case_m(sc, tape, "mode M, " + label, seed=args.seed + 82, moves=moves)
     if args.case == "masknsenders":
         ns, nj = int(rs.randint(3, 7)), int(rs.randint(0, 4))
         sc = random_scenario_n(rs, ns, nj, spread=args.spread, receive=bool(args.seed % 2))
@@ -279,7 +353,8 @@ def main():
         plan += [("positions", sd, 200), ("jammer", sd, 200), ("long", sd, 40), ("multiband", sd, 80),
                  ("maskdefault", sd, 120), ("maskjammer", sd, 120), ("masklong", sd, 20),
                  ("mobilityjam", sd, 120), ("maskmobilityjam", sd, 80), ("mobilityquirks", sd, 100),
-                 ("nsenders", sd, 120), ("masknsenders", sd, 40)]
+                 ("nsenders", sd, 120), ("masknsenders", sd, 40), ("nsendersmobility", sd, 80),
+                 ("masknsendersmobility", sd, 30)]
     failed = 0
     for case, sd, steps in plan:
         rc = subprocess.call([sys.executable, os.path.abspath(__file__), "--case", case,

@@ -47,6 +47,7 @@ CASES = {
     "nsenders_8s_6p_seed32": ("nsenders:8:6:1:1", 32, 60),
     "nsenders_3s_16p_seed33": ("nsenders:3:16:0:0", 33, 40),
     "modeM_nsenders_4s_2p_seed34": ("masknsenders:4:2:1:0", 34, 40),
+    "nsenders_mobility_5s_3p_seed35": ("nsendersmove:5:3:1:0", 35, 60),
 }
 
 MASK_SEED, MASK_ENV = 20261018, 4242
@@ -100,7 +101,7 @@ def make_case(kind, seed, steps):
         sc["bands"][0]["devices"][0]["receive"] = True
         sc["bands"][0]["devices"][1]["receive"] = True
         sc["bands"][0]["devices"][1]["max_ticks"] = 45
-    elif kind.startswith("nsenders:") or kind.startswith("masknsenders:"):
+    elif kind.startswith("nsenders:") or kind.startswith("masknsenders:") or kind.startswith("nsendersmove:"):
         # ns MAC senders + RRM + nj PHY-only senders, with / without receive mode and finite bursts
         _, ns, nj, rcv, bursts = kind.split(":")
         sc = CR.random_scenario_n(rs, int(ns), int(nj), spread=2.5, receive=bool(int(rcv)), bursts=bool(int(bursts)))
@@ -114,6 +115,8 @@ def child(name):
     kind, seed, steps = CASES[name]
     H.setup_paths()
     sc, tape, do_reset, use_default = make_case(kind, seed, steps)
+    # (nsender_moves also makes the PHY-only senders busy: before the env is constructed)
+    pre_moves = CR.nsender_moves(np.random.RandomState(seed + 3), sc, steps) if kind.startswith("nsendersmove:") else None
     tr = H.Tracer()
     mode_m = kind.startswith("mask")
     if mode_m:
@@ -134,6 +137,8 @@ def child(name):
         for t in range(1, steps, 2):
             devs = sorted(set(int(v) for v in mrs.randint(4, size=int(mrs.randint(1, 3)))))
             moves[t] = [(0, d, float(mrs.uniform(-2.5, 2.5)), float(mrs.uniform(-2.5, 2.5))) for d in devs]
+    if kind.startswith("nsendersmove:"):
+        moves = pre_moves
     if kind == "mobilityquirks":
         # jumps beyond STANDBY_THRESHOLD, onto another device's position and back -- from before the first
         # step on, i.e. also while the pair's attenuation model does not exist yet

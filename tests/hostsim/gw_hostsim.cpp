@@ -320,7 +320,8 @@ int hs_gen_run(int ns, int nj, int factor, double frequency, double bandwidth, c
                const double *cfg_d, const double *pos, int per_env_pos, const double *power, int mode, uint64_t seed,
                int64_t env_offset, int64_t nenv, int nsteps,
                int reset_at, const int32_t *dev_tape, const int32_t *dur_tape, int64_t *obs, double *reward, uint8_t *done,
-               double *now_out, int64_t *counts, double *trace, int trace_cap, int32_t *trace_counts)
+               double *now_out, int64_t *counts, double *trace, int trace_cap, int32_t *trace_counts,
+               const HsMove *moves, int nmoves)
 {
     Params P;
     std::memset(&P, 0, sizeof P);
@@ -343,16 +344,20 @@ int hs_gen_run(int ns, int nj, int factor, double frequency, double bandwidth, c
         B.jamInterval[j] = cfg_d[8 + j]; B.jamDelay[j] = cfg_d[24 + j];
     }
     const int nd = B.nd, fw = gen_f64_words(ns, nj), iw = gen_i32_words(ns, nj);
-    std::vector<double> f((size_t)fw * nenv), srx((size_t)nd * nd * (per_env_pos ? nenv : 1));
+    const bool tables = per_env_pos || nmoves > 0;      // devices that move need the band-sim's own tables
+    std::vector<double> f((size_t)fw * nenv), srx((size_t)nd * nd * (tables ? nenv : 1));
+    std::vector<double> att(tables ? (size_t)nd * nd * nenv : 1), cur(tables ? (size_t)2 * nd * nenv : 1);
     std::vector<int32_t> iv((size_t)iw * nenv);
     auto view = [&](int64_t e) {
         GenView v;
         v.f = f.data() + e; v.i = iv.data() + e; v.stride = nenv;
-        v.srx = per_env_pos ? srx.data() + e : srx.data(); v.srxStride = per_env_pos ? nenv : 1;
+        v.srx = tables ? srx.data() + e : srx.data(); v.srxStride = tables ? nenv : 1;
+        v.att = tables ? att.data() + e : nullptr; v.pos = tables ? cur.data() + e : nullptr;
         v.ns = ns; v.nj = nj; v.nd = nd; v.env = env_offset + e; v.mode = mode; v.trace = nullptr; v.ntrace = 0; v.traceCap = 0;
         return v;
     };
-    if (per_env_pos) for (int64_t e = 0; e < nenv; ++e) gen_power_table(nd, pos + (size_t)e * nd * 2, power, frequency, srx.data() + e, nenv);
+    if (tables) for (int64_t e = 0; e < nenv; ++e)
+        gen_power_table(nd, pos + (per_env_pos ? (size_t)e * nd * 2 : 0), power, frequency, srx.data() + e, nenv, att.data() + e, cur.data() + e);
     else gen_power_table(nd, pos, power, frequency, srx.data(), 1);
     for (int64_t e = 0; e < nenv; ++e) { GenView v = view(e); gen_init(v, B); }
     int used = 0, fault = 0;
@@ -361,6 +366,16 @@ int hs_gen_run(int ns, int nj, int factor, double frequency, double bandwidth, c
             GenView v = view(e);
             if (t == reset_at) gen_reset(v, B);
             if (e == 0 && trace) { v.trace = trace + (size_t)used * 8; v.traceCap = trace_cap - used; }
+            {   // devices that jump before this step (all envs alike): successive Position.set calls in the order given
+                std::vector<double> want(2 * nd);
+                bool any = false;
+                for (int k = 0; k < nmoves; ++k) {
+                    if (moves[k].step != t) continue;
+                    if (!any) { for (int q = 0; q < 2 * nd; ++q) want[q] = cur[(size_t)q * nenv + e]; any = true; }
+                    want[2 * moves[k].dev] = moves[k].x; want[2 * moves[k].dev + 1] = moves[k].y;
+                }
+                if (any) gen_move_devices(v, P, B, power, frequency, want.data());
+            }
             long long o; double r; unsigned char d;
             gen_step(v, P, B, dev_tape[(size_t)t * nenv + e], dur_tape[(size_t)t * nenv + e], o, r, d);
             obs[(size_t)t * nenv + e] = o; reward[(size_t)t * nenv + e] = r; done[(size_t)t * nenv + e] = d;

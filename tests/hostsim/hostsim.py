@@ -197,7 +197,8 @@ def grid_run(scenario, durations, move_delays=None, offsets=None, move_interval=
     return {"rc": rc, "now": list(now), "records": records, "stats": stats}
 
 
-def gen_run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, reset_at=None, trace_cap=400000, mode=0, seed=0, env_offset=0):
+def gen_run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, reset_at=None, trace_cap=400000, mode=0, seed=0, env_offset=0,
+            moves=None):
     """General band engine (``gw_band.cuh``) on the host: a one-band scenario dict with any number of senders
     (<= 8), the RRM and PHY-only senders (<= 16); ``dev_tape`` / ``dur_tape`` int32 ``[nsteps, nenv]``; ``pos``
     optional float64 ``[nenv, nd, 2]``.  Returns obs / reward / done / now ``[nsteps, nenv]``, ``counts``
@@ -236,13 +237,18 @@ def gen_run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, reset_at=None
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     L.hs_gen_run.restype = C.c_int
     L.hs_gen_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int,
-                             C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_void_p]
+                             C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 8 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    # moves: {step: [(band, dev, x, y), ...]} -- devices that jump before that step (ascending device index), in every env
+    mv = [(t, d, x, y) for t, lst in sorted((moves or {}).items()) for (_, d, x, y) in sorted(lst, key=lambda m: m[1])]
+    arr = (HsMove * max(len(mv), 1))()
+    for k, (t, d, x, y) in enumerate(mv):
+        arr[k].step, arr[k].band, arr[k].dev, arr[k].x, arr[k].y = int(t), 0, int(d), float(x), float(y)
     if reset_at is None:
         reset_at = 0 if do_reset else -1
     rc = L.hs_gen_run(ns, nj, int(scenario.get("assignment_duration_factor", 1000)), float(band.get("frequency", 2.4e9)),
                       float(band.get("bandwidth", 22e6)), ptr(ci), ptr(cj), ptr(cd), ptr(p), 0 if pos is None else 1, ptr(power),
                       int(mode), int(seed), int(env_offset), nenv, nsteps, int(reset_at), ptr(dev_tape), ptr(dur_tape), ptr(obs), ptr(rew), ptr(done), ptr(now),
-                      ptr(counts), ptr(trace), trace_cap, ptr(tc))
+                      ptr(counts), ptr(trace), trace_cap, ptr(tc), C.cast(arr, C.c_void_p), len(mv))
     assert int(tc.sum()) <= trace_cap, "raise trace_cap"
     return {"rc": rc, "obs": obs, "reward": rew, "done": done, "now": now, "counts": counts,
             "records": records_from_trace(trace, tc)}

@@ -392,3 +392,143 @@ def test_cuda_general_maximum_configuration_ragged_batch_vs_oracle():
         env.check()
         assert (env.transmissions().cpu().numpy() == o["counts"][:, 0, 0]).all()
         assert (env.delivered().cpu().numpy() == o["counts"][:, 0, 1:9]).all()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# devices moving between steps (gw_genband_set_positions)
+# ------------------------------------------------------------------------------------------------------------
+
+def _random_moves(rs, sc, steps, start=1, colocate=True):
+    """Before every other step one to three devices (ascending index) jump: within the band's area, far beyond
+    STANDBY_THRESHOLD, or onto another device's position; busy PHY-only senders keep transmissions on the air."""
+    devs = sc["bands"][0]["devices"]
+    nd = len(devs)
+    for d in devs:
+        if d["role"] == "jammer":
+            d["interval"] = float(rs.uniform(0.008, 0.02))
+    cur = [(d["x"], d["y"]) for d in devs]
+    moves = {}
+    for t in range(start, steps, 2):
+        lst = []
+        for d in sorted(set(int(v) for v in rs.randint(nd, size=int(rs.randint(1, 4))))):
+            k = int(rs.randint(5))
+            if k == 0:
+                x, y = float(rs.uniform(4000, 6000)), float(rs.uniform(-10, 10))
+            elif k == 1 and colocate:
+                x, y = cur[int((d + 1 + rs.randint(nd - 1)) % nd)]
+            else:
+                x, y = float(rs.uniform(-3, 3)), float(rs.uniform(-3, 3))
+            cur[d] = (x, y)
+            lst.append((0, d, float(x), float(y)))
+        moves[t] = lst
+    return moves
+
+
+def _oracle_tape_moves(sc, dev, dur, moves, mode=O.MODE_R, seed=0, env_id=0):
+    ora = O.Oracle(sc, trace=True, mode=mode)
+    if mode == O.MODE_M:
+        ora.use_philox_masks(seed, env_id)
+    tape = [{"device": int(dev[t, 0]), "duration": int(dur[t, 0])} for t in range(dev.shape[0])]
+    res = O.run_tape(ora, tape, moves=moves)
+    ntx, nd = ora.counts()
+    return res["steps"], ntx, nd, ora.received(), ora
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_core_general_moving_devices_vs_oracle(seed):
+    """The engine equals the oracle record for record -- both move a device's links by ascending partner index."""
+    rs = np.random.RandomState(7000 + seed)
+    ns, nj = int(rs.randint(3, 7)), int(rs.randint(1, 5))
+    sc = random_scenario_n(rs, ns, nj, spread=2.5, receive=bool(seed % 2))
+    T = 50
+    dev = rs.randint(0, ns, size=(T, 1)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, 1)).astype(np.int32)
+    moves = _random_moves(rs, sc, T, start=seed % 2)
+    m = O.MODE_M if seed >= 6 else O.MODE_R
+    try:
+        steps, ntx, nd, nrecv, _ = _oracle_tape_moves(sc, dev, dur, moves, mode=m, seed=55, env_id=7)
+    except O.OracleFault:
+        pytest.skip("the reference raises in this scenario")
+    h = HS.gen_run(sc, dev, dur, moves=moves, mode=1 if m == O.MODE_M else 0, seed=55, env_offset=7)
+    _assert_host_equals(h, steps, ntx, nd, nrecv, ns, "moves seed %d" % seed)
+
+
+def test_oracle_and_core_match_reference_golden_nsenders_mobility():
+    from util import GOLDEN_NSENDERS_MOBILITY, assert_mobile_step_records
+    doc = load_golden(GOLDEN_NSENDERS_MOBILITY)
+    sc = doc["scenario"]
+    moves = {int(k): [tuple(m) for m in v] for k, v in doc["moves"].items()}
+    dev, dur = _tapes(doc)
+    steps, _, _, _, _ = _oracle_tape_moves(sc, dev, dur, moves)
+    h = HS.gen_run(sc, dev, dur, moves=moves)
+    assert h["rc"] == 0
+    for t, g in enumerate(doc["steps"]):
+        o = steps[t]
+        assert (o["obs"], o["reward"], o["done"], o["now"]) == (g["obs"], g["reward"], g["done"], g["now"]), t
+        assert (h["obs"][t, 0], h["reward"][t, 0], bool(h["done"][t, 0]), h["now"][t, 0]) == (g["obs"], g["reward"], g["done"], g["now"]), t
+        assert_mobile_step_records(o["records"], g["records"], "oracle step %d" % t)
+        assert_mobile_step_records(h["records"][t], g["records"], "core step %d" % t)
+        assert_step_records(h["records"][t], o["records"], "core vs oracle step %d" % t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(3))
+def test_cuda_general_band_moving_devices_vs_oracle(seed):
+    """GeneralBandEnv.set_positions between steps, 16 envs with the same tape of jumps: step results, step end times and
+    delivery counts equal the oracle's; modes R and M."""
+    import torch
+    rs = np.random.RandomState(7100 + seed)
+    ns, nj = int(rs.randint(3, 7)), int(rs.randint(1, 5))
+    sc = random_scenario_n(rs, ns, nj, spread=2.5, receive=bool(seed % 2))
+    nd, nenv, T = ns + 1 + nj, 16, 40
+    dev = np.repeat(rs.randint(0, ns, size=(T, 1)), nenv, axis=1).astype(np.int32)
+    dur = np.repeat(rs.randint(0, 20, size=(T, 1)), nenv, axis=1).astype(np.int32)
+    moves = _random_moves(rs, sc, T, start=seed % 2, colocate=False)
+    m = O.MODE_M if seed == 2 else O.MODE_R
+    steps, ntx, ndl, nrecv, _ = _oracle_tape_moves(sc, dev[:, :1], dur[:, :1], moves, mode=m, seed=9, env_id=0)
+    pos0 = np.array([[d["x"], d["y"]] for d in sc["bands"][0]["devices"]])
+    # every env has the same geometry and the same key (a batch of 16 one-env handles would do the same)
+    envs = [_gpu_env(sc, 1, positions=torch.as_tensor(pos0[None]), mode="mask_philox" if m == O.MODE_M else "reference", seed=9,
+                     env_id_offset=0)]
+    batch = _gpu_env(sc, nenv, positions=torch.as_tensor(np.repeat(pos0[None], nenv, axis=0)), mode="reference")
+    envs[0].reset(); batch.reset()
+    cur = pos0.copy()
+    for t in range(T):
+        if t in moves:
+            for (_, d, x, y) in moves[t]:
+                cur[d] = (x, y)
+            envs[0].set_positions(torch.as_tensor(cur[None]))
+            batch.set_positions(torch.as_tensor(np.repeat(cur[None], nenv, axis=0)))
+        obs, rew, done, _ = envs[0].step({"device": int(dev[t, 0]), "duration": int(dur[t, 0])})
+        s = steps[t]
+        assert (obs, rew, float(envs[0].now[0])) == (s["obs"], s["reward"], s["now"]), (seed, t)
+        ob, rb, _, _ = batch.step({"device": torch.as_tensor(dev[t]).cuda(), "duration": torch.as_tensor(dur[t]).cuda()})
+        if m == O.MODE_R:
+            assert (ob.cpu().numpy() == s["obs"]).all() and (batch.now.cpu().numpy() == s["now"]).all(), (seed, t)
+    assert envs[0].delivered()[0].tolist() == list(ndl[:ns]) and int(envs[0].transmissions()[0]) == ntx
+
+
+@pytest.mark.gpu
+def test_cuda_general_band_mobility_matches_reference_golden():
+    """The reference's own trace of a band of 5 senders + RRM + 3 PHY-only senders whose devices jump between steps
+    while transmissions are on the air: step results, transmissions, deliveries, verdicts exact; error sums and rates
+    within the tolerances that the reference's own set-order nondeterminism allows (util.assert_mobile_step_records)."""
+    import torch
+    from util import GOLDEN_NSENDERS_MOBILITY, assert_mobile_step_records
+    doc = load_golden(GOLDEN_NSENDERS_MOBILITY)
+    sc = doc["scenario"]
+    moves = {int(k): [tuple(m) for m in v] for k, v in doc["moves"].items()}
+    cur = np.array([[d["x"], d["y"]] for d in sc["bands"][0]["devices"]])
+    env = _gpu_env(sc, 1, positions=torch.as_tensor(cur[None]))
+    assert env.reset() == doc["reset_obs"]
+    for t, g in enumerate(doc["steps"]):
+        if t in moves:
+            for (_, d, x, y) in moves[t]:
+                cur[d] = (x, y)
+            env.set_positions(torch.as_tensor(cur[None]))
+        obs, rew, done, recs = env.step_traced({"device": g["action"]["device"], "duration": g["action"]["duration"]})
+        assert (obs, rew, done, float(env.now[0])) == (g["obs"], g["reward"], g["done"], g["now"]), t
+        # (the records of the jumps themselves belong to the set_positions call, which is not traced: compare the step's)
+        want = [r for r in g["records"] if not (r[0] == "ber" and r[1] == (doc["steps"][t - 1]["now"] if t else 0.0))]
+        got = [r for r in recs if not (r[0] == "ber" and r[1] == (doc["steps"][t - 1]["now"] if t else 0.0))]
+        assert_mobile_step_records(got, want, "step %d" % t)

@@ -102,6 +102,7 @@ def random_tapes(rs, nsteps, nenv, nb):
 
 
 GOLDEN_NSENDERS = ["nsenders_5s_3p_seed31", "nsenders_8s_6p_seed32", "nsenders_3s_16p_seed33"]
+GOLDEN_NSENDERS_MOBILITY = "nsenders_mobility_5s_3p_seed35"
 
 BER_RTOL = 1e-9          # north star: 1e-6 relative in fp64; observed ~1e-15 (libm / libdevice pow, log10 differ by <= 2 ulp)
 
@@ -127,6 +128,33 @@ def assert_step_records(got, want, label=""):
             worst = max(worst, rel)
             assert rel <= BER_RTOL, (label, g, w)
     return worst
+
+
+def assert_mobile_step_records(got, want, label="", err_rtol=2e-2, ber_rtol=1e-4):
+    """Trace records of one step against the REFERENCE's when devices moved while several transmissions were on the
+    air: a moving device's attenuation models are notified in Python-set order in the reference (``simtools.py:255``:
+    by object hash -- two runs of the reference itself differ), every notification charges the running reception
+    with the errors since the last RESET (appendix B #5) at the rate of that moment, so error sums depend on that
+    order at the 1e-2 level and the final rate of an instant at the 1e-8 level (more for astronomically small
+    rates).  Transmissions, deliveries, decider inputs (section, bit count) and verdicts: exact."""
+    got, want = [tuple(r) for r in got], [tuple(r) for r in want]
+    assert [r for r in got if r[0] in ("tx", "rx", "mrx")] == [r for r in want if r[0] in ("tx", "rx", "mrx")], label
+    key = lambda r: (r[3], r[1], r[4])
+    gd, wd = sorted([r for r in got if r[0] == "dec"], key=key), sorted([r for r in want if r[0] == "dec"], key=key)
+    assert len(gd) == len(wd), label
+    for a, b in zip(gd, wd):
+        assert a[:5] == b[:5] and a[6:] == b[6:], (label, a, b)
+        assert abs(a[5] - b[5]) <= err_rtol * max(abs(a[5]), abs(b[5]), 1e-300), (label, a, b)
+    gg, wg = {}, {}
+    for recs, g in ((got, gg), (want, wg)):
+        for r in recs:
+            if r[0] == "ber":
+                g.setdefault((r[3], r[1]), []).append(r[4])
+    assert sorted(gg) == sorted(wg), label
+    for k in wg:
+        assert len(gg[k]) == len(wg[k]), (label, k)
+        a, b = gg[k][-1], wg[k][-1]
+        assert abs(a - b) <= ber_rtol * max(abs(a), abs(b), 1e-30), (label, k, a, b)
 
 
 def random_scenario_n(rs, ns, nj, spread=2.5, factor=1000, receive=False, bursts=False):
