@@ -53,8 +53,8 @@ struct GenBand {
 };
 
 // words of one band-sim's state
-GW_HD int gen_f64_words(int ns, int nj) { return 3 + 9 * (ns + 1 + nj) + 3 * ns + nj; }
-GW_HD int gen_i32_words(int ns, int nj) { return 14 + 7 * (ns + 1 + nj) + 12 * ns + 3 * nj + kQueueCap * ns; }
+GW_HD int gen_f64_words(int ns, int nj) { return 4 + 9 * (ns + 1 + nj) + 3 * ns + nj; }
+GW_HD int gen_i32_words(int ns, int nj) { return 18 + 7 * (ns + 1 + nj) + 12 * ns + 3 * nj + kQueueCap * ns; }
 
 // view of one band-sim: word w of the fp64 / int32 state at f[w * stride] / i[w * stride]
 struct GenView {
@@ -78,27 +78,35 @@ struct GenView {
     GW_HD double &now() const { return f[0]; }
     GW_HD double &tRrm() const { return f[stride]; }
     GW_HD double &annSlots() const { return f[2 * stride]; }
+    GW_HD double &tTickMin() const { return f[3 * stride]; }    // a lower bound of the senders' next tick times (see gen_next_event)
     // PHY, per device (names as in gw_core.cuh::Sim)
-    GEN_F(P, 3) GEN_F(tEv, 3 + nd) GEN_F(tStop, 3 + 2 * nd) GEN_F(tC, 3 + 3 * nd) GEN_F(ber, 3 + 4 * nd)
-    GEN_F(err, 3 + 5 * nd) GEN_F(tReset, 3 + 6 * nd)
-    GEN_F(txStart, 3 + 7 * nd) GEN_F(segT0, 3 + 8 * nd)        // mode M: Transmission.startTime; start of the running segment
+    GEN_F(P, 4) GEN_F(tEv, 4 + nd) GEN_F(tStop, 4 + 2 * nd) GEN_F(tC, 4 + 3 * nd) GEN_F(ber, 4 + 4 * nd)
+    GEN_F(err, 4 + 5 * nd) GEN_F(tReset, 4 + 6 * nd)
+    GEN_F(txStart, 4 + 7 * nd) GEN_F(segT0, 4 + 8 * nd)        // mode M: Transmission.startTime; start of the running segment
     // senders
-    GEN_F(tTick, 3 + 9 * nd) GEN_F(stopW, 3 + 9 * nd + ns) GEN_F(rxT, 3 + 9 * nd + 2 * ns)
+    GEN_F(tTick, 4 + 9 * nd) GEN_F(stopW, 4 + 9 * nd + ns) GEN_F(rxT, 4 + 9 * nd + 2 * ns)
     // PHY-only senders
-    GEN_F(tJam, 3 + 9 * nd + 3 * ns)
+    GEN_F(tJam, 4 + 9 * nd + 3 * ns)
 
     enum : int { I_seq = 0, I_fault, I_ties, I_annDest, I_rrmPend, I_sRrm, I_assignDone, I_rv0, I_rv1, I_latestDiff,
-                 I_lastAbsDiff, I_done, I_nTx, I_pad, kScalars };
+                 I_lastAbsDiff, I_done, I_nTx,
+                 // summaries of the per-device / per-sender arrays, so that the event selection and the receiver loops of
+                 // the transition function visit only the entries that matter (the state lives in global memory):
+                 I_phyMask,             // bit d: PHY d has a timed event pending (sphase >= S_SLOT)
+                 I_rxMask,              // bit p: PHY p is receiving (rxOf >= 0)
+                 I_wMask,               // bit k: sender k's window time-out is pending
+                 I_condMask,            // bit k: sender k's MAC waits for a packet (MAC_WAIT_COND)
+                 I_pad, kScalars };
     GW_HD int32_t &sc(int w) const { return i[(long long)w * stride]; }
     GW_HD uint32_t &seq() const { return ((uint32_t *)i)[(long long)I_seq * stride]; }
-    GEN_I(sphase, 14) GEN_U(sEv, 14 + nd) GEN_U(sC, 14 + 2 * nd) GEN_I(cmdPay, 14 + 3 * nd) GEN_I(rxOf, 14 + 4 * nd)
-    GEN_I(rxSec, 14 + 5 * nd) GEN_U(txSeq, 14 + 6 * nd)
-    GEN_U(sTick, 14 + 7 * nd) GEN_U(epochK, 14 + 7 * nd + ns) GEN_I(qn, 14 + 7 * nd + 2 * ns) GEN_I(mac, 14 + 7 * nd + 3 * ns)
-    GEN_I(wDone, 14 + 7 * nd + 4 * ns) GEN_I(wPend, 14 + 7 * nd + 5 * ns) GEN_U(sW, 14 + 7 * nd + 6 * ns)
-    GEN_U(rxS, 14 + 7 * nd + 7 * ns) GEN_U(nDeliv, 14 + 7 * nd + 8 * ns) GEN_U(nRecv, 14 + 7 * nd + 9 * ns)
-    GEN_I(epochC, 14 + 7 * nd + 10 * ns) GEN_U(ticks, 14 + 7 * nd + 11 * ns)
-    GEN_U(sJam, 14 + 7 * nd + 12 * ns) GEN_I(jamStage, 14 + 7 * nd + 12 * ns + nj) GEN_I(jamPending, 14 + 7 * nd + 12 * ns + 2 * nj)
-    GW_HD int32_t &ring(int k, int slot) const { return i[(long long)(14 + 7 * nd + 12 * ns + 3 * nj + k * kQueueCap + slot) * stride]; }
+    GEN_I(sphase, 18) GEN_U(sEv, 18 + nd) GEN_U(sC, 18 + 2 * nd) GEN_I(cmdPay, 18 + 3 * nd) GEN_I(rxOf, 18 + 4 * nd)
+    GEN_I(rxSec, 18 + 5 * nd) GEN_U(txSeq, 18 + 6 * nd)
+    GEN_U(sTick, 18 + 7 * nd) GEN_U(epochK, 18 + 7 * nd + ns) GEN_I(qn, 18 + 7 * nd + 2 * ns) GEN_I(mac, 18 + 7 * nd + 3 * ns)
+    GEN_I(wDone, 18 + 7 * nd + 4 * ns) GEN_I(wPend, 18 + 7 * nd + 5 * ns) GEN_U(sW, 18 + 7 * nd + 6 * ns)
+    GEN_U(rxS, 18 + 7 * nd + 7 * ns) GEN_U(nDeliv, 18 + 7 * nd + 8 * ns) GEN_U(nRecv, 18 + 7 * nd + 9 * ns)
+    GEN_I(epochC, 18 + 7 * nd + 10 * ns) GEN_U(ticks, 18 + 7 * nd + 11 * ns)
+    GEN_U(sJam, 18 + 7 * nd + 12 * ns) GEN_I(jamStage, 18 + 7 * nd + 12 * ns + nj) GEN_I(jamPending, 18 + 7 * nd + 12 * ns + 2 * nj)
+    GW_HD int32_t &ring(int k, int slot) const { return i[(long long)(18 + 7 * nd + 12 * ns + 3 * nj + k * kQueueCap + slot) * stride]; }
 #undef GEN_F
 #undef GEN_I
 #undef GEN_U
@@ -108,7 +116,7 @@ struct GenView {
     GW_HD double &posw(int d, int c) const { return pos[(long long)(2 * d + c) * srxStride]; }
 };
 
-static_assert(GenView::kScalars == 14, "scalar block of the int32 state");
+static_assert(GenView::kScalars == 18, "scalar block of the int32 state");
 
 GW_HD void gen_rec(GenView &v, int kind, double t, int dev, double x0, double x1, double x2, double x3)
 {
@@ -140,7 +148,7 @@ GW_HD void gen_power_table(int nd, const double *pos, const double *power, doubl
 GW_HD void gen_init(GenView &v, const GenBand &B)
 {
     const int ns = v.ns, nj = v.nj, nd = v.nd;
-    v.now() = 0.0; v.tRrm() = 0.0; v.annSlots() = 0.0;
+    v.now() = 0.0; v.tRrm() = 0.0; v.annSlots() = 0.0; v.tTickMin() = 0.0;
     for (int w = 0; w < GenView::kScalars; ++w) v.sc(w) = 0;
     for (int p = 0; p < nd; ++p) {
         v.P(p) = B.thermal; v.tEv(p) = 0; v.tStop(p) = 0; v.tC(p) = 0; v.ber(p) = 0; v.err(p) = 0; v.tReset(p) = 0;
@@ -212,6 +220,29 @@ GW_HD void gen_ticks(GenView &v, const GenBand &B, int k, uint32_t c)
     v.ticks(k) += c;
 }
 
+GW_HD int gen_ctz(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+
+// state changes that the summary masks follow
+GW_HD void gen_set_sphase(GenView &v, int d, int ph)
+{
+    v.sphase(d) = ph;
+    const int bit = 1 << d;
+    if (ph >= S_SLOT) v.sc(GenView::I_phyMask) |= bit; else v.sc(GenView::I_phyMask) &= ~bit;
+}
+GW_HD void gen_set_mac(GenView &v, int k, int m)
+{
+    v.mac(k) = m;
+    const int bit = 1 << k;
+    if (m == MAC_WAIT_COND) v.sc(GenView::I_condMask) |= bit; else v.sc(GenView::I_condMask) &= ~bit;
+}
+
 // Silent ticks of sender k strictly before (tEnd, qEnd): the tick times are accumulated with the reference's fp64
 // additions, one per tick (counter_traffic.py:61); see gw_core.cuh::silent_ticks
 GW_HD void gen_silent_ticks(GenView &v, const GenBand &B, int k, double tEnd, uint32_t qEnd)
@@ -231,13 +262,6 @@ GW_HD void gen_silent_ticks(GenView &v, const GenBand &B, int k, double tEnd, ui
     v.sTick(k) = v.seq() - 1u;
 }
 
-// does sender k's tick go through the transition function?  (a MAC that waits for a packet wakes up; the last tick
-// of a burst ends the process)
-GW_HD bool gen_tick_wakes(const GenView &v, const GenBand &B, int k)
-{
-    return B.maxTicks[k] != 0 || v.mac(k) == MAC_WAIT_COND;
-}
-
 // earliest (time, creation number) among the timed slots; silent ticks in front of it are applied on the way
 GW_HD Event gen_next_event(GenView &v, const GenBand &B)
 {
@@ -252,20 +276,32 @@ GW_HD Event gen_next_event(GenView &v, const GenBand &B)
             e.t = t_; e.seq = q_; e.kind = (K); e.idx = (I);                            \
         }                                                                               \
     } while (0)
+    (void)nd;
     for (int j = 0; j < nj; ++j) GEN_CONSIDER(v.tJam(j), v.sJam(j), EV_JAM, j);
-    for (int d = 0; d < nd; ++d)
-        if (v.sphase(d) >= S_SLOT) GEN_CONSIDER(v.tEv(d), v.sEv(d), EV_PHY, d);
+    for (uint32_t m = (uint32_t)v.sc(GenView::I_phyMask); m; m &= m - 1u) {
+        const int d = gen_ctz(m);
+        GEN_CONSIDER(v.tEv(d), v.sEv(d), EV_PHY, d);
+    }
+    const uint32_t wMask = (uint32_t)v.sc(GenView::I_wMask), condMask = (uint32_t)v.sc(GenView::I_condMask);
     for (int k = 0; k < ns; ++k) {
-        if (v.wPend(k)) GEN_CONSIDER(v.stopW(k), v.sW(k), EV_W, k);
+        if ((wMask >> k) & 1u) GEN_CONSIDER(v.stopW(k), v.sW(k), EV_W, k);
         if (B.recv[k]) GEN_CONSIDER(v.rxT(k), v.rxS(k), EV_RXTO, k);
-        if (gen_tick_wakes(v, B, k) && v.tTick(k) < (double)INFINITY) GEN_CONSIDER(v.tTick(k), v.sTick(k), EV_TICK, k);
+        if ((B.maxTicks[k] != 0 || ((condMask >> k) & 1u)) && v.tTick(k) < (double)INFINITY) GEN_CONSIDER(v.tTick(k), v.sTick(k), EV_TICK, k);
     }
     if (v.sc(GenView::I_rrmPend)) GEN_CONSIDER(v.tRrm(), (uint32_t)v.sc(GenView::I_sRrm), EV_RRM, 0);
 #undef GEN_CONSIDER
     if (e.kind == EV_NONE) return e;
-    // ticks of different senders touch only their own sender's queue, so the senders are advanced one after the other
-    for (int k = 0; k < ns; ++k)
-        if (!gen_tick_wakes(v, B, k)) gen_silent_ticks(v, B, k, e.t, e.seq);
+    // Silent ticks in front of the event.  Ticks of different senders touch only their own sender's queue, so the
+    // senders are advanced one after the other.  tTickMin is a lower bound of all next tick times (tick times only
+    // grow): an event strictly before it has no tick in front of it, and the senders are not visited at all.
+    if (!(e.t < v.tTickMin())) {
+        double lo = INFINITY;
+        for (int k = 0; k < ns; ++k) {
+            if (!(B.maxTicks[k] != 0 || ((condMask >> k) & 1u))) gen_silent_ticks(v, B, k, e.t, e.seq);
+            lo = fmin(lo, v.tTick(k));
+        }
+        v.tTickMin() = lo;
+    }
     return e;
 }
 
@@ -318,8 +354,8 @@ GW_HD void gen_count(GenView &v, const Params &P, const GenBand &B, int p)
 GW_HD bool gen_power_change(GenView &v, const Params &P, const GenBand &B, int p, double delta, bool completingOwn)
 {
     v.P(p) += delta;
+    if (!(((uint32_t)v.sc(GenView::I_rxMask) >> p) & 1u) || delta == 0.0) return false;
     const int e = v.rxOf(p);
-    if (e < 0 || delta == 0.0) return false;
     gen_count(v, P, B, p);
     const bool completed = v.now() >= v.tStop(e);
     if (completed) return false;
@@ -339,6 +375,7 @@ GW_HD void gen_update_bers(GenView &v, const Params &P, uint32_t berMask)
 GW_HD void gen_rx_clear(GenView &v, int p)
 {
     v.rxOf(p) = -1; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = v.now();
+    v.sc(GenView::I_rxMask) &= ~(1 << p);
     if (v.mode != MODE_R) v.segT0(p) = v.now();
 }
 
@@ -354,12 +391,12 @@ GW_HD void gen_begin_slot_wait(GenView &v, int d)
     // self._transmitting = True; yield SimMan.nextTimeSlot(TIME_SLOT_LENGTH)  (simple_stack.py:202-204, simtools.py:53)
     v.tEv(d) = v.now() + (kSlot - fmod_slot(v.now()));
     v.sEv(d) = v.seq()++;
-    v.sphase(d) = S_SLOT;
+    gen_set_sphase(v, d, S_SLOT);
 }
 
 GW_HD void gen_phy_send_init(GenView &v, int d)
 {
-    if (v.rxOf(d) >= 0) v.sphase(d) = S_WAITRX;                     // yield self._nReceivingFinished.event
+    if (((uint32_t)v.sc(GenView::I_rxMask) >> d) & 1u) gen_set_sphase(v, d, S_WAITRX);  // yield self._nReceivingFinished.event
     else gen_begin_slot_wait(v, d);
 }
 
@@ -369,9 +406,9 @@ GW_HD void gen_mac_try_send(GenView &v, const Params &P, const GenBand &B, int k
     const int size = gen_head_size(v, B, k);
     const double timeLeft = v.stopW(k) - v.now();
     const double txTime = airtime_of(P, kMacHdr + kNetHdr + size);
-    if (!(timeLeft > txTime)) { v.mac(k) = MAC_IDLE; return; }      // yield timeoutEvent
+    if (!(timeLeft > txTime)) { gen_set_mac(v, k, MAC_IDLE); return; }     // yield timeoutEvent
     v.qn(k) -= 1;
-    v.mac(k) = MAC_WAIT_TX;
+    gen_set_mac(v, k, MAC_WAIT_TX);
     v.cmdPay(k) = kNetHdr + size;
     gen_phy_send_init(v, k);
 }
@@ -379,8 +416,8 @@ GW_HD void gen_mac_try_send(GenView &v, const Params &P, const GenBand &B, int k
 // loop head of the window loop (simple_stack.py:408-416)
 GW_HD void gen_mac_loop_head(GenView &v, const Params &P, const GenBand &B, int k)
 {
-    if (v.wDone(k)) { v.mac(k) = MAC_NONE; return; }
-    if (v.qn(k) == 0) { v.mac(k) = MAC_WAIT_COND; return; }
+    if (v.wDone(k)) { gen_set_mac(v, k, MAC_NONE); return; }
+    if (v.qn(k) == 0) { gen_set_mac(v, k, MAC_WAIT_COND); return; }
     gen_mac_try_send(v, P, B, k);
 }
 
@@ -405,7 +442,7 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
         gen_ticks(v, B, k, 1u);
         v.tTick(k) = v.now() + B.interval[k];
         v.sTick(k) = v.seq()++;
-        if (v.mac(k) == MAC_WAIT_COND) gen_mac_try_send(v, P, B, k);   // _packetAddedEvent wakes the window loop
+        if ((v.sc(GenView::I_condMask) >> k) & 1) gen_mac_try_send(v, P, B, k);     // _packetAddedEvent wakes the window loop
         break;
     }
     case EV_JAM: {
@@ -437,7 +474,7 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
             const double tH = now + (headerStop > now ? headerStop - now : 0.0);       // timeoutUntil
             const double tC = now + (stop > now ? stop - now : 0.0);
             const uint32_t qH = v.seq()++, qC = v.seq()++;
-            v.sphase(d) = S_HDR; v.tEv(d) = tH; v.sEv(d) = qH; v.tC(d) = tC; v.sC(d) = qC; v.tStop(d) = stop;
+            gen_set_sphase(v, d, S_HDR); v.tEv(d) = tH; v.sEv(d) = qH; v.tC(d) = tC; v.sC(d) = qC; v.tStop(d) = stop;
             if (v.mode != MODE_R) v.txStart(d) = now;
             v.txSeq(d) += 1u;
             v.sc(GenView::I_nTx) += 1;
@@ -448,8 +485,11 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
                 if (gen_power_change(v, P, B, p, v.rp(p, d), false)) berMask |= 1u << p;
             }
             // receive processes in PHY construction order: idle, non-transmitting PHYs lock on (simple_stack.py:214-235)
-            for (int p = 0; p < nd; ++p) {
-                if (p == d || v.rxOf(p) >= 0 || v.sphase(p) >= S_SLOT) continue;
+            const uint32_t all = nd >= 32 ? 0xffffffffu : (1u << nd) - 1u;
+            const uint32_t lock = all & ~(uint32_t)v.sc(GenView::I_rxMask) & ~(uint32_t)v.sc(GenView::I_phyMask) & ~(1u << d);
+            v.sc(GenView::I_rxMask) |= (int)lock;
+            for (uint32_t m = lock; m; m &= m - 1u) {
+                const int p = gen_ctz(m);
                 v.rxOf(p) = d; v.rxSec(p) = 0; v.err(p) = 0.0; v.ber(p) = 0.0; v.tReset(p) = now;
                 if (v.mode != MODE_R) v.segT0(p) = now;
                 berMask |= 1u << p;
@@ -458,7 +498,8 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
             // eHeaderCompletes: receivers decide on the header (simple_stack.py:241-251)
             const double hdrBits = (gen_hdr_bytes(v, B, d) * 8) * P.bitsFactor;
             uint32_t wake = 0;
-            for (int p = 0; p < nd; ++p) {
+            for (uint32_t m = (uint32_t)v.sc(GenView::I_rxMask); m; m &= m - 1u) {
+                const int p = gen_ctz(m);
                 if (v.rxOf(p) != d || v.rxSec(p) != 0) continue;
                 gen_count(v, P, B, p);
                 if (gen_decide(v, P, p, 0, hdrBits)) {
@@ -470,22 +511,24 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
                     if (v.sphase(p) == S_WAITRX) wake |= 1u << p;
                 }
             }
-            v.sphase(d) = S_PAY; v.tEv(d) = v.tC(d); v.sEv(d) = v.sC(d);
+            gen_set_sphase(v, d, S_PAY); v.tEv(d) = v.tC(d); v.sEv(d) = v.sC(d);
             for (int p = 0; p < nd; ++p) if ((wake >> p) & 1u) gen_begin_slot_wait(v, p);   // _nReceivingFinished.event
         } else {
             // eCompletes, callbacks in registration order:
             // 1. the sender's macInHandler resumes: _transmitting = False (simple_stack.py:210)
             const double payBits = (v.cmdPay(d) * 8) * P.bitsFactor;
-            v.sphase(d) = S_IDLE;
+            gen_set_sphase(v, d, S_IDLE);
             // 2. _onCompletingTransmission of every other PHY (simple_stack.py:146-157)
             for (int p = 0; p < nd; ++p) {
                 if (p == d) continue;
-                if (gen_power_change(v, P, B, p, -v.rp(p, d), v.rxOf(p) == d)) berMask |= 1u << p;
+                const bool own = (((uint32_t)v.sc(GenView::I_rxMask) >> p) & 1u) && v.rxOf(p) == d;
+                if (gen_power_change(v, P, B, p, -v.rp(p, d), own)) berMask |= 1u << p;
             }
             // 3. receivers that passed the header count again (appendix B #4), decide on the payload and deliver
             int window = -1;
             uint32_t wake = 0, received = 0;
-            for (int p = 0; p < nd; ++p) {
+            for (uint32_t m = (uint32_t)v.sc(GenView::I_rxMask); m; m &= m - 1u) {
+                const int p = gen_ctz(m);
                 if (v.rxOf(p) != d || v.rxSec(p) != 1) continue;
                 gen_count(v, P, B, p);
                 if (gen_decide(v, P, p, 1, payBits)) {
@@ -520,7 +563,7 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
                 const double timeTotal = v.annSlots() * kSlot;
                 v.stopW(window) = v.now() + timeTotal;
                 v.sW(window) = v.seq()++;
-                v.wPend(window) = 1;
+                v.wPend(window) = 1; v.sc(GenView::I_wMask) |= 1 << window;
                 v.wDone(window) = 0;
                 gen_mac_loop_head(v, P, B, window);
             }
@@ -557,9 +600,9 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
     case EV_W: {
         // window timeoutEvent processed (simple_stack.py:406-420)
         const int k = ev.idx;
-        v.wPend(k) = 0;
+        v.wPend(k) = 0; v.sc(GenView::I_wMask) &= ~(1 << k);
         if (v.mac(k) == MAC_WAIT_TX) v.wDone(k) = 1;
-        else v.mac(k) = MAC_NONE;
+        else gen_set_mac(v, k, MAC_NONE);
         break;
     }
     case EV_RRM:
@@ -679,9 +722,9 @@ GW_HD uint32_t gen_count_set(const GenView &v, const Event &ev)
     if (ev.kind != EV_PHY) return 0;
     const int d = ev.idx, ph = v.sphase(d);
     uint32_t set = 0;
-    for (int p = 0; p < v.nd; ++p) {
+    for (uint32_t m = (uint32_t)v.sc(GenView::I_rxMask); m; m &= m - 1u) {
+        const int p = gen_ctz(m);
         const int rx = v.rxOf(p);
-        if (rx < 0) continue;
         if (ph == S_HDR) {
             if (rx == d && v.rxSec(p) == 0) set |= 1u << p;
         } else {
