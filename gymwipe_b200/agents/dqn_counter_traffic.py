@@ -180,7 +180,7 @@ class DQNLearner:
             N.check(N.lib().gw_policy_boltzmann(
                 self._flat_weights().data_ptr(), self.nb_actions, self.nb_durations, obs.data_ptr(), n,
                 float(self.obs_center), float(self.tau), float(self.clip[0]), float(self.clip[1]),
-                int(self.seed) & (2 ** 64 - 1), self._draws, int(getattr(getattr(self.env, "_cfg", None), "env_id_offset", 0)),
+                int(self.seed) & (2 ** 64 - 1), self._draws, int(getattr(getattr(self.env, "_cfg", None), "env_id_offset", getattr(self.env, "env_id_offset", 0))),
                 flat.data_ptr(), dev.data_ptr(), dur.data_ptr(), probs.data_ptr() if want_probs else None,
                 torch.cuda.current_stream(obs.device).cuda_stream))
         shape = getattr(self.env, "_shape", (n,))
@@ -190,7 +190,7 @@ class DQNLearner:
         return (flat, action, probs) if want_probs else (flat, action)
 
     def _fused_ok(self):
-        return (self.device.type == "cuda" and self.nb_actions in (8, 20, 40)
+        return (self.device.type == "cuda" and 1 <= self.nb_actions <= 160
                 and [tuple(p.shape) for p in self.model.parameters()] ==
                 [(16, 1), (16,), (16, 16), (16,), (16, 16), (16,), (self.nb_actions, 16), (self.nb_actions,)])
 

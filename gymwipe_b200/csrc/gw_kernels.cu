@@ -1806,7 +1806,6 @@ __global__ void philox_kernel(const uint32_t *ctr, const uint32_t *key, uint32_t
 // the batch size or the sharding.  weights: float32, the order of torch's model.parameters() -- W1[16][1], b1[16],
 // W2[16][16], b2[16], W3[16][16], b3[16], W4[A][16], b4[A].
 constexpr int POLICY_HIDDEN = 16;
-constexpr int POLICY_MAX_ACTIONS = 64;
 
 template <int A>
 __global__ void __launch_bounds__(128)
@@ -1873,6 +1872,70 @@ policy_kernel(const float *weights, const long long *obs, long long n, float obs
 #pragma unroll
         for (int j = 0; j < A; ++j) probs[i * A + j] = e[j] / sum;
     }
+}
+
+// The same policy for action counts the unrolled kernels are not instantiated for (bands of 3..8 senders: 60..160
+// actions): run-time A, the q-values are evaluated twice (normalisation, then the inverse CDF) instead of being kept
+// in registers -- same arithmetic per value, same draw.
+constexpr int POLICY_MAX_ACTIONS_N = 160;
+
+__global__ void __launch_bounds__(128)
+policy_kernel_n(const float *weights, int A, const long long *obs, long long n, float obs_center, double tau, double clip_lo,
+                double clip_hi, unsigned long long seed, unsigned long long counter, long long env_offset, int n_durations,
+                long long *flat, int *device, int *duration, double *probs)
+{
+    constexpr int H = POLICY_HIDDEN;
+    __shared__ float w[H + H + H * H + H + H * H + H + POLICY_MAX_ACTIONS_N * H + POLICY_MAX_ACTIONS_N];
+    const int NW = H + H + H * H + H + H * H + H + A * H + A;
+    for (int t = threadIdx.x; t < NW; t += blockDim.x) w[t] = weights[t];
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *W1 = w, *b1 = W1 + H, *W2 = b1 + H, *b2 = W2 + H * H, *W3 = b2 + H, *b3 = W3 + H * H, *W4 = b3 + H,
+                *b4 = W4 + A * H;
+    const float x = (float)obs[i] - obs_center;
+    float h1[H], h2[H], h3[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) h1[j] = fmaxf(__fmaf_rn(W1[j], x, b1[j]), 0.f);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float a = b2[j];
+#pragma unroll
+        for (int k = 0; k < H; ++k) a = __fmaf_rn(W2[j * H + k], h1[k], a);
+        h2[j] = fmaxf(a, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float a = b3[j];
+#pragma unroll
+        for (int k = 0; k < H; ++k) a = __fmaf_rn(W3[j * H + k], h2[k], a);
+        h3[j] = fmaxf(a, 0.f);
+    }
+    auto weight_of = [&](int j) {
+        float q = b4[j];
+#pragma unroll
+        for (int k = 0; k < H; ++k) q = __fmaf_rn(W4[j * H + k], h3[k], q);
+        return exp(fmin(fmax((double)q / tau, clip_lo), clip_hi));
+    };
+    double sum = 0.0;
+    for (int j = 0; j < A; ++j) sum += weight_of(j);
+    uint32_t r[4];
+    const unsigned long long env = (unsigned long long)(env_offset + i);
+    philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), (uint32_t)counter, (uint32_t)(counter >> 32),
+                  (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const double u = ((double)r[0] * 4294967296.0 + (double)r[1] + 0.5) * (1.0 / 18446744073709551616.0);
+    const double target = u * sum;
+    double acc = 0.0;
+    int a = A - 1;
+    bool found = false;
+    for (int j = 0; j < A; ++j) {
+        const double e = weight_of(j);
+        acc += e;
+        if (!found && acc > target) { a = j; found = true; }
+        if (probs) probs[i * A + j] = e / sum;
+    }
+    if (flat) flat[i] = a;
+    if (device) { device[i] = a / n_durations; duration[i] = a % n_durations; }
 }
 
 __global__ void stats_copy_kernel(double *stats, double *out, int clear)
@@ -3154,7 +3217,10 @@ int gw_policy_boltzmann(const float *weights, int32_t n_actions, int32_t n_durat
     if (n_actions == 40) CALL_POLICY(40);               // 2 devices x 20 durations (envs/core.py:39-42)
     else if (n_actions == 20) CALL_POLICY(20);
     else if (n_actions == 8) CALL_POLICY(8);
-    else return fail(GW_E_INVALID, "policy kernels are instantiated for 8, 20 and 40 actions, not %d", n_actions);
+    else if (n_actions >= 1 && n_actions <= POLICY_MAX_ACTIONS_N)
+        policy_kernel_n<<<grid, 128, 0, s>>>(weights, n_actions, (const long long *)obs, n, obs_center, tau, clip_lo, clip_hi, seed, counter,
+                                             env_id_offset, n_durations, (long long *)flat_action, device, duration, probs);
+    else return fail(GW_E_INVALID, "the policy kernels take 1..%d actions, not %d", POLICY_MAX_ACTIONS_N, n_actions);
 #undef CALL_POLICY
     CUDA_TRY(cudaGetLastError());
     return GW_OK;

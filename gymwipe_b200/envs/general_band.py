@@ -135,6 +135,8 @@ class GeneralBandEnv(BaseEnv):
         self._obs = torch.full((n,), self.COUNTER_BOUND, dtype=torch.int64, device=self.device)
         self._reward = torch.zeros(n, dtype=torch.float64, device=self.device)
         self._done = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        self._shape_t = (n,)                # result shape of a batched step (the learner's allocation-free loop)
+        self.env_id_offset = int(env_id_offset)
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -154,9 +156,10 @@ class GeneralBandEnv(BaseEnv):
     def reset(self):
         """``counter_traffic.py:135-144``: sender counters and the interpreter are reset; time, queues and PHY
         state stay.  Returns the observation(s)."""
+        obs = self._obs if self._scalar_api else torch.empty(self.num_envs, dtype=torch.int64, device=self.device)
         with torch.cuda.device(self.device):
-            N.check(self._lib.gw_genband_reset(self._handle, self._obs.data_ptr(), self._stream()))
-        return int(self._obs[0]) if self._scalar_api else self._obs
+            N.check(self._lib.gw_genband_reset(self._handle, obs.data_ptr(), self._stream()))
+        return int(obs[0]) if self._scalar_api else obs
 
     def _actions(self, action):
         dev, dur = action["device"], action["duration"]
@@ -166,18 +169,28 @@ class GeneralBandEnv(BaseEnv):
         dur = torch.as_tensor(dur, dtype=torch.int32, device=self.device).reshape(self.num_envs).contiguous()
         return dev, dur
 
-    def step(self, action):
+    def step(self, action, out=None):
         """``counter_traffic.py:146-158`` for every env: ``action = {"device": int32 [num_envs], "duration": int32
-        [num_envs]}`` (CUDA tensors, or Python ints for ``num_envs == 1``) -> ``(obs, reward, done, info)``."""
+        [num_envs]}`` (CUDA tensors, or Python ints for ``num_envs == 1``) -> ``(obs, reward, done, info)``.
+        ``out``: optional ``(int64, float64, bool)`` tensors of shape ``[num_envs]`` to write the results into (an
+        allocation-free loop, as ``CounterTrafficEnv.step``); otherwise fresh tensors are returned."""
         dev, dur = self._actions(action)
+        if out is not None:
+            obs, reward, done = out
+        elif self._scalar_api:
+            obs, reward, done = self._obs, self._reward, self._done
+        else:
+            obs = torch.empty(self.num_envs, dtype=torch.int64, device=self.device)
+            reward = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+            done = torch.empty(self.num_envs, dtype=torch.bool, device=self.device)
         with torch.cuda.device(self.device):
-            N.check(self._lib.gw_genband_step(self._handle, dev.data_ptr(), dur.data_ptr(), self._obs.data_ptr(),
-                                              self._reward.data_ptr(), self._done.data_ptr(), self._stream()))
+            N.check(self._lib.gw_genband_step(self._handle, dev.data_ptr(), dur.data_ptr(), obs.data_ptr(),
+                                              reward.data_ptr(), done.data_ptr(), self._stream()))
         if self.strict:
             self.check()
-        if self._scalar_api:
-            return int(self._obs[0]), float(self._reward[0]), bool(self._done[0]), {}
-        return self._obs, self._reward, self._done.to(torch.bool), {}
+        if self._scalar_api and out is None:
+            return int(obs[0]), float(reward[0]), bool(done[0]), {}
+        return obs, reward, done if done.dtype == torch.bool else done.to(torch.bool), {}
 
     def step_traced(self, action, cap=8192):
         """:meth:`step` plus the event trace per env (tuples as ``CounterTrafficEnv.step_traced``)."""

@@ -478,7 +478,8 @@ int gw_count_bit_errors(const uint32_t *mask_words, int32_t words_per_row,
  * (W1[16][1], b1[16], W2[16][16], b2[16], W3[16][16], b3[16], W4[n_actions][16], b4[n_actions]); `obs`: device
  * int64 [n].  Outputs (device, each may be NULL): flat_action int64 [n]; device / duration int32 [n]
  * (flat // n_durations, flat % n_durations: CounterTrafficProcessor.process_action, :25-33 -- directly usable
- * as gw_step's action arrays); probs float64 [n][n_actions] (tests).  n_actions in {8, 20, 40}. */
+ * as gw_step's action arrays); probs float64 [n][n_actions] (tests).  n_actions <= 160 (8 senders x 20 durations:
+ * the action space of the largest band of the general engine; 8, 20 and 40 take unrolled kernels). */
 int gw_policy_boltzmann(const float *weights, int32_t n_actions, int32_t n_durations, const int64_t *obs, int64_t n,
                         float obs_center, double tau, double clip_lo, double clip_hi, uint64_t seed, uint64_t counter,
                         int64_t env_id_offset, int64_t *flat_action, int32_t *device, int32_t *duration, double *probs,

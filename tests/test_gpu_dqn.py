@@ -71,3 +71,35 @@ def test_learner_fit_uses_the_fused_policy():
     env.check()
     assert dqn._draws == 12 and len(hist["loss"]) >= 9
     assert set(dqn.memory.obs[:dqn.memory.size].unique().tolist()) <= {-2.0, 0.0, 2.0}
+
+
+def test_learner_on_a_band_of_three_senders():
+    """The learner consumes the general band engine as well: 3 senders x 20 durations = 60 actions through the
+    run-time-A policy kernel (probabilities against the eager PyTorch path), a short fit on 512 envs."""
+    import numpy as np
+    import gymwipe_b200
+    from gymwipe_b200.agents import DQNLearner
+    from gymwipe_b200.envs import GeneralBandEnv
+    sc = {"assignment_duration_factor": 1000, "bands": [{"frequency": 2.4e9, "bandwidth": 22e6, "devices": [
+        {"role": "sender", "x": 2.0, "y": 0.0, "mult": 1, "payload": "counter", "interval": 0.001, "dest": 1},
+        {"role": "sender", "x": -1.0, "y": 1.7, "mult": 3, "payload": "counter", "interval": 0.001, "dest": 2},
+        {"role": "sender", "x": -1.0, "y": -1.7, "mult": 2, "payload": "counter", "interval": 0.001, "dest": 0},
+        {"role": "rrm", "x": 0.0, "y": 0.0}]}]}
+    env = gymwipe_b200.make('CounterTraffic-v0', num_envs=512, scenario=sc, strict=False)
+    assert isinstance(env, GeneralBandEnv)
+    dqn = DQNLearner(env, nb_steps_warmup=1000, normalize_obs=True, tau=0.7)
+    assert dqn.nb_actions == 60 and dqn._fused_ok()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for p in dqn.model.parameters():
+        p.data.add_(0.3 * torch.randn(p.shape, generator=g, device="cuda"))
+    obs = 65536 + 2 * torch.randint(-1, 2, (2048,), generator=g, device="cuda")
+    flat, action, probs = dqn.select_action_fused(obs, want_probs=True)
+    with torch.no_grad():
+        want = torch.softmax(torch.clamp(dqn.model(dqn._features(obs)).double() / dqn.tau, dqn.clip[0], dqn.clip[1]), dim=1)
+    assert torch.allclose(probs, want, rtol=1e-5, atol=1e-9)
+    assert torch.equal(action["device"].long(), flat // 20) and torch.equal(action["duration"].long(), flat % 20)
+    assert int(flat.min()) >= 0 and int(flat.max()) < 60 and int(action["device"].max()) == 2
+    hist = dqn.fit(24)
+    env.check()
+    assert len(hist["mean_reward"]) == 24 and all(l == l for l in hist["loss"])
+    assert int(env.transmissions().sum()) > 24 * 512 and int(env.delivered().sum()) > 0
