@@ -185,6 +185,7 @@ _SIGNATURES = {
     "gw_genband_create": (C.c_int, [C.POINTER(GenBandConfig), C.c_int, _VP, _VP, C.POINTER(_VP)]),
     "gw_genband_destroy": (None, [_VP]),
     "gw_genband_set_positions": (C.c_int, [_VP, _VP, _VP]),
+    "gw_genband_set_movers": (C.c_int, [_VP, _VP, _VP, C.c_int32, C.c_double, _VP]),
     "gw_genband_reset": (C.c_int, [_VP, _VP, _VP]),
     "gw_genband_step": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "gw_genband_step_traced": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int32, _VP]),

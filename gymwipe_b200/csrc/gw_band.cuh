@@ -33,6 +33,7 @@
 namespace gw {
 
 constexpr int kGenMaxSend = 8, kGenMaxJam = 16, kGenMaxDev = kGenMaxSend + 1 + kGenMaxJam;
+constexpr int EV_MOVE = 7;              // a mobility process wakes up (next to gw_core.cuh's EV_* kinds)
 
 // band configuration, common to all band-sims of a handle; device order: senders, RRM, PHY-only senders
 struct GenBand {
@@ -42,6 +43,10 @@ struct GenBand {
     unsigned long long seed;            // mode M: Philox seed
     long long envOffset;                // mode M: global id of env 0 (sharding keeps results invariant)
     double thermal;
+    double frequency;
+    double power[kGenMaxDev];           // transmission power (dBm) per device: 0 for MACs and the RRM
+    int maxMoves;                       // mobility processes: jumps per device in the offset tape (0: none)
+    double moveInterval;
     int mult[kGenMaxSend];
     int payloadRule[kGenMaxSend];       // -1: byteSize = counter
     int dest[kGenMaxSend];              // device index of the sender its packets are addressed to
@@ -65,6 +70,10 @@ struct GenView {
     long long srxStride;
     double *att;                        // attenuation (dB), same layout, and current positions [nd][2] at pos[(2 * d + c) * srxStride]:
     double *pos;                        //   held for per-env geometries only (devices that move between steps), else null
+    // mobility processes (tests/test_benchmark.py:73-85), per-env geometries only; mvT == null: none
+    double *mvT, *mvDelay;              // next wake-up, first delay; entry d at [d * srxStride]
+    int32_t *mvI;                       // creation number, stage (0 first delay, 1 moving, 2 off), jumps done: [3][nd]
+    const double *offsets;              // this env's tape [nd][maxMoves][2] (accumulating jumps)
     int ns, nj, nd;
     long long env;                      // global env id (mode M: key of the error masks)
     int mode;                           // MODE_R / MODE_M_PHILOX: a compile-time constant in the kernels (no mode-M code or stores in mode R)
@@ -114,6 +123,11 @@ struct GenView {
     GW_HD double &rpw(int p, int d) const { return srx[(long long)(p * nd + d) * srxStride]; }
     GW_HD double &attw(int p, int d) const { return att[(long long)(p * nd + d) * srxStride]; }
     GW_HD double &posw(int d, int c) const { return pos[(long long)(2 * d + c) * srxStride]; }
+    GW_HD double &tMove(int d) const { return mvT[(long long)d * srxStride]; }
+    GW_HD double &moveDelay(int d) const { return mvDelay[(long long)d * srxStride]; }
+    GW_HD uint32_t &sMove(int d) const { return ((uint32_t *)mvI)[(long long)d * srxStride]; }
+    GW_HD int32_t &moveStage(int d) const { return mvI[(long long)(nd + d) * srxStride]; }
+    GW_HD int32_t &moveK(int d) const { return mvI[(long long)(2 * nd + d) * srxStride]; }
 };
 
 static_assert(GenView::kScalars == 18, "scalar block of the int32 state");
@@ -289,6 +303,9 @@ GW_HD Event gen_next_event(GenView &v, const GenBand &B)
         if ((B.maxTicks[k] != 0 || ((condMask >> k) & 1u)) && v.tTick(k) < (double)INFINITY) GEN_CONSIDER(v.tTick(k), v.sTick(k), EV_TICK, k);
     }
     if (v.sc(GenView::I_rrmPend)) GEN_CONSIDER(v.tRrm(), (uint32_t)v.sc(GenView::I_sRrm), EV_RRM, 0);
+    if (v.mvT != nullptr)
+        for (int d = 0; d < v.nd; ++d)
+            if (v.moveStage(d) < 2) GEN_CONSIDER(v.tMove(d), v.sMove(d), EV_MOVE, d);
 #undef GEN_CONSIDER
     if (e.kind == EV_NONE) return e;
     // Silent ticks in front of the event.  Ticks of different senders touch only their own sender's queue, so the
@@ -419,6 +436,57 @@ GW_HD void gen_mac_loop_head(GenView &v, const Params &P, const GenBand &B, int 
     if (v.wDone(k)) { gen_set_mac(v, k, MAC_NONE); return; }
     if (v.qn(k) == 0) { gen_set_mac(v, k, MAC_WAIT_COND); return; }
     gen_mac_try_send(v, P, B, k);
+}
+
+// Position.set of device m (devices/core.py:75-84) and everything it triggers -- the run-time-count form of
+// gw_core.cuh::move_devices, see the comments there: models beyond STANDBY_THRESHOLD or with coinciding devices keep
+// their value (physical.py:383-386, attenuation_models.py:31-33), only a NEW value triggers (physical.py:354-362), a
+// pair neither of whose devices has transmitted yet has no model (its table entry follows the positions), and
+// transmissions that are on the air go through SimplePhy._onAttenuationChange (simple_stack.py:119-128): the PHY's
+// power sum changes, a running reception counts the segment that ends and re-evaluates its bit error rate.
+GW_HD void gen_move_device(GenView &v, const Params &P, const GenBand &B, int m, double x, double y)
+{
+    const int nd = v.nd;
+    if (x == v.posw(m, 0) && y == v.posw(m, 1)) return;                     // Position.set: no trigger
+    v.posw(m, 0) = x; v.posw(m, 1) = y;
+    for (int j = 0; j < nd; ++j) {
+        if (j == m) continue;
+        const double dx = x - v.posw(j, 0), dy = y - v.posw(j, 1);
+        const double dist = sqrt(dx * dx + dy * dy);                        // devices/core.py:88-95
+        if (v.txSeq(m) == 0u && v.txSeq(j) == 0u) {
+            const double fresh = (dx == 0.0 && dy == 0.0) ? 0.0 : 20 * log10(dist) + 20 * log10(B.frequency) - 147.55;
+            v.attw(m, j) = fresh; v.attw(j, m) = fresh;
+            v.rpw(j, m) = rx_power_mw(B.power[m], fresh);
+            v.rpw(m, j) = rx_power_mw(B.power[j], fresh);
+            continue;
+        }
+        if (!(dist < 3000.0)) continue;                                     // STANDBY_THRESHOLD
+        if (dx == 0.0 && dy == 0.0) continue;                               // _update returns early
+        const double att = 20 * log10(dist) + 20 * log10(B.frequency) - 147.55;
+        if (att == v.attw(m, j)) continue;
+        v.attw(m, j) = att; v.attw(j, m) = att;
+        for (int dir = 0; dir < 2; ++dir) {                                 // (receiver j, sender m), (receiver m, sender j)
+            const int p = dir == 0 ? j : m, e = dir == 0 ? m : j;
+            const double rp = rx_power_mw(B.power[e], att);
+            const int ph = v.sphase(e);
+            const double delta = rp - v.rp(p, e);
+            v.rpw(p, e) = rp;
+            if (ph == S_HDR || ph == S_PAY) {
+                if (gen_power_change(v, P, B, p, delta, false)) gen_update_ber(v, P, p);
+            }
+        }
+    }
+}
+
+// Mobility processes (the mover of tests/test_benchmark.py:73-85, one per device with moveDelays[d] >= 0): started
+// now, in device order -- each an Initialize event that the engine sees as a wake-up at the current time.
+GW_HD void gen_start_movers(GenView &v, const double *moveDelays)
+{
+    for (int d = 0; d < v.nd; ++d) {
+        const bool on = moveDelays[d] >= 0.0;
+        v.tMove(d) = v.now(); v.moveDelay(d) = on ? moveDelays[d] : 0.0;
+        v.sMove(d) = on ? v.seq()++ : 0u; v.moveStage(d) = on ? 0 : 2; v.moveK(d) = 0;
+    }
 }
 
 GW_HD int gen_hdr_bytes(const GenView &v, const GenBand &B, int d) { return d > v.ns ? B.jamHdr[d - v.ns - 1] : kMacHdr; }
@@ -605,6 +673,22 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
         else gen_set_mac(v, k, MAC_NONE);
         break;
     }
+    case EV_MOVE: {
+        const int d = ev.idx;
+        if (v.moveStage(d) == 0) {                                  // yield SimMan.timeout(first delay)
+            v.moveStage(d) = 1; v.tMove(d) = v.now() + v.moveDelay(d); v.sMove(d) = v.seq()++;
+        } else if (v.moveK(d) < B.maxMoves) {
+            // d.position.set(initialPos.x + xOffset, initialPos.y + yOffset) with `initialPos` the moving Position
+            // object itself: the offsets accumulate; then yield SimMan.timeout(MOVE_INTERVAL)
+            const double *o = v.offsets + ((long long)d * B.maxMoves + v.moveK(d)) * 2;
+            v.moveK(d) += 1;
+            gen_move_device(v, P, B, d, v.posw(d, 0) + o[0], v.posw(d, 1) + o[1]);
+            v.tMove(d) = v.now() + B.moveInterval; v.sMove(d) = v.seq()++;
+        } else {
+            v.moveStage(d) = 2;                                     // tape exhausted: the process is not modelled further
+        }
+        break;
+    }
     case EV_RRM:
         // assignMessage.setProcessed() (simple_stack.py:561): the step ends here
         v.sc(GenView::I_rrmPend) = 0;
@@ -616,48 +700,11 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
     return berMask;
 }
 
-// Devices moving between steps (Position.set, devices/core.py:75-84): `want` [nd][2] are the requested positions, the
-// devices are moved one after the other by ascending index.  The run-time-count form of gw_core.cuh::move_devices --
-// see the comments there: models beyond STANDBY_THRESHOLD or with coinciding devices keep their value
-// (physical.py:383-386, attenuation_models.py:31-33), only a NEW value triggers (physical.py:354-362), a pair
-// neither of whose devices has transmitted yet has no model (its table entry follows the positions), and
-// transmissions that are on the air go through SimplePhy._onAttenuationChange (simple_stack.py:119-128): the PHY's
-// power sum changes, a running reception counts the segment that ends and re-evaluates its bit error rate.
-GW_HD void gen_move_devices(GenView &v, const Params &P, const GenBand &B, const double *power, double frequency, const double *want)
+// Devices moving between steps: `want` [nd][2] are the requested positions, the devices are moved one after the
+// other by ascending index like successive Position.set calls (gen_move_device)
+GW_HD void gen_move_devices(GenView &v, const Params &P, const GenBand &B, const double *want)
 {
-    const int nd = v.nd;
-    for (int m = 0; m < nd; ++m) {
-        const double x = want[2 * m], y = want[2 * m + 1];
-        if (x == v.posw(m, 0) && y == v.posw(m, 1)) continue;               // Position.set: no trigger
-        v.posw(m, 0) = x; v.posw(m, 1) = y;
-        for (int j = 0; j < nd; ++j) {
-            if (j == m) continue;
-            const double dx = x - v.posw(j, 0), dy = y - v.posw(j, 1);
-            const double dist = sqrt(dx * dx + dy * dy);                    // devices/core.py:88-95
-            if (v.txSeq(m) == 0u && v.txSeq(j) == 0u) {
-                const double fresh = (dx == 0.0 && dy == 0.0) ? 0.0 : 20 * log10(dist) + 20 * log10(frequency) - 147.55;
-                v.attw(m, j) = fresh; v.attw(j, m) = fresh;
-                v.rpw(j, m) = rx_power_mw(power[m], fresh);
-                v.rpw(m, j) = rx_power_mw(power[j], fresh);
-                continue;
-            }
-            if (!(dist < 3000.0)) continue;                                 // STANDBY_THRESHOLD
-            if (dx == 0.0 && dy == 0.0) continue;                           // _update returns early
-            const double att = 20 * log10(dist) + 20 * log10(frequency) - 147.55;
-            if (att == v.attw(m, j)) continue;
-            v.attw(m, j) = att; v.attw(j, m) = att;
-            for (int dir = 0; dir < 2; ++dir) {                             // (receiver j, sender m), (receiver m, sender j)
-                const int p = dir == 0 ? j : m, e = dir == 0 ? m : j;
-                const double rp = rx_power_mw(power[e], att);
-                const int ph = v.sphase(e);
-                const double delta = rp - v.rp(p, e);
-                v.rpw(p, e) = rp;
-                if (ph == S_HDR || ph == S_PAY) {
-                    if (gen_power_change(v, P, B, p, delta, false)) gen_update_ber(v, P, p);
-                }
-            }
-        }
-    }
+    for (int m = 0; m < v.nd; ++m) gen_move_device(v, P, B, m, want[2 * m], want[2 * m + 1]);
 }
 
 // SimpleRrmDevice.assignFrequencyBand + SimpleRrmMac._sendAnnouncement start (devices.py:178-203,

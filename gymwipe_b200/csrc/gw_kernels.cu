@@ -2072,6 +2072,9 @@ struct GenArgs {
     double *srx;                // [nd * nd][n_envs] or [nd * nd]
     double *att;                // [nd * nd][n_envs] attenuation (dB) and
     double *pos;                // [nd * 2][n_envs] current positions: per-env geometries only (devices may move)
+    double *mvT;                // [2][nd][n_envs] mobility processes: next wake-up, first delay (gw_genband_set_movers)
+    int32_t *mvI;               // [3][nd][n_envs] creation number, stage, jumps done
+    const double *offsets;      // [n_envs][nd][max_moves][2]
     long long n_envs;
     int per_env;
     double *trace;              // [n_envs][cap][8] or NULL
@@ -2087,6 +2090,8 @@ __device__ __forceinline__ GenView gen_view_of(const GenArgs &A, const GenBand &
     v.f = A.f64 + i; v.i = A.i32 + i; v.stride = A.n_envs;
     v.srx = A.per_env ? A.srx + i : A.srx; v.srxStride = A.per_env ? A.n_envs : 1;
     v.att = A.per_env ? A.att + i : nullptr; v.pos = A.per_env ? A.pos + i : nullptr;
+    v.mvT = A.mvT ? A.mvT + i : nullptr; v.mvDelay = A.mvT ? A.mvT + (long long)B.nd * A.n_envs + i : nullptr;
+    v.mvI = A.mvT ? A.mvI + i : nullptr; v.offsets = A.mvT ? A.offsets + i * B.nd * B.maxMoves * 2 : nullptr;
     v.ns = B.ns; v.nj = B.nj; v.nd = B.nd; v.env = B.envOffset + i;
     v.trace = nullptr; v.ntrace = 0; v.traceCap = 0;
     return v;
@@ -2104,13 +2109,21 @@ __global__ void genband_init_kernel(GenArgs A, GenBand B, const double *pos, con
 }
 
 // gw_genband_set_positions: every env moves its devices one after the other (gw_band.cuh::gen_move_devices)
-__global__ void genband_move_kernel(GenArgs A, Params P, GenBand B, const double *power, double frequency, const double *want)
+__global__ void genband_movers_kernel(GenArgs A, GenBand B, const double *move_delays)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n_envs) return;
+    GenView v = gen_view_of(A, B, i);
+    gen_start_movers(v, move_delays + i * B.nd);
+}
+
+__global__ void genband_move_kernel(GenArgs A, Params P, GenBand B, const double *want)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n_envs) return;
     GenView v = gen_view_of(A, B, i);
     if (v.sc(GenView::I_fault)) return;
-    gen_move_devices(v, P, B, power, frequency, want + i * B.nd * 2);
+    gen_move_devices(v, P, B, want + i * B.nd * 2);
     const int fault = v.sc(GenView::I_fault);
     if (fault) { if (atomicCAS(A.errflag, 0, GW_E_SIMFAULT) == 0) { A.errflag[1] = (int)i; A.errflag[2] = fault; } }
 }
@@ -3377,6 +3390,7 @@ int gw_genband_create(const gw_genband_config *cfg, int device, const double *po
     B.ns = ns; B.nj = nj; B.nd = ns + 1 + nj; B.maxDuration = cfg->max_assign_duration;
     B.mode = cfg->mode == GW_MODE_MASK_PHILOX ? MODE_M_PHILOX : MODE_R; B.seed = cfg->seed; B.envOffset = cfg->env_id_offset;
     B.thermal = 1.38e-23 * (20.0 + 273.15) * cfg->bandwidth_hz * 1000;        // simple_stack.py:57, physical.py:61-78
+    B.frequency = cfg->frequency_hz; B.maxMoves = 0; B.moveInterval = 0.0;
     double power[GW_GENBAND_MAX_DEVICES];
     for (int d = 0; d < B.nd; ++d) power[d] = 0.0;                              // MACs and the RRM send at 0 dBm
     for (int k = 0; k < ns; ++k) {
@@ -3389,6 +3403,7 @@ int gw_genband_create(const gw_genband_config *cfg, int device, const double *po
         B.jamHdr[j] = cfg->phy_header_bytes[j]; B.jamPay[j] = cfg->phy_payload_bytes[j];
         power[ns + 1 + j] = cfg->phy_power_dbm[j];
     }
+    for (int d = 0; d < B.nd; ++d) B.power[d] = power[d];
     GenArgs &A = h->A;
     A.n_envs = cfg->n_envs; A.per_env = cfg->per_env_positions ? 1 : 0;
     const size_t n = (size_t)cfg->n_envs;
@@ -3436,6 +3451,8 @@ void gw_genband_destroy(gw_genband_handle *h)
     if (h->A.srx) cudaFree(h->A.srx);
     if (h->A.att) cudaFree(h->A.att);
     if (h->A.pos) cudaFree(h->A.pos);
+    if (h->A.mvT) cudaFree(h->A.mvT);
+    if (h->A.mvI) cudaFree(h->A.mvI);
     if (h->dpower) cudaFree(h->dpower);
     if (h->errflag) cudaFree(h->errflag);
     delete h;
@@ -3446,7 +3463,26 @@ int gw_genband_set_positions(gw_genband_handle *h, const double *positions, void
     if (!h || !positions) return fail(GW_E_INVALID, "NULL argument");
     if (!h->A.per_env) return fail(GW_E_INVALID, "handle was created with per_env_positions = 0");
     CUDA_TRY(cudaSetDevice(h->device));
-    genband_move_kernel<<<grid_for(h->A.n_envs, 64), 64, 0, (cudaStream_t)stream>>>(h->A, h->P, h->B, h->dpower, h->cfg.frequency_hz, positions);
+    genband_move_kernel<<<grid_for(h->A.n_envs, 64), 64, 0, (cudaStream_t)stream>>>(h->A, h->P, h->B, positions);
+    CUDA_TRY(cudaGetLastError());
+    return GW_OK;
+}
+
+int gw_genband_set_movers(gw_genband_handle *h, const double *move_delays, const double *offsets, int32_t max_moves,
+                          double move_interval, void *stream)
+{
+    if (!h || !move_delays || !offsets) return fail(GW_E_INVALID, "NULL argument");
+    if (!h->A.per_env) return fail(GW_E_INVALID, "handle was created with per_env_positions = 0");
+    if (max_moves < 1 || !(move_interval > 0)) return fail(GW_E_INVALID, "max_moves must be >= 1 and move_interval > 0");
+    if (h->A.mvT) return fail(GW_E_INVALID, "the mobility processes of this handle are running already");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->A.n_envs;
+    cudaError_t e = cudaMalloc((void **)&h->A.mvT, sizeof(double) * 2 * h->B.nd * n);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&h->A.mvI, sizeof(int32_t) * 3 * h->B.nd * n);
+    if (e != cudaSuccess) return fail(GW_E_CUDA, "allocation failed: %s", cudaGetErrorString(e));
+    h->A.offsets = offsets;
+    h->B.maxMoves = max_moves; h->B.moveInterval = move_interval;
+    genband_movers_kernel<<<grid_for(h->A.n_envs, 64), 64, 0, (cudaStream_t)stream>>>(h->A, h->B, move_delays);
     CUDA_TRY(cudaGetLastError());
     return GW_OK;
 }

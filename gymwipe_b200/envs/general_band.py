@@ -224,6 +224,21 @@ class GeneralBandEnv(BaseEnv):
         if self.strict:
             self.check()
 
+    def set_movers(self, move_delays, offsets, move_interval=1e-3):
+        """Mobility processes that move devices DURING the steps (the mover of ``tests/test_benchmark.py:73-85``):
+        ``move_delays`` float64 ``[num_envs, n_devices]`` (first delay; negative: no process for that device),
+        ``offsets`` float64 ``[num_envs, n_devices, K, 2]`` (the jumps, which accumulate; a process ends with its tape),
+        one jump every ``move_interval``.  Needs per-env geometries; once per env object."""
+        md = torch.as_tensor(move_delays, dtype=torch.float64, device=self.device).contiguous()
+        self._offsets = torch.as_tensor(offsets, dtype=torch.float64, device=self.device).contiguous()
+        if tuple(md.shape) != (self.num_envs, self.n_devices) or self._offsets.dim() != 4 or \
+                tuple(self._offsets.shape[:2]) != (self.num_envs, self.n_devices) or self._offsets.shape[3] != 2:
+            raise ValueError("move_delays [num_envs, n_devices], offsets [num_envs, n_devices, K, 2]")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.gw_genband_set_movers(self._handle, md.data_ptr(), self._offsets.data_ptr(),
+                                                    int(self._offsets.shape[2]), float(move_interval), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()        # `md` is consumed on the stream
+
     def check(self):
         """Synchronises and raises if an action was outside the action space or an env hit a condition under
         which the reference raises."""

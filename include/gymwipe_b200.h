@@ -426,6 +426,14 @@ void gw_genband_destroy(gw_genband_handle *h);
  * transmitted yet follow the positions, and transmissions that are on the air go through
  * SimplePhy._onAttenuationChange (simple_stack.py:119-128). */
 int gw_genband_set_positions(gw_genband_handle *h, const double *positions, void *stream);
+/* Mobility processes that move devices DURING the steps (the mover of tests/test_benchmark.py:73-85), for handles with
+ * per_env_positions, started at the envs' current time in device order: move_delays device float64
+ * [n_envs][n_devices] (the first delay; < 0: the device has no process), offsets [n_envs][n_devices][max_moves][2]
+ * (the jumps, which accumulate: the reference's `initialPos` is the moving Position object; a process ends with its
+ * tape), one jump every move_interval.  `offsets` must stay alive as long as the handle; `move_delays` is consumed
+ * on `stream`.  Once per handle. */
+int gw_genband_set_movers(gw_genband_handle *h, const double *move_delays, const double *offsets, int32_t max_moves,
+                          double move_interval, void *stream);
 /* CounterTrafficEnv.reset (counter_traffic.py:135-144) of every env; obs (device int64 [n_envs]) may be NULL. */
 int gw_genband_reset(gw_genband_handle *h, int64_t *obs, void *stream);
 /* CounterTrafficEnv.step (counter_traffic.py:146-158).  Device arrays [n_envs]: device in [0, n_senders),

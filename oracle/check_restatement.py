@@ -125,14 +125,17 @@ def run_case_m(scenario, tape, label, seed=77, env_id=12345, moves=None):
     return bad
 
 
-def run_case(scenario, tape, label, do_reset=True, use_default_class=False, moves=None, mobile=False):
+def run_case(scenario, tape, label, do_reset=True, use_default_class=False, moves=None, mobile=False, movers=None):
     tr = H.Tracer()
     if use_default_class:
         env = H.make_default_env(tr)
     else:
-        env = H.ScenarioEnv(scenario, tr)
+        env = H.ScenarioEnv(scenario, tr, movers=movers)
     ref = H.run_tape(env, tape, tr, do_reset=do_reset, moves=moves)
-    ora = O.run_tape(O.Oracle(scenario, trace=True), tape, do_reset=do_reset, moves=moves)
+    ora_env = O.Oracle(scenario, trace=True)
+    for i in sorted(movers or {}):
+        ora_env.add_mover(0, i, movers[i][0], movers[i][1], movers[i][2])
+    ora = O.run_tape(ora_env, tape, do_reset=do_reset, moves=moves)
     bad = compare_mobile(ref, ora, label) if mobile else compare(ref, ora, label)
     ev_ref = sum(s["events"] for s in ref["steps"])
     ev_ora = sum(s["events"] for s in ora["steps"])
@@ -215,6 +218,16 @@ def nsender_moves(rs, sc, steps, start=1):
             lst.append((0, d, float(x), float(y)))
         moves[t] = lst
     return moves
+
+
+def nsender_movers(rs, nd, jumps=1500, interval=1e-3):
+    """{device: (first delay, interval, offsets)}: most devices get a mobility process (jumps of up to +-0.2 m per axis
+    every millisecond, as the mobile_device_grid fixture draws them)."""
+    out = {}
+    for d in range(nd):
+        if rs.rand() < 0.75:
+            out[d] = (float(rs.uniform(0, interval)), float(interval), rs.uniform(-.2, .2, size=(jumps, 2)))
+    return out
 
 
 def child(args):
@@ -309,6 +322,14 @@ def child(args):
         if args.case == "nsendersmobility":
             return run_case(sc, tape, label, moves=moves, mobile=True)
         return run_case_m(sc, tape, "mode M, " + label, seed=args.seed + 82, moves=moves)
+    if args.case == "nsendersmovers":
+        # mobility processes DURING the steps (the mover of tests/test_benchmark.py:73-85) on a band with MACs and an RRM
+        ns, nj = int(rs.randint(3, 7)), int(rs.randint(0, 4))
+        sc = random_scenario_n(rs, ns, nj, spread=args.spread, receive=bool(args.seed % 2))
+        tape = H.random_actions(args.steps, seed=args.seed + 14000, devices=ns)
+        movers = nsender_movers(rs, ns + 1 + nj)
+        return run_case(sc, tape, "%d senders + RRM + %d PHY-only senders with mobility processes, seed %d" % (ns, nj, args.seed),
+                        mobile=True, movers=movers)
     if args.case == "masknsenders":
         ns, nj = int(rs.randint(3, 7)), int(rs.randint(0, 4))
         sc = random_scenario_n(rs, ns, nj, spread=args.spread, receive=bool(args.seed % 2))
@@ -354,7 +375,7 @@ def main():
                  ("maskdefault", sd, 120), ("maskjammer", sd, 120), ("masklong", sd, 20),
                  ("mobilityjam", sd, 120), ("maskmobilityjam", sd, 80), ("mobilityquirks", sd, 100),
                  ("nsenders", sd, 120), ("masknsenders", sd, 40), ("nsendersmobility", sd, 80),
-                 ("masknsendersmobility", sd, 30)]
+                 ("masknsendersmobility", sd, 30), ("nsendersmovers", sd, 60)]
     failed = 0
     for case, sd, steps in plan:
         rc = subprocess.call([sys.executable, os.path.abspath(__file__), "--case", case,

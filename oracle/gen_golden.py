@@ -48,6 +48,7 @@ CASES = {
     "nsenders_3s_16p_seed33": ("nsenders:3:16:0:0", 33, 40),
     "modeM_nsenders_4s_2p_seed34": ("masknsenders:4:2:1:0", 34, 40),
     "nsenders_mobility_5s_3p_seed35": ("nsendersmove:5:3:1:0", 35, 60),
+    "nsenders_movers_4s_2p_seed36": ("nsendersmovers:4:2:1:0", 36, 40),
 }
 
 MASK_SEED, MASK_ENV = 20261018, 4242
@@ -101,7 +102,7 @@ def make_case(kind, seed, steps):
         sc["bands"][0]["devices"][0]["receive"] = True
         sc["bands"][0]["devices"][1]["receive"] = True
         sc["bands"][0]["devices"][1]["max_ticks"] = 45
-    elif kind.startswith("nsenders:") or kind.startswith("masknsenders:") or kind.startswith("nsendersmove:"):
+    elif kind.startswith("nsenders:") or kind.startswith("masknsenders:") or kind.startswith("nsendersmove:") or kind.startswith("nsendersmovers:"):
         # ns MAC senders + RRM + nj PHY-only senders, with / without receive mode and finite bursts
         _, ns, nj, rcv, bursts = kind.split(":")
         sc = CR.random_scenario_n(rs, int(ns), int(nj), spread=2.5, receive=bool(int(rcv)), bursts=bool(int(bursts)))
@@ -117,12 +118,15 @@ def child(name):
     sc, tape, do_reset, use_default = make_case(kind, seed, steps)
     # (nsender_moves also makes the PHY-only senders busy: before the env is constructed)
     pre_moves = CR.nsender_moves(np.random.RandomState(seed + 3), sc, steps) if kind.startswith("nsendersmove:") else None
+    movers = None
+    if kind.startswith("nsendersmovers:"):
+        movers = CR.nsender_movers(np.random.RandomState(seed + 4), len(sc["bands"][0]["devices"]), jumps=700)
     tr = H.Tracer()
     mode_m = kind.startswith("mask")
     if mode_m:
         H.install_masked_phy(lambda band, sender, seq, receiver, k0, k1, ber:
                              H.philox_mask_errors(MASK_SEED, MASK_ENV, band, sender, seq, receiver, k0, k1, ber), tr)
-    env = H.make_default_env(tr) if use_default else H.ScenarioEnv(sc, tr)
+    env = H.make_default_env(tr) if use_default else H.ScenarioEnv(sc, tr, movers=movers)
     moves = None
     if kind == "mobility":
         # every 3rd step one device jumps to a new position (between steps: nothing is on the air)
@@ -165,6 +169,8 @@ def child(name):
            + (" + oracle.ref_harness.MaskedPhy (SimplePhy subclass)" if mode_m else ""),
            "scenario": sc, "reset_obs": trace["reset_obs"],
            "moves": {str(k): v for k, v in moves.items()} if moves else None,
+           "movers": {str(i): {"first_delay": m[0], "interval": m[1], "offsets": np.asarray(m[2]).tolist()}
+                      for i, m in movers.items()} if movers else None,
            "steps": [{"action": s["action"], "obs": s["obs"], "reward": s["reward"], "done": s["done"],
                       "now": s["now"], "events": s["events"],
                       "records": [list(r) for r in s["records"]]} for s in trace["steps"]]}

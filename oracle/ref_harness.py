@@ -274,7 +274,10 @@ class ScenarioEnv:
     COUNTER_BOUND = 65536
     COUNTER_BYTE_LENGTH = 2
 
-    def __init__(self, scenario, tracer=None):
+    def __init__(self, scenario, tracer=None, movers=None):
+        """``movers``: optional ``{device index: (first delay, interval, offsets [k][2])}`` for band 0 -- mobility
+        processes after ``tests/test_benchmark.py:73-85`` (the draws come from the tape), started after the whole
+        scenario has been constructed, in device order."""
         setup_paths()
         from gymwipe.envs.counter_traffic import CounterTrafficEnv
         from gymwipe.networking.attenuation_models import FsplAttenuation
@@ -416,6 +419,16 @@ class ScenarioEnv:
             for i, d in enumerate(bspec["devices"]):
                 if d["role"] == "sender" and d.get("receive"):
                     self.bands[b]["devices"][i].receiving = True
+
+        def mover(dev, first, interval, offsets):       # tests/test_benchmark.py:75-82 with the draws from the tape
+            yield SimMan.timeout(first)
+            initialPos = dev.position
+            for (xOffset, yOffset) in offsets:
+                dev.position.set(initialPos.x + float(xOffset), initialPos.y + float(yOffset))
+                yield SimMan.timeout(interval)
+        for i in sorted(movers or {}):
+            first, interval, offsets = movers[i]
+            SimMan.process(mover(self.bands[0]["devices"][i], float(first), float(interval), offsets))
 
     # gym-like API --------------------------------------------------------
     def reset(self):

@@ -321,7 +321,8 @@ int hs_gen_run(int ns, int nj, int factor, double frequency, double bandwidth, c
                int64_t env_offset, int64_t nenv, int nsteps,
                int reset_at, const int32_t *dev_tape, const int32_t *dur_tape, int64_t *obs, double *reward, uint8_t *done,
                double *now_out, int64_t *counts, double *trace, int trace_cap, int32_t *trace_counts,
-               const HsMove *moves, int nmoves)
+               const HsMove *moves, int nmoves, const double *move_delays, const double *offsets, int max_moves,
+               double move_interval)
 {
     Params P;
     std::memset(&P, 0, sizeof P);
@@ -334,6 +335,8 @@ int hs_gen_run(int ns, int nj, int factor, double frequency, double bandwidth, c
     std::memset(&B, 0, sizeof B);
     B.ns = ns; B.nj = nj; B.nd = ns + 1 + nj; B.maxDuration = 20;
     B.mode = mode; B.seed = seed; B.envOffset = env_offset;
+    B.frequency = frequency; B.maxMoves = max_moves; B.moveInterval = move_interval;
+    for (int d = 0; d < ns + 1 + nj; ++d) B.power[d] = power[d];
     B.thermal = 1.38e-23 * (20.0 + 273.15) * bandwidth * 1000;
     for (int k = 0; k < ns; ++k) {
         B.mult[k] = cfg_i[0 * 8 + k]; B.payloadRule[k] = cfg_i[1 * 8 + k]; B.dest[k] = cfg_i[2 * 8 + k];
@@ -344,22 +347,26 @@ int hs_gen_run(int ns, int nj, int factor, double frequency, double bandwidth, c
         B.jamInterval[j] = cfg_d[8 + j]; B.jamDelay[j] = cfg_d[24 + j];
     }
     const int nd = B.nd, fw = gen_f64_words(ns, nj), iw = gen_i32_words(ns, nj);
-    const bool tables = per_env_pos || nmoves > 0;      // devices that move need the band-sim's own tables
+    const bool tables = per_env_pos || nmoves > 0 || max_moves > 0;     // devices that move need the band-sim's own tables
     std::vector<double> f((size_t)fw * nenv), srx((size_t)nd * nd * (tables ? nenv : 1));
     std::vector<double> att(tables ? (size_t)nd * nd * nenv : 1), cur(tables ? (size_t)2 * nd * nenv : 1);
     std::vector<int32_t> iv((size_t)iw * nenv);
+    std::vector<double> mvT(max_moves > 0 ? (size_t)2 * nd * nenv : 1);
+    std::vector<int32_t> mvI(max_moves > 0 ? (size_t)3 * nd * nenv : 1);
     auto view = [&](int64_t e) {
         GenView v;
         v.f = f.data() + e; v.i = iv.data() + e; v.stride = nenv;
         v.srx = tables ? srx.data() + e : srx.data(); v.srxStride = tables ? nenv : 1;
         v.att = tables ? att.data() + e : nullptr; v.pos = tables ? cur.data() + e : nullptr;
+        v.mvT = max_moves > 0 ? mvT.data() + e : nullptr; v.mvDelay = max_moves > 0 ? mvT.data() + (size_t)nd * nenv + e : nullptr;
+        v.mvI = max_moves > 0 ? mvI.data() + e : nullptr; v.offsets = offsets;         // (every env the same tape here)
         v.ns = ns; v.nj = nj; v.nd = nd; v.env = env_offset + e; v.mode = mode; v.trace = nullptr; v.ntrace = 0; v.traceCap = 0;
         return v;
     };
     if (tables) for (int64_t e = 0; e < nenv; ++e)
         gen_power_table(nd, pos + (per_env_pos ? (size_t)e * nd * 2 : 0), power, frequency, srx.data() + e, nenv, att.data() + e, cur.data() + e);
     else gen_power_table(nd, pos, power, frequency, srx.data(), 1);
-    for (int64_t e = 0; e < nenv; ++e) { GenView v = view(e); gen_init(v, B); }
+    for (int64_t e = 0; e < nenv; ++e) { GenView v = view(e); gen_init(v, B); if (max_moves > 0) gen_start_movers(v, move_delays); }
     int used = 0, fault = 0;
     for (int t = 0; t < nsteps; ++t) {
         for (int64_t e = 0; e < nenv; ++e) {
@@ -374,7 +381,7 @@ int hs_gen_run(int ns, int nj, int factor, double frequency, double bandwidth, c
                     if (!any) { for (int q = 0; q < 2 * nd; ++q) want[q] = cur[(size_t)q * nenv + e]; any = true; }
                     want[2 * moves[k].dev] = moves[k].x; want[2 * moves[k].dev + 1] = moves[k].y;
                 }
-                if (any) gen_move_devices(v, P, B, power, frequency, want.data());
+                if (any) gen_move_devices(v, P, B, want.data());
             }
             long long o; double r; unsigned char d;
             gen_step(v, P, B, dev_tape[(size_t)t * nenv + e], dur_tape[(size_t)t * nenv + e], o, r, d);

@@ -532,3 +532,112 @@ def test_cuda_general_band_mobility_matches_reference_golden():
         want = [r for r in g["records"] if not (r[0] == "ber" and r[1] == (doc["steps"][t - 1]["now"] if t else 0.0))]
         got = [r for r in recs if not (r[0] == "ber" and r[1] == (doc["steps"][t - 1]["now"] if t else 0.0))]
         assert_mobile_step_records(got, want, "step %d" % t)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# mobility processes DURING the steps (gw_genband_set_movers; the mover of tests/test_benchmark.py:73-85)
+# ------------------------------------------------------------------------------------------------------------
+
+def _movers_from_golden(doc, nd):
+    K = max(len(m["offsets"]) for m in doc["movers"].values())
+    md = -np.ones(nd)
+    off = np.zeros((nd, K, 2))
+    for i, m in doc["movers"].items():
+        md[int(i)] = m["first_delay"]
+        off[int(i), :len(m["offsets"])] = np.array(m["offsets"])
+    return md, off, float(next(iter(doc["movers"].values()))["interval"])
+
+
+def _oracle_with_movers(sc, md, off, interval, mode=O.MODE_R, seed=0, env_id=0):
+    ora = O.Oracle(sc, trace=True, mode=mode)
+    if mode == O.MODE_M:
+        ora.use_philox_masks(seed, env_id)
+    for d in range(len(md)):
+        if md[d] >= 0:
+            ora.add_mover(0, d, float(md[d]), interval, off[d])
+    return ora
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_core_general_mobility_processes_vs_oracle(seed):
+    rs = np.random.RandomState(7500 + seed)
+    ns, nj = int(rs.randint(3, 7)), int(rs.randint(0, 5))
+    sc = random_scenario_n(rs, ns, nj, spread=2.5, receive=bool(seed % 2))
+    nd, T = ns + 1 + nj, 40
+    dev = rs.randint(0, ns, size=(T, 1)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, 1)).astype(np.int32)
+    md = rs.uniform(0, 1e-3, size=nd)
+    md[rs.rand(nd) < 0.3] = -1.0                        # some devices stay put
+    off = rs.uniform(-.2, .2, size=(nd, 600, 2))
+    m = O.MODE_M if seed >= 4 else O.MODE_R
+    ora = _oracle_with_movers(sc, md, off, 1e-3, mode=m, seed=55, env_id=7)
+    res = O.run_tape(ora, [{"device": int(dev[t, 0]), "duration": int(dur[t, 0])} for t in range(T)])
+    ntx, ndl = ora.counts()
+    h = HS.gen_run(sc, dev, dur, move_delays=md, offsets=off, mode=1 if m == O.MODE_M else 0, seed=55, env_offset=7)
+    _assert_host_equals(h, res["steps"], ntx, ndl, ora.received(), ns, "movers seed %d" % seed)
+
+
+def test_oracle_and_core_match_reference_golden_nsenders_movers():
+    """The reference's own trace of a band of 4 senders + RRM + 2 PHY-only senders whose devices run mobility processes
+    (a jump every millisecond, while transmissions are on the air)."""
+    from util import GOLDEN_NSENDERS_MOVERS, assert_mobile_step_records
+    doc = load_golden(GOLDEN_NSENDERS_MOVERS)
+    sc = doc["scenario"]
+    nd = len(sc["bands"][0]["devices"])
+    md, off, interval = _movers_from_golden(doc, nd)
+    dev, dur = _tapes(doc)
+    ora = _oracle_with_movers(sc, md, off, interval)
+    res = O.run_tape(ora, [s["action"] for s in doc["steps"]])
+    h = HS.gen_run(sc, dev, dur, move_delays=md, offsets=off, move_interval=interval)
+    assert h["rc"] == 0
+    for t, g in enumerate(doc["steps"]):
+        o = res["steps"][t]
+        assert (o["obs"], o["reward"], o["done"], o["now"]) == (g["obs"], g["reward"], g["done"], g["now"]), t
+        assert (h["obs"][t, 0], h["reward"][t, 0], bool(h["done"][t, 0]), h["now"][t, 0]) == (g["obs"], g["reward"], g["done"], g["now"]), t
+        assert_mobile_step_records(o["records"], g["records"], "oracle step %d" % t)
+        assert_mobile_step_records(h["records"][t], g["records"], "core step %d" % t)
+        assert_step_records(h["records"][t], o["records"], "core vs oracle step %d" % t)
+
+
+@pytest.mark.gpu
+def test_cuda_general_band_mobility_processes():
+    """GeneralBandEnv.set_movers: the reference golden through the traced kernel, and a batch of 96 envs (every env
+    its own tape) against the oracle -- step results, step end times, delivery counts."""
+    import torch
+    from util import GOLDEN_NSENDERS_MOVERS, assert_mobile_step_records
+    doc = load_golden(GOLDEN_NSENDERS_MOVERS)
+    sc = doc["scenario"]
+    nd = len(sc["bands"][0]["devices"])
+    ns = sum(1 for d in sc["bands"][0]["devices"] if d["role"] == "sender")
+    md, off, interval = _movers_from_golden(doc, nd)
+    pos0 = np.array([[d["x"], d["y"]] for d in sc["bands"][0]["devices"]])
+    env = _gpu_env(sc, 1, positions=torch.as_tensor(pos0[None]))
+    env.set_movers(torch.as_tensor(md[None]), torch.as_tensor(off[None]), interval)
+    assert env.reset() == doc["reset_obs"]
+    for t, g in enumerate(doc["steps"]):
+        obs, rew, done, recs = env.step_traced({"device": g["action"]["device"], "duration": g["action"]["duration"]})
+        assert (obs, rew, done, float(env.now[0])) == (g["obs"], g["reward"], g["done"], g["now"]), t
+        assert_mobile_step_records(recs, g["records"], "step %d" % t)
+    # a batch, every env its own delays / tapes / actions
+    rs = np.random.RandomState(7600)
+    nenv, T = 96, 24
+    mds = rs.uniform(0, 1e-3, size=(nenv, nd))
+    mds[rs.rand(nenv, nd) < 0.3] = -1.0
+    offs = rs.uniform(-.2, .2, size=(nenv, nd, 400, 2))
+    dev = rs.randint(0, ns, size=(T, nenv)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, nenv)).astype(np.int32)
+    batch = _gpu_env(sc, nenv, positions=torch.as_tensor(np.repeat(pos0[None], nenv, axis=0)))
+    batch.set_movers(torch.as_tensor(mds), torch.as_tensor(offs), 1e-3)
+    batch.reset()
+    got_obs, got_now = [], []
+    for t in range(T):
+        obs, rew, done, _ = batch.step({"device": torch.as_tensor(dev[t]).cuda(), "duration": torch.as_tensor(dur[t]).cuda()})
+        got_obs.append(obs.cpu().numpy()); got_now.append(batch.now.cpu().numpy())
+    batch.check()
+    deliv = batch.delivered().cpu().numpy()
+    for e in range(0, nenv, 7):
+        ora = _oracle_with_movers(sc, mds[e], offs[e], 1e-3)
+        res = O.run_tape(ora, [{"device": int(dev[t, e]), "duration": int(dur[t, e])} for t in range(T)])
+        for t, s in enumerate(res["steps"]):
+            assert got_obs[t][e] == s["obs"] and got_now[t][e] == s["now"], (e, t)
+        assert list(deliv[e]) == list(ora.counts()[1][:ns])

@@ -103,6 +103,7 @@ def random_tapes(rs, nsteps, nenv, nb):
 
 GOLDEN_NSENDERS = ["nsenders_5s_3p_seed31", "nsenders_8s_6p_seed32", "nsenders_3s_16p_seed33"]
 GOLDEN_NSENDERS_MOBILITY = "nsenders_mobility_5s_3p_seed35"
+GOLDEN_NSENDERS_MOVERS = "nsenders_movers_4s_2p_seed36"
 
 BER_RTOL = 1e-9          # north star: 1e-6 relative in fp64; observed ~1e-15 (libm / libdevice pow, log10 differ by <= 2 ulp)
 
