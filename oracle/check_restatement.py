@@ -68,12 +68,12 @@ def compare(ref, ora, label, ber_rtol=0.0):
     return bad
 
 
-def compare_mobile(ref, ora, label, err_rtol=2e-2, ber_rtol=1e-4):
+def compare_mobile(ref, ora, label, err_rtol=5e-2, ber_rtol=1e-4):
     """
     Comparison for devices that move while SEVERAL transmissions are on the air.  A moving device's attenuation models
     are notified in Python-set order in the reference (simtools.py:255: by object hash -- two runs of the reference
     itself differ), every notification charges the running reception with the errors since the last RESET (appendix
-    B #5) at the rate of that moment, so error sums (and the rates in between) depend on that order at the 1e-3 level,
+    B #5) at the rate of that moment, so error sums (and the rates in between) depend on that order (observed: up to 3e-2 between two runs of the reference),
     the final rate of an instant through the rounding of the power sum at the 1e-8 level (times the exponent of
     exp(-Eb/N0) for rates that are astronomically small: observed 6e-6 at rates of 1e-58).  Compared: step results,
     transmissions, deliveries exactly; decisions: time / device / section / bit count / verdict exactly, error sum
@@ -99,7 +99,10 @@ def compare_mobile(ref, ora, label, err_rtol=2e-2, ber_rtol=1e-4):
         if ok:
             for k in ga:
                 x, y = ga[k][-1], gb[k][-1]
-                ok = ok and len(ga[k]) == len(gb[k]) and abs(x - y) <= ber_rtol * max(abs(x), abs(y), 1e-30)
+                # (a rate of 0.49..0.5 is the S ~ N regime, where `sd <= nd` decides between exactly 0.5 and the formula
+                # on a noise power that is mostly rounding residue: order-dependent in the reference itself)
+                close = abs(x - y) <= ber_rtol * max(abs(x), abs(y), 1e-30) or (min(x, y) >= 0.45 and abs(x - y) <= 0.02)
+                ok = ok and len(ga[k]) == len(gb[k]) and close
         if not ok:
             bad += 1
             if bad == 1:
@@ -107,7 +110,7 @@ def compare_mobile(ref, ora, label, err_rtol=2e-2, ber_rtol=1e-4):
     return bad
 
 
-def run_case_m(scenario, tape, label, seed=77, env_id=12345, moves=None):
+def run_case_m(scenario, tape, label, seed=77, env_id=12345, moves=None, mobile=False):
     """mode M: reference + MaskedPhy subclass (numpy Philox) vs the restatement (C Philox)."""
     tr = H.Tracer()
     H.setup_paths()
@@ -118,7 +121,7 @@ def run_case_m(scenario, tape, label, seed=77, env_id=12345, moves=None):
     ora_env = O.Oracle(scenario, trace=True, mode=O.MODE_M)
     ora_env.use_philox_masks(seed, env_id)
     ora = O.run_tape(ora_env, tape, moves=moves)
-    bad = compare(ref, ora, label)
+    bad = compare_mobile(ref, ora, label) if mobile else compare(ref, ora, label)
     ndec = sum(1 for s in ref["steps"] for r in s["records"] if r[0] == "dec")
     nfail = sum(1 for s in ref["steps"] for r in s["records"] if r[0] == "dec" and not r[7])
     print("[%s] steps %d mismatching %d ; decisions %d (failed %d)" % (label, len(tape), bad, ndec, nfail))
@@ -321,7 +324,7 @@ def child(args):
         label = "%d senders + RRM + %d PHY-only senders moving between steps, seed %d" % (ns, nj, args.seed)
         if args.case == "nsendersmobility":
             return run_case(sc, tape, label, moves=moves, mobile=True)
-        return run_case_m(sc, tape, "mode M, " + label, seed=args.seed + 82, moves=moves)
+        return run_case_m(sc, tape, "mode M, " + label, seed=args.seed + 82, moves=moves, mobile=True)
     if args.case == "nsendersmovers":
         # mobility processes DURING the steps (the mover of tests/test_benchmark.py:73-85) on a band with MACs and an RRM
         ns, nj = int(rs.randint(3, 7)), int(rs.randint(0, 4))
