@@ -265,3 +265,71 @@ def test_debug_stamps_record_every_launch():
     s = st.cpu().numpy().astype(np.uint64)
     assert (s[:, 0] <= s[:, 1]).all() and (s[:, 1] < s[:, 2]).all()
     assert (s[1:, 1] >= s[:-1, 2]).all()                # a launch passes its grid dependency after the previous one ended
+
+
+def test_raw_ctypes_general_band_engine_matches_oracle():
+    """The general band engine through a bare ctypes.CDLL, as a C caller would drive it: a gw_genband_config struct
+    declared field by field from include/gymwipe_b200.h, gw_genband_create -> _reset -> _step x T -> _read -> _check
+    -> _destroy on a band of 3 senders + RRM + 1 PHY-only sender; results equal the oracle's."""
+    import gymwipe_b200
+    gymwipe_b200.build()
+    lib = C.CDLL(LIB)
+    lib.gw_last_error.restype = C.c_char_p
+
+    class gw_genband_config(C.Structure):
+        _fields_ = [("abi_version", C.c_int32), ("n_envs", C.c_int64), ("n_senders", C.c_int32), ("n_phy_senders", C.c_int32),
+                    ("assignment_duration_factor", C.c_int32), ("max_assign_duration", C.c_int32), ("per_env_positions", C.c_int32),
+                    ("mode", C.c_int32), ("seed", C.c_uint64), ("env_id_offset", C.c_int64),
+                    ("frequency_hz", C.c_double), ("bandwidth_hz", C.c_double),
+                    ("multiplicity", C.c_int32 * 8), ("payload_bytes", C.c_int32 * 8), ("destination", C.c_int32 * 8),
+                    ("max_ticks", C.c_int32 * 8), ("receive", C.c_int32 * 8), ("interval", C.c_double * 8),
+                    ("phy_interval", C.c_double * 16), ("phy_delay", C.c_double * 16), ("phy_power_dbm", C.c_double * 16),
+                    ("phy_header_bytes", C.c_int32 * 16), ("phy_payload_bytes", C.c_int32 * 16)]
+
+    sc = {"assignment_duration_factor": 1000, "bands": [{"frequency": 2.4e9, "bandwidth": 22e6, "devices": [
+        {"role": "sender", "x": 2.0, "y": 0.0, "mult": 1, "payload": "counter", "interval": 0.001, "dest": 1},
+        {"role": "sender", "x": -1.0, "y": 1.7, "mult": 3, "payload": "counter", "interval": 0.001, "dest": 2},
+        {"role": "sender", "x": -1.0, "y": -1.7, "mult": 2, "payload": 30, "interval": 0.001, "dest": 0},
+        {"role": "rrm", "x": 0.0, "y": 0.0},
+        {"role": "jammer", "x": 4.0, "y": 4.0, "interval": 0.012, "delay": 0.002, "power": 10.0, "hdr": 13, "payload": 50}]}]}
+    n, T = 48, 20
+    cfg = gw_genband_config()
+    cfg.abi_version = lib.gw_abi_version()
+    cfg.n_envs, cfg.n_senders, cfg.n_phy_senders = n, 3, 1
+    cfg.assignment_duration_factor, cfg.max_assign_duration, cfg.per_env_positions, cfg.mode = 1000, 20, 0, 0
+    cfg.frequency_hz, cfg.bandwidth_hz = 2.4e9, 22e6
+    for k, (m, p, d) in enumerate([(1, -1, 1), (3, -1, 2), (2, 30, 0)]):
+        cfg.multiplicity[k], cfg.payload_bytes[k], cfg.destination[k], cfg.interval[k] = m, p, d, 0.001
+    cfg.phy_interval[0], cfg.phy_delay[0], cfg.phy_power_dbm[0] = 0.012, 0.002, 10.0
+    cfg.phy_header_bytes[0], cfg.phy_payload_bytes[0] = 13, 50
+    pos = torch.tensor([[2.0, 0.0], [-1.0, 1.7], [-1.0, -1.7], [0.0, 0.0], [4.0, 4.0]], dtype=torch.float64, device="cuda")
+    h = C.c_void_p()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.gw_genband_create(C.byref(cfg), C.c_int(0), _vp(pos), stream, C.byref(h))
+    assert rc == 0, lib.gw_last_error()
+    rs = np.random.RandomState(12)
+    dev = rs.randint(0, 3, size=(T, n)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, n)).astype(np.int32)
+    ref = O.run_batch(sc, dev, dur)
+    d_dev, d_dur = torch.as_tensor(dev).cuda(), torch.as_tensor(dur).cuda()
+    obs = torch.empty(n, dtype=torch.int64, device="cuda")
+    rew = torch.empty(n, dtype=torch.float64, device="cuda")
+    done = torch.empty(n, dtype=torch.uint8, device="cuda")
+    assert lib.gw_genband_reset(h, _vp(obs), stream) == 0
+    assert (obs.cpu().numpy() == 65536).all()
+    now = torch.empty(n, dtype=torch.float64, device="cuda")
+    for t in range(T):
+        rc = lib.gw_genband_step(h, _vp(d_dev[t]), _vp(d_dur[t]), _vp(obs), _vp(rew), _vp(done), stream)
+        assert rc == 0, lib.gw_last_error()
+        assert lib.gw_genband_read(h, C.c_int(0), _vp(now), stream) == 0            # GW_GENBAND_FIELD_NOW
+        assert (obs.cpu().numpy() == ref["obs"][t, :, 0]).all() and (rew.cpu().numpy() == ref["reward"][t, :, 0]).all(), t
+        assert (now.cpu().numpy() == ref["now"][t]).all(), t
+    assert lib.gw_genband_check(h, stream) == 0
+    deliv = torch.empty((3, n), dtype=torch.float64, device="cuda")
+    assert lib.gw_genband_read(h, C.c_int(1), _vp(deliv), stream) == 0              # GW_GENBAND_FIELD_DELIVERED
+    assert (deliv.t().cpu().numpy() == ref["counts"][:, 0, 1:4]).all() and ref["counts"][:, 0, 1:4].sum() > 0
+    # an action outside the action space is reported by gw_genband_check and leaves that env untouched
+    bad = d_dev[0].clone(); bad[5] = 3
+    assert lib.gw_genband_step(h, _vp(bad), _vp(d_dur[0]), _vp(obs), _vp(rew), _vp(done), stream) == 0
+    assert lib.gw_genband_check(h, stream) == -4                                    # GW_E_ACTION
+    lib.gw_genband_destroy(h)
