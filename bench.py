@@ -396,6 +396,66 @@ def general_band(dev_t, rank=0, world=1, steps=24, n=65536, ns=8, nj=4, mode="re
     return out
 
 
+def large_batch(dev_t, rank=0, world=1, n=1048576, batches=8, steps=6):
+    """
+    The headline workload with 1,048,576 envs per env object / launch instead of 65,536 (the kernel's grid is capped at
+    one resident wave and strides over the batch, so a large launch has no partial wave and overlaps its own state
+    loads): a population of `batches` such batches, steady state (128 untimed steps), population steps over the
+    streams of EnvPopulation.step replayed from CUDA graphs.  Reported next to the headline, which stays on
+    BASELINE configs[1]'s 65,536-env batches.
+    """
+    import torch
+    import gymwipe_b200
+    from gymwipe_b200.envs import EnvPopulation
+    pop = EnvPopulation([gymwipe_b200.make('CounterTraffic-v0', num_envs=n, device=dev_t, env_id_offset=(rank * batches + b) * n,
+                                           strict=False) for b in range(batches)])
+    pop.reset()
+    g = torch.Generator(device=dev_t).manual_seed(77 + rank)
+    ROWS = 13
+    a_dev = torch.randint(0, 2, (ROWS, n), generator=g, device=dev_t, dtype=torch.int32)
+    a_dur = torch.randint(0, 20, (ROWS, n), generator=g, device=dev_t, dtype=torch.int32)
+    stream = torch.cuda.Stream(device=dev_t)
+    counter = [0]
+
+    def pop_step():
+        j = counter[0]
+        pop.step([{"device": a_dev[(j + b) % ROWS], "duration": a_dur[(j + b) % ROWS]} for b in range(batches)])
+        counter[0] = j + batches
+
+    with torch.cuda.stream(stream):
+        for _ in range(128):
+            pop_step()
+        graphs = []
+        for _ in range(steps):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=stream):
+                pop_step()
+            graphs.append(gr)
+        for gr in graphs:
+            gr.replay()                                  # graph upload is warm-up
+        torch.cuda.synchronize(dev_t)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(3):
+            for gr in graphs:
+                gr.replay()
+        e1.record(stream)
+        torch.cuda.synchronize(dev_t)
+    pop.check()
+    ms = e0.elapsed_time(e1) / (3 * steps)               # per population step
+    peak, _ = measured_peak()
+    us_launch = 1e3 * ms / batches
+    out = {"workload": "the headline workload with %d envs per launch: population of %d batches, steady state, %d population "
+                       "steps from CUDA graphs x 3" % (n, batches, steps),
+           "n_envs": n * batches, "envs_per_launch": n, "env_steps_per_s": n * batches / (ms * 1e-3), "ms_per_step": ms,
+           "us_per_launch": us_launch,
+           "roofline_frac": ALGO_BYTES_PER_ENV_STEP * n / (us_launch * 1e-6) / 1e9 / peak}
+    pop.close()
+    del pop, graphs
+    torch.cuda.empty_cache()
+    return out
+
+
 def grid_benchmark(dev_t, rank=0, world=1, n_envs=4096, n_devices=20):
     """
     The reference's own benchmark (tests/test_benchmark.py:52-91, `make benchmark`): a grid of 20 PHY-only
@@ -731,6 +791,7 @@ def own_arm(args, rank, world, local_rank):
         for name, fn in (("cfg3_long_packet_mode_m", lambda: cfg3_long_packet(dev_t, peak, rank, world)),
                          ("cfg4_multiband", lambda: cfg4_multiband(dev_t, rank, world)),
                          ("cfg5_pendulum", lambda: cfg5_pendulum(dev_t, rank, world)),
+                         ("large_batch_1m_envs", lambda: large_batch(dev_t, rank, world)),
                          ("general_band_8_senders", lambda: general_band(dev_t, rank, world)),
                          ("reference_benchmark_grid", lambda: grid_benchmark(dev_t, rank, world)),
                          ("mask_scan", lambda: mask_scan_roofline(dev_t, peak, "random") if world == 1 else None)):
