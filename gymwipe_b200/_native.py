@@ -75,7 +75,7 @@ GW_GENBAND_MAX_SENDERS, GW_GENBAND_MAX_PHY_SENDERS = 8, 16
 GW_GENBAND_MAX_DEVICES = GW_GENBAND_MAX_SENDERS + 1 + GW_GENBAND_MAX_PHY_SENDERS
 (GW_GENBAND_FIELD_NOW, GW_GENBAND_FIELD_DELIVERED, GW_GENBAND_FIELD_RECEIVED, GW_GENBAND_FIELD_TRANSMISSIONS,
  GW_GENBAND_FIELD_FAULT, GW_GENBAND_FIELD_RECEIVED_POWER, GW_GENBAND_FIELD_QUEUE_LENGTH, GW_GENBAND_FIELD_COUNTER,
- GW_GENBAND_FIELD_TIES) = range(9)
+ GW_GENBAND_FIELD_TIES, GW_GENBAND_FIELD_RECEIVED_VALUES) = range(10)
 
 
 class GenBandConfig(C.Structure):

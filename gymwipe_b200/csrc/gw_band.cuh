@@ -105,7 +105,8 @@ struct GenView {
                  I_rxMask,              // bit p: PHY p is receiving (rxOf >= 0)
                  I_wMask,               // bit k: sender k's window time-out is pending
                  I_condMask,            // bit k: sender k's MAC waits for a packet (MAC_WAIT_COND)
-                 I_pad, kScalars };
+                 I_rvMask,              // bit k: the interpreter's receivedValues[k] is set (payload.value = 2; 0 after reset)
+                 kScalars };
     GW_HD int32_t &sc(int w) const { return i[(long long)w * stride]; }
     GW_HD uint32_t &seq() const { return ((uint32_t *)i)[(long long)I_seq * stride]; }
     GEN_I(sphase, 18) GEN_U(sEv, 18 + nd) GEN_U(sC, 18 + 2 * nd) GEN_I(cmdPay, 18 + 3 * nd) GEN_I(rxOf, 18 + 4 * nd)
@@ -223,6 +224,7 @@ GW_HD void gen_reset(GenView &v, const GenBand &B)
         v.epochC(k) = 0;
     }
     v.sc(GenView::I_latestDiff) = 0; v.sc(GenView::I_lastAbsDiff) = 0; v.sc(GenView::I_rv0) = 0; v.sc(GenView::I_rv1) = 0;
+    v.sc(GenView::I_rvMask) = 0;
     v.sc(GenView::I_done) = 0;
 }
 
@@ -617,6 +619,7 @@ GW_HD uint32_t gen_apply(GenView &v, const Params &P, const GenBand &B, const Ev
                             if (d == 0) v.sc(GenView::I_rv0) = kCounterByteLen;
                             if (d == 1) v.sc(GenView::I_rv1) = kCounterByteLen;
                             v.sc(GenView::I_latestDiff) = v.sc(GenView::I_rv0) - v.sc(GenView::I_rv1);
+                            v.sc(GenView::I_rvMask) |= 1 << d;
                             v.nDeliv(d) += 1u;
                         }
                         gen_rec(v, REC_RX, v.now(), d, 0.0, 0.0, 0.0, 0.0);

@@ -2249,6 +2249,7 @@ __global__ void genband_read_kernel(GenArgs A, GenBand B, int field, double *out
             else if (field == GW_GENBAND_FIELD_RECEIVED) x = v.nRecv(k);
             else if (field == GW_GENBAND_FIELD_QUEUE_LENGTH) x = v.qn(k);
             else if (field == GW_GENBAND_FIELD_COUNTER) x = gen_counter_at(v, k, v.ticks(k));
+            else if (field == GW_GENBAND_FIELD_RECEIVED_VALUES) x = ((v.sc(GenView::I_rvMask) >> k) & 1) ? kCounterByteLen : 0;
             out[k * n + i] = x;
         }
     }
@@ -3529,7 +3530,7 @@ int gw_genband_step_traced(gw_genband_handle *h, const int32_t *device, const in
 int gw_genband_read(gw_genband_handle *h, int field, double *out, void *stream)
 {
     if (!h || !out) return fail(GW_E_INVALID, "NULL argument");
-    if (field < GW_GENBAND_FIELD_NOW || field > GW_GENBAND_FIELD_TIES) return fail(GW_E_INVALID, "unknown field %d", field);
+    if (field < GW_GENBAND_FIELD_NOW || field > GW_GENBAND_FIELD_RECEIVED_VALUES) return fail(GW_E_INVALID, "unknown field %d", field);
     CUDA_TRY(cudaSetDevice(h->device));
     genband_read_kernel<<<grid_for(h->A.n_envs, 64), 64, 0, (cudaStream_t)stream>>>(h->A, h->B, field, out);
     CUDA_TRY(cudaGetLastError());

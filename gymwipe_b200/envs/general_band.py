@@ -52,6 +52,28 @@ def _trace_tuples(rows):
     return recs
 
 
+class _LazyInfo(dict):
+    """``info`` of a batched step: ``"Latest received values"`` is read back from the device on first access
+    (the reference returns ``str(receivedValues)``, ``counter_traffic.py:109-112``)."""
+
+    def __init__(self, env):
+        super().__init__()
+        self._env = env
+
+    def __missing__(self, key):
+        if key == "Latest received values":
+            v = self._env.received_values()
+            self[key] = v
+            return v
+        raise KeyError(key)
+
+    def keys(self):
+        return ["Latest received values"]
+
+    def __contains__(self, key):
+        return key == "Latest received values" or super().__contains__(key)
+
+
 class GeneralBandEnv(BaseEnv):
     """
     Args:
@@ -189,8 +211,8 @@ class GeneralBandEnv(BaseEnv):
         if self.strict:
             self.check()
         if self._scalar_api and out is None:
-            return int(obs[0]), float(reward[0]), bool(done[0]), {}
-        return obs, reward, done if done.dtype == torch.bool else done.to(torch.bool), {}
+            return int(obs[0]), float(reward[0]), bool(done[0]), {"Latest received values": str(self.received_values()[0].tolist())}
+        return obs, reward, done if done.dtype == torch.bool else done.to(torch.bool), _LazyInfo(self)
 
     def step_traced(self, action, cap=8192):
         """:meth:`step` plus the event trace per env (tuples as ``CounterTrafficEnv.step_traced``)."""
@@ -264,6 +286,10 @@ class GeneralBandEnv(BaseEnv):
     def received(self):
         """int64 ``[num_envs, n_senders]``: packets handed to ``onReceive`` (MAC receive mode)."""
         return self._read(N.GW_GENBAND_FIELD_RECEIVED, (self.n_senders, self.num_envs)).t().to(torch.int64)
+
+    def received_values(self):
+        """int64 ``[num_envs, n_senders]``: the interpreter's ``receivedValues`` (``counter_traffic.py:69-80``)."""
+        return self._read(N.GW_GENBAND_FIELD_RECEIVED_VALUES, (self.n_senders, self.num_envs)).t().to(torch.int64)
 
     def transmissions(self):
         return self._read(N.GW_GENBAND_FIELD_TRANSMISSIONS, (self.num_envs,)).to(torch.int64)

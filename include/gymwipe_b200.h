@@ -453,6 +453,7 @@ int gw_genband_step_traced(gw_genband_handle *h, const int32_t *device, const in
 #define GW_GENBAND_FIELD_QUEUE_LENGTH 6     /* [n_senders][n_envs] */
 #define GW_GENBAND_FIELD_COUNTER 7          /* [n_senders][n_envs] */
 #define GW_GENBAND_FIELD_TIES 8             /* [n_envs] exact-time ties between independent events (diagnostic) */
+#define GW_GENBAND_FIELD_RECEIVED_VALUES 9  /* [n_senders][n_envs] CounterTrafficInterpreter.receivedValues (counter_traffic.py:69-80) */
 int gw_genband_read(gw_genband_handle *h, int field, double *out, void *stream);
 /* Synchronises; GW_E_ACTION / GW_E_SIMFAULT like gw_check. */
 int gw_genband_check(gw_genband_handle *h, void *stream);

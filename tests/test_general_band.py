@@ -156,6 +156,10 @@ def test_cuda_general_band_matches_reference_golden(name):
     n_rx = [sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "rx" and r[3] == k) for k in range(ns)]
     n_mrx = [sum(1 for s in doc["steps"] for r in s["records"] if r[0] == "mrx" and r[3] == k) for k in range(ns)]
     assert env.delivered()[0].tolist() == n_rx and env.received()[0].tolist() == n_mrx
+    # the interpreter's receivedValues (payload.value = 2 for every sender the RRM has decoded since the reset)
+    assert env.received_values()[0].tolist() == [2 if c > 0 else 0 for c in n_rx]
+    info = env.step({"device": 0, "duration": 0})[3]              # (num_envs == 1: the reference's info dict)
+    assert set(info) == {"Latest received values"} and info["Latest received values"].startswith("[")
     print("%s: max relative BER / error-sum deviation vs reference %.3e" % (name, worst))
 
 
