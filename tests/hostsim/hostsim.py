@@ -198,7 +198,7 @@ def grid_run(scenario, durations, move_delays=None, offsets=None, move_interval=
 
 
 def gen_run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, reset_at=None, trace_cap=400000, mode=0, seed=0, env_offset=0,
-            moves=None, move_delays=None, offsets=None, move_interval=1e-3):
+            moves=None, move_delays=None, offsets=None, move_interval=1e-3, trace=True):
     """General band engine (``gw_band.cuh``) on the host: a one-band scenario dict with any number of senders
     (<= 8), the RRM and PHY-only senders (<= 16); ``dev_tape`` / ``dur_tape`` int32 ``[nsteps, nenv]``; ``pos``
     optional float64 ``[nenv, nd, 2]``.  Returns obs / reward / done / now ``[nsteps, nenv]``, ``counts``
@@ -233,7 +233,8 @@ def gen_run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, reset_at=None
     obs, rew = np.zeros((nsteps, nenv), np.int64), np.zeros((nsteps, nenv), np.float64)
     done, now = np.zeros((nsteps, nenv), np.uint8), np.zeros((nsteps, nenv), np.float64)
     counts = np.zeros((nenv, 17), np.int64)
-    trace, tc = np.zeros((trace_cap, 8)), np.zeros(nsteps, np.int32)
+    trace_on = trace
+    trace, tc = np.zeros((trace_cap if trace_on else 1, 8)), np.zeros(nsteps, np.int32)
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     L.hs_gen_run.restype = C.c_int
     L.hs_gen_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int,
@@ -252,7 +253,7 @@ def gen_run(scenario, dev_tape, dur_tape, pos=None, do_reset=True, reset_at=None
     rc = L.hs_gen_run(ns, nj, int(scenario.get("assignment_duration_factor", 1000)), float(band.get("frequency", 2.4e9)),
                       float(band.get("bandwidth", 22e6)), ptr(ci), ptr(cj), ptr(cd), ptr(p), 0 if pos is None else 1, ptr(power),
                       int(mode), int(seed), int(env_offset), nenv, nsteps, int(reset_at), ptr(dev_tape), ptr(dur_tape), ptr(obs), ptr(rew), ptr(done), ptr(now),
-                      ptr(counts), ptr(trace), trace_cap, ptr(tc), C.cast(arr, C.c_void_p), len(mv),
+                      ptr(counts), ptr(trace) if trace_on else None, trace_cap, ptr(tc), C.cast(arr, C.c_void_p), len(mv),
                       ptr(md), ptr(off), off.shape[1] if offsets is not None else 0, float(move_interval))
     assert int(tc.sum()) <= trace_cap, "raise trace_cap"
     return {"rc": rc, "obs": obs, "reward": rew, "done": done, "now": now, "counts": counts,

@@ -645,3 +645,42 @@ def test_cuda_general_band_mobility_processes():
         for t, s in enumerate(res["steps"]):
             assert got_obs[t][e] == s["obs"] and got_now[t][e] == s["now"], (e, t)
         assert list(deliv[e]) == list(ora.counts()[1][:ns])
+
+
+def test_core_general_long_run_through_counter_saturation():
+    """7,000 steps (~75 simulated seconds) of a 3-sender band: the counters saturate at COUNTER_BOUND = 65,536, the
+    queues sit at their capacity of 100 with drop-oldest, packets outgrow every window (the reference's degenerate
+    steady state) -- step results, step end times and counts equal the oracle's throughout, with
+    a reset() on the way."""
+    rs = np.random.RandomState(99)
+    sc = random_scenario_n(rs, 3, 1, spread=2.0)
+    for d in sc["bands"][0]["devices"][:3]:
+        d["payload"] = "counter"
+        d["interval"] = 0.001
+    T = 7000
+    dev = rs.randint(0, 3, size=(T, 1)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, 1)).astype(np.int32)
+    ora = O.Oracle(sc)
+    ora.reset()
+    obs, now = np.zeros(T, np.int64), np.zeros(T)
+    for t in range(T):
+        if t == 4000:
+            ora.reset()
+        o, r, d = ora.step({"device": int(dev[t, 0]), "duration": int(dur[t, 0])})
+        obs[t], now[t] = o, ora.now
+    h = HS.gen_run(sc, dev, dur, reset_at=None, do_reset=True, trace=False)
+    h2 = HS.gen_run(sc, dev[:4000], dur[:4000], trace=False)
+    assert h2["rc"] == 0 and (h2["obs"][:, 0] == obs[:4000]).all() and (h2["now"][:, 0] == now[:4000]).all()
+    # (the host driver resets once, before `reset_at`: the second half is checked with the reset at step 4000)
+    h3 = HS.gen_run(sc, dev, dur, do_reset=False, reset_at=4000, trace=False)
+    ora2 = O.Oracle(sc)
+    obs2, now2 = np.zeros(T, np.int64), np.zeros(T)
+    for t in range(T):
+        if t == 4000:
+            ora2.reset()
+        o, r, d = ora2.step({"device": int(dev[t, 0]), "duration": int(dur[t, 0])})
+        obs2[t], now2[t] = o, ora2.now
+    assert h3["rc"] == 0 and (h3["obs"][:, 0] == obs2).all() and (h3["now"][:, 0] == now2).all()
+    ntx, nd = ora2.counts()
+    assert h3["counts"][0, 0] == ntx and list(h3["counts"][0, 1:4]) == list(nd[:3])
+    assert now2[-1] > 65.0 and h["rc"] == 0
