@@ -148,3 +148,34 @@ def test_bench_reference_arm_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert 1e4 < line["value"] < 1e9                  # a CPU rate, not a timing artefact
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_ctypes_structs_mirror_the_header_layout(tmp_path):
+    """include/gymwipe_b200.h compiled as plain C (it is the boundary a C caller sees): sizeof and field offsets of
+    gw_config, gw_grid_config and gw_genband_config equal those of the ctypes mirrors in gymwipe_b200/_native.py."""
+    import subprocess
+    from gymwipe_b200 import _native as N
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "gymwipe_b200.h"
+int main(void) {
+    printf("gw_config %zu %zu %zu %zu\n", sizeof(gw_config), offsetof(gw_config, seed), offsetof(gw_config, band), offsetof(gw_config, plant));
+    printf("gw_grid_config %zu %zu %zu %zu\n", sizeof(gw_grid_config), offsetof(gw_grid_config, power_dbm), offsetof(gw_grid_config, header_bytes), offsetof(gw_grid_config, max_moves));
+    printf("gw_genband_config %zu %zu %zu %zu %zu %zu\n", sizeof(gw_genband_config), offsetof(gw_genband_config, seed),
+           offsetof(gw_genband_config, frequency_hz), offsetof(gw_genband_config, multiplicity), offsetof(gw_genband_config, interval),
+           offsetof(gw_genband_config, phy_payload_bytes));
+    return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = {l.split()[0]: [int(x) for x in l.split()[1:]] for l in subprocess.check_output([str(exe)], text=True).splitlines()}
+    C_ = N.Config
+    assert got["gw_config"] == [C.sizeof(C_), C_.seed.offset, C_.band.offset, C_.plant.offset]
+    G = N.GridConfig
+    assert got["gw_grid_config"] == [C.sizeof(G), G.power_dbm.offset, G.header_bytes.offset, G.max_moves.offset]
+    B = N.GenBandConfig
+    assert got["gw_genband_config"] == [C.sizeof(B), B.seed.offset, B.frequency_hz.offset, B.multiplicity.offset, B.interval.offset,
+                                        B.phy_payload_bytes.offset]
