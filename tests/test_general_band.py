@@ -684,3 +684,21 @@ def test_core_general_long_run_through_counter_saturation():
     ntx, nd = ora2.counts()
     assert h3["counts"][0, 0] == ntx and list(h3["counts"][0, 1:4]) == list(nd[:3])
     assert now2[-1] > 65.0 and h["rc"] == 0
+
+
+def test_core_general_mode_m_is_sharding_invariant():
+    """The error masks are keyed by the GLOBAL env id: two shards with their own env offsets give the results of the
+    whole batch (what lets the env batch be split over GPUs with no data-path collective)."""
+    rs = np.random.RandomState(31)
+    sc = random_scenario_n(rs, 4, 2, spread=2.0, receive=True)
+    nenv, T = 10, 24
+    dev = rs.randint(0, 4, size=(T, nenv)).astype(np.int32)
+    dur = rs.randint(0, 20, size=(T, nenv)).astype(np.int32)
+    whole = HS.gen_run(sc, dev, dur, mode=1, seed=17, env_offset=1000, trace=False)
+    lo = HS.gen_run(sc, dev[:, :6], dur[:, :6], mode=1, seed=17, env_offset=1000, trace=False)
+    hi = HS.gen_run(sc, dev[:, 6:], dur[:, 6:], mode=1, seed=17, env_offset=1006, trace=False)
+    for key in ("obs", "reward", "now"):
+        assert (np.concatenate([lo[key], hi[key]], axis=1) == whole[key]).all(), key
+    assert (np.concatenate([lo["counts"], hi["counts"]], axis=0) == whole["counts"]).all()
+    other = HS.gen_run(sc, dev[:, 6:], dur[:, 6:], mode=1, seed=17, env_offset=0, trace=False)
+    assert not (other["counts"] == hi["counts"]).all() or not (other["now"] == hi["now"]).all()     # another key, other masks
